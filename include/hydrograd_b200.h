@@ -1,0 +1,184 @@
+/* hydrograd_b200.h -- C ABI of the B200-native 2-D shallow-water RHS / VJP path.
+ *
+ * This is the drop-in boundary for ONE hot path of psu-efd/Hydrograd.jl: the function
+ *
+ *     swe_2d_rhs(dQdt, Q, params_vector, t, p_extra)
+ *         src/fvm/discretization/semi_discretize_swe_2D.jl:18-277
+ *
+ * that src/applications/solve_swe_2D.jl:281-307 wraps into the ODEFunction handed to
+ * OrdinaryDiffEq / SciMLSensitivity, its reverse-mode derivative (what Zygote derives from it,
+ * contract at src/utilities/debug_AD.jl:60,75), and the hand-rolled explicit Euler stepper
+ * src/ode_solvers/custom_ODE_solvers.jl:5-95.
+ *
+ * The reference has no FFI of its own (it is 100 % Julia); the entry points below are what a Julia
+ * `@ccall` shim binds (hydrograd.jl_b200/julia/HydrogradB200.jl).  Conventions:
+ *   - plain pointers and sizes only; every function returns 0 on success, non-zero on error;
+ *     the message is available from hg_last_error(ctx) (or hg_last_error(NULL) for hg_create).
+ *   - the caller owns every buffer it passes; the library copies what it needs during the call and
+ *     never keeps a host pointer.  Host-pointer calls are synchronous.
+ *   - one caller per ctx at a time (the reference is single threaded); different ctxs are independent.
+ *   - fp64 everywhere; ids are int64 as in Julia; `index_base` says whether ids start at 1 (Julia) or 0.
+ *   - state vector layout Q = [xi(1:N); q_x(1:N); q_y(1:N)]  (semi_discretize_swe_2D.jl:93-95).
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device (sm_100a build).
+ */
+#ifndef HYDROGRAD_B200_H
+#define HYDROGRAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_ABI_VERSION 1
+
+typedef struct hg_ctx hg_ctx;
+
+/* active_param_name of SWE2D_Extra_Parameters (src/applications/application_commons.jl:9):
+ * which model parameter `params_vector` carries (semi_discretize_swe_2D.jl:114,153,190). */
+enum {
+  HG_PARAM_NONE = 0,     /* forward simulation: params_vector unused                          */
+  HG_PARAM_ZB = 1,       /* "zb":       params = zb_cells[N]        -> update_bed_data        */
+  HG_PARAM_MANNING = 2,  /* "ManningN": params = n per zone[n_mat]  -> n_cells = p[matID+1]   */
+  HG_PARAM_Q = 3         /* "Q":        params = inletQ_TotalQ[n_inletq]                      */
+};
+
+/* error codes */
+enum {
+  HG_OK = 0,
+  HG_ERR_ARG = 1,         /* bad argument / wrong array length / inconsistent mesh             */
+  HG_ERR_CUDA = 2,        /* CUDA runtime failure or no sm_100 device                          */
+  HG_ERR_CONVEYANCE = 3,  /* inlet-q total conveyance <= 1e-10 (bc_2D.jl:678-680 assert)       */
+  HG_ERR_SOLVER = 4,      /* unknown Riemann solver (semi_discretize_swe_2D.jl:356-361)        */
+  HG_ERR_STATE = 5        /* call sequence error (e.g. device state never set)                 */
+};
+
+/* ---- mesh_2D (src/meshes/mesh_2D.jl:2-71): the fields swe_2d_rhs reads, flattened. -------------
+ * N x ld tables are column-major like Julia's `cellFacesList` (entry (i,j) at i + N*j, 0-based i,j).
+ * cell_neighbors / cell_normals are `cellNeighbors_Dict` / `cell_normals` written into the same
+ * N x ld shape by the shim.  cell j-th face of cell i:  face id  cell_faces[i + N*j],
+ * neighbour cell id -- or GHOST id when face_is_boundary[face] -- cell_neighbors[i + N*j],
+ * outward unit normal (cell_normals[i + N*(j + ld*0)], cell_normals[i + N*(j + ld*1)]).          */
+typedef struct {
+  int64_t n_cells;                 /* numOfCells                                                 */
+  int64_t n_faces;                 /* numOfFaces                                                 */
+  int64_t n_ghost;                 /* numOfAllBounaryFaces (= number of ghost cells)             */
+  int64_t ld;                      /* second dim of the tables (8 = gMax_Nodes_per_Element)      */
+  int32_t index_base;              /* 1: ids as in Julia, 0: C ids                               */
+  const int64_t* cell_nfaces;      /* [N]       cellNodesCount                                   */
+  const int64_t* cell_faces;       /* [N*ld]    cellFacesList (sign ignored)                     */
+  const int64_t* cell_neighbors;   /* [N*ld]    cellNeighbors_Dict                               */
+  const double* cell_normals;      /* [N*ld*2]  cell_normals                                     */
+  const uint8_t* face_is_boundary; /* [F]       bFace_is_boundary                                */
+  const double* face_lengths;      /* [F]       face_lengths                                     */
+  const double* cell_areas;        /* [N]       cell_areas                                       */
+  const double* cell_centroids;    /* [N*2] column-major cell_centroids, or NULL (only used to
+                                      order cells for locality / to partition across GPUs)      */
+} hg_mesh_desc;
+
+/* ---- BoundaryConditions2D (src/fvm/boundary_conditions/bc_2D.jl:3-47), static part, flattened.
+ * Boundaries are listed in the reference's processing order: all inlet-q, then exit-h, wall, symm
+ * (bc_2D.jl:279-295); entry arrays are the per-boundary vectors concatenated in that order.       */
+typedef struct {
+  int64_t n_inletq, n_exith, n_wall, n_symm; /* nInletQ_BCs, nExitH_BCs, nWall_BCs, nSymm_BCs    */
+  const int64_t* bc_ptr;           /* [n_bc+1] 0-based offsets of each boundary's entries        */
+  const int64_t* ghost_ids;        /* [B] *_ghostCellIDs            (all_boundary_ghost_ids)     */
+  const int64_t* internal_cells;   /* [B] *_internalCellIDs                                      */
+  const double* outward_normals;   /* [B*2] column-major *_faceOutwardNormals / *_outwardNormals */
+  const double* face_lengths;      /* [B] inletQ_Length (read for inlet-q entries only)          */
+} hg_bc_desc;
+
+/* ---- SWE2D_Extra_Parameters (src/applications/application_commons.jl:7-44) + swe_2D_consts
+ * (src/constants/swe_2D_constants.jl:4-17): the frozen fields the RHS reads.                     */
+typedef struct {
+  double g, k_n, h_small;          /* swe_2D_constants.g, .k_n, .h_small                         */
+  const char* riemann_solver;      /* swe_2D_constants.RiemannSolver; only "Roe" exists          */
+  const double* hstill;            /* [N]                                                        */
+  const double* hstill_ghost;      /* [B]   hstill_ghostCells                                    */
+  const double* zb_cells;          /* [N]                                                        */
+  const double* zb_ghost;          /* [B]   zb_ghostCells                                        */
+  const double* S0_cells;          /* [2N]  N x 2 column-major                                   */
+  const double* ManningN_cells;    /* [N]                                                        */
+  const int64_t* matID_cells;      /* [N]   srh_all_Dict["matID_cells"], 0-based zone ids; may be
+                                            NULL when HG_PARAM_MANNING is never used             */
+  int64_t n_mat;                   /* number of Manning zones (length of the ManningN params)    */
+  const double* inletQ_TotalQ;     /* [n_inletq]                                                 */
+  const double* exitH_WSE;         /* [n_exith]                                                  */
+} hg_fields_desc;
+
+typedef struct {
+  int32_t device;                  /* CUDA device ordinal                                        */
+  int32_t tile_cells;              /* cells per CTA tile of the fused kernel; 0 = default        */
+  int32_t reorder;                 /* 1 = renumber cells for locality (needs cell_centroids)     */
+  int32_t strict;                  /* 1 = reference evaluation order, no FMA contraction         */
+  int32_t path;                    /* 0 = fused tile kernel, 1 = plain 3-kernel path (ghost/face/cell) */
+  int32_t reserved[11];
+} hg_options;
+
+/* fills *opt with the defaults */
+void hg_default_options(hg_options* opt);
+
+int hg_abi_version(void);
+
+/* Build a context (device copies of the mesh in the internal face/tile layout).  Replaces the
+ * per-call unpacking of p_extra at semi_discretize_swe_2D.jl:26-67.                              */
+int hg_create(hg_ctx** out, const hg_mesh_desc* mesh, const hg_bc_desc* bc,
+              const hg_fields_desc* fields, const hg_options* opt);
+void hg_destroy(hg_ctx* ctx);
+const char* hg_last_error(const hg_ctx* ctx);
+
+int64_t hg_n_cells(const hg_ctx* ctx);
+
+/* Replace frozen fields after creation (setup_* in solve_swe_2D.jl:148-221); NULL = keep.        */
+int hg_set_fields(hg_ctx* ctx, const double* ManningN_cells, const double* zb_cells,
+                  const double* zb_ghost, const double* S0_cells, const double* inletQ_TotalQ,
+                  const double* exitH_WSE);
+
+/* dQdt = swe_2d_rhs(Q, params, t)   -- host buffers, reference cell order.
+ * semi_discretize_swe_2D.jl:18-277.  `t` is accepted and unused exactly like the reference.      */
+int hg_rhs(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params,
+           int32_t active_param, double t, double* dQdt);
+
+/* Vector-Jacobian product of the same call: Qbar = (d rhs/dQ)^T lambda  [3N],
+ * pbar = (d rhs/dparams)^T lambda  [n_params] (NULL allowed when active_param = NONE),
+ * ncell_bar (optional, may be NULL) = d(lambda . rhs)/d ManningN_cells  [N]  (UDE hook).
+ * Replaces Zygote.pullback on swe_2d_rhs (debug_AD.jl:60,75; swe_2D_inversion.jl:339).           */
+int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params,
+               int32_t active_param, double t, const double* lambda, double* Qbar, double* pbar,
+               double* ncell_bar);
+
+/* ---- device-resident state (no host round trip per stage) ---------------------------------- */
+int hg_set_state(hg_ctx* ctx, const double* Q);          /* host [3N] -> device                  */
+int hg_get_state(hg_ctx* ctx, double* Q);                /* device -> host [3N]                  */
+int hg_set_params(hg_ctx* ctx, const double* params, int64_t n_params, int32_t active_param);
+/* dQdt of the resident state into a resident buffer; hg_get_rhs copies it out.  Asynchronous on
+ * the ctx stream; hg_sync waits.                                                                 */
+int hg_rhs_resident(hg_ctx* ctx);
+int hg_get_rhs(hg_ctx* ctx, double* dQdt);
+int hg_sync(hg_ctx* ctx);
+
+/* nsteps of custom_ODE_update_cells (custom_ODE_solvers.jl:5-33) on the resident state:
+ * Q+ = Q + dt*rhs(Q); where xi+ < h_small: xi+ = h_small, q+ = 0 (the reference's mask is on xi).
+ * Fused into the RHS kernel (one launch per step, captured in a CUDA graph).                      */
+int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps);
+
+/* custom_ODE_solve (custom_ODE_solvers.jl:36-95): steps over t_start:dt:t_end, saving every
+ * state; sol is [3N x n_saves] column-major, n_saves_capacity columns available; *n_saves out.   */
+int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params,
+                        int32_t active_param, double t_start, double t_end, double dt, double* sol,
+                        int64_t n_saves_capacity, int64_t* n_saves);
+
+/* ---- timing hooks used by bench.py (device time of the last N launches, CUDA events on the
+ * ctx stream) and introspection for the roofline arithmetic.                                     */
+int hg_time_rhs(hg_ctx* ctx, int32_t n_launches, int32_t fused_euler, double dt, float* ms_total);
+int hg_time_vjp(hg_ctx* ctx, int32_t n_launches, float* ms_total);
+int64_t hg_kernel_launches(const hg_ctx* ctx);            /* kernels launched so far             */
+int hg_mesh_stats(const hg_ctx* ctx, int64_t* n_cells, int64_t* n_faces, int64_t* sum_cell_faces,
+                  int64_t* n_tiles, int64_t* device_bytes);
+/* write `bytes` bytes of device scratch (L2 flush between timed iterations)                      */
+int hg_flush_l2(hg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDROGRAD_B200_H */

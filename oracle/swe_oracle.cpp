@@ -1,0 +1,406 @@
+// ORACLE -- test infrastructure, NOT product code.
+//
+// CPU restatement (C++17, fp64) of Hydrograd.jl's 2-D shallow-water RHS in the reference's own
+// structure and evaluation order: cell-centric loop, every interior face evaluated twice,
+// left-to-right face accumulation, no FMA contraction (build with -ffp-contract=off).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load this library; the product (hydrograd.jl_b200/) never does.
+//
+// PARITY PINNING: the reference cannot be executed here (Julia is absent from this image and from
+// the GPU box).  The setup side (zb, S0) and the friction formula are pinned bit-exactly / to
+// <= 6e-16 against the reference's committed truth JSONs (tests/test_oracle_golden.py); a single
+// swe_2d_rhs call and its derivative are pinned by NO reference fixture ("parity unpinned" for
+// a2/a3/a5/a12 in SURVEY.md section 8c) beyond the soft steady-state check on the committed
+// sensitivity trajectory.
+//
+// Reference files followed (relative to /root/reference/src):
+//   fvm/discretization/semi_discretize_swe_2D.jl          18-277, 281-434, 449-559
+//   fvm/discretization/Riemman_solvers/swe_2D_solvers.jl  4-164
+//   fvm/boundary_conditions/bc_2D.jl                      575-875
+//   utilities/smooth_functions.jl                         4-52
+//   parameters/process_bed_2D.jl 46-66, fvm/discretization/fvm_schemes_2D.jl 3-30, 89-105, 133-167
+//   parameters/process_ManningN_2D.jl                     71-98
+//   ode_solvers/custom_ODE_solvers.jl                     5-33
+//
+// The derivative oracle is forward-mode dual numbers through the SAME templated code (what
+// ForwardDiff does to the reference): ifelse/max/wet flags become piecewise-constant selectors.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../include/hydrograd_b200.h"
+
+namespace {
+
+constexpr double EPS = 2.220446049250313e-16;  // eps(Float64), smooth_functions.jl
+
+// ------------------------------------------------------------------ dual numbers
+struct Dual {
+  double v, d;
+  Dual() : v(0), d(0) {}
+  Dual(double v_) : v(v_), d(0) {}
+  Dual(double v_, double d_) : v(v_), d(d_) {}
+};
+inline Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+inline Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+inline Dual operator-(Dual a) { return {-a.v, -a.d}; }
+inline Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+inline Dual operator/(Dual a, Dual b) {
+  double q = a.v / b.v;
+  return {q, (a.d - q * b.d) / b.v};
+}
+inline Dual sqrtT(Dual a) {
+  double s = std::sqrt(a.v);
+  return {s, a.d / (2.0 * s)};
+}
+inline Dual powT(Dual a, double p) {
+  double r = std::pow(a.v, p);
+  return {r, p * std::pow(a.v, p - 1.0) * a.d};
+}
+inline double sqrtT(double a) { return std::sqrt(a); }
+inline double powT(double a, double p) { return std::pow(a, p); }
+inline double val(double a) { return a; }
+inline double val(Dual a) { return a.v; }
+
+// smooth_functions.jl:4-52
+template <class T> inline T smooth_abs(T x) { return sqrtT(x * x + T(EPS)); }
+template <class T> inline T smooth_sqrt(T x) { return sqrtT(x + T(EPS)); }
+template <class T> inline T smooth_pow2(T x) { T y = x + T(EPS); return y * y; }  // (x+eps)^2, y::Int = 2
+
+// ------------------------------------------------------------------ Riemann_2D_Roe
+// swe_2D_solvers.jl:4-164.  zb_face and S0_on_face are accepted by the reference but unused.
+template <class T>
+inline void riemann_roe(T xiL, T hstillL, T hL, T huL, T hvL, T zbL, T xiR, T hstillR, T hR, T huR, T hvR,
+                        T zbR, double g, double nx, double ny, double hmin, T out[3]) {
+  if (val(hL) <= hmin && val(hR) <= hmin) {  // :16
+    out[0] = out[1] = out[2] = T(0.0);
+    return;
+  } else if ((val(hL) + val(zbL)) < (val(zbR) + hmin) && val(hR) <= hmin) {  // :23 wall-like, fall through
+    hR = hL; huR = -huL; hvR = -hvL;
+  } else if ((val(hR) + val(zbR)) < (val(zbL) + hmin) && val(hL) <= hmin) {  // :39
+    hL = hR; huL = -huR; hvL = -hvR;
+  } else if (val(hL) <= hmin) {  // :54 left dry
+    T p = T(0.5 * g) * smooth_pow2(hR);
+    out[0] = huR * T(nx) + hvR * T(ny);
+    out[1] = (huR * (huR / hR) + p) * T(nx) + huR * (hvR / hR) * T(ny);
+    out[2] = (hvR * (huR / hR)) * T(nx) + (hvR * (hvR / hR) + p) * T(ny);
+    return;
+  } else if (val(hR) <= hmin) {  // :65 right dry
+    T p = T(0.5 * g) * smooth_pow2(hL);
+    out[0] = huL * T(nx) + hvL * T(ny);
+    out[1] = (huL * (huL / hL) + p) * T(nx) + huL * (hvL / hL) * T(ny);
+    out[2] = (hvL * (huL / hL)) * T(nx) + (hvL * (hvL / hL) + p) * T(ny);
+    return;
+  }
+  T uL = huL / hL, vL = hvL / hL, uR = huR / hR, vR = hvR / hR;  // :79-82
+  T sL = smooth_sqrt(hL), sR = smooth_sqrt(hR);                  // :89-90
+  T hRoe = (hL + hR) / T(2.0);                                   // :91 arithmetic average
+  T uRoe = (sL * uL + sR * uR) / (sL + sR);
+  T vRoe = (sL * vL + sR * vR) / (sL + sR);
+  T unRoe = uRoe * T(nx) + vRoe * T(ny);
+  T cRoe = smooth_sqrt(T(g) * hRoe);                             // :95
+  T o2c = T(1.0) / T(2.0) / cRoe;                                // :96
+
+  // R_mat, L_mat, absLamda (:103-113); products are StaticArrays' unrolled left-to-right sums
+  T R22 = uRoe - cRoe * T(nx), R23 = uRoe + cRoe * T(nx);
+  T R32 = vRoe - cRoe * T(ny), R33 = vRoe + cRoe * T(ny);
+  T L11 = -(uRoe * T(ny) - vRoe * T(nx)), L12 = T(ny), L13 = T(-nx);
+  T L21 = unRoe * o2c + T(0.5), L22 = T(-nx) * o2c, L23 = T(-ny) * o2c;
+  T L31 = -unRoe * o2c + T(0.5), L32 = T(nx) * o2c, L33 = T(ny) * o2c;
+  T a1 = smooth_abs(unRoe), a2 = smooth_abs(unRoe - cRoe), a3 = smooth_abs(unRoe + cRoe);
+  T d1 = xiR - xiL, d2 = huR - huL, d3 = hvR - hvL;              // :115
+  T w1 = (L11 * d1 + L12 * d2) + L13 * d3;
+  T w2 = (L21 * d1 + L22 * d2) + L23 * d3;
+  T w3 = (L31 * d1 + L32 * d2) + L33 * d3;
+  T z1 = (a1 * w1 + T(0.0) * w2) + T(0.0) * w3;
+  T z2 = (T(0.0) * w1 + a2 * w2) + T(0.0) * w3;
+  T z3 = (T(0.0) * w1 + T(0.0) * w2) + a3 * w3;
+  T y1 = (T(0.0) * z1 + T(1.0) * z2) + T(1.0) * z3;
+  T y2 = (T(ny) * z1 + R22 * z2) + R23 * z3;
+  T y3 = (T(-nx) * z1 + R32 * z2) + R33 * z3;
+
+  T pL = T(0.5 * g) * (smooth_pow2(xiL) + T(2.0) * xiL * hstillL);  // :122
+  T pR = T(0.5 * g) * (smooth_pow2(xiR) + T(2.0) * xiR * hstillR);
+  T f1L = huL * T(nx) + hvL * T(ny);
+  T f2L = (huL * uL + pL) * T(nx) + huL * vL * T(ny);
+  T f3L = (hvL * uL) * T(nx) + (hvL * vL + pL) * T(ny);
+  T f1R = huR * T(nx) + hvR * T(ny);
+  T f2R = (huR * uR + pR) * T(nx) + huR * vR * T(ny);
+  T f3R = (hvR * uR) * T(nx) + (hvR * vR + pR) * T(ny);
+  out[0] = (f1L + f1R - y1) / T(2.0);  // :131-133
+  out[1] = (f2L + f2R - y2) / T(2.0);
+  out[2] = (f3L + f3R - y3) / T(2.0);
+}
+
+// ------------------------------------------------------------------ flat mesh accessors
+struct View {
+  const hg_mesh_desc& m;
+  const hg_bc_desc& b;
+  const hg_fields_desc& f;
+  int64_t N, F, B, ld, base, nbc;
+  View(const hg_mesh_desc& m_, const hg_bc_desc& b_, const hg_fields_desc& f_)
+      : m(m_), b(b_), f(f_), N(m_.n_cells), F(m_.n_faces), B(m_.n_ghost), ld(m_.ld), base(m_.index_base),
+        nbc(b_.n_inletq + b_.n_exith + b_.n_wall + b_.n_symm) {}
+  int64_t face(int64_t i, int64_t j) const { int64_t v = m.cell_faces[i + N * j]; return (v < 0 ? -v : v) - base; }
+  int64_t neigh(int64_t i, int64_t j) const { return m.cell_neighbors[i + N * j] - base; }
+  double nx(int64_t i, int64_t j) const { return m.cell_normals[i + N * (j + ld * 0)]; }
+  double ny(int64_t i, int64_t j) const { return m.cell_normals[i + N * (j + ld * 1)]; }
+};
+
+// update_bed_data (process_bed_2D.jl:46-66): zb_ghost, S0_cells from zb_cells
+template <class T>
+void bed_from_zb(const View& v, const T* zb, T* zbg, T* S0x, T* S0y) {
+  for (int64_t e = 0; e < v.B; ++e) zbg[v.b.ghost_ids[e] - v.base] = zb[v.b.internal_cells[e] - v.base];
+  for (int64_t i = 0; i < v.N; ++i) {
+    T gx(0.0), gy(0.0);
+    for (int64_t j = 0; j < v.m.cell_nfaces[i]; ++j) {
+      int64_t fid = v.face(i, j);
+      T zf = v.m.face_is_boundary[fid] ? zb[i] : (zb[i] + zb[v.neigh(i, j)]) / T(2.0);  // fvm_schemes_2D.jl:89-105
+      gx = gx + T(v.nx(i, j)) * zf * T(v.m.face_lengths[fid]);                           // :133-167
+      gy = gy + T(v.ny(i, j)) * zf * T(v.m.face_lengths[fid]);
+    }
+    S0x[i] = T(-1.0) * (gx / T(v.m.cell_areas[i]));
+    S0y[i] = T(-1.0) * (gy / T(v.m.cell_areas[i]));
+  }
+}
+
+template <class T>
+struct Work {
+  std::vector<T> h, qx, qy, zb, zbg, S0x, S0y, n, Qin, hg, qxg, qyg, xig;
+};
+
+// swe_2d_rhs (semi_discretize_swe_2D.jl:18-277)
+template <class T>
+int rhs_impl(const View& v, const T* Q, const T* params, int64_t np, int active, T* dQ, int nthreads,
+             T* ghost_out /* optional [4B]: h, qx, qy, xi in ghost order */) {
+  const int64_t N = v.N, B = v.B, base = v.base;
+  const double g = v.f.g, kn = v.f.k_n, hs = v.f.h_small;
+  Work<T> w;
+  w.h.resize(N); w.qx.resize(N); w.qy.resize(N);
+  const T* xi = Q;
+  for (int64_t i = 0; i < N; ++i) {  // :101-106
+    T h = xi[i] + T(v.f.hstill[i]);
+    bool dry = val(h) <= hs;
+    w.h[i] = dry ? T(hs) : h;
+    w.qx[i] = dry ? T(0.0) : Q[N + i];
+    w.qy[i] = dry ? T(0.0) : Q[2 * N + i];
+  }
+  // ---- bind the active parameter (:114-126, 153-161, 190-199)
+  w.zb.resize(N); w.zbg.resize(B); w.S0x.resize(N); w.S0y.resize(N); w.n.resize(N);
+  const int64_t nI = v.b.n_inletq, nE = v.b.n_exith;
+  w.Qin.resize(nI);
+  if (active == HG_PARAM_ZB) {
+    if (np != N) return HG_ERR_ARG;
+    for (int64_t i = 0; i < N; ++i) w.zb[i] = params[i];
+    bed_from_zb(v, w.zb.data(), w.zbg.data(), w.S0x.data(), w.S0y.data());
+  } else {
+    for (int64_t i = 0; i < N; ++i) { w.zb[i] = T(v.f.zb_cells[i]); w.S0x[i] = T(v.f.S0_cells[i]); w.S0y[i] = T(v.f.S0_cells[N + i]); }
+    for (int64_t e = 0; e < B; ++e) w.zbg[e] = T(v.f.zb_ghost[e]);
+  }
+  if (active == HG_PARAM_MANNING) {
+    if (np != v.f.n_mat || !v.f.matID_cells) return HG_ERR_ARG;
+    for (int64_t i = 0; i < N; ++i) w.n[i] = params[v.f.matID_cells[i]];  // process_ManningN_2D.jl:88
+  } else {
+    for (int64_t i = 0; i < N; ++i) w.n[i] = T(v.f.ManningN_cells[i]);
+  }
+  if (active == HG_PARAM_Q) {
+    if (np != nI) return HG_ERR_ARG;
+    for (int64_t k = 0; k < nI; ++k) w.Qin[k] = params[k];
+  } else {
+    for (int64_t k = 0; k < nI; ++k) w.Qin[k] = T(v.f.inletQ_TotalQ[k]);
+  }
+
+  // ---- process_all_boundaries_2d (bc_2D.jl:575-875): ghost states in ghost order
+  w.hg.assign(B, T(0.0)); w.qxg.assign(B, T(0.0)); w.qyg.assign(B, T(0.0)); w.xig.assign(B, T(0.0));
+  int64_t k = 0;
+  for (int64_t kk = 0; kk < nI; ++kk, ++k) {  // inlet-q :640-730
+    int64_t e0 = v.b.bc_ptr[k], e1 = v.b.bc_ptr[k + 1];
+    T totalA(0.0);
+    bool first = true;
+    for (int64_t e = e0; e < e1; ++e) {
+      int64_t c = v.b.internal_cells[e] - base;
+      double wet = val(w.h[c]) > hs ? 1.0 : 0.0;  // :665 (a constant for AD)
+      T term = T(std::pow(v.b.face_lengths[e], 5.0 / 3.0)) * w.h[c] / w.n[c] * T(wet);
+      totalA = first ? term : totalA + term;       // sum over a generator: left fold
+      first = false;
+    }
+    if (!(val(totalA) > 1e-10)) return HG_ERR_CONVEYANCE;  // :678-680
+    for (int64_t e = e0; e < e1; ++e) {
+      int64_t c = v.b.internal_cells[e] - base, gi = v.b.ghost_ids[e] - base;
+      double wet = val(w.h[c]) > hs ? 1.0 : 0.0;
+      T vn = w.Qin[kk] / totalA * T(std::pow(v.b.face_lengths[e], 2.0 / 3.0)) / w.n[c];  // :690-691
+      w.hg[gi] = w.h[c];
+      w.qxg[gi] = -w.h[c] * vn * T(v.b.outward_normals[e]) * T(wet);          // :693
+      w.qyg[gi] = -w.h[c] * vn * T(v.b.outward_normals[B + e]) * T(wet);      // :694
+    }
+  }
+  for (int64_t kk = 0; kk < nE; ++kk, ++k) {  // exit-h :748-773
+    for (int64_t e = v.b.bc_ptr[k]; e < v.b.bc_ptr[k + 1]; ++e) {
+      int64_t c = v.b.internal_cells[e] - base, gi = v.b.ghost_ids[e] - base;
+      T hn = T(v.f.exitH_WSE[kk]) - w.zb[c];
+      w.hg[gi] = (val(hn) > hs) ? hn : T(hs);  // max(h_small, WSE - zb)
+      w.qxg[gi] = w.qx[c];
+      w.qyg[gi] = w.qy[c];
+    }
+  }
+  for (int64_t kk = 0; kk < v.b.n_wall; ++kk, ++k) {  // wall :777-799
+    for (int64_t e = v.b.bc_ptr[k]; e < v.b.bc_ptr[k + 1]; ++e) {
+      int64_t c = v.b.internal_cells[e] - base, gi = v.b.ghost_ids[e] - base;
+      w.hg[gi] = w.h[c]; w.qxg[gi] = -w.qx[c]; w.qyg[gi] = -w.qy[c];
+    }
+  }
+  for (int64_t kk = 0; kk < v.b.n_symm; ++kk, ++k) {  // symm :803-834
+    for (int64_t e = v.b.bc_ptr[k]; e < v.b.bc_ptr[k + 1]; ++e) {
+      int64_t c = v.b.internal_cells[e] - base, gi = v.b.ghost_ids[e] - base;
+      T nx(v.b.outward_normals[e]), ny(v.b.outward_normals[B + e]);
+      T vdn = w.qx[c] * nx + w.qy[c] * ny;
+      w.hg[gi] = w.h[c];
+      w.qxg[gi] = w.qx[c] - T(2.0) * vdn * nx;
+      w.qyg[gi] = w.qy[c] - T(2.0) * vdn * ny;
+    }
+  }
+  for (int64_t e = 0; e < B; ++e) w.xig[e] = w.hg[e] - T(v.f.hstill_ghost[e]);  // semi_discretize:220
+  if (ghost_out)
+    for (int64_t e = 0; e < B; ++e) {
+      ghost_out[e] = w.hg[e]; ghost_out[B + e] = w.qxg[e]; ghost_out[2 * B + e] = w.qyg[e]; ghost_out[3 * B + e] = w.xig[e];
+    }
+
+  // ---- compute_inviscid_fluxes (:281-434) + compute_source_terms (:449-559) + sum (:252-265)
+  const double kn2 = kn * kn;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+#endif
+  for (int64_t i = 0; i < N; ++i) {
+    T s0(0.0), s1(0.0), s2(0.0);
+    const int64_t nf = v.m.cell_nfaces[i];
+    for (int64_t j = 0; j < nf; ++j) {
+      int64_t fid = v.face(i, j), r = v.neigh(i, j);
+      T fl[3];
+      if (!v.m.face_is_boundary[fid]) {
+        riemann_roe<T>(xi[i], T(v.f.hstill[i]), w.h[i], w.qx[i], w.qy[i], w.zb[i], xi[r], T(v.f.hstill[r]), w.h[r],
+                       w.qx[r], w.qy[r], w.zb[r], g, v.nx(i, j), v.ny(i, j), hs, fl);
+      } else {
+        riemann_roe<T>(xi[i], T(v.f.hstill[i]), w.h[i], w.qx[i], w.qy[i], w.zb[i], w.xig[r], T(v.f.hstill_ghost[r]),
+                       w.hg[r], w.qxg[r], w.qyg[r], w.zbg[r], g, v.nx(i, j), v.ny(i, j), hs, fl);
+      }
+      T L(v.m.face_lengths[fid]);
+      s0 = s0 + fl[0] * L; s1 = s1 + fl[1] * L; s2 = s2 + fl[2] * L;  // :387
+    }
+    T A(v.m.cell_areas[i]);
+    T inv0 = -s0 / A, inv1 = -s1 / A, inv2 = -s2 / A;  // :415
+    // friction (:544-547) and sources (:463-478)
+    T n = w.n[i];
+    T mag = smooth_sqrt(w.qx[i] * w.qx[i] + w.qy[i] * w.qy[i]);
+    T coef = T(g) * (n * n) / T(kn2) / powT(w.h[i] + T(hs), 7.0 / 3.0);
+    T frx = coef * mag * w.qx[i];
+    T fry = coef * mag * w.qy[i];
+    double wet = val(w.h[i]) > hs ? 1.0 : 0.0;
+    T sx = T(wet) * (T(g) * xi[i] * w.S0x[i] - frx);
+    T sy = T(wet) * (T(g) * xi[i] * w.S0y[i] - fry);
+    dQ[i] = inv0 + T(0.0);
+    dQ[N + i] = inv1 + sx;
+    dQ[2 * N + i] = inv2 + sy;
+  }
+  return HG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+// dQdt = swe_2d_rhs(Q, params); ghost_out may be NULL or [4B] (h, q_x, q_y, xi of the ghost cells)
+int oracle_rhs(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, const double* Q,
+               const double* params, int64_t np, int active, double* dQ, int nthreads, double* ghost_out) {
+  View v(*m, *b, *f);
+  return rhs_impl<double>(v, Q, params, np, active, dQ, nthreads, ghost_out);
+}
+
+// Directional derivative: jvp = d rhs/dQ . vQ + d rhs/dp . vP   (ForwardDiff semantics)
+int oracle_rhs_jvp(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, const double* Q,
+                   const double* vQ, const double* params, const double* vP, int64_t np, int active, double* dQ,
+                   double* jvp) {
+  View v(*m, *b, *f);
+  const int64_t N = v.N;
+  std::vector<Dual> q(3 * N), p(np > 0 ? np : 1), out(3 * N);
+  for (int64_t i = 0; i < 3 * N; ++i) q[i] = Dual(Q[i], vQ ? vQ[i] : 0.0);
+  for (int64_t i = 0; i < np; ++i) p[i] = Dual(params[i], vP ? vP[i] : 0.0);
+  int rc = rhs_impl<Dual>(v, q.data(), p.data(), np, active, out.data(), 1, nullptr);
+  if (rc) return rc;
+  for (int64_t i = 0; i < 3 * N; ++i) { if (dQ) dQ[i] = out[i].v; jvp[i] = out[i].d; }
+  return HG_OK;
+}
+
+// Exact J^T lambda by 3N + np forward passes (small meshes only): Qbar[k] = lambda . (J e_k)
+int oracle_rhs_vjp_bruteforce(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, const double* Q,
+                              const double* params, int64_t np, int active, const double* lambda, double* Qbar,
+                              double* pbar, int nthreads) {
+  View v(*m, *b, *f);
+  const int64_t N = v.N, tot = 3 * N + (active ? np : 0);
+  int rc_all = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1)
+#endif
+  for (int64_t kseed = 0; kseed < tot; ++kseed) {
+    std::vector<Dual> q(3 * N), p(np > 0 ? np : 1), out(3 * N);
+    for (int64_t i = 0; i < 3 * N; ++i) q[i] = Dual(Q[i], i == kseed ? 1.0 : 0.0);
+    for (int64_t i = 0; i < np; ++i) p[i] = Dual(params[i], (3 * N + i) == kseed ? 1.0 : 0.0);
+    int rc = rhs_impl<Dual>(v, q.data(), p.data(), np, active, out.data(), 1, nullptr);
+    if (rc) { rc_all = rc; continue; }
+    double s = 0.0;
+    for (int64_t i = 0; i < 3 * N; ++i) s += lambda[i] * out[i].d;
+    if (kseed < 3 * N) Qbar[kseed] = s; else pbar[kseed - 3 * N] = s;
+  }
+  return rc_all;
+}
+
+// custom_ODE_update_cells (custom_ODE_solvers.jl:5-33): nsteps explicit Euler steps with the xi-mask quirk
+int oracle_euler(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, double* Q, const double* params,
+                 int64_t np, int active, double dt, int64_t nsteps, int nthreads) {
+  View v(*m, *b, *f);
+  const int64_t N = v.N;
+  std::vector<double> dQ(3 * N);
+  for (int64_t s = 0; s < nsteps; ++s) {
+    int rc = rhs_impl<double>(v, Q, params, np, active, dQ.data(), nthreads, nullptr);
+    if (rc) return rc;
+    for (int64_t i = 0; i < 3 * N; ++i) Q[i] = Q[i] + dt * dQ[i];  // :16
+    for (int64_t i = 0; i < N; ++i)
+      if (Q[i] < f->h_small) { Q[i] = f->h_small; Q[N + i] = 0.0; Q[2 * N + i] = 0.0; }  // :19-26 (mask on xi)
+  }
+  return HG_OK;
+}
+
+// update_bed_data: zb_cells -> zb_ghost[B], S0[2N]
+int oracle_bed(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, const double* zb, double* zbg,
+               double* S0) {
+  View v(*m, *b, *f);
+  bed_from_zb<double>(v, zb, zbg, S0, S0 + v.N);
+  return HG_OK;
+}
+
+// one Riemann_2D_Roe call: s = [xiL,hstillL,hL,huL,hvL,zbL, xiR,hstillR,hR,huR,hvR,zbR]
+void oracle_roe(const double* s, double g, double nx, double ny, double hmin, double* flux) {
+  riemann_roe<double>(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[9], s[10], s[11], g, nx, ny, hmin, flux);
+}
+
+// friction terms only (compute_friction_terms :544-547) for the golden friction_x/y check
+void oracle_friction(int64_t n, const double* h, const double* qx, const double* qy, const double* mann, double g,
+                     double kn, double hs, double* fx, double* fy) {
+  for (int64_t i = 0; i < n; ++i) {
+    double mag = smooth_sqrt(qx[i] * qx[i] + qy[i] * qy[i]);
+    double coef = g * (mann[i] * mann[i]) / (kn * kn) / std::pow(h[i] + hs, 7.0 / 3.0);
+    fx[i] = coef * mag * qx[i];
+    fy[i] = coef * mag * qy[i];
+  }
+}
+}

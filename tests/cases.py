@@ -1,0 +1,68 @@
+"""Shared loaders for the committed reference fixtures (tests/golden) and random states for fuzzing."""
+import os
+
+import numpy as np
+
+from oracle import srh2d_ref as R
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+_STEMS = {
+    "savannah": "savana_SI",
+    "oneD_bump": "oneD_channel_with_bump_refined",
+    "oneD_uniform": "oneD_channel_uniform_flow_refined",
+    "simple": "simple",
+    "oneD_bump_sens": "oneD_channel_with_bump_refined",
+}
+_IC = {
+    "oneD_bump": ("constant", [0.33, 0.2, 0.0, 0.0]),          # run_control.json of the case
+    "oneD_bump_sens": ("constant", [0.33, 0.2, 0.0, 0.0]),
+    "oneD_uniform": ("constant", [3.857205, 3.0, 0.0, 0.0]),
+    "simple": ("constant", [1.0, 0.5, 0.0, 0.0]),
+}
+_cache = {}
+
+
+def load(name):
+    if name not in _cache:
+        d = os.path.join(GOLD, name)
+        ic = _IC.get(name)
+        if name == "savannah":
+            z = np.load(os.path.join(d, "ic.npz"))
+            import json, tempfile
+            with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+                json.dump({k: z[k].tolist() for k in z.files}, f)
+            ic = ("from_file", f.name)
+        _cache[name] = R.load_case(d, _STEMS[name] + ".srhhydro", ic)
+    return _cache[name]
+
+
+def truth(name):
+    return np.load(os.path.join(GOLD, name, "truth.npz"))
+
+
+def random_state(case, seed, dry_frac=0.05):
+    """SURVEY 8(d) fuzz: h ~ LogUniform(1e-4, 10) (about 5 % below h_small), |u| ~ U(0,3), random direction."""
+    rng = np.random.default_rng(seed)
+    N = case.mesh.numOfCells
+    h = np.exp(rng.uniform(np.log(1e-4), np.log(10.0), N))
+    # force the requested share of (nearly) dry cells, including exact ties with h_small
+    k = rng.random(N) < dry_frac
+    h[k] = rng.choice([5e-4, 1e-3, 9.999e-4], size=int(k.sum()))
+    sp = rng.uniform(0, 3, N)
+    th = rng.uniform(0, 2 * np.pi, N)
+    xi = h - case.hstill
+    return np.concatenate([xi, h * sp * np.cos(th), h * sp * np.sin(th)])
+
+
+def flux_scale(case, Q):
+    """Denominator for 'relative' RHS errors: sum |flux*L|/A + |source| magnitude proxy per cell
+    (BASELINE.md parity gates: relative to the un-cancelled magnitude, not to the residual)."""
+    N = case.mesh.numOfCells
+    h = np.maximum(Q[:N] + case.hstill, case.h_small)
+    per = np.array([sum(case.mesh.face_lengths[f - 1] for f in case.mesh.cellFacesList[c, :case.mesh.cellNodesCount[c]])
+                    for c in range(N)])
+    u2 = (Q[N:2 * N] ** 2 + Q[2 * N:] ** 2) / h ** 2
+    c = np.sqrt(case.g * h)
+    s = (0.5 * case.g * h * h + h * u2 + h * np.sqrt(u2) * c + c * h) * per / case.mesh.cell_areas
+    return np.concatenate([s, s, s]) + 1e-300

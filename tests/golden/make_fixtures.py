@@ -1,0 +1,83 @@
+"""Builds tests/golden/ from the reference's own committed example data (DATA only, no code).
+
+Run once in the build container (needs /root/reference):  python tests/golden/make_fixtures.py
+The GPU box has no /root/reference, so everything the tests need is copied / condensed here:
+
+  <case>/*.srhgeom|.srhhydro|.srhmat     mesh inputs, copied verbatim
+  <case>/truth.npz                       arrays of forward_simulation_solution_truth.json (float64, exact)
+  <case>/ic.npz                          forward_simulation_initial_condition.json (Savannah)
+  oneD_bump_sens/trajectory.npz          columns 0, 50, 100 of the 3N x 101 sensitivity trajectory
+
+JSON numbers are written by the reference with 17 significant digits, so the float64 values round-trip exactly.
+"""
+import json
+import os
+import shutil
+
+import numpy as np
+
+REF = "/root/reference/examples/SWE_2D"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    "savannah": ("forward_simulation/Savannah_River", "savana_SI"),
+    "oneD_bump": ("forward_simulation/oneD_channel_with_bump", "oneD_channel_with_bump_refined"),
+    "oneD_uniform": ("forward_simulation/oneD_channel_uniform_flow", "oneD_channel_uniform_flow_refined"),
+    "simple": ("inversion/bathymetry_inversion/simple", "simple"),
+    "oneD_bump_sens": ("sensitivity_analysis/ManningN/oneD_channel_with_bump", "oneD_channel_with_bump_refined"),
+}
+
+
+def main():
+    for name, (rel, stem) in CASES.items():
+        src = os.path.join(REF, rel)
+        dst = os.path.join(HERE, name)
+        os.makedirs(dst, exist_ok=True)
+        for ext in (".srhgeom", ".srhhydro", ".srhmat"):
+            shutil.copyfile(os.path.join(src, stem + ext), os.path.join(dst, stem + ext))
+            os.chmod(os.path.join(dst, stem + ext), 0o644)
+        shutil.copyfile(os.path.join(src, "run_control.json"), os.path.join(dst, "run_control.json"))
+        os.chmod(os.path.join(dst, "run_control.json"), 0o644)
+        t = os.path.join(src, "forward_simulation_solution_truth.json")
+        if os.path.exists(t):
+            d = json.load(open(t))
+            arrs = {}
+            for k, v in d.items():
+                try:
+                    arrs[k] = np.array(v, dtype=np.float64)
+                except (ValueError, TypeError):
+                    # S0_faces_truth is ragged [N][nF][2]; pad to [N, 8, 2]
+                    a = np.zeros((len(v), 8, 2))
+                    for i, row in enumerate(v):
+                        for j, p in enumerate(row):
+                            a[i, j] = p
+                    arrs[k] = a
+            np.savez_compressed(os.path.join(dst, "truth.npz"), **arrs)
+        ic = os.path.join(src, "forward_simulation_initial_condition.json")
+        if os.path.exists(ic):
+            d = json.load(open(ic))
+            np.savez_compressed(os.path.join(dst, "ic.npz"), **{k: np.array(v, dtype=np.float64) for k, v in d.items()})
+        fr = os.path.join(src, "forward_simulation_results.json")
+        if os.path.exists(fr):
+            d = json.load(open(fr))
+            print(name, "forward_simulation_results keys:", {k: np.shape(v) for k, v in d.items()})
+            out = {}
+            for k, v in d.items():
+                a = np.array(v, dtype=np.float64)
+                if k == "forward_simulation_results":        # 3N x 101 column-major, flattened
+                    a = a.reshape(101, -1)                   # -> [101, 3N]
+                    out[k] = a[[0, 50, 100]]
+                else:
+                    out[k] = a
+            np.savez_compressed(os.path.join(dst, "trajectory.npz"), **out)
+        sr = os.path.join(src, "sensitivity_results.json")
+        if os.path.exists(sr):
+            d = json.load(open(sr))
+            print(name, "sensitivity_results keys:", {k: np.shape(v) for k, v in d.items()})
+            np.savez_compressed(os.path.join(dst, "sensitivity.npz"),
+                                **{k: np.array(v, dtype=np.float64) for k, v in d.items()
+                                   if not isinstance(v, str)})
+
+
+if __name__ == "__main__":
+    main()

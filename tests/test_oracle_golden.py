@@ -1,0 +1,90 @@
+"""CPU tests: pin the oracle against every fixture the reference commits for this path."""
+import numpy as np
+import pytest
+
+from oracle import srh2d_ref as R
+from oracle.oracle import Oracle
+from tests import cases
+
+
+@pytest.mark.parametrize("name", ["savannah", "oneD_bump", "oneD_uniform", "simple"])
+def test_bed_elevation_and_slope_bit_exact(name, oracle_lib):
+    """zb_cell_truth / S0_cells_truth pin mesh geometry + update_bed_data (a8) to the bit."""
+    c, t = cases.load(name), cases.truth(name)
+    assert np.array_equal(c.zb_cells, t["zb_cell_truth"])
+    if "S0_cells_truth" in t.files:
+        assert np.array_equal(c.S0_cells.ravel(order="F"), t["S0_cells_truth"])
+        # the C++ restatement of update_bed_data gives the same bits as the numpy one
+        zbg, S0 = Oracle(R.flatten(c)).bed(c.zb_cells)
+        assert np.array_equal(S0, t["S0_cells_truth"])
+        assert np.array_equal(zbg, c.zb_ghost)
+
+
+def test_mesh_sizes_match_survey(oracle_lib):
+    c = cases.load("savannah")
+    assert (c.mesh.numOfCells, c.mesh.numOfFaces, c.mesh.numOfAllBounaryFaces) == (1306, 2737, 276)
+    assert [len(b["faceIDs"]) for b in c.bc.kinds["inletQ"]] == [10]
+    assert [len(b["faceIDs"]) for b in c.bc.kinds["exitH"]] == [10]
+    assert sum(len(b["faceIDs"]) for b in c.bc.kinds["wall"]) == 256
+    c = cases.load("oneD_bump")
+    assert (c.mesh.numOfCells, c.mesh.numOfFaces, c.mesh.numOfAllBounaryFaces) == (200, 601, 402)
+    c = cases.load("simple")   # two MONITORING node strings are skipped, default wall appended
+    assert c.mesh.numOfCells == 12 and len(c.bc.kinds["wall"]) == 1
+
+
+@pytest.mark.parametrize("name", ["savannah", "oneD_bump", "oneD_uniform"])
+def test_friction_truth(name, oracle_lib):
+    """friction_x/y_truth pin compute_friction_terms (a6) to <= 6e-16 relative."""
+    c, t = cases.load(name), cases.truth(name)
+    hs = c.h_small
+    h = t["h_truth"]
+    qx, qy = t["u_truth"] * (h + hs), t["v_truth"] * (h + hs)   # process_forward_simulation_results_2D.jl:32-33
+    fx, fy = Oracle(R.flatten(c)).friction(h, qx, qy, t["ManningN_cells_truth"], c.g, c.k_n, hs)
+    assert np.abs(fx - t["friction_x_truth"]).max() <= 6e-16 * np.abs(t["friction_x_truth"]).max()
+    assert np.abs(fy - t["friction_y_truth"]).max() <= 6e-16 * max(np.abs(t["friction_y_truth"]).max(), 1e-30) + 1e-30
+
+
+def test_steady_state_of_reference_trajectory(oracle_lib):
+    """The reference's saved Tsit5 trajectory (sensitivity case, ManningN = [0.03,0.02,0.03]) converges to the
+    oracle RHS's own steady state: residual at the last save ~2e-5, and explicit Euler integration of the
+    oracle RHS from the same IC lands on the saved final state to ~1e-6 (soft pin of a1-a6 together)."""
+    c = cases.load("oneD_bump_sens")
+    tj = np.load(cases.GOLD + "/oneD_bump_sens/trajectory.npz")
+    assert np.array_equal(tj["hstill"], c.hstill) and np.array_equal(tj["zb_cells"], c.zb_cells)
+    traj = tj["forward_simulation_results"]
+    assert np.array_equal(traj[0], c.Q0)
+    o = Oracle(R.flatten(c))
+    p = np.array([0.03, 0.02, 0.03])
+    r = [np.abs(o.rhs(traj[k], p, 2)).max() for k in range(3)]
+    assert r[0] > 1.0 and r[1] < 2e-3 and r[2] < 5e-5
+    Q = o.euler(c.Q0, 0.01, 20000, p, 2)                       # t = 200 s
+    assert np.abs(Q[:200] - traj[2][:200]).max() < 5e-6        # xi
+    assert np.abs(Q[200:400] - traj[2][200:400]).max() < 5e-6  # q_x (|q_x| ~ 0.2)
+
+
+def test_jvp_matches_finite_differences(oracle_lib):
+    c = cases.load("savannah")
+    o = Oracle(R.flatten(c))
+    rng = np.random.default_rng(0)
+    Q = cases.random_state(c, 1, dry_frac=0.0)
+    v = rng.standard_normal(Q.size)
+    p = c.ManningN_zone.copy()
+    vp = rng.standard_normal(p.size) * 0.01
+    _, jv = o.jvp(Q, v, p, vp, 2)
+    e = 1e-7   # small enough that no wet/dry selector flips between the two evaluations
+    fd = (o.rhs(Q + e * v, p + e * vp, 2) - o.rhs(Q - e * v, p - e * vp, 2)) / (2 * e)
+    assert np.abs(jv - fd).max() <= 1e-6 * np.abs(fd).max()
+
+
+def test_vjp_bruteforce_dot_identity(oracle_lib):
+    c = cases.load("simple")
+    o = Oracle(R.flatten(c))
+    rng = np.random.default_rng(3)
+    Q = cases.random_state(c, 2)
+    lam, v = rng.standard_normal(Q.size), rng.standard_normal(Q.size)
+    p = c.zb_cells.copy()
+    vp = rng.standard_normal(p.size)
+    Qbar, pbar = o.vjp_bruteforce(Q, lam, p, 1)
+    _, jv = o.jvp(Q, v, p, vp, 1)
+    lhs, rhs = lam @ jv, Qbar @ v + pbar @ vp
+    assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), 1.0)
