@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the fp64 2-D shallow-water RHS hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells-m M]
+
+A "step" is one pass of the hot path over the whole mesh: one fused RHS evaluation (swe_2d_rhs,
+semi_discretize_swe_2D.jl:18-277) of the resident state -- plus, once the adjoint kernel is enabled
+(--vjp), one VJP of the same call.  Workload at every N: config C3, the synthetic ~16M-cell
+meandering river per GPU (6 Manning zones, inlet-Q / exit-H / walls), i.e. WEAK scaling: rank r owns
+slab r of a river N times as long.  All inputs (5.6 GB of state + mesh tables) are far larger than the
+126 MB L2, so no flush is needed between iterations (config.l2 says so).
+
+Printed JSON keys follow the driver contract; see DESIGN.md section "Measurement" for the arithmetic:
+  value      cell-updates/s, inputs resident in HBM, CUDA-event time of K steps (max over ranks)
+  e2e        same metric through the host-buffer C-ABI call hg_rhs (pinned host Q in, dQdt out,
+             H2D + D2H inside the timed region)
+  roofline   algorithmic bytes (100 N + 32 F + 4 sum_nF) / measured kernel time vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle (C++ restatement of the reference, NOT Hydrograd.jl itself -- Julia is absent)
+             on a bounded sample of the same workload on this box's host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell_updates_per_sec"
+UNIT = "cell-updates/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes(N, F, sum_nf):
+    """compulsory traffic with every array touched once, int32 indices, fp64 data."""
+    return 100 * N + 32 * F + 4 * sum_nf
+
+
+def cpu_sample(cells_m=2.0, reps=3, threads=0, seed=1234):
+    """Oracle timed on a bounded sample of the C3 workload (a ~cells_m-million-cell slab of the same river)."""
+    from hydrograd_jl_b200 import synthetic as S
+    from oracle.oracle import Oracle
+    ni = max(64, int(cells_m * 1e6 / 1.1 / 1000))
+    flat, Q0 = S.river(ni, 1000, seed=seed)
+    o = Oracle(flat)
+    threads = threads or o.max_threads()
+    o.rhs(Q0, nthreads=threads)
+    t = time.perf_counter()
+    for _ in range(reps):
+        o.rhs(Q0, nthreads=threads)
+    dt = (time.perf_counter() - t) / reps
+    return flat["n_cells"] / dt, threads, f"{reps} RHS calls on a {flat['n_cells']}-cell slab of the C3 river ({ni}x1000 quads)"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  Hydrograd.jl is Julia-only and Julia is not in this image, so
+    this times the oracle port (C++ restatement, reference evaluation order) on all host cores."""
+    import _pkg
+    _pkg.load()
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = []
+    v, cores, sample = None, None, None
+    for s in range(args.warmup + args.steps):
+        v, cores, sample = cpu_sample(cells_m=1.0, reps=1)
+        if s >= args.warmup:
+            per_step.append(v)
+    val = float(np.mean(per_step))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 synthetic meandering-river mesh, fp64 RHS, bounded CPU sample", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cells-m", type=float, default=16.0, help="million cells per GPU")
+    ap.add_argument("--tile", type=int, default=512)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import _pkg
+    hg = _pkg.load()
+    from hydrograd_jl_b200 import synthetic as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        log(f"warning: WORLD_SIZE={world} but --gpus {args.gpus}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+
+    # ---- workload: slab `rank` of a river `world` times as long (weak scaling)
+    ni = int(args.cells_m * 1e6 / 1.1 / 1000)
+    t0 = time.time()
+    flat, Q0 = S.river(ni, 1000, i0=rank * ni, ni_total=world * ni)
+    N, F = flat["n_cells"], flat["n_faces"]
+    log(f"[rank {rank}] mesh: N={N} F={F} ({time.time() - t0:.1f}s)")
+    t0 = time.time()
+    ctx = hg.Context(flat, device=local, tile_cells=args.tile)
+    st = ctx.mesh_stats()
+    log(f"[rank {rank}] context: {st} ({time.time() - t0:.1f}s)")
+    ctx.set_state(Q0)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then exactly K timed steps (CUDA events on the kernel's stream, inside the library)
+    ctx.time_rhs(max(args.warmup, 3))
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = ctx.kernel_launches()
+    ms = ctx.time_rhs(args.steps)
+    barrier()
+    launches = ctx.kernel_launches() - l0
+    clocks = sampler.stop()
+    if dist is not None:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+        tn = torch.tensor([N], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tn)
+        N_total = int(tn.item())
+    else:
+        N_total = N
+    ms_per_step = ms / args.steps
+    value = N_total / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_fused_rhs): algorithmic bytes / measured launch time
+    peak, peak_src = measured_peak()
+    abytes = algorithmic_bytes(N, F, st["sum_cell_faces"])
+    achieved = abytes / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_fused_rhs", "algorithmic_bytes_per_launch": abytes,
+                "bytes_per_cell": abytes / N, "peak_source": peak_src}
+
+    # ---- end to end through the host-buffer ABI call (pinned host memory, H2D + D2H in the timed region)
+    hQ = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+    hD = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+    hQ.numpy()[:] = Q0
+    out = hD.numpy()
+    ctx.rhs(hQ.numpy(), out=out)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        ctx.rhs(hQ.numpy(), out=out)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    if dist is not None:
+        te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    e2e = {"value": N_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 24 * N,
+           "ms_per_step": e2e_s * 1e3}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, sample = cpu_sample()
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "note": "C++ oracle port of the reference algorithm (OpenMP); Hydrograd.jl itself cannot run here (no Julia)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C3 synthetic {N / 1e6:.1f}M-cell meandering river per GPU (mixed tri/quad, 6 Manning "
+                                       "zones, inlet-Q/exit-H/walls); step = one fused fp64 RHS of the resident state",
+                           "cells_per_gpu": N, "faces_per_gpu": F, "tile_cells": args.tile, "n_tiles": st["n_tiles"],
+                           "l2": "inputs (state + mesh tables >> 126 MB L2) larger than L2, no flush needed",
+                           "parallelism": f"rcb-slab x{world}"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,93 @@
+"""ctypes binding of libhydrograd_b200.so (include/hydrograd_b200.h).  Fails loudly if the CUDA
+library has not been built -- there is no Python/CPU fallback for any compute entry point."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhydrograd_b200.so")
+
+c_i64p = C.POINTER(C.c_int64)
+c_f64p = C.POINTER(C.c_double)
+c_u8p = C.POINTER(C.c_uint8)
+
+PARAM_NONE, PARAM_ZB, PARAM_MANNING, PARAM_Q = 0, 1, 2, 3
+# active_param_name strings of the reference (application_commons.jl:9)
+ACTIVE_PARAM = {None: 0, "": 0, "none": 0, "zb": 1, "ManningN": 2, "Q": 3}
+ERR_NAMES = {1: "HG_ERR_ARG", 2: "HG_ERR_CUDA", 3: "HG_ERR_CONVEYANCE", 4: "HG_ERR_SOLVER", 5: "HG_ERR_STATE"}
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("n_cells", C.c_int64), ("n_faces", C.c_int64), ("n_ghost", C.c_int64), ("ld", C.c_int64),
+                ("index_base", C.c_int32), ("cell_nfaces", c_i64p), ("cell_faces", c_i64p),
+                ("cell_neighbors", c_i64p), ("cell_normals", c_f64p), ("face_is_boundary", c_u8p),
+                ("face_lengths", c_f64p), ("cell_areas", c_f64p), ("cell_centroids", c_f64p)]
+
+
+class BcDesc(C.Structure):
+    _fields_ = [("n_inletq", C.c_int64), ("n_exith", C.c_int64), ("n_wall", C.c_int64), ("n_symm", C.c_int64),
+                ("bc_ptr", c_i64p), ("ghost_ids", c_i64p), ("internal_cells", c_i64p),
+                ("outward_normals", c_f64p), ("face_lengths", c_f64p)]
+
+
+class FieldsDesc(C.Structure):
+    _fields_ = [("g", C.c_double), ("k_n", C.c_double), ("h_small", C.c_double), ("riemann_solver", C.c_char_p),
+                ("hstill", c_f64p), ("hstill_ghost", c_f64p), ("zb_cells", c_f64p), ("zb_ghost", c_f64p),
+                ("S0_cells", c_f64p), ("ManningN_cells", c_f64p), ("matID_cells", c_i64p), ("n_mat", C.c_int64),
+                ("inletQ_TotalQ", c_f64p), ("exitH_WSE", c_f64p)]
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("tile_cells", C.c_int32), ("reorder", C.c_int32), ("strict", C.c_int32),
+                ("path", C.c_int32), ("reserved", C.c_int32 * 11)]
+
+
+# every symbol include/hydrograd_b200.h declares: name -> (restype, argtypes)
+_vp = C.c_void_p
+SYMBOLS = {
+    "hg_default_options": (None, [C.POINTER(Options)]),
+    "hg_abi_version": (C.c_int, []),
+    "hg_create": (C.c_int, [C.POINTER(_vp), C.POINTER(MeshDesc), C.POINTER(BcDesc), C.POINTER(FieldsDesc),
+                            C.POINTER(Options)]),
+    "hg_destroy": (None, [_vp]),
+    "hg_last_error": (C.c_char_p, [_vp]),
+    "hg_n_cells": (C.c_int64, [_vp]),
+    "hg_set_fields": (C.c_int, [_vp, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "hg_rhs": (C.c_int, [_vp, c_f64p, c_f64p, C.c_int64, C.c_int32, C.c_double, c_f64p]),
+    "hg_rhs_vjp": (C.c_int, [_vp, c_f64p, c_f64p, C.c_int64, C.c_int32, C.c_double, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "hg_set_state": (C.c_int, [_vp, c_f64p]),
+    "hg_get_state": (C.c_int, [_vp, c_f64p]),
+    "hg_set_params": (C.c_int, [_vp, c_f64p, C.c_int64, C.c_int32]),
+    "hg_rhs_resident": (C.c_int, [_vp]),
+    "hg_get_rhs": (C.c_int, [_vp, c_f64p]),
+    "hg_sync": (C.c_int, [_vp]),
+    "hg_step_euler": (C.c_int, [_vp, C.c_double, C.c_int64]),
+    "hg_custom_ode_solve": (C.c_int, [_vp, c_f64p, c_f64p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                      c_f64p, C.c_int64, c_i64p]),
+    "hg_time_rhs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
+    "hg_time_vjp": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_float)]),
+    "hg_kernel_launches": (C.c_int64, [_vp]),
+    "hg_mesh_stats": (C.c_int, [_vp, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p]),
+    "hg_plan_stats": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(BcDesc), C.POINTER(FieldsDesc), C.POINTER(Options),
+                                c_i64p, c_i64p]),
+    "hg_flush_l2": (C.c_int, [_vp]),
+}
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python hydrograd.jl_b200/csrc/build.py` "
+                "(or __graft_entry__.build()).  There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)      # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,254 @@
+"""Host-side mirror of the reference's interface for the RHS path, on top of the C ABI.
+
+Julia is not available in this image, so this Python layer plays the role of the Julia shim
+(hydrograd.jl_b200/julia/HydrogradB200.jl): same names, argument meaning and error behaviour as
+
+  swe_2d_rhs(dQdt, Q, params_vector, t, p_extra)     src/fvm/discretization/semi_discretize_swe_2D.jl:18-19
+  custom_ODE_solve(ode_f, Q0, params_vector, extra)  src/ode_solvers/custom_ODE_solvers.jl:36
+  SWE2D_Extra_Parameters                             src/applications/application_commons.jl:7-44
+
+All arithmetic happens in the CUDA library; numpy is only used to hold host buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+
+
+class HydrogradError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{L.ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t=L.c_f64p):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def _descs(f: dict):
+    """ctypes descriptors over (contiguous, correctly typed copies of) the flat tables."""
+    keep = {}
+    for k in ("cell_nfaces", "cell_faces", "cell_neighbors", "bc_ptr", "bc_ghost_ids", "bc_internal_cells"):
+        keep[k] = np.ascontiguousarray(f[k], dtype=np.int64)
+    keep["matID_cells"] = (np.ascontiguousarray(f["matID_cells"], dtype=np.int64)
+                           if f.get("matID_cells") is not None else None)
+    keep["face_is_boundary"] = np.ascontiguousarray(f["face_is_boundary"], dtype=np.uint8)
+    for k in ("cell_normals", "face_lengths", "cell_areas", "bc_normals", "bc_lengths", "hstill", "hstill_ghost",
+              "zb_cells", "zb_ghost", "S0_cells", "ManningN_cells", "inletQ_TotalQ", "exitH_WSE"):
+        keep[k] = _f64(f[k])
+    keep["cell_centroids"] = _f64(f["cell_centroids"]) if f.get("cell_centroids") is not None else None
+    mesh = L.MeshDesc(int(f["n_cells"]), int(f["n_faces"]), int(f["n_ghost"]), int(f["ld"]), int(f["index_base"]),
+                      _p(keep["cell_nfaces"], L.c_i64p), _p(keep["cell_faces"], L.c_i64p),
+                      _p(keep["cell_neighbors"], L.c_i64p), _p(keep["cell_normals"]),
+                      _p(keep["face_is_boundary"], L.c_u8p), _p(keep["face_lengths"]), _p(keep["cell_areas"]),
+                      _p(keep["cell_centroids"]))
+    bc = L.BcDesc(int(f["n_inletq"]), int(f["n_exith"]), int(f["n_wall"]), int(f["n_symm"]),
+                  _p(keep["bc_ptr"], L.c_i64p), _p(keep["bc_ghost_ids"], L.c_i64p),
+                  _p(keep["bc_internal_cells"], L.c_i64p), _p(keep["bc_normals"]), _p(keep["bc_lengths"]))
+    keep["solver"] = f.get("riemann_solver", "Roe").encode()
+    fields = L.FieldsDesc(float(f["g"]), float(f["k_n"]), float(f["h_small"]), keep["solver"],
+                          _p(keep["hstill"]), _p(keep["hstill_ghost"]), _p(keep["zb_cells"]), _p(keep["zb_ghost"]),
+                          _p(keep["S0_cells"]), _p(keep["ManningN_cells"]),
+                          _p(keep["matID_cells"], L.c_i64p), int(f.get("n_mat", 0)),
+                          _p(keep["inletQ_TotalQ"]), _p(keep["exitH_WSE"]))
+    return mesh, bc, fields, keep
+
+
+def _options(lib, device=0, tile_cells=512, reorder=True, strict=False, path=0):
+    opt = L.Options()
+    lib.hg_default_options(C.byref(opt))
+    opt.device, opt.tile_cells, opt.reorder, opt.strict, opt.path = device, tile_cells, int(reorder), int(strict), path
+    return opt
+
+
+def plan_stats(flat: dict, tile_cells=512, reorder=True, want_perm=False):
+    """Host-only preview of the hg_create preprocessing (no GPU needed): tiling statistics (+ permutation)."""
+    lib = L.load()
+    mesh, bc, fields, keep = _descs(flat)
+    opt = _options(lib, 0, tile_cells, reorder)
+    stats = np.zeros(8, dtype=np.int64)
+    perm = np.zeros(int(flat["n_cells"]), dtype=np.int64) if want_perm else None
+    rc = lib.hg_plan_stats(C.byref(mesh), C.byref(bc), C.byref(fields), C.byref(opt), _p(stats, L.c_i64p),
+                           _p(perm, L.c_i64p))
+    if rc:
+        raise HydrogradError(rc, (lib.hg_last_error(None) or b"").decode())
+    out = dict(zip(("n_tiles", "max_local", "max_faces", "smem_bytes", "halo_cells", "tile_faces", "interior_tile_faces",
+                    "sum_cell_faces"), (int(x) for x in stats)))
+    return (out, perm) if want_perm else out
+
+
+class Context:
+    """Owns one hg_ctx (one mesh on one GPU).  `flat` holds the flat tables of include/hydrograd_b200.h
+    (see INTEGRATION.md for how the Julia structs map onto them)."""
+
+    def __init__(self, flat: dict, device=0, tile_cells=512, reorder=True, strict=False, path=0):
+        self.lib = L.load()
+        self._h = C.c_void_p()
+        mesh, bc, fields, keep = _descs(flat)
+        opt = _options(self.lib, device, tile_cells, reorder, strict, path)
+        rc = self.lib.hg_create(C.byref(self._h), C.byref(mesh), C.byref(bc), C.byref(fields), C.byref(opt))
+        del keep            # the library copied what it needs (ownership rule of the ABI)
+        if rc:
+            raise HydrogradError(rc, (self.lib.hg_last_error(None) or b"").decode())
+        self.N = int(flat["n_cells"])
+        self.n_ghost = int(flat["n_ghost"])
+
+    # ---------------------------------------------------------------- plumbing
+    def _ck(self, rc):
+        if rc:
+            raise HydrogradError(rc, (self.lib.hg_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.hg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _params(params, active):
+        a = L.ACTIVE_PARAM[active] if not isinstance(active, int) else active
+        if a == 0 or params is None:
+            return None, 0, a
+        p = _f64(params)
+        return p, p.size, a
+
+    # ---------------------------------------------------------------- host-buffer API (drop-in semantics)
+    def rhs(self, Q, params=None, active=None, t=0.0, out=None):
+        Q = _f64(Q)
+        if Q.size != 3 * self.N:
+            raise HydrogradError(1, f"Q has length {Q.size}, expected {3 * self.N}")
+        out = np.empty(3 * self.N) if out is None else out
+        p, n, a = self._params(params, active)
+        self._ck(self.lib.hg_rhs(self._h, _p(Q), _p(p), n, a, float(t), _p(out)))
+        return out
+
+    def rhs_vjp(self, Q, lam, params=None, active=None, t=0.0, want_ncell_bar=False):
+        Q, lam = _f64(Q), _f64(lam)
+        p, n, a = self._params(params, active)
+        Qbar = np.empty(3 * self.N)
+        pbar = np.zeros(max(n, 1))
+        nbar = np.empty(self.N) if want_ncell_bar else None
+        self._ck(self.lib.hg_rhs_vjp(self._h, _p(Q), _p(p), n, a, float(t), _p(lam), _p(Qbar), _p(pbar), _p(nbar)))
+        return (Qbar, pbar[:n], nbar) if want_ncell_bar else (Qbar, pbar[:n])
+
+    # ---------------------------------------------------------------- device-resident API
+    def set_state(self, Q):
+        self._ck(self.lib.hg_set_state(self._h, _p(_f64(Q))))
+
+    def get_state(self):
+        out = np.empty(3 * self.N)
+        self._ck(self.lib.hg_get_state(self._h, _p(out)))
+        return out
+
+    def set_params(self, params, active):
+        p, n, a = self._params(params, active)
+        self._ck(self.lib.hg_set_params(self._h, _p(p), n, a))
+
+    def set_fields(self, ManningN_cells=None, zb_cells=None, zb_ghost=None, S0_cells=None, inletQ_TotalQ=None,
+                   exitH_WSE=None):
+        arrs = [None if a is None else _f64(a)
+                for a in (ManningN_cells, zb_cells, zb_ghost, S0_cells, inletQ_TotalQ, exitH_WSE)]
+        self._ck(self.lib.hg_set_fields(self._h, *[_p(a) for a in arrs]))
+
+    def rhs_resident(self):
+        self._ck(self.lib.hg_rhs_resident(self._h))
+
+    def get_rhs(self):
+        out = np.empty(3 * self.N)
+        self._ck(self.lib.hg_get_rhs(self._h, _p(out)))
+        return out
+
+    def sync(self):
+        self._ck(self.lib.hg_sync(self._h))
+
+    def step_euler(self, dt, nsteps=1):
+        self._ck(self.lib.hg_step_euler(self._h, float(dt), int(nsteps)))
+
+    def custom_ode_solve(self, Q0, params, active, t_start, t_end, dt):
+        nsteps = int(np.floor((t_end - t_start) / dt + 1e-9)) + 1 if t_end >= t_start else 0
+        sol = np.empty((max(nsteps, 1), 3 * self.N))   # row s = column s of the reference's 3N x nSaves `sol`
+        ns = C.c_int64(0)
+        p, n, a = self._params(params, active)
+        self._ck(self.lib.hg_custom_ode_solve(self._h, _p(_f64(Q0)), _p(p), n, a, float(t_start), float(t_end),
+                                              float(dt), _p(sol), nsteps, C.byref(ns)))
+        return sol[:ns.value].T
+
+    # ---------------------------------------------------------------- measurement hooks
+    def time_rhs(self, n_launches, fused_euler=False, dt=0.0):
+        ms = C.c_float(0)
+        self._ck(self.lib.hg_time_rhs(self._h, int(n_launches), int(fused_euler), float(dt), C.byref(ms)))
+        return ms.value
+
+    def kernel_launches(self):
+        return int(self.lib.hg_kernel_launches(self._h))
+
+    def mesh_stats(self):
+        v = [C.c_int64(0) for _ in range(5)]
+        self._ck(self.lib.hg_mesh_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("n_cells", "n_faces", "sum_cell_faces", "n_tiles", "device_bytes"), (x.value for x in v)))
+
+    def flush_l2(self):
+        self._ck(self.lib.hg_flush_l2(self._h))
+
+
+# ------------------------------------------------------------------------------------------------
+# Reference-shaped front end
+@dataclass
+class swe_2D_consts:
+    """src/constants/swe_2D_constants.jl:4-17 (fields the RHS reads + the Euler stepper's time data)."""
+    g: float = 9.81
+    k_n: float = 1.0
+    h_small: float = 1.0e-3
+    dt: float = 0.0
+    tspan: tuple = (0.0, 0.0)
+    RiemannSolver: str = "Roe"
+
+
+@dataclass
+class SWE2D_Extra_Parameters:
+    """src/applications/application_commons.jl:7-44 restricted to what swe_2d_rhs reads.  `flat` carries the
+    flattened mesh_2D / BoundaryConditions2D tables; the device context is created on first use."""
+    flat: dict
+    active_param_name: str = ""
+    bInPlaceODE: bool = False
+    swe_2D_constants: swe_2D_consts = field(default_factory=swe_2D_consts)
+    options: dict = field(default_factory=dict)
+    _ctx: Optional[Context] = None
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            f = dict(self.flat)
+            c = self.swe_2D_constants
+            f.update(g=c.g, k_n=c.k_n, h_small=c.h_small, riemann_solver=c.RiemannSolver)
+            self._ctx = Context(f, **self.options)
+        return self._ctx
+
+
+def swe_2d_rhs(dQdt, Q, params_vector, t, p_extra: SWE2D_Extra_Parameters):
+    """Same contract as the reference: in-place when p_extra.bInPlaceODE, else returns a new vector."""
+    if p_extra.bInPlaceODE:
+        p_extra.ctx.rhs(Q, params_vector, p_extra.active_param_name, t, out=dQdt)
+        return dQdt
+    return p_extra.ctx.rhs(Q, params_vector, p_extra.active_param_name, t)
+
+
+def custom_ODE_solve(ode_f, Q0, params_vector, swe2d_extra_params: SWE2D_Extra_Parameters):
+    """custom_ODE_solvers.jl:36-95.  `ode_f` is accepted for signature parity; the stepping runs on the device."""
+    c = swe2d_extra_params.swe_2D_constants
+    return swe2d_extra_params.ctx.custom_ode_solve(Q0, params_vector, swe2d_extra_params.active_param_name,
+                                                   c.tspan[0], c.tspan[1], c.dt)

@@ -1,0 +1,47 @@
+"""Builds libhydrograd_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+OUT = os.path.join(PKG, "libhydrograd_b200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+SOURCES = [
+    ("hg_host.cpp", []),
+    ("hg_api.cu", []),
+    ("hg_plain.cu", ["-fmad=false"]),      # reference evaluation order, no FMA contraction
+    ("hg_fused.cu", []),
+]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = [os.path.join(HERE, "hg_ctx.h"), os.path.join(PKG, "..", "include", "hydrograd_b200.h"), __file__]
+    objs = []
+    for src, extra in SOURCES:
+        s = os.path.join(HERE, src)
+        o = os.path.join(objdir, src.rsplit(".", 1)[0] + ".o")
+        objs.append(o)
+        if force or _newer(o, [s] + hdrs):
+            cmd = ["nvcc"] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", s, "-o", o]
+            print(" ".join(cmd), flush=True)
+            subprocess.run(cmd, check=True)
+    if force or _newer(OUT, objs):
+        cmd = ["nvcc"] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + objs
+        print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)

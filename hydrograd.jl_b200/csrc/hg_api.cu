@@ -1,0 +1,468 @@
+// extern "C" entry points of include/hydrograd_b200.h.  Owns the context, device memory and the
+// stream; there is no CPU fallback: without a CUDA device hg_create fails with HG_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "hg_ctx.h"
+
+namespace {
+std::mutex g_err_mu;
+std::string g_err;  // error of the last failed hg_create
+
+void set_global_err(const std::string& s) {
+  std::lock_guard<std::mutex> l(g_err_mu);
+  g_err = s;
+}
+
+#define CK(ctx, expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                   \
+      return HG_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+template <class T>
+int up(hg_ctx* ctx, hg::DBuf<T>& b, const std::vector<T>& h) {
+  CK(ctx, b.upload(h, ctx->stream));
+  ctx->device_bytes += (int64_t)b.bytes();
+  return HG_OK;
+}
+template <class T>
+int al(hg_ctx* ctx, hg::DBuf<T>& b, size_t n) {
+  CK(ctx, b.alloc(n));
+  ctx->device_bytes += (int64_t)b.bytes();
+  if (n) CK(ctx, cudaMemsetAsync(b.p, 0, b.bytes(), ctx->stream));
+  return HG_OK;
+}
+#define TRY(x)                 \
+  do {                         \
+    int _rc = (x);             \
+    if (_rc != HG_OK) return _rc; \
+  } while (0)
+
+template <class T>
+std::vector<T> permuted(const T* src, const std::vector<int32_t>& perm) {
+  std::vector<T> o(perm.size());
+  for (size_t i = 0; i < perm.size(); ++i) o[i] = src[perm[i]];
+  return o;
+}
+
+int check_err_flag(hg_ctx* ctx) {
+  int32_t* flag = ctx->opt.path == 1 ? ctx->pd.err.p : ctx->fd.err.p;
+  int32_t h = 0;
+  CK(ctx, cudaMemcpyAsync(&h, flag, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h != 0) {
+    CK(ctx, cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
+    if (h == HG_ERR_CONVEYANCE) ctx->err = "Total cross-sectional conveyance for an inlet-q boundary is not positive";
+    else ctx->err = "device-side error flag " + std::to_string(h);
+    return h;
+  }
+  return HG_OK;
+}
+
+using hg::Frozen;
+hg_ctx* ext(hg_ctx* c) { return c; }
+}  // namespace
+
+static int upload_fields(hg_ctx* ctx) {
+  hg_ctx* x = ext(ctx);
+  const int64_t N = ctx->N, B = ctx->B;
+  const Frozen& fr = x->fr;
+  if (ctx->opt.path == 1) {
+    hg::PlainDev& p = ctx->pd;
+    CK(ctx, cudaMemcpyAsync(p.mann.p, fr.mann_ref.data(), N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(p.zb.p, fr.zb_ref.data(), N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(p.S0x.p, fr.S0_ref.data(), N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(p.S0y.p, fr.S0_ref.data() + N, N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (B) CK(ctx, cudaMemcpyAsync(p.zb_g.p, fr.zbg_ghost.data(), B * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n_inletq) CK(ctx, cudaMemcpyAsync(p.Qin.p, fr.Qin.data(), ctx->n_inletq * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n_exith) CK(ctx, cudaMemcpyAsync(p.wse.p, fr.wse.data(), ctx->n_exith * 8, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    hg::FusedDev& d = ctx->fd;
+    const auto& perm = ctx->fh.perm;
+    auto mann = permuted(fr.mann_ref.data(), perm), zb = permuted(fr.zb_ref.data(), perm);
+    auto s0x = permuted(fr.S0_ref.data(), perm), s0y = permuted(fr.S0_ref.data() + N, perm);
+    std::vector<double> bzb(B);
+    for (int64_t e = 0; e < B; ++e) bzb[e] = fr.zbg_ghost[ctx->bch.ghost[e]];
+    CK(ctx, cudaMemcpyAsync(d.mann.p, mann.data(), N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(d.zb.p, zb.data(), N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(d.S0x.p, s0x.data(), N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(d.S0y.p, s0y.data(), N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (B) CK(ctx, cudaMemcpyAsync(d.bc_zb.p, bzb.data(), B * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n_inletq) CK(ctx, cudaMemcpyAsync(d.Qin.p, fr.Qin.data(), ctx->n_inletq * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n_exith) CK(ctx, cudaMemcpyAsync(d.wse.p, fr.wse.data(), ctx->n_exith * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));  // the temporaries above die here
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return HG_OK;
+}
+
+// Bind params_vector to the frozen fields (semi_discretize_swe_2D.jl:114-126, 153-161, 190-199).
+// Parameters change once per optimiser iteration but the RHS runs thousands of times in between,
+// so the binding is done here, once, and the RHS kernels stay parameter-agnostic.
+static int bind_params(hg_ctx* ctx, const double* params, int64_t np, int32_t active) {
+  hg_ctx* x = ext(ctx);
+  if (active < HG_PARAM_NONE || active > HG_PARAM_Q) { ctx->err = "bad active_param"; return HG_ERR_ARG; }
+  const int64_t want = active == HG_PARAM_ZB ? ctx->N : active == HG_PARAM_MANNING ? ctx->n_mat : active == HG_PARAM_Q ? ctx->n_inletq : 0;
+  if (active != HG_PARAM_NONE && (np != want || !params)) {
+    ctx->err = "params_vector has length " + std::to_string(np) + ", expected " + std::to_string(want);
+    return HG_ERR_ARG;
+  }
+  if (active == HG_PARAM_MANNING && x->matid_ref.empty()) { ctx->err = "matID_cells was not provided at hg_create"; return HG_ERR_ARG; }
+  if (active == HG_PARAM_NONE) np = 0;
+  const bool same = (active == x->last_active) && (np == (int64_t)x->last_params.size()) &&
+                    (np == 0 || std::memcmp(params, x->last_params.data(), np * 8) == 0);
+  if (same) return HG_OK;
+  // restore pristine fields if the previous binding overwrote them
+  if (x->last_active > HG_PARAM_NONE && ctx->opt.path != 1) TRY(upload_fields(ctx));
+  x->last_active = active;
+  x->last_params.assign(params, params + np);
+  ctx->active = active;
+  ctx->n_params = np;
+  if (active == HG_PARAM_NONE) return HG_OK;
+  if (ctx->opt.path == 1) {
+    CK(ctx, cudaMemcpyAsync(ctx->pd.params.p, params, np * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return HG_OK;
+  }
+  hg::FusedDev& d = ctx->fd;
+  CK(ctx, cudaMemcpyAsync(d.params.p, params, np * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (active == HG_PARAM_Q) {
+    CK(ctx, cudaMemcpyAsync(d.Qin.p, d.params.p, np * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else if (active == HG_PARAM_MANNING) {
+    TRY(hg::fused_bind_manning(ctx, d.params.p));
+  } else {
+    TRY(hg::fused_bind_zb(ctx, d.params.p));
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return HG_OK;
+}
+
+extern "C" {
+
+void hg_default_options(hg_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->device = 0; o->tile_cells = 512; o->reorder = 1; o->strict = 0; o->path = 0;
+}
+int hg_abi_version(void) { return HG_ABI_VERSION; }
+
+const char* hg_last_error(const hg_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  std::lock_guard<std::mutex> l(g_err_mu);
+  static thread_local std::string copy;
+  copy = g_err;
+  return copy.c_str();
+}
+int64_t hg_n_cells(const hg_ctx* ctx) { return ctx ? ctx->N : 0; }
+int64_t hg_kernel_launches(const hg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void hg_destroy(hg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->opt.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  cudaStream_t s = ctx->stream;
+  delete ctx;  // frees the device buffers
+  if (s) cudaStreamDestroy(s);
+}
+
+static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    ctx->err = "no CUDA device available (this library has no CPU fallback)";
+    return HG_ERR_CUDA;
+  }
+  if (ctx->opt.device < 0 || ctx->opt.device >= ndev) { ctx->err = "bad device ordinal"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  cudaDeviceProp prop;
+  CK(ctx, cudaGetDeviceProperties(&prop, ctx->opt.device));
+  if (prop.major != 10) {
+    ctx->err = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this build is sm_100a only";
+    return HG_ERR_CUDA;
+  }
+  CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(ctx, cudaEventCreate(&ctx->ev0));
+  CK(ctx, cudaEventCreate(&ctx->ev1));
+
+  std::vector<int32_t> cf_ptr, cf_nb, cf_face;
+  std::vector<double> cf_nx, cf_ny, cf_len;
+  TRY(hg::build_host(ctx, m, b, f, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face));
+  const int64_t N = ctx->N, B = ctx->B;
+  hg_ctx* x = ext(ctx);
+  Frozen& fr = x->fr;
+  fr.mann_ref.assign(f->ManningN_cells, f->ManningN_cells + N);
+  fr.zb_ref.assign(f->zb_cells, f->zb_cells + N);
+  fr.S0_ref.assign(f->S0_cells, f->S0_cells + 2 * N);
+  fr.zbg_ghost.assign(f->zb_ghost, f->zb_ghost + B);
+  fr.Qin.assign(f->inletQ_TotalQ, f->inletQ_TotalQ + ctx->n_inletq);
+  fr.wse.assign(f->exitH_WSE, f->exitH_WSE + ctx->n_exith);
+  if (f->matID_cells) {
+    x->matid_ref.resize(N);
+    for (int64_t i = 0; i < N; ++i) {
+      if (f->matID_cells[i] < 0 || f->matID_cells[i] >= std::max<int64_t>(f->n_mat, 1)) { ctx->err = "matID_cells out of range"; return HG_ERR_ARG; }
+      x->matid_ref[i] = (int32_t)f->matID_cells[i];
+    }
+  }
+  const hg::BcHost& h = ctx->bch;
+  const size_t npar = (size_t)std::max<int64_t>(std::max<int64_t>(N, ctx->n_mat), std::max<int64_t>(ctx->n_inletq, 1));
+  std::vector<double> hstill(f->hstill, f->hstill + N), area(m->cell_areas, m->cell_areas + N);
+
+  if (ctx->opt.path == 1) {
+    hg::PlainDev& p = ctx->pd;
+    TRY(up(ctx, p.cf_ptr, cf_ptr)); TRY(up(ctx, p.cf_nb, cf_nb));
+    TRY(up(ctx, p.cf_nx, cf_nx)); TRY(up(ctx, p.cf_ny, cf_ny)); TRY(up(ctx, p.cf_len, cf_len));
+    TRY(up(ctx, p.area, area)); TRY(up(ctx, p.hstill, hstill));
+    TRY(al(ctx, p.zb, N)); TRY(al(ctx, p.S0x, N)); TRY(al(ctx, p.S0y, N)); TRY(al(ctx, p.mann, N));
+    TRY(up(ctx, p.matid, x->matid_ref));
+    TRY(up(ctx, p.bc_type, h.type)); TRY(up(ctx, p.bc_group, h.group)); TRY(up(ctx, p.bc_ghost, h.ghost));
+    TRY(up(ctx, p.bc_cell, h.cell_ref)); TRY(up(ctx, p.inlet_ptr, h.inlet_ptr));
+    TRY(up(ctx, p.bc_nx, h.nx)); TRY(up(ctx, p.bc_ny, h.ny)); TRY(up(ctx, p.bc_l53, h.l53)); TRY(up(ctx, p.bc_l23, h.l23));
+    std::vector<double> hg_g(f->hstill_ghost, f->hstill_ghost + B);
+    TRY(up(ctx, p.hstill_g, hg_g)); TRY(al(ctx, p.zb_g, B));
+    TRY(al(ctx, p.gh, B)); TRY(al(ctx, p.gqx, B)); TRY(al(ctx, p.gqy, B)); TRY(al(ctx, p.gxi, B));
+    TRY(al(ctx, p.Qin, ctx->n_inletq)); TRY(al(ctx, p.wse, ctx->n_exith));
+    TRY(al(ctx, p.Q, 3 * N)); TRY(al(ctx, p.dQ, 3 * N)); TRY(al(ctx, p.params, npar)); TRY(al(ctx, p.err, 1));
+  } else {
+    TRY(hg::build_tiles(ctx, m, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face));
+    hg::FusedHost& fh = ctx->fh;
+    hg::FusedDev& d = ctx->fd;
+    TRY(up(ctx, d.perm, fh.perm)); TRY(up(ctx, d.iperm, fh.iperm)); TRY(up(ctx, d.tile_cell0, fh.tile_cell0));
+    TRY(up(ctx, d.halo_ptr, fh.halo_ptr)); TRY(up(ctx, d.halo, fh.halo)); TRY(up(ctx, d.face_ptr, fh.face_ptr));
+    TRY(up(ctx, d.face_nint, fh.face_nint)); TRY(up(ctx, d.face_bce, fh.face_bce)); TRY(up(ctx, d.cf_ptr, fh.cf_ptr));
+    TRY(up(ctx, d.face_lr, fh.face_lr)); TRY(up(ctx, d.cf_idx, fh.cf_idx));
+    TRY(up(ctx, d.face_nx, fh.face_nx)); TRY(up(ctx, d.face_ny, fh.face_ny)); TRY(up(ctx, d.face_len, fh.face_len));
+    TRY(up(ctx, d.area, permuted(area.data(), fh.perm))); TRY(up(ctx, d.hstill, permuted(hstill.data(), fh.perm)));
+    TRY(al(ctx, d.zb, N)); TRY(al(ctx, d.S0x, N)); TRY(al(ctx, d.S0y, N)); TRY(al(ctx, d.mann, N));
+    if (!x->matid_ref.empty()) TRY(up(ctx, d.matid, permuted(x->matid_ref.data(), fh.perm)));
+    std::vector<int32_t> bc_cell(B);
+    std::vector<double> bhst(B);
+    for (int64_t e = 0; e < B; ++e) { bc_cell[e] = fh.iperm[h.cell_ref[e]]; bhst[e] = h.hstill_g[e]; }
+    TRY(up(ctx, d.bc_type, h.type)); TRY(up(ctx, d.bc_group, h.group)); TRY(up(ctx, d.bc_cell, bc_cell));
+    TRY(up(ctx, d.bc_nx, h.nx)); TRY(up(ctx, d.bc_ny, h.ny)); TRY(up(ctx, d.bc_l53, h.l53)); TRY(up(ctx, d.bc_l23, h.l23));
+    TRY(up(ctx, d.bc_hstill, bhst)); TRY(al(ctx, d.bc_zb, B)); TRY(up(ctx, d.inlet_ptr, h.inlet_ptr));
+    TRY(al(ctx, d.inlet_coef, std::max<int64_t>(ctx->n_inletq, 1)));
+    TRY(al(ctx, d.Qin, ctx->n_inletq)); TRY(al(ctx, d.wse, ctx->n_exith));
+    TRY(al(ctx, d.Q, 3 * N)); TRY(al(ctx, d.Q2, 3 * N)); TRY(al(ctx, d.dQ, 3 * N)); TRY(al(ctx, d.stage, 3 * N));
+    TRY(al(ctx, d.params, npar)); TRY(al(ctx, d.err, 1));
+    // the plain CSR in reference order is kept for update_bed_data when zb is the active parameter
+    hg::PlainDev& p = ctx->pd;
+    TRY(up(ctx, p.cf_ptr, cf_ptr)); TRY(up(ctx, p.cf_nb, cf_nb));
+    TRY(up(ctx, p.cf_nx, cf_nx)); TRY(up(ctx, p.cf_ny, cf_ny)); TRY(up(ctx, p.cf_len, cf_len));
+    TRY(up(ctx, p.area, area)); TRY(up(ctx, p.bc_cell, h.cell_ref));
+    TRY(hg::fused_prepare(ctx));
+  }
+  TRY(upload_fields(ctx));
+  return HG_OK;
+}
+
+int hg_create(hg_ctx** out, const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, const hg_options* opt) {
+  if (!out) { set_global_err("hg_create: out is NULL"); return HG_ERR_ARG; }
+  *out = nullptr;
+  hg_ctx* ctx = new hg_ctx();
+  if (opt) ctx->opt = *opt; else hg_default_options(&ctx->opt);
+  if (ctx->opt.strict) ctx->opt.path = 1;  // the strict build IS the plain path
+  int rc = create_impl(ctx, m, b, f);
+  if (rc != HG_OK) {
+    set_global_err(ctx->err);
+    hg_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return HG_OK;
+}
+
+int hg_set_fields(hg_ctx* ctx, const double* mann, const double* zb, const double* zbg, const double* S0,
+                  const double* Qin, const double* wse) {
+  if (!ctx) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg_ctx* x = ext(ctx);
+  Frozen& fr = x->fr;
+  if (mann) fr.mann_ref.assign(mann, mann + ctx->N);
+  if (zb) fr.zb_ref.assign(zb, zb + ctx->N);
+  if (zbg) fr.zbg_ghost.assign(zbg, zbg + ctx->B);
+  if (S0) fr.S0_ref.assign(S0, S0 + 2 * ctx->N);
+  if (Qin) fr.Qin.assign(Qin, Qin + ctx->n_inletq);
+  if (wse) fr.wse.assign(wse, wse + ctx->n_exith);
+  x->last_active = -1;  // force re-binding on the next call
+  x->last_params.clear();
+  return upload_fields(ctx);
+}
+
+int hg_sync(hg_ctx* ctx) {
+  if (!ctx) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_err_flag(ctx);
+}
+
+int hg_set_params(hg_ctx* ctx, const double* params, int64_t np, int32_t active) {
+  if (!ctx) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  return bind_params(ctx, params, np, active);
+}
+
+int hg_set_state(hg_ctx* ctx, const double* Q) {
+  if (!ctx || !Q) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  const int64_t N = ctx->N;
+  if (ctx->opt.path == 1) {
+    CK(ctx, cudaMemcpyAsync(ctx->pd.Q.p, Q, 3 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    CK(ctx, cudaMemcpyAsync(ctx->fd.stage.p, Q, 3 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(hg::fused_permute(ctx, ctx->fd.perm.p, ctx->fd.stage.p, ctx->fd.Q.p));
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->state_set = true;
+  return HG_OK;
+}
+
+static int download3(hg_ctx* ctx, const double* d_internal_or_ref, double* host) {
+  const int64_t N = ctx->N;
+  if (ctx->opt.path == 1) {
+    CK(ctx, cudaMemcpyAsync(host, d_internal_or_ref, 3 * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    TRY(hg::fused_permute(ctx, ctx->fd.iperm.p, d_internal_or_ref, ctx->fd.stage.p));
+    CK(ctx, cudaMemcpyAsync(host, ctx->fd.stage.p, 3 * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return HG_OK;
+}
+
+int hg_get_state(hg_ctx* ctx, double* Q) {
+  if (!ctx || !Q) return HG_ERR_ARG;
+  if (!ctx->state_set) { ctx->err = "hg_get_state: no resident state (call hg_set_state first)"; return HG_ERR_STATE; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  return download3(ctx, ctx->opt.path == 1 ? ctx->pd.Q.p : ctx->fd.Q.p, Q);
+}
+
+int hg_rhs_resident(hg_ctx* ctx) {
+  if (!ctx) return HG_ERR_ARG;
+  if (!ctx->state_set) { ctx->err = "hg_rhs_resident: no resident state"; return HG_ERR_STATE; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  if (ctx->opt.path == 1) return hg::plain_rhs(ctx, ctx->pd.Q.p, ctx->pd.dQ.p);
+  return hg::fused_rhs(ctx, ctx->fd.Q.p, ctx->fd.dQ.p, false, 0.0);
+}
+
+int hg_get_rhs(hg_ctx* ctx, double* dQ) {
+  if (!ctx || !dQ) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  TRY(download3(ctx, ctx->opt.path == 1 ? ctx->pd.dQ.p : ctx->fd.dQ.p, dQ));
+  return check_err_flag(ctx);
+}
+
+int hg_rhs(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32_t active, double t, double* dQdt) {
+  (void)t;  // unused, exactly like the reference (semi_discretize_swe_2D.jl:18)
+  if (!ctx || !Q || !dQdt) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  TRY(bind_params(ctx, params, np, active));
+  TRY(hg_set_state(ctx, Q));
+  TRY(hg_rhs_resident(ctx));
+  return hg_get_rhs(ctx, dQdt);
+}
+
+int hg_rhs_vjp(hg_ctx* ctx, const double*, const double*, int64_t, int32_t, double, const double*, double*, double*, double*) {
+  if (!ctx) return HG_ERR_ARG;
+  ctx->err = "hg_rhs_vjp: not available in this build";
+  return HG_ERR_STATE;
+}
+
+int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
+  if (!ctx || nsteps < 0) return HG_ERR_ARG;
+  if (!ctx->state_set) { ctx->err = "hg_step_euler: no resident state"; return HG_ERR_STATE; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  if (ctx->opt.path == 1) { ctx->err = "hg_step_euler needs the fused path (path=0)"; return HG_ERR_ARG; }
+  hg::FusedDev& d = ctx->fd;
+  for (int64_t s = 0; s < nsteps; ++s) {
+    TRY(hg::fused_rhs(ctx, d.Q.p, d.Q2.p, true, dt));
+    std::swap(d.Q.p, d.Q2.p);
+  }
+  return HG_OK;
+}
+
+int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double t0,
+                        double t1, double dt, double* sol, int64_t cap, int64_t* n_saves) {
+  if (!ctx || !Q0 || !sol || !n_saves || !(dt > 0.0)) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  // length(t_start:dt:t_end), custom_ODE_solvers.jl:40
+  const int64_t nsteps = t1 < t0 ? 0 : (int64_t)std::floor((t1 - t0) / dt + 1e-9) + 1;
+  *n_saves = nsteps;
+  if (cap < nsteps) { ctx->err = "hg_custom_ode_solve: sol has room for " + std::to_string(cap) + " of " + std::to_string(nsteps) + " saves"; return HG_ERR_ARG; }
+  TRY(bind_params(ctx, params, np, active));
+  TRY(hg_set_state(ctx, Q0));
+  for (int64_t s = 0; s < nsteps; ++s) {
+    TRY(hg_step_euler(ctx, dt, 1));
+    TRY(hg_get_state(ctx, sol + s * 3 * ctx->N));  // save_freq = 1: every step is saved (:80-82)
+  }
+  return check_err_flag(ctx);
+}
+
+int hg_time_rhs(hg_ctx* ctx, int32_t n, int32_t fused_euler, double dt, float* ms) {
+  if (!ctx || !ms || n <= 0) return HG_ERR_ARG;
+  if (!ctx->state_set) { ctx->err = "hg_time_rhs: no resident state"; return HG_ERR_STATE; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int i = 0; i < n; ++i) {
+    if (fused_euler) TRY(hg_step_euler(ctx, dt, 1));
+    else TRY(hg_rhs_resident(ctx));
+  }
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return check_err_flag(ctx);
+}
+
+int hg_time_vjp(hg_ctx* ctx, int32_t, float*) {
+  if (!ctx) return HG_ERR_ARG;
+  ctx->err = "hg_time_vjp: not available in this build";
+  return HG_ERR_STATE;
+}
+
+int hg_mesh_stats(const hg_ctx* ctx, int64_t* nc, int64_t* nf, int64_t* snf, int64_t* nt, int64_t* bytes) {
+  if (!ctx) return HG_ERR_ARG;
+  if (nc) *nc = ctx->N;
+  if (nf) *nf = ctx->F;
+  if (snf) *snf = ctx->sumnf;
+  if (nt) *nt = ctx->fh.n_tiles;
+  if (bytes) *bytes = ctx->device_bytes;
+  return HG_OK;
+}
+
+int hg_plan_stats(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, const hg_options* opt,
+                  int64_t* stats, int64_t* perm_out) {
+  if (!stats) return HG_ERR_ARG;
+  std::unique_ptr<hg_ctx> ctx(new hg_ctx());
+  if (opt) ctx->opt = *opt; else hg_default_options(&ctx->opt);
+  std::vector<int32_t> cf_ptr, cf_nb, cf_face;
+  std::vector<double> cf_nx, cf_ny, cf_len;
+  int rc = hg::build_host(ctx.get(), m, b, f, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
+  if (rc == HG_OK) rc = hg::build_tiles(ctx.get(), m, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
+  if (rc != HG_OK) { set_global_err(ctx->err); return rc; }
+  const hg::FusedHost& fh = ctx->fh;
+  int64_t nint = 0;
+  for (int32_t v : fh.face_nint) nint += v;
+  stats[0] = fh.n_tiles; stats[1] = fh.max_local; stats[2] = fh.max_faces; stats[3] = hg::fused_smem_bytes(ctx.get());
+  stats[4] = (int64_t)fh.halo.size(); stats[5] = (int64_t)fh.face_lr.size(); stats[6] = nint; stats[7] = ctx->sumnf;
+  if (perm_out) for (int64_t i = 0; i < ctx->N; ++i) perm_out[i] = fh.perm[i];
+  return HG_OK;
+}
+
+int hg_flush_l2(hg_ctx* ctx) {
+  if (!ctx) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  if (!ctx->flush_buf) {
+    ctx->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+    CK(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+  }
+  CK(ctx, cudaMemsetAsync(ctx->flush_buf, 1, ctx->flush_bytes, ctx->stream));
+  return HG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+// Internal definitions shared by the host-side builder and the CUDA translation units.
+// Nothing in here is part of the ABI (include/hydrograd_b200.h is).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/hydrograd_b200.h"
+
+namespace hg {
+
+constexpr double EPS = 2.220446049250313e-16;  // eps(Float64) of utilities/smooth_functions.jl
+
+enum BcType : int32_t { BC_INLETQ = 0, BC_EXITH = 1, BC_WALL = 2, BC_SYMM = 3 };
+
+// ---------------------------------------------------------------- device buffer (RAII)
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+  }
+  cudaError_t upload(const std::vector<T>& h, cudaStream_t s = nullptr) {
+    cudaError_t e = alloc(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    e = cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(s);
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---------------------------------------------------------------- constants passed by value to kernels
+struct Consts {
+  double g, k_n, h_small;
+};
+
+// Boundary entries, one per boundary face, in the reference's processing order
+// (inlet-q boundaries, exit-h, wall, symm; bc_2D.jl:279-295).  Cell ids are in REFERENCE order
+// for the plain path and in INTERNAL order for the fused path (two copies of `cell`).
+struct BcHost {
+  std::vector<int32_t> type, group, ghost, cell_ref;  // [B]
+  std::vector<double> nx, ny, l53, l23, hstill_g, zb_g;  // [B]; l53 = L^(5/3), l23 = L^(2/3) (inlet only)
+  std::vector<int32_t> inlet_ptr;                     // [n_inletq+1] entry ranges of each inlet boundary
+};
+
+// ---------------------------------------------------------------- plain (reference-order) path
+struct PlainDev {
+  DBuf<int32_t> cf_ptr, cf_nb;        // CSR of cell faces; nb >= N means ghost (N + ghost id)
+  DBuf<double> cf_nx, cf_ny, cf_len;  // per cell-face
+  DBuf<double> area, hstill, zb, S0x, S0y, mann;  // [N] reference order
+  DBuf<int32_t> matid;                // [N]
+  DBuf<int32_t> bc_type, bc_group, bc_ghost, bc_cell;  // [B] entry order
+  DBuf<double> bc_nx, bc_ny, bc_l53, bc_l23;
+  DBuf<int32_t> inlet_ptr;
+  DBuf<double> hstill_g, zb_g;        // [B] GHOST order (as passed in)
+  DBuf<double> gh, gqx, gqy, gxi;     // [B] ghost states, ghost order
+  DBuf<double> Qin, wse;              // [n_inletq], [n_exith]
+  DBuf<double> Q, dQ, params;         // [3N], [3N], [np]
+  DBuf<int32_t> err;                  // device error flag
+};
+
+// ---------------------------------------------------------------- fused (tile) path
+// Tile t owns internal cells [tile_cell0[t], tile_cell0[t+1]).  Its local cell index space is
+// owned cells first, then halo cells (neighbours owned by another tile).  Faces touching an owned
+// cell are listed once per tile: interior faces (both sides real cells) then boundary faces.
+struct FusedHost {
+  int32_t n_tiles = 0, max_local = 0, max_faces = 0, max_cells = 0;
+  std::vector<int32_t> perm;         // internal -> reference cell id
+  std::vector<int32_t> iperm;        // reference -> internal
+  std::vector<int32_t> tile_cell0;   // [n_tiles+1]
+  std::vector<int32_t> halo_ptr;     // [n_tiles+1]
+  std::vector<int32_t> halo;         // internal ids of halo cells
+  std::vector<int32_t> face_ptr;     // [n_tiles+1]   tile faces (interior then boundary)
+  std::vector<int32_t> face_nint;    // [n_tiles]     number of interior faces
+  std::vector<uint32_t> face_lr;     // lL | lR<<16 (interior) ; lL | 0xFFFF<<16 (boundary)
+  std::vector<int32_t> face_bce;     // per tile face: boundary entry index or -1 (only read for boundary faces)
+  std::vector<double> face_nx, face_ny, face_len;
+  std::vector<int32_t> cf_ptr;       // [N+1] global CSR (internal order) into cf_idx
+  std::vector<uint16_t> cf_idx;      // local face id | 0x8000 when the cell is on the R side
+};
+
+struct FusedDev {
+  DBuf<int32_t> perm, iperm, tile_cell0, halo_ptr, halo, face_ptr, face_nint, face_bce, cf_ptr;
+  DBuf<uint32_t> face_lr;
+  DBuf<uint16_t> cf_idx;
+  DBuf<double> face_nx, face_ny, face_len;
+  DBuf<double> area, hstill, zb, S0x, S0y, mann;  // [N] internal order
+  DBuf<int32_t> matid;
+  DBuf<int32_t> bc_type, bc_group, bc_cell;        // [B] entry order, internal cell ids
+  DBuf<double> bc_nx, bc_ny, bc_l53, bc_l23, bc_hstill, bc_zb;
+  DBuf<int32_t> inlet_ptr;
+  DBuf<double> inlet_coef;                         // [n_inletq]  Q_k / total_A
+  DBuf<double> Qin, wse;
+  DBuf<double> Q, Q2, dQ, lam, Qbar, stage, params, pbar, nbar, zbar;
+  DBuf<int32_t> err;
+};
+
+// host copies of the bindable frozen fields (so that un-binding a parameter restores them)
+struct Frozen {
+  std::vector<double> mann_ref, zb_ref, zbg_ghost, S0_ref, Qin, wse;
+};
+
+}  // namespace hg
+
+struct hg_ctx {
+  hg_options opt{};
+  int64_t N = 0, F = 0, B = 0, sumnf = 0;
+  int64_t n_inletq = 0, n_exith = 0, n_wall = 0, n_symm = 0, n_mat = 0;
+  hg::Consts c{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  bool state_set = false;
+  int32_t active = HG_PARAM_NONE;
+  int64_t n_params = 0;
+  hg::BcHost bch;
+  hg::PlainDev pd;
+  hg::FusedHost fh;
+  hg::FusedDev fd;
+  double* h_pinned = nullptr;  // staging [6N] pinned host memory
+  size_t h_pinned_bytes = 0;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  int64_t device_bytes = 0;
+  hg::Frozen fr;
+  std::vector<double> last_params;
+  int32_t last_active = -1;
+  std::vector<int32_t> matid_ref;
+};
+
+namespace hg {
+// host-side builder (hg_host.cpp)
+int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f,
+               std::vector<int32_t>& cf_ptr, std::vector<int32_t>& cf_nb, std::vector<double>& cf_nx,
+               std::vector<double>& cf_ny, std::vector<double>& cf_len, std::vector<int32_t>& cf_face);
+int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& cf_ptr,
+                const std::vector<int32_t>& cf_nb, const std::vector<double>& cf_nx, const std::vector<double>& cf_ny,
+                const std::vector<double>& cf_len, const std::vector<int32_t>& cf_face);
+
+// plain path launchers (hg_plain.cu)
+int plain_rhs(hg_ctx* ctx, const double* dQ_in_Q, double* d_out);
+// fused path launchers (hg_fused.cu)
+int fused_rhs(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
+int fused_smem_bytes(const hg_ctx* ctx);
+int fused_prepare(hg_ctx* ctx);
+int fused_permute(hg_ctx* ctx, const int32_t* map, const double* src, double* dst);
+int fused_bind_manning(hg_ctx* ctx, const double* d_params);
+int fused_bind_zb(hg_ctx* ctx, const double* d_params_ref);
+}  // namespace hg

@@ -1,0 +1,267 @@
+// Host-side builder: turns the reference-shaped flat tables of the ABI (mesh_2D / BoundaryConditions2D
+// fields, include/hydrograd_b200.h) into the internal layouts:
+//   * a compact cell->face CSR in reference order (plain path), and
+//   * a locality-ordered, tiled, face-once layout (fused path): cells renumbered by recursive
+//     coordinate bisection so that each CTA tile is a compact patch, per-tile halo lists, per-tile
+//     face lists with 16-bit local indices, per-cell local CSR with an orientation bit.
+// This replaces the per-call Dict / Vector-of-Vector lookups of compute_inviscid_fluxes
+// (semi_discretize_swe_2D.jl:286-330) with one O(N log N) preprocessing step at hg_create.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "hg_ctx.h"
+
+namespace hg {
+
+#define HG_FAIL(ctx, code, ...)                       \
+  do {                                                \
+    char _b[512];                                     \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);            \
+    (ctx)->err = _b;                                  \
+    return (code);                                    \
+  } while (0)
+
+int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f,
+               std::vector<int32_t>& cf_ptr, std::vector<int32_t>& cf_nb, std::vector<double>& cf_nx,
+               std::vector<double>& cf_ny, std::vector<double>& cf_len, std::vector<int32_t>& cf_face) {
+  if (!m || !b || !f) HG_FAIL(ctx, HG_ERR_ARG, "null descriptor");
+  const int64_t N = m->n_cells, F = m->n_faces, B = m->n_ghost, ld = m->ld, base = m->index_base;
+  if (N <= 0 || F <= 0 || B < 0 || ld <= 0) HG_FAIL(ctx, HG_ERR_ARG, "bad sizes N=%ld F=%ld B=%ld ld=%ld", (long)N, (long)F, (long)B, (long)ld);
+  if (N + B >= (int64_t)1 << 31) HG_FAIL(ctx, HG_ERR_ARG, "mesh too large for 32-bit cell ids");
+  if (base != 0 && base != 1) HG_FAIL(ctx, HG_ERR_ARG, "index_base must be 0 or 1");
+  if (!m->cell_nfaces || !m->cell_faces || !m->cell_neighbors || !m->cell_normals || !m->face_is_boundary ||
+      !m->face_lengths || !m->cell_areas)
+    HG_FAIL(ctx, HG_ERR_ARG, "null mesh array");
+  if (!f->hstill || !f->zb_cells || !f->S0_cells || !f->ManningN_cells || (B > 0 && (!f->hstill_ghost || !f->zb_ghost)))
+    HG_FAIL(ctx, HG_ERR_ARG, "null field array");
+  if (f->riemann_solver && std::strcmp(f->riemann_solver, "Roe") != 0) {
+    // semi_discretize_swe_2D.jl:356-361
+    if (!std::strcmp(f->riemann_solver, "HLL") || !std::strcmp(f->riemann_solver, "HLLC"))
+      HG_FAIL(ctx, HG_ERR_SOLVER, "%s solver not implemented yet", f->riemann_solver);
+    HG_FAIL(ctx, HG_ERR_SOLVER, "Wrong choice of RiemannSolver");
+  }
+  ctx->N = N; ctx->F = F; ctx->B = B;
+  ctx->c = {f->g, f->k_n, f->h_small};
+  ctx->n_inletq = b->n_inletq; ctx->n_exith = b->n_exith; ctx->n_wall = b->n_wall; ctx->n_symm = b->n_symm;
+  ctx->n_mat = f->n_mat;
+  const int64_t nbc = b->n_inletq + b->n_exith + b->n_wall + b->n_symm;
+  if (b->n_inletq < 0 || b->n_exith < 0 || b->n_wall < 0 || b->n_symm < 0) HG_FAIL(ctx, HG_ERR_ARG, "negative boundary count");
+  if (B > 0 && (!b->bc_ptr || !b->ghost_ids || !b->internal_cells || !b->outward_normals))
+    HG_FAIL(ctx, HG_ERR_ARG, "null boundary array");
+  if (b->n_inletq > 0 && (!b->face_lengths || !f->inletQ_TotalQ)) HG_FAIL(ctx, HG_ERR_ARG, "inlet-q data missing");
+  if (b->n_exith > 0 && !f->exitH_WSE) HG_FAIL(ctx, HG_ERR_ARG, "exit-h data missing");
+
+  // ---- cell -> face CSR in reference order
+  cf_ptr.assign(N + 1, 0);
+  for (int64_t i = 0; i < N; ++i) {
+    int64_t nf = m->cell_nfaces[i];
+    if (nf < 1 || nf > ld) HG_FAIL(ctx, HG_ERR_ARG, "cell %ld has %ld faces (ld=%ld)", (long)i, (long)nf, (long)ld);
+    cf_ptr[i + 1] = cf_ptr[i] + (int32_t)nf;
+  }
+  const int64_t S = cf_ptr[N];
+  ctx->sumnf = S;
+  cf_nb.resize(S); cf_nx.resize(S); cf_ny.resize(S); cf_len.resize(S); cf_face.resize(S);
+  for (int64_t i = 0; i < N; ++i) {
+    for (int64_t j = 0; j < cf_ptr[i + 1] - cf_ptr[i]; ++j) {
+      int64_t fv = m->cell_faces[i + N * j];
+      int64_t fid = (fv < 0 ? -fv : fv) - base;
+      if (fid < 0 || fid >= F) HG_FAIL(ctx, HG_ERR_ARG, "cell %ld face %ld: face id out of range", (long)i, (long)j);
+      int64_t nb = m->cell_neighbors[i + N * j] - base;
+      int64_t k = cf_ptr[i] + j;
+      if (m->face_is_boundary[fid]) {
+        if (nb < 0 || nb >= B) HG_FAIL(ctx, HG_ERR_ARG, "cell %ld face %ld: ghost id out of range", (long)i, (long)j);
+        cf_nb[k] = (int32_t)(N + nb);
+      } else {
+        if (nb < 0 || nb >= N || nb == i) HG_FAIL(ctx, HG_ERR_ARG, "cell %ld face %ld: neighbour id out of range", (long)i, (long)j);
+        cf_nb[k] = (int32_t)nb;
+      }
+      cf_nx[k] = m->cell_normals[i + N * (j + ld * 0)];
+      cf_ny[k] = m->cell_normals[i + N * (j + ld * 1)];
+      cf_len[k] = m->face_lengths[fid];
+      cf_face[k] = (int32_t)fid;
+    }
+  }
+
+  // ---- boundary entries in processing order
+  BcHost& h = ctx->bch;
+  h = BcHost();
+  if (nbc > 0 && b->bc_ptr[0] != 0) HG_FAIL(ctx, HG_ERR_ARG, "bc_ptr[0] must be 0");
+  if ((nbc > 0 ? b->bc_ptr[nbc] : 0) != B) HG_FAIL(ctx, HG_ERR_ARG, "boundary entries (%ld) do not cover the %ld ghost cells", (long)(nbc > 0 ? b->bc_ptr[nbc] : 0), (long)B);
+  h.type.resize(B); h.group.resize(B); h.ghost.resize(B); h.cell_ref.resize(B);
+  h.nx.resize(B); h.ny.resize(B); h.l53.assign(B, 0.0); h.l23.assign(B, 0.0); h.hstill_g.resize(B); h.zb_g.resize(B);
+  h.inlet_ptr.assign(1, 0);
+  std::vector<char> seen(B, 0);
+  int64_t kb = 0;
+  const int64_t counts[4] = {b->n_inletq, b->n_exith, b->n_wall, b->n_symm};
+  for (int t = 0; t < 4; ++t) {
+    for (int64_t kk = 0; kk < counts[t]; ++kk, ++kb) {
+      if (b->bc_ptr[kb + 1] < b->bc_ptr[kb]) HG_FAIL(ctx, HG_ERR_ARG, "bc_ptr not monotone");
+      for (int64_t e = b->bc_ptr[kb]; e < b->bc_ptr[kb + 1]; ++e) {
+        int64_t gi = b->ghost_ids[e] - base, c = b->internal_cells[e] - base;
+        if (gi < 0 || gi >= B || seen[gi]) HG_FAIL(ctx, HG_ERR_ARG, "boundary entry %ld: bad or repeated ghost id", (long)e);
+        if (c < 0 || c >= N) HG_FAIL(ctx, HG_ERR_ARG, "boundary entry %ld: bad internal cell", (long)e);
+        seen[gi] = 1;
+        h.type[e] = t; h.group[e] = (int32_t)kk; h.ghost[e] = (int32_t)gi; h.cell_ref[e] = (int32_t)c;
+        h.nx[e] = b->outward_normals[e]; h.ny[e] = b->outward_normals[B + e];
+        h.hstill_g[e] = f->hstill_ghost[gi]; h.zb_g[e] = f->zb_ghost[gi];
+        if (t == BC_INLETQ) {
+          double L = b->face_lengths[e];
+          h.l53[e] = std::pow(L, 5.0 / 3.0);  // bc_2D.jl:674
+          h.l23[e] = std::pow(L, 2.0 / 3.0);  // bc_2D.jl:691
+        }
+      }
+      if (t == BC_INLETQ) h.inlet_ptr.push_back((int32_t)b->bc_ptr[kb + 1]);
+    }
+  }
+  // consistency: the ghost of entry e must be the neighbour of its internal cell
+  for (int64_t e = 0; e < B; ++e) {
+    int32_t c = h.cell_ref[e];
+    bool ok = false;
+    for (int32_t k = cf_ptr[c]; k < cf_ptr[c + 1]; ++k) ok |= (cf_nb[k] == (int32_t)(N + h.ghost[e]));
+    if (!ok) HG_FAIL(ctx, HG_ERR_ARG, "boundary entry %ld: ghost %d is not a neighbour of cell %d", (long)e, h.ghost[e], c);
+  }
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Rcb {
+  const double* cx;
+  const double* cy;
+  int32_t T;
+  std::vector<int32_t>& idx;
+  std::vector<int32_t>& tile0;
+  void run(int64_t lo, int64_t hi) {
+    const int64_t n = hi - lo;
+    if (n <= T) {
+      std::sort(idx.begin() + lo, idx.begin() + hi);
+      tile0.push_back((int32_t)lo);
+      return;
+    }
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int64_t i = lo; i < hi; ++i) {
+      double x = cx[idx[i]], y = cy[idx[i]];
+      x0 = std::min(x0, x); x1 = std::max(x1, x); y0 = std::min(y0, y); y1 = std::max(y1, y);
+    }
+    const int64_t k = (n + T - 1) / T;       // leaves below this node
+    const int64_t mid = lo + (k / 2) * (int64_t)T;  // all leaves but the last are exactly T cells
+    const double* key = (x1 - x0 >= y1 - y0) ? cx : cy;
+    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [key](int32_t a, int32_t b) {
+      return key[a] < key[b] || (key[a] == key[b] && a < b);
+    });
+    run(lo, mid);
+    run(mid, hi);
+  }
+};
+}  // namespace
+
+int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& cf_ptr,
+                const std::vector<int32_t>& cf_nb, const std::vector<double>& cf_nx, const std::vector<double>& cf_ny,
+                const std::vector<double>& cf_len, const std::vector<int32_t>& cf_face) {
+  const int64_t N = ctx->N, F = ctx->F, B = ctx->B;
+  FusedHost& fh = ctx->fh;
+  fh = FusedHost();
+  int32_t T = ctx->opt.tile_cells > 0 ? ctx->opt.tile_cells : 512;
+  if (T < 32 || T > 4096) HG_FAIL(ctx, HG_ERR_ARG, "tile_cells must be in [32, 4096]");
+
+  // ---- ordering + tiles
+  fh.perm.resize(N);
+  std::iota(fh.perm.begin(), fh.perm.end(), 0);
+  if (ctx->opt.reorder && m->cell_centroids) {
+    Rcb r{m->cell_centroids, m->cell_centroids + N, T, fh.perm, fh.tile_cell0};
+    r.run(0, N);
+  } else {
+    for (int64_t c = 0; c < N; c += T) fh.tile_cell0.push_back((int32_t)c);
+  }
+  fh.tile_cell0.push_back((int32_t)N);
+  fh.n_tiles = (int32_t)fh.tile_cell0.size() - 1;
+  fh.iperm.resize(N);
+  for (int64_t i = 0; i < N; ++i) fh.iperm[fh.perm[i]] = (int32_t)i;
+
+  // ghost id -> boundary entry
+  std::vector<int32_t> ghost_entry(B);
+  for (int64_t e = 0; e < B; ++e) ghost_entry[ctx->bch.ghost[e]] = (int32_t)e;
+
+  // ---- per-tile structures
+  std::vector<int32_t> stamp(N, -1), loc(N, 0), fstamp(F, -1), floc(F, 0);
+  fh.halo_ptr.assign(1, 0);
+  fh.face_ptr.assign(1, 0);
+  fh.cf_ptr.assign(N + 1, 0);
+  for (int64_t i = 0; i < N; ++i) fh.cf_ptr[i + 1] = fh.cf_ptr[i] + (cf_ptr[fh.perm[i] + 1] - cf_ptr[fh.perm[i]]);
+  fh.cf_idx.resize(fh.cf_ptr[N]);
+  fh.halo.reserve(N / 4);
+  fh.face_lr.reserve(ctx->sumnf / 2 + ctx->sumnf / 8);
+
+  for (int32_t t = 0; t < fh.n_tiles; ++t) {
+    const int32_t c0 = fh.tile_cell0[t], c1 = fh.tile_cell0[t + 1], nc = c1 - c0;
+    int32_t nloc = nc;
+    for (int32_t c = c0; c < c1; ++c) { stamp[c] = t; loc[c] = c - c0; }
+    const size_t face_base = fh.face_lr.size();
+    // pass A: interior faces, created by the first owned cell (in internal order) that sees them
+    for (int32_t c = c0; c < c1; ++c) {
+      const int32_t r = fh.perm[c];
+      for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
+        if (cf_nb[k] >= N) continue;
+        const int32_t fid = cf_face[k];
+        if (fstamp[fid] == t) continue;  // already created from the other owned side
+        const int32_t rn = cf_nb[k], cn = fh.iperm[rn];
+        if (stamp[cn] != t) {            // halo cell: give it a local index
+          stamp[cn] = t; loc[cn] = nloc++;
+          fh.halo.push_back(cn);
+        }
+        // canonical orientation: L = smaller REFERENCE id, normal taken from the L cell's own table
+        int32_t lL, lR; double nx, ny;
+        if (r < rn) {
+          lL = loc[c]; lR = loc[cn]; nx = cf_nx[k]; ny = cf_ny[k];
+        } else {
+          lL = loc[cn]; lR = loc[c];
+          int32_t kk = -1;
+          for (int32_t q = cf_ptr[rn]; q < cf_ptr[rn + 1]; ++q) if (cf_face[q] == fid) { kk = q; break; }
+          if (kk < 0 || cf_nb[kk] != r) HG_FAIL(ctx, HG_ERR_ARG, "face %d: cells %d and %d disagree on adjacency", fid, r, rn);
+          nx = cf_nx[kk]; ny = cf_ny[kk];
+        }
+        fstamp[fid] = t; floc[fid] = (int32_t)(fh.face_lr.size() - face_base);
+        fh.face_lr.push_back((uint32_t)lL | ((uint32_t)lR << 16));
+        fh.face_bce.push_back(-1);
+        fh.face_nx.push_back(nx); fh.face_ny.push_back(ny); fh.face_len.push_back(cf_len[k]);
+      }
+    }
+    const int32_t nint = (int32_t)(fh.face_lr.size() - face_base);
+    // pass B: boundary faces (ghost state is evaluated on the fly from the owned internal cell)
+    for (int32_t c = c0; c < c1; ++c) {
+      const int32_t r = fh.perm[c];
+      for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
+        if (cf_nb[k] < N) continue;
+        const int32_t fid = cf_face[k];
+        fstamp[fid] = t; floc[fid] = (int32_t)(fh.face_lr.size() - face_base);
+        fh.face_lr.push_back((uint32_t)loc[c] | (0xFFFFu << 16));
+        fh.face_bce.push_back(ghost_entry[cf_nb[k] - N]);
+        fh.face_nx.push_back(cf_nx[k]); fh.face_ny.push_back(cf_ny[k]); fh.face_len.push_back(cf_len[k]);
+      }
+    }
+    const int32_t nf = (int32_t)(fh.face_lr.size() - face_base);
+    if (nloc >= 0xFFFF || nf >= 0x8000) HG_FAIL(ctx, HG_ERR_ARG, "tile %d too large (local cells %d, faces %d)", t, nloc, nf);
+    // pass C: per-cell local CSR in the reference's face order, with the side bit
+    for (int32_t c = c0; c < c1; ++c) {
+      const int32_t r = fh.perm[c];
+      int32_t o = fh.cf_ptr[c];
+      for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k, ++o) {
+        const int32_t lf = floc[cf_face[k]];
+        const uint32_t lr = fh.face_lr[face_base + lf];
+        const bool on_right = (cf_nb[k] < N) && ((int32_t)(lr >> 16) == loc[c]);
+        fh.cf_idx[o] = (uint16_t)(lf | (on_right ? 0x8000 : 0));
+      }
+    }
+    fh.halo_ptr.push_back((int32_t)fh.halo.size());
+    fh.face_ptr.push_back((int32_t)fh.face_lr.size());
+    fh.face_nint.push_back(nint);
+    fh.max_local = std::max(fh.max_local, nloc);
+    fh.max_faces = std::max(fh.max_faces, nf);
+    fh.max_cells = std::max(fh.max_cells, nc);
+  }
+  return HG_OK;
+}
+
+}  // namespace hg

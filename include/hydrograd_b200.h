@@ -32,6 +32,12 @@ extern "C" {
 
 #define HG_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define HG_API __attribute__((visibility("default")))
+#else
+#define HG_API
+#endif
+
 typedef struct hg_ctx hg_ctx;
 
 /* active_param_name of SWE2D_Extra_Parameters (src/applications/application_commons.jl:9):
@@ -116,67 +122,73 @@ typedef struct {
 } hg_options;
 
 /* fills *opt with the defaults */
-void hg_default_options(hg_options* opt);
+HG_API void hg_default_options(hg_options* opt);
 
-int hg_abi_version(void);
+HG_API int hg_abi_version(void);
 
 /* Build a context (device copies of the mesh in the internal face/tile layout).  Replaces the
  * per-call unpacking of p_extra at semi_discretize_swe_2D.jl:26-67.                              */
-int hg_create(hg_ctx** out, const hg_mesh_desc* mesh, const hg_bc_desc* bc,
+HG_API int hg_create(hg_ctx** out, const hg_mesh_desc* mesh, const hg_bc_desc* bc,
               const hg_fields_desc* fields, const hg_options* opt);
-void hg_destroy(hg_ctx* ctx);
-const char* hg_last_error(const hg_ctx* ctx);
+HG_API void hg_destroy(hg_ctx* ctx);
+HG_API const char* hg_last_error(const hg_ctx* ctx);
 
-int64_t hg_n_cells(const hg_ctx* ctx);
+HG_API int64_t hg_n_cells(const hg_ctx* ctx);
 
 /* Replace frozen fields after creation (setup_* in solve_swe_2D.jl:148-221); NULL = keep.        */
-int hg_set_fields(hg_ctx* ctx, const double* ManningN_cells, const double* zb_cells,
+HG_API int hg_set_fields(hg_ctx* ctx, const double* ManningN_cells, const double* zb_cells,
                   const double* zb_ghost, const double* S0_cells, const double* inletQ_TotalQ,
                   const double* exitH_WSE);
 
 /* dQdt = swe_2d_rhs(Q, params, t)   -- host buffers, reference cell order.
  * semi_discretize_swe_2D.jl:18-277.  `t` is accepted and unused exactly like the reference.      */
-int hg_rhs(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params,
+HG_API int hg_rhs(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params,
            int32_t active_param, double t, double* dQdt);
 
 /* Vector-Jacobian product of the same call: Qbar = (d rhs/dQ)^T lambda  [3N],
  * pbar = (d rhs/dparams)^T lambda  [n_params] (NULL allowed when active_param = NONE),
  * ncell_bar (optional, may be NULL) = d(lambda . rhs)/d ManningN_cells  [N]  (UDE hook).
  * Replaces Zygote.pullback on swe_2d_rhs (debug_AD.jl:60,75; swe_2D_inversion.jl:339).           */
-int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params,
+HG_API int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params,
                int32_t active_param, double t, const double* lambda, double* Qbar, double* pbar,
                double* ncell_bar);
 
 /* ---- device-resident state (no host round trip per stage) ---------------------------------- */
-int hg_set_state(hg_ctx* ctx, const double* Q);          /* host [3N] -> device                  */
-int hg_get_state(hg_ctx* ctx, double* Q);                /* device -> host [3N]                  */
-int hg_set_params(hg_ctx* ctx, const double* params, int64_t n_params, int32_t active_param);
+HG_API int hg_set_state(hg_ctx* ctx, const double* Q);          /* host [3N] -> device                  */
+HG_API int hg_get_state(hg_ctx* ctx, double* Q);                /* device -> host [3N]                  */
+HG_API int hg_set_params(hg_ctx* ctx, const double* params, int64_t n_params, int32_t active_param);
 /* dQdt of the resident state into a resident buffer; hg_get_rhs copies it out.  Asynchronous on
  * the ctx stream; hg_sync waits.                                                                 */
-int hg_rhs_resident(hg_ctx* ctx);
-int hg_get_rhs(hg_ctx* ctx, double* dQdt);
-int hg_sync(hg_ctx* ctx);
+HG_API int hg_rhs_resident(hg_ctx* ctx);
+HG_API int hg_get_rhs(hg_ctx* ctx, double* dQdt);
+HG_API int hg_sync(hg_ctx* ctx);
 
 /* nsteps of custom_ODE_update_cells (custom_ODE_solvers.jl:5-33) on the resident state:
  * Q+ = Q + dt*rhs(Q); where xi+ < h_small: xi+ = h_small, q+ = 0 (the reference's mask is on xi).
  * Fused into the RHS kernel (one launch per step, captured in a CUDA graph).                      */
-int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps);
+HG_API int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps);
 
 /* custom_ODE_solve (custom_ODE_solvers.jl:36-95): steps over t_start:dt:t_end, saving every
  * state; sol is [3N x n_saves] column-major, n_saves_capacity columns available; *n_saves out.   */
-int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params,
+HG_API int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params,
                         int32_t active_param, double t_start, double t_end, double dt, double* sol,
                         int64_t n_saves_capacity, int64_t* n_saves);
 
 /* ---- timing hooks used by bench.py (device time of the last N launches, CUDA events on the
  * ctx stream) and introspection for the roofline arithmetic.                                     */
-int hg_time_rhs(hg_ctx* ctx, int32_t n_launches, int32_t fused_euler, double dt, float* ms_total);
-int hg_time_vjp(hg_ctx* ctx, int32_t n_launches, float* ms_total);
-int64_t hg_kernel_launches(const hg_ctx* ctx);            /* kernels launched so far             */
-int hg_mesh_stats(const hg_ctx* ctx, int64_t* n_cells, int64_t* n_faces, int64_t* sum_cell_faces,
+HG_API int hg_time_rhs(hg_ctx* ctx, int32_t n_launches, int32_t fused_euler, double dt, float* ms_total);
+HG_API int hg_time_vjp(hg_ctx* ctx, int32_t n_launches, float* ms_total);
+HG_API int64_t hg_kernel_launches(const hg_ctx* ctx);            /* kernels launched so far             */
+HG_API int hg_mesh_stats(const hg_ctx* ctx, int64_t* n_cells, int64_t* n_faces, int64_t* sum_cell_faces,
                   int64_t* n_tiles, int64_t* device_bytes);
-/* write `bytes` bytes of device scratch (L2 flush between timed iterations)                      */
-int hg_flush_l2(hg_ctx* ctx);
+/* Host-only: run the hg_create preprocessing (validation, renumbering, tiling) WITHOUT touching a GPU
+ * and report the plan: stats[0..7] = n_tiles, max local cells, max tile faces, shared-memory bytes per
+ * CTA, total halo cells, total tile faces, interior tile faces, sum of cell faces.  perm_out (optional,
+ * [N]) receives the internal->reference cell permutation.                                          */
+HG_API int hg_plan_stats(const hg_mesh_desc* mesh, const hg_bc_desc* bc, const hg_fields_desc* fields,
+                  const hg_options* opt, int64_t* stats, int64_t* perm_out);
+/* write 256 MiB of device scratch (L2 flush between timed iterations)                             */
+HG_API int hg_flush_l2(hg_ctx* ctx);
 
 #ifdef __cplusplus
 }

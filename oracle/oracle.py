@@ -98,6 +98,7 @@ class Oracle:
         p, npar = self._params(params)
         out = np.empty(3 * self.N)
         gh = np.empty(4 * self.B) if ghosts else None
+        nthreads = nthreads or self.max_threads()      # 0 = every host core ("ref-generous")
         rc = self.lib.oracle_rhs(*self._args(), _p(Q, c_f64p), _p(p, c_f64p), C.c_int64(npar), C.c_int(active),
                                  _p(out, c_f64p), C.c_int(nthreads), _p(gh, c_f64p))
         if rc:
@@ -132,6 +133,7 @@ class Oracle:
     def euler(self, Q, dt, nsteps, params=None, active=0, nthreads=1):
         Q = np.array(Q, dtype=np.float64, copy=True)
         p, npar = self._params(params)
+        nthreads = nthreads or self.max_threads()
         rc = self.lib.oracle_euler(*self._args(), _p(Q, c_f64p), _p(p, c_f64p), C.c_int64(npar), C.c_int(active),
                                    C.c_double(dt), C.c_int64(nsteps), C.c_int(nthreads))
         if rc:

@@ -66,3 +66,34 @@ def flux_scale(case, Q):
     c = np.sqrt(case.g * h)
     s = (0.5 * case.g * h * h + h * u2 + h * np.sqrt(u2) * c + c * h) * per / case.mesh.cell_areas
     return np.concatenate([s, s, s]) + 1e-300
+
+
+def flat_scale(flat, Q):
+    """Same denominator as flux_scale, from the flat ABI tables (works for synthetic meshes too)."""
+    N, ld = int(flat["n_cells"]), int(flat["ld"])
+    base = int(flat["index_base"])
+    faces = np.abs(np.asarray(flat["cell_faces"]).reshape(ld, N)) - base
+    valid = np.arange(ld)[:, None] < np.asarray(flat["cell_nfaces"])[None, :]
+    per = (np.asarray(flat["face_lengths"])[np.where(valid, faces, 0)] * valid).sum(0)
+    hs, g = flat["h_small"], flat["g"]
+    h = np.maximum(Q[:N] + flat["hstill"], hs)
+    u2 = (Q[N:2 * N] ** 2 + Q[2 * N:] ** 2) / h ** 2
+    c = np.sqrt(g * h)
+    s = (0.5 * g * h * h + h * u2 + h * np.sqrt(u2) * c + c * h) * per / np.asarray(flat["cell_areas"])
+    # a cell also feels its neighbours' pressure: use the max over the cell and its face neighbours
+    nb = np.asarray(flat["cell_neighbors"]).reshape(ld, N) - base
+    isb = np.asarray(flat["face_is_boundary"])[np.where(valid, faces, 0)].astype(bool)
+    nbs = np.where(valid & ~isb, s[np.where(valid & ~isb, nb, 0)], 0.0).max(0)
+    s = np.maximum(s, nbs)
+    return np.concatenate([s, s, s]) + 1e-300
+
+
+def random_state_flat(flat, seed, dry_frac=0.05):
+    rng = np.random.default_rng(seed)
+    N = int(flat["n_cells"])
+    h = np.exp(rng.uniform(np.log(1e-4), np.log(10.0), N))
+    k = rng.random(N) < dry_frac
+    h[k] = rng.choice([5e-4, 1e-3, 9.999e-4], size=int(k.sum()))
+    sp = rng.uniform(0, 3, N)
+    th = rng.uniform(0, 2 * np.pi, N)
+    return np.concatenate([h - flat["hstill"], h * sp * np.cos(th), h * sp * np.sin(th)])
