@@ -1,0 +1,184 @@
+# HydrogradB200.jl -- thin Julia shim over libhydrograd_b200.so (include/hydrograd_b200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: neither the build container nor the GPU boxes have a `julia`
+# binary (SURVEY.md, environment table).  The file is the reference-side binding a Hydrograd.jl
+# maintainer would add; the same ABI is exercised end to end from Python (hydrograd.jl_b200/api.py,
+# tests/test_gpu_parity.py).  Everything below only flattens Hydrograd.jl's own structs and forwards
+# pointers -- no arithmetic happens on the Julia side.
+#
+# Drop-in usage (src/applications/solve_swe_2D.jl:281-307): replace the two closures by
+#
+#     b200 = HydrogradB200.Context(swe_extra_params)           # once, after SWE2D_Extra_Parameters is built
+#     ode_f = ODEFunction((u, p, t)      -> HydrogradB200.swe_2d_rhs(similar(u), u, p, t, b200);  jac_prototype = nothing)
+#     ode_f = ODEFunction((du, u, p, t)  -> HydrogradB200.swe_2d_rhs(du, u, p, t, b200))        # bInPlaceODE
+#
+# `swe_2d_rhs` keeps the reference signature (semi_discretize_swe_2D.jl:18-19) with the context in
+# place of p_extra.  The ChainRulesCore.rrule below makes Zygote / ZygoteVJP-based SciMLSensitivity
+# adjoints use the hand-written CUDA VJP (hg_rhs_vjp) instead of differentiating through the RHS.
+# Forward-mode callers (ForwardDiff.Dual state, e.g. ForwardDiffSensitivity) cannot be served by a
+# Float64 kernel: `swe_2d_rhs` has no method for Dual and the driver must pick an adjoint sensealg
+# such as InterpolatingAdjoint(autojacvec=ZygoteVJP()).
+module HydrogradB200
+
+using ChainRulesCore
+
+const LIB = get(ENV, "HYDROGRAD_B200_LIB", joinpath(@__DIR__, "..", "libhydrograd_b200.so"))
+
+const HG_PARAM = Dict("" => Int32(0), "zb" => Int32(1), "ManningN" => Int32(2), "Q" => Int32(3))
+
+# ---- mirrors of the C structs (field order and types must match hydrograd_b200.h) ----------------
+struct MeshDesc
+    n_cells::Int64; n_faces::Int64; n_ghost::Int64; ld::Int64
+    index_base::Int32
+    cell_nfaces::Ptr{Int64}; cell_faces::Ptr{Int64}; cell_neighbors::Ptr{Int64}
+    cell_normals::Ptr{Float64}; face_is_boundary::Ptr{UInt8}
+    face_lengths::Ptr{Float64}; cell_areas::Ptr{Float64}; cell_centroids::Ptr{Float64}
+end
+struct BcDesc
+    n_inletq::Int64; n_exith::Int64; n_wall::Int64; n_symm::Int64
+    bc_ptr::Ptr{Int64}; ghost_ids::Ptr{Int64}; internal_cells::Ptr{Int64}
+    outward_normals::Ptr{Float64}; face_lengths::Ptr{Float64}
+end
+struct FieldsDesc
+    g::Float64; k_n::Float64; h_small::Float64
+    riemann_solver::Cstring
+    hstill::Ptr{Float64}; hstill_ghost::Ptr{Float64}; zb_cells::Ptr{Float64}; zb_ghost::Ptr{Float64}
+    S0_cells::Ptr{Float64}; ManningN_cells::Ptr{Float64}; matID_cells::Ptr{Int64}; n_mat::Int64
+    inletQ_TotalQ::Ptr{Float64}; exitH_WSE::Ptr{Float64}
+end
+struct Options
+    device::Int32; tile_cells::Int32; reorder::Int32; strict::Int32; path::Int32
+    reserved::NTuple{11,Int32}
+end
+
+mutable struct Context
+    handle::Ptr{Cvoid}
+    N::Int
+    active::Int32
+    function Context(p_extra; device::Integer=0, tile_cells::Integer=512, strict::Bool=false)
+        h = _create(p_extra, Int32(device), Int32(tile_cells), strict)
+        ctx = new(h, p_extra.my_mesh_2D.numOfCells, HG_PARAM[p_extra.active_param_name])
+        finalizer(c -> (c.handle != C_NULL && ccall((:hg_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle); c.handle = C_NULL), ctx)
+        return ctx
+    end
+end
+
+_err(h) = unsafe_string(ccall((:hg_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
+_check(rc, h) = rc == 0 ? nothing : error("hydrograd_b200 error $rc: " * _err(h))
+
+# Flatten mesh_2D / BoundaryConditions2D / SWE2D_Extra_Parameters (no copies of the big matrices that
+# are already dense: cellFacesList, cellNodesCount, face_lengths, cell_areas, cell_centroids, S0_cells).
+function _create(px, device::Int32, tile::Int32, strict::Bool)
+    m  = px.my_mesh_2D
+    bc = px.boundary_conditions
+    N, ld = m.numOfCells, size(m.cellFacesList, 2)
+    neigh   = zeros(Int64, N, ld)                       # cellNeighbors_Dict -> N x ld
+    normals = zeros(Float64, N, ld, 2)                  # cell_normals       -> N x ld x 2
+    for i in 1:N, j in 1:m.cellNodesCount[i]
+        neigh[i, j] = m.cellNeighbors_Dict[i][j]
+        normals[i, j, 1] = m.cell_normals[i][j][1]
+        normals[i, j, 2] = m.cell_normals[i][j][2]
+    end
+    isb = UInt8.(m.bFace_is_boundary)
+    # boundary entries in the reference's own processing order (bc_2D.jl:279-295)
+    ptr = Int64[0]; gh = Int64[]; ic = Int64[]; nx = Float64[]; ny = Float64[]; len = Float64[]
+    for k in 1:bc.nInletQ_BCs
+        append!(gh, bc.inletQ_ghostCellIDs[k]); append!(ic, bc.inletQ_internalCellIDs[k])
+        append!(nx, bc.inletQ_faceOutwardNormals[k][:, 1]); append!(ny, bc.inletQ_faceOutwardNormals[k][:, 2])
+        append!(len, px.inletQ_Length[k]); push!(ptr, length(gh))
+    end
+    for k in 1:bc.nExitH_BCs
+        append!(gh, bc.exitH_ghostCellIDs[k]); append!(ic, bc.exitH_internalCellIDs[k])
+        append!(nx, bc.exitH_faceOutwardNormals[k][:, 1]); append!(ny, bc.exitH_faceOutwardNormals[k][:, 2])
+        append!(len, zeros(length(bc.exitH_ghostCellIDs[k]))); push!(ptr, length(gh))
+    end
+    for k in 1:bc.nWall_BCs
+        append!(gh, bc.wall_ghostCellIDs[k]); append!(ic, bc.wall_internalCellIDs[k])
+        append!(nx, bc.wall_outwardNormals[k][:, 1]); append!(ny, bc.wall_outwardNormals[k][:, 2])
+        append!(len, zeros(length(bc.wall_ghostCellIDs[k]))); push!(ptr, length(gh))
+    end
+    for k in 1:bc.nSymm_BCs
+        append!(gh, bc.symm_ghostCellIDs[k]); append!(ic, bc.symm_internalCellIDs[k])
+        append!(nx, bc.symm_outwardNormals[k][:, 1]); append!(ny, bc.symm_outwardNormals[k][:, 2])
+        append!(len, zeros(length(bc.symm_ghostCellIDs[k]))); push!(ptr, length(gh))
+    end
+    bnorm = vcat(nx, ny)
+    cellfaces = Matrix{Int64}(m.cellFacesList); nfaces = Vector{Int64}(m.cellNodesCount)
+    flen = Vector{Float64}(m.face_lengths); areas = Vector{Float64}(m.cell_areas)
+    cent = Matrix{Float64}(m.cell_centroids); S0 = Matrix{Float64}(px.S0_cells)
+    matid = Vector{Int64}(px.srh_all_Dict["matID_cells"])
+    nmat = length(px.srh_all_Dict["srhhydro_ManningsN"])
+    c = px.swe_2D_constants
+    solver = c.RiemannSolver
+    handle = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve neigh normals isb ptr gh ic bnorm len cellfaces nfaces flen areas cent S0 matid solver px begin
+        mesh = MeshDesc(N, m.numOfFaces, m.numOfAllBounaryFaces, ld, Int32(1), pointer(nfaces), pointer(cellfaces),
+                        pointer(neigh), pointer(normals), pointer(isb), pointer(flen), pointer(areas), pointer(cent))
+        bcd = BcDesc(bc.nInletQ_BCs, bc.nExitH_BCs, bc.nWall_BCs, bc.nSymm_BCs, pointer(ptr), pointer(gh), pointer(ic),
+                     pointer(bnorm), pointer(len))
+        fld = FieldsDesc(c.g, c.k_n, c.h_small, Base.unsafe_convert(Cstring, solver),
+                         pointer(px.hstill), pointer(px.hstill_ghostCells), pointer(px.zb_cells), pointer(px.zb_ghostCells),
+                         pointer(S0), pointer(px.ManningN_cells), pointer(matid), nmat,
+                         pointer(px.inletQ_TotalQ), pointer(px.exitH_WSE))
+        opt = Ref(Options(device, tile, Int32(1), Int32(strict), Int32(0), ntuple(_ -> Int32(0), 11)))
+        rc = ccall((:hg_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{MeshDesc}, Ref{BcDesc}, Ref{FieldsDesc}, Ref{Options}),
+                   handle, Ref(mesh), Ref(bcd), Ref(fld), opt)
+        _check(rc, C_NULL)
+    end
+    return handle[]
+end
+
+"""
+    swe_2d_rhs(dQdt, Q, params_vector, t, ctx) -> dQdt
+
+Same contract as Hydrograd.swe_2d_rhs (semi_discretize_swe_2D.jl:18-277): `dQdt` is overwritten and returned.
+"""
+function swe_2d_rhs(dQdt::Vector{Float64}, Q::Vector{Float64}, params_vector::Vector{Float64}, t::Float64, ctx::Context)
+    np = ctx.active == 0 ? 0 : length(params_vector)
+    GC.@preserve dQdt Q params_vector begin
+        rc = ccall((:hg_rhs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64, Ptr{Float64}),
+                   ctx.handle, Q, params_vector, np, ctx.active, t, dQdt)
+        _check(rc, ctx.handle)
+    end
+    return dQdt
+end
+swe_2d_rhs(Q::Vector{Float64}, p::Vector{Float64}, t::Float64, ctx::Context) = swe_2d_rhs(similar(Q), Q, p, t, ctx)
+
+"Vector-Jacobian product (Qbar, pbar) = (dRHS/dQ)' * lambda, (dRHS/dp)' * lambda -- what Zygote.pullback returns (debug_AD.jl:60,75)."
+function swe_2d_rhs_vjp(Q::Vector{Float64}, params_vector::Vector{Float64}, t::Float64, lambda::Vector{Float64}, ctx::Context)
+    Qbar = similar(Q); pbar = zeros(max(length(params_vector), 1))
+    np = ctx.active == 0 ? 0 : length(params_vector)
+    GC.@preserve Q params_vector lambda Qbar pbar begin
+        rc = ccall((:hg_rhs_vjp, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   ctx.handle, Q, params_vector, np, ctx.active, t, lambda, Qbar, pbar, C_NULL)
+        _check(rc, ctx.handle)
+    end
+    return Qbar, pbar[1:length(params_vector)]
+end
+
+function ChainRulesCore.rrule(::typeof(swe_2d_rhs), Q::Vector{Float64}, p::Vector{Float64}, t::Float64, ctx::Context)
+    y = swe_2d_rhs(Q, p, t, ctx)
+    function pullback(ybar)
+        Qbar, pbar = swe_2d_rhs_vjp(Q, p, t, collect(Float64, unthunk(ybar)), ctx)
+        return NoTangent(), Qbar, (ctx.active == 0 ? ZeroTangent() : pbar), NoTangent(), NoTangent()
+    end
+    return y, pullback
+end
+
+"custom_ODE_solve (ode_solvers/custom_ODE_solvers.jl:36-95) on the device; returns the 3N x nSaves matrix."
+function custom_ODE_solve(Q0::Vector{Float64}, params_vector::Vector{Float64}, tspan::Tuple{Float64,Float64}, dt::Float64, ctx::Context)
+    nsave = length(tspan[1]:dt:tspan[2])
+    sol = Matrix{Float64}(undef, 3 * ctx.N, nsave)
+    n = Ref{Int64}(0)
+    np = ctx.active == 0 ? 0 : length(params_vector)
+    GC.@preserve Q0 params_vector sol begin
+        rc = ccall((:hg_custom_ode_solve, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64, Float64, Float64, Ptr{Float64}, Int64, Ref{Int64}),
+                   ctx.handle, Q0, params_vector, np, ctx.active, tspan[1], tspan[2], dt, sol, nsave, n)
+        _check(rc, ctx.handle)
+    end
+    return sol[:, 1:n[]]
+end
+
+end # module

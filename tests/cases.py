@@ -79,12 +79,20 @@ def flat_scale(flat, Q):
     h = np.maximum(Q[:N] + flat["hstill"], hs)
     u2 = (Q[N:2 * N] ** 2 + Q[2 * N:] ** 2) / h ** 2
     c = np.sqrt(g * h)
-    s = (0.5 * g * h * h + h * u2 + h * np.sqrt(u2) * c + c * h) * per / np.asarray(flat["cell_areas"])
+    xi, hst = np.abs(Q[:N]), np.abs(np.asarray(flat["hstill"]))
+    # the momentum flux carries the xi-form pressure 0.5 g (xi^2 + 2 xi hstill) (swe_2D_solvers.jl:122), whose
+    # magnitude -- not 0.5 g h^2 -- is what cancels around a cell
+    s = (0.5 * g * (h * h + xi * xi + 2 * xi * hst) + h * u2 + h * np.sqrt(u2) * c + c * (h + xi)) * per / np.asarray(flat["cell_areas"])
     # a cell also feels its neighbours' pressure: use the max over the cell and its face neighbours
     nb = np.asarray(flat["cell_neighbors"]).reshape(ld, N) - base
     isb = np.asarray(flat["face_is_boundary"])[np.where(valid, faces, 0)].astype(bool)
     nbs = np.where(valid & ~isb, s[np.where(valid & ~isb, nb, 0)], 0.0).max(0)
     s = np.maximum(s, nbs)
+    # source magnitudes: Manning friction and bed-slope terms (semi_discretize_swe_2D.jl:463-478, 544-547)
+    q = np.sqrt(Q[N:2 * N] ** 2 + Q[2 * N:] ** 2)
+    fr = g * np.asarray(flat["ManningN_cells"]) ** 2 / flat["k_n"] ** 2 / (h + hs) ** (7.0 / 3.0) * q * q
+    S0 = np.asarray(flat["S0_cells"])
+    s = s + fr + g * np.abs(Q[:N]) * np.hypot(S0[:N], S0[N:])
     return np.concatenate([s, s, s]) + 1e-300
 
 
@@ -94,6 +102,10 @@ def random_state_flat(flat, seed, dry_frac=0.05):
     h = np.exp(rng.uniform(np.log(1e-4), np.log(10.0), N))
     k = rng.random(N) < dry_frac
     h[k] = rng.choice([5e-4, 1e-3, 9.999e-4], size=int(k.sum()))
+    # the reference asserts a positive inlet conveyance (bc_2D.jl:678-680): keep inlet-adjacent cells wet
+    ni = int(np.asarray(flat["bc_ptr"])[int(flat["n_inletq"])])
+    ic = np.asarray(flat["bc_internal_cells"])[:ni] - int(flat["index_base"])
+    h[ic] = np.maximum(h[ic], 0.05)
     sp = rng.uniform(0, 3, N)
     th = rng.uniform(0, 2 * np.pi, N)
     return np.concatenate([h - flat["hstill"], h * sp * np.cos(th), h * sp * np.sin(th)])
