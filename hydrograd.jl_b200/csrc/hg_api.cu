@@ -39,6 +39,16 @@ int al(hg_ctx* ctx, hg::DBuf<T>& b, size_t n) {
   if (n) CK(ctx, cudaMemsetAsync(b.p, 0, b.bytes(), ctx->stream));
   return HG_OK;
 }
+// cell-indexed arrays of the fused path are padded to Ns elements (TMA copies may over-read the last tile)
+template <class T>
+int upN(hg_ctx* ctx, hg::DBuf<T>& b, const std::vector<T>& h, size_t padded) {
+  CK(ctx, b.alloc(padded));
+  ctx->device_bytes += (int64_t)b.bytes();
+  CK(ctx, cudaMemsetAsync(b.p, 0, b.bytes(), ctx->stream));
+  if (!h.empty()) CK(ctx, cudaMemcpyAsync(b.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return HG_OK;
+}
 #define TRY(x)                 \
   do {                         \
     int _rc = (x);             \
@@ -234,13 +244,13 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(hg::build_tiles(ctx, m, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face));
     hg::FusedHost& fh = ctx->fh;
     hg::FusedDev& d = ctx->fd;
-    TRY(up(ctx, d.perm, fh.perm)); TRY(up(ctx, d.iperm, fh.iperm)); TRY(up(ctx, d.tile_cell0, fh.tile_cell0));
-    TRY(up(ctx, d.halo_ptr, fh.halo_ptr)); TRY(up(ctx, d.halo, fh.halo)); TRY(up(ctx, d.face_ptr, fh.face_ptr));
-    TRY(up(ctx, d.face_nint, fh.face_nint)); TRY(up(ctx, d.face_bce, fh.face_bce)); TRY(up(ctx, d.cf_ptr, fh.cf_ptr));
-    TRY(up(ctx, d.face_lr, fh.face_lr)); TRY(up(ctx, d.cf_idx, fh.cf_idx));
+    const size_t Ns = (size_t)fh.Ns;
+    TRY(up(ctx, d.perm, fh.perm)); TRY(up(ctx, d.iperm, fh.iperm)); TRY(up(ctx, d.tile_desc, fh.tile_desc));
+    TRY(up(ctx, d.halo, fh.halo)); TRY(up(ctx, d.bface_e, fh.bface_e));
+    TRY(up(ctx, d.face_lr, fh.face_lr)); TRY(up(ctx, d.cf_off, fh.cf_off)); TRY(up(ctx, d.cf_idx, fh.cf_idx));
     TRY(up(ctx, d.face_nx, fh.face_nx)); TRY(up(ctx, d.face_ny, fh.face_ny)); TRY(up(ctx, d.face_len, fh.face_len));
-    TRY(up(ctx, d.area, permuted(area.data(), fh.perm))); TRY(up(ctx, d.hstill, permuted(hstill.data(), fh.perm)));
-    TRY(al(ctx, d.zb, N)); TRY(al(ctx, d.S0x, N)); TRY(al(ctx, d.S0y, N)); TRY(al(ctx, d.mann, N));
+    TRY(upN(ctx, d.area, permuted(area.data(), fh.perm), Ns)); TRY(upN(ctx, d.hstill, permuted(hstill.data(), fh.perm), Ns));
+    TRY(al(ctx, d.zb, Ns)); TRY(al(ctx, d.S0x, Ns)); TRY(al(ctx, d.S0y, Ns)); TRY(al(ctx, d.mann, Ns));
     if (!x->matid_ref.empty()) TRY(up(ctx, d.matid, permuted(x->matid_ref.data(), fh.perm)));
     std::vector<int32_t> bc_cell(B);
     std::vector<double> bhst(B);
@@ -250,7 +260,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(up(ctx, d.bc_hstill, bhst)); TRY(al(ctx, d.bc_zb, B)); TRY(up(ctx, d.inlet_ptr, h.inlet_ptr));
     TRY(al(ctx, d.inlet_coef, std::max<int64_t>(ctx->n_inletq, 1)));
     TRY(al(ctx, d.Qin, ctx->n_inletq)); TRY(al(ctx, d.wse, ctx->n_exith));
-    TRY(al(ctx, d.Q, 3 * N)); TRY(al(ctx, d.Q2, 3 * N)); TRY(al(ctx, d.dQ, 3 * N)); TRY(al(ctx, d.stage, 3 * N));
+    TRY(al(ctx, d.Q, 3 * Ns)); TRY(al(ctx, d.Q2, 3 * Ns)); TRY(al(ctx, d.dQ, 3 * Ns)); TRY(al(ctx, d.stage, 3 * N));
     TRY(al(ctx, d.params, npar)); TRY(al(ctx, d.err, 1));
     // the plain CSR in reference order is kept for update_bed_data when zb is the active parameter
     hg::PlainDev& p = ctx->pd;
@@ -317,7 +327,7 @@ int hg_set_state(hg_ctx* ctx, const double* Q) {
     CK(ctx, cudaMemcpyAsync(ctx->pd.Q.p, Q, 3 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
   } else {
     CK(ctx, cudaMemcpyAsync(ctx->fd.stage.p, Q, 3 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
-    TRY(hg::fused_permute(ctx, ctx->fd.perm.p, ctx->fd.stage.p, ctx->fd.Q.p));
+    TRY(hg::fused_permute(ctx, true, ctx->fd.stage.p, ctx->fd.Q.p));
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->state_set = true;
@@ -329,7 +339,7 @@ static int download3(hg_ctx* ctx, const double* d_internal_or_ref, double* host)
   if (ctx->opt.path == 1) {
     CK(ctx, cudaMemcpyAsync(host, d_internal_or_ref, 3 * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
   } else {
-    TRY(hg::fused_permute(ctx, ctx->fd.iperm.p, d_internal_or_ref, ctx->fd.stage.p));
+    TRY(hg::fused_permute(ctx, false, d_internal_or_ref, ctx->fd.stage.p));
     CK(ctx, cudaMemcpyAsync(host, ctx->fd.stage.p, 3 * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -446,10 +456,13 @@ int hg_plan_stats(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_de
   if (rc == HG_OK) rc = hg::build_tiles(ctx.get(), m, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
   if (rc != HG_OK) { set_global_err(ctx->err); return rc; }
   const hg::FusedHost& fh = ctx->fh;
-  int64_t nint = 0;
-  for (int32_t v : fh.face_nint) nint += v;
+  int64_t nint = 0, nhalo = 0, nfaces = 0;
+  for (int32_t t = 0; t < fh.n_tiles; ++t) {
+    const int32_t* d = &fh.tile_desc[(size_t)t * hg::kTileDesc];
+    nint += d[9]; nhalo += d[3]; nfaces += d[5];
+  }
   stats[0] = fh.n_tiles; stats[1] = fh.max_local; stats[2] = fh.max_faces; stats[3] = hg::fused_smem_bytes(ctx.get());
-  stats[4] = (int64_t)fh.halo.size(); stats[5] = (int64_t)fh.face_lr.size(); stats[6] = nint; stats[7] = ctx->sumnf;
+  stats[4] = nhalo; stats[5] = nfaces; stats[6] = nint; stats[7] = ctx->sumnf;
   if (perm_out) for (int64_t i = 0; i < ctx->N; ++i) perm_out[i] = fh.perm[i];
   return HG_OK;
 }

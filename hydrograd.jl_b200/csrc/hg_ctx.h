@@ -77,38 +77,44 @@ struct PlainDev {
 };
 
 // ---------------------------------------------------------------- fused (tile) path
-// Tile t owns internal cells [tile_cell0[t], tile_cell0[t+1]).  Its local cell index space is
-// owned cells first, then halo cells (neighbours owned by another tile).  Faces touching an owned
-// cell are listed once per tile: interior faces (both sides real cells) then boundary faces.
+// Cells are renumbered so that tile t owns the internal cells [t*T, t*T + nc) -- every tile but the
+// last has exactly T cells.  Everything a tile needs lives in CONTIGUOUS, 16-byte aligned, padded
+// segments of the global arrays so that one CTA can pull its whole working set into shared memory
+// with a handful of TMA bulk copies (cp.async.bulk):
+//   cells  [c0, c0+nc)                  state (3 comps, stride Ns), hstill, zb, area, mann, S0x, S0y
+//   faces  [fp, fp+nfp)                 lr (lL | lR<<16), nx, ny, len; interior faces first, then
+//                                       boundary faces (lR = 0xFFFF), then zero-length padding to 4
+//   halo   [hp, hp+nh)                  internal ids of the neighbour cells owned by other tiles
+//   cf     [cfi, cfi+ncfp)              per-cell local face ids (bit 15 = cell is on the R side)
+//   cf_off [t*(T+8), ...)               per-cell offsets into the tile's cf segment
+// Local cell index space of a tile: owned cells 0..nc-1, halo cells ncp.. (ncp = nc rounded up to 2).
+constexpr int kTileDesc = 12;  // ints per tile: c0 nc hp nh fp nf nfp cfi ncfp nint bfp (pad)
 struct FusedHost {
-  int32_t n_tiles = 0, max_local = 0, max_faces = 0, max_cells = 0;
+  int32_t n_tiles = 0, T = 0, max_local = 0, max_faces = 0, max_cf = 0, max_halo = 0;
+  int64_t Ns = 0;                    // padded component stride of cell-indexed arrays
   std::vector<int32_t> perm;         // internal -> reference cell id
   std::vector<int32_t> iperm;        // reference -> internal
-  std::vector<int32_t> tile_cell0;   // [n_tiles+1]
-  std::vector<int32_t> halo_ptr;     // [n_tiles+1]
-  std::vector<int32_t> halo;         // internal ids of halo cells
-  std::vector<int32_t> face_ptr;     // [n_tiles+1]   tile faces (interior then boundary)
-  std::vector<int32_t> face_nint;    // [n_tiles]     number of interior faces
-  std::vector<uint32_t> face_lr;     // lL | lR<<16 (interior) ; lL | 0xFFFF<<16 (boundary)
-  std::vector<int32_t> face_bce;     // per tile face: boundary entry index or -1 (only read for boundary faces)
+  std::vector<int32_t> tile_desc;    // [n_tiles * kTileDesc]
+  std::vector<int32_t> halo;
+  std::vector<uint32_t> face_lr;
   std::vector<double> face_nx, face_ny, face_len;
-  std::vector<int32_t> cf_ptr;       // [N+1] global CSR (internal order) into cf_idx
-  std::vector<uint16_t> cf_idx;      // local face id | 0x8000 when the cell is on the R side
+  std::vector<int32_t> bface_e;      // boundary entry of each tile's boundary faces (tile order)
+  std::vector<uint16_t> cf_off, cf_idx;
 };
 
 struct FusedDev {
-  DBuf<int32_t> perm, iperm, tile_cell0, halo_ptr, halo, face_ptr, face_nint, face_bce, cf_ptr;
+  DBuf<int32_t> perm, iperm, tile_desc, halo, bface_e;
   DBuf<uint32_t> face_lr;
-  DBuf<uint16_t> cf_idx;
+  DBuf<uint16_t> cf_off, cf_idx;
   DBuf<double> face_nx, face_ny, face_len;
-  DBuf<double> area, hstill, zb, S0x, S0y, mann;  // [N] internal order
+  DBuf<double> area, hstill, zb, S0x, S0y, mann;  // [Ns] internal order
   DBuf<int32_t> matid;
   DBuf<int32_t> bc_type, bc_group, bc_cell;        // [B] entry order, internal cell ids
   DBuf<double> bc_nx, bc_ny, bc_l53, bc_l23, bc_hstill, bc_zb;
   DBuf<int32_t> inlet_ptr;
   DBuf<double> inlet_coef;                         // [n_inletq]  Q_k / total_A
   DBuf<double> Qin, wse;
-  DBuf<double> Q, Q2, dQ, lam, Qbar, stage, params, pbar, nbar, zbar;
+  DBuf<double> Q, Q2, dQ, lam, Qbar, stage, params, pbar, nbar, zbar;  // state-like: [3*Ns]
   DBuf<int32_t> err;
 };
 
@@ -161,7 +167,7 @@ int plain_rhs(hg_ctx* ctx, const double* dQ_in_Q, double* d_out);
 int fused_rhs(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 int fused_smem_bytes(const hg_ctx* ctx);
 int fused_prepare(hg_ctx* ctx);
-int fused_permute(hg_ctx* ctx, const int32_t* map, const double* src, double* dst);
+int fused_permute(hg_ctx* ctx, bool to_internal, const double* src, double* dst);
 int fused_bind_manning(hg_ctx* ctx, const double* d_params);
 int fused_bind_zb(hg_ctx* ctx, const double* d_params_ref);
 }  // namespace hg

@@ -164,50 +164,49 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
   FusedHost& fh = ctx->fh;
   fh = FusedHost();
   int32_t T = ctx->opt.tile_cells > 0 ? ctx->opt.tile_cells : 512;
-  if (T < 32 || T > 4096) HG_FAIL(ctx, HG_ERR_ARG, "tile_cells must be in [32, 4096]");
+  if (T < 32 || T > 2048 || (T % 8) != 0) HG_FAIL(ctx, HG_ERR_ARG, "tile_cells must be a multiple of 8 in [32, 2048]");
+  fh.T = T;
+  fh.Ns = ((N + 15) / 16) * 16 + 16;  // slack: the last tile's TMA copy may read one element past N
 
-  // ---- ordering + tiles
+  // ---- ordering: tile t = internal cells [t*T, min(N, (t+1)*T))
   fh.perm.resize(N);
   std::iota(fh.perm.begin(), fh.perm.end(), 0);
   if (ctx->opt.reorder && m->cell_centroids) {
-    Rcb r{m->cell_centroids, m->cell_centroids + N, T, fh.perm, fh.tile_cell0};
+    std::vector<int32_t> leaves;
+    Rcb r{m->cell_centroids, m->cell_centroids + N, T, fh.perm, leaves};
     r.run(0, N);
-  } else {
-    for (int64_t c = 0; c < N; c += T) fh.tile_cell0.push_back((int32_t)c);
+    for (size_t k = 0; k < leaves.size(); ++k)
+      if (leaves[k] != (int64_t)k * T) HG_FAIL(ctx, HG_ERR_ARG, "internal error: RCB leaf %zu starts at %d", k, leaves[k]);
   }
-  fh.tile_cell0.push_back((int32_t)N);
-  fh.n_tiles = (int32_t)fh.tile_cell0.size() - 1;
+  fh.n_tiles = (int32_t)((N + T - 1) / T);
   fh.iperm.resize(N);
   for (int64_t i = 0; i < N; ++i) fh.iperm[fh.perm[i]] = (int32_t)i;
 
-  // ghost id -> boundary entry
   std::vector<int32_t> ghost_entry(B);
   for (int64_t e = 0; e < B; ++e) ghost_entry[ctx->bch.ghost[e]] = (int32_t)e;
 
-  // ---- per-tile structures
   std::vector<int32_t> stamp(N, -1), loc(N, 0), fstamp(F, -1), floc(F, 0);
-  fh.halo_ptr.assign(1, 0);
-  fh.face_ptr.assign(1, 0);
-  fh.cf_ptr.assign(N + 1, 0);
-  for (int64_t i = 0; i < N; ++i) fh.cf_ptr[i + 1] = fh.cf_ptr[i] + (cf_ptr[fh.perm[i] + 1] - cf_ptr[fh.perm[i]]);
-  fh.cf_idx.resize(fh.cf_ptr[N]);
+  fh.tile_desc.assign((size_t)fh.n_tiles * kTileDesc, 0);
+  fh.cf_off.assign((size_t)fh.n_tiles * (T + 8), 0);
   fh.halo.reserve(N / 4);
   fh.face_lr.reserve(ctx->sumnf / 2 + ctx->sumnf / 8);
+  fh.cf_idx.reserve(ctx->sumnf + (size_t)fh.n_tiles * 8);
 
   for (int32_t t = 0; t < fh.n_tiles; ++t) {
-    const int32_t c0 = fh.tile_cell0[t], c1 = fh.tile_cell0[t + 1], nc = c1 - c0;
-    int32_t nloc = nc;
+    const int32_t c0 = t * T, c1 = (int32_t)std::min<int64_t>(N, (int64_t)c0 + T), nc = c1 - c0, ncp = (nc + 1) & ~1;
+    int32_t nloc = ncp;
     for (int32_t c = c0; c < c1; ++c) { stamp[c] = t; loc[c] = c - c0; }
-    const size_t face_base = fh.face_lr.size();
-    // pass A: interior faces, created by the first owned cell (in internal order) that sees them
+    const size_t face_base = fh.face_lr.size(), halo_base = fh.halo.size(), cf_base = fh.cf_idx.size(),
+                 bf_base = fh.bface_e.size();
+    // pass A: interior faces, created by the first owned cell (internal order) that sees them
     for (int32_t c = c0; c < c1; ++c) {
       const int32_t r = fh.perm[c];
       for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
         if (cf_nb[k] >= N) continue;
         const int32_t fid = cf_face[k];
-        if (fstamp[fid] == t) continue;  // already created from the other owned side
+        if (fstamp[fid] == t) continue;
         const int32_t rn = cf_nb[k], cn = fh.iperm[rn];
-        if (stamp[cn] != t) {            // halo cell: give it a local index
+        if (stamp[cn] != t) {  // halo cell: next local index
           stamp[cn] = t; loc[cn] = nloc++;
           fh.halo.push_back(cn);
         }
@@ -224,12 +223,11 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
         }
         fstamp[fid] = t; floc[fid] = (int32_t)(fh.face_lr.size() - face_base);
         fh.face_lr.push_back((uint32_t)lL | ((uint32_t)lR << 16));
-        fh.face_bce.push_back(-1);
         fh.face_nx.push_back(nx); fh.face_ny.push_back(ny); fh.face_len.push_back(cf_len[k]);
       }
     }
     const int32_t nint = (int32_t)(fh.face_lr.size() - face_base);
-    // pass B: boundary faces (ghost state is evaluated on the fly from the owned internal cell)
+    // pass B: boundary faces (their ghost state is evaluated on the fly from the owned internal cell)
     for (int32_t c = c0; c < c1; ++c) {
       const int32_t r = fh.perm[c];
       for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
@@ -237,30 +235,45 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
         const int32_t fid = cf_face[k];
         fstamp[fid] = t; floc[fid] = (int32_t)(fh.face_lr.size() - face_base);
         fh.face_lr.push_back((uint32_t)loc[c] | (0xFFFFu << 16));
-        fh.face_bce.push_back(ghost_entry[cf_nb[k] - N]);
+        fh.bface_e.push_back(ghost_entry[cf_nb[k] - N]);
         fh.face_nx.push_back(cf_nx[k]); fh.face_ny.push_back(cf_ny[k]); fh.face_len.push_back(cf_len[k]);
       }
     }
     const int32_t nf = (int32_t)(fh.face_lr.size() - face_base);
     if (nloc >= 0xFFFF || nf >= 0x8000) HG_FAIL(ctx, HG_ERR_ARG, "tile %d too large (local cells %d, faces %d)", t, nloc, nf);
+    while ((fh.face_lr.size() - face_base) % 4) {  // zero-length padding faces keep the segments 16-byte sized
+      fh.face_lr.push_back(0u); fh.face_nx.push_back(1.0); fh.face_ny.push_back(0.0); fh.face_len.push_back(0.0);
+    }
+    const int32_t nfp = (int32_t)(fh.face_lr.size() - face_base);
     // pass C: per-cell local CSR in the reference's face order, with the side bit
+    uint16_t* off = &fh.cf_off[(size_t)t * (T + 8)];
     for (int32_t c = c0; c < c1; ++c) {
       const int32_t r = fh.perm[c];
-      int32_t o = fh.cf_ptr[c];
-      for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k, ++o) {
+      off[c - c0] = (uint16_t)(fh.cf_idx.size() - cf_base);
+      for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
         const int32_t lf = floc[cf_face[k]];
         const uint32_t lr = fh.face_lr[face_base + lf];
         const bool on_right = (cf_nb[k] < N) && ((int32_t)(lr >> 16) == loc[c]);
-        fh.cf_idx[o] = (uint16_t)(lf | (on_right ? 0x8000 : 0));
+        fh.cf_idx.push_back((uint16_t)(lf | (on_right ? 0x8000 : 0)));
       }
     }
-    fh.halo_ptr.push_back((int32_t)fh.halo.size());
-    fh.face_ptr.push_back((int32_t)fh.face_lr.size());
-    fh.face_nint.push_back(nint);
-    fh.max_local = std::max(fh.max_local, nloc);
-    fh.max_faces = std::max(fh.max_faces, nf);
-    fh.max_cells = std::max(fh.max_cells, nc);
+    if (fh.cf_idx.size() - cf_base >= 0xFFFF) HG_FAIL(ctx, HG_ERR_ARG, "tile %d has too many cell faces", t);
+    off[nc] = (uint16_t)(fh.cf_idx.size() - cf_base);
+    while ((fh.cf_idx.size() - cf_base) % 8) fh.cf_idx.push_back(0);
+    const int32_t ncfp = (int32_t)(fh.cf_idx.size() - cf_base);
+    const int32_t nh = (int32_t)(fh.halo.size() - halo_base);
+    while ((fh.halo.size() - halo_base) % 4) fh.halo.push_back(0);
+    int32_t* d = &fh.tile_desc[(size_t)t * kTileDesc];
+    d[0] = c0; d[1] = nc; d[2] = (int32_t)halo_base; d[3] = nh; d[4] = (int32_t)face_base; d[5] = nf; d[6] = nfp;
+    d[7] = (int32_t)cf_base; d[8] = ncfp; d[9] = nint; d[10] = (int32_t)bf_base; d[11] = 0;
+    fh.max_local = std::max(fh.max_local, ncp + nh);
+    fh.max_faces = std::max(fh.max_faces, nfp);
+    fh.max_cf = std::max(fh.max_cf, ncfp);
+    fh.max_halo = std::max(fh.max_halo, nh);
   }
+  fh.max_local = (fh.max_local + 1) & ~1;
+  if (fh.halo.empty()) fh.halo.push_back(0);
+  if (fh.bface_e.empty()) fh.bface_e.push_back(0);
   return HG_OK;
 }
 
