@@ -129,7 +129,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cells-m", type=float, default=16.0, help="million cells per GPU")
-    ap.add_argument("--tile", type=int, default=512)
+    ap.add_argument("--tile", type=int, default=256)
+    ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the fused kernel (tuning)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
@@ -162,7 +163,7 @@ def main():
     N, F = flat["n_cells"], flat["n_faces"]
     log(f"[rank {rank}] mesh: N={N} F={F} ({time.time() - t0:.1f}s)")
     t0 = time.time()
-    ctx = hg.Context(flat, device=local, tile_cells=args.tile)
+    ctx = hg.Context(flat, device=local, tile_cells=args.tile, threads=args.threads)
     st = ctx.mesh_stats()
     log(f"[rank {rank}] context: {st} ({time.time() - t0:.1f}s)")
     ctx.set_state(Q0)

@@ -158,7 +158,7 @@ extern "C" {
 
 void hg_default_options(hg_options* o) {
   std::memset(o, 0, sizeof(*o));
-  o->device = 0; o->tile_cells = 512; o->reorder = 1; o->strict = 0; o->path = 0;
+  o->device = 0; o->tile_cells = 256; o->reorder = 1; o->strict = 0; o->path = 0;
 }
 int hg_abi_version(void) { return HG_ABI_VERSION; }
 
@@ -247,7 +247,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     const size_t Ns = (size_t)fh.Ns;
     TRY(up(ctx, d.perm, fh.perm)); TRY(up(ctx, d.iperm, fh.iperm)); TRY(up(ctx, d.tile_desc, fh.tile_desc));
     TRY(up(ctx, d.halo, fh.halo)); TRY(up(ctx, d.bface_e, fh.bface_e));
-    TRY(up(ctx, d.face_lr, fh.face_lr)); TRY(up(ctx, d.cf_off, fh.cf_off)); TRY(up(ctx, d.cf_idx, fh.cf_idx));
+    TRY(up(ctx, d.face_lr, fh.face_lr)); TRY(up(ctx, d.cf_idx, fh.cf_idx));
     TRY(up(ctx, d.face_nx, fh.face_nx)); TRY(up(ctx, d.face_ny, fh.face_ny)); TRY(up(ctx, d.face_len, fh.face_len));
     TRY(upN(ctx, d.area, permuted(area.data(), fh.perm), Ns)); TRY(upN(ctx, d.hstill, permuted(hstill.data(), fh.perm), Ns));
     TRY(al(ctx, d.zb, Ns)); TRY(al(ctx, d.S0x, Ns)); TRY(al(ctx, d.S0y, Ns)); TRY(al(ctx, d.mann, Ns));

@@ -85,12 +85,13 @@ struct PlainDev {
 //   faces  [fp, fp+nfp)                 lr (lL | lR<<16), nx, ny, len; interior faces first, then
 //                                       boundary faces (lR = 0xFFFF), then zero-length padding to 4
 //   halo   [hp, hp+nh)                  internal ids of the neighbour cells owned by other tiles
-//   cf     [cfi, cfi+ncfp)              per-cell local face ids (bit 15 = cell is on the R side)
-//   cf_off [t*(T+8), ...)               per-cell offsets into the tile's cf segment
+//   cf     [t*T*NF, (t+1)*T*NF)         NF slots per cell: local face ids in the reference's face order
+//                                       (bit 15 = cell is on the R side); unused slots point at the
+//                                       tile's zero-flux slot (index nfp)
 // Local cell index space of a tile: owned cells 0..nc-1, halo cells ncp.. (ncp = nc rounded up to 2).
-constexpr int kTileDesc = 12;  // ints per tile: c0 nc hp nh fp nf nfp cfi ncfp nint bfp (pad)
+constexpr int kTileDesc = 12;  // ints per tile: c0 nc hp nh fp nf nfp (unused) (unused) nint bfp (pad)
 struct FusedHost {
-  int32_t n_tiles = 0, T = 0, max_local = 0, max_faces = 0, max_cf = 0, max_halo = 0;
+  int32_t n_tiles = 0, T = 0, NF = 4, max_local = 0, max_faces = 0, max_halo = 0, max_cell_faces = 0;
   int64_t Ns = 0;                    // padded component stride of cell-indexed arrays
   std::vector<int32_t> perm;         // internal -> reference cell id
   std::vector<int32_t> iperm;        // reference -> internal
@@ -99,13 +100,13 @@ struct FusedHost {
   std::vector<uint32_t> face_lr;
   std::vector<double> face_nx, face_ny, face_len;
   std::vector<int32_t> bface_e;      // boundary entry of each tile's boundary faces (tile order)
-  std::vector<uint16_t> cf_off, cf_idx;
+  std::vector<uint16_t> cf_idx;      // [n_tiles * T * NF]
 };
 
 struct FusedDev {
   DBuf<int32_t> perm, iperm, tile_desc, halo, bface_e;
   DBuf<uint32_t> face_lr;
-  DBuf<uint16_t> cf_off, cf_idx;
+  DBuf<uint16_t> cf_idx;
   DBuf<double> face_nx, face_ny, face_len;
   DBuf<double> area, hstill, zb, S0x, S0y, mann;  // [Ns] internal order
   DBuf<int32_t> matid;
@@ -167,6 +168,7 @@ int plain_rhs(hg_ctx* ctx, const double* dQ_in_Q, double* d_out);
 int fused_rhs(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 int fused_smem_bytes(const hg_ctx* ctx);
 int fused_prepare(hg_ctx* ctx);
+bool fused_config_ok(const hg_ctx* ctx);
 int fused_permute(hg_ctx* ctx, bool to_internal, const double* src, double* dst);
 int fused_bind_manning(hg_ctx* ctx, const double* d_params);
 int fused_bind_zb(hg_ctx* ctx, const double* d_params_ref);

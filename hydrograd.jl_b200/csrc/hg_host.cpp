@@ -157,15 +157,47 @@ struct Rcb {
 };
 }  // namespace
 
+static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& cf_ptr,
+                         const std::vector<int32_t>& cf_nb, const std::vector<double>& cf_nx, const std::vector<double>& cf_ny,
+                         const std::vector<double>& cf_len, const std::vector<int32_t>& cf_face);
+
+// Tile the mesh for one of the compiled kernel configurations (hg_fused.cu): the requested tile size if
+// its tiles fit the configuration's shared-memory caps, else the small general configuration (T = 128,
+// up to 8 faces per cell).
 int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& cf_ptr,
                 const std::vector<int32_t>& cf_nb, const std::vector<double>& cf_nx, const std::vector<double>& cf_ny,
                 const std::vector<double>& cf_len, const std::vector<int32_t>& cf_face) {
+  int32_t want = ctx->opt.tile_cells > 0 ? ctx->opt.tile_cells : 256;
+  if (want != 128 && want != 256 && want != 512) HG_FAIL(ctx, HG_ERR_ARG, "tile_cells must be 128, 256 or 512");
+  int32_t maxnf = 0;
+  for (int64_t i = 0; i < ctx->N; ++i) maxnf = std::max(maxnf, cf_ptr[i + 1] - cf_ptr[i]);
+  if (maxnf > 4) want = 128;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ctx->opt.tile_cells = want;
+    int rc = build_tiles_T(ctx, m, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
+    if (rc != HG_OK) return rc;
+    if (fused_config_ok(ctx)) return HG_OK;
+    if (want == 128) break;
+    want = 128;
+  }
+  HG_FAIL(ctx, HG_ERR_ARG, "mesh does not fit the compiled tile configurations (tile needs %d local cells, %d faces): "
+          "renumber the mesh for locality or pass cell_centroids", ctx->fh.max_local, ctx->fh.max_faces);
+}
+
+static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& cf_ptr,
+                         const std::vector<int32_t>& cf_nb, const std::vector<double>& cf_nx, const std::vector<double>& cf_ny,
+                         const std::vector<double>& cf_len, const std::vector<int32_t>& cf_face) {
   const int64_t N = ctx->N, F = ctx->F, B = ctx->B;
   FusedHost& fh = ctx->fh;
   fh = FusedHost();
-  int32_t T = ctx->opt.tile_cells > 0 ? ctx->opt.tile_cells : 512;
-  if (T < 32 || T > 2048 || (T % 8) != 0) HG_FAIL(ctx, HG_ERR_ARG, "tile_cells must be a multiple of 8 in [32, 2048]");
+  const int32_t T = ctx->opt.tile_cells;
   fh.T = T;
+  int32_t maxnf = 0;
+  for (int64_t i = 0; i < N; ++i) maxnf = std::max(maxnf, cf_ptr[i + 1] - cf_ptr[i]);
+  fh.max_cell_faces = maxnf;
+  fh.NF = (maxnf <= 4 && T != 128) ? 4 : 8;
+  const int32_t NF = fh.NF;
+  if (maxnf > 8) HG_FAIL(ctx, HG_ERR_ARG, "cells with %d faces are not supported (max 8 = gMax_Nodes_per_Element)", maxnf);
   fh.Ns = ((N + 15) / 16) * 16 + 16;  // slack: the last tile's TMA copy may read one element past N
 
   // ---- ordering: tile t = internal cells [t*T, min(N, (t+1)*T))
@@ -187,17 +219,15 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
 
   std::vector<int32_t> stamp(N, -1), loc(N, 0), fstamp(F, -1), floc(F, 0);
   fh.tile_desc.assign((size_t)fh.n_tiles * kTileDesc, 0);
-  fh.cf_off.assign((size_t)fh.n_tiles * (T + 8), 0);
+  fh.cf_idx.assign((size_t)fh.n_tiles * T * NF, 0);
   fh.halo.reserve(N / 4);
   fh.face_lr.reserve(ctx->sumnf / 2 + ctx->sumnf / 8);
-  fh.cf_idx.reserve(ctx->sumnf + (size_t)fh.n_tiles * 8);
 
   for (int32_t t = 0; t < fh.n_tiles; ++t) {
     const int32_t c0 = t * T, c1 = (int32_t)std::min<int64_t>(N, (int64_t)c0 + T), nc = c1 - c0, ncp = (nc + 1) & ~1;
     int32_t nloc = ncp;
     for (int32_t c = c0; c < c1; ++c) { stamp[c] = t; loc[c] = c - c0; }
-    const size_t face_base = fh.face_lr.size(), halo_base = fh.halo.size(), cf_base = fh.cf_idx.size(),
-                 bf_base = fh.bface_e.size();
+    const size_t face_base = fh.face_lr.size(), halo_base = fh.halo.size(), bf_base = fh.bface_e.size();
     // pass A: interior faces, created by the first owned cell (internal order) that sees them
     for (int32_t c = c0; c < c1; ++c) {
       const int32_t r = fh.perm[c];
@@ -245,30 +275,27 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
       fh.face_lr.push_back(0u); fh.face_nx.push_back(1.0); fh.face_ny.push_back(0.0); fh.face_len.push_back(0.0);
     }
     const int32_t nfp = (int32_t)(fh.face_lr.size() - face_base);
-    // pass C: per-cell local CSR in the reference's face order, with the side bit
-    uint16_t* off = &fh.cf_off[(size_t)t * (T + 8)];
+    // pass C: NF slots per cell, local face ids in the reference's face order with the side bit; unused
+    // slots point at the zero-flux slot nfp (adding 0.0 last leaves the left-to-right sum unchanged)
+    uint16_t* slots = &fh.cf_idx[(size_t)t * T * NF];
+    for (int32_t l = 0; l < T * NF; ++l) slots[l] = (uint16_t)nfp;
     for (int32_t c = c0; c < c1; ++c) {
       const int32_t r = fh.perm[c];
-      off[c - c0] = (uint16_t)(fh.cf_idx.size() - cf_base);
-      for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
+      int32_t j = 0;
+      for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k, ++j) {
         const int32_t lf = floc[cf_face[k]];
         const uint32_t lr = fh.face_lr[face_base + lf];
         const bool on_right = (cf_nb[k] < N) && ((int32_t)(lr >> 16) == loc[c]);
-        fh.cf_idx.push_back((uint16_t)(lf | (on_right ? 0x8000 : 0)));
+        slots[(c - c0) * NF + j] = (uint16_t)(lf | (on_right ? 0x8000 : 0));
       }
     }
-    if (fh.cf_idx.size() - cf_base >= 0xFFFF) HG_FAIL(ctx, HG_ERR_ARG, "tile %d has too many cell faces", t);
-    off[nc] = (uint16_t)(fh.cf_idx.size() - cf_base);
-    while ((fh.cf_idx.size() - cf_base) % 8) fh.cf_idx.push_back(0);
-    const int32_t ncfp = (int32_t)(fh.cf_idx.size() - cf_base);
     const int32_t nh = (int32_t)(fh.halo.size() - halo_base);
     while ((fh.halo.size() - halo_base) % 4) fh.halo.push_back(0);
     int32_t* d = &fh.tile_desc[(size_t)t * kTileDesc];
     d[0] = c0; d[1] = nc; d[2] = (int32_t)halo_base; d[3] = nh; d[4] = (int32_t)face_base; d[5] = nf; d[6] = nfp;
-    d[7] = (int32_t)cf_base; d[8] = ncfp; d[9] = nint; d[10] = (int32_t)bf_base; d[11] = 0;
+    d[7] = 0; d[8] = 0; d[9] = nint; d[10] = (int32_t)bf_base; d[11] = 0;
     fh.max_local = std::max(fh.max_local, ncp + nh);
     fh.max_faces = std::max(fh.max_faces, nfp);
-    fh.max_cf = std::max(fh.max_cf, ncfp);
     fh.max_halo = std::max(fh.max_halo, nh);
   }
   fh.max_local = (fh.max_local + 1) & ~1;

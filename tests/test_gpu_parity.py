@@ -95,8 +95,9 @@ def test_tiling_and_ordering_do_not_change_bits(hg):
     flat, Q0 = synth("river")
     Q = cases.random_state_flat(flat, 11)
     base = hg.Context(flat, tile_cells=512, reorder=True).rhs(Q)
-    for tile, reorder in ((64, True), (200, True), (512, False), (96, False)):
-        assert np.array_equal(base, hg.Context(flat, tile_cells=tile, reorder=reorder).rhs(Q)), (tile, reorder)
+    for tile, reorder, threads in ((128, True, 0), (256, True, 128), (256, True, 256), (512, False, 384), (128, False, 0)):
+        got = hg.Context(flat, tile_cells=tile, reorder=reorder, threads=threads).rhs(Q)
+        assert np.array_equal(base, got), (tile, reorder, threads)
 
 
 @pytest.mark.parametrize("strict", [True, False])
