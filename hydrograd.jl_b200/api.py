@@ -194,6 +194,11 @@ class Context:
         self._ck(self.lib.hg_time_rhs(self._h, int(n_launches), int(fused_euler), float(dt), C.byref(ms)))
         return ms.value
 
+    def time_vjp(self, n_launches):
+        ms = C.c_float(0)
+        self._ck(self.lib.hg_time_vjp(self._h, int(n_launches), C.byref(ms)))
+        return ms.value
+
     def kernel_launches(self):
         return int(self.lib.hg_kernel_launches(self._h))
 

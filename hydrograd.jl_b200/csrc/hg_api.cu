@@ -262,12 +262,24 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(al(ctx, d.Qin, ctx->n_inletq)); TRY(al(ctx, d.wse, ctx->n_exith));
     TRY(al(ctx, d.Q, 3 * Ns)); TRY(al(ctx, d.Q2, 3 * Ns)); TRY(al(ctx, d.dQ, 3 * Ns)); TRY(al(ctx, d.stage, 3 * N));
     TRY(al(ctx, d.params, npar)); TRY(al(ctx, d.err, 1));
+    // adjoint buffers
+    TRY(al(ctx, d.lam, 3 * Ns)); TRY(al(ctx, d.Qbar, 3 * Ns)); TRY(al(ctx, d.nbar, Ns)); TRY(al(ctx, d.s0bar, 2 * Ns));
+    TRY(al(ctx, d.pbar, npar)); TRY(al(ctx, d.ent_c, std::max<int64_t>(B, 1))); TRY(al(ctx, d.ent_n, std::max<int64_t>(B, 1)));
+    TRY(al(ctx, d.ent_z, std::max<int64_t>(B, 1))); TRY(al(ctx, d.ent_h, std::max<int64_t>(B, 1)));
+    TRY(al(ctx, d.Qinbar, std::max<int64_t>(ctx->n_inletq, 1))); TRY(al(ctx, d.inlet_A, std::max<int64_t>(ctx->n_inletq, 1)));
+    {
+      std::vector<int32_t> bcell_int(h.bcell_ref.size());
+      for (size_t q = 0; q < bcell_int.size(); ++q) bcell_int[q] = fh.iperm[h.bcell_ref[q]];
+      TRY(up(ctx, d.bcell, bcell_int)); TRY(up(ctx, d.bcell_ref, h.bcell_ref));
+      TRY(up(ctx, d.bcell_ptr, h.bcell_ptr)); TRY(up(ctx, d.bcell_ent, h.bcell_ent));
+    }
     // the plain CSR in reference order is kept for update_bed_data when zb is the active parameter
     hg::PlainDev& p = ctx->pd;
     TRY(up(ctx, p.cf_ptr, cf_ptr)); TRY(up(ctx, p.cf_nb, cf_nb));
     TRY(up(ctx, p.cf_nx, cf_nx)); TRY(up(ctx, p.cf_ny, cf_ny)); TRY(up(ctx, p.cf_len, cf_len));
-    TRY(up(ctx, p.area, area)); TRY(up(ctx, p.bc_cell, h.cell_ref));
+    TRY(up(ctx, p.area, area)); TRY(up(ctx, p.bc_cell, h.cell_ref)); TRY(up(ctx, p.cf_rev, h.cf_rev));
     TRY(hg::fused_prepare(ctx));
+    TRY(hg::fused_vjp_prepare(ctx, hg::fused_cfg_id(ctx)));
   }
   TRY(upload_fields(ctx));
   return HG_OK;
@@ -378,10 +390,36 @@ int hg_rhs(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32
   return hg_get_rhs(ctx, dQdt);
 }
 
-int hg_rhs_vjp(hg_ctx* ctx, const double*, const double*, int64_t, int32_t, double, const double*, double*, double*, double*) {
-  if (!ctx) return HG_ERR_ARG;
-  ctx->err = "hg_rhs_vjp: not available in this build";
-  return HG_ERR_STATE;
+static int set_lambda(hg_ctx* ctx, const double* lam) {
+  const int64_t N = ctx->N;
+  CK(ctx, cudaMemcpyAsync(ctx->fd.stage.p, lam, 3 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TRY(hg::fused_permute(ctx, true, ctx->fd.stage.p, ctx->fd.lam.p));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->lam_set = true;
+  return HG_OK;
+}
+
+int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32_t active, double t, const double* lambda,
+               double* Qbar, double* pbar, double* ncell_bar) {
+  (void)t;
+  if (!ctx || !Q || !lambda || !Qbar) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "hg_rhs_vjp needs the fused path (strict = 0)"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  TRY(bind_params(ctx, params, np, active));
+  if (ctx->active != HG_PARAM_NONE && !pbar) { ctx->err = "hg_rhs_vjp: pbar is NULL"; return HG_ERR_ARG; }
+  TRY(hg_set_state(ctx, Q));
+  TRY(set_lambda(ctx, lambda));
+  hg::FusedDev& d = ctx->fd;
+  TRY(hg::fused_vjp(ctx, hg::fused_cfg_id(ctx), d.Q.p, d.lam.p, d.Qbar.p));
+  TRY(download3(ctx, d.Qbar.p, Qbar));
+  if (ctx->active != HG_PARAM_NONE)
+    CK(ctx, cudaMemcpyAsync(pbar, d.pbar.p, ctx->n_params * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ncell_bar) {
+    TRY(hg::fused_nbar_to_ref(ctx, d.stage.p));
+    CK(ctx, cudaMemcpyAsync(ncell_bar, d.stage.p, ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_err_flag(ctx);
 }
 
 int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
@@ -429,10 +467,22 @@ int hg_time_rhs(hg_ctx* ctx, int32_t n, int32_t fused_euler, double dt, float* m
   return check_err_flag(ctx);
 }
 
-int hg_time_vjp(hg_ctx* ctx, int32_t, float*) {
-  if (!ctx) return HG_ERR_ARG;
-  ctx->err = "hg_time_vjp: not available in this build";
-  return HG_ERR_STATE;
+int hg_time_vjp(hg_ctx* ctx, int32_t n, float* ms) {
+  if (!ctx || !ms || n <= 0) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "hg_time_vjp needs the fused path"; return HG_ERR_ARG; }
+  if (!ctx->state_set) { ctx->err = "hg_time_vjp: no resident state"; return HG_ERR_STATE; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  if (!ctx->lam_set) {  // default cotangent: the resident dQdt-shaped buffer filled with ones
+    std::vector<double> ones(3 * ctx->N, 1.0);
+    TRY(set_lambda(ctx, ones.data()));
+  }
+  CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int i = 0; i < n; ++i) TRY(hg::fused_vjp(ctx, hg::fused_cfg_id(ctx), d.Q.p, d.lam.p, d.Qbar.p));
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return check_err_flag(ctx);
 }
 
 int hg_mesh_stats(const hg_ctx* ctx, int64_t* nc, int64_t* nf, int64_t* snf, int64_t* nt, int64_t* bytes) {

@@ -58,11 +58,13 @@ struct BcHost {
   std::vector<int32_t> type, group, ghost, cell_ref;  // [B]
   std::vector<double> nx, ny, l53, l23, hstill_g, zb_g;  // [B]; l53 = L^(5/3), l23 = L^(2/3) (inlet only)
   std::vector<int32_t> inlet_ptr;                     // [n_inletq+1] entry ranges of each inlet boundary
+  std::vector<int32_t> bcell_ref, bcell_ptr, bcell_ent; // distinct boundary-adjacent cells (reference ids) -> entries
+  std::vector<int32_t> cf_rev;                        // per cell-face: index of the same face in the neighbour's list
 };
 
 // ---------------------------------------------------------------- plain (reference-order) path
 struct PlainDev {
-  DBuf<int32_t> cf_ptr, cf_nb;        // CSR of cell faces; nb >= N means ghost (N + ghost id)
+  DBuf<int32_t> cf_ptr, cf_nb, cf_rev; // CSR of cell faces; nb >= N means ghost (N + ghost id); rev = same face in nb's list
   DBuf<double> cf_nx, cf_ny, cf_len;  // per cell-face
   DBuf<double> area, hstill, zb, S0x, S0y, mann;  // [N] reference order
   DBuf<int32_t> matid;                // [N]
@@ -115,7 +117,9 @@ struct FusedDev {
   DBuf<int32_t> inlet_ptr;
   DBuf<double> inlet_coef;                         // [n_inletq]  Q_k / total_A
   DBuf<double> Qin, wse;
-  DBuf<double> Q, Q2, dQ, lam, Qbar, stage, params, pbar, nbar, zbar;  // state-like: [3*Ns]
+  DBuf<double> Q, Q2, dQ, lam, Qbar, stage, params, pbar, nbar, s0bar;  // state-like: [3*Ns]
+  DBuf<double> ent_c, ent_n, ent_z, ent_h, Qinbar, inlet_A, zone_part;   // VJP: per boundary entry / per inlet
+  DBuf<int32_t> bcell, bcell_ref, bcell_ptr, bcell_ent;                 // boundary-adjacent cells -> their entries
   DBuf<int32_t> err;
 };
 
@@ -129,7 +133,8 @@ struct Frozen {
 struct hg_ctx {
   hg_options opt{};
   int64_t N = 0, F = 0, B = 0, sumnf = 0;
-  int64_t n_inletq = 0, n_exith = 0, n_wall = 0, n_symm = 0, n_mat = 0;
+  int64_t n_inletq = 0, n_exith = 0, n_wall = 0, n_symm = 0, n_mat = 0, nbcell = 0;
+  bool lam_set = false;
   hg::Consts c{};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -172,4 +177,10 @@ bool fused_config_ok(const hg_ctx* ctx);
 int fused_permute(hg_ctx* ctx, bool to_internal, const double* src, double* dst);
 int fused_bind_manning(hg_ctx* ctx, const double* d_params);
 int fused_bind_zb(hg_ctx* ctx, const double* d_params_ref);
+int fused_cfg_id(const hg_ctx* ctx);
+void fused_inlet_coef(hg_ctx* ctx, const double* d_Q);
+// fused VJP (hg_vjp.cu)
+int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
+int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);
+int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 }  // namespace hg

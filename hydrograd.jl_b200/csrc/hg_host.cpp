@@ -122,6 +122,36 @@ int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg
     for (int32_t k = cf_ptr[c]; k < cf_ptr[c + 1]; ++k) ok |= (cf_nb[k] == (int32_t)(N + h.ghost[e]));
     if (!ok) HG_FAIL(ctx, HG_ERR_ARG, "boundary entry %ld: ghost %d is not a neighbour of cell %d", (long)e, h.ghost[e], c);
   }
+  // ---- per cell-face: where the same face sits in the neighbour's list (transposed Green-Gauss of the VJP)
+  h.cf_rev.assign(S, -1);
+  {
+    std::vector<int32_t> first(F, -1);
+    for (int64_t k = 0; k < S; ++k) {
+      if (cf_nb[k] >= N) continue;
+      const int32_t fid = cf_face[k];
+      if (first[fid] < 0) first[fid] = (int32_t)k;
+      else { h.cf_rev[k] = first[fid]; h.cf_rev[first[fid]] = (int32_t)k; }
+    }
+    for (int64_t k = 0; k < S; ++k)
+      if (cf_nb[k] < N && h.cf_rev[k] < 0) HG_FAIL(ctx, HG_ERR_ARG, "interior face %d is listed by one cell only", cf_face[k]);
+  }
+  // ---- distinct boundary-adjacent cells -> their boundary entries (deterministic scatter of BC adjoints)
+  {
+    std::vector<int32_t> order(B);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return h.cell_ref[x] < h.cell_ref[y]; });
+    h.bcell_ptr.assign(1, 0);
+    for (int64_t q = 0; q < B; ++q) {
+      const int32_t e = order[q];
+      if (q == 0 || h.cell_ref[e] != h.cell_ref[order[q - 1]]) {
+        if (q) h.bcell_ptr.push_back((int32_t)h.bcell_ent.size());
+        h.bcell_ref.push_back(h.cell_ref[e]);
+      }
+      h.bcell_ent.push_back(e);
+    }
+    if (B) h.bcell_ptr.push_back((int32_t)h.bcell_ent.size());
+    ctx->nbcell = (int64_t)h.bcell_ref.size();
+  }
   return HG_OK;
 }
 

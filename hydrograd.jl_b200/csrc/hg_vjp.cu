@@ -1,0 +1,608 @@
+// Hand-written adjoint (vector-Jacobian product) of the fused RHS -- replaces Zygote on swe_2d_rhs for the
+// inversion / UDE loss gradients (call sites: swe_2D_inversion.jl:339, swe_2D_UDE.jl:666; contract
+// debug_AD.jl:60,75:  back(lambda) -> (Qbar, pbar)).
+//
+// Same tile structure and TMA staging as hg_fused.cu; forward intermediates are RECOMPUTED, not stored:
+//   phase 1  cells + halo -> shared memory: clamped state, derived values, mu = lambda / area;
+//   phase 2  every face once: Fbar = len * (mu_R - mu_L); reverse-mode sweep through Riemann_2D_Roe
+//            (swe_2D_solvers.jl:4-164; branch predicates, clamps and wet flags are constants exactly as in
+//            Zygote / ForwardDiff) -> adjoints of (xi, h, u, v, s, P) on both sides, parked in shared memory;
+//            boundary faces additionally pull the ghost adjoint back through the boundary condition
+//            (bc_2D.jl:640-834) onto their internal cell;
+//   phase 3  each owned cell GATHERS the L- or R-side adjoints of its faces through the same slots used by the
+//            forward pass (the adjoint of a gather done as a gather: no atomics, deterministic), adds the adjoint
+//            of the bed-slope and Manning-friction sources, undoes the derived-variable map and the dry clamp.
+// Boundary-wide couplings (inlet conveyance split) and parameter reductions run in small follow-up kernels
+// with fixed reduction trees.
+#include "hg_device.cuh"
+
+namespace hg {
+namespace {
+using namespace dev;
+
+struct VjpArgs {
+  int32_t N, n_tiles, want_s0;
+  int64_t Ns;
+  Consts c;
+  const int32_t *tile_desc, *halo, *bface_e;
+  const uint32_t* face_lr;
+  const uint16_t* cf_idx;
+  const double *face_nx, *face_ny, *face_len;
+  const double *area, *hstill, *zb, *S0x, *S0y, *mann;
+  const int32_t *bc_type, *bc_group;
+  const double *bc_nx, *bc_ny, *bc_l23, *bc_hstill, *bc_zb, *inlet_coef, *wse;
+  const double *Q, *lam;
+  double *Qbar, *nbar, *s0bar;          // [3Ns], [Ns], [2Ns]
+  double *ent_c, *ent_n, *ent_z;        // per boundary entry: inlet coef adjoint share, n adjoint, zb adjoint
+};
+
+struct Adj {
+  double xi, h, u, v, s, P;   // adjoints of the staged per-cell variables (hu = h*u, hv = h*v folded in)
+};
+
+__device__ __forceinline__ void sabs_r(double x, double& A, double& r) {  // A = sqrt(x^2+eps), r = 1/A
+  const double y = fma(x, x, EPS);
+  r = fast_rsqrt(y);
+  A = y * r;
+  A = fma(fma(-A, A, y), 0.5 * r, A);
+}
+
+// Reverse sweep of the face flux.  (b0,b1,b2) = adjoint of the returned flux.  Outputs aL, aR.
+__device__ __forceinline__ void roe_flux_adj(Side L, Side R, const double* zbLp, const double* zbRp, double nx, double ny,
+                                             double g, double hmin, double f0b, double f1b, double f2b, Adj& aL, Adj& aR) {
+  aL = Adj{0, 0, 0, 0, 0, 0};
+  aR = Adj{0, 0, 0, 0, 0, 0};
+  const bool dryL = L.h <= hmin, dryR = R.h <= hmin;
+  int mirror = 0;  // 1: R is the mirror image of L, 2: L is the mirror image of R
+  if (dryL || dryR) {
+    if (dryL && dryR) return;                                  // zero flux
+    const double zbL = *zbLp, zbR = *zbRp;
+    if ((L.h + zbL) < (zbR + hmin) && dryR) {
+      mirror = 1;
+      R.h = L.h; R.hu = -L.hu; R.hv = -L.hv; R.u = -L.u; R.v = -L.v; R.s = L.s;
+    } else if ((R.h + zbR) < (zbL + hmin) && dryL) {
+      mirror = 2;
+      L.h = R.h; L.hu = -R.hu; L.hv = -R.hv; L.u = -R.u; L.v = -R.v; L.s = R.s;
+    } else {
+      // one-sided physical flux of the wet side W: o0 = hu nx + hv ny, o1 = hu un + p nx, o2 = hv un + p ny
+      const Side& W = dryL ? R : L;
+      Adj& aW = dryL ? aR : aL;
+      const double un = W.u * nx + W.v * ny;
+      const double hub = f0b * nx + f1b * un, hvb = f0b * ny + f2b * un;
+      const double unb = f1b * W.hu + f2b * W.hv;
+      const double pb = f1b * nx + f2b * ny;
+      aW.u = unb * nx + hub * W.h;
+      aW.v = unb * ny + hvb * W.h;
+      aW.h = pb * g * (W.h + EPS) + hub * W.u + hvb * W.v;
+      return;
+    }
+  }
+  // ---- forward recompute (same statements as dev::roe_flux)
+  const double hRoe = 0.5 * (L.h + R.h);
+  const double rs = fast_rcp(L.s + R.s);
+  const double a_ = L.s * L.u + R.s * R.u, b_ = L.s * L.v + R.s * R.v;
+  const double uRoe = a_ * rs, vRoe = b_ * rs;
+  const double un = uRoe * nx + vRoe * ny;
+  const double c2 = fma(g, hRoe, EPS);
+  const double rc = fast_rsqrt(c2);
+  const double c = c2 * rc, k = 0.5 * rc;
+  const double d1 = R.xi - L.xi, d2 = R.hu - L.hu, d3 = R.hv - L.hv;
+  const double t1 = uRoe * ny - vRoe * nx;
+  const double w1 = -t1 * d1 + ny * d2 - nx * d3;
+  const double e_ = un * d1 - (nx * d2 + ny * d3);
+  const double m = k * e_;
+  const double w2 = 0.5 * d1 + m, w3 = 0.5 * d1 - m;
+  const double l1 = un, l2 = un - c, l3 = un + c;
+  double A1, A2, A3, r1, r2, r3;
+  sabs_r(l1, A1, r1); sabs_r(l2, A2, r2); sabs_r(l3, A3, r3);
+  const double z2 = A2 * w2, z3 = A3 * w3;
+  const double zs = z2 + z3;
+  const double unL = L.u * nx + L.v * ny, unR = R.u * nx + R.v * ny;
+  // ---- reverse
+  const double b0 = 0.5 * f0b, b1 = 0.5 * f1b, b2 = 0.5 * f2b;
+  const double y1b = -b0, y2b = -b1, y3b = -b2;
+  double huLb = b0 * nx + b1 * unL, hvLb = b0 * ny + b2 * unL;
+  double huRb = b0 * nx + b1 * unR, hvRb = b0 * ny + b2 * unR;
+  const double unLb = b1 * L.hu + b2 * L.hv, unRb = b1 * R.hu + b2 * R.hv;
+  const double Pb = b1 * nx + b2 * ny;
+  double uLb = unLb * nx, vLb = unLb * ny, uRb = unRb * nx, vRb = unRb * ny;
+  const double z1b = ny * y2b - nx * y3b;
+  const double zsb = y1b + uRoe * y2b + vRoe * y3b;
+  const double zdb = nx * y2b + ny * y3b;
+  double uRoeb = zs * y2b, vRoeb = zs * y3b;
+  double cb = zdb * (z3 - z2);
+  const double z3b = zsb + c * zdb, z2b = zsb - c * zdb;
+  const double A1b = z1b * w1, w1b = z1b * A1;
+  const double A2b = z2b * w2, w2b = z2b * A2;
+  const double A3b = z3b * w3, w3b = z3b * A3;
+  const double l1b = A1b * l1 * r1, l2b = A2b * l2 * r2, l3b = A3b * l3 * r3;   // d sqrt(x^2+eps)/dx = x / sqrt(..)
+  double unb = l1b + l2b + l3b;
+  cb += l3b - l2b;
+  double d1b = 0.5 * (w2b + w3b);
+  const double mb = w2b - w3b;
+  const double kb = mb * e_, eb = mb * k;
+  unb += eb * d1;
+  d1b += eb * un;
+  double d2b = -eb * nx, d3b = -eb * ny;
+  const double t1b = -w1b * d1;
+  d1b -= w1b * t1;
+  d2b += w1b * ny;
+  d3b -= w1b * nx;
+  uRoeb += t1b * ny;
+  vRoeb -= t1b * nx;
+  huRb += d2b; huLb -= d2b; hvRb += d3b; hvLb -= d3b;
+  const double c2b = cb * k - 2.0 * kb * k * k * k;             // c = sqrt(c2), k = 1/(2 sqrt(c2))
+  const double hRoeb = g * c2b;
+  uRoeb += unb * nx;
+  vRoeb += unb * ny;
+  const double ab = uRoeb * rs, bb = vRoeb * rs;
+  const double Sb = -(uRoeb * a_ + vRoeb * b_) * rs * rs;
+  const double sLb = ab * L.u + bb * L.v + Sb, sRb = ab * R.u + bb * R.v + Sb;
+  uLb += ab * L.s; vLb += bb * L.s; uRb += ab * R.s; vRb += bb * R.s;
+  // ---- fold hu = h*u, hv = h*v into (h, u, v)
+  Adj tL, tR;
+  tL.xi = -d1b; tL.P = Pb; tL.s = sLb;
+  tL.u = uLb + huLb * L.h; tL.v = vLb + hvLb * L.h; tL.h = 0.5 * hRoeb + huLb * L.u + hvLb * L.v;
+  tR.xi = d1b; tR.P = Pb; tR.s = sRb;
+  tR.u = uRb + huRb * R.h; tR.v = vRb + hvRb * R.h; tR.h = 0.5 * hRoeb + huRb * R.u + hvRb * R.v;
+  if (mirror == 0) { aL = tL; aR = tR; }
+  else if (mirror == 1) {  // R' = (L.h, -L.u, -L.v, L.s); xi_R, P_R stay R's own (swe_2D_solvers.jl:34-36)
+    aL = tL; aL.h += tR.h; aL.u -= tR.u; aL.v -= tR.v; aL.s += tR.s;
+    aR.xi = tR.xi; aR.P = tR.P;
+  } else {                 // :49-51
+    aR = tR; aR.h += tL.h; aR.u -= tL.u; aR.v -= tL.v; aR.s += tL.s;
+    aL.xi = tL.xi; aL.P = tL.P;
+  }
+}
+
+template <class Cfg>
+struct __align__(16) VjpSmem {
+  uint64_t bar[2];
+  double xi[Cfg::ML], h[Cfg::ML], zb[Cfg::ML], u[Cfg::ML], v[Cfg::ML], s[Cfg::ML], P[Cfg::ML];
+  double m0[Cfg::ML], m1[Cfg::ML], m2[Cfg::ML];           // mu = lambda / area (lambda itself on arrival)
+  double o[12][Cfg::MF];                                  // rows 0..2: nx, ny, len on arrival; then face adjoints
+  double area[Cfg::T], mann[Cfg::T], sx[Cfg::T], sy[Cfg::T], hst[Cfg::T];
+  uint32_t lr[Cfg::MF];
+  uint16_t cf[Cfg::T * Cfg::NF];
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) k_fused_vjp(const __grid_constant__ VjpArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  VjpSmem<Cfg>& sm = *reinterpret_cast<VjpSmem<Cfg>*>(smraw);
+  constexpr int T = Cfg::T, NF = Cfg::NF, kThreads = Cfg::THREADS;
+
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc));
+  const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 1);
+  const int4 d2 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 2);
+  const int32_t c0 = d0.x, nc = d0.y, hp = d0.z, nh = d0.w;
+  const int32_t fp = d1.x, nf = d1.y, nfp = d1.z;
+  const int32_t nint = d2.y, bfp = d2.z;
+  const int32_t ncp = (nc + 1) & ~1;
+  const double g = a.c.g, hs = a.c.h_small;
+  const int64_t Ns = a.Ns;
+
+  if (tid == 0) mbar_init(sm.bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t cb = (uint32_t)ncp * 8u, fb = (uint32_t)nfp * 8u;
+    mbar_expect_tx(sm.bar, 12u * cb + 3u * fb + (uint32_t)nfp * 4u + (uint32_t)(T * NF) * 2u);
+    bulk_g2s(sm.xi, a.Q + c0, cb, sm.bar);
+    bulk_g2s(sm.u, a.Q + Ns + c0, cb, sm.bar);
+    bulk_g2s(sm.v, a.Q + 2 * Ns + c0, cb, sm.bar);
+    bulk_g2s(sm.hst, a.hstill + c0, cb, sm.bar);
+    bulk_g2s(sm.zb, a.zb + c0, cb, sm.bar);
+    bulk_g2s(sm.m0, a.lam + c0, cb, sm.bar);
+    bulk_g2s(sm.m1, a.lam + Ns + c0, cb, sm.bar);
+    bulk_g2s(sm.m2, a.lam + 2 * Ns + c0, cb, sm.bar);
+    bulk_g2s(sm.o[0], a.face_nx + fp, fb, sm.bar);
+    bulk_g2s(sm.o[1], a.face_ny + fp, fb, sm.bar);
+    bulk_g2s(sm.o[2], a.face_len + fp, fb, sm.bar);
+    bulk_g2s(sm.lr, a.face_lr + fp, (uint32_t)nfp * 4u, sm.bar);
+    bulk_g2s(sm.area, a.area + c0, cb, sm.bar);
+    bulk_g2s(sm.mann, a.mann + c0, cb, sm.bar);
+    bulk_g2s(sm.sx, a.S0x + c0, cb, sm.bar);
+    bulk_g2s(sm.sy, a.S0y + c0, cb, sm.bar);
+    bulk_g2s(sm.cf, a.cf_idx + (size_t)t * (T * NF), (uint32_t)(T * NF) * 2u, sm.bar);
+  }
+  // halo cells: state + lambda/area
+  for (int32_t k = tid; k < nh; k += kThreads) {
+    const int32_t gi = __ldg(a.halo + hp + k);
+    Side s;
+    s.xi = a.Q[gi];
+    const double qx = a.Q[Ns + gi], qy = a.Q[2 * Ns + gi];
+    const double hst = a.hstill[gi];
+    const double rA = fast_rcp(a.area[gi]);
+    const double l0 = a.lam[gi], l1 = a.lam[Ns + gi], l2 = a.lam[2 * Ns + gi];
+    s.zb = a.zb[gi];
+    const double h = s.xi + hst;
+    const bool dry = h <= hs;
+    s.h = dry ? hs : h; s.hu = dry ? 0.0 : qx; s.hv = dry ? 0.0 : qy;
+    derive(s, hst, g);
+    const int32_t l = ncp + k;
+    sm.xi[l] = s.xi; sm.h[l] = s.h; sm.zb[l] = s.zb; sm.u[l] = s.u; sm.v[l] = s.v; sm.s[l] = s.s; sm.P[l] = s.P;
+    sm.m0[l] = l0 * rA; sm.m1[l] = l1 * rA; sm.m2[l] = l2 * rA;
+  }
+  mbar_wait(sm.bar, 0);
+
+  // ---- phase 1: owned cells.  lambda stays in registers for phase 3 (<= 2 cells per thread would do, but keep it
+  // simple: re-read from global in phase 3 is avoided by storing raw q and lambda back-computed: lambda = mu * area)
+  for (int32_t l = tid; l < nc; l += kThreads) {
+    Side s;
+    s.xi = sm.xi[l];
+    const double hst = sm.hst[l];
+    const double h = s.xi + hst;
+    const bool dry = h <= hs;
+    s.h = dry ? hs : h; s.hu = dry ? 0.0 : sm.u[l]; s.hv = dry ? 0.0 : sm.v[l];
+    derive(s, hst, g);
+    sm.h[l] = s.h; sm.u[l] = s.u; sm.v[l] = s.v; sm.s[l] = s.s; sm.P[l] = s.P;
+    const double rA = fast_rcp(sm.area[l]);
+    sm.m0[l] *= rA; sm.m1[l] *= rA; sm.m2[l] *= rA;
+  }
+  __syncthreads();
+
+  // ---- phase 2: face adjoints
+  for (int32_t f = tid; f < nf; f += kThreads) {
+    const uint32_t lr = sm.lr[f];
+    const int32_t lL = lr & 0xFFFFu, lR = lr >> 16;
+    const double nx = sm.o[0][f], ny = sm.o[1][f], len = sm.o[2][f];
+    Side L, R;
+    L.xi = sm.xi[lL]; L.h = sm.h[lL]; L.u = sm.u[lL]; L.v = sm.v[lL]; L.s = sm.s[lL]; L.P = sm.P[lL];
+    L.hu = L.h * L.u; L.hv = L.h * L.v;
+    double f0b = -sm.m0[lL], f1b = -sm.m1[lL], f2b = -sm.m2[lL];
+    Adj aL, aR;
+    if (f < nint) {
+      R.xi = sm.xi[lR]; R.h = sm.h[lR]; R.u = sm.u[lR]; R.v = sm.v[lR]; R.s = sm.s[lR]; R.P = sm.P[lR];
+      R.hu = R.h * R.u; R.hv = R.h * R.v;
+      f0b += sm.m0[lR]; f1b += sm.m1[lR]; f2b += sm.m2[lR];
+      roe_flux_adj(L, R, &sm.zb[lL], &sm.zb[lR], nx, ny, g, hs, f0b * len, f1b * len, f2b * len, aL, aR);
+    } else {
+      // boundary face: rebuild the ghost state (bc_2D.jl:640-834), sweep, pull the ghost adjoint back
+      const int32_t e = __ldg(a.bface_e + bfp + (f - nint));
+      const int32_t ty = a.bc_type[e], kgrp = a.bc_group[e];
+      const double bnx = a.bc_nx[e], bny = a.bc_ny[e];
+      const double zbc = sm.zb[lL];
+      double vn = 0.0, wet = 0.0, mannc = 1.0;
+      bool exit_free = false;
+      if (ty == BC_INLETQ) {
+        wet = L.h > hs ? 1.0 : 0.0;
+        mannc = sm.mann[lL];
+        vn = a.inlet_coef[kgrp] * a.bc_l23[e] / mannc;
+        R.h = L.h; R.hu = -L.h * vn * bnx * wet; R.hv = -L.h * vn * bny * wet;
+      } else if (ty == BC_EXITH) {
+        const double hg = a.wse[kgrp] - zbc;
+        exit_free = hg > hs;                       // max(h_small, .) passes the derivative only when not clamped
+        R.h = exit_free ? hg : hs; R.hu = L.hu; R.hv = L.hv;
+      } else if (ty == BC_WALL) {
+        R.h = L.h; R.hu = -L.hu; R.hv = -L.hv;
+      } else {
+        const double vdn = L.hu * bnx + L.hv * bny;
+        R.h = L.h; R.hu = L.hu - 2.0 * vdn * bnx; R.hv = L.hv - 2.0 * vdn * bny;
+      }
+      const double hstg = a.bc_hstill[e];
+      R.xi = R.h - hstg;
+      const double zbg = a.bc_zb[e];
+      derive(R, hstg, g);
+      roe_flux_adj(L, R, &zbc, &zbg, nx, ny, g, hs, f0b * len, f1b * len, f2b * len, aL, aR);
+      // ghost (xi, h, u, v, s, P) adjoints -> ghost primitives (h_g, hu_g, hv_g); xi_g = h_g - hstill_g
+      const double rhg = fast_rcp(R.h);
+      const double hub = aR.u * rhg, hvb = aR.v * rhg;
+      const double xib = aR.xi + aR.P * g * (R.xi + EPS + hstg);
+      const double hgb = aR.h - (aR.u * R.u + aR.v * R.v) * rhg + aR.s * 0.5 * fast_rcp(R.s) + xib;
+      // boundary condition transposed: adjoints of the internal cell's clamped (h, hu, hv)
+      double hcb = 0.0, hucb = 0.0, hvcb = 0.0, ec = 0.0, en = 0.0, ez = 0.0;
+      if (ty == BC_INLETQ) {
+        const double G = -(hub * bnx + hvb * bny) * wet;   // d(hu_g, hv_g) = -n wet d(h_c vn)
+        hcb = hgb + G * vn;
+        en = -G * L.h * vn / mannc;                        // vn = coef L^(2/3) / n_c
+        ec = G * L.h * a.bc_l23[e] / mannc;                // share of the adjoint of coef_k = Q_k / A_k
+      } else if (ty == BC_EXITH) {
+        hucb = hub; hvcb = hvb;
+        ez = exit_free ? -hgb : 0.0;                       // h_g = WSE - zb_c
+      } else if (ty == BC_WALL) {
+        hcb = hgb; hucb = -hub; hvcb = -hvb;
+      } else {
+        const double dn = hub * bnx + hvb * bny;
+        hcb = hgb; hucb = hub - 2.0 * dn * bnx; hvcb = hvb - 2.0 * dn * bny;
+      }
+      a.ent_c[e] = ec; a.ent_n[e] = en; a.ent_z[e] = ez;
+      aL.u += hucb * L.h; aL.v += hvcb * L.h; aL.h += hcb + hucb * L.u + hvcb * L.v;
+      aR = Adj{0, 0, 0, 0, 0, 0};
+    }
+    sm.o[0][f] = aL.xi; sm.o[1][f] = aL.h; sm.o[2][f] = aL.u; sm.o[3][f] = aL.v; sm.o[4][f] = aL.s; sm.o[5][f] = aL.P;
+    sm.o[6][f] = aR.xi; sm.o[7][f] = aR.h; sm.o[8][f] = aR.u; sm.o[9][f] = aR.v; sm.o[10][f] = aR.s; sm.o[11][f] = aR.P;
+  }
+  if (tid < 12) sm.o[tid][nfp] = 0.0;   // the zero slot of unused cf entries
+  __syncthreads();
+
+  // ---- phase 3: per-cell gather of face adjoints + source adjoint + undo derived map and clamp
+  const double kfr = g / (a.c.k_n * a.c.k_n);
+  for (int32_t l = tid; l < nc; l += kThreads) {
+    const int32_t gi = c0 + l;
+    uint16_t slot[NF];
+    if constexpr (NF == 4) {
+      const uint2 w = *reinterpret_cast<const uint2*>(&sm.cf[l * 4]);
+      slot[0] = (uint16_t)(w.x & 0xFFFFu); slot[1] = (uint16_t)(w.x >> 16);
+      slot[2] = (uint16_t)(w.y & 0xFFFFu); slot[3] = (uint16_t)(w.y >> 16);
+    } else {
+      const uint4 w = *reinterpret_cast<const uint4*>(&sm.cf[l * 8]);
+      slot[0] = (uint16_t)(w.x & 0xFFFFu); slot[1] = (uint16_t)(w.x >> 16);
+      slot[2] = (uint16_t)(w.y & 0xFFFFu); slot[3] = (uint16_t)(w.y >> 16);
+      slot[4] = (uint16_t)(w.z & 0xFFFFu); slot[5] = (uint16_t)(w.z >> 16);
+      slot[6] = (uint16_t)(w.w & 0xFFFFu); slot[7] = (uint16_t)(w.w >> 16);
+    }
+    double xib = 0.0, hb = 0.0, ub = 0.0, vb = 0.0, sb = 0.0, Pb = 0.0;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      const int32_t f = slot[j] & 0x7FFF;
+      const int side = (slot[j] & 0x8000) ? 6 : 0;
+      xib += sm.o[side + 0][f]; hb += sm.o[side + 1][f]; ub += sm.o[side + 2][f];
+      vb += sm.o[side + 3][f]; sb += sm.o[side + 4][f]; Pb += sm.o[side + 5][f];
+    }
+    const double xi = sm.xi[l], h = sm.h[l], u = sm.u[l], v = sm.v[l], s = sm.s[l], hst = sm.hst[l];
+    const double A = sm.area[l], n = sm.mann[l];
+    const double lam1 = sm.m1[l] * A, lam2 = sm.m2[l] * A;   // mu * area = lambda
+    const double rh = fast_rcp(h);
+    // derived map: u = hu/h, v = hv/h, s = sqrt(h+eps), P(xi)
+    double qxb = ub * rh, qyb = vb * rh;
+    hb += -(ub * u + vb * v) * rh + sb * 0.5 * fast_rcp(s);
+    xib += Pb * g * (xi + EPS + hst);
+    // sources (wet cells): r1 += g xi S0x - C m qx,  C = g n^2/k_n^2 (h+hs)^(-7/3),  m = sqrt(qx^2+qy^2+eps)
+    const bool wet = h > hs;
+    double nb = 0.0, s0xb = 0.0, s0yb = 0.0;
+    if (wet) {
+      const double qx = h * u, qy = h * v;
+      const double y = fma(qx, qx, fma(qy, qy, EPS));
+      const double rm = fast_rsqrt(y);
+      const double mag = y * rm;
+      const double C = kfr * n * n * pow_m73(h + hs);
+      const double fxb = -lam1, fyb = -lam2;
+      const double cross = C * qx * qy * rm;
+      qxb += fxb * (C * mag + C * qx * qx * rm) + fyb * cross;
+      qyb += fyb * (C * mag + C * qy * qy * rm) + fxb * cross;
+      const double D = (fxb * qx + fyb * qy) * C * mag;      // fxb*fx + fyb*fy
+      hb += -(7.0 / 3.0) * D * fast_rcp(h + hs);
+      nb = 2.0 * D * fast_rcp(n);
+      xib += g * (sm.sx[l] * lam1 + sm.sy[l] * lam2);
+      s0xb = g * xi * lam1; s0yb = g * xi * lam2;
+    }
+    // dry clamp (semi_discretize_swe_2D.jl:104-106): clamped h, q are constants; xi itself is never clamped
+    const bool dry = (xi + hst) <= hs;
+    a.Qbar[gi] = dry ? xib : xib + hb;
+    a.Qbar[Ns + gi] = dry ? 0.0 : qxb;
+    a.Qbar[2 * Ns + gi] = dry ? 0.0 : qyb;
+    a.nbar[gi] = nb;
+    if (a.want_s0) { a.s0bar[gi] = s0xb; a.s0bar[Ns + gi] = s0yb; }
+  }
+}
+
+// ---------------------------------------------------------------- boundary-wide couplings of the inlet-q split
+// coef_k = Q_k / A_k,  A_k = sum_e L^(5/3) h_c / n_c wet  (bc_2D.jl:674-691).  One CTA per inlet boundary:
+// coefbar_k = sum_e ent_c[e] (fixed tree), Qbar_k = coefbar_k / A_k, Abar_k = -coefbar_k coef_k / A_k; then every
+// wet entry receives  hbar_c += Abar L^(5/3)/n_c  and  nbar_c -= Abar L^(5/3) h_c / n_c^2  (stored per entry).
+__global__ void __launch_bounds__(256) k_inlet_adj(Consts c, const int32_t* inlet_ptr, const int32_t* bc_cell,
+                                                   const double* bc_l53, const double* Q, const double* hstill,
+                                                   const double* mann, const double* Atot, const double* coef,
+                                                   const double* ent_c, double* ent_h, double* ent_n, double* Qinbar) {
+  __shared__ double red[256];
+  __shared__ double sAbar;
+  const int k = blockIdx.x;
+  double acc = 0.0;
+  for (int32_t e = inlet_ptr[k] + threadIdx.x; e < inlet_ptr[k + 1]; e += 256) acc += ent_c[e];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double cbar = red[0];
+    const double rA = 1.0 / Atot[k];              // coef = Q / A
+    Qinbar[k] = cbar * rA;                        // d coef / d Q = 1 / A
+    sAbar = -cbar * coef[k] * rA;                 // d coef / d A = -Q / A^2
+  }
+  __syncthreads();
+  const double Abar = sAbar;
+  for (int32_t e = inlet_ptr[k] + threadIdx.x; e < inlet_ptr[k + 1]; e += 256) {
+    const int32_t ci = bc_cell[e];
+    const double h = Q[ci] + hstill[ci];
+    const bool wet = h > c.h_small;
+    const double n = mann[ci];
+    ent_h[e] = wet ? Abar * bc_l53[e] / n : 0.0;
+    ent_n[e] += wet ? -Abar * bc_l53[e] * h / (n * n) : 0.0;
+  }
+}
+
+// One thread per boundary-adjacent cell: add its entries' contributions in fixed order (deterministic).
+__global__ void k_bc_scatter(int32_t nbcell, const int32_t* __restrict__ bcell, const int32_t* __restrict__ bcell_ptr,
+                             const int32_t* __restrict__ bcell_ent, const int32_t* __restrict__ bc_type,
+                             const double* __restrict__ ent_h, const double* __restrict__ ent_n, double* Qbar, double* nbar) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nbcell) return;
+  const int32_t c = bcell[i];
+  double hb = 0.0, nb = 0.0;
+  for (int32_t k = bcell_ptr[i]; k < bcell_ptr[i + 1]; ++k) {
+    const int32_t e = bcell_ent[k];
+    if (bc_type[e] == BC_INLETQ) { hb += ent_h[e]; nb += ent_n[e]; }
+  }
+  Qbar[c] += hb;   // inlet cells that receive this are wet, hence unclamped: xi_bar += h_bar
+  nbar[c] += nb;
+}
+
+// pbar_z = sum_{cells of zone z} nbar  (process_ManningN_2D.jl:88 transposed): two fixed-shape stages
+constexpr int kZoneBlock = 256, kZoneChunk = 4096;
+__global__ void __launch_bounds__(kZoneBlock) k_zone_partial(int32_t N, int32_t n_mat, const int32_t* __restrict__ matid,
+                                                             const double* __restrict__ nbar, double* __restrict__ part) {
+  extern __shared__ double zs[];   // [kZoneBlock][n_mat] would be too big for many zones: loop zones instead
+  const int32_t b0 = blockIdx.x * kZoneChunk;
+  for (int32_t z = 0; z < n_mat; ++z) {
+    double acc = 0.0;
+    for (int32_t i = b0 + threadIdx.x; i < min(N, b0 + kZoneChunk); i += kZoneBlock)
+      if (matid[i] == z) acc += nbar[i];
+    zs[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = kZoneBlock / 2; s > 0; s >>= 1) {
+      if (threadIdx.x < s) zs[threadIdx.x] += zs[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * n_mat + z] = zs[0];
+    __syncthreads();
+  }
+}
+__global__ void k_zone_final(int32_t nblocks, int32_t n_mat, const double* __restrict__ part, double* __restrict__ pbar) {
+  const int32_t z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= n_mat) return;
+  double acc = 0.0;
+  for (int32_t b = 0; b < nblocks; ++b) acc += part[(size_t)b * n_mat + z];
+  pbar[z] = acc;
+}
+
+// zbar (reference order) = (update_bed_data)^T S0bar + exit-h entries.  Transposed Green-Gauss as a gather:
+// cell i collects, per face, its own term and the neighbour's term through the shared face value
+// zb_f = (zb_i + zb_nb)/2 (interior) or zb_i (boundary)  (fvm_schemes_2D.jl:89-105, 133-167).
+__global__ void k_zb_bar(int32_t N, int64_t Ns, const int32_t* __restrict__ iperm, const int32_t* __restrict__ cf_ptr,
+                         const int32_t* __restrict__ cf_nb, const int32_t* __restrict__ cf_rev,
+                         const double* __restrict__ cf_nx, const double* __restrict__ cf_ny,
+                         const double* __restrict__ cf_len, const double* __restrict__ area_ref,
+                         const double* __restrict__ s0bar, double* __restrict__ zbar) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const int32_t i = iperm[r];
+  const double gx = -s0bar[i] / area_ref[r], gy = -s0bar[Ns + i] / area_ref[r];   // S0 = -1 * (sum / A)
+  double acc = 0.0;
+  for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
+    const int32_t nb = cf_nb[k];
+    const double own = (cf_nx[k] * gx + cf_ny[k] * gy) * cf_len[k];
+    if (nb >= N) { acc += own; continue; }
+    const int32_t j = iperm[nb], kk = cf_rev[k];
+    const double hx = -s0bar[j] / area_ref[nb], hy = -s0bar[Ns + j] / area_ref[nb];
+    acc += 0.5 * (own + (cf_nx[kk] * hx + cf_ny[kk] * hy) * cf_len[kk]);
+  }
+  zbar[r] = acc;
+}
+__global__ void k_zb_bar_exit(int32_t nbcell, const int32_t* __restrict__ bcell_ref, const int32_t* __restrict__ bcell_ptr,
+                              const int32_t* __restrict__ bcell_ent, const int32_t* __restrict__ bc_type,
+                              const double* __restrict__ ent_z, double* __restrict__ zbar) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nbcell) return;
+  double acc = 0.0;
+  for (int32_t k = bcell_ptr[i]; k < bcell_ptr[i + 1]; ++k) {
+    const int32_t e = bcell_ent[k];
+    if (bc_type[e] == BC_EXITH) acc += ent_z[e];
+  }
+  zbar[bcell_ref[i]] += acc;
+}
+
+__global__ void k_gather1(int32_t N, const int32_t* __restrict__ map, const double* __restrict__ src, double* __restrict__ dst) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) dst[i] = src[map[i]];
+}
+
+}  // namespace
+
+int fused_vjp_smem_bytes(int cfg_id) {
+  switch (cfg_id) {
+#define X(id, T, ML, MF, NF, TH, MB) case id: return (int)sizeof(VjpSmem<TileCfg<T, ML, MF, NF, TH, MB>>);
+    HG_TILE_CONFIGS(X)
+#undef X
+  }
+  return 0;
+}
+
+int fused_vjp_prepare(hg_ctx* ctx, int cfg_id) {
+  cudaError_t e = cudaSuccess;
+  switch (cfg_id) {
+#define X(id, T, ML, MF, NF, TH, MB)                                                                              \
+  case id: {                                                                                                      \
+    using C = TileCfg<T, ML, MF, NF, TH, MB>;                                                                     \
+    if (sizeof(VjpSmem<C>) > 227 * 1024) { ctx->err = "VJP tile does not fit shared memory"; return HG_ERR_ARG; } \
+    e = cudaFuncSetAttribute(k_fused_vjp<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VjpSmem<C>)); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_vjp<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+  } break;
+    HG_TILE_CONFIGS(X)
+#undef X
+  }
+  if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute(vjp): ") + cudaGetErrorString(e); return HG_ERR_CUDA; }
+  return HG_OK;
+}
+
+// Qbar (internal order, [3Ns]) and the parameter adjoint for the active parameter (pbar, device).
+int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar) {
+  FusedDev& d = ctx->fd;
+  const FusedHost& fh = ctx->fh;
+  const int th = 256;
+  if (ctx->n_inletq > 0) fused_inlet_coef(ctx, d_Q);
+  VjpArgs a;
+  a.N = (int32_t)ctx->N; a.n_tiles = fh.n_tiles; a.want_s0 = ctx->active == HG_PARAM_ZB ? 1 : 0;
+  a.Ns = fh.Ns; a.c = ctx->c;
+  a.tile_desc = d.tile_desc.p; a.halo = d.halo.p; a.bface_e = d.bface_e.p; a.face_lr = d.face_lr.p;
+  a.cf_idx = d.cf_idx.p; a.face_nx = d.face_nx.p; a.face_ny = d.face_ny.p; a.face_len = d.face_len.p;
+  a.area = d.area.p; a.hstill = d.hstill.p; a.zb = d.zb.p; a.S0x = d.S0x.p; a.S0y = d.S0y.p; a.mann = d.mann.p;
+  a.bc_type = d.bc_type.p; a.bc_group = d.bc_group.p; a.bc_nx = d.bc_nx.p; a.bc_ny = d.bc_ny.p;
+  a.bc_l23 = d.bc_l23.p; a.bc_hstill = d.bc_hstill.p; a.bc_zb = d.bc_zb.p; a.inlet_coef = d.inlet_coef.p;
+  a.wse = d.wse.p; a.Q = d_Q; a.lam = d_lam; a.Qbar = d_Qbar; a.nbar = d.nbar.p; a.s0bar = d.s0bar.p;
+  a.ent_c = d.ent_c.p; a.ent_n = d.ent_n.p; a.ent_z = d.ent_z.p;
+  const unsigned grid = (unsigned)fh.n_tiles;
+  switch (cfg_id) {
+#define X(id, T, ML, MF, NF, TH, MB)                                                        \
+  case id: {                                                                                \
+    using C = TileCfg<T, ML, MF, NF, TH, MB>;                                               \
+    k_fused_vjp<C><<<grid, C::THREADS, sizeof(VjpSmem<C>), ctx->stream>>>(a);               \
+  } break;
+    HG_TILE_CONFIGS(X)
+#undef X
+    default: ctx->err = "no tile configuration"; return HG_ERR_ARG;
+  }
+  ctx->launches++;
+  if (ctx->n_inletq > 0) {
+    k_inlet_adj<<<(unsigned)ctx->n_inletq, 256, 0, ctx->stream>>>(ctx->c, d.inlet_ptr.p, d.bc_cell.p, d.bc_l53.p, d_Q,
+                                                                 d.hstill.p, d.mann.p, d.inlet_A.p, d.inlet_coef.p, d.ent_c.p,
+                                                                 d.ent_h.p, d.ent_n.p, d.Qinbar.p);
+    ctx->launches++;
+    if (ctx->nbcell > 0) {
+      k_bc_scatter<<<(unsigned)((ctx->nbcell + th - 1) / th), th, 0, ctx->stream>>>((int32_t)ctx->nbcell, d.bcell.p, d.bcell_ptr.p,
+                                                                                 d.bcell_ent.p, d.bc_type.p, d.ent_h.p,
+                                                                                 d.ent_n.p, d_Qbar, d.nbar.p);
+      ctx->launches++;
+    }
+  }
+  // ---- parameter adjoints
+  if (ctx->active == HG_PARAM_MANNING) {
+    const int nblocks = (int)((ctx->N + kZoneChunk - 1) / kZoneChunk);
+    if (d.zone_part.n < (size_t)nblocks * ctx->n_mat) {
+      if (d.zone_part.alloc((size_t)nblocks * ctx->n_mat) != cudaSuccess) { ctx->err = "cudaMalloc(zone_part)"; return HG_ERR_CUDA; }
+    }
+    k_zone_partial<<<nblocks, kZoneBlock, kZoneBlock * sizeof(double), ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid.p,
+                                                                                      d.nbar.p, d.zone_part.p);
+    k_zone_final<<<(unsigned)((ctx->n_mat + 63) / 64), 64, 0, ctx->stream>>>(nblocks, (int32_t)ctx->n_mat, d.zone_part.p, d.pbar.p);
+    ctx->launches += 2;
+  } else if (ctx->active == HG_PARAM_ZB) {
+    PlainDev& p = ctx->pd;
+    k_zb_bar<<<(unsigned)((ctx->N + th - 1) / th), th, 0, ctx->stream>>>((int32_t)ctx->N, fh.Ns, d.iperm.p, p.cf_ptr.p, p.cf_nb.p,
+                                                                       p.cf_rev.p, p.cf_nx.p, p.cf_ny.p, p.cf_len.p, p.area.p,
+                                                                       d.s0bar.p, d.pbar.p);
+    ctx->launches++;
+    if (ctx->nbcell > 0) {
+      k_zb_bar_exit<<<(unsigned)((ctx->nbcell + th - 1) / th), th, 0, ctx->stream>>>((int32_t)ctx->nbcell, d.bcell_ref.p,
+                                                                                  d.bcell_ptr.p, d.bcell_ent.p, d.bc_type.p,
+                                                                                  d.ent_z.p, d.pbar.p);
+      ctx->launches++;
+    }
+  } else if (ctx->active == HG_PARAM_Q) {
+    cudaMemcpyAsync(d.pbar.p, d.Qinbar.p, ctx->n_inletq * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = std::string("fused_vjp launch: ") + cudaGetErrorString(e); return HG_ERR_CUDA; }
+  return HG_OK;
+}
+
+// ncell_bar in reference order (UDE hook): dst[r] = nbar[iperm[r]]
+int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst) {
+  const int th = 256;
+  k_gather1<<<(unsigned)((ctx->N + th - 1) / th), th, 0, ctx->stream>>>((int32_t)ctx->N, ctx->fd.iperm.p, ctx->fd.nbar.p, d_dst);
+  ctx->launches++;
+  return cudaGetLastError() == cudaSuccess ? HG_OK : HG_ERR_CUDA;
+}
+
+}  // namespace hg
