@@ -192,16 +192,34 @@ def main():
         N_total = int(tn.item())
     else:
         N_total = N
-    ms_per_step = ms / args.steps
+    # ---- the adjoint of the same call (hand-written VJP kernel), same protocol
+    ctx.time_vjp(max(args.warmup, 3))
+    barrier()
+    l1 = ctx.kernel_launches()
+    ms_vjp = ctx.time_vjp(args.steps)
+    barrier()
+    launches += ctx.kernel_launches() - l1
+    if dist is not None:
+        tv = torch.tensor([ms_vjp], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        ms_vjp = float(tv.item())
+    ms_rhs_step = ms / args.steps
+    ms_vjp_step = ms_vjp / args.steps
+    ms_per_step = ms_rhs_step + ms_vjp_step
     value = N_total / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (k_fused_rhs): algorithmic bytes / measured launch time
     peak, peak_src = measured_peak()
     abytes = algorithmic_bytes(N, F, st["sum_cell_faces"])
-    achieved = abytes / (ms_per_step * 1e-3) / 1e9
+    achieved = abytes / (ms_rhs_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "k_fused_rhs", "algorithmic_bytes_per_launch": abytes,
-                "bytes_per_cell": abytes / N, "peak_source": peak_src}
+                "bytes_per_cell": abytes / N, "peak_source": peak_src, "ms_per_launch": ms_rhs_step}
+    vbytes = abytes + 32 * N          # RHS inputs re-read + lambda (24 B) + Qbar (24 B) + nbar (8 B) - dQ (24 B)
+    vach = vbytes / (ms_vjp_step * 1e-3) / 1e9
+    roofline_vjp = {"bound": "hbm", "achieved": vach, "peak": peak, "unit": "GB/s", "frac": vach / peak, "traffic": None,
+                    "kernel": "k_fused_vjp", "algorithmic_bytes_per_launch": vbytes, "bytes_per_cell": vbytes / N,
+                    "ms_per_launch": ms_vjp_step}
 
     # ---- end to end through the host-buffer ABI call (pinned host memory, H2D + D2H in the timed region)
     hQ = torch.empty(3 * N, dtype=torch.float64).pin_memory()
@@ -233,11 +251,14 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"C3 synthetic {N / 1e6:.1f}M-cell meandering river per GPU (mixed tri/quad, 6 Manning "
-                                       "zones, inlet-Q/exit-H/walls); step = one fused fp64 RHS of the resident state",
+                                       "zones, inlet-Q/exit-H/walls); step = one fused fp64 RHS + one hand-written VJP of the resident state",
                            "cells_per_gpu": N, "faces_per_gpu": F, "tile_cells": args.tile, "n_tiles": st["n_tiles"],
                            "l2": "inputs (state + mesh tables >> 126 MB L2) larger than L2, no flush needed",
                            "parallelism": f"rcb-slab x{world}"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "roofline": roofline, "roofline_vjp": roofline_vjp,
+                "rhs": {"value": N_total / (ms_rhs_step * 1e-3), "unit": UNIT, "ms": ms_rhs_step},
+                "vjp": {"value": N_total / (ms_vjp_step * 1e-3), "unit": UNIT, "ms": ms_vjp_step},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -28,7 +28,8 @@ class MeshDesc(C.Structure):
 class BcDesc(C.Structure):
     _fields_ = [("n_inletq", C.c_int64), ("n_exith", C.c_int64), ("n_wall", C.c_int64), ("n_symm", C.c_int64),
                 ("bc_ptr", c_i64p), ("ghost_ids", c_i64p), ("internal_cells", c_i64p),
-                ("outward_normals", c_f64p), ("face_lengths", c_f64p)]
+                ("outward_normals", c_f64p), ("face_lengths", c_f64p),
+                ("n_halo", C.c_int64), ("halo_flip", c_u8p), ("halo_area", c_f64p)]
 
 
 class FieldsDesc(C.Structure):
@@ -65,6 +66,14 @@ SYMBOLS = {
     "hg_step_euler": (C.c_int, [_vp, C.c_double, C.c_int64]),
     "hg_custom_ode_solve": (C.c_int, [_vp, c_f64p, c_f64p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double,
                                       c_f64p, C.c_int64, c_i64p]),
+    "hg_halo_info": (C.c_int, [_vp, c_i64p, c_i64p]),
+    "hg_halo_counts": (C.c_int, [_vp, c_i64p]),
+    "hg_halo_buffers": (C.c_int, [_vp, C.POINTER(c_f64p), C.POINTER(c_f64p), c_i64p]),
+    "hg_halo_pack": (C.c_int, [_vp, C.c_int32]),
+    "hg_set_stream": (C.c_int, [_vp, _vp]),
+    "hg_set_lambda": (C.c_int, [_vp, c_f64p]),
+    "hg_vjp_resident": (C.c_int, [_vp]),
+    "hg_get_vjp": (C.c_int, [_vp, c_f64p, c_f64p, c_f64p]),
     "hg_time_rhs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "hg_time_vjp": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_float)]),
     "hg_kernel_launches": (C.c_int64, [_vp]),

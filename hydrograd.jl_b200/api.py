@@ -51,9 +51,13 @@ def _descs(f: dict):
                       _p(keep["cell_neighbors"], L.c_i64p), _p(keep["cell_normals"]),
                       _p(keep["face_is_boundary"], L.c_u8p), _p(keep["face_lengths"]), _p(keep["cell_areas"]),
                       _p(keep["cell_centroids"]))
+    n_halo = int(f.get("n_halo", 0))
+    keep["halo_flip"] = np.ascontiguousarray(f["halo_flip"], dtype=np.uint8) if n_halo else None
+    keep["halo_area"] = _f64(f["halo_area"]) if n_halo else None
     bc = L.BcDesc(int(f["n_inletq"]), int(f["n_exith"]), int(f["n_wall"]), int(f["n_symm"]),
                   _p(keep["bc_ptr"], L.c_i64p), _p(keep["bc_ghost_ids"], L.c_i64p),
-                  _p(keep["bc_internal_cells"], L.c_i64p), _p(keep["bc_normals"]), _p(keep["bc_lengths"]))
+                  _p(keep["bc_internal_cells"], L.c_i64p), _p(keep["bc_normals"]), _p(keep["bc_lengths"]),
+                  n_halo, _p(keep["halo_flip"], L.c_u8p), _p(keep["halo_area"]))
     keep["solver"] = f.get("riemann_solver", "Roe").encode()
     fields = L.FieldsDesc(float(f["g"]), float(f["k_n"]), float(f["h_small"]), keep["solver"],
                           _p(keep["hstill"]), _p(keep["hstill_ghost"]), _p(keep["zb_cells"]), _p(keep["zb_ghost"]),
@@ -164,6 +168,40 @@ class Context:
         arrs = [None if a is None else _f64(a)
                 for a in (ManningN_cells, zb_cells, zb_ghost, S0_cells, inletQ_TotalQ, exitH_WSE)]
         self._ck(self.lib.hg_set_fields(self._h, *[_p(a) for a in arrs]))
+
+    # ---------------------------------------------------------------- adjoint on the resident state
+    def set_lambda(self, lam):
+        self._ck(self.lib.hg_set_lambda(self._h, _p(_f64(lam))))
+
+    def vjp_resident(self):
+        self._ck(self.lib.hg_vjp_resident(self._h))
+
+    def get_vjp(self, n_params=0, want_ncell_bar=False):
+        Qbar = np.empty(3 * self.N)
+        pbar = np.zeros(max(n_params, 1))
+        nbar = np.empty(self.N) if want_ncell_bar else None
+        self._ck(self.lib.hg_get_vjp(self._h, _p(Qbar), _p(pbar), _p(nbar)))
+        return (Qbar, pbar[:n_params], nbar) if want_ncell_bar else (Qbar, pbar[:n_params])
+
+    # ---------------------------------------------------------------- multi-GPU halo plumbing
+    def halo_info(self):
+        nn, ne = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.hg_halo_info(self._h, C.byref(nn), C.byref(ne)))
+        counts = np.zeros(max(nn.value, 1), dtype=np.int64)
+        self._ck(self.lib.hg_halo_counts(self._h, _p(counts, L.c_i64p)))
+        return counts[:nn.value]
+
+    def halo_buffers(self):
+        """(send_ptr, recv_ptr, n_doubles): device addresses of the context-owned halo buffers."""
+        s, r, n = L.c_f64p(), L.c_f64p(), C.c_int64(0)
+        self._ck(self.lib.hg_halo_buffers(self._h, C.byref(s), C.byref(r), C.byref(n)))
+        return C.cast(s, C.c_void_p).value, C.cast(r, C.c_void_p).value, n.value
+
+    def halo_pack(self, with_lambda=False):
+        self._ck(self.lib.hg_halo_pack(self._h, int(with_lambda)))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.hg_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
     def rhs_resident(self):
         self._ck(self.lib.hg_rhs_resident(self._h))

@@ -179,7 +179,7 @@ void hg_destroy(hg_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->own_stream;
   delete ctx;  // frees the device buffers
   if (s) cudaStreamDestroy(s);
 }
@@ -199,6 +199,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     return HG_ERR_CUDA;
   }
   CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = ctx->stream;
   CK(ctx, cudaEventCreate(&ctx->ev0));
   CK(ctx, cudaEventCreate(&ctx->ev1));
 
@@ -262,6 +263,9 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(al(ctx, d.Qin, ctx->n_inletq)); TRY(al(ctx, d.wse, ctx->n_exith));
     TRY(al(ctx, d.Q, 3 * Ns)); TRY(al(ctx, d.Q2, 3 * Ns)); TRY(al(ctx, d.dQ, 3 * Ns)); TRY(al(ctx, d.stage, 3 * N));
     TRY(al(ctx, d.params, npar)); TRY(al(ctx, d.err, 1));
+    TRY(up(ctx, d.halo_off, h.halo_off)); TRY(up(ctx, d.halo_cnt, h.halo_cnt));
+    TRY(al(ctx, d.halo_send, std::max<int64_t>(6 * ctx->n_halo_entries, 1)));
+    TRY(al(ctx, d.halo_recv, std::max<int64_t>(6 * ctx->n_halo_entries, 1)));
     // adjoint buffers
     TRY(al(ctx, d.lam, 3 * Ns)); TRY(al(ctx, d.Qbar, 3 * Ns)); TRY(al(ctx, d.nbar, Ns)); TRY(al(ctx, d.s0bar, 2 * Ns));
     TRY(al(ctx, d.pbar, npar)); TRY(al(ctx, d.ent_c, std::max<int64_t>(B, 1))); TRY(al(ctx, d.ent_n, std::max<int64_t>(B, 1)));
@@ -420,6 +424,71 @@ int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   return check_err_flag(ctx);
+}
+
+int hg_set_lambda(hg_ctx* ctx, const double* lambda) {
+  if (!ctx || !lambda) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "hg_set_lambda needs the fused path"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  return set_lambda(ctx, lambda);
+}
+
+int hg_vjp_resident(hg_ctx* ctx) {
+  if (!ctx) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "hg_vjp_resident needs the fused path"; return HG_ERR_ARG; }
+  if (!ctx->state_set || !ctx->lam_set) { ctx->err = "hg_vjp_resident: state or lambda not set"; return HG_ERR_STATE; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  return hg::fused_vjp(ctx, hg::fused_cfg_id(ctx), ctx->fd.Q.p, ctx->fd.lam.p, ctx->fd.Qbar.p);
+}
+
+int hg_get_vjp(hg_ctx* ctx, double* Qbar, double* pbar, double* ncell_bar) {
+  if (!ctx || !Qbar) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "hg_get_vjp needs the fused path"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  TRY(download3(ctx, d.Qbar.p, Qbar));
+  if (ctx->active != HG_PARAM_NONE && pbar)
+    CK(ctx, cudaMemcpyAsync(pbar, d.pbar.p, ctx->n_params * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ncell_bar) {
+    TRY(hg::fused_nbar_to_ref(ctx, d.stage.p));
+    CK(ctx, cudaMemcpyAsync(ncell_bar, d.stage.p, ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_err_flag(ctx);
+}
+
+int hg_halo_info(const hg_ctx* ctx, int64_t* n_neighbors, int64_t* n_entries) {
+  if (!ctx) return HG_ERR_ARG;
+  if (n_neighbors) *n_neighbors = ctx->n_halo;
+  if (n_entries) *n_entries = ctx->n_halo_entries;
+  return HG_OK;
+}
+int hg_halo_counts(const hg_ctx* ctx, int64_t* counts) {
+  if (!ctx || !counts) return HG_ERR_ARG;
+  for (size_t k = 0; k < ctx->bch.halo_counts.size(); ++k) counts[k] = ctx->bch.halo_counts[k];
+  return HG_OK;
+}
+int hg_halo_buffers(hg_ctx* ctx, double** d_send, double** d_recv, int64_t* n_doubles) {
+  if (!ctx) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "halo exchange needs the fused path"; return HG_ERR_ARG; }
+  if (d_send) *d_send = ctx->fd.halo_send.p;
+  if (d_recv) *d_recv = ctx->fd.halo_recv.p;
+  if (n_doubles) *n_doubles = 6 * ctx->n_halo_entries;
+  return HG_OK;
+}
+int hg_halo_pack(hg_ctx* ctx, int32_t with_lambda) {
+  if (!ctx) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "halo exchange needs the fused path"; return HG_ERR_ARG; }
+  if (!ctx->state_set || (with_lambda && !ctx->lam_set)) { ctx->err = "hg_halo_pack: state or lambda not set"; return HG_ERR_STATE; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  return hg::fused_halo_pack(ctx, with_lambda != 0);
+}
+int hg_set_stream(hg_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return HG_OK;
 }
 
 int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps) {

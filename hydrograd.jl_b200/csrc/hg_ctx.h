@@ -14,7 +14,7 @@ namespace hg {
 
 constexpr double EPS = 2.220446049250313e-16;  // eps(Float64) of utilities/smooth_functions.jl
 
-enum BcType : int32_t { BC_INLETQ = 0, BC_EXITH = 1, BC_WALL = 2, BC_SYMM = 3 };
+enum BcType : int32_t { BC_INLETQ = 0, BC_EXITH = 1, BC_WALL = 2, BC_SYMM = 3, BC_HALO = 4 };
 
 // ---------------------------------------------------------------- device buffer (RAII)
 template <class T>
@@ -60,6 +60,8 @@ struct BcHost {
   std::vector<int32_t> inlet_ptr;                     // [n_inletq+1] entry ranges of each inlet boundary
   std::vector<int32_t> bcell_ref, bcell_ptr, bcell_ent; // distinct boundary-adjacent cells (reference ids) -> entries
   std::vector<int32_t> cf_rev;                        // per cell-face: index of the same face in the neighbour's list
+  std::vector<int32_t> halo_off, halo_cnt;            // [B] per halo entry: offset of xi in the halo buffers, n_k
+  std::vector<int64_t> halo_counts;                   // [n_halo] entries per neighbour
 };
 
 // ---------------------------------------------------------------- plain (reference-order) path
@@ -120,6 +122,8 @@ struct FusedDev {
   DBuf<double> Q, Q2, dQ, lam, Qbar, stage, params, pbar, nbar, s0bar;  // state-like: [3*Ns]
   DBuf<double> ent_c, ent_n, ent_z, ent_h, Qinbar, inlet_A, zone_part;   // VJP: per boundary entry / per inlet
   DBuf<int32_t> bcell, bcell_ref, bcell_ptr, bcell_ent;                 // boundary-adjacent cells -> their entries
+  DBuf<int32_t> halo_off, halo_cnt;                                     // [B]
+  DBuf<double> halo_send, halo_recv;                                    // [6 * n_halo_entries]
   DBuf<int32_t> err;
 };
 
@@ -134,6 +138,8 @@ struct hg_ctx {
   hg_options opt{};
   int64_t N = 0, F = 0, B = 0, sumnf = 0;
   int64_t n_inletq = 0, n_exith = 0, n_wall = 0, n_symm = 0, n_mat = 0, nbcell = 0;
+  int64_t n_halo = 0, halo_e0 = 0, n_halo_entries = 0;
+  cudaStream_t own_stream = nullptr;
   bool lam_set = false;
   hg::Consts c{};
   cudaStream_t stream = nullptr;
@@ -183,4 +189,5 @@ void fused_inlet_coef(hg_ctx* ctx, const double* d_Q);
 int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);
 int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
+int fused_halo_pack(hg_ctx* ctx, bool with_lambda);
 }  // namespace hg

@@ -46,7 +46,9 @@ int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg
   ctx->c = {f->g, f->k_n, f->h_small};
   ctx->n_inletq = b->n_inletq; ctx->n_exith = b->n_exith; ctx->n_wall = b->n_wall; ctx->n_symm = b->n_symm;
   ctx->n_mat = f->n_mat;
-  const int64_t nbc = b->n_inletq + b->n_exith + b->n_wall + b->n_symm;
+  const int64_t nbc = b->n_inletq + b->n_exith + b->n_wall + b->n_symm + b->n_halo;
+  ctx->n_halo = b->n_halo;
+  if (b->n_halo < 0 || (b->n_halo > 0 && (!b->halo_flip || !b->halo_area))) HG_FAIL(ctx, HG_ERR_ARG, "halo boundary data missing");
   if (b->n_inletq < 0 || b->n_exith < 0 || b->n_wall < 0 || b->n_symm < 0) HG_FAIL(ctx, HG_ERR_ARG, "negative boundary count");
   if (B > 0 && (!b->bc_ptr || !b->ghost_ids || !b->internal_cells || !b->outward_normals))
     HG_FAIL(ctx, HG_ERR_ARG, "null boundary array");
@@ -94,8 +96,10 @@ int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg
   h.inlet_ptr.assign(1, 0);
   std::vector<char> seen(B, 0);
   int64_t kb = 0;
-  const int64_t counts[4] = {b->n_inletq, b->n_exith, b->n_wall, b->n_symm};
-  for (int t = 0; t < 4; ++t) {
+  const int64_t counts[5] = {b->n_inletq, b->n_exith, b->n_wall, b->n_symm, b->n_halo};
+  h.halo_off.assign(B, 0); h.halo_cnt.assign(B, 0);
+  ctx->halo_e0 = B; ctx->n_halo_entries = 0;
+  for (int t = 0; t < 5; ++t) {
     for (int64_t kk = 0; kk < counts[t]; ++kk, ++kb) {
       if (b->bc_ptr[kb + 1] < b->bc_ptr[kb]) HG_FAIL(ctx, HG_ERR_ARG, "bc_ptr not monotone");
       for (int64_t e = b->bc_ptr[kb]; e < b->bc_ptr[kb + 1]; ++e) {
@@ -111,10 +115,21 @@ int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg
           h.l53[e] = std::pow(L, 5.0 / 3.0);  // bc_2D.jl:674
           h.l23[e] = std::pow(L, 2.0 / 3.0);  // bc_2D.jl:691
         }
+        if (t == BC_HALO) {
+          const int64_t nk = b->bc_ptr[kb + 1] - b->bc_ptr[kb];
+          if (ctx->halo_e0 == B) ctx->halo_e0 = b->bc_ptr[kb];
+          h.group[e] = b->halo_flip[e] ? 1 : 0;          // the flip flag rides in `group`
+          h.l23[e] = b->halo_area[e];                    // ... and the remote cell's area in `l23`
+          h.halo_off[e] = (int32_t)(6 * (b->bc_ptr[kb] - ctx->halo_e0) + (e - b->bc_ptr[kb]));
+          h.halo_cnt[e] = (int32_t)nk;
+          if (!(b->halo_area[e] > 0.0)) HG_FAIL(ctx, HG_ERR_ARG, "halo entry %ld: bad remote cell area", (long)e);
+        }
       }
+      if (t == BC_HALO) h.halo_counts.push_back(b->bc_ptr[kb + 1] - b->bc_ptr[kb]);
       if (t == BC_INLETQ) h.inlet_ptr.push_back((int32_t)b->bc_ptr[kb + 1]);
     }
   }
+  ctx->n_halo_entries = B - ctx->halo_e0;
   // consistency: the ghost of entry e must be the neighbour of its internal cell
   for (int64_t e = 0; e < B; ++e) {
     int32_t c = h.cell_ref[e];

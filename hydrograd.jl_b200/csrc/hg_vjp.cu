@@ -31,6 +31,8 @@ struct VjpArgs {
   const double *area, *hstill, *zb, *S0x, *S0y, *mann;
   const int32_t *bc_type, *bc_group;
   const double *bc_nx, *bc_ny, *bc_l23, *bc_hstill, *bc_zb, *inlet_coef, *wse;
+  const int32_t *halo_off, *halo_cnt;
+  const double* halo_recv;
   const double *Q, *lam;
   double *Qbar, *nbar, *s0bar;          // [3Ns], [Ns], [2Ns]
   double *ent_c, *ent_n, *ent_z;        // per boundary entry: inlet coef adjoint share, n adjoint, zb adjoint
@@ -246,68 +248,97 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) k_fused_vjp(const __grid_cons
   for (int32_t f = tid; f < nf; f += kThreads) {
     const uint32_t lr = sm.lr[f];
     const int32_t lL = lr & 0xFFFFu, lR = lr >> 16;
-    const double nx = sm.o[0][f], ny = sm.o[1][f], len = sm.o[2][f];
+    double nx = sm.o[0][f], ny = sm.o[1][f];
+    const double len = sm.o[2][f];
     Side L, R;
     L.xi = sm.xi[lL]; L.h = sm.h[lL]; L.u = sm.u[lL]; L.v = sm.v[lL]; L.s = sm.s[lL]; L.P = sm.P[lL];
-    L.hu = L.h * L.u; L.hv = L.h * L.v;
+    L.hu = __dmul_rn(L.h, L.u); L.hv = __dmul_rn(L.h, L.v);   // never contracted into the flux FMAs
     double f0b = -sm.m0[lL], f1b = -sm.m1[lL], f2b = -sm.m2[lL];
-    Adj aL, aR;
+    const double* zbLp = &sm.zb[lL];
+    const double* zbRp = &sm.zb[lR < Cfg::ML ? lR : 0];
+    double zbg = 0.0, hstg = 0.0, bnx = 0.0, bny = 0.0, vn = 0.0, wet = 0.0, mannc = 1.0;
+    int32_t ty = -1, e = 0;
+    bool flip = false, exit_free = false;
     if (f < nint) {
       R.xi = sm.xi[lR]; R.h = sm.h[lR]; R.u = sm.u[lR]; R.v = sm.v[lR]; R.s = sm.s[lR]; R.P = sm.P[lR];
-      R.hu = R.h * R.u; R.hv = R.h * R.v;
+      R.hu = __dmul_rn(R.h, R.u); R.hv = __dmul_rn(R.h, R.v);
       f0b += sm.m0[lR]; f1b += sm.m1[lR]; f2b += sm.m2[lR];
-      roe_flux_adj(L, R, &sm.zb[lL], &sm.zb[lR], nx, ny, g, hs, f0b * len, f1b * len, f2b * len, aL, aR);
     } else {
-      // boundary face: rebuild the ghost state (bc_2D.jl:640-834), sweep, pull the ghost adjoint back
-      const int32_t e = __ldg(a.bface_e + bfp + (f - nint));
-      const int32_t ty = a.bc_type[e], kgrp = a.bc_group[e];
-      const double bnx = a.bc_nx[e], bny = a.bc_ny[e];
-      const double zbc = sm.zb[lL];
-      double vn = 0.0, wet = 0.0, mannc = 1.0;
-      bool exit_free = false;
+      // boundary face: rebuild the ghost state (bc_2D.jl:640-834)
+      e = __ldg(a.bface_e + bfp + (f - nint));
+      ty = a.bc_type[e];
+      const int32_t kgrp = a.bc_group[e];
+      bnx = a.bc_nx[e]; bny = a.bc_ny[e];
+      hstg = a.bc_hstill[e];
+      zbg = a.bc_zb[e];
+      zbRp = &zbg;
       if (ty == BC_INLETQ) {
         wet = L.h > hs ? 1.0 : 0.0;
         mannc = sm.mann[lL];
         vn = a.inlet_coef[kgrp] * a.bc_l23[e] / mannc;
         R.h = L.h; R.hu = -L.h * vn * bnx * wet; R.hv = -L.h * vn * bny * wet;
       } else if (ty == BC_EXITH) {
-        const double hg = a.wse[kgrp] - zbc;
+        const double hg = a.wse[kgrp] - sm.zb[lL];
         exit_free = hg > hs;                       // max(h_small, .) passes the derivative only when not clamped
         R.h = exit_free ? hg : hs; R.hu = L.hu; R.hv = L.hv;
       } else if (ty == BC_WALL) {
         R.h = L.h; R.hu = -L.hu; R.hv = -L.hv;
-      } else {
+      } else if (ty == BC_SYMM) {
         const double vdn = L.hu * bnx + L.hv * bny;
         R.h = L.h; R.hu = L.hu - 2.0 * vdn * bnx; R.hv = L.hv - 2.0 * vdn * bny;
-      }
-      const double hstg = a.bc_hstill[e];
-      R.xi = R.h - hstg;
-      const double zbg = a.bc_zb[e];
-      derive(R, hstg, g);
-      roe_flux_adj(L, R, &zbc, &zbg, nx, ny, g, hs, f0b * len, f1b * len, f2b * len, aL, aR);
-      // ghost (xi, h, u, v, s, P) adjoints -> ghost primitives (h_g, hu_g, hv_g); xi_g = h_g - hstill_g
-      const double rhg = fast_rcp(R.h);
-      const double hub = aR.u * rhg, hvb = aR.v * rhg;
-      const double xib = aR.xi + aR.P * g * (R.xi + EPS + hstg);
-      const double hgb = aR.h - (aR.u * R.u + aR.v * R.v) * rhg + aR.s * 0.5 * fast_rcp(R.s) + xib;
-      // boundary condition transposed: adjoints of the internal cell's clamped (h, hu, hv)
-      double hcb = 0.0, hucb = 0.0, hvcb = 0.0, ec = 0.0, en = 0.0, ez = 0.0;
-      if (ty == BC_INLETQ) {
-        const double G = -(hub * bnx + hvb * bny) * wet;   // d(hu_g, hv_g) = -n wet d(h_c vn)
-        hcb = hgb + G * vn;
-        en = -G * L.h * vn / mannc;                        // vn = coef L^(2/3) / n_c
-        ec = G * L.h * a.bc_l23[e] / mannc;                // share of the adjoint of coef_k = Q_k / A_k
-      } else if (ty == BC_EXITH) {
-        hucb = hub; hvcb = hvb;
-        ez = exit_free ? -hgb : 0.0;                       // h_g = WSE - zb_c
-      } else if (ty == BC_WALL) {
-        hcb = hgb; hucb = -hub; hvcb = -hvb;
       } else {
-        const double dn = hub * bnx + hvb * bny;
-        hcb = hgb; hucb = hub - 2.0 * dn * bnx; hvcb = hvb - 2.0 * dn * bny;
+        // remote cell: state and cotangent arrived through the halo buffers; its own adjoint is computed by its owner
+        const int32_t off = a.halo_off[e], n = a.halo_cnt[e];
+        const double xr = a.halo_recv[off], qxr = a.halo_recv[off + n], qyr = a.halo_recv[off + 2 * n];
+        const double rAr = fast_rcp(a.bc_l23[e]);          // remote cell area rides in l23
+        // mu_remote is a rounded product exactly like an in-tile cell's (no FMA contraction with the sum)
+        f0b += __dmul_rn(a.halo_recv[off + 3 * n], rAr); f1b += __dmul_rn(a.halo_recv[off + 4 * n], rAr);
+        f2b += __dmul_rn(a.halo_recv[off + 5 * n], rAr);
+        const double hr = xr + hstg;
+        const bool dryr = hr <= hs;
+        R.h = dryr ? hs : hr; R.hu = dryr ? 0.0 : qxr; R.hv = dryr ? 0.0 : qyr; R.xi = xr;
+        flip = kgrp != 0;
+      }
+      if (ty != BC_HALO) R.xi = R.h - hstg;
+      derive(R, hstg, g);
+      if (ty == BC_HALO) { R.hu = __dmul_rn(R.h, R.u); R.hv = __dmul_rn(R.h, R.v); }
+    }
+    f0b *= len; f1b *= len; f2b *= len;
+    if (flip) {   // evaluated with the remote cell as L (see hg_fused.cu): flux_out = -roe(R, L, -n)
+      const Side tmp = L; L = R; R = tmp;
+      const double* tp = zbLp; zbLp = zbRp; zbRp = tp;
+      nx = -nx; ny = -ny; f0b = -f0b; f1b = -f1b; f2b = -f2b;
+    }
+    Adj aL, aR;
+    roe_flux_adj(L, R, zbLp, zbRp, nx, ny, g, hs, f0b, f1b, f2b, aL, aR);
+    if (flip) { const Adj ta = aL; aL = aR; aR = ta; const Side tmp = L; L = R; R = tmp; }
+    if (ty >= 0) {
+      double ec = 0.0, en = 0.0, ez = 0.0;
+      if (ty != BC_HALO) {
+        // ghost (xi, h, u, v, s, P) adjoints -> ghost primitives (h_g, hu_g, hv_g); xi_g = h_g - hstill_g
+        const double rhg = fast_rcp(R.h);
+        const double hub = aR.u * rhg, hvb = aR.v * rhg;
+        const double xib = aR.xi + aR.P * g * (R.xi + EPS + hstg);
+        const double hgb = aR.h - (aR.u * R.u + aR.v * R.v) * rhg + aR.s * 0.5 * fast_rcp(R.s) + xib;
+        // boundary condition transposed: adjoints of the internal cell's clamped (h, hu, hv)
+        double hcb = 0.0, hucb = 0.0, hvcb = 0.0;
+        if (ty == BC_INLETQ) {
+          const double G = -(hub * bnx + hvb * bny) * wet;   // d(hu_g, hv_g) = -n wet d(h_c vn)
+          hcb = hgb + G * vn;
+          en = -G * L.h * vn / mannc;                        // vn = coef L^(2/3) / n_c
+          ec = G * L.h * a.bc_l23[e] / mannc;                // share of the adjoint of coef_k = Q_k / A_k
+        } else if (ty == BC_EXITH) {
+          hucb = hub; hvcb = hvb;
+          ez = exit_free ? -hgb : 0.0;                       // h_g = WSE - zb_c
+        } else if (ty == BC_WALL) {
+          hcb = hgb; hucb = -hub; hvcb = -hvb;
+        } else {
+          const double dn = hub * bnx + hvb * bny;
+          hcb = hgb; hucb = hub - 2.0 * dn * bnx; hvcb = hvb - 2.0 * dn * bny;
+        }
+        aL.u += hucb * L.h; aL.v += hvcb * L.h; aL.h += hcb + hucb * L.u + hvcb * L.v;
       }
       a.ent_c[e] = ec; a.ent_n[e] = en; a.ent_z[e] = ez;
-      aL.u += hucb * L.h; aL.v += hvcb * L.h; aL.h += hcb + hucb * L.u + hvcb * L.v;
       aR = Adj{0, 0, 0, 0, 0, 0};
     }
     sm.o[0][f] = aL.xi; sm.o[1][f] = aL.h; sm.o[2][f] = aL.u; sm.o[3][f] = aL.v; sm.o[4][f] = aL.s; sm.o[5][f] = aL.P;
@@ -541,6 +572,7 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
   a.area = d.area.p; a.hstill = d.hstill.p; a.zb = d.zb.p; a.S0x = d.S0x.p; a.S0y = d.S0y.p; a.mann = d.mann.p;
   a.bc_type = d.bc_type.p; a.bc_group = d.bc_group.p; a.bc_nx = d.bc_nx.p; a.bc_ny = d.bc_ny.p;
   a.bc_l23 = d.bc_l23.p; a.bc_hstill = d.bc_hstill.p; a.bc_zb = d.bc_zb.p; a.inlet_coef = d.inlet_coef.p;
+  a.halo_off = d.halo_off.p; a.halo_cnt = d.halo_cnt.p; a.halo_recv = d.halo_recv.p;
   a.wse = d.wse.p; a.Q = d_Q; a.lam = d_lam; a.Qbar = d_Qbar; a.nbar = d.nbar.p; a.s0bar = d.s0bar.p;
   a.ent_c = d.ent_c.p; a.ent_n = d.ent_n.p; a.ent_z = d.ent_z.p;
   const unsigned grid = (unsigned)fh.n_tiles;

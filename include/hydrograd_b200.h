@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 1
+#define HG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define HG_API __attribute__((visibility("default")))
@@ -92,6 +92,16 @@ typedef struct {
   const int64_t* internal_cells;   /* [B] *_internalCellIDs                                      */
   const double* outward_normals;   /* [B*2] column-major *_faceOutwardNormals / *_outwardNormals */
   const double* face_lengths;      /* [B] inletQ_Length (read for inlet-q entries only)          */
+  /* ---- multi-GPU extension (no counterpart in the reference, which is a single serial process): after the
+   * symm boundaries come n_halo "halo boundaries", one per neighbouring rank.  Their entries are the faces
+   * this rank shares with that neighbour, in an order both ranks agree on (sorted by the global ids of the
+   * two cells); the ghost cell of such an entry mirrors the neighbour's cell and is refreshed through the
+   * halo buffers (hg_halo_*) before each RHS.  NULL / 0 on a single GPU.                             */
+  int64_t n_halo;
+  const uint8_t* halo_flip;        /* [B] 1 where the ghost (remote) cell has the smaller GLOBAL id: the face is
+                                      then evaluated with the remote cell as L so that every rank computes the
+                                      same bits as a single-GPU run                                     */
+  const double* halo_area;         /* [B] area of the remote cell (VJP needs lambda/area of both sides)   */
 } hg_bc_desc;
 
 /* ---- SWE2D_Extra_Parameters (src/applications/application_commons.jl:7-44) + swe_2D_consts
@@ -173,6 +183,22 @@ HG_API int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps);
 HG_API int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params,
                         int32_t active_param, double t_start, double t_end, double dt, double* sol,
                         int64_t n_saves_capacity, int64_t* n_saves);
+
+/* ---- multi-GPU halo exchange (one context per rank; the transport -- NCCL send/recv -- is the caller's).
+ * Buffers are device memory owned by the context: for neighbour k (k-th halo boundary, n_k entries) a block of
+ * 6*n_k doubles [xi | q_x | q_y | lambda_0 | lambda_1 | lambda_2] at offset 6*(entries before k).  A RHS-only
+ * exchange moves the first 3*n_k doubles of each block.                                              */
+HG_API int hg_halo_info(const hg_ctx* ctx, int64_t* n_neighbors, int64_t* n_entries);
+HG_API int hg_halo_counts(const hg_ctx* ctx, int64_t* counts /* [n_neighbors] */);
+HG_API int hg_halo_buffers(hg_ctx* ctx, double** d_send, double** d_recv, int64_t* n_doubles);
+HG_API int hg_halo_pack(hg_ctx* ctx, int32_t with_lambda);   /* resident state (and lambda) -> send buffer      */
+/* run every kernel of this context on the caller's CUDA stream (e.g. torch's current stream) so that packing,
+ * the NCCL transfers and the RHS are ordered without host synchronisation; NULL restores the own stream   */
+HG_API int hg_set_stream(hg_ctx* ctx, void* cuda_stream);
+/* resident cotangent for hg_vjp_resident / hg_time_vjp */
+HG_API int hg_set_lambda(hg_ctx* ctx, const double* lambda);
+HG_API int hg_vjp_resident(hg_ctx* ctx);
+HG_API int hg_get_vjp(hg_ctx* ctx, double* Qbar, double* pbar, double* ncell_bar);
 
 /* ---- timing hooks used by bench.py (device time of the last N launches, CUDA events on the
  * ctx stream) and introspection for the roofline arithmetic.                                     */

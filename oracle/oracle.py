@@ -30,7 +30,8 @@ class MeshDesc(C.Structure):
 class BcDesc(C.Structure):
     _fields_ = [("n_inletq", C.c_int64), ("n_exith", C.c_int64), ("n_wall", C.c_int64), ("n_symm", C.c_int64),
                 ("bc_ptr", c_i64p), ("ghost_ids", c_i64p), ("internal_cells", c_i64p),
-                ("outward_normals", c_f64p), ("face_lengths", c_f64p)]
+                ("outward_normals", c_f64p), ("face_lengths", c_f64p),
+                ("n_halo", C.c_int64), ("halo_flip", c_u8p), ("halo_area", c_f64p)]
 
 
 class FieldsDesc(C.Structure):
@@ -74,7 +75,7 @@ class Oracle:
                              _p(f["cell_areas"], c_f64p), _p(cc, c_f64p))
         self.bc = BcDesc(f["n_inletq"], f["n_exith"], f["n_wall"], f["n_symm"], _p(f["bc_ptr"], c_i64p),
                          _p(f["bc_ghost_ids"], c_i64p), _p(f["bc_internal_cells"], c_i64p),
-                         _p(f["bc_normals"], c_f64p), _p(f["bc_lengths"], c_f64p))
+                         _p(f["bc_normals"], c_f64p), _p(f["bc_lengths"], c_f64p), 0, None, None)
         self.fields = FieldsDesc(f["g"], f["k_n"], f["h_small"], b"Roe", _p(f["hstill"], c_f64p),
                                  _p(f["hstill_ghost"], c_f64p), _p(f["zb_cells"], c_f64p), _p(f["zb_ghost"], c_f64p),
                                  _p(f["S0_cells"], c_f64p), _p(f["ManningN_cells"], c_f64p),

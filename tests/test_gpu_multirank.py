@@ -1,0 +1,80 @@
+"""GPU tests of the multi-rank path on ONE device: P contexts (one per part) exchange their halo blocks through
+the same buffers NCCL would fill; the assembled result must be bit-identical to the single-context run
+(redundant cut faces + canonical orientation; SURVEY 8e 'determinism')."""
+import numpy as np
+import pytest
+
+import _pkg
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hg():
+    return _pkg.load()
+
+
+def _route(ctxs, infos, with_lambda):
+    """Copy every rank's send block k into the matching recv block of its peer (what send/recv does)."""
+    import torch
+    from hydrograd_jl_b200.parallel import _DevArray
+    bufs = []
+    for c in ctxs:
+        c.halo_pack(with_lambda)
+        c.sync()
+        sp, rp, n = c.halo_buffers()
+        bufs.append((torch.as_tensor(_DevArray(sp, n), device="cuda") if n else None,
+                     torch.as_tensor(_DevArray(rp, n), device="cuda") if n else None))
+    per = 6 if with_lambda else 3
+    for r, info in enumerate(infos):
+        off = np.concatenate([[0], np.cumsum([6 * c for c in info["counts"]])])
+        for k, (peer, nk) in enumerate(zip(info["neighbors"], info["counts"])):
+            pinfo = infos[peer]
+            kk = pinfo["neighbors"].index(r)
+            poff = int(np.concatenate([[0], np.cumsum([6 * c for c in pinfo["counts"]])])[kk])
+            bufs[peer][1][poff:poff + per * nk] = bufs[r][0][int(off[k]):int(off[k]) + per * nk]
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("case", ["dam_rcb4", "river_slab3", "dam_thin_rcb3"])
+def test_partitioned_rhs_and_vjp_match_single_context_bitwise(hg, case):
+    from hydrograd_jl_b200 import parallel as P
+    from hydrograd_jl_b200 import synthetic as S
+    if case == "dam_rcb4":
+        flat, Q0 = S.dam_break(40); Pn = 4
+    elif case == "dam_thin_rcb3":
+        flat, Q0 = S.dam_break(36, thin_film=True); Pn = 3
+    else:
+        flat, Q0 = S.river(90, 24); Pn = 3
+    N = flat["n_cells"]
+    if case.startswith("river"):
+        part = (np.arange(N) * Pn // N).astype(np.int32)
+    else:
+        part = P.rcb_partition(flat["cell_centroids"][:N], flat["cell_centroids"][N:], Pn)
+    rng = np.random.default_rng(2)
+    Q = cases.random_state_flat(flat, 7, dry_frac=0.05) if case != "river_slab3" else Q0
+    lam = rng.standard_normal(3 * N)
+    single = hg.Context(flat, tile_cells=128)
+    ref = single.rhs(Q)
+    ref_bar, _ = single.rhs_vjp(Q, lam)
+    locs = [P.extract_local(flat, part, r, Q) for r in range(Pn)]
+    ctxs = [hg.Context(loc, tile_cells=128) for loc, _ in locs]
+    infos = [info for _, info in locs]
+    for c, info in zip(ctxs, infos):
+        c.set_state(info["Q"])
+        c.set_lambda(np.concatenate([lam[k * N + info["own"]] for k in range(3)]))
+    _route(ctxs, infos, with_lambda=True)
+    got = np.zeros(3 * N)
+    bar = np.zeros(3 * N)
+    for c, info in zip(ctxs, infos):
+        c.rhs_resident()
+        d = c.get_rhs()
+        c.vjp_resident()
+        b, _ = c.get_vjp()
+        n = info["own"].size
+        for k in range(3):
+            got[k * N + info["own"]] = d[k * n:(k + 1) * n]
+            bar[k * N + info["own"]] = b[k * n:(k + 1) * n]
+    assert np.array_equal(got, ref), f"max diff {np.abs(got - ref).max()}"
+    assert np.array_equal(bar, ref_bar), f"max diff {np.abs(bar - ref_bar).max()}"
