@@ -137,6 +137,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE line (the JSON record of rank 0): everything else any library prints while we
+    # run (NCCL's version banner, warnings) is sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import _pkg
     hg = _pkg.load()
@@ -156,10 +161,30 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
 
-    # ---- workload: slab `rank` of a river `world` times as long (weak scaling)
+    # ---- workload: slab `rank` of a river `world` times as long (weak scaling).  The slab decomposition is what
+    # recursive coordinate bisection yields for this elongated domain; each rank generates its slab plus one
+    # column on each cut side and extracts its local mesh (owned cells + halo boundaries) with the general
+    # partitioner code (hydrograd.jl_b200/parallel.py).
+    from hydrograd_jl_b200 import parallel as PAR
     ni = int(args.cells_m * 1e6 / 1.1 / 1000)
     t0 = time.time()
-    flat, Q0 = S.river(ni, 1000, i0=rank * ni, ni_total=world * ni)
+    if world == 1:
+        flat, Q0 = S.river(ni, 1000)
+        ranks = []
+    else:
+        lo = rank * ni - (1 if rank > 0 else 0)
+        hi = (rank + 1) * ni + (1 if rank < world - 1 else 0)
+        gflat, gQ = S.river(hi - lo, 1000, i0=lo, ni_total=world * ni)
+        # owner of every cell of the extended slab, from the stream-wise column of its centroid's quad
+        col = S.cell_columns(gflat, hi - lo, 1000)
+        part = np.full(gflat["n_cells"], rank, dtype=np.int32)
+        if rank > 0:
+            part[col == 0] = rank - 1
+        if rank < world - 1:
+            part[col == (hi - lo - 1)] = rank + 1
+        flat, info = PAR.extract_local(gflat, part, rank, gQ)
+        Q0, ranks = info["Q"], info["neighbors"]
+        del gflat, gQ
     N, F = flat["n_cells"], flat["n_faces"]
     log(f"[rank {rank}] mesh: N={N} F={F} ({time.time() - t0:.1f}s)")
     t0 = time.time()
@@ -167,42 +192,68 @@ def main():
     st = ctx.mesh_stats()
     log(f"[rank {rank}] context: {st} ({time.time() - t0:.1f}s)")
     ctx.set_state(Q0)
+    rng = np.random.default_rng(99 + rank)
+    ctx.set_lambda(rng.standard_normal(3 * N))
+    # one explicit (non-default) stream for everything: pack kernel, NCCL transfers, RHS / VJP kernels, timing events
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ex = PAR.attach_exchanger(ctx, ranks) if world > 1 else None
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up, then exactly K timed steps (CUDA events on the kernel's stream, inside the library)
-    ctx.time_rhs(max(args.warmup, 3))
+    def rhs_step():
+        if ex is not None:
+            ctx.halo_pack(False)
+            ex.exchange(False)
+        ctx.rhs_resident()
+
+    def vjp_step():
+        if ex is not None:
+            ctx.halo_pack(True)
+            ex.exchange(True)
+        ctx.vjp_resident()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    def allmax(x):
+        if dist is None:
+            return x
+        tt = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- warm-up, then exactly K timed steps; CUDA events on the stream every kernel and transfer is ordered on
+    W = max(args.warmup, 3)
+    timed(rhs_step, W); timed(vjp_step, W)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     l0 = ctx.kernel_launches()
-    ms = ctx.time_rhs(args.steps)
+    ms = timed(rhs_step, args.steps)
+    barrier()
+    ms_vjp = timed(vjp_step, args.steps)
     barrier()
     launches = ctx.kernel_launches() - l0
     clocks = sampler.stop()
+    ctx.sync()
+    ms, ms_vjp = allmax(ms), allmax(ms_vjp)
     if dist is not None:
-        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
         tn = torch.tensor([N], device="cuda", dtype=torch.float64)
         dist.all_reduce(tn)
         N_total = int(tn.item())
     else:
         N_total = N
-    # ---- the adjoint of the same call (hand-written VJP kernel), same protocol
-    ctx.time_vjp(max(args.warmup, 3))
-    barrier()
-    l1 = ctx.kernel_launches()
-    ms_vjp = ctx.time_vjp(args.steps)
-    barrier()
-    launches += ctx.kernel_launches() - l1
-    if dist is not None:
-        tv = torch.tensor([ms_vjp], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-        ms_vjp = float(tv.item())
     ms_rhs_step = ms / args.steps
     ms_vjp_step = ms_vjp / args.steps
     ms_per_step = ms_rhs_step + ms_vjp_step
@@ -221,24 +272,30 @@ def main():
                     "kernel": "k_fused_vjp", "algorithmic_bytes_per_launch": vbytes, "bytes_per_cell": vbytes / N,
                     "ms_per_launch": ms_vjp_step}
 
-    # ---- end to end through the host-buffer ABI call (pinned host memory, H2D + D2H in the timed region)
+    # ---- end to end through the host-buffer ABI (pinned host memory; H2D + D2H inside the timed region): at N = 1
+    # this is exactly hg_rhs; at N > 1 the same three stages with the halo exchange in between
     hQ = torch.empty(3 * N, dtype=torch.float64).pin_memory()
     hD = torch.empty(3 * N, dtype=torch.float64).pin_memory()
     hQ.numpy()[:] = Q0
     out = hD.numpy()
-    ctx.rhs(hQ.numpy(), out=out)  # warm-up
+
+    def e2e_step():
+        if ex is None:
+            ctx.rhs(hQ.numpy(), out=out)
+        else:
+            ctx.set_state(hQ.numpy())
+            rhs_step()
+            ctx.get_rhs(out=out)
+
+    e2e_step()  # warm-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        ctx.rhs(hQ.numpy(), out=out)
+        e2e_step()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    if dist is not None:
-        te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
+    e2e_s = allmax((time.perf_counter() - t0) / args.e2e_steps)
     e2e = {"value": N_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 24 * N,
-           "ms_per_step": e2e_s * 1e3}
+           "ms_per_step": e2e_s * 1e3, "what": "one RHS through host buffers (hg_rhs): H2D state, kernel, D2H dQdt"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -254,12 +311,13 @@ def main():
                                        "zones, inlet-Q/exit-H/walls); step = one fused fp64 RHS + one hand-written VJP of the resident state",
                            "cells_per_gpu": N, "faces_per_gpu": F, "tile_cells": args.tile, "n_tiles": st["n_tiles"],
                            "l2": "inputs (state + mesh tables >> 126 MB L2) larger than L2, no flush needed",
-                           "parallelism": f"rcb-slab x{world}"},
+                           "parallelism": f"rcb-slab x{world}, one-layer halo, NCCL send/recv per step" if world > 1 else "single GPU"},
                 "roofline": roofline, "roofline_vjp": roofline_vjp,
                 "rhs": {"value": N_total / (ms_rhs_step * 1e-3), "unit": UNIT, "ms": ms_rhs_step},
                 "vjp": {"value": N_total / (ms_vjp_step * 1e-3), "unit": UNIT, "ms": ms_vjp_step},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -206,8 +206,8 @@ class Context:
     def rhs_resident(self):
         self._ck(self.lib.hg_rhs_resident(self._h))
 
-    def get_rhs(self):
-        out = np.empty(3 * self.N)
+    def get_rhs(self, out=None):
+        out = np.empty(3 * self.N) if out is None else out
         self._ck(self.lib.hg_get_rhs(self._h, _p(out)))
         return out
 

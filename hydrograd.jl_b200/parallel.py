@@ -221,5 +221,6 @@ def attach_exchanger(ctx, ranks, group=None):
         return HaloExchanger(None, None, [], [])
     send = torch.as_tensor(_DevArray(sp, n), device="cuda")
     recv = torch.as_tensor(_DevArray(rp, n), device="cuda")
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    if torch.cuda.current_stream().cuda_stream != 0:
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     return HaloExchanger(send, recv, ranks, counts, group)

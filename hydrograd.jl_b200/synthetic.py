@@ -241,3 +241,14 @@ def river(ni=16000, nj=1000, seed=1234, i0=0, ni_total=None, perturb=0.05):
                 exitH_WSE=np.full(flat["n_exith"], 10.0 - slope * ni_total + 3.0))
     Q0 = np.concatenate([h - hstill, h * u * np.cos(ph), h * u * np.sin(ph)])
     return flat, Q0
+
+
+def cell_columns(flat, ni, nj):
+    """Stream-wise quad column (0..ni-1) of every cell of a `river`/`dam_break` mesh (cells are numbered i-major,
+    a split quad contributes two consecutive cells)."""
+    N = flat["n_cells"]
+    nf = np.asarray(flat["cell_nfaces"])
+    # walk the cells in order: a quad closes one logical cell, two consecutive triangles close one
+    w = np.where(nf == 4, 1.0, 0.5)
+    q = np.floor(np.cumsum(w) - w + 1e-9).astype(np.int64)     # logical quad index of every cell
+    return np.minimum(q // nj, ni - 1)
