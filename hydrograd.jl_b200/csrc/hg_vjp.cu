@@ -168,11 +168,14 @@ struct __align__(16) VjpSmem {
   uint16_t cf[Cfg::T * Cfg::NF];
 };
 
+// The adjoint sweep needs ~170 registers un-capped, which leaves ONE 5-warp CTA per SM (per-SMSP register file);
+// 192 threads capped at 168 registers keep two CTAs (3 warps per SMSP) resident next to the 96 KB of shared memory.
+constexpr int kVjpThreads = 192;
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) k_fused_vjp(const __grid_constant__ VjpArgs a) {
+__global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_constant__ VjpArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   VjpSmem<Cfg>& sm = *reinterpret_cast<VjpSmem<Cfg>*>(smraw);
-  constexpr int T = Cfg::T, NF = Cfg::NF, kThreads = Cfg::THREADS;
+  constexpr int T = Cfg::T, NF = Cfg::NF, kThreads = kVjpThreads;
 
   const int t = blockIdx.x, tid = threadIdx.x;
   const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc));
@@ -580,7 +583,7 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
 #define X(id, T, ML, MF, NF, TH, MB)                                                        \
   case id: {                                                                                \
     using C = TileCfg<T, ML, MF, NF, TH, MB>;                                               \
-    k_fused_vjp<C><<<grid, C::THREADS, sizeof(VjpSmem<C>), ctx->stream>>>(a);               \
+    k_fused_vjp<C><<<grid, kVjpThreads, sizeof(VjpSmem<C>), ctx->stream>>>(a);               \
   } break;
     HG_TILE_CONFIGS(X)
 #undef X
