@@ -74,6 +74,12 @@ SYMBOLS = {
     "hg_set_lambda": (C.c_int, [_vp, c_f64p]),
     "hg_vjp_resident": (C.c_int, [_vp]),
     "hg_get_vjp": (C.c_int, [_vp, c_f64p, c_f64p, c_f64p]),
+    "hg_ensemble_alloc": (C.c_int, [_vp, C.c_int64, C.c_int32]),
+    "hg_ensemble_set_member": (C.c_int, [_vp, C.c_int64, c_f64p, c_f64p, C.c_int64, C.c_int32]),
+    "hg_ensemble_step_euler": (C.c_int, [_vp, C.c_double, C.c_int64]),
+    "hg_ensemble_rhs": (C.c_int, [_vp]),
+    "hg_ensemble_get_member": (C.c_int, [_vp, C.c_int64, C.c_int32, c_f64p]),
+    "hg_time_ensemble": (C.c_int, [_vp, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "hg_time_rhs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "hg_time_vjp": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_float)]),
     "hg_kernel_launches": (C.c_int64, [_vp]),

@@ -226,6 +226,30 @@ class Context:
                                               float(dt), _p(sol), nsteps, C.byref(ns)))
         return sol[:ns.value].T
 
+    # ---------------------------------------------------------------- parameter ensembles
+    def ensemble_alloc(self, n_members, per_member_manning=False):
+        self._ck(self.lib.hg_ensemble_alloc(self._h, int(n_members), int(per_member_manning)))
+
+    def ensemble_set_member(self, m, Q, params=None, active=None):
+        p, n, a = self._params(params, active)
+        self._ck(self.lib.hg_ensemble_set_member(self._h, int(m), _p(_f64(Q)), _p(p), n, a))
+
+    def ensemble_step_euler(self, dt, nsteps=1):
+        self._ck(self.lib.hg_ensemble_step_euler(self._h, float(dt), int(nsteps)))
+
+    def ensemble_rhs(self):
+        self._ck(self.lib.hg_ensemble_rhs(self._h))
+
+    def ensemble_get_member(self, m, what="state"):
+        out = np.empty(3 * self.N)
+        self._ck(self.lib.hg_ensemble_get_member(self._h, int(m), 0 if what == "state" else 1, _p(out)))
+        return out
+
+    def time_ensemble(self, n_steps, dt):
+        ms = C.c_float(0)
+        self._ck(self.lib.hg_time_ensemble(self._h, int(n_steps), float(dt), C.byref(ms)))
+        return ms.value
+
     # ---------------------------------------------------------------- measurement hooks
     def time_rhs(self, n_launches, fused_euler=False, dt=0.0):
         ms = C.c_float(0)

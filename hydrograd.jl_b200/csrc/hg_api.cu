@@ -491,6 +491,92 @@ int hg_set_stream(hg_ctx* ctx, void* cuda_stream) {
   return HG_OK;
 }
 
+// ---------------------------------------------------------------- parameter ensembles
+int hg_ensemble_alloc(hg_ctx* ctx, int64_t M, int32_t per_member_manning) {
+  if (!ctx || M <= 0) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "ensembles need the fused path"; return HG_ERR_ARG; }
+  if ((int64_t)ctx->fh.n_tiles * M >= ((int64_t)1 << 31)) { ctx->err = "too many members for one launch"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  const size_t Ns = (size_t)ctx->fh.Ns, nI = (size_t)std::max<int64_t>(ctx->n_inletq, 1);
+  TRY(al(ctx, d.ens_Q, (size_t)M * 3 * Ns)); TRY(al(ctx, d.ens_Q2, (size_t)M * 3 * Ns));
+  if (per_member_manning) TRY(al(ctx, d.ens_mann, (size_t)M * Ns));
+  TRY(al(ctx, d.ens_Qin, (size_t)M * nI)); TRY(al(ctx, d.ens_coef, (size_t)M * nI)); TRY(al(ctx, d.ens_A, (size_t)M * nI));
+  for (int64_t m = 0; m < M && ctx->n_inletq > 0; ++m)
+    CK(ctx, cudaMemcpyAsync(d.ens_Qin.p + m * ctx->n_inletq, d.Qin.p, ctx->n_inletq * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int64_t m = 0; m < M && per_member_manning; ++m)
+    CK(ctx, cudaMemcpyAsync(d.ens_mann.p + m * Ns, d.mann.p, Ns * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->ens_members = M;
+  ctx->ens_per_member_mann = per_member_manning != 0;
+  return HG_OK;
+}
+
+int hg_ensemble_set_member(hg_ctx* ctx, int64_t m, const double* Q, const double* params, int64_t np, int32_t active) {
+  if (!ctx || !Q || m < 0 || m >= ctx->ens_members) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  const int64_t N = ctx->N, Ns = ctx->fh.Ns;
+  CK(ctx, cudaMemcpyAsync(d.stage.p, Q, 3 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TRY(hg::fused_permute(ctx, true, d.stage.p, d.ens_Q.p + m * 3 * Ns));
+  if (active == HG_PARAM_MANNING) {
+    if (!ctx->ens_per_member_mann || np != ctx->n_mat || !params || ctx->matid_ref.empty()) {
+      ctx->err = "hg_ensemble_set_member: ManningN members need per_member_manning, matID_cells and n_mat values";
+      return HG_ERR_ARG;
+    }
+    CK(ctx, cudaMemcpyAsync(d.params.p, params, np * 8, cudaMemcpyHostToDevice, ctx->stream));
+    double* keep = d.mann.p;
+    d.mann.p = d.ens_mann.p + m * Ns;            // expand the zone values straight into the member's field
+    int rc = hg::fused_bind_manning(ctx, d.params.p);
+    d.mann.p = keep;
+    if (rc != HG_OK) return rc;
+  } else if (active == HG_PARAM_Q) {
+    if (np != ctx->n_inletq || !params) { ctx->err = "hg_ensemble_set_member: wrong number of inlet discharges"; return HG_ERR_ARG; }
+    CK(ctx, cudaMemcpyAsync(d.ens_Qin.p + m * ctx->n_inletq, params, np * 8, cudaMemcpyHostToDevice, ctx->stream));
+  } else if (active != HG_PARAM_NONE) {
+    ctx->err = "hg_ensemble_set_member: only ManningN and Q vary per member";
+    return HG_ERR_ARG;
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return HG_OK;
+}
+
+int hg_ensemble_step_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
+  if (!ctx || nsteps < 0 || ctx->ens_members <= 0) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  for (int64_t s = 0; s < nsteps; ++s) {
+    TRY(hg::fused_rhs_ensemble(ctx, d.ens_Q.p, d.ens_Q2.p, true, dt));
+    std::swap(d.ens_Q.p, d.ens_Q2.p);
+  }
+  return HG_OK;
+}
+
+int hg_ensemble_rhs(hg_ctx* ctx) {
+  if (!ctx || ctx->ens_members <= 0) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  return hg::fused_rhs_ensemble(ctx, ctx->fd.ens_Q.p, ctx->fd.ens_Q2.p, false, 0.0);
+}
+
+int hg_ensemble_get_member(hg_ctx* ctx, int64_t m, int32_t what, double* out) {
+  if (!ctx || !out || m < 0 || m >= ctx->ens_members) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  TRY(download3(ctx, (what ? d.ens_Q2.p : d.ens_Q.p) + m * 3 * ctx->fh.Ns, out));
+  return check_err_flag(ctx);
+}
+
+int hg_time_ensemble(hg_ctx* ctx, int32_t n, double dt, float* ms) {
+  if (!ctx || !ms || n <= 0 || ctx->ens_members <= 0) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  TRY(hg_ensemble_step_euler(ctx, dt, n));
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return check_err_flag(ctx);
+}
+
 int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
   if (!ctx || nsteps < 0) return HG_ERR_ARG;
   if (!ctx->state_set) { ctx->err = "hg_step_euler: no resident state"; return HG_ERR_STATE; }

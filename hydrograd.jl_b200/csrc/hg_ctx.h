@@ -123,6 +123,7 @@ struct FusedDev {
   DBuf<double> ent_c, ent_n, ent_z, ent_h, Qinbar, inlet_A, zone_part;   // VJP: per boundary entry / per inlet
   DBuf<int32_t> bcell, bcell_ref, bcell_ptr, bcell_ent;                 // boundary-adjacent cells -> their entries
   DBuf<int32_t> halo_off, halo_cnt;                                     // [B]
+  DBuf<double> ens_Q, ens_Q2, ens_mann, ens_Qin, ens_coef, ens_A;       // parameter ensembles: [M][...]
   DBuf<double> halo_send, halo_recv;                                    // [6 * n_halo_entries]
   DBuf<int32_t> err;
 };
@@ -140,6 +141,8 @@ struct hg_ctx {
   int64_t n_inletq = 0, n_exith = 0, n_wall = 0, n_symm = 0, n_mat = 0, nbcell = 0;
   int64_t n_halo = 0, halo_e0 = 0, n_halo_entries = 0;
   cudaStream_t own_stream = nullptr;
+  int64_t ens_members = 0;
+  bool ens_per_member_mann = false;
   bool lam_set = false;
   hg::Consts c{};
   cudaStream_t stream = nullptr;
@@ -190,4 +193,5 @@ int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);
 int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 int fused_halo_pack(hg_ctx* ctx, bool with_lambda);
+int fused_rhs_ensemble(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 }  // namespace hg

@@ -200,6 +200,19 @@ HG_API int hg_set_lambda(hg_ctx* ctx, const double* lambda);
 HG_API int hg_vjp_resident(hg_ctx* ctx);
 HG_API int hg_get_vjp(hg_ctx* ctx, double* Qbar, double* pbar, double* ncell_bar);
 
+/* ---- parameter ensembles (sensitivity / uncertainty runs: BASELINE config "1024 parameter sets"): M independent
+ * members on ONE mesh advance in ONE launch per step (member index fastest in the CTA order, so the mesh tables of
+ * a tile are fetched from HBM once and shared through L2).  Members differ in state, and optionally in the Manning
+ * zone values (active = HG_PARAM_MANNING) or the inlet discharges (HG_PARAM_Q).  No communication: shard members
+ * across GPUs by creating one context per GPU.                                                      */
+HG_API int hg_ensemble_alloc(hg_ctx* ctx, int64_t n_members, int32_t per_member_manning);
+HG_API int hg_ensemble_set_member(hg_ctx* ctx, int64_t member, const double* Q, const double* params, int64_t n_params,
+                           int32_t active_param);
+HG_API int hg_ensemble_step_euler(hg_ctx* ctx, double dt, int64_t nsteps);
+HG_API int hg_ensemble_rhs(hg_ctx* ctx);                                /* dQdt of every member (resident)       */
+HG_API int hg_ensemble_get_member(hg_ctx* ctx, int64_t member, int32_t what /* 0 state, 1 dQdt */, double* out);
+HG_API int hg_time_ensemble(hg_ctx* ctx, int32_t n_steps, double dt, float* ms_total);
+
 /* ---- timing hooks used by bench.py (device time of the last N launches, CUDA events on the
  * ctx stream) and introspection for the roofline arithmetic.                                     */
 HG_API int hg_time_rhs(hg_ctx* ctx, int32_t n_launches, int32_t fused_euler, double dt, float* ms_total);
