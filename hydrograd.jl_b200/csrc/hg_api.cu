@@ -179,6 +179,10 @@ void hg_destroy(hg_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_cmp) cudaEventDestroy(e);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   cudaStream_t s = ctx->own_stream;
   delete ctx;  // frees the device buffers
   if (s) cudaStreamDestroy(s);
@@ -263,6 +267,17 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(al(ctx, d.Qin, ctx->n_inletq)); TRY(al(ctx, d.wse, ctx->n_exith));
     TRY(al(ctx, d.Q, 3 * Ns)); TRY(al(ctx, d.Q2, 3 * Ns)); TRY(al(ctx, d.dQ, 3 * Ns)); TRY(al(ctx, d.stage, 3 * N));
     TRY(al(ctx, d.params, npar)); TRY(al(ctx, d.err, 1));
+    TRY(up(ctx, d.tile_order, fh.tile_order));
+    if (fh.n_chunks > 1) {
+      TRY(al(ctx, d.stage_out, 3 * N));
+      CK(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+      CK(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+      ctx->ev_in.resize(fh.n_chunks); ctx->ev_cmp.resize(fh.n_chunks);
+      for (int k = 0; k < fh.n_chunks; ++k) {
+        CK(ctx, cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&ctx->ev_cmp[k], cudaEventDisableTiming));
+      }
+    }
     TRY(up(ctx, d.halo_off, h.halo_off)); TRY(up(ctx, d.halo_cnt, h.halo_cnt));
     TRY(al(ctx, d.halo_send, std::max<int64_t>(6 * ctx->n_halo_entries, 1)));
     TRY(al(ctx, d.halo_recv, std::max<int64_t>(6 * ctx->n_halo_entries, 1)));
@@ -384,11 +399,52 @@ int hg_get_rhs(hg_ctx* ctx, double* dQ) {
   return check_err_flag(ctx);
 }
 
+// Host-buffer RHS as a three-stream pipeline: the state arrives over PCIe in reference-order chunks (s_in); after each
+// chunk the compute stream scatters it into the internal order and runs every tile whose cells and halo have landed;
+// finished chunks of dQdt are gathered back and leave on s_out while later chunks are still arriving.  PCIe is full
+// duplex, so a call costs ~max(H2D, D2H) instead of their sum.  (Pinned host buffers are needed for the copies to be
+// asynchronous; pageable buffers still work, serialised by the driver.)
+static int rhs_pipelined(hg_ctx* ctx, const double* Q, double* dQdt) {
+  hg::FusedDev& d = ctx->fd;
+  const hg::FusedHost& fh = ctx->fh;
+  const int K = fh.n_chunks;
+  const int64_t N = ctx->N, csz = (N + K - 1) / K;
+  cudaStream_t sc = ctx->stream;
+  CK(ctx, cudaStreamSynchronize(sc));
+  for (int c = 0; c < K; ++c) {
+    const int64_t r0 = c * csz, r1 = std::min<int64_t>(N, r0 + csz);
+    for (int q = 0; q < 3; ++q)
+      CK(ctx, cudaMemcpyAsync(d.stage.p + q * N + r0, Q + q * N + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    CK(ctx, cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+  }
+  for (int s = 0; s < K; ++s) {
+    const int64_t r0 = s * csz, r1 = std::min<int64_t>(N, r0 + csz);
+    CK(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[s], 0));
+    TRY(hg::fused_permute_range(ctx, true, d.stage.p, d.Q.p, r0, r1));
+    if (s == K - 1 && ctx->n_inletq > 0) hg::fused_inlet_coef(ctx, d.Q.p);
+    TRY(hg::fused_rhs_tiles(ctx, d.Q.p, d.dQ.p, fh.stage_ptr[s], fh.stage_ptr[s + 1] - fh.stage_ptr[s]));
+    for (int c = 0; c < K; ++c) {
+      if (fh.chunk_done[c] != s) continue;
+      const int64_t q0 = c * csz, q1 = std::min<int64_t>(N, q0 + csz);
+      TRY(hg::fused_permute_range(ctx, false, d.dQ.p, d.stage_out.p, q0, q1));
+      CK(ctx, cudaEventRecord(ctx->ev_cmp[c], sc));
+      CK(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[c], 0));
+      for (int q = 0; q < 3; ++q)
+        CK(ctx, cudaMemcpyAsync(dQdt + q * N + q0, d.stage_out.p + q * N + q0, (q1 - q0) * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->s_out));
+  CK(ctx, cudaStreamSynchronize(sc));
+  ctx->state_set = true;
+  return check_err_flag(ctx);
+}
+
 int hg_rhs(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32_t active, double t, double* dQdt) {
   (void)t;  // unused, exactly like the reference (semi_discretize_swe_2D.jl:18)
   if (!ctx || !Q || !dQdt) return HG_ERR_ARG;
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
+  if (ctx->opt.path != 1 && ctx->fh.n_chunks > 1 && ctx->n_halo == 0) return rhs_pipelined(ctx, Q, dQdt);
   TRY(hg_set_state(ctx, Q));
   TRY(hg_rhs_resident(ctx));
   return hg_get_rhs(ctx, dQdt);

@@ -105,10 +105,17 @@ struct FusedHost {
   std::vector<double> face_nx, face_ny, face_len;
   std::vector<int32_t> bface_e;      // boundary entry of each tile's boundary faces (tile order)
   std::vector<uint16_t> cf_idx;      // [n_tiles * T * NF]
+  // host-buffer pipeline (hg_rhs): reference-order chunks arrive one by one over PCIe; a tile can run once the
+  // chunks holding its cells and halo cells have landed; a chunk can leave once its tiles are done
+  int32_t n_chunks = 1;
+  std::vector<int32_t> tile_order;   // tiles sorted by the stage at which they become ready
+  std::vector<int32_t> stage_ptr;    // [n_chunks+1] ranges of tile_order
+  std::vector<int32_t> chunk_done;   // [n_chunks] stage after which every cell of the chunk has been computed
 };
 
 struct FusedDev {
-  DBuf<int32_t> perm, iperm, tile_desc, halo, bface_e;
+  DBuf<int32_t> perm, iperm, tile_desc, halo, bface_e, tile_order;
+  DBuf<double> stage_out;
   DBuf<uint32_t> face_lr;
   DBuf<uint16_t> cf_idx;
   DBuf<double> face_nx, face_ny, face_len;
@@ -140,7 +147,8 @@ struct hg_ctx {
   int64_t N = 0, F = 0, B = 0, sumnf = 0;
   int64_t n_inletq = 0, n_exith = 0, n_wall = 0, n_symm = 0, n_mat = 0, nbcell = 0;
   int64_t n_halo = 0, halo_e0 = 0, n_halo_entries = 0;
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_cmp;
   int64_t ens_members = 0;
   bool ens_per_member_mann = false;
   bool lam_set = false;
@@ -180,6 +188,8 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
 int plain_rhs(hg_ctx* ctx, const double* dQ_in_Q, double* d_out);
 // fused path launchers (hg_fused.cu)
 int fused_rhs(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
+int fused_rhs_tiles(hg_ctx* ctx, const double* d_Q, double* d_out, int32_t tile_base, int32_t n_tiles);
+int fused_permute_range(hg_ctx* ctx, bool to_internal, const double* src, double* dst, int64_t r0, int64_t r1);
 int fused_smem_bytes(const hg_ctx* ctx);
 int fused_prepare(hg_ctx* ctx);
 bool fused_config_ok(const hg_ctx* ctx);

@@ -357,6 +357,34 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     fh.max_halo = std::max(fh.max_halo, nh);
   }
   fh.max_local = (fh.max_local + 1) & ~1;
+  // ---- stages of the host-buffer pipeline
+  {
+    const int32_t K = N >= (1 << 20) ? (int32_t)std::min<int64_t>(32, std::max<int64_t>(8, N >> 19)) : 1;   // ~0.5M cells (12 MB) per chunk
+    fh.n_chunks = K;
+    const int64_t csz = (N + K - 1) / K;
+    std::vector<int32_t> tstage(fh.n_tiles, 0);
+    for (int32_t t = 0; t < fh.n_tiles; ++t) {
+      const int32_t* d = &fh.tile_desc[(size_t)t * kTileDesc];
+      int32_t st = 0;
+      for (int32_t c = d[0]; c < d[0] + d[1]; ++c) st = std::max(st, (int32_t)(fh.perm[c] / csz));
+      for (int32_t q = d[2]; q < d[2] + d[3]; ++q) st = std::max(st, (int32_t)(fh.perm[fh.halo[q]] / csz));
+      // tiles with inlet-q faces wait for the boundary-wide conveyance sum, i.e. for the last chunk
+      for (int32_t q = 0; q < d[5] - d[9]; ++q)
+        if (ctx->bch.type[fh.bface_e[d[10] + q]] == BC_INLETQ) st = K - 1;
+      tstage[t] = st;
+    }
+    fh.tile_order.resize(fh.n_tiles);
+    std::iota(fh.tile_order.begin(), fh.tile_order.end(), 0);
+    std::stable_sort(fh.tile_order.begin(), fh.tile_order.end(), [&](int32_t x, int32_t y) { return tstage[x] < tstage[y]; });
+    fh.stage_ptr.assign(K + 1, 0);
+    for (int32_t t = 0; t < fh.n_tiles; ++t) fh.stage_ptr[tstage[t] + 1]++;
+    for (int32_t k = 0; k < K; ++k) fh.stage_ptr[k + 1] += fh.stage_ptr[k];
+    fh.chunk_done.assign(K, 0);
+    for (int64_t r = 0; r < N; ++r) {
+      const int32_t c = (int32_t)(r / csz), t = fh.iperm[r] / T;
+      fh.chunk_done[c] = std::max(fh.chunk_done[c], tstage[t]);
+    }
+  }
   if (fh.halo.empty()) fh.halo.push_back(0);
   if (fh.bface_e.empty()) fh.bface_e.push_back(0);
   return HG_OK;
