@@ -10,6 +10,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 SOURCES = [
     ("hg_host.cpp", []),
+    ("hg_srh.cpp", []),
     ("hg_api.cu", []),
     ("hg_plain.cu", ["-fmad=false"]),      # reference evaluation order, no FMA contraction
     ("hg_fused.cu", []),

@@ -213,6 +213,20 @@ HG_API int hg_ensemble_rhs(hg_ctx* ctx);                                /* dQdt 
 HG_API int hg_ensemble_get_member(hg_ctx* ctx, int64_t member, int32_t what /* 0 state, 1 dQdt */, double* out);
 HG_API int hg_time_ensemble(hg_ctx* ctx, int32_t n_steps, double dt, float* ms_total);
 
+/* ---- SRH-2D case reader + mesh / boundary / bed builder, host only, linear time (replaces, for callers without the
+ * Julia package, utilities/SRH_2D/* + meshes/mesh_2D.jl:75-652 + bc_2D.jl:50-570 + process_bed_2D.jl:9-66; the
+ * reference builder is O(N*B) and cannot feed million-cell meshes).  The case owns its arrays; fetch them by name:
+ * cell_nfaces cell_faces cell_neighbors cell_nodes (int64), cell_normals face_lengths cell_areas cell_centroids
+ * bc_normals bc_lengths zb_cells zb_ghost S0_cells ManningN_cells ManningN_zone inletQ_TotalQ exitH_WSE node_coords
+ * (float64), bc_ptr bc_ghost_ids bc_internal_cells matID_cells (int64), face_is_boundary (uint8).  Ids are 1-based
+ * (index_base = 1), N x 8 tables column-major.  dims = {N, F, B, ld, index_base, n_inletq, n_exith, n_wall, n_symm,
+ * n_mat, n_nodes, ...}.                                                                              */
+typedef struct hg_case hg_case;
+HG_API int hg_case_load_srh2d(hg_case** out, const char* srhhydro_path, char* err, int64_t errlen);
+HG_API void hg_case_free(hg_case* c);
+HG_API int hg_case_dims(const hg_case* c, int64_t* dims /* [16] */);
+HG_API int hg_case_array(const hg_case* c, const char* name, const void** ptr, int64_t* count, int32_t* dtype /* 0 f64, 1 i64, 2 u8 */);
+
 /* ---- timing hooks used by bench.py (device time of the last N launches, CUDA events on the
  * ctx stream) and introspection for the roofline arithmetic.                                     */
 HG_API int hg_time_rhs(hg_ctx* ctx, int32_t n_launches, int32_t fused_euler, double dt, float* ms_total);
