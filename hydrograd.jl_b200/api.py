@@ -217,6 +217,9 @@ class Context:
     def step_euler(self, dt, nsteps=1):
         self._ck(self.lib.hg_step_euler(self._h, float(dt), int(nsteps)))
 
+    def step_rk4(self, dt, nsteps=1):
+        self._ck(self.lib.hg_step_rk4(self._h, float(dt), int(nsteps)))
+
     def custom_ode_solve(self, Q0, params, active, t_start, t_end, dt):
         nsteps = int(np.floor((t_end - t_start) / dt + 1e-9)) + 1 if t_end >= t_start else 0
         sol = np.empty((max(nsteps, 1), 3 * self.N))   # row s = column s of the reference's 3N x nSaves `sol`

@@ -646,6 +646,32 @@ int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
   return HG_OK;
 }
 
+int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps) {
+  if (!ctx || nsteps < 0) return HG_ERR_ARG;
+  if (!ctx->state_set) { ctx->err = "hg_step_rk4: no resident state"; return HG_ERR_STATE; }
+  if (ctx->opt.path == 1) { ctx->err = "hg_step_rk4 needs the fused path (path=0)"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  const size_t n = 3 * (size_t)ctx->fh.Ns;
+  if (d.rk_k.n != n) { TRY(al(ctx, d.rk_k, n)); TRY(al(ctx, d.rk_acc, n)); TRY(al(ctx, d.rk_tmp, n)); }
+  for (int64_t s = 0; s < nsteps; ++s) {
+    // k1 = f(Q);            tmp = Q + dt/2 k1;   acc  = dt/6 k1
+    TRY(hg::fused_rhs(ctx, d.Q.p, d.rk_k.p, false, 0.0));
+    TRY(hg::fused_axpy(ctx, d.rk_tmp.p, d.Q.p, d.rk_k.p, 0.5 * dt, nullptr, d.rk_acc.p, dt / 6.0));
+    // k2 = f(tmp);          tmp = Q + dt/2 k2;   acc += dt/3 k2
+    TRY(hg::fused_rhs(ctx, d.rk_tmp.p, d.rk_k.p, false, 0.0));
+    TRY(hg::fused_axpy(ctx, d.rk_tmp.p, d.Q.p, d.rk_k.p, 0.5 * dt, d.rk_acc.p, d.rk_acc.p, dt / 3.0));
+    // k3 = f(tmp);          tmp = Q + dt k3;     acc += dt/3 k3
+    TRY(hg::fused_rhs(ctx, d.rk_tmp.p, d.rk_k.p, false, 0.0));
+    TRY(hg::fused_axpy(ctx, d.rk_tmp.p, d.Q.p, d.rk_k.p, dt, d.rk_acc.p, d.rk_acc.p, dt / 3.0));
+    // k4 = f(tmp);          Q += acc + dt/6 k4
+    TRY(hg::fused_rhs(ctx, d.rk_tmp.p, d.rk_k.p, false, 0.0));
+    TRY(hg::fused_axpy(ctx, nullptr, nullptr, d.rk_k.p, 0.0, d.rk_acc.p, d.rk_acc.p, dt / 6.0));
+    TRY(hg::fused_axpy(ctx, d.Q.p, d.Q.p, d.rk_acc.p, 1.0, nullptr, nullptr, 0.0));
+  }
+  return HG_OK;
+}
+
 int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double t0,
                         double t1, double dt, double* sol, int64_t cap, int64_t* n_saves) {
   if (!ctx || !Q0 || !sol || !n_saves || !(dt > 0.0)) return HG_ERR_ARG;

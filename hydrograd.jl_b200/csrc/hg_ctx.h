@@ -131,6 +131,7 @@ struct FusedDev {
   DBuf<int32_t> bcell, bcell_ref, bcell_ptr, bcell_ent;                 // boundary-adjacent cells -> their entries
   DBuf<int32_t> halo_off, halo_cnt;                                     // [B]
   DBuf<double> ens_Q, ens_Q2, ens_mann, ens_Qin, ens_coef, ens_A;       // parameter ensembles: [M][...]
+  DBuf<double> rk_k, rk_acc, rk_tmp;                                   // RK4 stages
   DBuf<double> halo_send, halo_recv;                                    // [6 * n_halo_entries]
   DBuf<int32_t> err;
 };
@@ -203,5 +204,6 @@ int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);
 int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 int fused_halo_pack(hg_ctx* ctx, bool with_lambda);
+int fused_axpy(hg_ctx* ctx, double* y, const double* x, const double* k, double a, const double* acc_in, double* acc_out, double b);
 int fused_rhs_ensemble(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 }  // namespace hg

@@ -178,6 +178,10 @@ HG_API int hg_sync(hg_ctx* ctx);
  * Fused into the RHS kernel (one launch per step, captured in a CUDA graph).                      */
 HG_API int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps);
 
+/* nsteps of the classical fixed-step RK4 on the resident state (what `solve(prob, RK4(), adaptive=false, dt=dt)` does
+ * in swe_2D_forward_simulation.jl:44), four fused RHS launches + three axpy kernels per step, no host round trip.   */
+HG_API int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps);
+
 /* custom_ODE_solve (custom_ODE_solvers.jl:36-95): steps over t_start:dt:t_end, saving every
  * state; sol is [3N x n_saves] column-major, n_saves_capacity columns available; *n_saves out.   */
 HG_API int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params,
