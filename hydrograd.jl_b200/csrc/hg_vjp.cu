@@ -49,36 +49,10 @@ __device__ __forceinline__ void sabs_r(double x, double& A, double& r) {  // A =
   A = fma(fma(-A, A, y), 0.5 * r, A);
 }
 
-// Reverse sweep of the face flux.  (b0,b1,b2) = adjoint of the returned flux.  Outputs aL, aR.
-__device__ __forceinline__ void roe_flux_adj(Side L, Side R, const double* zbLp, const double* zbRp, double nx, double ny,
-                                             double g, double hmin, double f0b, double f1b, double f2b, Adj& aL, Adj& aR) {
-  aL = Adj{0, 0, 0, 0, 0, 0};
-  aR = Adj{0, 0, 0, 0, 0, 0};
-  const bool dryL = L.h <= hmin, dryR = R.h <= hmin;
-  int mirror = 0;  // 1: R is the mirror image of L, 2: L is the mirror image of R
-  if (dryL || dryR) {
-    if (dryL && dryR) return;                                  // zero flux
-    const double zbL = *zbLp, zbR = *zbRp;
-    if ((L.h + zbL) < (zbR + hmin) && dryR) {
-      mirror = 1;
-      R.h = L.h; R.hu = -L.hu; R.hv = -L.hv; R.u = -L.u; R.v = -L.v; R.s = L.s;
-    } else if ((R.h + zbR) < (zbL + hmin) && dryL) {
-      mirror = 2;
-      L.h = R.h; L.hu = -R.hu; L.hv = -R.hv; L.u = -R.u; L.v = -R.v; L.s = R.s;
-    } else {
-      // one-sided physical flux of the wet side W: o0 = hu nx + hv ny, o1 = hu un + p nx, o2 = hv un + p ny
-      const Side& W = dryL ? R : L;
-      Adj& aW = dryL ? aR : aL;
-      const double un = W.u * nx + W.v * ny;
-      const double hub = f0b * nx + f1b * un, hvb = f0b * ny + f2b * un;
-      const double unb = f1b * W.hu + f2b * W.hv;
-      const double pb = f1b * nx + f2b * ny;
-      aW.u = unb * nx + hub * W.h;
-      aW.v = unb * ny + hvb * W.h;
-      aW.h = pb * g * (W.h + EPS) + hub * W.u + hvb * W.v;
-      return;
-    }
-  }
+// Reverse sweep of the face flux, main (both sides wet) branch only: straight-line code.
+// (f0b,f1b,f2b) = adjoint of the returned flux.  Outputs aL, aR = adjoints of (xi, h, u, v, s, P) per side.
+__device__ __forceinline__ void roe_adj_wet(const Side& L, const Side& R, double nx, double ny, double g, double f0b,
+                                            double f1b, double f2b, Adj& aL, Adj& aR) {
   // ---- forward recompute (same statements as dev::roe_flux)
   const double hRoe = 0.5 * (L.h + R.h);
   const double rs = fast_rcp(L.s + R.s);
@@ -142,19 +116,52 @@ __device__ __forceinline__ void roe_flux_adj(Side L, Side R, const double* zbLp,
   const double sLb = ab * L.u + bb * L.v + Sb, sRb = ab * R.u + bb * R.v + Sb;
   uLb += ab * L.s; vLb += bb * L.s; uRb += ab * R.s; vRb += bb * R.s;
   // ---- fold hu = h*u, hv = h*v into (h, u, v)
-  Adj tL, tR;
-  tL.xi = -d1b; tL.P = Pb; tL.s = sLb;
-  tL.u = uLb + huLb * L.h; tL.v = vLb + hvLb * L.h; tL.h = 0.5 * hRoeb + huLb * L.u + hvLb * L.v;
-  tR.xi = d1b; tR.P = Pb; tR.s = sRb;
-  tR.u = uRb + huRb * R.h; tR.v = vRb + hvRb * R.h; tR.h = 0.5 * hRoeb + huRb * R.u + hvRb * R.v;
-  if (mirror == 0) { aL = tL; aR = tR; }
-  else if (mirror == 1) {  // R' = (L.h, -L.u, -L.v, L.s); xi_R, P_R stay R's own (swe_2D_solvers.jl:34-36)
-    aL = tL; aL.h += tR.h; aL.u -= tR.u; aL.v -= tR.v; aL.s += tR.s;
-    aR.xi = tR.xi; aR.P = tR.P;
-  } else {                 // :49-51
-    aR = tR; aR.h += tL.h; aR.u -= tL.u; aR.v -= tL.v; aR.s += tL.s;
-    aL.xi = tL.xi; aL.P = tL.P;
+  aL.xi = -d1b; aL.P = Pb; aL.s = sLb;
+  aL.u = uLb + huLb * L.h; aL.v = vLb + hvLb * L.h; aL.h = 0.5 * hRoeb + huLb * L.u + hvLb * L.v;
+  aR.xi = d1b; aR.P = Pb; aR.s = sRb;
+  aR.u = uRb + huRb * R.h; aR.v = vRb + hvRb * R.h; aR.h = 0.5 * hRoeb + huRb * R.u + hvRb * R.v;
+}
+
+// General face: the five wet/dry branches of Riemann_2D_Roe (swe_2D_solvers.jl:16-76) around the main sweep.
+// Rare (dry fronts, boundary faces); the common path calls roe_adj_wet directly.
+__device__ __forceinline__ void roe_flux_adj(Side L, Side R, const double* zbLp, const double* zbRp, double nx, double ny,
+                                          double g, double hmin, double f0b, double f1b, double f2b, Adj* paL, Adj* paR) {
+  Adj aL = Adj{0, 0, 0, 0, 0, 0}, aR = Adj{0, 0, 0, 0, 0, 0};
+  const bool dryL = L.h <= hmin, dryR = R.h <= hmin;
+  int mirror = 0;  // 1: R is the mirror image of L, 2: L is the mirror image of R
+  if (dryL || dryR) {
+    if (dryL && dryR) { *paL = aL; *paR = aR; return; }        // zero flux
+    const double zbL = *zbLp, zbR = *zbRp;
+    if ((L.h + zbL) < (zbR + hmin) && dryR) {
+      mirror = 1;
+      R.h = L.h; R.hu = -L.hu; R.hv = -L.hv; R.u = -L.u; R.v = -L.v; R.s = L.s;
+    } else if ((R.h + zbR) < (zbL + hmin) && dryL) {
+      mirror = 2;
+      L.h = R.h; L.hu = -R.hu; L.hv = -R.hv; L.u = -R.u; L.v = -R.v; L.s = R.s;
+    } else {
+      // one-sided physical flux of the wet side W: o0 = hu nx + hv ny, o1 = hu un + p nx, o2 = hv un + p ny
+      const Side& W = dryL ? R : L;
+      Adj& aW = dryL ? aR : aL;
+      const double un = W.u * nx + W.v * ny;
+      const double hub = f0b * nx + f1b * un, hvb = f0b * ny + f2b * un;
+      const double unb = f1b * W.hu + f2b * W.hv;
+      const double pb = f1b * nx + f2b * ny;
+      aW.u = unb * nx + hub * W.h;
+      aW.v = unb * ny + hvb * W.h;
+      aW.h = pb * g * (W.h + EPS) + hub * W.u + hvb * W.v;
+      *paL = aL; *paR = aR;
+      return;
+    }
   }
+  roe_adj_wet(L, R, nx, ny, g, f0b, f1b, f2b, aL, aR);
+  if (mirror == 1) {         // R' = (L.h, -L.u, -L.v, L.s); xi_R, P_R stay R's own (swe_2D_solvers.jl:34-36)
+    aL.h += aR.h; aL.u -= aR.u; aL.v -= aR.v; aL.s += aR.s;
+    aR.h = 0.0; aR.u = 0.0; aR.v = 0.0; aR.s = 0.0;
+  } else if (mirror == 2) {  // :49-51
+    aR.h += aL.h; aR.u -= aL.u; aR.v -= aL.v; aR.s += aL.s;
+    aL.h = 0.0; aL.u = 0.0; aL.v = 0.0; aL.s = 0.0;
+  }
+  *paL = aL; *paR = aR;
 }
 
 template <class Cfg>
@@ -247,8 +254,27 @@ __global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_const
   }
   __syncthreads();
 
-  // ---- phase 2: face adjoints
-  for (int32_t f = tid; f < nf; f += kThreads) {
+  // ---- phase 2a: interior faces (the common case) -- straight-line code, no boundary / orientation logic
+  for (int32_t f = tid; f < nint; f += kThreads) {
+    const uint32_t lr = sm.lr[f];
+    const int32_t lL = lr & 0xFFFFu, lR = lr >> 16;
+    const double nx = sm.o[0][f], ny = sm.o[1][f], len = sm.o[2][f];
+    Side L, R;
+    L.xi = sm.xi[lL]; L.h = sm.h[lL]; L.u = sm.u[lL]; L.v = sm.v[lL]; L.s = sm.s[lL]; L.P = sm.P[lL];
+    L.hu = __dmul_rn(L.h, L.u); L.hv = __dmul_rn(L.h, L.v);
+    R.xi = sm.xi[lR]; R.h = sm.h[lR]; R.u = sm.u[lR]; R.v = sm.v[lR]; R.s = sm.s[lR]; R.P = sm.P[lR];
+    R.hu = __dmul_rn(R.h, R.u); R.hv = __dmul_rn(R.h, R.v);
+    const double f0b = (sm.m0[lR] - sm.m0[lL]) * len, f1b = (sm.m1[lR] - sm.m1[lL]) * len, f2b = (sm.m2[lR] - sm.m2[lL]) * len;
+    Adj aL, aR;
+    if (__builtin_expect(L.h <= hs || R.h <= hs, 0)) roe_flux_adj(L, R, &sm.zb[lL], &sm.zb[lR], nx, ny, g, hs, f0b, f1b, f2b, &aL, &aR);
+    else roe_adj_wet(L, R, nx, ny, g, f0b, f1b, f2b, aL, aR);
+    sm.o[0][f] = aL.xi; sm.o[1][f] = aL.h; sm.o[2][f] = aL.u; sm.o[3][f] = aL.v; sm.o[4][f] = aL.s; sm.o[5][f] = aL.P;
+    sm.o[6][f] = aR.xi; sm.o[7][f] = aR.h; sm.o[8][f] = aR.u; sm.o[9][f] = aR.v; sm.o[10][f] = aR.s; sm.o[11][f] = aR.P;
+  }
+  // ---- phase 2b: boundary faces (physical boundaries and halo faces): rebuild the ghost state, sweep, pull back.
+  // A second inlined copy of the sweep: its bits may differ from phase 2a's in the last place, so a halo face is
+  // reproduced across rank counts to ~1e-15, not bit for bit (the RHS kernel is bit-identical).
+  for (int32_t f = nint + tid; f < nf; f += kThreads) {
     const uint32_t lr = sm.lr[f];
     const int32_t lL = lr & 0xFFFFu, lR = lr >> 16;
     double nx = sm.o[0][f], ny = sm.o[1][f];
@@ -262,11 +288,7 @@ __global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_const
     double zbg = 0.0, hstg = 0.0, bnx = 0.0, bny = 0.0, vn = 0.0, wet = 0.0, mannc = 1.0;
     int32_t ty = -1, e = 0;
     bool flip = false, exit_free = false;
-    if (f < nint) {
-      R.xi = sm.xi[lR]; R.h = sm.h[lR]; R.u = sm.u[lR]; R.v = sm.v[lR]; R.s = sm.s[lR]; R.P = sm.P[lR];
-      R.hu = __dmul_rn(R.h, R.u); R.hv = __dmul_rn(R.h, R.v);
-      f0b += sm.m0[lR]; f1b += sm.m1[lR]; f2b += sm.m2[lR];
-    } else {
+    {
       // boundary face: rebuild the ghost state (bc_2D.jl:640-834)
       e = __ldg(a.bface_e + bfp + (f - nint));
       ty = a.bc_type[e];
@@ -313,7 +335,7 @@ __global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_const
       nx = -nx; ny = -ny; f0b = -f0b; f1b = -f1b; f2b = -f2b;
     }
     Adj aL, aR;
-    roe_flux_adj(L, R, zbLp, zbRp, nx, ny, g, hs, f0b, f1b, f2b, aL, aR);
+    roe_flux_adj(L, R, zbLp, zbRp, nx, ny, g, hs, f0b, f1b, f2b, &aL, &aR);
     if (flip) { const Adj ta = aL; aL = aR; aR = ta; const Side tmp = L; L = R; R = tmp; }
     if (ty >= 0) {
       double ec = 0.0, en = 0.0, ez = 0.0;
