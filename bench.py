@@ -47,23 +47,41 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~1 kHz; nvidia-smi as a fallback)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
 
     def run(self):
+        nv = self.nv
         while not self._stop_evt.is_set():
             try:
+                if nv is not None:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    flags = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+                    self.rows.append([str(sm), str(self.max_sm)] + ["Active" if r & m else "Not Active" for _, m in flags])
+                    self._stop_evt.wait(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -73,7 +91,16 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nv is not None else "nvidia-smi"}
+
+
+def measured_traffic(kernel, N):
+    """DRAM bytes per launch from the committed `ncu --set full` capture of the same kernel (profiles/), scaled per cell."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p)).get(kernel)
+    return None if t is None else t["dram_bytes_per_cell"] * N
 
 
 def algorithmic_bytes(N, F, sum_nf):
@@ -264,11 +291,11 @@ def main():
     abytes = algorithmic_bytes(N, F, st["sum_cell_faces"])
     achieved = abytes / (ms_rhs_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_fused_rhs", "algorithmic_bytes_per_launch": abytes,
+                "traffic": measured_traffic("k_fused_rhs", N), "kernel": "k_fused_rhs", "algorithmic_bytes_per_launch": abytes,
                 "bytes_per_cell": abytes / N, "peak_source": peak_src, "ms_per_launch": ms_rhs_step}
     vbytes = abytes + 32 * N          # RHS inputs re-read + lambda (24 B) + Qbar (24 B) + nbar (8 B) - dQ (24 B)
     vach = vbytes / (ms_vjp_step * 1e-3) / 1e9
-    roofline_vjp = {"bound": "hbm", "achieved": vach, "peak": peak, "unit": "GB/s", "frac": vach / peak, "traffic": None,
+    roofline_vjp = {"bound": "hbm", "achieved": vach, "peak": peak, "unit": "GB/s", "frac": vach / peak, "traffic": measured_traffic("k_fused_vjp", N),
                     "kernel": "k_fused_vjp", "algorithmic_bytes_per_launch": vbytes, "bytes_per_cell": vbytes / N,
                     "ms_per_launch": ms_vjp_step}
 
