@@ -88,3 +88,27 @@ def test_vjp_bruteforce_dot_identity(oracle_lib):
     _, jv = o.jvp(Q, v, p, vp, 1)
     lhs, rhs = lam @ jv, Qbar @ v + pbar @ vp
     assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), 1.0)
+
+
+@pytest.mark.slow
+def test_sensitivity_fixture_pins_the_derivative(oracle_lib):
+    """The reference's committed sensitivity_results.json (ForwardDiff through adaptive Tsit5, d(final state)/d(n_zone),
+    sensitivity_analysis/ManningN/oneD_channel_with_bump) against forward sensitivities propagated through explicit
+    Euler with the oracle's dual-number JVP: at the (near-steady) final time they agree to ~2e-5 relative.  This is the
+    one reference fixture that pins the DERIVATIVE of the path (softly)."""
+    c = cases.load("oneD_bump_sens")
+    o = Oracle(R.flatten(c))
+    S = np.load(cases.GOLD + "/oneD_bump_sens/sensitivity.npz")["sensitivity_results"].reshape(3, 600).T
+    p = np.array([0.03, 0.02, 0.03])
+    dt, nsteps = 0.02, 10000                      # t = 200 s, as in the case's run_control.json
+    Q = c.Q0.copy()
+    dQ = np.zeros((3, 600))
+    eye = np.eye(3)
+    for _ in range(nsteps):
+        f = o.rhs(Q, p, 2)
+        for k in (1, 2):                           # zone 0 (default material) owns no cell: its column is zero
+            dQ[k] += dt * o.jvp(Q, dQ[k], p, eye[k], 2)[1]
+        Q = Q + dt * f
+    assert np.abs(S[:, 0]).max() == 0.0
+    for k in (1, 2):
+        assert np.abs(dQ[k] - S[:, k]).max() <= 1e-4 * np.abs(S[:, k]).max()
