@@ -672,6 +672,50 @@ int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps) {
   return HG_OK;
 }
 
+int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double dt, int64_t nsteps,
+                     const double* lambda_T, double* Q_T, double* Q0bar, double* pbar) {
+  if (!ctx || !Q0 || !lambda_T || !Q0bar || nsteps < 1 || !(dt > 0.0)) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "hg_euler_adjoint needs the fused path"; return HG_ERR_ARG; }
+  if (ctx->n_halo > 0) { ctx->err = "hg_euler_adjoint: multi-rank contexts are not supported"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  TRY(bind_params(ctx, params, np, active));
+  if (ctx->active != HG_PARAM_NONE && !pbar) { ctx->err = "hg_euler_adjoint: pbar is NULL"; return HG_ERR_ARG; }
+  hg::FusedDev& d = ctx->fd;
+  const size_t n3 = 3 * (size_t)ctx->fh.Ns;
+  const int64_t npar = ctx->active == HG_PARAM_NONE ? 0 : ctx->n_params;
+  // checkpoint spacing ~ sqrt(nsteps): (nsteps/C + C) resident states
+  const int64_t C = std::max<int64_t>(1, (int64_t)std::ceil(std::sqrt((double)nsteps)));
+  const int64_t nck = (nsteps + C - 1) / C;
+  hg::DBuf<double> ck, seg, lam, lam_tmp, pacc;
+  CK(ctx, ck.alloc((size_t)nck * n3)); CK(ctx, seg.alloc((size_t)(C + 1) * n3));
+  CK(ctx, lam.alloc(n3)); CK(ctx, lam_tmp.alloc(n3)); CK(ctx, pacc.alloc((size_t)std::max<int64_t>(npar, 1)));
+  CK(ctx, cudaMemsetAsync(pacc.p, 0, pacc.bytes(), ctx->stream));
+  CK(ctx, cudaMemsetAsync(lam.p, 0, lam.bytes(), ctx->stream));
+  // ---- forward sweep, storing the state at the start of every segment
+  TRY(hg_set_state(ctx, Q0));
+  for (int64_t s = 0; s < nsteps; ++s) {
+    if (s % C == 0) CK(ctx, cudaMemcpyAsync(ck.p + (s / C) * n3, d.Q.p, n3 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    TRY(hg::fused_rhs(ctx, d.Q.p, d.Q2.p, true, dt));
+    std::swap(d.Q.p, d.Q2.p);
+  }
+  if (Q_T) TRY(download3(ctx, d.Q.p, Q_T));
+  // ---- terminal cotangent (reference order -> internal)
+  CK(ctx, cudaMemcpyAsync(d.stage.p, lambda_T, 3 * ctx->N * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TRY(hg::fused_permute(ctx, true, d.stage.p, lam.p));
+  // ---- reverse sweep, one segment at a time
+  for (int64_t k = nck - 1; k >= 0; --k) {
+    const int64_t s0 = k * C, s1 = std::min<int64_t>(nsteps, s0 + C);
+    CK(ctx, cudaMemcpyAsync(seg.p, ck.p + k * n3, n3 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int64_t s = s0; s < s1; ++s) TRY(hg::fused_rhs(ctx, seg.p + (s - s0) * n3, seg.p + (s - s0 + 1) * n3, true, dt));
+    for (int64_t s = s1 - 1; s >= s0; --s)
+      TRY(hg::fused_adjoint_step(ctx, seg.p + (s - s0) * n3, seg.p + (s - s0 + 1) * n3, lam.p, lam_tmp.p, pacc.p, npar, dt));
+  }
+  TRY(download3(ctx, lam.p, Q0bar));
+  if (npar > 0) CK(ctx, cudaMemcpyAsync(pbar, pacc.p, npar * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_err_flag(ctx);
+}
+
 int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double t0,
                         double t1, double dt, double* sol, int64_t cap, int64_t* n_saves) {
   if (!ctx || !Q0 || !sol || !n_saves || !(dt > 0.0)) return HG_ERR_ARG;

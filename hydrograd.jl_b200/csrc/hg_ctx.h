@@ -204,6 +204,7 @@ int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);
 int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 int fused_halo_pack(hg_ctx* ctx, bool with_lambda);
+int fused_adjoint_step(hg_ctx* ctx, const double* Qn, const double* Qn1, double* lam, double* lam_tmp, double* pbar_acc, int64_t np, double dt);
 int fused_axpy(hg_ctx* ctx, double* y, const double* x, const double* k, double a, const double* acc_in, double* acc_out, double b);
 int fused_rhs_ensemble(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 }  // namespace hg

@@ -182,6 +182,14 @@ HG_API int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps);
  * in swe_2D_forward_simulation.jl:44), four fused RHS launches + three axpy kernels per step, no host round trip.   */
 HG_API int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps);
 
+/* Discrete adjoint of nsteps of hg_step_euler (what SciMLSensitivity + Zygote produce for the "customized" Euler
+ * solver inside compute_loss_inversion, swe_2D_inversion.jl:339): given lambda_T = d loss / d Q(T) it returns
+ * Q0bar = d loss / d Q0 [3N] and pbar = d loss / d params [n_params] (NULL when active_param = NONE).  The forward
+ * sweep keeps sqrt(nsteps)-spaced checkpoints on the device, the reverse sweep recomputes each segment and calls the
+ * VJP kernel once per step; the dry mask of custom_ODE_update_cells is a constant selector, like every other clamp. */
+HG_API int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params, int32_t active_param,
+                     double dt, int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar);
+
 /* custom_ODE_solve (custom_ODE_solvers.jl:36-95): steps over t_start:dt:t_end, saving every
  * state; sol is [3N x n_saves] column-major, n_saves_capacity columns available; *n_saves out.   */
 HG_API int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params,
