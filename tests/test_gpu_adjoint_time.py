@@ -68,3 +68,28 @@ def test_euler_adjoint_with_dry_mask(hg):
     assert np.abs(QT - QT_ref).max() <= 1e-9 * max(1.0, np.abs(QT_ref).max())
     lhs, rhs = lamT @ DT, Q0bar @ v
     assert abs(lhs - rhs) <= 1e-9 * np.abs(lamT * DT).sum()
+
+
+def test_inversion_loss_gradient_savannah(hg):
+    """Config C4: Manning's-n inversion step on the Savannah mesh -- loss (swe_2D_inversion.jl:388-467) and its gradient
+    from the device forward + adjoint sweeps, against central finite differences of the oracle's Euler run."""
+    from hydrograd_jl_b200 import inversion as inv
+    c, t = cases.load("savannah"), cases.truth("savannah")
+    flat = R.flatten(c)
+    o = Oracle(flat)
+    observed = dict(WSE_truth=t["wse_truth"], u_truth=t["u_truth"], v_truth=t["v_truth"], zb_cell_truth=t["zb_cell_truth"])
+    p = np.full(6, 0.03)                                   # the inversion's initial guess (SURVEY 8d, C4)
+    dt, nsteps = 0.01, 150
+    ctx = hg.Context(flat)
+    loss, parts, grad = inv.loss_and_gradient(ctx, flat, c.Q0, p, "ManningN", observed, dt, nsteps, bound=(0.01, 0.06))
+
+    def oracle_loss(pp):
+        QT = o.euler(c.Q0, dt, nsteps, pp, 2)
+        return inv.loss_terms(QT, pp, observed, flat, "ManningN", bound=(0.01, 0.06))[0]
+
+    assert abs(loss - oracle_loss(p)) <= 1e-10 * loss
+    fd = np.zeros(6)
+    for k in range(6):
+        e = np.zeros(6); e[k] = 1e-6
+        fd[k] = (oracle_loss(p + e) - oracle_loss(p - e)) / 2e-6
+    assert np.abs(grad - fd).max() <= 1e-5 * np.abs(fd).max(), (grad, fd)
