@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--cells-m", type=float, default=16.0, help="million cells per GPU")
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the fused kernel (tuning)")
+    ap.add_argument("--pipeline", type=int, default=0, help="1 = persistent pipelined RHS kernel")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
@@ -215,7 +216,7 @@ def main():
     N, F = flat["n_cells"], flat["n_faces"]
     log(f"[rank {rank}] mesh: N={N} F={F} ({time.time() - t0:.1f}s)")
     t0 = time.time()
-    ctx = hg.Context(flat, device=local, tile_cells=args.tile, threads=args.threads)
+    ctx = hg.Context(flat, device=local, tile_cells=args.tile, threads=args.threads, pipeline=args.pipeline)
     st = ctx.mesh_stats()
     log(f"[rank {rank}] context: {st} ({time.time() - t0:.1f}s)")
     ctx.set_state(Q0)

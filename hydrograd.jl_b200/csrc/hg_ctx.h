@@ -150,6 +150,7 @@ struct hg_ctx {
   int64_t n_halo = 0, halo_e0 = 0, n_halo_entries = 0;
   cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_cmp;
+  int n_sm = 148;
   int64_t ens_members = 0;
   bool ens_per_member_mann = false;
   bool lam_set = false;

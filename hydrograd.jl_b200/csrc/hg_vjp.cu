@@ -124,14 +124,13 @@ __device__ __forceinline__ void roe_adj_wet(const Side& L, const Side& R, double
 
 // General face: the five wet/dry branches of Riemann_2D_Roe (swe_2D_solvers.jl:16-76) around the main sweep.
 // Rare (dry fronts, boundary faces); the common path calls roe_adj_wet directly.
-__device__ __forceinline__ void roe_flux_adj(Side L, Side R, const double* zbLp, const double* zbRp, double nx, double ny,
+__device__ __forceinline__ void roe_flux_adj(Side L, Side R, double zbL, double zbR, double nx, double ny,
                                           double g, double hmin, double f0b, double f1b, double f2b, Adj* paL, Adj* paR) {
   Adj aL = Adj{0, 0, 0, 0, 0, 0}, aR = Adj{0, 0, 0, 0, 0, 0};
   const bool dryL = L.h <= hmin, dryR = R.h <= hmin;
   int mirror = 0;  // 1: R is the mirror image of L, 2: L is the mirror image of R
   if (dryL || dryR) {
     if (dryL && dryR) { *paL = aL; *paR = aR; return; }        // zero flux
-    const double zbL = *zbLp, zbR = *zbRp;
     if ((L.h + zbL) < (zbR + hmin) && dryR) {
       mirror = 1;
       R.h = L.h; R.hu = -L.hu; R.hv = -L.hv; R.u = -L.u; R.v = -L.v; R.s = L.s;
@@ -164,25 +163,39 @@ __device__ __forceinline__ void roe_flux_adj(Side L, Side R, const double* zbLp,
   *paL = aL; *paR = aR;
 }
 
-template <class Cfg>
+template <int T, int ML, int MF, int NF>
 struct __align__(16) VjpSmem {
   uint64_t bar[2];
-  double xi[Cfg::ML], h[Cfg::ML], zb[Cfg::ML], u[Cfg::ML], v[Cfg::ML], s[Cfg::ML], P[Cfg::ML];
-  double m0[Cfg::ML], m1[Cfg::ML], m2[Cfg::ML];           // mu = lambda / area (lambda itself on arrival)
-  double o[12][Cfg::MF];                                  // rows 0..2: nx, ny, len on arrival; then face adjoints
-  double area[Cfg::T], mann[Cfg::T], sx[Cfg::T], sy[Cfg::T], hst[Cfg::T];
-  uint32_t lr[Cfg::MF];
-  uint16_t cf[Cfg::T * Cfg::NF];
+  double xi[ML], h[ML], u[ML], v[ML], s[ML], P[ML];       // staged forward state (clamped, derived)
+  double rh[ML], rs2[ML], dP[ML];                         // 1/h, 1/(2 s), dP/dxi = g (xi + eps + hstill): the derived map's transpose
+  double m0[ML], m1[ML], m2[ML];                          // mu = lambda / area (lambda itself on arrival)
+  double o[6][MF];                                        // rows 0..2: nx, ny, len on arrival; then (xi, q_x, q_y) adjoints, L side | R side
+  double area[T], mann[T], sx[T], sy[T];
+  uint32_t lr[MF];
+  uint16_t cf[T * NF];
 };
 
-// The adjoint sweep needs ~170 registers un-capped, which leaves ONE 5-warp CTA per SM (per-SMSP register file);
-// 192 threads capped at 168 registers keep two CTAs (3 warps per SMSP) resident next to the 96 KB of shared memory.
-constexpr int kVjpThreads = 192;
-template <class Cfg>
-__global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_constant__ VjpArgs a) {
+// adjoints of one side's staged variables (xi, h, u, v, s, P) -> adjoints of its raw state (xi, q_x, q_y): the
+// transpose of the derived map u = hu/h, v = hv/h, s = sqrt(h+eps), P(xi) and of the dry clamp
+// (semi_discretize_swe_2D.jl:104-106: a clamped cell's h, q are constants; xi itself is never clamped).
+__device__ __forceinline__ void fold_side(const Adj& a, double h, double u, double v, double rh, double rs2, double dP,
+                                          double hs, double& xb, double& qxb, double& qyb) {
+  const bool wet = h > hs;                                 // clamped h == h_small  <=>  the cell was clamped
+  const double ht = fma(a.s, rs2, fma(-(a.u * u + a.v * v), rh, a.h));
+  const double x0 = fma(a.P, dP, a.xi);
+  xb = wet ? x0 + ht : x0;
+  qxb = wet ? a.u * rh : 0.0;
+  qyb = wet ? a.v * rh : 0.0;
+}
+
+// The reverse sweep keeps ~70 doubles live; TH x MB is picked per tile size so that MB CTAs fit next to each other
+// in shared memory and TH*MB*regs <= 64K (vjp_pick below).
+template <int T, int ML, int MF, int NF, int TH, int MB>
+__global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ VjpArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  VjpSmem<Cfg>& sm = *reinterpret_cast<VjpSmem<Cfg>*>(smraw);
-  constexpr int T = Cfg::T, NF = Cfg::NF, kThreads = kVjpThreads;
+  using Smem = VjpSmem<T, ML, MF, NF>;
+  Smem& sm = *reinterpret_cast<Smem*>(smraw);
+  constexpr int kThreads = TH;
 
   const int t = blockIdx.x, tid = threadIdx.x;
   const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc));
@@ -194,17 +207,18 @@ __global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_const
   const int32_t ncp = (nc + 1) & ~1;
   const double g = a.c.g, hs = a.c.h_small;
   const int64_t Ns = a.Ns;
+  // bed elevation of a tile-local cell: only the (rare) faces with a dry side and boundary faces read it
+  auto zb_local = [&](int32_t l) { return a.zb[l < ncp ? c0 + l : __ldg(a.halo + hp + (l - ncp))]; };
 
   if (tid == 0) mbar_init(sm.bar, 1);
   __syncthreads();
   if (tid == 0) {
     const uint32_t cb = (uint32_t)ncp * 8u, fb = (uint32_t)nfp * 8u;
-    mbar_expect_tx(sm.bar, 12u * cb + 3u * fb + (uint32_t)nfp * 4u + (uint32_t)(T * NF) * 2u);
+    mbar_expect_tx(sm.bar, 11u * cb + 3u * fb + (uint32_t)nfp * 4u + (uint32_t)(T * NF) * 2u);
     bulk_g2s(sm.xi, a.Q + c0, cb, sm.bar);
-    bulk_g2s(sm.u, a.Q + Ns + c0, cb, sm.bar);
-    bulk_g2s(sm.v, a.Q + 2 * Ns + c0, cb, sm.bar);
-    bulk_g2s(sm.hst, a.hstill + c0, cb, sm.bar);
-    bulk_g2s(sm.zb, a.zb + c0, cb, sm.bar);
+    bulk_g2s(sm.u, a.Q + Ns + c0, cb, sm.bar);             // raw q_x; u replaces it in place
+    bulk_g2s(sm.v, a.Q + 2 * Ns + c0, cb, sm.bar);         // raw q_y
+    bulk_g2s(sm.dP, a.hstill + c0, cb, sm.bar);            // raw hstill; dP replaces it in place
     bulk_g2s(sm.m0, a.lam + c0, cb, sm.bar);
     bulk_g2s(sm.m1, a.lam + Ns + c0, cb, sm.bar);
     bulk_g2s(sm.m2, a.lam + 2 * Ns + c0, cb, sm.bar);
@@ -218,37 +232,38 @@ __global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_const
     bulk_g2s(sm.sy, a.S0y + c0, cb, sm.bar);
     bulk_g2s(sm.cf, a.cf_idx + (size_t)t * (T * NF), (uint32_t)(T * NF) * 2u, sm.bar);
   }
+  // clamp + derived values + the factors of the derived map's transpose, for local cell l
+  auto stage_cell = [&](int32_t l, double xi, double qx, double qy, double hst) {
+    const double h0 = xi + hst;
+    const bool dry = h0 <= hs;
+    const double h = dry ? hs : h0;
+    const double rh = fast_rcp(h);
+    const double y = h + EPS;
+    const double r = fast_rsqrt(y);
+    double s = y * r;
+    s = fma(fma(-s, s, y), 0.5 * r, s);
+    const double xe = xi + EPS;
+    sm.h[l] = h; sm.u[l] = dry ? 0.0 : qx * rh; sm.v[l] = dry ? 0.0 : qy * rh; sm.s[l] = s;
+    sm.P[l] = 0.5 * g * fma(xe, xe, 2.0 * xi * hst);
+    sm.rh[l] = rh; sm.rs2[l] = 0.5 * r; sm.dP[l] = g * (xe + hst);
+  };
   // halo cells: state + lambda/area
   for (int32_t k = tid; k < nh; k += kThreads) {
     const int32_t gi = __ldg(a.halo + hp + k);
-    Side s;
-    s.xi = a.Q[gi];
-    const double qx = a.Q[Ns + gi], qy = a.Q[2 * Ns + gi];
+    const double xi = a.Q[gi], qx = a.Q[Ns + gi], qy = a.Q[2 * Ns + gi];
     const double hst = a.hstill[gi];
     const double rA = fast_rcp(a.area[gi]);
     const double l0 = a.lam[gi], l1 = a.lam[Ns + gi], l2 = a.lam[2 * Ns + gi];
-    s.zb = a.zb[gi];
-    const double h = s.xi + hst;
-    const bool dry = h <= hs;
-    s.h = dry ? hs : h; s.hu = dry ? 0.0 : qx; s.hv = dry ? 0.0 : qy;
-    derive(s, hst, g);
     const int32_t l = ncp + k;
-    sm.xi[l] = s.xi; sm.h[l] = s.h; sm.zb[l] = s.zb; sm.u[l] = s.u; sm.v[l] = s.v; sm.s[l] = s.s; sm.P[l] = s.P;
+    sm.xi[l] = xi;
+    stage_cell(l, xi, qx, qy, hst);
     sm.m0[l] = l0 * rA; sm.m1[l] = l1 * rA; sm.m2[l] = l2 * rA;
   }
   mbar_wait(sm.bar, 0);
 
-  // ---- phase 1: owned cells.  lambda stays in registers for phase 3 (<= 2 cells per thread would do, but keep it
-  // simple: re-read from global in phase 3 is avoided by storing raw q and lambda back-computed: lambda = mu * area)
+  // ---- phase 1: owned cells, in place
   for (int32_t l = tid; l < nc; l += kThreads) {
-    Side s;
-    s.xi = sm.xi[l];
-    const double hst = sm.hst[l];
-    const double h = s.xi + hst;
-    const bool dry = h <= hs;
-    s.h = dry ? hs : h; s.hu = dry ? 0.0 : sm.u[l]; s.hv = dry ? 0.0 : sm.v[l];
-    derive(s, hst, g);
-    sm.h[l] = s.h; sm.u[l] = s.u; sm.v[l] = s.v; sm.s[l] = s.s; sm.P[l] = s.P;
+    stage_cell(l, sm.xi[l], sm.u[l], sm.v[l], sm.dP[l]);
     const double rA = fast_rcp(sm.area[l]);
     sm.m0[l] *= rA; sm.m1[l] *= rA; sm.m2[l] *= rA;
   }
@@ -266,113 +281,110 @@ __global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_const
     R.hu = __dmul_rn(R.h, R.u); R.hv = __dmul_rn(R.h, R.v);
     const double f0b = (sm.m0[lR] - sm.m0[lL]) * len, f1b = (sm.m1[lR] - sm.m1[lL]) * len, f2b = (sm.m2[lR] - sm.m2[lL]) * len;
     Adj aL, aR;
-    if (__builtin_expect(L.h <= hs || R.h <= hs, 0)) roe_flux_adj(L, R, &sm.zb[lL], &sm.zb[lR], nx, ny, g, hs, f0b, f1b, f2b, &aL, &aR);
+    if (__builtin_expect(L.h <= hs || R.h <= hs, 0)) roe_flux_adj(L, R, zb_local(lL), zb_local(lR), nx, ny, g, hs, f0b, f1b, f2b, &aL, &aR);
     else roe_adj_wet(L, R, nx, ny, g, f0b, f1b, f2b, aL, aR);
-    sm.o[0][f] = aL.xi; sm.o[1][f] = aL.h; sm.o[2][f] = aL.u; sm.o[3][f] = aL.v; sm.o[4][f] = aL.s; sm.o[5][f] = aL.P;
-    sm.o[6][f] = aR.xi; sm.o[7][f] = aR.h; sm.o[8][f] = aR.u; sm.o[9][f] = aR.v; sm.o[10][f] = aR.s; sm.o[11][f] = aR.P;
+    double xb, qxb, qyb;
+    fold_side(aL, L.h, L.u, L.v, sm.rh[lL], sm.rs2[lL], sm.dP[lL], hs, xb, qxb, qyb);
+    sm.o[0][f] = xb; sm.o[1][f] = qxb; sm.o[2][f] = qyb;
+    fold_side(aR, R.h, R.u, R.v, sm.rh[lR], sm.rs2[lR], sm.dP[lR], hs, xb, qxb, qyb);
+    sm.o[3][f] = xb; sm.o[4][f] = qxb; sm.o[5][f] = qyb;
   }
   // ---- phase 2b: boundary faces (physical boundaries and halo faces): rebuild the ghost state, sweep, pull back.
   // A second inlined copy of the sweep: its bits may differ from phase 2a's in the last place, so a halo face is
   // reproduced across rank counts to ~1e-15, not bit for bit (the RHS kernel is bit-identical).
   for (int32_t f = nint + tid; f < nf; f += kThreads) {
     const uint32_t lr = sm.lr[f];
-    const int32_t lL = lr & 0xFFFFu, lR = lr >> 16;
+    const int32_t lL = lr & 0xFFFFu;
     double nx = sm.o[0][f], ny = sm.o[1][f];
     const double len = sm.o[2][f];
     Side L, R;
     L.xi = sm.xi[lL]; L.h = sm.h[lL]; L.u = sm.u[lL]; L.v = sm.v[lL]; L.s = sm.s[lL]; L.P = sm.P[lL];
     L.hu = __dmul_rn(L.h, L.u); L.hv = __dmul_rn(L.h, L.v);   // never contracted into the flux FMAs
     double f0b = -sm.m0[lL], f1b = -sm.m1[lL], f2b = -sm.m2[lL];
-    const double* zbLp = &sm.zb[lL];
-    const double* zbRp = &sm.zb[lR < Cfg::ML ? lR : 0];
-    double zbg = 0.0, hstg = 0.0, bnx = 0.0, bny = 0.0, vn = 0.0, wet = 0.0, mannc = 1.0;
-    int32_t ty = -1, e = 0;
+    double zbl = a.zb[c0 + lL];                                // boundary faces always touch an owned cell
+    // boundary face: rebuild the ghost state (bc_2D.jl:640-834)
+    const int32_t e = __ldg(a.bface_e + bfp + (f - nint));
+    const int32_t ty = a.bc_type[e];
+    const int32_t kgrp = a.bc_group[e];
+    const double bnx = a.bc_nx[e], bny = a.bc_ny[e];
+    const double hstg = a.bc_hstill[e];
+    double zbr = a.bc_zb[e];
+    double vn = 0.0, wet = 0.0, mannc = 1.0;
     bool flip = false, exit_free = false;
-    {
-      // boundary face: rebuild the ghost state (bc_2D.jl:640-834)
-      e = __ldg(a.bface_e + bfp + (f - nint));
-      ty = a.bc_type[e];
-      const int32_t kgrp = a.bc_group[e];
-      bnx = a.bc_nx[e]; bny = a.bc_ny[e];
-      hstg = a.bc_hstill[e];
-      zbg = a.bc_zb[e];
-      zbRp = &zbg;
-      if (ty == BC_INLETQ) {
-        wet = L.h > hs ? 1.0 : 0.0;
-        mannc = sm.mann[lL];
-        vn = a.inlet_coef[kgrp] * a.bc_l23[e] / mannc;
-        R.h = L.h; R.hu = -L.h * vn * bnx * wet; R.hv = -L.h * vn * bny * wet;
-      } else if (ty == BC_EXITH) {
-        const double hg = a.wse[kgrp] - sm.zb[lL];
-        exit_free = hg > hs;                       // max(h_small, .) passes the derivative only when not clamped
-        R.h = exit_free ? hg : hs; R.hu = L.hu; R.hv = L.hv;
-      } else if (ty == BC_WALL) {
-        R.h = L.h; R.hu = -L.hu; R.hv = -L.hv;
-      } else if (ty == BC_SYMM) {
-        const double vdn = L.hu * bnx + L.hv * bny;
-        R.h = L.h; R.hu = L.hu - 2.0 * vdn * bnx; R.hv = L.hv - 2.0 * vdn * bny;
-      } else {
-        // remote cell: state and cotangent arrived through the halo buffers; its own adjoint is computed by its owner
-        const int32_t off = a.halo_off[e], n = a.halo_cnt[e];
-        const double xr = a.halo_recv[off], qxr = a.halo_recv[off + n], qyr = a.halo_recv[off + 2 * n];
-        const double rAr = fast_rcp(a.bc_l23[e]);          // remote cell area rides in l23
-        // mu_remote is a rounded product exactly like an in-tile cell's (no FMA contraction with the sum)
-        f0b += __dmul_rn(a.halo_recv[off + 3 * n], rAr); f1b += __dmul_rn(a.halo_recv[off + 4 * n], rAr);
-        f2b += __dmul_rn(a.halo_recv[off + 5 * n], rAr);
-        const double hr = xr + hstg;
-        const bool dryr = hr <= hs;
-        R.h = dryr ? hs : hr; R.hu = dryr ? 0.0 : qxr; R.hv = dryr ? 0.0 : qyr; R.xi = xr;
-        flip = kgrp != 0;
-      }
-      if (ty != BC_HALO) R.xi = R.h - hstg;
-      derive(R, hstg, g);
-      if (ty == BC_HALO) { R.hu = __dmul_rn(R.h, R.u); R.hv = __dmul_rn(R.h, R.v); }
+    if (ty == BC_INLETQ) {
+      wet = L.h > hs ? 1.0 : 0.0;
+      mannc = sm.mann[lL];
+      vn = a.inlet_coef[kgrp] * a.bc_l23[e] / mannc;
+      R.h = L.h; R.hu = -L.h * vn * bnx * wet; R.hv = -L.h * vn * bny * wet;
+    } else if (ty == BC_EXITH) {
+      const double hg = a.wse[kgrp] - zbl;
+      exit_free = hg > hs;                       // max(h_small, .) passes the derivative only when not clamped
+      R.h = exit_free ? hg : hs; R.hu = L.hu; R.hv = L.hv;
+    } else if (ty == BC_WALL) {
+      R.h = L.h; R.hu = -L.hu; R.hv = -L.hv;
+    } else if (ty == BC_SYMM) {
+      const double vdn = L.hu * bnx + L.hv * bny;
+      R.h = L.h; R.hu = L.hu - 2.0 * vdn * bnx; R.hv = L.hv - 2.0 * vdn * bny;
+    } else {
+      // remote cell: state and cotangent arrived through the halo buffers; its own adjoint is computed by its owner
+      const int32_t off = a.halo_off[e], n = a.halo_cnt[e];
+      const double xr = a.halo_recv[off], qxr = a.halo_recv[off + n], qyr = a.halo_recv[off + 2 * n];
+      const double rAr = fast_rcp(a.bc_l23[e]);          // remote cell area rides in l23
+      // mu_remote is a rounded product exactly like an in-tile cell's (no FMA contraction with the sum)
+      f0b += __dmul_rn(a.halo_recv[off + 3 * n], rAr); f1b += __dmul_rn(a.halo_recv[off + 4 * n], rAr);
+      f2b += __dmul_rn(a.halo_recv[off + 5 * n], rAr);
+      const double hr = xr + hstg;
+      const bool dryr = hr <= hs;
+      R.h = dryr ? hs : hr; R.hu = dryr ? 0.0 : qxr; R.hv = dryr ? 0.0 : qyr; R.xi = xr;
+      flip = kgrp != 0;
     }
+    if (ty != BC_HALO) R.xi = R.h - hstg;
+    derive(R, hstg, g);
+    if (ty == BC_HALO) { R.hu = __dmul_rn(R.h, R.u); R.hv = __dmul_rn(R.h, R.v); }
     f0b *= len; f1b *= len; f2b *= len;
     if (flip) {   // evaluated with the remote cell as L (see hg_fused.cu): flux_out = -roe(R, L, -n)
       const Side tmp = L; L = R; R = tmp;
-      const double* tp = zbLp; zbLp = zbRp; zbRp = tp;
+      const double tz = zbl; zbl = zbr; zbr = tz;
       nx = -nx; ny = -ny; f0b = -f0b; f1b = -f1b; f2b = -f2b;
     }
     Adj aL, aR;
-    roe_flux_adj(L, R, zbLp, zbRp, nx, ny, g, hs, f0b, f1b, f2b, &aL, &aR);
+    roe_flux_adj(L, R, zbl, zbr, nx, ny, g, hs, f0b, f1b, f2b, &aL, &aR);
     if (flip) { const Adj ta = aL; aL = aR; aR = ta; const Side tmp = L; L = R; R = tmp; }
-    if (ty >= 0) {
-      double ec = 0.0, en = 0.0, ez = 0.0;
-      if (ty != BC_HALO) {
-        // ghost (xi, h, u, v, s, P) adjoints -> ghost primitives (h_g, hu_g, hv_g); xi_g = h_g - hstill_g
-        const double rhg = fast_rcp(R.h);
-        const double hub = aR.u * rhg, hvb = aR.v * rhg;
-        const double xib = aR.xi + aR.P * g * (R.xi + EPS + hstg);
-        const double hgb = aR.h - (aR.u * R.u + aR.v * R.v) * rhg + aR.s * 0.5 * fast_rcp(R.s) + xib;
-        // boundary condition transposed: adjoints of the internal cell's clamped (h, hu, hv)
-        double hcb = 0.0, hucb = 0.0, hvcb = 0.0;
-        if (ty == BC_INLETQ) {
-          const double G = -(hub * bnx + hvb * bny) * wet;   // d(hu_g, hv_g) = -n wet d(h_c vn)
-          hcb = hgb + G * vn;
-          en = -G * L.h * vn / mannc;                        // vn = coef L^(2/3) / n_c
-          ec = G * L.h * a.bc_l23[e] / mannc;                // share of the adjoint of coef_k = Q_k / A_k
-        } else if (ty == BC_EXITH) {
-          hucb = hub; hvcb = hvb;
-          ez = exit_free ? -hgb : 0.0;                       // h_g = WSE - zb_c
-        } else if (ty == BC_WALL) {
-          hcb = hgb; hucb = -hub; hvcb = -hvb;
-        } else {
-          const double dn = hub * bnx + hvb * bny;
-          hcb = hgb; hucb = hub - 2.0 * dn * bnx; hvcb = hvb - 2.0 * dn * bny;
-        }
-        aL.u += hucb * L.h; aL.v += hvcb * L.h; aL.h += hcb + hucb * L.u + hvcb * L.v;
+    double ec = 0.0, en = 0.0, ez = 0.0;
+    if (ty != BC_HALO) {
+      // ghost (xi, h, u, v, s, P) adjoints -> ghost primitives (h_g, hu_g, hv_g); xi_g = h_g - hstill_g
+      const double rhg = fast_rcp(R.h);
+      const double hub = aR.u * rhg, hvb = aR.v * rhg;
+      const double xib = aR.xi + aR.P * g * (R.xi + EPS + hstg);
+      const double hgb = aR.h - (aR.u * R.u + aR.v * R.v) * rhg + aR.s * 0.5 * fast_rcp(R.s) + xib;
+      // boundary condition transposed: adjoints of the internal cell's clamped (h, hu, hv)
+      double hcb = 0.0, hucb = 0.0, hvcb = 0.0;
+      if (ty == BC_INLETQ) {
+        const double G = -(hub * bnx + hvb * bny) * wet;   // d(hu_g, hv_g) = -n wet d(h_c vn)
+        hcb = hgb + G * vn;
+        en = -G * L.h * vn / mannc;                        // vn = coef L^(2/3) / n_c
+        ec = G * L.h * a.bc_l23[e] / mannc;                // share of the adjoint of coef_k = Q_k / A_k
+      } else if (ty == BC_EXITH) {
+        hucb = hub; hvcb = hvb;
+        ez = exit_free ? -hgb : 0.0;                       // h_g = WSE - zb_c
+      } else if (ty == BC_WALL) {
+        hcb = hgb; hucb = -hub; hvcb = -hvb;
+      } else {
+        const double dn = hub * bnx + hvb * bny;
+        hcb = hgb; hucb = hub - 2.0 * dn * bnx; hvcb = hvb - 2.0 * dn * bny;
       }
-      a.ent_c[e] = ec; a.ent_n[e] = en; a.ent_z[e] = ez;
-      aR = Adj{0, 0, 0, 0, 0, 0};
+      aL.u += hucb * L.h; aL.v += hvcb * L.h; aL.h += hcb + hucb * L.u + hvcb * L.v;
     }
-    sm.o[0][f] = aL.xi; sm.o[1][f] = aL.h; sm.o[2][f] = aL.u; sm.o[3][f] = aL.v; sm.o[4][f] = aL.s; sm.o[5][f] = aL.P;
-    sm.o[6][f] = aR.xi; sm.o[7][f] = aR.h; sm.o[8][f] = aR.u; sm.o[9][f] = aR.v; sm.o[10][f] = aR.s; sm.o[11][f] = aR.P;
+    a.ent_c[e] = ec; a.ent_n[e] = en; a.ent_z[e] = ez;
+    double xb, qxb, qyb;
+    fold_side(aL, L.h, L.u, L.v, sm.rh[lL], sm.rs2[lL], sm.dP[lL], hs, xb, qxb, qyb);
+    sm.o[0][f] = xb; sm.o[1][f] = qxb; sm.o[2][f] = qyb;
+    sm.o[3][f] = 0.0; sm.o[4][f] = 0.0; sm.o[5][f] = 0.0;
   }
-  if (tid < 12) sm.o[tid][nfp] = 0.0;   // the zero slot of unused cf entries
+  if (tid < 6) sm.o[tid][nfp] = 0.0;   // the zero slot of unused cf entries
   __syncthreads();
 
-  // ---- phase 3: per-cell gather of face adjoints + source adjoint + undo derived map and clamp
+  // ---- phase 3: per-cell gather of the face adjoints (L or R side of each face) + source adjoint
   const double kfr = g / (a.c.k_n * a.c.k_n);
   for (int32_t l = tid; l < nc; l += kThreads) {
     const int32_t gi = c0 + l;
@@ -388,26 +400,20 @@ __global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_const
       slot[4] = (uint16_t)(w.z & 0xFFFFu); slot[5] = (uint16_t)(w.z >> 16);
       slot[6] = (uint16_t)(w.w & 0xFFFFu); slot[7] = (uint16_t)(w.w >> 16);
     }
-    double xib = 0.0, hb = 0.0, ub = 0.0, vb = 0.0, sb = 0.0, Pb = 0.0;
+    double xib = 0.0, qxb = 0.0, qyb = 0.0;
 #pragma unroll
     for (int j = 0; j < NF; ++j) {
       const int32_t f = slot[j] & 0x7FFF;
-      const int side = (slot[j] & 0x8000) ? 6 : 0;
-      xib += sm.o[side + 0][f]; hb += sm.o[side + 1][f]; ub += sm.o[side + 2][f];
-      vb += sm.o[side + 3][f]; sb += sm.o[side + 4][f]; Pb += sm.o[side + 5][f];
+      const int side = (slot[j] & 0x8000) ? 3 : 0;
+      xib += sm.o[side + 0][f]; qxb += sm.o[side + 1][f]; qyb += sm.o[side + 2][f];
     }
-    const double xi = sm.xi[l], h = sm.h[l], u = sm.u[l], v = sm.v[l], s = sm.s[l], hst = sm.hst[l];
-    const double A = sm.area[l], n = sm.mann[l];
-    const double lam1 = sm.m1[l] * A, lam2 = sm.m2[l] * A;   // mu * area = lambda
-    const double rh = fast_rcp(h);
-    // derived map: u = hu/h, v = hv/h, s = sqrt(h+eps), P(xi)
-    double qxb = ub * rh, qyb = vb * rh;
-    hb += -(ub * u + vb * v) * rh + sb * 0.5 * fast_rcp(s);
-    xib += Pb * g * (xi + EPS + hst);
     // sources (wet cells): r1 += g xi S0x - C m qx,  C = g n^2/k_n^2 (h+hs)^(-7/3),  m = sqrt(qx^2+qy^2+eps)
-    const bool wet = h > hs;
+    const double h = sm.h[l];
     double nb = 0.0, s0xb = 0.0, s0yb = 0.0;
-    if (wet) {
+    if (h > hs) {
+      const double xi = sm.xi[l], u = sm.u[l], v = sm.v[l];
+      const double A = sm.area[l], n = sm.mann[l];
+      const double lam1 = sm.m1[l] * A, lam2 = sm.m2[l] * A;   // mu * area = lambda
       const double qx = h * u, qy = h * v;
       const double y = fma(qx, qx, fma(qy, qy, EPS));
       const double rm = fast_rsqrt(y);
@@ -418,16 +424,14 @@ __global__ void __launch_bounds__(kVjpThreads, 2) k_fused_vjp(const __grid_const
       qxb += fxb * (C * mag + C * qx * qx * rm) + fyb * cross;
       qyb += fyb * (C * mag + C * qy * qy * rm) + fxb * cross;
       const double D = (fxb * qx + fyb * qy) * C * mag;      // fxb*fx + fyb*fy
-      hb += -(7.0 / 3.0) * D * fast_rcp(h + hs);
+      xib += -(7.0 / 3.0) * D * fast_rcp(h + hs);            // through h = xi + hstill (the cell is wet, hence unclamped)
       nb = 2.0 * D * fast_rcp(n);
       xib += g * (sm.sx[l] * lam1 + sm.sy[l] * lam2);
       s0xb = g * xi * lam1; s0yb = g * xi * lam2;
     }
-    // dry clamp (semi_discretize_swe_2D.jl:104-106): clamped h, q are constants; xi itself is never clamped
-    const bool dry = (xi + hst) <= hs;
-    a.Qbar[gi] = dry ? xib : xib + hb;
-    a.Qbar[Ns + gi] = dry ? 0.0 : qxb;
-    a.Qbar[2 * Ns + gi] = dry ? 0.0 : qyb;
+    a.Qbar[gi] = xib;
+    a.Qbar[Ns + gi] = qxb;
+    a.Qbar[2 * Ns + gi] = qyb;
     a.nbar[gi] = nb;
     if (a.want_s0) { a.s0bar[gi] = s0xb; a.s0bar[Ns + gi] = s0yb; }
   }
@@ -555,30 +559,55 @@ __global__ void k_gather1(int32_t N, const int32_t* __restrict__ map, const doub
   if (i < N) dst[i] = src[map[i]];
 }
 
-}  // namespace
-
-int fused_vjp_smem_bytes(int cfg_id) {
+// ---- launch shapes.  (threads, CTAs/SM) per tile size: CTAs/SM is what the shared-memory footprint allows,
+// threads keeps threads*CTAs*registers <= 64K.  Variants 1, 2 (hg_options.reserved[2]) exist for tuning sweeps.
+struct VjpKernel {
+  const void* fn = nullptr;
+  int threads = 0, smem = 0;
+};
+template <int T, int ML, int MF, int NF, int TH, int MB>
+VjpKernel vjp_mk() {
+  return VjpKernel{(const void*)k_fused_vjp<T, ML, MF, NF, TH, MB>, TH, (int)sizeof(VjpSmem<T, ML, MF, NF>)};
+}
+template <int T, int ML, int MF, int NF>
+VjpKernel vjp_pick(int v) {
+  if constexpr (T == 256) {
+    if (v == 1) return vjp_mk<T, ML, MF, NF, 160, 3>();
+    if (v == 2) return vjp_mk<T, ML, MF, NF, 256, 3>();
+    return vjp_mk<T, ML, MF, NF, 192, 3>();
+  } else if constexpr (T == 192) {
+    if (v == 1) return vjp_mk<T, ML, MF, NF, 128, 4>();
+    if (v == 2) return vjp_mk<T, ML, MF, NF, 192, 3>();
+    return vjp_mk<T, ML, MF, NF, 160, 4>();
+  } else if constexpr (T == 128 && NF == 4) {
+    if (v == 1) return vjp_mk<T, ML, MF, NF, 128, 4>();
+    if (v == 2) return vjp_mk<T, ML, MF, NF, 96, 5>();
+    return vjp_mk<T, ML, MF, NF, 128, 5>();
+  } else if constexpr (T == 128) {
+    return vjp_mk<T, ML, MF, NF, 128, 3>();
+  } else {
+    return vjp_mk<T, ML, MF, NF, 512, 1>();
+  }
+}
+VjpKernel vjp_kernel(int cfg_id, int variant) {
   switch (cfg_id) {
-#define X(id, T, ML, MF, NF, TH, MB) case id: return (int)sizeof(VjpSmem<TileCfg<T, ML, MF, NF, TH, MB>>);
+#define X(id, T, ML, MF, NF, TH, MB) case id: return vjp_pick<T, ML, MF, NF>(variant);
     HG_TILE_CONFIGS(X)
 #undef X
   }
-  return 0;
+  return VjpKernel{};
 }
 
+}  // namespace
+
+int fused_vjp_smem_bytes(int cfg_id) { return vjp_kernel(cfg_id, 0).smem; }
+
 int fused_vjp_prepare(hg_ctx* ctx, int cfg_id) {
-  cudaError_t e = cudaSuccess;
-  switch (cfg_id) {
-#define X(id, T, ML, MF, NF, TH, MB)                                                                              \
-  case id: {                                                                                                      \
-    using C = TileCfg<T, ML, MF, NF, TH, MB>;                                                                     \
-    if (sizeof(VjpSmem<C>) > 227 * 1024) { ctx->err = "VJP tile does not fit shared memory"; return HG_ERR_ARG; } \
-    e = cudaFuncSetAttribute(k_fused_vjp<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VjpSmem<C>)); \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_vjp<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
-  } break;
-    HG_TILE_CONFIGS(X)
-#undef X
-  }
+  const VjpKernel k = vjp_kernel(cfg_id, ctx->opt.reserved[2]);
+  if (!k.fn) { ctx->err = "no VJP tile configuration"; return HG_ERR_ARG; }
+  if (k.smem > 227 * 1024) { ctx->err = "VJP tile does not fit shared memory"; return HG_ERR_ARG; }
+  cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute(vjp): ") + cudaGetErrorString(e); return HG_ERR_CUDA; }
   return HG_OK;
 }
@@ -601,15 +630,12 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
   a.wse = d.wse.p; a.Q = d_Q; a.lam = d_lam; a.Qbar = d_Qbar; a.nbar = d.nbar.p; a.s0bar = d.s0bar.p;
   a.ent_c = d.ent_c.p; a.ent_n = d.ent_n.p; a.ent_z = d.ent_z.p;
   const unsigned grid = (unsigned)fh.n_tiles;
-  switch (cfg_id) {
-#define X(id, T, ML, MF, NF, TH, MB)                                                        \
-  case id: {                                                                                \
-    using C = TileCfg<T, ML, MF, NF, TH, MB>;                                               \
-    k_fused_vjp<C><<<grid, kVjpThreads, sizeof(VjpSmem<C>), ctx->stream>>>(a);               \
-  } break;
-    HG_TILE_CONFIGS(X)
-#undef X
-    default: ctx->err = "no tile configuration"; return HG_ERR_ARG;
+  const VjpKernel kk = vjp_kernel(cfg_id, ctx->opt.reserved[2]);
+  if (!kk.fn) { ctx->err = "no VJP tile configuration"; return HG_ERR_ARG; }
+  {
+    void* kargs[] = {(void*)&a};
+    const cudaError_t le = cudaLaunchKernel(kk.fn, dim3(grid), dim3((unsigned)kk.threads), kargs, (size_t)kk.smem, ctx->stream);
+    if (le != cudaSuccess) { ctx->err = std::string("fused_vjp launch: ") + cudaGetErrorString(le); return HG_ERR_CUDA; }
   }
   ctx->launches++;
   if (ctx->n_inletq > 0) {

@@ -1,0 +1,17 @@
+"""RHS kernel tuning sweep on one mesh: python scripts/tune_rhs.py [million cells]"""
+import sys, time
+sys.path.insert(0, '.')
+import _pkg; hg = _pkg.load()
+from hydrograd_jl_b200 import synthetic as S
+M = float(sys.argv[1]) if len(sys.argv) > 1 else 16.0
+nx = int(M * 1e6 / 1.1 / 1000); flat, Q0 = S.river(nx, 1000)
+N, F = flat["n_cells"], flat["n_faces"]
+B = 100 * N + 32 * F + 4 * int(flat["cell_nfaces"].sum())
+print("N", N, "bytes/cell", B / N, flush=True)
+for tile, threads, pipe in [(256, 0, 0), (256, 0, 1), (192, 0, 1), (128, 0, 1), (512, 0, 1), (192, 0, 0)]:
+    ctx = hg.Context(flat, tile_cells=tile, threads=threads, pipeline=pipe)
+    ctx.set_state(Q0)
+    ctx.time_rhs(5)
+    t = min(ctx.time_rhs(20) / 20 for _ in range(3))
+    print(f"tile {tile} threads {threads} pipe {pipe}: {t:.4f} ms  {B / t / 1e6:.0f} GB/s  {B / t / 1e6 / 6448.1:.3f}", flush=True)
+    del ctx
