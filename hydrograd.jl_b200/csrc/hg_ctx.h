@@ -134,6 +134,7 @@ struct FusedDev {
   DBuf<double> rk_k, rk_acc, rk_tmp;                                   // RK4 stages
   DBuf<double> halo_send, halo_recv;                                    // [6 * n_halo_entries]
   DBuf<int32_t> err;
+  DBuf<int32_t> work_ctr;                                               // persistent kernels: next work item
 };
 
 // host copies of the bindable frozen fields (so that un-binding a parameter restores them)

@@ -273,6 +273,18 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     int32_t nloc = ncp;
     for (int32_t c = c0; c < c1; ++c) { stamp[c] = t; loc[c] = c - c0; }
     const size_t face_base = fh.face_lr.size(), halo_base = fh.halo.size(), bf_base = fh.bface_e.size();
+    // pass 0: the one-layer halo, in ascending internal order (so that the indirect loads of neighbouring lanes
+    // fall into the same sectors wherever the neighbouring tiles' cells are contiguous)
+    for (int32_t c = c0; c < c1; ++c) {
+      const int32_t r = fh.perm[c];
+      for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
+        if (cf_nb[k] >= N) continue;
+        const int32_t cn = fh.iperm[cf_nb[k]];
+        if (stamp[cn] != t) { stamp[cn] = t; fh.halo.push_back(cn); }
+      }
+    }
+    std::sort(fh.halo.begin() + halo_base, fh.halo.end());
+    for (size_t q = halo_base; q < fh.halo.size(); ++q) loc[fh.halo[q]] = nloc++;
     // pass A: interior faces, found by the first owned cell (internal order) that sees them ...
     struct TF { int32_t lL, lR, fid; double nx, ny, len; };
     std::vector<TF> tf;
@@ -283,10 +295,6 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
         const int32_t fid = cf_face[k];
         if (fstamp[fid] == t) continue;
         const int32_t rn = cf_nb[k], cn = fh.iperm[rn];
-        if (stamp[cn] != t) {  // halo cell: next local index
-          stamp[cn] = t; loc[cn] = nloc++;
-          fh.halo.push_back(cn);
-        }
         // canonical orientation: L = smaller REFERENCE id, normal taken from the L cell's own table
         int32_t lL, lR; double nx, ny;
         if (r < rn) {

@@ -22,6 +22,7 @@ using namespace dev;
 
 struct VjpArgs {
   int32_t N, n_tiles, want_s0;
+  int32_t prefetch;            // > 0: CTA b pulls the blocks of tile b + prefetch into L2 (see hg_fused.cu, prefetch_work)
   int64_t Ns;
   Consts c;
   const int32_t *tile_desc, *halo, *bface_e;
@@ -163,11 +164,88 @@ __device__ __forceinline__ void roe_flux_adj(Side L, Side R, double zbL, double 
   *paL = aL; *paR = aR;
 }
 
+// ---- the common case, both sides wet: reverse sweep in two parts so that few values stay live.
+// roe_adj_core: forward recompute + reverse through the Roe averages / eigen-decomposition, down to the adjoints of
+// the face-level combinations (d1, d2, d3 = jumps of xi, hu, hv; hRoe; a = sL uL + sR uR, b likewise; S = sL + sR).
+struct FaceCore {
+  double b0, b1, b2;            // 0.5 * adjoint of the flux
+  double d1b, d2b, d3b;         // adjoints of the jumps
+  double hh;                    // 0.5 * adjoint of hRoe  (= adjoint of each side's h through hRoe)
+  double ab, bb, Sb;            // adjoints of a, b, S
+};
+__device__ __forceinline__ void roe_adj_core(double xiL, double hL, double uL, double vL, double sL, double xiR, double hR,
+                                             double uR, double vR, double sR, double nx, double ny, double g, double f0b,
+                                             double f1b, double f2b, FaceCore& o) {
+  const double hRoe = 0.5 * (hL + hR);
+  const double rs = fast_rcp(sL + sR);
+  const double a_ = sL * uL + sR * uR, b_ = sL * vL + sR * vR;
+  const double uRoe = a_ * rs, vRoe = b_ * rs;
+  const double un = uRoe * nx + vRoe * ny;
+  const double c2 = fma(g, hRoe, EPS);
+  const double rc = fast_rsqrt(c2);
+  const double c = c2 * rc, k = 0.5 * rc;
+  const double d1 = xiR - xiL, d2 = __dmul_rn(hR, uR) - __dmul_rn(hL, uL), d3 = __dmul_rn(hR, vR) - __dmul_rn(hL, vL);
+  const double t1 = uRoe * ny - vRoe * nx;
+  const double w1 = -t1 * d1 + ny * d2 - nx * d3;
+  const double e_ = un * d1 - (nx * d2 + ny * d3);
+  const double m = k * e_;
+  const double w2 = 0.5 * d1 + m, w3 = 0.5 * d1 - m;
+  const double l2 = un - c, l3 = un + c;
+  double A1, A2, A3, r1, r2, r3;
+  sabs_r(un, A1, r1); sabs_r(l2, A2, r2); sabs_r(l3, A3, r3);
+  const double z2 = A2 * w2, z3 = A3 * w3;
+  const double zs = z2 + z3;
+  // ---- reverse
+  const double b0 = 0.5 * f0b, b1 = 0.5 * f1b, b2 = 0.5 * f2b;
+  const double z1b = nx * b2 - ny * b1;                       // y = R_mat z, ybar = -b
+  const double zsb = -(b0 + uRoe * b1 + vRoe * b2);
+  const double zdb = -(nx * b1 + ny * b2);
+  double uRoeb = -zs * b1, vRoeb = -zs * b2;
+  double cb = zdb * (z3 - z2);
+  const double z3b = zsb + c * zdb, z2b = zsb - c * zdb;
+  const double w1b = z1b * A1, w2b = z2b * A2, w3b = z3b * A3;
+  const double l1b = z1b * w1 * un * r1, l2b = z2b * w2 * l2 * r2, l3b = z3b * w3 * l3 * r3;   // d sqrt(x^2+eps)/dx = x / sqrt(..)
+  double unb = l1b + l2b + l3b;
+  cb += l3b - l2b;
+  double d1b = 0.5 * (w2b + w3b);
+  const double mb = w2b - w3b;
+  const double kb = mb * e_, eb = mb * k;
+  unb += eb * d1;
+  d1b += eb * un;
+  const double t1b = -w1b * d1;
+  d1b -= w1b * t1;
+  uRoeb += t1b * ny + unb * nx;
+  vRoeb += unb * ny - t1b * nx;
+  const double c2b = cb * k - 2.0 * kb * k * k * k;             // c = sqrt(c2), k = 1/(2 sqrt(c2))
+  o.b0 = b0; o.b1 = b1; o.b2 = b2;
+  o.d1b = d1b;
+  o.d2b = w1b * ny - eb * nx;
+  o.d3b = -w1b * nx - eb * ny;
+  o.hh = 0.5 * g * c2b;
+  o.ab = uRoeb * rs; o.bb = vRoeb * rs;
+  o.Sb = -(uRoeb * a_ + vRoeb * b_) * rs * rs;
+}
+// One side's (xi, q_x, q_y) adjoints from the core: the per-side part of the sweep (physical flux, jumps, Roe
+// weights) composed with the transpose of u = hu/h, v = hv/h, s = sqrt(h+eps), P(xi).  sgn = -1 for L, +1 for R.
+// With sigma = s/h and bu = b1 u + b2 v:
+//   qxb = [b0 nx + b1 un + sgn d2b] + bu nx + ab sigma          (likewise qyb)
+//   xb  = Pb dP + sgn d1b + (ab u + bb v)(1/(2s) - sigma) + Sb/(2s) + hh - bu un
+__device__ __forceinline__ void fold_core_side(const FaceCore& k, double sgn, double nx, double ny, double u, double v,
+                                               double sg, double rs2, double dP, double& xb, double& qxb, double& qyb) {
+  const double un = u * nx + v * ny;
+  const double bu = k.b1 * u + k.b2 * v;
+  const double abu = k.ab * u + k.bb * v;
+  qxb = fma(k.ab, sg, fma(bu + k.b0, nx, fma(k.b1, un, sgn * k.d2b)));
+  qyb = fma(k.bb, sg, fma(bu + k.b0, ny, fma(k.b2, un, sgn * k.d3b)));
+  const double Pb = k.b1 * nx + k.b2 * ny;
+  xb = fma(Pb, dP, sgn * k.d1b) + (fma(abu, rs2 - sg, fma(k.Sb, rs2, k.hh)) - bu * un);
+}
+
 template <int T, int ML, int MF, int NF>
 struct __align__(16) VjpSmem {
   uint64_t bar[2];
-  double xi[ML], h[ML], u[ML], v[ML], s[ML], P[ML];       // staged forward state (clamped, derived)
-  double rh[ML], rs2[ML], dP[ML];                         // 1/h, 1/(2 s), dP/dxi = g (xi + eps + hstill): the derived map's transpose
+  double xi[ML], h[ML], u[ML], v[ML], s[ML];              // staged forward state (clamped, derived); the pressure is not needed
+  double sg[ML], rs2[ML], dP[ML];                         // s/h, 1/(2 s), dP/dxi = g (xi + eps + hstill): the derived map's transpose
   double m0[ML], m1[ML], m2[ML];                          // mu = lambda / area (lambda itself on arrival)
   double o[6][MF];                                        // rows 0..2: nx, ny, len on arrival; then (xi, q_x, q_y) adjoints, L side | R side
   double area[T], mann[T], sx[T], sy[T];
@@ -188,117 +266,41 @@ __device__ __forceinline__ void fold_side(const Adj& a, double h, double u, doub
   qyb = wet ? a.v * rh : 0.0;
 }
 
-// The reverse sweep keeps ~70 doubles live; TH x MB is picked per tile size so that MB CTAs fit next to each other
-// in shared memory and TH*MB*regs <= 64K (vjp_pick below).
-template <int T, int ML, int MF, int NF, int TH, int MB>
-__global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ VjpArgs a) {
-  extern __shared__ __align__(128) unsigned char smraw[];
-  using Smem = VjpSmem<T, ML, MF, NF>;
-  Smem& sm = *reinterpret_cast<Smem*>(smraw);
-  constexpr int kThreads = TH;
-
-  const int t = blockIdx.x, tid = threadIdx.x;
-  const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc));
-  const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 1);
-  const int4 d2 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 2);
-  const int32_t c0 = d0.x, nc = d0.y, hp = d0.z, nh = d0.w;
-  const int32_t fp = d1.x, nf = d1.y, nfp = d1.z;
-  const int32_t nint = d2.y, bfp = d2.z;
-  const int32_t ncp = (nc + 1) & ~1;
-  const double g = a.c.g, hs = a.c.h_small;
-  const int64_t Ns = a.Ns;
-  // bed elevation of a tile-local cell: only the (rare) faces with a dry side and boundary faces read it
-  auto zb_local = [&](int32_t l) { return a.zb[l < ncp ? c0 + l : __ldg(a.halo + hp + (l - ncp))]; };
-
-  if (tid == 0) mbar_init(sm.bar, 1);
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t cb = (uint32_t)ncp * 8u, fb = (uint32_t)nfp * 8u;
-    mbar_expect_tx(sm.bar, 11u * cb + 3u * fb + (uint32_t)nfp * 4u + (uint32_t)(T * NF) * 2u);
-    bulk_g2s(sm.xi, a.Q + c0, cb, sm.bar);
-    bulk_g2s(sm.u, a.Q + Ns + c0, cb, sm.bar);             // raw q_x; u replaces it in place
-    bulk_g2s(sm.v, a.Q + 2 * Ns + c0, cb, sm.bar);         // raw q_y
-    bulk_g2s(sm.dP, a.hstill + c0, cb, sm.bar);            // raw hstill; dP replaces it in place
-    bulk_g2s(sm.m0, a.lam + c0, cb, sm.bar);
-    bulk_g2s(sm.m1, a.lam + Ns + c0, cb, sm.bar);
-    bulk_g2s(sm.m2, a.lam + 2 * Ns + c0, cb, sm.bar);
-    bulk_g2s(sm.o[0], a.face_nx + fp, fb, sm.bar);
-    bulk_g2s(sm.o[1], a.face_ny + fp, fb, sm.bar);
-    bulk_g2s(sm.o[2], a.face_len + fp, fb, sm.bar);
-    bulk_g2s(sm.lr, a.face_lr + fp, (uint32_t)nfp * 4u, sm.bar);
-    bulk_g2s(sm.area, a.area + c0, cb, sm.bar);
-    bulk_g2s(sm.mann, a.mann + c0, cb, sm.bar);
-    bulk_g2s(sm.sx, a.S0x + c0, cb, sm.bar);
-    bulk_g2s(sm.sy, a.S0y + c0, cb, sm.bar);
-    bulk_g2s(sm.cf, a.cf_idx + (size_t)t * (T * NF), (uint32_t)(T * NF) * 2u, sm.bar);
-  }
-  // clamp + derived values + the factors of the derived map's transpose, for local cell l
-  auto stage_cell = [&](int32_t l, double xi, double qx, double qy, double hst) {
-    const double h0 = xi + hst;
-    const bool dry = h0 <= hs;
-    const double h = dry ? hs : h0;
-    const double rh = fast_rcp(h);
-    const double y = h + EPS;
-    const double r = fast_rsqrt(y);
-    double s = y * r;
-    s = fma(fma(-s, s, y), 0.5 * r, s);
-    const double xe = xi + EPS;
-    sm.h[l] = h; sm.u[l] = dry ? 0.0 : qx * rh; sm.v[l] = dry ? 0.0 : qy * rh; sm.s[l] = s;
-    sm.P[l] = 0.5 * g * fma(xe, xe, 2.0 * xi * hst);
-    sm.rh[l] = rh; sm.rs2[l] = 0.5 * r; sm.dP[l] = g * (xe + hst);
-  };
-  // halo cells: state + lambda/area
-  for (int32_t k = tid; k < nh; k += kThreads) {
-    const int32_t gi = __ldg(a.halo + hp + k);
-    const double xi = a.Q[gi], qx = a.Q[Ns + gi], qy = a.Q[2 * Ns + gi];
-    const double hst = a.hstill[gi];
-    const double rA = fast_rcp(a.area[gi]);
-    const double l0 = a.lam[gi], l1 = a.lam[Ns + gi], l2 = a.lam[2 * Ns + gi];
-    const int32_t l = ncp + k;
-    sm.xi[l] = xi;
-    stage_cell(l, xi, qx, qy, hst);
-    sm.m0[l] = l0 * rA; sm.m1[l] = l1 * rA; sm.m2[l] = l2 * rA;
-  }
-  mbar_wait(sm.bar, 0);
-
-  // ---- phase 1: owned cells, in place
-  for (int32_t l = tid; l < nc; l += kThreads) {
-    stage_cell(l, sm.xi[l], sm.u[l], sm.v[l], sm.dP[l]);
-    const double rA = fast_rcp(sm.area[l]);
-    sm.m0[l] *= rA; sm.m1[l] *= rA; sm.m2[l] *= rA;
-  }
-  __syncthreads();
-
-  // ---- phase 2a: interior faces (the common case) -- straight-line code, no boundary / orientation logic
-  for (int32_t f = tid; f < nint; f += kThreads) {
+// ---- the rare faces
+// interior face on a wet/dry front (exactly one dry side)
+template <class Smem>
+__device__ __forceinline__ void vjp_front_face(Smem& sm, const VjpArgs& a, int32_t f, double zbL, double zbR) {
     const uint32_t lr = sm.lr[f];
     const int32_t lL = lr & 0xFFFFu, lR = lr >> 16;
+    const double hL = sm.h[lL], hR = sm.h[lR];
+    const double g = a.c.g, hs = a.c.h_small;
     const double nx = sm.o[0][f], ny = sm.o[1][f], len = sm.o[2][f];
-    Side L, R;
-    L.xi = sm.xi[lL]; L.h = sm.h[lL]; L.u = sm.u[lL]; L.v = sm.v[lL]; L.s = sm.s[lL]; L.P = sm.P[lL];
-    L.hu = __dmul_rn(L.h, L.u); L.hv = __dmul_rn(L.h, L.v);
-    R.xi = sm.xi[lR]; R.h = sm.h[lR]; R.u = sm.u[lR]; R.v = sm.v[lR]; R.s = sm.s[lR]; R.P = sm.P[lR];
-    R.hu = __dmul_rn(R.h, R.u); R.hv = __dmul_rn(R.h, R.v);
     const double f0b = (sm.m0[lR] - sm.m0[lL]) * len, f1b = (sm.m1[lR] - sm.m1[lL]) * len, f2b = (sm.m2[lR] - sm.m2[lL]) * len;
+    Side L, R;
+    L.xi = sm.xi[lL]; L.h = hL; L.u = sm.u[lL]; L.v = sm.v[lL]; L.s = sm.s[lL];
+    L.hu = __dmul_rn(L.h, L.u); L.hv = __dmul_rn(L.h, L.v);
+    R.xi = sm.xi[lR]; R.h = hR; R.u = sm.u[lR]; R.v = sm.v[lR]; R.s = sm.s[lR];
+    R.hu = __dmul_rn(R.h, R.u); R.hv = __dmul_rn(R.h, R.v);
     Adj aL, aR;
-    if (__builtin_expect(L.h <= hs || R.h <= hs, 0)) roe_flux_adj(L, R, zb_local(lL), zb_local(lR), nx, ny, g, hs, f0b, f1b, f2b, &aL, &aR);
-    else roe_adj_wet(L, R, nx, ny, g, f0b, f1b, f2b, aL, aR);
+    roe_flux_adj(L, R, zbL, zbR, nx, ny, g, hs, f0b, f1b, f2b, &aL, &aR);
     double xb, qxb, qyb;
-    fold_side(aL, L.h, L.u, L.v, sm.rh[lL], sm.rs2[lL], sm.dP[lL], hs, xb, qxb, qyb);
+    fold_side(aL, L.h, L.u, L.v, fast_rcp(L.h), sm.rs2[lL], sm.dP[lL], hs, xb, qxb, qyb);
     sm.o[0][f] = xb; sm.o[1][f] = qxb; sm.o[2][f] = qyb;
-    fold_side(aR, R.h, R.u, R.v, sm.rh[lR], sm.rs2[lR], sm.dP[lR], hs, xb, qxb, qyb);
+    fold_side(aR, R.h, R.u, R.v, fast_rcp(R.h), sm.rs2[lR], sm.dP[lR], hs, xb, qxb, qyb);
     sm.o[3][f] = xb; sm.o[4][f] = qxb; sm.o[5][f] = qyb;
-  }
-  // ---- phase 2b: boundary faces (physical boundaries and halo faces): rebuild the ghost state, sweep, pull back.
-  // A second inlined copy of the sweep: its bits may differ from phase 2a's in the last place, so a halo face is
-  // reproduced across rank counts to ~1e-15, not bit for bit (the RHS kernel is bit-identical).
-  for (int32_t f = nint + tid; f < nf; f += kThreads) {
+}
+// boundary face (physical boundary or halo face): rebuild the ghost state, sweep, pull back onto the owned cell.
+// Its sweep is a second copy of the code: bits may differ from an interior face's in the last place, so a halo
+// face is reproduced across rank counts to ~1e-15, not bit for bit (the RHS kernel is bit-identical).
+template <class Smem>
+__device__ __forceinline__ void vjp_boundary_face(Smem& sm, const VjpArgs& a, int32_t f, int32_t nint, int32_t bfp, int32_t c0) {
+    const double g = a.c.g, hs = a.c.h_small;
     const uint32_t lr = sm.lr[f];
     const int32_t lL = lr & 0xFFFFu;
     double nx = sm.o[0][f], ny = sm.o[1][f];
     const double len = sm.o[2][f];
     Side L, R;
-    L.xi = sm.xi[lL]; L.h = sm.h[lL]; L.u = sm.u[lL]; L.v = sm.v[lL]; L.s = sm.s[lL]; L.P = sm.P[lL];
+    L.xi = sm.xi[lL]; L.h = sm.h[lL]; L.u = sm.u[lL]; L.v = sm.v[lL]; L.s = sm.s[lL];
     L.hu = __dmul_rn(L.h, L.u); L.hv = __dmul_rn(L.h, L.v);   // never contracted into the flux FMAs
     double f0b = -sm.m0[lL], f1b = -sm.m1[lL], f2b = -sm.m2[lL];
     double zbl = a.zb[c0 + lL];                                // boundary faces always touch an owned cell
@@ -377,10 +379,137 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     }
     a.ent_c[e] = ec; a.ent_n[e] = en; a.ent_z[e] = ez;
     double xb, qxb, qyb;
-    fold_side(aL, L.h, L.u, L.v, sm.rh[lL], sm.rs2[lL], sm.dP[lL], hs, xb, qxb, qyb);
+    fold_side(aL, L.h, L.u, L.v, fast_rcp(L.h), sm.rs2[lL], sm.dP[lL], hs, xb, qxb, qyb);
     sm.o[0][f] = xb; sm.o[1][f] = qxb; sm.o[2][f] = qyb;
     sm.o[3][f] = 0.0; sm.o[4][f] = 0.0; sm.o[5][f] = 0.0;
+}
+
+// The common path needs ~90 registers; TH x MB is picked per tile size so that MB CTAs fit next to each other in
+// shared memory and TH*MB*regs <= 64K (vjp_pick below).
+template <int T, int ML, int MF, int NF, int TH, int MB>
+__global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ VjpArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  using Smem = VjpSmem<T, ML, MF, NF>;
+  Smem& sm = *reinterpret_cast<Smem*>(smraw);
+  constexpr int kThreads = TH;
+
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc));
+  const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 1);
+  const int4 d2 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 2);
+  const int32_t c0 = d0.x, nc = d0.y, hp = d0.z, nh = d0.w;
+  const int32_t fp = d1.x, nf = d1.y, nfp = d1.z;
+  const int32_t nint = d2.y, bfp = d2.z;
+  const int32_t ncp = (nc + 1) & ~1;
+  const double g = a.c.g, hs = a.c.h_small;
+  const int64_t Ns = a.Ns;
+  // bed elevation of a tile-local cell: only the (rare) faces with a dry side and boundary faces read it
+  auto zb_local = [&](int32_t l) { return a.zb[l < ncp ? c0 + l : __ldg(a.halo + hp + (l - ncp))]; };
+
+  if (tid == 0) mbar_init(sm.bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t cb = (uint32_t)ncp * 8u, fb = (uint32_t)nfp * 8u;
+    mbar_expect_tx(sm.bar, 11u * cb + 3u * fb + (uint32_t)nfp * 4u + (uint32_t)(T * NF) * 2u);
+    bulk_g2s(sm.xi, a.Q + c0, cb, sm.bar);
+    bulk_g2s(sm.u, a.Q + Ns + c0, cb, sm.bar);             // raw q_x; u replaces it in place
+    bulk_g2s(sm.v, a.Q + 2 * Ns + c0, cb, sm.bar);         // raw q_y
+    bulk_g2s(sm.dP, a.hstill + c0, cb, sm.bar);            // raw hstill; dP replaces it in place
+    bulk_g2s(sm.m0, a.lam + c0, cb, sm.bar);
+    bulk_g2s(sm.m1, a.lam + Ns + c0, cb, sm.bar);
+    bulk_g2s(sm.m2, a.lam + 2 * Ns + c0, cb, sm.bar);
+    bulk_g2s(sm.o[0], a.face_nx + fp, fb, sm.bar);
+    bulk_g2s(sm.o[1], a.face_ny + fp, fb, sm.bar);
+    bulk_g2s(sm.o[2], a.face_len + fp, fb, sm.bar);
+    bulk_g2s(sm.lr, a.face_lr + fp, (uint32_t)nfp * 4u, sm.bar);
+    bulk_g2s(sm.area, a.area + c0, cb, sm.bar);
+    bulk_g2s(sm.mann, a.mann + c0, cb, sm.bar);
+    bulk_g2s(sm.sx, a.S0x + c0, cb, sm.bar);
+    bulk_g2s(sm.sy, a.S0y + c0, cb, sm.bar);
+    bulk_g2s(sm.cf, a.cf_idx + (size_t)t * (T * NF), (uint32_t)(T * NF) * 2u, sm.bar);
   }
+  // clamp + derived values + the factors of the derived map's transpose, for local cell l
+  auto stage_cell = [&](int32_t l, double xi, double qx, double qy, double hst) {
+    const double h0 = xi + hst;
+    const bool dry = h0 <= hs;
+    const double h = dry ? hs : h0;
+    const double rh = fast_rcp(h);
+    const double y = h + EPS;
+    const double r = fast_rsqrt(y);
+    double s = y * r;
+    s = fma(fma(-s, s, y), 0.5 * r, s);
+    const double xe = xi + EPS;
+    sm.h[l] = h; sm.u[l] = dry ? 0.0 : qx * rh; sm.v[l] = dry ? 0.0 : qy * rh; sm.s[l] = s;
+    sm.sg[l] = s * rh; sm.rs2[l] = 0.5 * r; sm.dP[l] = g * (xe + hst);
+  };
+  // halo cells: state + lambda/area
+  for (int32_t k = tid; k < nh; k += kThreads) {
+    const int32_t gi = __ldg(a.halo + hp + k);
+    const double xi = a.Q[gi], qx = a.Q[Ns + gi], qy = a.Q[2 * Ns + gi];
+    const double hst = a.hstill[gi];
+    const double rA = fast_rcp(a.area[gi]);
+    const double l0 = a.lam[gi], l1 = a.lam[Ns + gi], l2 = a.lam[2 * Ns + gi];
+    const int32_t l = ncp + k;
+    sm.xi[l] = xi;
+    stage_cell(l, xi, qx, qy, hst);
+    sm.m0[l] = l0 * rA; sm.m1[l] = l1 * rA; sm.m2[l] = l2 * rA;
+  }
+  if (a.prefetch > 0 && tid == kThreads - 1 && t + a.prefetch < a.n_tiles) {
+    const int32_t tp = t + a.prefetch;
+    const int4 p0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)tp * kTileDesc));
+    const int4 p1 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)tp * kTileDesc) + 1);
+    const uint32_t cb = (uint32_t)((p0.y + 1) & ~1) * 8u, fb = (uint32_t)p1.z * 8u;
+    const int32_t pc = p0.x, pf = p1.x;
+    bulk_prefetch_l2(a.Q + pc, cb); bulk_prefetch_l2(a.Q + Ns + pc, cb); bulk_prefetch_l2(a.Q + 2 * Ns + pc, cb);
+    bulk_prefetch_l2(a.lam + pc, cb); bulk_prefetch_l2(a.lam + Ns + pc, cb); bulk_prefetch_l2(a.lam + 2 * Ns + pc, cb);
+    bulk_prefetch_l2(a.hstill + pc, cb); bulk_prefetch_l2(a.area + pc, cb); bulk_prefetch_l2(a.mann + pc, cb);
+    bulk_prefetch_l2(a.S0x + pc, cb); bulk_prefetch_l2(a.S0y + pc, cb);
+    bulk_prefetch_l2(a.face_nx + pf, fb); bulk_prefetch_l2(a.face_ny + pf, fb); bulk_prefetch_l2(a.face_len + pf, fb);
+    bulk_prefetch_l2(a.face_lr + pf, (uint32_t)p1.z * 4u);
+    bulk_prefetch_l2(a.cf_idx + (size_t)tp * (T * NF), (uint32_t)(T * NF) * 2u);
+    if (p0.w > 0) bulk_prefetch_l2(a.halo + p0.z, (uint32_t)((p0.w + 3) & ~3) * 4u);
+    if (tp + a.prefetch < a.n_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tile_desc + (size_t)(tp + a.prefetch) * kTileDesc));
+  }
+  mbar_wait(sm.bar, 0);
+
+  // ---- phase 1: owned cells, in place
+  for (int32_t l = tid; l < nc; l += kThreads) {
+    stage_cell(l, sm.xi[l], sm.u[l], sm.v[l], sm.dP[l]);
+    const double rA = fast_rcp(sm.area[l]);
+    sm.m0[l] *= rA; sm.m1[l] *= rA; sm.m2[l] *= rA;
+  }
+  __syncthreads();
+
+  // ---- phase 2a: interior faces, common cases only.  Both sides wet: straight-line sweep with the derived map's
+  // transpose folded in algebraically (roe_adj_core + fold_core_side, ~90 registers); both dry: zero flux, zero
+  // adjoint.  Faces with exactly one dry side (wet/dry fronts) take the general routine.  (Measured: moving the
+  // general routine out of line, or into a second scan over the faces, is 5-10 % slower.)
+  for (int32_t f = tid; f < nint; f += kThreads) {
+    const uint32_t lr = sm.lr[f];
+    const int32_t lL = lr & 0xFFFFu, lR = lr >> 16;
+    const double hL = sm.h[lL], hR = sm.h[lR];
+    const bool dL = hL <= hs, dR = hR <= hs;
+    if (__builtin_expect(dL || dR, 0)) {
+      if (dL && dR) {
+        sm.o[0][f] = 0.0; sm.o[1][f] = 0.0; sm.o[2][f] = 0.0; sm.o[3][f] = 0.0; sm.o[4][f] = 0.0; sm.o[5][f] = 0.0;
+      } else {
+        vjp_front_face(sm, a, f, zb_local(lL), zb_local(lR));
+      }
+      continue;
+    }
+    const double nx = sm.o[0][f], ny = sm.o[1][f], len = sm.o[2][f];
+    const double f0b = (sm.m0[lR] - sm.m0[lL]) * len, f1b = (sm.m1[lR] - sm.m1[lL]) * len, f2b = (sm.m2[lR] - sm.m2[lL]) * len;
+    FaceCore k;
+    roe_adj_core(sm.xi[lL], hL, sm.u[lL], sm.v[lL], sm.s[lL], sm.xi[lR], hR, sm.u[lR], sm.v[lR], sm.s[lR], nx, ny, g,
+                 f0b, f1b, f2b, k);
+    double xb, qxb, qyb;
+    fold_core_side(k, -1.0, nx, ny, sm.u[lL], sm.v[lL], sm.sg[lL], sm.rs2[lL], sm.dP[lL], xb, qxb, qyb);
+    sm.o[0][f] = xb; sm.o[1][f] = qxb; sm.o[2][f] = qyb;
+    fold_core_side(k, 1.0, nx, ny, sm.u[lR], sm.v[lR], sm.sg[lR], sm.rs2[lR], sm.dP[lR], xb, qxb, qyb);
+    sm.o[3][f] = xb; sm.o[4][f] = qxb; sm.o[5][f] = qyb;
+  }
+  // ---- phase 2b: boundary faces (physical boundaries and halo faces)
+  for (int32_t f = nint + tid; f < nf; f += kThreads) vjp_boundary_face(sm, a, f, nint, bfp, c0);
   if (tid < 6) sm.o[tid][nfp] = 0.0;   // the zero slot of unused cf entries
   __syncthreads();
 
@@ -563,17 +692,17 @@ __global__ void k_gather1(int32_t N, const int32_t* __restrict__ map, const doub
 // threads keeps threads*CTAs*registers <= 64K.  Variants 1, 2 (hg_options.reserved[2]) exist for tuning sweeps.
 struct VjpKernel {
   const void* fn = nullptr;
-  int threads = 0, smem = 0;
+  int threads = 0, smem = 0, ctas_per_sm = 1;
 };
 template <int T, int ML, int MF, int NF, int TH, int MB>
 VjpKernel vjp_mk() {
-  return VjpKernel{(const void*)k_fused_vjp<T, ML, MF, NF, TH, MB>, TH, (int)sizeof(VjpSmem<T, ML, MF, NF>)};
+  return VjpKernel{(const void*)k_fused_vjp<T, ML, MF, NF, TH, MB>, TH, (int)sizeof(VjpSmem<T, ML, MF, NF>), MB};
 }
 template <int T, int ML, int MF, int NF>
 VjpKernel vjp_pick(int v) {
   if constexpr (T == 256) {
     if (v == 1) return vjp_mk<T, ML, MF, NF, 160, 3>();
-    if (v == 2) return vjp_mk<T, ML, MF, NF, 256, 3>();
+    if (v == 2) return vjp_mk<T, ML, MF, NF, 224, 3>();
     return vjp_mk<T, ML, MF, NF, 192, 3>();
   } else if constexpr (T == 192) {
     if (v == 1) return vjp_mk<T, ML, MF, NF, 128, 4>();
@@ -633,6 +762,8 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
   const VjpKernel kk = vjp_kernel(cfg_id, ctx->opt.reserved[2]);
   if (!kk.fn) { ctx->err = "no VJP tile configuration"; return HG_ERR_ARG; }
   {
+    const int r3 = ctx->opt.reserved[3];
+    a.prefetch = r3 < 0 ? 0 : (r3 > 0 ? r3 : ctx->n_sm * kk.ctas_per_sm);
     void* kargs[] = {(void*)&a};
     const cudaError_t le = cudaLaunchKernel(kk.fn, dim3(grid), dim3((unsigned)kk.threads), kargs, (size_t)kk.smem, ctx->stream);
     if (le != cudaSuccess) { ctx->err = std::string("fused_vjp launch: ") + cudaGetErrorString(le); return HG_ERR_CUDA; }

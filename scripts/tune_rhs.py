@@ -8,10 +8,10 @@ nx = int(M * 1e6 / 1.1 / 1000); flat, Q0 = S.river(nx, 1000)
 N, F = flat["n_cells"], flat["n_faces"]
 B = 100 * N + 32 * F + 4 * int(flat["cell_nfaces"].sum())
 print("N", N, "bytes/cell", B / N, flush=True)
-for tile, threads, pipe in [(256, 0, 0), (256, 0, 1), (192, 0, 1), (128, 0, 1), (512, 0, 1), (192, 0, 0)]:
-    ctx = hg.Context(flat, tile_cells=tile, threads=threads, pipeline=pipe)
+for tile, threads, pipe, pf in [(256, 0, 2, 0), (256, 0, 1, 0), (256, 0, 1, 1)]:
+    ctx = hg.Context(flat, tile_cells=tile, threads=threads, pipeline=pipe, prefetch=pf)
     ctx.set_state(Q0)
     ctx.time_rhs(5)
     t = min(ctx.time_rhs(20) / 20 for _ in range(3))
-    print(f"tile {tile} threads {threads} pipe {pipe}: {t:.4f} ms  {B / t / 1e6:.0f} GB/s  {B / t / 1e6 / 6448.1:.3f}", flush=True)
+    print(f"tile {tile} threads {threads} mode {pipe} prefetch {pf}: {t:.4f} ms  {B / t / 1e6:.0f} GB/s  {B / t / 1e6 / 6448.1:.3f}", flush=True)
     del ctx

@@ -238,20 +238,26 @@ def test_rk4_stepper(hg):
 
 
 @pytest.mark.parametrize("tile", [128, 192, 256, 512])
-def test_pipelined_kernel_matches_one_cta_per_tile_bitwise(hg, tile):
-    """The persistent two-stage pipeline (hg_options.reserved[1] = 1) runs the same per-tile phases in the same
-    order => identical bits, for the RHS and for fused Euler steps (several tiles per CTA: the mesh has more tiles
-    than 148 SMs x resident CTAs)."""
+def test_persistent_kernel_matches_one_cta_per_tile_bitwise(hg, tile):
+    """Persistent CTAs (hg_options.reserved[1] = 1; next tile's descriptor and halo indices prefetched) run the same
+    per-tile phases in the same order => identical bits, for the RHS and for fused Euler steps (several tiles per
+    CTA: the mesh has more tiles than 148 SMs x resident CTAs).  The L2 prefetch only moves data earlier."""
     from hydrograd_jl_b200 import synthetic as S
     key = "river_big"
     if key not in _flat_cache:
         _flat_cache[key] = S.river(700, 260)
     flat, Q0 = _flat_cache[key]
     Q = cases.random_state_flat(flat, 3, dry_frac=0.03)
-    a = hg.Context(flat, tile_cells=tile)
-    b = hg.Context(flat, tile_cells=tile, pipeline=1)
+    a = hg.Context(flat, tile_cells=tile, pipeline=2, prefetch=-1)
+    others = [hg.Context(flat, tile_cells=tile, pipeline=1), hg.Context(flat, tile_cells=tile, pipeline=2, prefetch=0),
+              hg.Context(flat, tile_cells=tile, pipeline=2, prefetch=37)]
     for q in (Q0, Q):
-        assert np.array_equal(a.rhs(q), b.rhs(q)), tile
-    a.set_state(Q0); b.set_state(Q0)
-    a.step_euler(1e-3, 7); b.step_euler(1e-3, 7)
-    assert np.array_equal(a.get_state(), b.get_state())
+        ref = a.rhs(q)
+        for b in others:
+            assert np.array_equal(ref, b.rhs(q)), tile
+    a.set_state(Q0)
+    a.step_euler(1e-3, 7)
+    for b in others:
+        b.set_state(Q0)
+        b.step_euler(1e-3, 7)
+        assert np.array_equal(a.get_state(), b.get_state())
