@@ -109,19 +109,30 @@ def algorithmic_bytes(N, F, sum_nf):
 
 
 def cpu_sample(cells_m=2.0, reps=3, threads=0, seed=1234):
-    """Oracle timed on a bounded sample of the C3 workload (a ~cells_m-million-cell slab of the same river)."""
+    """Oracle timed on a bounded sample of the C3 workload (a ~cells_m-million-cell slab of the same river).
+    One CPU 'step' mirrors the GPU step: one RHS + one derivative pass.  The reference differentiates its RHS with
+    ForwardDiff / Zygote; the cheapest such pass is ONE forward-mode (dual-number) sweep, i.e. one direction of the
+    Jacobian -- the hand-written VJP delivers all directions at once, so this is generous to the CPU side."""
     from hydrograd_jl_b200 import synthetic as S
     from oracle.oracle import Oracle
     ni = max(64, int(cells_m * 1e6 / 1.1 / 1000))
     flat, Q0 = S.river(ni, 1000, seed=seed)
     o = Oracle(flat)
     threads = threads or o.max_threads()
+    v = np.ones_like(Q0)
     o.rhs(Q0, nthreads=threads)
     t = time.perf_counter()
     for _ in range(reps):
         o.rhs(Q0, nthreads=threads)
-    dt = (time.perf_counter() - t) / reps
-    return flat["n_cells"] / dt, threads, f"{reps} RHS calls on a {flat['n_cells']}-cell slab of the C3 river ({ni}x1000 quads)"
+    dt_rhs = (time.perf_counter() - t) / reps
+    t = time.perf_counter()
+    for _ in range(reps):
+        o.jvp(Q0, v, nthreads=threads)
+    dt_jvp = (time.perf_counter() - t) / reps
+    n = flat["n_cells"]
+    return {"value": n / (dt_rhs + dt_jvp), "rhs_only": n / dt_rhs, "cores": threads,
+            "sample": f"{reps} x (RHS + one forward-mode dual-number derivative pass) on a {n}-cell slab of the C3 river "
+                      f"({ni}x1000 quads), OpenMP over cells on {threads} threads"}
 
 
 def run_reference(args):
@@ -132,18 +143,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = []
-    v, cores, sample = None, None, None
+    per_step, per_step_rhs = [], []
+    c = None
     for s in range(args.warmup + args.steps):
-        v, cores, sample = cpu_sample(cells_m=1.0, reps=1)
+        c = cpu_sample(cells_m=1.0, reps=1)
         if s >= args.warmup:
-            per_step.append(v)
-    val = float(np.mean(per_step))
+            per_step.append(c["value"])
+            per_step_rhs.append(c["rhs_only"])
+    val, val_rhs = float(np.mean(per_step)), float(np.mean(per_step_rhs))
+    cores, sample = c["cores"], c["sample"]
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3 synthetic meandering-river mesh, fp64 RHS, bounded CPU sample", "sample": sample},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "rhs_only": val_rhs},
+            "rhs": {"value": val_rhs, "unit": UNIT},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -158,7 +172,6 @@ def main():
     ap.add_argument("--cells-m", type=float, default=16.0, help="million cells per GPU")
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the fused kernel (tuning)")
-    ap.add_argument("--pipeline", type=int, default=0, help="1 = persistent pipelined RHS kernel")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
@@ -216,7 +229,7 @@ def main():
     N, F = flat["n_cells"], flat["n_faces"]
     log(f"[rank {rank}] mesh: N={N} F={F} ({time.time() - t0:.1f}s)")
     t0 = time.time()
-    ctx = hg.Context(flat, device=local, tile_cells=args.tile, threads=args.threads, pipeline=args.pipeline)
+    ctx = hg.Context(flat, device=local, tile_cells=args.tile, threads=args.threads)
     st = ctx.mesh_stats()
     log(f"[rank {rank}] context: {st} ({time.time() - t0:.1f}s)")
     ctx.set_state(Q0)
@@ -304,10 +317,13 @@ def main():
     # this is exactly hg_rhs; at N > 1 the same three stages with the halo exchange in between
     hQ = torch.empty(3 * N, dtype=torch.float64).pin_memory()
     hD = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+    hL = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+    hB = torch.empty(3 * N, dtype=torch.float64).pin_memory()
     hQ.numpy()[:] = Q0
-    out = hD.numpy()
+    hL.numpy()[:] = 1.0
+    out, outb = hD.numpy(), hB.numpy()
 
-    def e2e_step():
+    def e2e_rhs():
         if ex is None:
             ctx.rhs(hQ.numpy(), out=out)
         else:
@@ -315,20 +331,39 @@ def main():
             rhs_step()
             ctx.get_rhs(out=out)
 
-    e2e_step()  # warm-up
+    def e2e_vjp():
+        if ex is None:
+            ctx.rhs_vjp_into(hQ.numpy(), hL.numpy(), outb)
+        else:
+            ctx.set_state(hQ.numpy())
+            ctx.set_lambda(hL.numpy())
+            vjp_step()
+            ctx.get_vjp_into(outb)
+
+    e2e_rhs(); e2e_vjp()  # warm-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        e2e_step()
+        e2e_rhs()
     barrier()
-    e2e_s = allmax((time.perf_counter() - t0) / args.e2e_steps)
-    e2e = {"value": N_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 24 * N,
-           "ms_per_step": e2e_s * 1e3, "what": "one RHS through host buffers (hg_rhs): H2D state, kernel, D2H dQdt"}
+    t1 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_vjp()
+    barrier()
+    t2 = time.perf_counter()
+    e2e_rhs_s = allmax((t1 - t0) / args.e2e_steps)
+    e2e_vjp_s = allmax((t2 - t1) / args.e2e_steps)
+    e2e_s = e2e_rhs_s + e2e_vjp_s
+    e2e = {"value": N_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 72 * N, "d2h_bytes_per_step": 48 * N,
+           "ms_per_step": e2e_s * 1e3, "rhs_ms": e2e_rhs_s * 1e3, "vjp_ms": e2e_vjp_s * 1e3,
+           "rhs_only": N_total / e2e_rhs_s,
+           "what": "one RHS + one VJP through pinned host buffers (hg_rhs: H2D state, kernel, D2H dQdt; hg_rhs_vjp: H2D state "
+                   "and lambda, kernel, D2H Qbar), chunked over three streams"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample = cpu_sample()
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        c = cpu_sample()
+        cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"], "rhs_only": c["rhs_only"],
                "note": "C++ oracle port of the reference algorithm (OpenMP); Hydrograd.jl itself cannot run here (no Julia)"}
 
     if rank == 0:

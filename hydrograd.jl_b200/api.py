@@ -67,12 +67,11 @@ def _descs(f: dict):
     return mesh, bc, fields, keep
 
 
-def _options(lib, device=0, tile_cells=256, reorder=True, strict=False, path=0, threads=0, pipeline=0, vjp_variant=0, prefetch=0):
+def _options(lib, device=0, tile_cells=256, reorder=True, strict=False, path=0, threads=0, vjp_variant=0, prefetch=0):
     opt = L.Options()
     lib.hg_default_options(C.byref(opt))
     opt.device, opt.tile_cells, opt.reorder, opt.strict, opt.path = device, tile_cells, int(reorder), int(strict), path
     opt.reserved[0] = threads
-    opt.reserved[1] = int(pipeline)
     opt.reserved[2] = int(vjp_variant)
     opt.reserved[3] = int(prefetch)
     return opt
@@ -98,12 +97,11 @@ class Context:
     """Owns one hg_ctx (one mesh on one GPU).  `flat` holds the flat tables of include/hydrograd_b200.h
     (see INTEGRATION.md for how the Julia structs map onto them)."""
 
-    def __init__(self, flat: dict, device=0, tile_cells=256, reorder=True, strict=False, path=0, threads=0, pipeline=0,
-                 vjp_variant=0, prefetch=0):
+    def __init__(self, flat: dict, device=0, tile_cells=256, reorder=True, strict=False, path=0, threads=0, vjp_variant=0, prefetch=0):
         self.lib = L.load()
         self._h = C.c_void_p()
         mesh, bc, fields, keep = _descs(flat)
-        opt = _options(self.lib, device, tile_cells, reorder, strict, path, threads, pipeline, vjp_variant, prefetch)
+        opt = _options(self.lib, device, tile_cells, reorder, strict, path, threads, vjp_variant, prefetch)
         rc = self.lib.hg_create(C.byref(self._h), C.byref(mesh), C.byref(bc), C.byref(fields), C.byref(opt))
         del keep            # the library copied what it needs (ownership rule of the ABI)
         if rc:
@@ -153,6 +151,13 @@ class Context:
         nbar = np.empty(self.N) if want_ncell_bar else None
         self._ck(self.lib.hg_rhs_vjp(self._h, _p(Q), _p(p), n, a, float(t), _p(lam), _p(Qbar), _p(pbar), _p(nbar)))
         return (Qbar, pbar[:n], nbar) if want_ncell_bar else (Qbar, pbar[:n])
+
+    def rhs_vjp_into(self, Q, lam, Qbar_out):
+        """hg_rhs_vjp with no active parameter into a caller-owned (e.g. pinned) buffer."""
+        self._ck(self.lib.hg_rhs_vjp(self._h, _p(_f64(Q)), None, 0, 0, 0.0, _p(_f64(lam)), _p(Qbar_out), None, None))
+
+    def get_vjp_into(self, Qbar_out):
+        self._ck(self.lib.hg_get_vjp(self._h, _p(Qbar_out), None, None))
 
     # ---------------------------------------------------------------- device-resident API
     def set_state(self, Q):

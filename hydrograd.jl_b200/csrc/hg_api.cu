@@ -459,6 +459,51 @@ static int set_lambda(hg_ctx* ctx, const double* lam) {
   return HG_OK;
 }
 
+// Host-buffer VJP through the same three-stream pipeline as rhs_pipelined: chunks of Q and lambda arrive on s_in, the
+// tiles whose cells and halo have landed run on the compute stream, finished chunks of Qbar leave on s_out.  The
+// boundary-wide inlet coupling and the parameter reductions run after the last stage (the tiles they touch are
+// last-stage tiles, see build_tiles), before the chunks holding those cells leave.
+static int vjp_pipelined(hg_ctx* ctx, const double* Q, const double* lambda, double* Qbar) {
+  hg::FusedDev& d = ctx->fd;
+  const hg::FusedHost& fh = ctx->fh;
+  const int K = fh.n_chunks;
+  const int64_t N = ctx->N, csz = (N + K - 1) / K;
+  cudaStream_t sc = ctx->stream;
+  if (d.stage_lam.n < (size_t)(3 * N)) CK(ctx, d.stage_lam.alloc(3 * N));
+  const int cfg = hg::fused_cfg_id(ctx);
+  CK(ctx, cudaStreamSynchronize(sc));
+  for (int c = 0; c < K; ++c) {
+    const int64_t r0 = c * csz, r1 = std::min<int64_t>(N, r0 + csz);
+    for (int q = 0; q < 3; ++q) {
+      CK(ctx, cudaMemcpyAsync(d.stage.p + q * N + r0, Q + q * N + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+      CK(ctx, cudaMemcpyAsync(d.stage_lam.p + q * N + r0, lambda + q * N + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    }
+    CK(ctx, cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+  }
+  for (int s = 0; s < K; ++s) {
+    const int64_t r0 = s * csz, r1 = std::min<int64_t>(N, r0 + csz);
+    CK(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[s], 0));
+    TRY(hg::fused_permute_range(ctx, true, d.stage.p, d.Q.p, r0, r1));
+    TRY(hg::fused_permute_range(ctx, true, d.stage_lam.p, d.lam.p, r0, r1));
+    if (s == K - 1 && ctx->n_inletq > 0) hg::fused_inlet_coef(ctx, d.Q.p);
+    TRY(hg::fused_vjp_tiles(ctx, cfg, d.Q.p, d.lam.p, d.Qbar.p, d.tile_order.p, fh.stage_ptr[s], fh.stage_ptr[s + 1] - fh.stage_ptr[s]));
+    if (s == K - 1) TRY(hg::fused_vjp_finish(ctx, d.Q.p, d.Qbar.p));
+    for (int c = 0; c < K; ++c) {
+      if (fh.chunk_done[c] != s) continue;
+      const int64_t q0 = c * csz, q1 = std::min<int64_t>(N, q0 + csz);
+      TRY(hg::fused_permute_range(ctx, false, d.Qbar.p, d.stage_out.p, q0, q1));
+      CK(ctx, cudaEventRecord(ctx->ev_cmp[c], sc));
+      CK(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[c], 0));
+      for (int q = 0; q < 3; ++q)
+        CK(ctx, cudaMemcpyAsync(Qbar + q * N + q0, d.stage_out.p + q * N + q0, (q1 - q0) * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->s_out));
+  ctx->state_set = true;
+  ctx->lam_set = true;
+  return HG_OK;
+}
+
 int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32_t active, double t, const double* lambda,
                double* Qbar, double* pbar, double* ncell_bar) {
   (void)t;
@@ -467,11 +512,15 @@ int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
   if (ctx->active != HG_PARAM_NONE && !pbar) { ctx->err = "hg_rhs_vjp: pbar is NULL"; return HG_ERR_ARG; }
-  TRY(hg_set_state(ctx, Q));
-  TRY(set_lambda(ctx, lambda));
   hg::FusedDev& d = ctx->fd;
-  TRY(hg::fused_vjp(ctx, hg::fused_cfg_id(ctx), d.Q.p, d.lam.p, d.Qbar.p));
-  TRY(download3(ctx, d.Qbar.p, Qbar));
+  if (ctx->fh.n_chunks > 1 && ctx->n_halo == 0) {
+    TRY(vjp_pipelined(ctx, Q, lambda, Qbar));
+  } else {
+    TRY(hg_set_state(ctx, Q));
+    TRY(set_lambda(ctx, lambda));
+    TRY(hg::fused_vjp(ctx, hg::fused_cfg_id(ctx), d.Q.p, d.lam.p, d.Qbar.p));
+    TRY(download3(ctx, d.Qbar.p, Qbar));
+  }
   if (ctx->active != HG_PARAM_NONE)
     CK(ctx, cudaMemcpyAsync(pbar, d.pbar.p, ctx->n_params * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (ncell_bar) {

@@ -115,7 +115,7 @@ struct FusedHost {
 
 struct FusedDev {
   DBuf<int32_t> perm, iperm, tile_desc, halo, bface_e, tile_order;
-  DBuf<double> stage_out;
+  DBuf<double> stage_out, stage_lam;
   DBuf<uint32_t> face_lr;
   DBuf<uint16_t> cf_idx;
   DBuf<double> face_nx, face_ny, face_len;
@@ -134,7 +134,6 @@ struct FusedDev {
   DBuf<double> rk_k, rk_acc, rk_tmp;                                   // RK4 stages
   DBuf<double> halo_send, halo_recv;                                    // [6 * n_halo_entries]
   DBuf<int32_t> err;
-  DBuf<int32_t> work_ctr;                                               // persistent kernels: next work item
 };
 
 // host copies of the bindable frozen fields (so that un-binding a parameter restores them)
@@ -204,6 +203,9 @@ void fused_inlet_coef(hg_ctx* ctx, const double* d_Q);
 // fused VJP (hg_vjp.cu)
 int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);
+int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar, const int32_t* tile_order,
+                    int32_t tile_base, int32_t n_run);
+int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar);
 int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 int fused_halo_pack(hg_ctx* ctx, bool with_lambda);
 int fused_adjoint_step(hg_ctx* ctx, const double* Qn, const double* Qn1, double* lam, double* lam_tmp, double* pbar_acc, int64_t np, double dt);

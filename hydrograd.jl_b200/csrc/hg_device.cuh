@@ -147,6 +147,8 @@ template <int T_, int ML_, int MF_, int NF_, int THREADS_, int MINB_>
 struct TileCfg {
   static constexpr int T = T_, ML = ML_, MF = MF_, NF = NF_, THREADS = THREADS_, MINB = MINB_;
   static constexpr int kSmem = 16 + 8 * (7 * ML + 3 * MF + 4 * T) + 4 * MF + 2 * T * NF;
+  // half as many threads as cells: every thread owns exactly two cells and ~four faces, processed pairwise
+  static constexpr bool kDual = 2 * THREADS_ <= T_;
 };
 
 
@@ -159,6 +161,8 @@ struct TileCfg {
 // T=256/192/4 0.184, T=512/384/2 0.195.
 #define HG_TILE_CONFIGS(X)            \
   X(7, 256, 336, 564, 4, 160, 5)      \
+  X(10, 256, 336, 564, 4, 128, 5)     \
+  X(11, 256, 336, 564, 4, 128, 4)     \
   X(1, 256, 352, 580, 4, 192, 4)      \
   X(0, 256, 352, 580, 4, 128, 4)      \
   X(2, 256, 352, 580, 4, 256, 3)      \

@@ -23,6 +23,8 @@ using namespace dev;
 struct VjpArgs {
   int32_t N, n_tiles, want_s0;
   int32_t prefetch;            // > 0: CTA b pulls the blocks of tile b + prefetch into L2 (see hg_fused.cu, prefetch_work)
+  const int32_t* tile_order;   // host-buffer pipeline: run the tiles tile_order[tile_base ...] (NULL: identity)
+  int32_t tile_base;
   int64_t Ns;
   Consts c;
   const int32_t *tile_desc, *halo, *bface_e;
@@ -386,14 +388,15 @@ __device__ __forceinline__ void vjp_boundary_face(Smem& sm, const VjpArgs& a, in
 
 // The common path needs ~90 registers; TH x MB is picked per tile size so that MB CTAs fit next to each other in
 // shared memory and TH*MB*regs <= 64K (vjp_pick below).
-template <int T, int ML, int MF, int NF, int TH, int MB>
+template <int T, int ML, int MF, int NF, int TH, int MB, int FPT>
 __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ VjpArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   using Smem = VjpSmem<T, ML, MF, NF>;
   Smem& sm = *reinterpret_cast<Smem*>(smraw);
   constexpr int kThreads = TH;
 
-  const int t = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int t = a.tile_order ? __ldg(a.tile_order + a.tile_base + (int)blockIdx.x) : (int)blockIdx.x;
   const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc));
   const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 1);
   const int4 d2 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 2);
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     stage_cell(l, xi, qx, qy, hst);
     sm.m0[l] = l0 * rA; sm.m1[l] = l1 * rA; sm.m2[l] = l2 * rA;
   }
-  if (a.prefetch > 0 && tid == kThreads - 1 && t + a.prefetch < a.n_tiles) {
+  if (a.prefetch > 0 && !a.tile_order && tid == kThreads - 1 && t + a.prefetch < a.n_tiles) {
     const int32_t tp = t + a.prefetch;
     const int4 p0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)tp * kTileDesc));
     const int4 p1 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)tp * kTileDesc) + 1);
@@ -473,10 +476,28 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
   mbar_wait(sm.bar, 0);
 
   // ---- phase 1: owned cells, in place
-  for (int32_t l = tid; l < nc; l += kThreads) {
+  auto own_cell = [&](int32_t l) {
     stage_cell(l, sm.xi[l], sm.u[l], sm.v[l], sm.dP[l]);
     const double rA = fast_rcp(sm.area[l]);
     sm.m0[l] *= rA; sm.m1[l] *= rA; sm.m2[l] *= rA;
+  };
+  if constexpr (FPT == 1) {
+    for (int32_t l = tid; l < nc; l += kThreads) own_cell(l);
+  } else {   // two cells per trip in one basic block (independent chains interleave)
+    for (int32_t l = tid; l < nc; l += 2 * kThreads) {
+      if (l + kThreads < nc) {
+        const int32_t l2 = l + kThreads;
+        const double x1 = sm.xi[l], qx1 = sm.u[l], qy1 = sm.v[l], hs1 = sm.dP[l], A1 = sm.area[l];
+        const double x2 = sm.xi[l2], qx2 = sm.u[l2], qy2 = sm.v[l2], hs2 = sm.dP[l2], A2 = sm.area[l2];
+        stage_cell(l, x1, qx1, qy1, hs1);
+        stage_cell(l2, x2, qx2, qy2, hs2);
+        const double rA1 = fast_rcp(A1), rA2 = fast_rcp(A2);
+        sm.m0[l] *= rA1; sm.m1[l] *= rA1; sm.m2[l] *= rA1;
+        sm.m0[l2] *= rA2; sm.m1[l2] *= rA2; sm.m2[l2] *= rA2;
+      } else {
+        own_cell(l);
+      }
+    }
   }
   __syncthreads();
 
@@ -484,10 +505,8 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
   // transpose folded in algebraically (roe_adj_core + fold_core_side, ~90 registers); both dry: zero flux, zero
   // adjoint.  Faces with exactly one dry side (wet/dry fronts) take the general routine.  (Measured: moving the
   // general routine out of line, or into a second scan over the faces, is 5-10 % slower.)
-  for (int32_t f = tid; f < nint; f += kThreads) {
-    const uint32_t lr = sm.lr[f];
-    const int32_t lL = lr & 0xFFFFu, lR = lr >> 16;
-    const double hL = sm.h[lL], hR = sm.h[lR];
+  // one face, any case
+  auto one_face = [&](int32_t f, int32_t lL, int32_t lR, double hL, double hR) {
     const bool dL = hL <= hs, dR = hR <= hs;
     if (__builtin_expect(dL || dR, 0)) {
       if (dL && dR) {
@@ -495,7 +514,7 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
       } else {
         vjp_front_face(sm, a, f, zb_local(lL), zb_local(lR));
       }
-      continue;
+      return;
     }
     const double nx = sm.o[0][f], ny = sm.o[1][f], len = sm.o[2][f];
     const double f0b = (sm.m0[lR] - sm.m0[lL]) * len, f1b = (sm.m1[lR] - sm.m1[lL]) * len, f2b = (sm.m2[lR] - sm.m2[lL]) * len;
@@ -507,6 +526,47 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     sm.o[0][f] = xb; sm.o[1][f] = qxb; sm.o[2][f] = qyb;
     fold_core_side(k, 1.0, nx, ny, sm.u[lR], sm.v[lR], sm.sg[lR], sm.rs2[lR], sm.dP[lR], xb, qxb, qyb);
     sm.o[3][f] = xb; sm.o[4][f] = qxb; sm.o[5][f] = qyb;
+  };
+  if constexpr (FPT == 1) {
+    for (int32_t f = tid; f < nint; f += kThreads) {
+      const uint32_t lr = sm.lr[f];
+      const int32_t lL = lr & 0xFFFFu, lR = lr >> 16;
+      one_face(f, lL, lR, sm.h[lL], sm.h[lR]);
+    }
+  } else {
+    // two faces per thread and trip: when both are in the common case their sweeps sit in one basic block, so the two
+    // independent dependency chains interleave (the sweep is latency-bound at the occupancy its registers allow)
+    for (int32_t fA = tid; fA < nint; fA += 2 * kThreads) {
+      const int32_t fB = fA + kThreads;
+      const uint32_t lrA = sm.lr[fA];
+      const int32_t aL = lrA & 0xFFFFu, aR = lrA >> 16;
+      const double hAL = sm.h[aL], hAR = sm.h[aR];
+      if (fB >= nint) { one_face(fA, aL, aR, hAL, hAR); break; }
+      const uint32_t lrB = sm.lr[fB];
+      const int32_t bL = lrB & 0xFFFFu, bR = lrB >> 16;
+      const double hBL = sm.h[bL], hBR = sm.h[bR];
+      if (__builtin_expect(hAL <= hs || hAR <= hs || hBL <= hs || hBR <= hs, 0)) {
+        one_face(fA, aL, aR, hAL, hAR);
+        one_face(fB, bL, bR, hBL, hBR);
+        continue;
+      }
+      const double nxA = sm.o[0][fA], nyA = sm.o[1][fA], lenA = sm.o[2][fA];
+      const double nxB = sm.o[0][fB], nyB = sm.o[1][fB], lenB = sm.o[2][fB];
+      FaceCore kA, kB;
+      roe_adj_core(sm.xi[aL], hAL, sm.u[aL], sm.v[aL], sm.s[aL], sm.xi[aR], hAR, sm.u[aR], sm.v[aR], sm.s[aR], nxA, nyA, g,
+                   (sm.m0[aR] - sm.m0[aL]) * lenA, (sm.m1[aR] - sm.m1[aL]) * lenA, (sm.m2[aR] - sm.m2[aL]) * lenA, kA);
+      roe_adj_core(sm.xi[bL], hBL, sm.u[bL], sm.v[bL], sm.s[bL], sm.xi[bR], hBR, sm.u[bR], sm.v[bR], sm.s[bR], nxB, nyB, g,
+                   (sm.m0[bR] - sm.m0[bL]) * lenB, (sm.m1[bR] - sm.m1[bL]) * lenB, (sm.m2[bR] - sm.m2[bL]) * lenB, kB);
+      double xA, qxA, qyA, xB, qxB, qyB;
+      fold_core_side(kA, -1.0, nxA, nyA, sm.u[aL], sm.v[aL], sm.sg[aL], sm.rs2[aL], sm.dP[aL], xA, qxA, qyA);
+      fold_core_side(kB, -1.0, nxB, nyB, sm.u[bL], sm.v[bL], sm.sg[bL], sm.rs2[bL], sm.dP[bL], xB, qxB, qyB);
+      sm.o[0][fA] = xA; sm.o[1][fA] = qxA; sm.o[2][fA] = qyA;
+      sm.o[0][fB] = xB; sm.o[1][fB] = qxB; sm.o[2][fB] = qyB;
+      fold_core_side(kA, 1.0, nxA, nyA, sm.u[aR], sm.v[aR], sm.sg[aR], sm.rs2[aR], sm.dP[aR], xA, qxA, qyA);
+      fold_core_side(kB, 1.0, nxB, nyB, sm.u[bR], sm.v[bR], sm.sg[bR], sm.rs2[bR], sm.dP[bR], xB, qxB, qyB);
+      sm.o[3][fA] = xA; sm.o[4][fA] = qxA; sm.o[5][fA] = qyA;
+      sm.o[3][fB] = xB; sm.o[4][fB] = qxB; sm.o[5][fB] = qyB;
+    }
   }
   // ---- phase 2b: boundary faces (physical boundaries and halo faces)
   for (int32_t f = nint + tid; f < nf; f += kThreads) vjp_boundary_face(sm, a, f, nint, bfp, c0);
@@ -515,8 +575,8 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
 
   // ---- phase 3: per-cell gather of the face adjoints (L or R side of each face) + source adjoint
   const double kfr = g / (a.c.k_n * a.c.k_n);
-  for (int32_t l = tid; l < nc; l += kThreads) {
-    const int32_t gi = c0 + l;
+  struct CellOut { double xib, qxb, qyb, nb, s0x, s0y; };
+  auto cell_adj = [&](int32_t l) {
     uint16_t slot[NF];
     if constexpr (NF == 4) {
       const uint2 w = *reinterpret_cast<const uint2*>(&sm.cf[l * 4]);
@@ -536,33 +596,53 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
       const int side = (slot[j] & 0x8000) ? 3 : 0;
       xib += sm.o[side + 0][f]; qxb += sm.o[side + 1][f]; qyb += sm.o[side + 2][f];
     }
-    // sources (wet cells): r1 += g xi S0x - C m qx,  C = g n^2/k_n^2 (h+hs)^(-7/3),  m = sqrt(qx^2+qy^2+eps)
+    // sources (wet cells): r1 += g xi S0x - C m qx,  C = g n^2/k_n^2 (h+hs)^(-7/3),  m = sqrt(qx^2+qy^2+eps).
+    // Evaluated branch-free (every operand is finite for a clamped cell too) and selected by the wet flag.
     const double h = sm.h[l];
-    double nb = 0.0, s0xb = 0.0, s0yb = 0.0;
-    if (h > hs) {
-      const double xi = sm.xi[l], u = sm.u[l], v = sm.v[l];
-      const double A = sm.area[l], n = sm.mann[l];
-      const double lam1 = sm.m1[l] * A, lam2 = sm.m2[l] * A;   // mu * area = lambda
-      const double qx = h * u, qy = h * v;
-      const double y = fma(qx, qx, fma(qy, qy, EPS));
-      const double rm = fast_rsqrt(y);
-      const double mag = y * rm;
-      const double C = kfr * n * n * pow_m73(h + hs);
-      const double fxb = -lam1, fyb = -lam2;
-      const double cross = C * qx * qy * rm;
-      qxb += fxb * (C * mag + C * qx * qx * rm) + fyb * cross;
-      qyb += fyb * (C * mag + C * qy * qy * rm) + fxb * cross;
-      const double D = (fxb * qx + fyb * qy) * C * mag;      // fxb*fx + fyb*fy
-      xib += -(7.0 / 3.0) * D * fast_rcp(h + hs);            // through h = xi + hstill (the cell is wet, hence unclamped)
-      nb = 2.0 * D * fast_rcp(n);
-      xib += g * (sm.sx[l] * lam1 + sm.sy[l] * lam2);
-      s0xb = g * xi * lam1; s0yb = g * xi * lam2;
+    const bool wet = h > hs;
+    const double xi = sm.xi[l], u = sm.u[l], v = sm.v[l];
+    const double A = sm.area[l], n = sm.mann[l];
+    const double lam1 = sm.m1[l] * A, lam2 = sm.m2[l] * A;   // mu * area = lambda
+    const double qx = h * u, qy = h * v;
+    const double y = fma(qx, qx, fma(qy, qy, EPS));
+    const double rm = fast_rsqrt(y);
+    const double mag = y * rm;
+    const double C = kfr * n * n * pow_m73(h + hs);
+    const double fxb = -lam1, fyb = -lam2;
+    const double cross = C * qx * qy * rm;
+    const double dqx = fxb * (C * mag + C * qx * qx * rm) + fyb * cross;
+    const double dqy = fyb * (C * mag + C * qy * qy * rm) + fxb * cross;
+    const double D = (fxb * qx + fyb * qy) * C * mag;      // fxb*fx + fyb*fy
+    // -(7/3) D / (h+hs): through h = xi + hstill (a wet cell is unclamped); bed slope: g xi S0 . lambda
+    const double dxi = -(7.0 / 3.0) * D * fast_rcp(h + hs) + g * (sm.sx[l] * lam1 + sm.sy[l] * lam2);
+    CellOut o;
+    o.xib = wet ? xib + dxi : xib;
+    o.qxb = wet ? qxb + dqx : qxb;
+    o.qyb = wet ? qyb + dqy : qyb;
+    o.nb = wet ? 2.0 * D * fast_rcp(n) : 0.0;
+    o.s0x = wet ? g * xi * lam1 : 0.0;
+    o.s0y = wet ? g * xi * lam2 : 0.0;
+    return o;
+  };
+  auto cell_store = [&](int32_t l, const CellOut& o) {
+    const int32_t gi = c0 + l;
+    a.Qbar[gi] = o.xib;
+    a.Qbar[Ns + gi] = o.qxb;
+    a.Qbar[2 * Ns + gi] = o.qyb;
+    a.nbar[gi] = o.nb;
+    if (a.want_s0) { a.s0bar[gi] = o.s0x; a.s0bar[Ns + gi] = o.s0y; }
+  };
+  if constexpr (FPT == 1) {
+    for (int32_t l = tid; l < nc; l += kThreads) cell_store(l, cell_adj(l));
+  } else {
+    for (int32_t l = tid; l < nc; l += 2 * kThreads) {
+      if (l + kThreads < nc) {
+        const CellOut o1 = cell_adj(l), o2 = cell_adj(l + kThreads);
+        cell_store(l, o1); cell_store(l + kThreads, o2);
+      } else {
+        cell_store(l, cell_adj(l));
+      }
     }
-    a.Qbar[gi] = xib;
-    a.Qbar[Ns + gi] = qxb;
-    a.Qbar[2 * Ns + gi] = qyb;
-    a.nbar[gi] = nb;
-    if (a.want_s0) { a.s0bar[gi] = s0xb; a.s0bar[Ns + gi] = s0yb; }
   }
 }
 
@@ -694,28 +774,28 @@ struct VjpKernel {
   const void* fn = nullptr;
   int threads = 0, smem = 0, ctas_per_sm = 1;
 };
-template <int T, int ML, int MF, int NF, int TH, int MB>
+template <int T, int ML, int MF, int NF, int TH, int MB, int FPT>
 VjpKernel vjp_mk() {
-  return VjpKernel{(const void*)k_fused_vjp<T, ML, MF, NF, TH, MB>, TH, (int)sizeof(VjpSmem<T, ML, MF, NF>), MB};
+  return VjpKernel{(const void*)k_fused_vjp<T, ML, MF, NF, TH, MB, FPT>, TH, (int)sizeof(VjpSmem<T, ML, MF, NF>), MB};
 }
 template <int T, int ML, int MF, int NF>
 VjpKernel vjp_pick(int v) {
   if constexpr (T == 256) {
-    if (v == 1) return vjp_mk<T, ML, MF, NF, 160, 3>();
-    if (v == 2) return vjp_mk<T, ML, MF, NF, 224, 3>();
-    return vjp_mk<T, ML, MF, NF, 192, 3>();
+    // measured at 16M cells (ms): 128x3 two faces per trip 0.92 | 192x3 one face 1.02 | 160x3 two faces 1.14 (spills)
+    if (v == 1) return vjp_mk<T, ML, MF, NF, 192, 3, 1>();
+    if (v == 2) return vjp_mk<T, ML, MF, NF, 160, 3, 2>();
+    return vjp_mk<T, ML, MF, NF, 128, 3, 2>();
   } else if constexpr (T == 192) {
-    if (v == 1) return vjp_mk<T, ML, MF, NF, 128, 4>();
-    if (v == 2) return vjp_mk<T, ML, MF, NF, 192, 3>();
-    return vjp_mk<T, ML, MF, NF, 160, 4>();
+    // 96x4 two faces per trip 0.91 | 128x4 one face 0.96 | 128x4 two faces 1.07 (spills)
+    if (v == 1) return vjp_mk<T, ML, MF, NF, 128, 4, 1>();
+    if (v == 2) return vjp_mk<T, ML, MF, NF, 128, 4, 2>();
+    return vjp_mk<T, ML, MF, NF, 96, 4, 2>();
   } else if constexpr (T == 128 && NF == 4) {
-    if (v == 1) return vjp_mk<T, ML, MF, NF, 128, 4>();
-    if (v == 2) return vjp_mk<T, ML, MF, NF, 96, 5>();
-    return vjp_mk<T, ML, MF, NF, 128, 5>();
+    return vjp_mk<T, ML, MF, NF, 128, 4, 1>();
   } else if constexpr (T == 128) {
-    return vjp_mk<T, ML, MF, NF, 128, 3>();
+    return vjp_mk<T, ML, MF, NF, 128, 3, 1>();
   } else {
-    return vjp_mk<T, ML, MF, NF, 512, 1>();
+    return vjp_mk<T, ML, MF, NF, 512, 1, 1>();
   }
 }
 VjpKernel vjp_kernel(int cfg_id, int variant) {
@@ -741,12 +821,13 @@ int fused_vjp_prepare(hg_ctx* ctx, int cfg_id) {
   return HG_OK;
 }
 
-// Qbar (internal order, [3Ns]) and the parameter adjoint for the active parameter (pbar, device).
-int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar) {
+// The tile kernel over the tiles tile_order[tile_base .. tile_base + n_run) (tile_order NULL: all tiles, identity).
+// The inlet coefficients must be current (fused_inlet_coef).
+int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar, const int32_t* tile_order,
+                    int32_t tile_base, int32_t n_run) {
   FusedDev& d = ctx->fd;
   const FusedHost& fh = ctx->fh;
-  const int th = 256;
-  if (ctx->n_inletq > 0) fused_inlet_coef(ctx, d_Q);
+  if (n_run == 0) return HG_OK;
   VjpArgs a;
   a.N = (int32_t)ctx->N; a.n_tiles = fh.n_tiles; a.want_s0 = ctx->active == HG_PARAM_ZB ? 1 : 0;
   a.Ns = fh.Ns; a.c = ctx->c;
@@ -758,7 +839,8 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
   a.halo_off = d.halo_off.p; a.halo_cnt = d.halo_cnt.p; a.halo_recv = d.halo_recv.p;
   a.wse = d.wse.p; a.Q = d_Q; a.lam = d_lam; a.Qbar = d_Qbar; a.nbar = d.nbar.p; a.s0bar = d.s0bar.p;
   a.ent_c = d.ent_c.p; a.ent_n = d.ent_n.p; a.ent_z = d.ent_z.p;
-  const unsigned grid = (unsigned)fh.n_tiles;
+  a.tile_order = tile_order; a.tile_base = tile_base;
+  const unsigned grid = (unsigned)(n_run >= 0 ? n_run : fh.n_tiles);
   const VjpKernel kk = vjp_kernel(cfg_id, ctx->opt.reserved[2]);
   if (!kk.fn) { ctx->err = "no VJP tile configuration"; return HG_ERR_ARG; }
   {
@@ -769,6 +851,15 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
     if (le != cudaSuccess) { ctx->err = std::string("fused_vjp launch: ") + cudaGetErrorString(le); return HG_ERR_CUDA; }
   }
   ctx->launches++;
+  return HG_OK;
+}
+
+// Boundary-wide couplings (inlet conveyance split) and the parameter adjoint of the active parameter (pbar, device),
+// after every tile has run.
+int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar) {
+  FusedDev& d = ctx->fd;
+  const FusedHost& fh = ctx->fh;
+  const int th = 256;
   if (ctx->n_inletq > 0) {
     k_inlet_adj<<<(unsigned)ctx->n_inletq, 256, 0, ctx->stream>>>(ctx->c, d.inlet_ptr.p, d.bc_cell.p, d.bc_l53.p, d_Q,
                                                                  d.hstill.p, d.mann.p, d.inlet_A.p, d.inlet_coef.p, d.ent_c.p,
@@ -809,6 +900,14 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ctx->err = std::string("fused_vjp launch: ") + cudaGetErrorString(e); return HG_ERR_CUDA; }
   return HG_OK;
+}
+
+
+// Qbar (internal order, [3Ns]) and the parameter adjoint for the active parameter (pbar, device).
+int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar) {
+  if (ctx->n_inletq > 0) fused_inlet_coef(ctx, d_Q);
+  const int rc = fused_vjp_tiles(ctx, cfg_id, d_Q, d_lam, d_Qbar, nullptr, 0, -1);
+  return rc != HG_OK ? rc : fused_vjp_finish(ctx, d_Q, d_Qbar);
 }
 
 // ncell_bar in reference order (UDE hook): dst[r] = nbar[iperm[r]]

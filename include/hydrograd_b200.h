@@ -129,7 +129,7 @@ typedef struct {
   int32_t strict;                  /* 1 = reference evaluation order, no FMA contraction         */
   int32_t path;                    /* 0 = fused tile kernel, 1 = plain 3-kernel path (ghost/face/cell) */
   int32_t reserved[11];            /* reserved[0]: threads per CTA of the fused kernel (0 = default), tuning only;
-                                      reserved[1]: 1 = persistent CTAs with a two-stage tile pipeline (experiment; slower);
+                                      reserved[1]: unused;
                                       reserved[2]: launch-shape variant of the VJP kernel (0 = default), tuning only;
                                       reserved[3]: L2 prefetch distance in tiles (0 = one residency ahead, -1 = off) */
 } hg_options;

@@ -106,14 +106,15 @@ class Oracle:
             raise RuntimeError(f"oracle_rhs failed with code {rc}")
         return (out, gh.reshape(4, self.B)) if ghosts else out
 
-    def jvp(self, Q, vQ, params=None, vP=None, active=0):
+    def jvp(self, Q, vQ, params=None, vP=None, active=0, nthreads=1):
         Q = np.ascontiguousarray(Q, dtype=np.float64)
         vQ = np.ascontiguousarray(vQ if vQ is not None else np.zeros_like(Q), dtype=np.float64)
         p, npar = self._params(params)
         vp = np.ascontiguousarray(vP if vP is not None else np.zeros_like(p), dtype=np.float64)
         out, jv = np.empty(3 * self.N), np.empty(3 * self.N)
         rc = self.lib.oracle_rhs_jvp(*self._args(), _p(Q, c_f64p), _p(vQ, c_f64p), _p(p, c_f64p), _p(vp, c_f64p),
-                                     C.c_int64(npar), C.c_int(active), _p(out, c_f64p), _p(jv, c_f64p))
+                                     C.c_int64(npar), C.c_int(active), _p(out, c_f64p), _p(jv, c_f64p),
+                                     C.c_int(nthreads or self.max_threads()))
         if rc:
             raise RuntimeError(f"oracle_rhs_jvp failed with code {rc}")
         return out, jv

@@ -329,13 +329,13 @@ int oracle_rhs(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc*
 // Directional derivative: jvp = d rhs/dQ . vQ + d rhs/dp . vP   (ForwardDiff semantics)
 int oracle_rhs_jvp(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, const double* Q,
                    const double* vQ, const double* params, const double* vP, int64_t np, int active, double* dQ,
-                   double* jvp) {
+                   double* jvp, int nthreads) {
   View v(*m, *b, *f);
   const int64_t N = v.N;
   std::vector<Dual> q(3 * N), p(np > 0 ? np : 1), out(3 * N);
   for (int64_t i = 0; i < 3 * N; ++i) q[i] = Dual(Q[i], vQ ? vQ[i] : 0.0);
   for (int64_t i = 0; i < np; ++i) p[i] = Dual(params[i], vP ? vP[i] : 0.0);
-  int rc = rhs_impl<Dual>(v, q.data(), p.data(), np, active, out.data(), 1, nullptr);
+  int rc = rhs_impl<Dual>(v, q.data(), p.data(), np, active, out.data(), nthreads > 0 ? nthreads : 1, nullptr);
   if (rc) return rc;
   for (int64_t i = 0; i < 3 * N; ++i) { if (dQ) dQ[i] = out[i].v; jvp[i] = out[i].d; }
   return HG_OK;

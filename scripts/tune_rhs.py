@@ -8,8 +8,8 @@ nx = int(M * 1e6 / 1.1 / 1000); flat, Q0 = S.river(nx, 1000)
 N, F = flat["n_cells"], flat["n_faces"]
 B = 100 * N + 32 * F + 4 * int(flat["cell_nfaces"].sum())
 print("N", N, "bytes/cell", B / N, flush=True)
-for tile, threads, pipe, pf in [(256, 0, 2, 0), (256, 0, 1, 0), (256, 0, 1, 1)]:
-    ctx = hg.Context(flat, tile_cells=tile, threads=threads, pipeline=pipe, prefetch=pf)
+for tile, threads, pipe, pf in [(256, 0, 0, 0), (256, 1010, 0, 0), (256, 1011, 0, 0), (512, 256, 0, 0)]:
+    ctx = hg.Context(flat, tile_cells=tile, threads=threads, prefetch=pf)
     ctx.set_state(Q0)
     ctx.time_rhs(5)
     t = min(ctx.time_rhs(20) / 20 for _ in range(3))

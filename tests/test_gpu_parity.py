@@ -95,7 +95,8 @@ def test_tiling_and_ordering_do_not_change_bits(hg):
     flat, Q0 = synth("river")
     Q = cases.random_state_flat(flat, 11)
     base = hg.Context(flat, tile_cells=512, reorder=True).rhs(Q)
-    for tile, reorder, threads in ((128, True, 0), (256, True, 128), (256, True, 256), (512, False, 384), (128, False, 0)):
+    for tile, reorder, threads in ((128, True, 0), (256, True, 128), (256, True, 256), (512, False, 384), (128, False, 0),
+                                  (256, True, 1010), (256, True, 1011), (512, True, 256)):   # two-faces-per-trip configurations
         got = hg.Context(flat, tile_cells=tile, reorder=reorder, threads=threads).rhs(Q)
         assert np.array_equal(base, got), (tile, reorder, threads)
 
@@ -237,24 +238,28 @@ def test_rk4_stepper(hg):
     assert np.abs(got - Q).max() <= 1e-9 * max(1.0, np.abs(Q).max())
 
 
-@pytest.mark.parametrize("tile", [128, 192, 256, 512])
-def test_persistent_kernel_matches_one_cta_per_tile_bitwise(hg, tile):
-    """Persistent CTAs (hg_options.reserved[1] = 1; next tile's descriptor and halo indices prefetched) run the same
-    per-tile phases in the same order => identical bits, for the RHS and for fused Euler steps (several tiles per
-    CTA: the mesh has more tiles than 148 SMs x resident CTAs).  The L2 prefetch only moves data earlier."""
+@pytest.mark.parametrize("tile", [128, 256])
+def test_l2_prefetch_does_not_change_bits(hg, tile):
+    """The L2 prefetch (hg_options.reserved[3]) only moves data earlier: identical bits with it off, at the default
+    distance and at an odd distance, for the RHS, fused Euler steps and the VJP (mesh with more tiles than resident CTAs)."""
     from hydrograd_jl_b200 import synthetic as S
     key = "river_big"
     if key not in _flat_cache:
         _flat_cache[key] = S.river(700, 260)
     flat, Q0 = _flat_cache[key]
     Q = cases.random_state_flat(flat, 3, dry_frac=0.03)
-    a = hg.Context(flat, tile_cells=tile, pipeline=2, prefetch=-1)
-    others = [hg.Context(flat, tile_cells=tile, pipeline=1), hg.Context(flat, tile_cells=tile, pipeline=2, prefetch=0),
-              hg.Context(flat, tile_cells=tile, pipeline=2, prefetch=37)]
+    lam = np.random.default_rng(4).standard_normal(Q.size)
+    a = hg.Context(flat, tile_cells=tile, prefetch=-1)
+    others = [hg.Context(flat, tile_cells=tile, prefetch=0), hg.Context(flat, tile_cells=tile, prefetch=37)]
     for q in (Q0, Q):
         ref = a.rhs(q)
+        ref_v = a.rhs_vjp(q, lam)
         for b in others:
             assert np.array_equal(ref, b.rhs(q)), tile
+            got_v = b.rhs_vjp(q, lam)
+            for x, y in zip(ref_v, got_v):
+                if x is not None:
+                    assert np.array_equal(x, y)
     a.set_state(Q0)
     a.step_euler(1e-3, 7)
     for b in others:

@@ -93,3 +93,47 @@ def test_ncell_bar_hook(hg):
     Qbar, pbar, nbar = ctx.rhs_vjp(Q, lam, c.ManningN_zone, "ManningN", want_ncell_bar=True)
     z = np.array([nbar[c.matID == k].sum() for k in range(c.ManningN_zone.size)])
     assert np.abs(z - pbar).max() <= 1e-12 * np.abs(pbar).max()
+
+
+def test_vjp_launch_shapes_agree(hg):
+    """Every compiled launch shape of the VJP kernel (tile size x threads x one/two faces per trip) on a mesh with
+    wet/dry fronts and all boundary types: same result to rounding (the shapes differ only in instruction order)."""
+    from hydrograd_jl_b200 import synthetic as S
+    flat, _ = S.river(300, 120)
+    Q = cases.random_state_flat(flat, 12, dry_frac=0.06)
+    lam = np.random.default_rng(8).standard_normal(Q.size)
+    p = np.full(flat["n_mat"], 0.035)
+    base = None
+    for tile, variant in ((256, 0), (256, 1), (256, 2), (192, 0), (192, 1), (192, 2), (128, 0), (512, 0)):
+        Qbar, pbar = hg.Context(flat, tile_cells=tile, vjp_variant=variant).rhs_vjp(Q, lam, p, "ManningN")
+        if base is None:
+            base = (Qbar, pbar)
+            continue
+        assert np.abs(Qbar - base[0]).max() <= 1e-13 * np.abs(base[0]).max(), (tile, variant)
+        assert np.abs(pbar - base[1]).max() <= 1e-12 * np.abs(base[1]).max(), (tile, variant)
+
+
+@pytest.mark.parametrize("mode", ["ManningN", "zb", "Q"])
+def test_host_buffer_vjp_pipeline_matches_resident(hg, mode):
+    """>= 1M cells: hg_rhs_vjp streams Q and lambda in chunks over three streams (tiles run as their chunks land,
+    Qbar chunks leave meanwhile; inlet coupling and parameter reductions after the last stage).  Same kernels on the
+    same data as the device-resident sequence => identical bits, Qbar and pbar, for every parameter mode."""
+    from hydrograd_jl_b200 import synthetic as S
+    flat, Q0 = S.river(1000, 1050)
+    N = flat["n_cells"]
+    assert N >= 1 << 20
+    rng = np.random.default_rng(5)
+    lam = rng.standard_normal(3 * N)
+    p = {"ManningN": np.full(flat["n_mat"], 0.03) * (1 + 0.1 * rng.uniform(-1, 1, flat["n_mat"])),
+         "zb": flat["zb_cells"] + 0.01 * rng.standard_normal(N), "Q": np.asarray(flat["inletQ_TotalQ"]) * 0.9}[mode]
+    ctx = hg.Context(flat)
+    Qbar, pbar, nbar = ctx.rhs_vjp(Q0, lam, p, mode, want_ncell_bar=True)
+    ref = hg.Context(flat)
+    ref.set_params(p, mode)
+    ref.set_state(Q0)
+    ref.set_lambda(lam)
+    ref.vjp_resident()
+    Qbar2, pbar2, nbar2 = ref.get_vjp(p.size, want_ncell_bar=True)
+    assert np.array_equal(Qbar, Qbar2)
+    assert np.array_equal(pbar, pbar2)
+    assert np.array_equal(nbar, nbar2)
