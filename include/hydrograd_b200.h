@@ -131,7 +131,8 @@ typedef struct {
   int32_t reserved[11];            /* reserved[0]: threads per CTA of the fused kernel (0 = default), tuning only;
                                       reserved[1]: unused;
                                       reserved[2]: launch-shape variant of the VJP kernel (0 = default), tuning only;
-                                      reserved[3]: L2 prefetch distance in tiles (0 = one residency ahead, -1 = off) */
+                                      reserved[3]: L2 prefetch distance in tiles (0 = one residency ahead, -1 = off);
+                                      reserved[4]: 1 = do not regroup a tile's faces into bank-conflict-free blocks of 16 */
 } hg_options;
 
 /* fills *opt with the defaults */

@@ -6,7 +6,7 @@ sys.path.insert(0, '.')
 import _pkg; hg = _pkg.load()
 from hydrograd_jl_b200 import synthetic as S
 flat, Q0 = S.river(int(16e6 / 1.1 / 1000), 1000)
-ctx = hg.Context(flat, tile_cells=$1, pipeline=$2)
+ctx = hg.Context(flat, tile_cells=$1)
 ctx.set_state(Q0)
 ctx.time_rhs(3)
 PY
