@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the fused kernel (tuning)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs: the launch list then holds the timed region only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -315,50 +316,52 @@ def main():
 
     # ---- end to end through the host-buffer ABI (pinned host memory; H2D + D2H inside the timed region): at N = 1
     # this is exactly hg_rhs; at N > 1 the same three stages with the halo exchange in between
-    hQ = torch.empty(3 * N, dtype=torch.float64).pin_memory()
-    hD = torch.empty(3 * N, dtype=torch.float64).pin_memory()
-    hL = torch.empty(3 * N, dtype=torch.float64).pin_memory()
-    hB = torch.empty(3 * N, dtype=torch.float64).pin_memory()
-    hQ.numpy()[:] = Q0
-    hL.numpy()[:] = 1.0
-    out, outb = hD.numpy(), hB.numpy()
+    e2e = None
+    if not args.no_e2e:
+        hQ = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+        hD = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+        hL = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+        hB = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+        hQ.numpy()[:] = Q0
+        hL.numpy()[:] = 1.0
+        out, outb = hD.numpy(), hB.numpy()
 
-    def e2e_rhs():
-        if ex is None:
-            ctx.rhs(hQ.numpy(), out=out)
-        else:
-            ctx.set_state(hQ.numpy())
-            rhs_step()
-            ctx.get_rhs(out=out)
+        def e2e_rhs():
+            if ex is None:
+                ctx.rhs(hQ.numpy(), out=out)
+            else:
+                ctx.set_state(hQ.numpy())
+                rhs_step()
+                ctx.get_rhs(out=out)
 
-    def e2e_vjp():
-        if ex is None:
-            ctx.rhs_vjp_into(hQ.numpy(), hL.numpy(), outb)
-        else:
-            ctx.set_state(hQ.numpy())
-            ctx.set_lambda(hL.numpy())
-            vjp_step()
-            ctx.get_vjp_into(outb)
+        def e2e_vjp():
+            if ex is None:
+                ctx.rhs_vjp_into(hQ.numpy(), hL.numpy(), outb)
+            else:
+                ctx.set_state(hQ.numpy())
+                ctx.set_lambda(hL.numpy())
+                vjp_step()
+                ctx.get_vjp_into(outb)
 
-    e2e_rhs(); e2e_vjp()  # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_rhs()
-    barrier()
-    t1 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_vjp()
-    barrier()
-    t2 = time.perf_counter()
-    e2e_rhs_s = allmax((t1 - t0) / args.e2e_steps)
-    e2e_vjp_s = allmax((t2 - t1) / args.e2e_steps)
-    e2e_s = e2e_rhs_s + e2e_vjp_s
-    e2e = {"value": N_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 72 * N, "d2h_bytes_per_step": 48 * N,
-           "ms_per_step": e2e_s * 1e3, "rhs_ms": e2e_rhs_s * 1e3, "vjp_ms": e2e_vjp_s * 1e3,
-           "rhs_only": N_total / e2e_rhs_s,
-           "what": "one RHS + one VJP through pinned host buffers (hg_rhs: H2D state, kernel, D2H dQdt; hg_rhs_vjp: H2D state "
-                   "and lambda, kernel, D2H Qbar), chunked over three streams"}
+        e2e_rhs(); e2e_vjp()  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_rhs()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_vjp()
+        barrier()
+        t2 = time.perf_counter()
+        e2e_rhs_s = allmax((t1 - t0) / args.e2e_steps)
+        e2e_vjp_s = allmax((t2 - t1) / args.e2e_steps)
+        e2e_s = e2e_rhs_s + e2e_vjp_s
+        e2e = {"value": N_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 72 * N, "d2h_bytes_per_step": 48 * N,
+               "ms_per_step": e2e_s * 1e3, "rhs_ms": e2e_rhs_s * 1e3, "vjp_ms": e2e_vjp_s * 1e3,
+               "rhs_only": N_total / e2e_rhs_s,
+               "what": "one RHS + one VJP through pinned host buffers (hg_rhs: H2D state, kernel, D2H dQdt; hg_rhs_vjp: H2D state "
+                       "and lambda, kernel, D2H Qbar), chunked over three streams"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
