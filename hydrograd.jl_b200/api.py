@@ -180,6 +180,18 @@ class Context:
                 for a in (ManningN_cells, zb_cells, zb_ghost, S0_cells, inletQ_TotalQ, exitH_WSE)]
         self._ck(self.lib.hg_set_fields(self._h, *[_p(a) for a in arrs]))
 
+    MANNING_TYPES = {"constant": 0, "power_law": 1, "sigmoid": 2, "inverse": 3, "h_Umag_ks": 4}
+
+    def set_manning_function(self, kind="constant", n_lower=0.0, n_upper=0.0, k=0.0, h_mid=0.0, ks_cells=None):
+        """forward_settings.ManningN_option = "variable" (semi_discretize_swe_2D.jl:140-149): n(h) / n(h, |U|, ks) evaluated
+        inside every RHS; `kind` and the parameters are ManningN_function_type / ManningN_function_parameters of the control
+        file (create_manning_function, process_ManningN_2D.jl:119-133); ks_cells[N] for "h_Umag_ks"."""
+        if kind not in self.MANNING_TYPES:
+            raise ValueError(f"Unknown Manning's n function type: {kind}. Supported types: {', '.join(self.MANNING_TYPES)}.")
+        p = np.array([n_lower, n_upper, k, h_mid], dtype=np.float64)
+        ks = None if ks_cells is None else _f64(ks_cells)
+        self._ck(self.lib.hg_set_manning_function(self._h, self.MANNING_TYPES[kind], _p(p), _p(ks)))
+
     # ---------------------------------------------------------------- adjoint on the resident state
     def set_lambda(self, lam):
         self._ck(self.lib.hg_set_lambda(self._h, _p(_f64(lam))))

@@ -116,6 +116,13 @@ static int upload_fields(hg_ctx* ctx) {
 // Bind params_vector to the frozen fields (semi_discretize_swe_2D.jl:114-126, 153-161, 190-199).
 // Parameters change once per optimiser iteration but the RHS runs thousands of times in between,
 // so the binding is done here, once, and the RHS kernels stay parameter-agnostic.
+// The reference evaluates the closures in forward simulations only (semi_discretize_swe_2D.jl:140-149): no derivative path
+static int no_closure(hg_ctx* ctx, const char* what) {
+  if (ctx->mfn.type == HG_MANNING_CONSTANT) return HG_OK;
+  ctx->err = std::string(what) + ": not available while a variable Manning's n closure is set (forward simulation only)";
+  return HG_ERR_ARG;
+}
+
 static int bind_params(hg_ctx* ctx, const double* params, int64_t np, int32_t active) {
   hg_ctx* x = ext(ctx);
   if (active < HG_PARAM_NONE || active > HG_PARAM_Q) { ctx->err = "bad active_param"; return HG_ERR_ARG; }
@@ -125,6 +132,7 @@ static int bind_params(hg_ctx* ctx, const double* params, int64_t np, int32_t ac
     return HG_ERR_ARG;
   }
   if (active == HG_PARAM_MANNING && x->matid_ref.empty()) { ctx->err = "matID_cells was not provided at hg_create"; return HG_ERR_ARG; }
+  if (active == HG_PARAM_MANNING) TRY(no_closure(ctx, "active parameter ManningN"));
   if (active == HG_PARAM_NONE) np = 0;
   const bool same = (active == x->last_active) && (np == (int64_t)x->last_params.size()) &&
                     (np == 0 || std::memcmp(params, x->last_params.data(), np * 8) == 0);
@@ -337,6 +345,33 @@ int hg_set_fields(hg_ctx* ctx, const double* mann, const double* zb, const doubl
   return upload_fields(ctx);
 }
 
+int hg_set_manning_function(hg_ctx* ctx, int32_t type, const double* params, const double* ks_cells) {
+  if (!ctx) return HG_ERR_ARG;
+  if (type < HG_MANNING_CONSTANT || type > HG_MANNING_H_UMAG_KS) { ctx->err = "hg_set_manning_function: unknown type"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::MannFn m;
+  m.type = type;
+  if (type != HG_MANNING_CONSTANT) {
+    if (!params) { ctx->err = "hg_set_manning_function: params is NULL"; return HG_ERR_ARG; }
+    m.n_lower = params[0]; m.n_upper = params[1]; m.k = params[2]; m.h_mid = params[3];
+    if (type != HG_MANNING_H_UMAG_KS && !(m.k > 0.0)) { ctx->err = "hg_set_manning_function: k must be positive"; return HG_ERR_ARG; }   // process_ManningN_2D.jl:141,158,175
+    if (type == HG_MANNING_SIGMOID && !(m.h_mid > 0.0)) { ctx->err = "hg_set_manning_function: h_mid must be positive"; return HG_ERR_ARG; }   // :176
+    if (type == HG_MANNING_H_UMAG_KS && !ks_cells) { ctx->err = "hg_set_manning_function: ks_cells is NULL"; return HG_ERR_ARG; }
+    if (ctx->active == HG_PARAM_MANNING) { ctx->err = "hg_set_manning_function: ManningN is the active parameter"; return HG_ERR_ARG; }
+    const int64_t N = ctx->N;
+    std::vector<double> ks(N, 1.0);
+    if (ks_cells) ks.assign(ks_cells, ks_cells + N);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->opt.path == 1) {
+      TRY(up(ctx, ctx->pd.ks, ks));
+    } else {
+      TRY(upN(ctx, ctx->fd.ks, permuted(ks.data(), ctx->fh.perm), (size_t)ctx->fh.Ns));
+    }
+  }
+  ctx->mfn = m;
+  return HG_OK;
+}
+
 int hg_sync(hg_ctx* ctx) {
   if (!ctx) return HG_ERR_ARG;
   CK(ctx, cudaSetDevice(ctx->opt.device));
@@ -509,6 +544,7 @@ int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   (void)t;
   if (!ctx || !Q || !lambda || !Qbar) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "hg_rhs_vjp needs the fused path (strict = 0)"; return HG_ERR_ARG; }
+  TRY(no_closure(ctx, "hg_rhs_vjp"));
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
   if (ctx->active != HG_PARAM_NONE && !pbar) { ctx->err = "hg_rhs_vjp: pbar is NULL"; return HG_ERR_ARG; }
@@ -542,6 +578,7 @@ int hg_vjp_resident(hg_ctx* ctx) {
   if (!ctx) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "hg_vjp_resident needs the fused path"; return HG_ERR_ARG; }
   if (!ctx->state_set || !ctx->lam_set) { ctx->err = "hg_vjp_resident: state or lambda not set"; return HG_ERR_STATE; }
+  TRY(no_closure(ctx, "hg_vjp_resident"));
   CK(ctx, cudaSetDevice(ctx->opt.device));
   return hg::fused_vjp(ctx, hg::fused_cfg_id(ctx), ctx->fd.Q.p, ctx->fd.lam.p, ctx->fd.Qbar.p);
 }
@@ -600,6 +637,7 @@ int hg_set_stream(hg_ctx* ctx, void* cuda_stream) {
 int hg_ensemble_alloc(hg_ctx* ctx, int64_t M, int32_t per_member_manning) {
   if (!ctx || M <= 0) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "ensembles need the fused path"; return HG_ERR_ARG; }
+  TRY(no_closure(ctx, "hg_ensemble_alloc"));
   if ((int64_t)ctx->fh.n_tiles * M >= ((int64_t)1 << 31)) { ctx->err = "too many members for one launch"; return HG_ERR_ARG; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   hg::FusedDev& d = ctx->fd;
@@ -725,6 +763,7 @@ int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params, int64_
                      const double* lambda_T, double* Q_T, double* Q0bar, double* pbar) {
   if (!ctx || !Q0 || !lambda_T || !Q0bar || nsteps < 1 || !(dt > 0.0)) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "hg_euler_adjoint needs the fused path"; return HG_ERR_ARG; }
+  TRY(no_closure(ctx, "hg_euler_adjoint"));
   if (ctx->n_halo > 0) { ctx->err = "hg_euler_adjoint: multi-rank contexts are not supported"; return HG_ERR_ARG; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
@@ -800,6 +839,7 @@ int hg_time_rhs(hg_ctx* ctx, int32_t n, int32_t fused_euler, double dt, float* m
 int hg_time_vjp(hg_ctx* ctx, int32_t n, float* ms) {
   if (!ctx || !ms || n <= 0) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "hg_time_vjp needs the fused path"; return HG_ERR_ARG; }
+  TRY(no_closure(ctx, "hg_time_vjp"));
   if (!ctx->state_set) { ctx->err = "hg_time_vjp: no resident state"; return HG_ERR_STATE; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   hg::FusedDev& d = ctx->fd;

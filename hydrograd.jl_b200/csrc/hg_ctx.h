@@ -51,6 +51,41 @@ struct Consts {
   double g, k_n, h_small;
 };
 
+// state-dependent Manning's n (hg_set_manning_function); type 0 = off
+struct MannFn {
+  int32_t type = 0;
+  double n_lower = 0.0, n_upper = 0.0, k = 0.0, h_mid = 0.0;
+};
+#ifdef __CUDACC__
+// closures of parameters/process_ManningN_2D.jl:140-213, same operation order (x^9 by squaring as Julia's ^ Int)
+// (products feeding a sum are rounded separately, __dmul_rn: the closures are ill-conditioned near the ends of their validity
+// range and an FMA-contracted ulp would show up amplified)
+__device__ __forceinline__ double manning_closure(const MannFn& m, double h, double umag, double ks) {
+  const double span = m.n_upper - m.n_lower;
+  if (m.type == HG_MANNING_POWER_LAW) return m.n_lower + __dmul_rn(span, pow(h + 2.220446049250313e-16, -m.k));
+  if (m.type == HG_MANNING_SIGMOID) return m.n_lower + span / (1.0 + exp(m.k * (h - m.h_mid)));
+  if (m.type == HG_MANNING_INVERSE) return m.n_lower + span / (1.0 + __dmul_rn(m.k, h));
+  const double Re = __dmul_rn(umag, h) / 1.0e-6;
+  const double h_ks = h / ks;
+  const double x = Re / 850.0, x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+  const double alpha = 1.0 / (1.0 + __dmul_rn(x8, x));
+  const double r2 = Re / (h_ks * 160.0);
+  const double beta = 1.0 / (1.0 + __dmul_rn(r2, r2));
+  const double part1 = pow(Re / 24.0, alpha);
+  const double part2 = pow(1.8 * log10(Re / 2.1), 2.0 * (1.0 - alpha) * beta);
+  const double part3 = pow(2.0 * log10(11.8 * h_ks), 2.0 * (1.0 - alpha) * (1.0 - beta));
+  const double f = 1.0 / (part1 * part2 * part3);
+  return sqrt(f / 8.0) * pow(h, 1.0 / 6.0) / sqrt(9.81);
+}
+// n of one cell from its raw state (clamp of semi_discretize_swe_2D.jl:101-106, u = q/h, |U| = sqrt(u^2+v^2) :143-146)
+__device__ __forceinline__ double manning_of_state(const MannFn& m, double xi, double qx, double qy, double hst, double ks, double hs) {
+  const double h0 = xi + hst;
+  const bool dry = h0 <= hs;
+  const double h = dry ? hs : h0, u = dry ? 0.0 : qx / h, v = dry ? 0.0 : qy / h;
+  return manning_closure(m, h, sqrt(__dadd_rn(__dmul_rn(u, u), __dmul_rn(v, v))), ks);
+}
+#endif
+
 // Boundary entries, one per boundary face, in the reference's processing order
 // (inlet-q boundaries, exit-h, wall, symm; bc_2D.jl:279-295).  Cell ids are in REFERENCE order
 // for the plain path and in INTERNAL order for the fused path (two copies of `cell`).
@@ -73,6 +108,7 @@ struct PlainDev {
   DBuf<int32_t> bc_type, bc_group, bc_ghost, bc_cell;  // [B] entry order
   DBuf<double> bc_nx, bc_ny, bc_l53, bc_l23;
   DBuf<int32_t> inlet_ptr;
+  DBuf<double> ks;                    // [N] roughness height (variable Manning's n)
   DBuf<double> hstill_g, zb_g;        // [B] GHOST order (as passed in)
   DBuf<double> gh, gqx, gqy, gxi;     // [B] ghost states, ghost order
   DBuf<double> Qin, wse;              // [n_inletq], [n_exith]
@@ -120,6 +156,7 @@ struct FusedDev {
   DBuf<uint16_t> cf_idx;
   DBuf<double> face_nx, face_ny, face_len;
   DBuf<double> area, hstill, zb, S0x, S0y, mann;  // [Ns] internal order
+  DBuf<double> ks;                                // [Ns] roughness height (variable Manning's n)
   DBuf<int32_t> matid;
   DBuf<int32_t> bc_type, bc_group, bc_cell;        // [B] entry order, internal cell ids
   DBuf<double> bc_nx, bc_ny, bc_l53, bc_l23, bc_hstill, bc_zb;
@@ -155,6 +192,7 @@ struct hg_ctx {
   bool ens_per_member_mann = false;
   bool lam_set = false;
   hg::Consts c{};
+  hg::MannFn mfn{};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;

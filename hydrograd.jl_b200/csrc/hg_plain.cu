@@ -74,7 +74,8 @@ struct PlainArgs {
   Consts c;
   const int32_t *cf_ptr, *cf_nb;
   const double *cf_nx, *cf_ny, *cf_len;
-  const double *area, *hstill, *zb, *S0x, *S0y, *mann;
+  const double *area, *hstill, *zb, *S0x, *S0y, *mann, *ks;
+  MannFn mfn;
   const int32_t* matid;
   const int32_t *bc_type, *bc_group, *bc_ghost, *bc_cell, *inlet_ptr;
   const double *bc_nx, *bc_ny, *bc_l53, *bc_l23, *hstill_g, *zb_g;
@@ -93,6 +94,8 @@ __device__ __forceinline__ void load_cell(const PlainArgs& a, int32_t i, double&
   qy = dry ? 0.0 : a.Q[2 * a.N + i];
 }
 __device__ __forceinline__ double mann_of(const PlainArgs& a, int32_t i) {
+  if (a.mfn.type)   // variable Manning's n of forward simulations (semi_discretize_swe_2D.jl:140-149)
+    return manning_of_state(a.mfn, a.Q[i], a.Q[a.N + i], a.Q[2 * (int64_t)a.N + i], a.hstill[i], a.ks[i], a.c.h_small);
   return a.active == HG_PARAM_MANNING ? a.params[a.matid[i]] : a.mann[i];
 }
 __device__ __forceinline__ double zb_of(const PlainArgs& a, int32_t i) {
@@ -201,6 +204,7 @@ int plain_rhs(hg_ctx* ctx, const double* d_Q, double* d_out) {
   a.c = ctx->c;
   a.cf_ptr = p.cf_ptr.p; a.cf_nb = p.cf_nb.p; a.cf_nx = p.cf_nx.p; a.cf_ny = p.cf_ny.p; a.cf_len = p.cf_len.p;
   a.area = p.area.p; a.hstill = p.hstill.p; a.zb = p.zb.p; a.S0x = p.S0x.p; a.S0y = p.S0y.p; a.mann = p.mann.p;
+  a.ks = p.ks.p; a.mfn = ctx->mfn;
   a.matid = p.matid.p;
   a.bc_type = p.bc_type.p; a.bc_group = p.bc_group.p; a.bc_ghost = p.bc_ghost.p; a.bc_cell = p.bc_cell.p;
   a.inlet_ptr = p.inlet_ptr.p;

@@ -167,6 +167,21 @@ function ChainRulesCore.rrule(::typeof(swe_2d_rhs), Q::Vector{Float64}, p::Vecto
 end
 
 "custom_ODE_solve (ode_solvers/custom_ODE_solvers.jl:36-95) on the device; returns the 3N x nSaves matrix."
+# forward_settings.ManningN_option == "variable" (semi_discretize_swe_2D.jl:140-149): select the closure once; every
+# following RHS / Euler step evaluates n(h) / n(h, |U|, ks) on the device.  kind = ManningN_function_type of the control file.
+const MANNING_TYPES = Dict("constant" => 0, "power_law" => 1, "sigmoid" => 2, "inverse" => 3, "h_Umag_ks" => 4)
+function set_manning_function(ctx::Context, kind::String, params::Dict, ks_cells::Union{Vector{Float64},Nothing}=nothing)
+    haskey(MANNING_TYPES, kind) || error("Unknown Manning's n function type: $kind. Supported types: constant, power_law, sigmoid, inverse.")
+    p = Float64[get(params, "n_lower", 0.0), get(params, "n_upper", 0.0), get(params, "k", 0.0), get(params, "h_mid", 0.0)]
+    ks = ks_cells === nothing ? Ptr{Float64}(C_NULL) : pointer(ks_cells)
+    GC.@preserve p ks_cells begin
+        rc = ccall((:hg_set_manning_function, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}),
+                   ctx.handle, Int32(MANNING_TYPES[kind]), p, ks)
+        rc == 0 || error(unsafe_string(ccall((:hg_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.handle)))
+    end
+    return nothing
+end
+
 function custom_ODE_solve(Q0::Vector{Float64}, params_vector::Vector{Float64}, tspan::Tuple{Float64,Float64}, dt::Float64, ctx::Context)
     nsave = length(tspan[1]:dt:tspan[2])
     sol = Matrix{Float64}(undef, 3 * ctx.N, nsave)

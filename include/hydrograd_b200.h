@@ -135,6 +135,16 @@ typedef struct {
                                       reserved[4]: 1 = do not regroup a tile's faces into bank-conflict-free blocks of 16 */
 } hg_options;
 
+/* Manning's n as a function of the state, the reference's forward-simulation option ManningN_option = "variable"
+ * (semi_discretize_swe_2D.jl:140-149; closures of parameters/process_ManningN_2D.jl:119-213). */
+enum hg_manning_function {
+  HG_MANNING_CONSTANT = 0,   /* ManningN_cells as bound (default)                                                  */
+  HG_MANNING_POWER_LAW = 1,  /* n = n_lower + (n_upper - n_lower) (h + eps)^(-k)                                    */
+  HG_MANNING_SIGMOID = 2,    /* n = n_lower + (n_upper - n_lower) / (1 + exp(k (h - h_mid)))                        */
+  HG_MANNING_INVERSE = 3,    /* n = n_lower + (n_upper - n_lower) / (1 + k h)                                       */
+  HG_MANNING_H_UMAG_KS = 4   /* Cheng (2008) friction factor f(Re, h/ks) -> n = sqrt(f/8) h^(1/6) / sqrt(9.81)      */
+};
+
 /* fills *opt with the defaults */
 HG_API void hg_default_options(hg_options* opt);
 
@@ -153,6 +163,12 @@ HG_API int64_t hg_n_cells(const hg_ctx* ctx);
 HG_API int hg_set_fields(hg_ctx* ctx, const double* ManningN_cells, const double* zb_cells,
                   const double* zb_ghost, const double* S0_cells, const double* inletQ_TotalQ,
                   const double* exitH_WSE);
+
+/* Selects the Manning's n closure evaluated inside every RHS from the clamped (h, q) of each cell; params = {n_lower,
+ * n_upper, k, h_mid}; ks_cells[N] (reference order) is the roughness height per cell, needed by HG_MANNING_H_UMAG_KS
+ * (ks per material zone gathered through matID, process_ManningN_2D.jl:56-60).  Forward simulation only, like the
+ * reference: the VJP / adjoint / ensemble entry points and active = HG_PARAM_MANNING return HG_ERR_ARG while a closure is set. */
+HG_API int hg_set_manning_function(hg_ctx* ctx, int32_t type, const double* params, const double* ks_cells);
 
 /* dQdt = swe_2d_rhs(Q, params, t)   -- host buffers, reference cell order.
  * semi_discretize_swe_2D.jl:18-277.  `t` is accepted and unused exactly like the reference.      */

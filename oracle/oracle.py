@@ -132,6 +132,26 @@ class Oracle:
             raise RuntimeError(f"oracle_rhs_vjp_bruteforce failed with code {rc}")
         return Qbar, pbar[:npar]
 
+    MANNING_TYPES = {"constant": 0, "power_law": 1, "sigmoid": 2, "inverse": 3, "h_Umag_ks": 4}
+
+    def set_manning_function(self, kind="constant", n_lower=0.0, n_upper=0.0, k=0.0, h_mid=0.0, ks_cells=None):
+        """Variable Manning's n of forward simulations (semi_discretize_swe_2D.jl:140-149) for the following calls."""
+        p = np.array([n_lower, n_upper, k, h_mid], dtype=np.float64)
+        ks = None if ks_cells is None else np.ascontiguousarray(ks_cells, dtype=np.float64)
+        rc = self.lib.oracle_set_manning_function(C.c_int(self.MANNING_TYPES[kind]), _p(p, c_f64p), _p(ks, c_f64p), C.c_int64(self.N))
+        if rc:
+            raise RuntimeError(f"oracle_set_manning_function failed with code {rc}")
+
+    def manning_closure(self, kind, h, Umag=None, ks=None, n_lower=0.0, n_upper=0.0, k=0.0, h_mid=0.0):
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        U = None if Umag is None else np.ascontiguousarray(Umag, dtype=np.float64)
+        K = None if ks is None else np.ascontiguousarray(ks, dtype=np.float64)
+        p = np.array([n_lower, n_upper, k, h_mid], dtype=np.float64)
+        out = [np.zeros(h.size) for _ in range(4)]
+        self.lib.oracle_manning_closure(C.c_int(self.MANNING_TYPES[kind]), _p(p, c_f64p), C.c_int64(h.size), _p(h, c_f64p),
+                                        _p(U, c_f64p), _p(K, c_f64p), *[_p(o, c_f64p) for o in out])
+        return dict(zip(("n", "h_ks", "f", "Re"), out))
+
     def euler(self, Q, dt, nsteps, params=None, active=0, nthreads=1):
         Q = np.array(Q, dtype=np.float64, copy=True)
         p, npar = self._params(params)

@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -173,6 +174,47 @@ struct Work {
 };
 
 // swe_2d_rhs (semi_discretize_swe_2D.jl:18-277)
+// ---- state-dependent Manning's n for forward simulations ("variable" ManningN_option), semi_discretize_swe_2D.jl:140-149;
+// closures restated from parameters/process_ManningN_2D.jl:119-213.  Test-only global (set by oracle_set_manning_function).
+struct MannFn {
+  int type = 0;                 // 0 constant, 1 power_law, 2 sigmoid, 3 inverse, 4 h_Umag_ks
+  double n_lower = 0, n_upper = 0, k = 0, h_mid = 0;
+  std::vector<double> ks;       // [N] (type 4)
+};
+MannFn g_mfn;
+
+inline double ipow9(double x) {  // Julia's x^9 (power_by_squaring): x^8 * x with x^8 by three squarings
+  const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+  return x8 * x;
+}
+// returns n; optional outputs h/ks, friction factor f, Reynolds number (process_ManningN_2D.jl:181-213)
+inline double manning_closure(const MannFn& m, double h, double Umag, double ks, double* h_ks_out = nullptr,
+                              double* f_out = nullptr, double* Re_out = nullptr) {
+  const double eps = 2.220446049250313e-16;
+  switch (m.type) {
+    case 1: return m.n_lower + (m.n_upper - m.n_lower) * std::pow(h + eps, -m.k);              // :156-168
+    case 2: return m.n_lower + (m.n_upper - m.n_lower) / (1.0 + std::exp(m.k * (h - m.h_mid)));   // :173-186
+    case 3: return m.n_lower + (m.n_upper - m.n_lower) / (1.0 + m.k * h);                       // :140-152
+    case 4: {
+      const double nu = 1.0e-6;
+      const double Re = Umag * h / nu;
+      const double h_ks = h / ks;
+      const double alpha = 1.0 / (1.0 + ipow9(Re / 850.0));
+      const double r2 = Re / (h_ks * 160.0);
+      const double beta = 1.0 / (1.0 + r2 * r2);
+      const double part1 = std::pow(Re / 24.0, alpha);
+      const double part2 = std::pow(1.8 * std::log10(Re / 2.1), 2.0 * (1.0 - alpha) * beta);
+      const double part3 = std::pow(2.0 * std::log10(11.8 * h_ks), 2.0 * (1.0 - alpha) * (1.0 - beta));
+      const double f = 1.0 / (part1 * part2 * part3);
+      if (h_ks_out) *h_ks_out = h_ks;
+      if (f_out) *f_out = f;
+      if (Re_out) *Re_out = Re;
+      return std::sqrt(f / 8.0) * std::pow(h, 1.0 / 6.0) / std::sqrt(9.81);
+    }
+  }
+  return 0.0;
+}
+
 template <class T>
 int rhs_impl(const View& v, const T* Q, const T* params, int64_t np, int active, T* dQ, int nthreads,
              T* ghost_out /* optional [4B]: h, qx, qy, xi in ghost order */) {
@@ -205,6 +247,14 @@ int rhs_impl(const View& v, const T* Q, const T* params, int64_t np, int active,
     for (int64_t i = 0; i < N; ++i) w.n[i] = params[v.f.matID_cells[i]];  // process_ManningN_2D.jl:88
   } else {
     for (int64_t i = 0; i < N; ++i) w.n[i] = T(v.f.ManningN_cells[i]);
+  }
+  if (g_mfn.type != 0) {   // forward simulation with a variable Manning's n (:140-149): n from the clamped h, q
+    if (!std::is_same<T, double>::value || active == HG_PARAM_MANNING) return HG_ERR_ARG;
+    if (g_mfn.type == 4 && (int64_t)g_mfn.ks.size() != N) return HG_ERR_ARG;
+    for (int64_t i = 0; i < N; ++i) {
+      const double h = val(w.h[i]), u = val(w.qx[i]) / h, vv = val(w.qy[i]) / h;
+      w.n[i] = T(manning_closure(g_mfn, h, std::sqrt(u * u + vv * vv), g_mfn.type == 4 ? g_mfn.ks[i] : 0.0));
+    }
   }
   if (active == HG_PARAM_Q) {
     if (np != nI) return HG_ERR_ARG;
@@ -324,6 +374,24 @@ int oracle_rhs(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc*
                const double* params, int64_t np, int active, double* dQ, int nthreads, double* ghost_out) {
   View v(*m, *b, *f);
   return rhs_impl<double>(v, Q, params, np, active, dQ, nthreads, ghost_out);
+}
+
+// variable Manning's n for the following oracle_rhs / oracle_euler calls (type 0 switches it off); params = n_lower, n_upper, k, h_mid
+int oracle_set_manning_function(int type, const double* params, const double* ks, int64_t n) {
+  g_mfn = MannFn();
+  g_mfn.type = type;
+  if (type != 0 && params) { g_mfn.n_lower = params[0]; g_mfn.n_upper = params[1]; g_mfn.k = params[2]; g_mfn.h_mid = params[3]; }
+  if (type == 4) { if (!ks) return HG_ERR_ARG; g_mfn.ks.assign(ks, ks + n); }
+  return HG_OK;
+}
+// the closure itself on arrays (golden check against ManningN_cells_truth / Re / h_ks / friction factor)
+void oracle_manning_closure(int type, const double* params, int64_t n, const double* h, const double* Umag, const double* ks,
+                            double* n_out, double* h_ks, double* f, double* Re) {
+  MannFn m;
+  m.type = type;
+  if (params) { m.n_lower = params[0]; m.n_upper = params[1]; m.k = params[2]; m.h_mid = params[3]; }
+  for (int64_t i = 0; i < n; ++i)
+    n_out[i] = manning_closure(m, h[i], Umag ? Umag[i] : 0.0, ks ? ks[i] : 0.0, h_ks ? h_ks + i : nullptr, f ? f + i : nullptr, Re ? Re + i : nullptr);
 }
 
 // Directional derivative: jvp = d rhs/dQ . vQ + d rhs/dp . vP   (ForwardDiff semantics)

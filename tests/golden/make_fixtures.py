@@ -28,7 +28,27 @@ CASES = {
 }
 
 
+# forward simulations with a state-dependent Manning's n (semi_discretize_swe_2D.jl:140-149): only the truth arrays and the
+# closure parameters are needed (savannah_ks runs on the savannah mesh files, byte-identical in the reference)
+VARIABLE_N = {
+    "savannah_ks": "forward_simulation/Savannah_River_ManningN_ks_h_Umag",
+    "oneD_bump_nh": "forward_simulation/oneD_channel_with_bump_ManningN_h",
+}
+
+
+def variable_n():
+    for name, rel in VARIABLE_N.items():
+        src = os.path.join(REF, rel)
+        dst = os.path.join(HERE, name)
+        os.makedirs(dst, exist_ok=True)
+        shutil.copyfile(os.path.join(src, "run_control.json"), os.path.join(dst, "run_control.json"))
+        os.chmod(os.path.join(dst, "run_control.json"), 0o644)
+        d = json.load(open(os.path.join(src, "forward_simulation_solution_truth.json")))
+        np.savez_compressed(os.path.join(dst, "truth.npz"), **{k: np.array(v, dtype=np.float64) for k, v in d.items()})
+
+
 def main():
+    variable_n()
     for name, (rel, stem) in CASES.items():
         src = os.path.join(REF, rel)
         dst = os.path.join(HERE, name)

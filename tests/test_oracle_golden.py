@@ -1,4 +1,6 @@
 """CPU tests: pin the oracle against every fixture the reference commits for this path."""
+import os
+
 import numpy as np
 import pytest
 
@@ -112,3 +114,50 @@ def test_sensitivity_fixture_pins_the_derivative(oracle_lib):
     assert np.abs(S[:, 0]).max() == 0.0
     for k in (1, 2):
         assert np.abs(dQ[k] - S[:, k]).max() <= 1e-4 * np.abs(S[:, k]).max()
+
+
+# ---------------------------------------------------------------- variable Manning's n (forward simulation option)
+def _closure_inputs(t, h_small=1e-3):
+    """The reference post-processes with u = q/(h + h_small) (process_forward_simulation_results_2D.jl:32-38)."""
+    return t["h_truth"], np.sqrt(t["u_truth"] ** 2 + t["v_truth"] ** 2)
+
+
+def test_manning_closure_h_Umag_ks_matches_reference_truth():
+    """Cheng (2008) n(h, |U|, ks) (process_ManningN_2D.jl:181-213) against ManningN_cells_truth, Re_cells_truth,
+    h_ks_cells_truth and friction_factor_cells_truth of Savannah_River_ManningN_ks_h_Umag."""
+    import json
+    d = os.path.join(cases.GOLD, "savannah_ks")
+    t = np.load(os.path.join(d, "truth.npz"))
+    rc = json.load(open(os.path.join(d, "run_control.json")))
+    ks_zone = np.array(rc["forward_simulation_options"]["forward_simulation_ManningN_function_parameters"]["ks"])
+    c = cases.load("savannah")                     # same mesh files (byte-identical in the reference)
+    ks_cells = ks_zone[c.matID]                    # process_SRH_2D_input.jl:159-164, process_ManningN_2D.jl:56-60
+    h, U = _closure_inputs(t)
+    o = Oracle(R.flatten(c))
+    got = o.manning_closure("h_Umag_ks", h, U, ks_cells)
+    moving = U > 0                                 # still cells: Re = 0 -> f = Inf -> NaN, written as 0 by replace_nan
+    for key, ref in (("n", "ManningN_cells_truth"), ("Re", "Re_cells_truth"), ("h_ks", "h_ks_cells_truth"), ("f", "friction_factor_cells_truth")):
+        a, b = got[key][moving], t[ref][moving]
+        ok = np.isfinite(a) & np.isfinite(b) & (b != 0)
+        assert ok.sum() > 1000
+        assert np.abs(a[ok] / b[ok] - 1).max() <= 1e-12, key
+
+
+def test_manning_closure_sigmoid_matches_reference_truth():
+    """sigmoid n(h) (process_ManningN_2D.jl:173-186) against ManningN_cells_truth of oneD_channel_with_bump_ManningN_h."""
+    import json
+    d = os.path.join(cases.GOLD, "oneD_bump_nh")
+    t = np.load(os.path.join(d, "truth.npz"))
+    p = json.load(open(os.path.join(d, "run_control.json")))["forward_simulation_options"]["forward_simulation_ManningN_function_parameters"]
+    o = Oracle(R.flatten(cases.load("oneD_bump")))
+    got = o.manning_closure("sigmoid", t["h_truth"], n_lower=p["n_lower"], n_upper=p["n_upper"], k=p["k"], h_mid=p["h_mid"])["n"]
+    assert np.abs(got / t["ManningN_cells_truth"] - 1).max() <= 1e-14
+
+
+def test_manning_closures_power_law_and_inverse_formulas():
+    """n_lower + (n_upper - n_lower) (h + eps)^-k and n_lower + (n_upper - n_lower)/(1 + k h) (:140-168): restated directly."""
+    o = Oracle(R.flatten(cases.load("simple")))
+    h = np.exp(np.random.default_rng(0).uniform(np.log(1e-3), np.log(10), 500))
+    nl, nu, k = 0.02, 0.08, 0.7
+    assert np.allclose(o.manning_closure("power_law", h, n_lower=nl, n_upper=nu, k=k)["n"], nl + (nu - nl) * (h + np.finfo(float).eps) ** (-k), rtol=1e-15)
+    assert np.allclose(o.manning_closure("inverse", h, n_lower=nl, n_upper=nu, k=k)["n"], nl + (nu - nl) / (1 + k * h), rtol=1e-15)
