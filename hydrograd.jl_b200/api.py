@@ -196,8 +196,8 @@ class Context:
     def set_lambda(self, lam):
         self._ck(self.lib.hg_set_lambda(self._h, _p(_f64(lam))))
 
-    def vjp_resident(self):
-        self._ck(self.lib.hg_vjp_resident(self._h))
+    def vjp_resident(self, phase=0):
+        self._ck(self.lib.hg_vjp_resident_phase(self._h, phase) if phase else self.lib.hg_vjp_resident(self._h))
 
     def get_vjp(self, n_params=0, want_ncell_bar=False):
         Qbar = np.empty(3 * self.N)
@@ -226,8 +226,9 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.lib.hg_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
-    def rhs_resident(self):
-        self._ck(self.lib.hg_rhs_resident(self._h))
+    def rhs_resident(self, phase=0):
+        """phase 1 / 2: tiles without / with halo faces (multi-GPU overlap, hg_rhs_resident_phase)."""
+        self._ck(self.lib.hg_rhs_resident_phase(self._h, phase) if phase else self.lib.hg_rhs_resident(self._h))
 
     def get_rhs(self, out=None):
         out = np.empty(3 * self.N) if out is None else out

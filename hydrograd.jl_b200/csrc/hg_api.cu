@@ -276,6 +276,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(al(ctx, d.Q, 3 * Ns)); TRY(al(ctx, d.Q2, 3 * Ns)); TRY(al(ctx, d.dQ, 3 * Ns)); TRY(al(ctx, d.stage, 3 * N));
     TRY(al(ctx, d.params, npar)); TRY(al(ctx, d.err, 1));
     TRY(up(ctx, d.tile_order, fh.tile_order));
+    TRY(up(ctx, d.band_order, fh.band_order));
     if (fh.n_chunks > 1) {
       TRY(al(ctx, d.stage_out, 3 * N));
       CK(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
@@ -425,6 +426,15 @@ int hg_rhs_resident(hg_ctx* ctx) {
   CK(ctx, cudaSetDevice(ctx->opt.device));
   if (ctx->opt.path == 1) return hg::plain_rhs(ctx, ctx->pd.Q.p, ctx->pd.dQ.p);
   return hg::fused_rhs(ctx, ctx->fd.Q.p, ctx->fd.dQ.p, false, 0.0);
+}
+
+int hg_rhs_resident_phase(hg_ctx* ctx, int32_t phase) {
+  if (!ctx || phase < 0 || phase > 2) return HG_ERR_ARG;
+  if (phase == 0) return hg_rhs_resident(ctx);
+  if (ctx->opt.path == 1) { ctx->err = "hg_rhs_resident_phase needs the fused path"; return HG_ERR_ARG; }
+  if (!ctx->state_set) { ctx->err = "hg_rhs_resident_phase: no resident state"; return HG_ERR_STATE; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  return hg::fused_rhs_phase(ctx, ctx->fd.Q.p, ctx->fd.dQ.p, phase);
 }
 
 int hg_get_rhs(hg_ctx* ctx, double* dQ) {
@@ -581,6 +591,24 @@ int hg_vjp_resident(hg_ctx* ctx) {
   TRY(no_closure(ctx, "hg_vjp_resident"));
   CK(ctx, cudaSetDevice(ctx->opt.device));
   return hg::fused_vjp(ctx, hg::fused_cfg_id(ctx), ctx->fd.Q.p, ctx->fd.lam.p, ctx->fd.Qbar.p);
+}
+
+int hg_vjp_resident_phase(hg_ctx* ctx, int32_t phase) {
+  if (!ctx || phase < 0 || phase > 2) return HG_ERR_ARG;
+  if (phase == 0) return hg_vjp_resident(ctx);
+  if (ctx->opt.path == 1) { ctx->err = "hg_vjp_resident_phase needs the fused path"; return HG_ERR_ARG; }
+  if (!ctx->state_set || !ctx->lam_set) { ctx->err = "hg_vjp_resident_phase: state or lambda not set"; return HG_ERR_STATE; }
+  TRY(no_closure(ctx, "hg_vjp_resident_phase"));
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  const hg::FusedHost& fh = ctx->fh;
+  const int cfg = hg::fused_cfg_id(ctx);
+  if (phase == 1) {
+    if (ctx->n_inletq > 0) hg::fused_inlet_coef(ctx, d.Q.p);
+    return hg::fused_vjp_tiles(ctx, cfg, d.Q.p, d.lam.p, d.Qbar.p, d.band_order.p, 0, fh.n_interior_tiles);
+  }
+  TRY(hg::fused_vjp_tiles(ctx, cfg, d.Q.p, d.lam.p, d.Qbar.p, d.band_order.p, fh.n_interior_tiles, fh.n_tiles - fh.n_interior_tiles));
+  return hg::fused_vjp_finish(ctx, d.Q.p, d.Qbar.p);
 }
 
 int hg_get_vjp(hg_ctx* ctx, double* Qbar, double* pbar, double* ncell_bar) {

@@ -147,10 +147,13 @@ struct FusedHost {
   std::vector<int32_t> tile_order;   // tiles sorted by the stage at which they become ready
   std::vector<int32_t> stage_ptr;    // [n_chunks+1] ranges of tile_order
   std::vector<int32_t> chunk_done;   // [n_chunks] stage after which every cell of the chunk has been computed
+  // multi-GPU overlap: tiles without halo-boundary faces first (they can run while the halo is in flight), then the band
+  std::vector<int32_t> band_order;   // [n_tiles]
+  int32_t n_interior_tiles = 0;
 };
 
 struct FusedDev {
-  DBuf<int32_t> perm, iperm, tile_desc, halo, bface_e, tile_order;
+  DBuf<int32_t> perm, iperm, tile_desc, halo, bface_e, tile_order, band_order;
   DBuf<double> stage_out, stage_lam;
   DBuf<uint32_t> face_lr;
   DBuf<uint16_t> cf_idx;
@@ -229,6 +232,7 @@ int plain_rhs(hg_ctx* ctx, const double* dQ_in_Q, double* d_out);
 // fused path launchers (hg_fused.cu)
 int fused_rhs(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 int fused_rhs_tiles(hg_ctx* ctx, const double* d_Q, double* d_out, int32_t tile_base, int32_t n_tiles);
+int fused_rhs_phase(hg_ctx* ctx, const double* d_Q, double* d_out, int phase);
 int fused_permute_range(hg_ctx* ctx, bool to_internal, const double* src, double* dst, int64_t r0, int64_t r1);
 int fused_smem_bytes(const hg_ctx* ctx);
 int fused_prepare(hg_ctx* ctx);

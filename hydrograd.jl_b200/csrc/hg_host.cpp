@@ -442,6 +442,20 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     fh.max_halo = std::max(fh.max_halo, nh);
   }
   fh.max_local = (fh.max_local + 1) & ~1;
+  // ---- multi-GPU overlap: a tile belongs to the band if one of its boundary faces is a halo face
+  {
+    std::vector<int32_t> band;
+    fh.band_order.clear();
+    for (int32_t t = 0; t < fh.n_tiles; ++t) {
+      const int32_t* d = &fh.tile_desc[(size_t)t * kTileDesc];
+      bool is_band = false;
+      for (int32_t q = 0; q < d[5] - d[9]; ++q)
+        if (ctx->bch.type[fh.bface_e[d[10] + q]] == BC_HALO) { is_band = true; break; }
+      (is_band ? band : fh.band_order).push_back(t);
+    }
+    fh.n_interior_tiles = (int32_t)fh.band_order.size();
+    fh.band_order.insert(fh.band_order.end(), band.begin(), band.end());
+  }
   // ---- stages of the host-buffer pipeline
   {
     const int32_t K = N >= (1 << 20) ? (int32_t)std::min<int64_t>(32, std::max<int64_t>(8, N >> 19)) : 1;   // ~0.5M cells (12 MB) per chunk

@@ -23,8 +23,8 @@ using namespace dev;
 struct VjpArgs {
   int32_t N, n_tiles, want_s0;
   int32_t prefetch;            // > 0: CTA b pulls the blocks of tile b + prefetch into L2 (see hg_fused.cu, prefetch_work)
-  const int32_t* tile_order;   // host-buffer pipeline: run the tiles tile_order[tile_base ...] (NULL: identity)
-  int32_t tile_base;
+  const int32_t* tile_order;   // run the tiles tile_order[tile_base .. tile_base + n_run) (NULL: identity)
+  int32_t tile_base, n_run;
   int64_t Ns;
   Consts c;
   const int32_t *tile_desc, *halo, *bface_e;
@@ -457,8 +457,9 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     stage_cell(l, xi, qx, qy, hst);
     sm.m0[l] = l0 * rA; sm.m1[l] = l1 * rA; sm.m2[l] = l2 * rA;
   }
-  if (a.prefetch > 0 && !a.tile_order && tid == kThreads - 1 && t + a.prefetch < a.n_tiles) {
-    const int32_t tp = t + a.prefetch;
+  if (a.prefetch > 0 && tid == kThreads - 1 && (int)blockIdx.x + a.prefetch < a.n_run) {
+    const int32_t wp = (int)blockIdx.x + a.prefetch;
+    const int32_t tp = a.tile_order ? __ldg(a.tile_order + a.tile_base + wp) : wp;
     const int4 p0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)tp * kTileDesc));
     const int4 p1 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)tp * kTileDesc) + 1);
     const uint32_t cb = (uint32_t)((p0.y + 1) & ~1) * 8u, fb = (uint32_t)p1.z * 8u;
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     bulk_prefetch_l2(a.face_lr + pf, (uint32_t)p1.z * 4u);
     bulk_prefetch_l2(a.cf_idx + (size_t)tp * (T * NF), (uint32_t)(T * NF) * 2u);
     if (p0.w > 0) bulk_prefetch_l2(a.halo + p0.z, (uint32_t)((p0.w + 3) & ~3) * 4u);
-    if (tp + a.prefetch < a.n_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tile_desc + (size_t)(tp + a.prefetch) * kTileDesc));
+    if (!a.tile_order && wp + a.prefetch < a.n_run) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tile_desc + (size_t)(wp + a.prefetch) * kTileDesc));
   }
   mbar_wait(sm.bar, 0);
 
@@ -841,6 +842,7 @@ int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_
   a.ent_c = d.ent_c.p; a.ent_n = d.ent_n.p; a.ent_z = d.ent_z.p;
   a.tile_order = tile_order; a.tile_base = tile_base;
   const unsigned grid = (unsigned)(n_run >= 0 ? n_run : fh.n_tiles);
+  a.n_run = (int32_t)grid;
   const VjpKernel kk = vjp_kernel(cfg_id, ctx->opt.reserved[2]);
   if (!kk.fn) { ctx->err = "no VJP tile configuration"; return HG_ERR_ARG; }
   {

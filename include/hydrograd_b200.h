@@ -230,6 +230,13 @@ HG_API int hg_set_stream(hg_ctx* ctx, void* cuda_stream);
 /* resident cotangent for hg_vjp_resident / hg_time_vjp */
 HG_API int hg_set_lambda(hg_ctx* ctx, const double* lambda);
 HG_API int hg_vjp_resident(hg_ctx* ctx);
+
+/* Multi-GPU overlap of the halo exchange with the tiles that need no remote cell.  phase 1: everything that does not
+ * touch a halo face (launch it right after hg_halo_pack, while the exchange is in flight on another stream); phase 2: the
+ * band of tiles with halo faces (launch it once the received block is complete); phase 0 = hg_rhs_resident /
+ * hg_vjp_resident.  Phases 1 + 2 together give bitwise the result of phase 0. */
+HG_API int hg_rhs_resident_phase(hg_ctx* ctx, int32_t phase);
+HG_API int hg_vjp_resident_phase(hg_ctx* ctx, int32_t phase);
 HG_API int hg_get_vjp(hg_ctx* ctx, double* Qbar, double* pbar, double* ncell_bar);
 
 /* ---- parameter ensembles (sensitivity / uncertainty runs: BASELINE config "1024 parameter sets"): M independent

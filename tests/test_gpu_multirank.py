@@ -68,10 +68,16 @@ def test_partitioned_rhs_and_vjp_match_single_context_bitwise(hg, case):
     got = np.zeros(3 * N)
     bar = np.zeros(3 * N)
     for c, info in zip(ctxs, infos):
+        # overlap launches first (fresh output buffers): tiles without halo faces, then the band; same bits as one launch
+        c.rhs_resident(1); c.rhs_resident(2)
+        d12 = c.get_rhs()
+        c.vjp_resident(1); c.vjp_resident(2)
+        b12, _ = c.get_vjp()
         c.rhs_resident()
         d = c.get_rhs()
         c.vjp_resident()
         b, _ = c.get_vjp()
+        assert np.array_equal(d12, d) and np.array_equal(b12, b)
         n = info["own"].size
         for k in range(3):
             got[k * N + info["own"]] = d[k * n:(k + 1) * n]
