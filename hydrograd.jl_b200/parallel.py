@@ -15,8 +15,22 @@ from __future__ import annotations
 import numpy as np
 
 
-def rcb_partition(cx, cy, P):
-    """Recursive coordinate bisection: split the longer extent at the weighted median until P parts exist."""
+def inlet_cell_groups(flat):
+    """Internal cells of every inlet-q boundary (0-based ids), one array per inlet: the groups a partition must keep on
+    one rank, because the conveyance-weighted discharge split sums over ALL faces of the inlet (bc_2D.jl:665-691)."""
+    base = int(flat["index_base"])
+    bc_ptr = np.asarray(flat["bc_ptr"], dtype=np.int64)
+    b_ic = np.asarray(flat["bc_internal_cells"], dtype=np.int64) - base
+    return [np.unique(b_ic[bc_ptr[k]:bc_ptr[k + 1]]) for k in range(int(flat["n_inletq"]))]
+
+
+def rcb_partition(cx, cy, P, keep_together=None):
+    """Recursive coordinate bisection: split the longer extent at the weighted median until P parts exist.
+
+    `keep_together`: list of cell-id arrays (e.g. inlet_cell_groups(flat)); after the bisection every group is moved as a
+    whole to the rank that already owns most of it (ties: the lowest rank).  An inlet is a few hundred cells, so the load
+    balance is unaffected, and because the per-rank results do not depend on the partition (redundant cut faces, canonical
+    orientation) neither are the bits.  This is how split inlet-q boundaries are avoided instead of all-reduced."""
     N = cx.size
     part = np.zeros(N, dtype=np.int32)
 
@@ -33,6 +47,10 @@ def rcb_partition(cx, cy, P):
         rec(idx[order[k:]], p0 + pl, p - pl)
 
     rec(np.arange(N), 0, P)
+    for g in keep_together or []:
+        g = np.asarray(g, dtype=np.int64)
+        if g.size:
+            part[g] = np.bincount(part[g], minlength=P).argmax()
     return part
 
 
@@ -84,8 +102,8 @@ def extract_local(flat, part, rank, Q=None, gid=None):
             m = g2l[b_ic[sl]] >= 0
             if m.any():
                 if t == 0 and not m.all():
-                    raise NotImplementedError("an inlet-q boundary is split across ranks: its conveyance sum needs an "
-                                              "all-reduce, which this build does not do")
+                    raise NotImplementedError("an inlet-q boundary is split across ranks: its conveyance sum runs over all of its "
+                                              "faces -- partition with rcb_partition(..., keep_together=inlet_cell_groups(flat))")
                 new_counts[t] += 1
                 e_gh.append(b_gh[sl][m]); e_ic.append(g2l[b_ic[sl][m]]); e_n.append(b_n[sl][m]); e_len.append(b_len[sl][m])
                 ptr.append(ptr[-1] + int(m.sum()))

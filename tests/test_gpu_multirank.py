@@ -37,7 +37,7 @@ def _route(ctxs, infos, with_lambda):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("case", ["dam_rcb4", "river_slab3", "dam_thin_rcb3"])
+@pytest.mark.parametrize("case", ["dam_rcb4", "river_slab3", "dam_thin_rcb3", "river_rcb4_inlet"])
 def test_partitioned_rhs_and_vjp_match_single_context_bitwise(hg, case):
     from hydrograd_jl_b200 import parallel as P
     from hydrograd_jl_b200 import synthetic as S
@@ -45,15 +45,22 @@ def test_partitioned_rhs_and_vjp_match_single_context_bitwise(hg, case):
         flat, Q0 = S.dam_break(40); Pn = 4
     elif case == "dam_thin_rcb3":
         flat, Q0 = S.dam_break(36, thin_film=True); Pn = 3
+    elif case == "river_rcb4_inlet":
+        flat, Q0 = S.river(60, 48); Pn = 4      # RCB cuts through the inlet node-string: its cells are kept on one rank
     else:
         flat, Q0 = S.river(90, 24); Pn = 3
     N = flat["n_cells"]
-    if case.startswith("river"):
+    if case == "river_slab3":
         part = (np.arange(N) * Pn // N).astype(np.int32)
+    elif case == "river_rcb4_inlet":
+        cx, cy = flat["cell_centroids"][:N], flat["cell_centroids"][N:]
+        groups = P.inlet_cell_groups(flat)
+        assert len(np.unique(P.rcb_partition(cx, cy, Pn)[groups[0]])) > 1, "plain RCB must split the inlet in this case"
+        part = P.rcb_partition(cx, cy, Pn, keep_together=groups)
     else:
         part = P.rcb_partition(flat["cell_centroids"][:N], flat["cell_centroids"][N:], Pn)
     rng = np.random.default_rng(2)
-    Q = cases.random_state_flat(flat, 7, dry_frac=0.05) if case != "river_slab3" else Q0
+    Q = cases.random_state_flat(flat, 7, dry_frac=0.05) if not case.startswith("river") else Q0
     lam = rng.standard_normal(3 * N)
     single = hg.Context(flat, tile_cells=128)
     ref = single.rhs(Q)

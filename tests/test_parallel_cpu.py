@@ -122,3 +122,40 @@ def test_halo_exchange_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
+
+
+def test_partition_keeps_inlets_whole():
+    """An RCB cut along the stream splits the river's inlet node-string between ranks; with keep_together the inlet's
+    cells move to one rank as a whole (the conveyance sum of bc_2D.jl:665-691 runs over all of its faces), every rank's
+    local mesh builds, exactly one rank holds the inlet, and the balance stays within the size of the inlet."""
+    flat, Q0 = S.river(40, 48)
+    N = flat["n_cells"]
+    cx, cy = flat["cell_centroids"][:N], flat["cell_centroids"][N:]
+    groups = P.inlet_cell_groups(flat)
+    assert len(groups) == 1 and groups[0].size >= 40
+    # cut the domain ACROSS the inlet: sort by the cross-stream coordinate of the inlet cells' neighbourhood
+    g = groups[0]
+    d = np.stack([cx[g] - cx[g].mean(), cy[g] - cy[g].mean()])
+    axis = np.linalg.svd(d, full_matrices=False)[0][:, 0]      # direction along the inlet node-string
+    key = (cx - cx[g].mean()) * axis[0] + (cy - cy[g].mean()) * axis[1]
+    part = (key > np.median(key)).astype(np.int32)
+    assert len(np.unique(part[g])) == 2, "the test partition must split the inlet"
+    with pytest.raises(NotImplementedError):
+        for r in range(2):
+            P.extract_local(flat, part, r, Q0)
+    fixed = part.copy()
+    for grp in groups:
+        fixed[grp] = np.bincount(fixed[grp], minlength=2).argmax()
+    n_in = 0
+    for r in range(2):
+        loc, info = P.extract_local(flat, fixed, r, Q0)
+        n_in += loc["n_inletq"]
+        assert hg.plan_stats(loc, tile_cells=128)["n_tiles"] >= 1
+    assert n_in == 1
+    # the same fix-up inside rcb_partition
+    for Pn in (2, 4, 8):
+        pr = P.rcb_partition(cx, cy, Pn, keep_together=groups)
+        assert len(np.unique(pr[g])) == 1
+        cnt = np.bincount(pr, minlength=Pn)
+        assert cnt.max() - cnt.min() <= 2 + g.size
+        assert sum(P.extract_local(flat, pr, r, Q0)[0]["n_inletq"] for r in range(Pn)) == 1
