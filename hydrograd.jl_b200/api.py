@@ -330,6 +330,10 @@ class SWE2D_Extra_Parameters:
     bInPlaceODE: bool = False
     swe_2D_constants: swe_2D_consts = field(default_factory=swe_2D_consts)
     options: dict = field(default_factory=dict)
+    # "forward_simulation_options" of the reference's run_control.json (ManningN_option / function_type / function_parameters,
+    # forward_simulation settings of process_control_file): a "variable" Manning's n selects the device closure, with
+    # ks_cells gathered per material zone exactly like process_SRH_2D_input.jl:159-164 / process_ManningN_2D.jl:56-60
+    forward_settings: dict = field(default_factory=dict)
     _ctx: Optional[Context] = None
 
     @property
@@ -339,6 +343,15 @@ class SWE2D_Extra_Parameters:
             c = self.swe_2D_constants
             f.update(g=c.g, k_n=c.k_n, h_small=c.h_small, riemann_solver=c.RiemannSolver)
             self._ctx = Context(f, **self.options)
+            fs = {k.replace("forward_simulation_", ""): v for k, v in self.forward_settings.items()}
+            if fs.get("ManningN_option", "constant") == "variable":
+                kind = fs["ManningN_function_type"]
+                prm = dict(fs.get("ManningN_function_parameters", {}))
+                ks_cells = None
+                if "ks" in prm:
+                    base = 0
+                    ks_cells = np.asarray(prm.pop("ks"), dtype=np.float64)[np.asarray(f["matID_cells"], dtype=np.int64) - base]
+                self._ctx.set_manning_function(kind, ks_cells=ks_cells, **{k: float(v) for k, v in prm.items()})
         return self._ctx
 
 

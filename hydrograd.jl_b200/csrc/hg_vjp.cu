@@ -3,15 +3,18 @@
 // debug_AD.jl:60,75:  back(lambda) -> (Qbar, pbar)).
 //
 // Same tile structure and TMA staging as hg_fused.cu; forward intermediates are RECOMPUTED, not stored:
-//   phase 1  cells + halo -> shared memory: clamped state, derived values, mu = lambda / area;
+//   phase 1  cells + halo -> shared memory: clamped state, derived values (u, v, s = sqrt(h+eps)), the factors of the
+//            derived map's transpose (s/h, 1/(2s), dP/dxi) and mu = lambda / area;
 //   phase 2  every face once: Fbar = len * (mu_R - mu_L); reverse-mode sweep through Riemann_2D_Roe
 //            (swe_2D_solvers.jl:4-164; branch predicates, clamps and wet flags are constants exactly as in
-//            Zygote / ForwardDiff) -> adjoints of (xi, h, u, v, s, P) on both sides, parked in shared memory;
-//            boundary faces additionally pull the ghost adjoint back through the boundary condition
-//            (bc_2D.jl:640-834) onto their internal cell;
+//            Zygote / ForwardDiff), composed with the transpose of the derived map and of the dry clamp, so that each
+//            face parks only the adjoints of the raw state (xi, q_x, q_y) of its two sides in shared memory; two
+//            faces per thread and trip where the launch shape has the registers (FPT = 2).  Boundary faces
+//            additionally pull the ghost adjoint back through the boundary condition (bc_2D.jl:640-834) onto their
+//            internal cell;
 //   phase 3  each owned cell GATHERS the L- or R-side adjoints of its faces through the same slots used by the
-//            forward pass (the adjoint of a gather done as a gather: no atomics, deterministic), adds the adjoint
-//            of the bed-slope and Manning-friction sources, undoes the derived-variable map and the dry clamp.
+//            forward pass (the adjoint of a gather done as a gather: no atomics, deterministic) and adds the adjoint
+//            of the bed-slope and Manning-friction sources.
 // Boundary-wide couplings (inlet conveyance split) and parameter reductions run in small follow-up kernels
 // with fixed reduction trees.
 #include "hg_device.cuh"

@@ -143,3 +143,26 @@ def test_variable_manning_on_tiled_synthetic_river_and_guards(hg):
         ctx.rhs(Q0, np.full(flat["n_mat"], 0.03), "ManningN")
     with pytest.raises(hg.HydrogradError):
         ctx.set_manning_function("sigmoid", n_lower=0.02, n_upper=0.05, k=-1.0, h_mid=0.3)
+
+
+def test_reference_control_file_drives_the_closure(hg):
+    """The reference's own run_control.json of Savannah_River_ManningN_ks_h_Umag handed to the host mirror: swe_2d_rhs then
+    evaluates n(h, |U|, ks) with ks per material zone, as the forward simulation does (semi_discretize_swe_2D.jl:140-149)."""
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    rc = json.load(open(os.path.join(cases.GOLD, "savannah_ks", "run_control.json")))
+    t = np.load(os.path.join(cases.GOLD, "savannah_ks", "truth.npz"))
+    h = t["h_truth"]
+    Q = np.concatenate([t["xi_truth"], t["u_truth"] * (h + c.h_small), t["v_truth"] * (h + c.h_small)])
+    px = hg.SWE2D_Extra_Parameters(flat, forward_settings=rc["forward_simulation_options"], options=dict(tile_cells=128))
+    got = hg.swe_2d_rhs(None, Q, np.zeros(0), 0.0, px)
+    o = Oracle(flat)
+    o.set_manning_function("h_Umag_ks", ks_cells=_ks_cells(c))
+    try:
+        ref = o.rhs(Q)
+    finally:
+        o.set_manning_function("constant")
+    assert np.isfinite(ref).all()
+    assert _rel(flat, Q, got, ref) <= 5e-12
+    plain = hg.SWE2D_Extra_Parameters(flat, options=dict(tile_cells=128))
+    assert np.abs(hg.swe_2d_rhs(None, Q, np.zeros(0), 0.0, plain) - got).max() > 1e-6
