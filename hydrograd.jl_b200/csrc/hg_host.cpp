@@ -383,6 +383,9 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
         left -= npick;
       }
       tf.swap(out);
+      // (Tried: also permuting the faces INSIDE each block so that the phase-3 slot gathers -- the j-th faces of 16
+      // consecutive cells -- hit distinct banks; a greedy placement left 1.75 wavefronts per half-warp vs 1.77, since one
+      // collision per group already costs a wavefront and late blocks have no freedom left.  Not kept.)
     }
     if (getenv("HG_DEBUG_TILES") && t == fh.n_tiles / 2) {
       // average number of wavefronts a half-warp's 64-bit gather of the L cells / R cells takes (1 = conflict-free)
@@ -431,6 +434,25 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
         const bool on_right = (cf_nb[k] < N) && ((int32_t)(lr >> 16) == loc[c]);
         slots[(c - c0) * NF + j] = (uint16_t)(lf | (on_right ? 0x8000 : 0));
       }
+    }
+    if (getenv("HG_DEBUG_TILES") && t == fh.n_tiles / 2) {
+      // average wavefronts of a half-warp's gather of one flux row at slot j (1 = conflict-free; same face = broadcast)
+      double w = 0; int ng = 0;
+      for (int32_t l0 = 0; l0 + 16 <= nc; l0 += 16)
+        for (int32_t j = 0; j < NF; ++j) {
+          int cnt[16] = {0}, mx = 0;
+          int32_t seen[16]; int ns = 0;
+          for (int32_t l = l0; l < l0 + 16; ++l) {
+            const int32_t f = slots[l * NF + j] & 0x7FFF;
+            bool dup = false;
+            for (int q = 0; q < ns; ++q) dup |= seen[q] == f;
+            if (dup) continue;
+            seen[ns++] = f;
+            mx = std::max(mx, ++cnt[f & 15]);
+          }
+          w += mx; ++ng;
+        }
+      fprintf(stderr, "[hg] tile %d: phase-3 slot gather wavefronts per half-warp %.2f\n", t, w / std::max(ng, 1));
     }
     const int32_t nh = (int32_t)(fh.halo.size() - halo_base);
     while ((fh.halo.size() - halo_base) % 4) fh.halo.push_back(0);
