@@ -244,6 +244,16 @@ class Context:
     def step_rk4(self, dt, nsteps=1):
         self._ck(self.lib.hg_step_rk4(self._h, float(dt), int(nsteps)))
 
+    def solve_tsit5(self, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=()):
+        """solve(prob, Tsit5(), adaptive=adaptive, dt=dt, saveat=t_save; abstol, reltol) on the resident state
+        (swe_2D_forward_simulation.jl:38-41); returns (saved states [len(t_save), 3N], stats dict)."""
+        ts = _f64(np.asarray(t_save, dtype=np.float64)) if len(t_save) else None
+        out = np.empty((len(t_save), 3 * self.N)) if len(t_save) else None
+        stats = np.zeros(3, dtype=np.int64)
+        self._ck(self.lib.hg_solve_tsit5(self._h, float(t0), float(t1), float(dt), int(bool(adaptive)), float(abstol), float(reltol),
+                                         _p(ts), len(t_save), _p(out), _p(stats, L.c_i64p)))
+        return out, dict(accepted=int(stats[0]), rejected=int(stats[1]), rhs=int(stats[2]))
+
     def euler_adjoint(self, Q0, lam_T, dt, nsteps, params=None, active=None):
         """Discrete adjoint of nsteps Euler steps: returns (Q_T, Q0bar, pbar)."""
         p, n, a = self._params(params, active)

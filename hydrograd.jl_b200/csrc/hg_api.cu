@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <utility>
+#include <vector>
 #include <memory>
 #include <mutex>
 
@@ -785,6 +787,112 @@ int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps) {
     TRY(hg::fused_axpy(ctx, d.Q.p, d.Q.p, d.rk_acc.p, 1.0, nullptr, nullptr, 0.0));
   }
   return HG_OK;
+}
+
+// Tsit5 (Tsitouras 2011) with OrdinaryDiffEq's PI step-size controller -- what the reference's forward and sensitivity
+// drivers run by default: solve(prob, Tsit5(), adaptive=..., dt=dt, saveat=t_save; abstol=1e-6, reltol=1e-3)
+// (swe_2D_forward_simulation.jl:38-41, swe_2D_sensitivity.jl:38-43).  Device-resident: seven fused RHS launches per step
+// (six with FSAL), stage states by k_lincomb, the scaled error norm by a fixed-shape reduction; one 8-byte D2H per step
+// for the accept / reject decision.  Save times are tstops (the step is clipped to land on them, the controller's own
+// proposal is kept), not interpolated: OrdinaryDiffEq's dense-output polynomials are not restated.
+int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol, const double* t_save,
+                   int64_t n_save, double* Q_save, int64_t* stats) {
+  if (!ctx || !(t1 > t0) || !(dt > 0.0) || n_save < 0 || (n_save > 0 && (!t_save || !Q_save))) return HG_ERR_ARG;
+  if (adaptive && (!(abstol > 0.0) || !(reltol > 0.0))) { ctx->err = "hg_solve_tsit5: tolerances must be positive"; return HG_ERR_ARG; }
+  if (!ctx->state_set) { ctx->err = "hg_solve_tsit5: no resident state"; return HG_ERR_STATE; }
+  if (ctx->opt.path == 1) { ctx->err = "hg_solve_tsit5 needs the fused path (path=0)"; return HG_ERR_ARG; }
+  if (ctx->n_halo > 0) { ctx->err = "hg_solve_tsit5: multi-rank contexts are not supported"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  static const double A[7][6] = {
+      {0, 0, 0, 0, 0, 0},
+      {0.161, 0, 0, 0, 0, 0},
+      {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+      {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+      {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+      {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+      {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+  static const double BT[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                               0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
+  const double beta2 = 2.0 / 25.0, beta1 = 7.0 / 50.0, gamma = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
+  hg::FusedDev& d = ctx->fd;
+  const size_t n3 = 3 * (size_t)ctx->fh.Ns;
+  for (int m = 0; m < 7; ++m)
+    if (d.ts_k[m].n != n3) { TRY(al(ctx, d.ts_k[m], n3)); CK(ctx, cudaMemsetAsync(d.ts_k[m].p, 0, n3 * 8, ctx->stream)); }
+  if (d.ts_new.n != n3) { TRY(al(ctx, d.ts_new, n3)); CK(ctx, cudaMemsetAsync(d.ts_new.p, 0, n3 * 8, ctx->stream)); }
+  if (d.rk_tmp.n != n3) TRY(al(ctx, d.rk_tmp, n3));
+  const int nblk = hg::fused_err_blocks(ctx);
+  if (d.ts_part.n != (size_t)nblk) TRY(al(ctx, d.ts_part, nblk));
+  if (d.ts_sum.n != 1) TRY(al(ctx, d.ts_sum, 1));
+  // the stops: save times inside (t0, t1] in ascending order, then t1
+  std::vector<std::pair<double, int64_t>> stops;
+  for (int64_t i = 0; i < n_save; ++i) {
+    if (t_save[i] == t0) TRY(download3(ctx, d.Q.p, Q_save + (size_t)i * 3 * ctx->N));
+    else if (t_save[i] > t0 && t_save[i] <= t1) stops.push_back({t_save[i], i});
+    else { ctx->err = "hg_solve_tsit5: save time outside [t0, t1]"; return HG_ERR_ARG; }
+  }
+  std::sort(stops.begin(), stops.end());
+  if (stops.empty() || stops.back().first < t1) stops.push_back({t1, -1});
+  int64_t n_acc = 0, n_rej = 0, n_rhs = 0;
+  double t = t0, dt_ctrl = dt, qold = qoldinit;
+  double* k[7];
+  for (int m = 0; m < 7; ++m) k[m] = d.ts_k[m].p;
+  TRY(hg::fused_rhs(ctx, d.Q.p, k[0], false, 0.0));
+  ++n_rhs;
+  for (size_t si = 0; si < stops.size(); ++si) {
+    const double ts = stops[si].first;
+    while (t < ts) {
+      double h = std::min(dt_ctrl, ts - t);
+      const bool clipped = h < dt_ctrl;
+      if (ts - (t + h) < 1e-12 * std::max(1.0, std::fabs(ts))) h = ts - t;   // do not leave a sliver before the stop
+      double coef[7];
+      for (int i = 1; i < 7; ++i) {
+        for (int j = 0; j < i; ++j) coef[j] = h * A[i][j];
+        double* y = i < 6 ? d.rk_tmp.p : d.ts_new.p;
+        TRY(hg::fused_lincomb(ctx, y, d.Q.p, i, k, coef));
+        TRY(hg::fused_rhs(ctx, y, k[i], false, 0.0));
+        ++n_rhs;
+      }
+      bool accept = true;
+      double q = 1.0, q11 = 0.0, eest = 0.0;
+      if (adaptive) {
+        for (int m = 0; m < 7; ++m) coef[m] = h * BT[m];
+        TRY(hg::fused_err_norm(ctx, d.Q.p, d.ts_new.p, 7, k, coef, abstol, reltol, d.ts_part.p, d.ts_sum.p));
+        double sum = 0.0;
+        CK(ctx, cudaMemcpyAsync(&sum, d.ts_sum.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        eest = std::sqrt(sum / (3.0 * (double)ctx->N));
+        if (!(eest == eest)) { ctx->err = "hg_solve_tsit5: the error estimate is NaN"; return HG_ERR_STATE; }
+        if (eest == 0.0) { q11 = 0.0; q = 1.0 / qmax; }
+        else {
+          q11 = std::pow(eest, beta1);
+          q = q11 / std::pow(qold, beta2);
+          q = std::max(1.0 / qmax, std::min(1.0 / qmin, q / gamma));
+        }
+        accept = eest <= 1.0;
+      }
+      if (accept) {
+        std::swap(d.Q.p, d.ts_new.p);            // the candidate becomes the state (equal sizes, like hg_step_euler's swap)
+        std::swap(d.ts_k[0].p, d.ts_k[6].p);     // FSAL: k7 of this step is k1 of the next
+        for (int m = 0; m < 7; ++m) k[m] = d.ts_k[m].p;
+        t += h;
+        ++n_acc;
+        if (adaptive) {
+          qold = std::max(eest, qoldinit);
+          const double prop = h / q;
+          dt_ctrl = clipped ? std::max(prop, dt_ctrl) : prop;   // a step clipped by a stop does not shrink the proposal
+        }
+      } else {
+        ++n_rej;
+        dt_ctrl = h / std::min(1.0 / qmin, q11 / gamma);
+        if (!(dt_ctrl > 1e-14 * std::max(1.0, std::fabs(t)))) { ctx->err = "hg_solve_tsit5: step size underflow"; return HG_ERR_STATE; }
+      }
+    }
+    t = ts;
+    if (stops[si].second >= 0) TRY(download3(ctx, d.Q.p, Q_save + (size_t)stops[si].second * 3 * ctx->N));
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) { stats[0] = n_acc; stats[1] = n_rej; stats[2] = n_rhs; }
+  return check_err_flag(ctx);
 }
 
 int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double dt, int64_t nsteps,

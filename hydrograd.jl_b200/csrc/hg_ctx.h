@@ -172,6 +172,7 @@ struct FusedDev {
   DBuf<int32_t> halo_off, halo_cnt;                                     // [B]
   DBuf<double> ens_Q, ens_Q2, ens_mann, ens_Qin, ens_coef, ens_A;       // parameter ensembles: [M][...]
   DBuf<double> rk_k, rk_acc, rk_tmp;                                   // RK4 stages
+  DBuf<double> ts_k[7], ts_new, ts_part, ts_sum;                       // Tsit5 stages, candidate state, error-norm scratch
   DBuf<double> halo_send, halo_recv;                                    // [6 * n_halo_entries]
   DBuf<int32_t> err;
 };
@@ -252,5 +253,9 @@ int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 int fused_halo_pack(hg_ctx* ctx, bool with_lambda);
 int fused_adjoint_step(hg_ctx* ctx, const double* Qn, const double* Qn1, double* lam, double* lam_tmp, double* pbar_acc, int64_t np, double dt);
 int fused_axpy(hg_ctx* ctx, double* y, const double* x, const double* k, double a, const double* acc_in, double* acc_out, double b);
+int fused_lincomb(hg_ctx* ctx, double* y, const double* x, int n, const double* const* k, const double* coef);
+int fused_err_blocks(const hg_ctx* ctx);
+int fused_err_norm(hg_ctx* ctx, const double* u, const double* unew, int n, const double* const* k, const double* coef, double abstol,
+                   double reltol, double* d_part, double* d_sum);
 int fused_rhs_ensemble(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 }  // namespace hg

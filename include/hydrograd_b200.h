@@ -202,6 +202,15 @@ HG_API int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps);
  * in swe_2D_forward_simulation.jl:44), four fused RHS launches + three axpy kernels per step, no host round trip.   */
 HG_API int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps);
 
+/* Tsit5 (adaptive with OrdinaryDiffEq's PI controller, or fixed-step when adaptive = 0) on the resident state from t0 to
+ * t1 -- `solve(prob, Tsit5(), adaptive=..., dt=dt, saveat=t_save; abstol=1e-6, reltol=1e-3)` of
+ * swe_2D_forward_simulation.jl:38-41 / swe_2D_sensitivity.jl:38-43 without a host round trip per stage.  dt is the initial
+ * (adaptive) or the fixed step.  t_save[n_save] in [t0, t1] are stops at which the state is copied to Q_save[n_save][3N]
+ * (reference order); OrdinaryDiffEq interpolates its saves instead, both agree within the integration tolerance.
+ * stats[3] (may be NULL) = accepted steps, rejected steps, RHS evaluations. */
+HG_API int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol,
+                          const double* t_save, int64_t n_save, double* Q_save, int64_t* stats);
+
 /* Discrete adjoint of nsteps of hg_step_euler (what SciMLSensitivity + Zygote produce for the "customized" Euler
  * solver inside compute_loss_inversion, swe_2D_inversion.jl:339): given lambda_T = d loss / d Q(T) it returns
  * Q0bar = d loss / d Q0 [3N] and pbar = d loss / d params [n_params] (NULL when active_param = NONE).  The forward

@@ -87,6 +87,9 @@ def main():
                 if k == "forward_simulation_results":        # 3N x 101 column-major, flattened
                     a = a.reshape(101, -1)                   # -> [101, 3N]
                     out[k] = a[[0, 50, 100]]
+                    early = [1, 2, 3, 5, 8, 12, 20, 30]      # the transient (saves are 2 s apart)
+                    out["early_index"] = np.array(early)
+                    out["forward_simulation_results_early"] = a[early]
                 else:
                     out[k] = a
             np.savez_compressed(os.path.join(dst, "trajectory.npz"), **out)

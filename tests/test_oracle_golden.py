@@ -161,3 +161,50 @@ def test_manning_closures_power_law_and_inverse_formulas():
     nl, nu, k = 0.02, 0.08, 0.7
     assert np.allclose(o.manning_closure("power_law", h, n_lower=nl, n_upper=nu, k=k)["n"], nl + (nu - nl) * (h + np.finfo(float).eps) ** (-k), rtol=1e-15)
     assert np.allclose(o.manning_closure("inverse", h, n_lower=nl, n_upper=nu, k=k)["n"], nl + (nu - nl) / (1 + k * h), rtol=1e-15)
+
+
+def test_tsit5_tableau():
+    """The restated Tsit5 coefficients: row sums = c, order-5 conditions of the propagating weights, order-4 of the
+    embedded ones, error weights summing to zero (all to rounding) -- the tableau is the published one."""
+    from tests import tsit5_ref as T
+    A = np.zeros((7, 7))
+    for i, row in enumerate(T.A):
+        A[i, :len(row)] = row
+    c, b, bt = np.array(T.C), A[6].copy(), np.array(T.BTILDE)
+    assert np.abs(A.sum(1) - c).max() < 1e-15
+    for p in range(5):
+        assert abs((b * c ** p).sum() - 1 / (p + 1)) < 1e-15
+    for val, ref in ((b @ A @ c, 1 / 6), (b @ A @ c ** 2, 1 / 12), (b @ A @ A @ c, 1 / 24), (b @ A @ c ** 3, 1 / 20),
+                     (b @ A @ A @ A @ c, 1 / 120), ((b * c) @ A @ c, 1 / 8), ((b * c) @ A @ c ** 2, 1 / 15), (b @ (A @ c) ** 2, 1 / 20)):
+        assert abs(val - ref) < 1e-15
+    bh = b - bt
+    for p in range(4):
+        assert abs((bh * c ** p).sum() - 1 / (p + 1)) < 1e-15
+    assert abs(bt.sum()) < 1e-15
+
+
+def test_transient_of_reference_trajectory_with_tsit5(oracle_lib):
+    """The reference's saved Tsit5 trajectory (adaptive, abstol 1e-6, reltol 1e-3, dt0 = 0.02, saves 2 s apart) during the
+    TRANSIENT (t = 2 ... 60 s, where the state still moves by O(0.1)): the oracle RHS integrated by the restated Tsit5 +
+    PI controller stays within the integration tolerance of it.  Soft pin of a1-a6 off the steady state."""
+    from tests import tsit5_ref as T
+    c = cases.load("oneD_bump_sens")
+    tj = np.load(cases.GOLD + "/oneD_bump_sens/trajectory.npz")
+    idx = tj["early_index"]
+    ref = tj["forward_simulation_results_early"]
+    o = Oracle(R.flatten(c))
+    p = np.array([0.03, 0.02, 0.03])
+    t_save = 2.0 * idx
+    N = 200
+    moved = np.abs(ref[0][:N] - c.Q0[:N]).max()
+    assert moved > 0.02                                          # a real transient: xi moves by ~0.1 m
+    # (a) the reference's own settings: both solutions carry the tolerance's error
+    _, saves, st = T.solve(lambda u: o.rhs(u, p, 2), c.Q0, 0.0, float(t_save[-1]), 0.02, True, 1e-6, 1e-3, t_save)
+    assert st["accepted"] > 100 and st["rejected"] < st["accepted"]
+    for k, (got, want) in enumerate(zip(saves, ref)):
+        assert np.abs(got[:N] - want[:N]).max() < 1e-3 and np.abs(got[N:2 * N] - want[N:2 * N]).max() < 1e-3, int(idx[k])
+    # (b) a tight solve: what is left is the reference's integration error (measured 7e-5 at t = 2 s falling to 5e-7 at 60 s)
+    _, saves, st = T.solve(lambda u: o.rhs(u, p, 2), c.Q0, 0.0, float(t_save[-1]), 0.02, True, 1e-9, 1e-7, t_save)
+    for k, (got, want) in enumerate(zip(saves, ref)):
+        lim = 4e-4 if idx[k] < 20 else 1e-5
+        assert np.abs(got[:N] - want[:N]).max() < lim and np.abs(got[N:2 * N] - want[N:2 * N]).max() < lim, int(idx[k])
