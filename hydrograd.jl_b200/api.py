@@ -262,6 +262,16 @@ class Context:
                                            _p(QT), _p(Q0bar), _p(pbar)))
         return QT, Q0bar, pbar[:n]
 
+    RK_METHODS = {"RK4": 0, "Tsit5": 1}
+
+    def rk_adjoint(self, method, Q0, lam_T, dt, nsteps, params=None, active=None):
+        """Discrete adjoint of nsteps fixed steps of `method` ("RK4" | "Tsit5"): returns (Q_T, Q0bar, pbar)."""
+        p, n, a = self._params(params, active)
+        QT, Q0bar, pbar = np.empty(3 * self.N), np.empty(3 * self.N), np.zeros(max(n, 1))
+        self._ck(self.lib.hg_rk_adjoint(self._h, self.RK_METHODS[method], _p(_f64(Q0)), _p(p), n, a, float(dt), int(nsteps),
+                                        _p(_f64(lam_T)), _p(QT), _p(Q0bar), _p(pbar)))
+        return QT, Q0bar, pbar[:n]
+
     def custom_ode_solve(self, Q0, params, active, t_start, t_end, dt):
         nsteps = int(np.floor((t_end - t_start) / dt + 1e-9)) + 1 if t_end >= t_start else 0
         sol = np.empty((max(nsteps, 1), 3 * self.N))   # row s = column s of the reference's 3N x nSaves `sol`

@@ -940,6 +940,115 @@ int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params, int64_
   return check_err_flag(ctx);
 }
 
+// ---- discrete adjoint of nsteps of a fixed-step explicit Runge-Kutta method (method 0: classical RK4, 1: Tsit5) --
+// "discretise, then differentiate": exactly the derivative of what hg_step_rk4 / hg_solve_tsit5(adaptive = 0) compute, the
+// counterpart for the SciML solvers of what hg_euler_adjoint is for the customized Euler loop (swe_2D_inversion.jl:304-339).
+//   forward   Y_i = u_n + h sum_{j<i} a_ij k_j,  k_i = f(Y_i),  u_{n+1} = u_n + h sum_i b_i k_i
+//   reverse   kbar_i = h b_i lam + h sum_{j>i} a_ji Ybar_j,  Ybar_i = J_u(Y_i)^T kbar_i,  pbar += J_p(Y_i)^T kbar_i  (i = s..1),
+//             lam <- lam + sum_i Ybar_i
+// The stage states of a step are recomputed from its start state; start states are kept per segment (~sqrt(nsteps)
+// checkpoints), like hg_euler_adjoint.
+namespace {
+struct RkTable {
+  int s;
+  double a[7][6];
+  double b[7];
+};
+const RkTable kRK4 = {4, {{0}, {0.5}, {0, 0.5}, {0, 0, 1.0}}, {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0}};
+const RkTable kTsit5 = {6,
+                        {{0},
+                         {0.161},
+                         {-0.008480655492356989, 0.335480655492357},
+                         {2.8971530571054935, -6.359448489975075, 4.3622954328695815},
+                         {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525},
+                         {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383}},
+                        {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+
+// one step from un: stage states into Y[1..s-1] (Y_0 is un itself), slopes into K[0..s-1], result into unext
+int rk_forward_step(hg_ctx* ctx, const RkTable& tb, double h, const double* un, double* const* Y, double* const* K, double* unext) {
+  double coef[7];
+  for (int i = 0; i < tb.s; ++i) {
+    const double* y = un;
+    if (i > 0) {
+      for (int j = 0; j < i; ++j) coef[j] = h * tb.a[i][j];
+      TRY(hg::fused_lincomb(ctx, Y[i], un, i, K, coef));
+      y = Y[i];
+    }
+    TRY(hg::fused_rhs(ctx, y, K[i], false, 0.0));
+  }
+  for (int i = 0; i < tb.s; ++i) coef[i] = h * tb.b[i];
+  return hg::fused_lincomb(ctx, unext, un, tb.s, K, coef);
+}
+}  // namespace
+
+int hg_rk_adjoint(hg_ctx* ctx, int32_t method, const double* Q0, const double* params, int64_t np, int32_t active, double dt,
+                  int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar) {
+  if (!ctx || !Q0 || !lambda_T || !Q0bar || nsteps < 1 || !(dt > 0.0) || method < 0 || method > 1) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "hg_rk_adjoint needs the fused path"; return HG_ERR_ARG; }
+  TRY(no_closure(ctx, "hg_rk_adjoint"));
+  if (ctx->n_halo > 0) { ctx->err = "hg_rk_adjoint: multi-rank contexts are not supported"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  TRY(bind_params(ctx, params, np, active));
+  if (ctx->active != HG_PARAM_NONE && !pbar) { ctx->err = "hg_rk_adjoint: pbar is NULL"; return HG_ERR_ARG; }
+  const RkTable& tb = method == 0 ? kRK4 : kTsit5;
+  hg::FusedDev& d = ctx->fd;
+  const size_t n3 = 3 * (size_t)ctx->fh.Ns;
+  const int64_t npar = ctx->active == HG_PARAM_NONE ? 0 : ctx->n_params;
+  const int64_t C = std::max<int64_t>(1, (int64_t)std::ceil(std::sqrt((double)nsteps)));
+  const int64_t nck = (nsteps + C - 1) / C;
+  hg::DBuf<double> ck, seg, lam, zero, pacc, Ybuf[7], Kbuf[7];
+  CK(ctx, ck.alloc((size_t)nck * n3)); CK(ctx, seg.alloc((size_t)(C + 1) * n3));
+  CK(ctx, lam.alloc(n3)); CK(ctx, zero.alloc(n3)); CK(ctx, pacc.alloc((size_t)std::max<int64_t>(npar, 1)));
+  double *Y[7] = {}, *K[7] = {};
+  for (int i = 0; i < tb.s; ++i) {
+    CK(ctx, Ybuf[i].alloc(n3)); CK(ctx, Kbuf[i].alloc(n3));
+    CK(ctx, cudaMemsetAsync(Ybuf[i].p, 0, n3 * 8, ctx->stream)); CK(ctx, cudaMemsetAsync(Kbuf[i].p, 0, n3 * 8, ctx->stream));
+    Y[i] = Ybuf[i].p; K[i] = Kbuf[i].p;
+  }
+  CK(ctx, cudaMemsetAsync(pacc.p, 0, pacc.bytes(), ctx->stream));
+  CK(ctx, cudaMemsetAsync(lam.p, 0, lam.bytes(), ctx->stream));
+  CK(ctx, cudaMemsetAsync(zero.p, 0, zero.bytes(), ctx->stream));
+  CK(ctx, cudaMemsetAsync(seg.p, 0, seg.bytes(), ctx->stream));
+  // ---- forward sweep, storing the state at the start of every segment
+  TRY(hg_set_state(ctx, Q0));
+  for (int64_t s = 0; s < nsteps; ++s) {
+    if (s % C == 0) CK(ctx, cudaMemcpyAsync(ck.p + (s / C) * n3, d.Q.p, n3 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    TRY(rk_forward_step(ctx, tb, dt, d.Q.p, Y, K, d.Q2.p));
+    std::swap(d.Q.p, d.Q2.p);
+  }
+  if (Q_T) TRY(download3(ctx, d.Q.p, Q_T));
+  // ---- terminal cotangent (reference order -> internal)
+  CK(ctx, cudaMemcpyAsync(d.stage.p, lambda_T, 3 * ctx->N * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TRY(hg::fused_permute(ctx, true, d.stage.p, lam.p));
+  const int cfg = hg::fused_cfg_id(ctx);
+  // ---- reverse sweep, one segment at a time; K[] is reused for the stage cotangents kbar_i once a step's Y_i are known
+  for (int64_t k = nck - 1; k >= 0; --k) {
+    const int64_t s0 = k * C, s1 = std::min<int64_t>(nsteps, s0 + C);
+    CK(ctx, cudaMemcpyAsync(seg.p, ck.p + k * n3, n3 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int64_t s = s0; s < s1 - 1; ++s) TRY(rk_forward_step(ctx, tb, dt, seg.p + (s - s0) * n3, Y, K, seg.p + (s - s0 + 1) * n3));
+    for (int64_t s = s1 - 1; s >= s0; --s) {
+      const double* un = seg.p + (s - s0) * n3;
+      TRY(rk_forward_step(ctx, tb, dt, un, Y, K, d.Q2.p));                 // the step's stage states Y_1 .. Y_{s-1}
+      for (int i = 0; i < tb.s; ++i) {                                     // kbar_i = h b_i lam
+        const double* one[1] = {lam.p};
+        const double cb[1] = {dt * tb.b[i]};
+        TRY(hg::fused_lincomb(ctx, K[i], zero.p, 1, one, cb));
+      }
+      for (int i = tb.s - 1; i >= 0; --i) {
+        TRY(hg::fused_vjp(ctx, cfg, i == 0 ? un : Y[i], K[i], d.Qbar.p));  // Ybar_i and the parameter adjoint of this stage
+        TRY(hg::fused_acc_pbar(ctx, npar, pacc.p, 1.0));
+        TRY(hg::fused_axpy(ctx, lam.p, lam.p, d.Qbar.p, 1.0, nullptr, nullptr, 0.0));
+        for (int j = 0; j < i; ++j)
+          if (tb.a[i][j] != 0.0) TRY(hg::fused_axpy(ctx, K[j], K[j], d.Qbar.p, dt * tb.a[i][j], nullptr, nullptr, 0.0));
+      }
+    }
+  }
+  TRY(download3(ctx, lam.p, Q0bar));
+  if (npar > 0) CK(ctx, cudaMemcpyAsync(pbar, pacc.p, npar * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_err_flag(ctx);
+}
+
 int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double t0,
                         double t1, double dt, double* sol, int64_t cap, int64_t* n_saves) {
   if (!ctx || !Q0 || !sol || !n_saves || !(dt > 0.0)) return HG_ERR_ARG;

@@ -252,6 +252,7 @@ int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar);
 int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 int fused_halo_pack(hg_ctx* ctx, bool with_lambda);
 int fused_adjoint_step(hg_ctx* ctx, const double* Qn, const double* Qn1, double* lam, double* lam_tmp, double* pbar_acc, int64_t np, double dt);
+int fused_acc_pbar(hg_ctx* ctx, int64_t np, double* acc, double a);
 int fused_axpy(hg_ctx* ctx, double* y, const double* x, const double* k, double a, const double* acc_in, double* acc_out, double b);
 int fused_lincomb(hg_ctx* ctx, double* y, const double* x, int n, const double* const* k, const double* coef);
 int fused_err_blocks(const hg_ctx* ctx);

@@ -219,6 +219,13 @@ HG_API int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t 
 HG_API int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params, int32_t active_param,
                      double dt, int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar);
 
+/* Discrete adjoint of nsteps of a fixed-step explicit Runge-Kutta method -- method 0: classical RK4 (hg_step_rk4),
+ * 1: Tsit5 (hg_solve_tsit5 with adaptive = 0) -- i.e. the exact derivative of those steppers ("discretise, then
+ * differentiate"), the counterpart of hg_euler_adjoint for the SciML solvers of swe_2D_inversion.jl:339.  Same arguments
+ * and outputs as hg_euler_adjoint; stage states are recomputed per step, ~sqrt(nsteps) checkpoints are kept. */
+HG_API int hg_rk_adjoint(hg_ctx* ctx, int32_t method, const double* Q0, const double* params, int64_t np, int32_t active,
+                         double dt, int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar);
+
 /* custom_ODE_solve (custom_ODE_solvers.jl:36-95): steps over t_start:dt:t_end, saving every
  * state; sol is [3N x n_saves] column-major, n_saves_capacity columns available; *n_saves out.   */
 HG_API int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params,

@@ -93,3 +93,67 @@ def test_inversion_loss_gradient_savannah(hg):
         e = np.zeros(6); e[k] = 1e-6
         fd[k] = (oracle_loss(p + e) - oracle_loss(p - e)) / 2e-6
     assert np.abs(grad - fd).max() <= 1e-5 * np.abs(fd).max(), (grad, fd)
+
+
+def _rk_tables():
+    from tests import tsit5_ref as T
+    rk4 = (((), (0.5,), (0.0, 0.5), (0.0, 0.0, 1.0)), (1 / 6, 1 / 3, 1 / 3, 1 / 6))
+    tsit = (T.A[:6], T.A[6])
+    return {"RK4": rk4, "Tsit5": tsit}
+
+
+def oracle_rk_forward_sensitivity(o, Q0, p, code, v, w, dt, nsteps, table):
+    """State and tangent through nsteps fixed steps of an explicit RK method, the tangent by the dual-number JVP per stage."""
+    A, b = table
+    Q, D = Q0.copy(), v.copy()
+    for _ in range(nsteps):
+        k, dk = [], []
+        for i in range(len(A)):
+            Y, dY = Q.copy(), D.copy()
+            for j, a in enumerate(A[i]):
+                Y += dt * a * k[j]
+                dY += dt * a * dk[j]
+            f, jv = o.jvp(Y, dY, p, w, code)
+            k.append(f); dk.append(jv)
+        for i, bi in enumerate(b):
+            Q = Q + dt * bi * k[i]
+            D = D + dt * bi * dk[i]
+    return Q, D
+
+
+@pytest.mark.parametrize("method,name,mode,nsteps", [("RK4", "oneD_bump", "ManningN", 60), ("Tsit5", "oneD_bump", "zb", 40),
+                                                     ("Tsit5", "savannah", "ManningN", 30), ("RK4", "savannah", "Q", 30),
+                                                     ("Tsit5", "simple", None, 50)])
+def test_rk_adjoint_matches_forward_sensitivities(hg, method, name, mode, nsteps):
+    """hg_rk_adjoint (discrete adjoint of fixed-step RK4 / Tsit5) against forward sensitivities of the same steps propagated
+    with the oracle's dual-number JVP:  lambda_T . dQ_T/d(Q0,p)[v,w] == Q0bar . v + pbar . w   (gate 1e-9)."""
+    c = cases.load(name)
+    flat = R.flatten(c)
+    o = Oracle(flat)
+    rng = np.random.default_rng(43)
+    code = {"ManningN": 2, "zb": 1, "Q": 3, None: 0}[mode]
+    p = {"ManningN": c.ManningN_zone * (1 + 0.1 * rng.uniform(-1, 1, c.ManningN_zone.size)), "zb": c.zb_cells.copy(),
+         "Q": np.asarray(c.bc.inletQ_TotalQ, dtype=float) * 0.9, None: None}[mode]
+    N = c.mesh.numOfCells
+    dt = 0.01 if name != "savannah" else 0.02
+    v = rng.standard_normal(3 * N) * 1e-2
+    w = None if p is None else rng.standard_normal(p.size) * (1e-3 if mode != "Q" else 1.0)
+    lam_T = rng.standard_normal(3 * N)
+    QT_ref, DT = oracle_rk_forward_sensitivity(o, c.Q0, p, code, v, w, dt, nsteps, _rk_tables()[method])
+    ctx = hg.Context(flat, tile_cells=128)
+    QT, Q0bar, pbar = ctx.rk_adjoint(method, c.Q0, lam_T, dt, nsteps, p, mode)
+    assert np.abs(QT - QT_ref).max() <= 1e-9 * max(1.0, np.abs(QT_ref).max())
+    lhs = lam_T @ DT
+    rhs = Q0bar @ v + (pbar @ w if p is not None else 0.0)
+    scale = np.abs(lam_T * DT).sum()
+    assert abs(lhs - rhs) <= 1e-9 * scale, (method, name, mode, lhs, rhs)
+    # and the forward part is what the steppers themselves do
+    ctx2 = hg.Context(flat, tile_cells=128)
+    if p is not None:
+        ctx2.set_params(p, mode)
+    ctx2.set_state(c.Q0)
+    if method == "RK4":
+        ctx2.step_rk4(dt, nsteps)
+    else:
+        ctx2.solve_tsit5(0.0, dt * nsteps, dt, adaptive=False)
+    assert np.abs(ctx2.get_state() - QT).max() <= 1e-10 * max(1.0, np.abs(QT).max())
