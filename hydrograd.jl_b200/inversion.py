@@ -57,13 +57,24 @@ def loss_terms(Q_T, params, observed, flat, active_param_name, bWSE=True, buv=Tr
     return parts["WSE"] + parts["uv"] + parts["bound"], parts, lam, dp
 
 
-def loss_and_gradient(ctx, flat, Q0, params, active_param_name, observed, dt, nsteps, **kw):
-    """One optimiser iteration's work: forward Euler sweep, loss, discrete adjoint sweep -> (loss, parts, d loss/d params)."""
-    # forward state is produced inside hg_euler_adjoint; the terminal cotangent needs Q(T) first, so run forward once
+def loss_and_gradient(ctx, flat, Q0, params, active_param_name, observed, dt, nsteps, method="Euler", **kw):
+    """One optimiser iteration's work: forward sweep, loss, discrete adjoint sweep -> (loss, parts, d loss/d params).
+    method: "Euler" (the reference's customized solver, custom_ODE_solvers.jl), "RK4" or "Tsit5" (fixed-step SciML solvers)."""
+    # the terminal cotangent needs Q(T) first, so run forward once; the adjoint call repeats the forward sweep with checkpoints
     ctx.set_params(params, active_param_name)
     ctx.set_state(Q0)
-    ctx.step_euler(dt, nsteps)
+    if method == "Euler":
+        ctx.step_euler(dt, nsteps)
+    elif method == "RK4":
+        ctx.step_rk4(dt, nsteps)
+    elif method == "Tsit5":
+        ctx.solve_tsit5(0.0, dt * nsteps, dt, adaptive=False)
+    else:
+        raise ValueError(f"unknown method {method}")
     Q_T = ctx.get_state()
     loss, parts, lam, dp = loss_terms(Q_T, params, observed, flat, active_param_name, **kw)
-    _, _, pbar = ctx.euler_adjoint(Q0, lam, dt, nsteps, params, active_param_name)
+    if method == "Euler":
+        _, _, pbar = ctx.euler_adjoint(Q0, lam, dt, nsteps, params, active_param_name)
+    else:
+        _, _, pbar = ctx.rk_adjoint(method, Q0, lam, dt, nsteps, params, active_param_name)
     return loss, parts, pbar + dp

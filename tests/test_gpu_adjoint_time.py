@@ -157,3 +157,29 @@ def test_rk_adjoint_matches_forward_sensitivities(hg, method, name, mode, nsteps
     else:
         ctx2.solve_tsit5(0.0, dt * nsteps, dt, adaptive=False)
     assert np.abs(ctx2.get_state() - QT).max() <= 1e-10 * max(1.0, np.abs(QT).max())
+
+
+def test_inversion_loss_gradient_savannah_tsit5(hg):
+    """The same inversion step with the SciML default integrator (fixed-step Tsit5) instead of the customized Euler loop:
+    loss and gradient from hg_solve_tsit5 + hg_rk_adjoint against central finite differences of the host Tsit5 on the oracle."""
+    from hydrograd_jl_b200 import inversion as inv
+    from tests import tsit5_ref as T
+    c, t = cases.load("savannah"), cases.truth("savannah")
+    flat = R.flatten(c)
+    o = Oracle(flat)
+    observed = dict(WSE_truth=t["wse_truth"], u_truth=t["u_truth"], v_truth=t["v_truth"], zb_cell_truth=t["zb_cell_truth"])
+    p = np.full(6, 0.03)
+    dt, nsteps = 0.05, 40
+    ctx = hg.Context(flat)
+    loss, parts, grad = inv.loss_and_gradient(ctx, flat, c.Q0, p, "ManningN", observed, dt, nsteps, method="Tsit5", bound=(0.01, 0.06))
+
+    def oracle_loss(pp):
+        QT, _, _ = T.solve(lambda u: o.rhs(u, pp, 2), c.Q0, 0.0, dt * nsteps, dt, adaptive=False)
+        return inv.loss_terms(QT, pp, observed, flat, "ManningN", bound=(0.01, 0.06))[0]
+
+    assert abs(loss - oracle_loss(p)) <= 1e-10 * loss
+    fd = np.zeros(6)
+    for k in range(6):
+        e = np.zeros(6); e[k] = 1e-6
+        fd[k] = (oracle_loss(p + e) - oracle_loss(p - e)) / 2e-6
+    assert np.abs(grad - fd).max() <= 1e-5 * np.abs(fd).max(), (grad, fd)
