@@ -65,6 +65,8 @@ SYMBOLS = {
     "hg_rhs_resident_phase": (C.c_int, [_vp, C.c_int32]),
     "hg_solve_tsit5": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, c_f64p, C.c_int64, c_f64p,
                                  c_i64p]),
+    "hg_solve_tsit5_dense": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, c_f64p, C.c_int64, c_f64p,
+                                 c_i64p]),
     "hg_vjp_resident_phase": (C.c_int, [_vp, C.c_int32]),
     "hg_get_rhs": (C.c_int, [_vp, c_f64p]),
     "hg_sync": (C.c_int, [_vp]),

@@ -244,14 +244,18 @@ class Context:
     def step_rk4(self, dt, nsteps=1):
         self._ck(self.lib.hg_step_rk4(self._h, float(dt), int(nsteps)))
 
-    def solve_tsit5(self, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=()):
+    def solve_tsit5(self, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(), saveat="stop"):
         """solve(prob, Tsit5(), adaptive=adaptive, dt=dt, saveat=t_save; abstol, reltol) on the resident state
-        (swe_2D_forward_simulation.jl:38-41); returns (saved states [len(t_save), 3N], stats dict)."""
+        (swe_2D_forward_simulation.jl:38-41); returns (saved states [len(t_save), 3N], stats dict).
+        saveat="interp": OrdinaryDiffEq's own saveat (dense output, steps independent of t_save); "stop": save times are stops."""
+        if saveat not in ("stop", "interp"):
+            raise ValueError(f"saveat must be 'stop' or 'interp', got {saveat!r}")
+        fn = self.lib.hg_solve_tsit5_dense if saveat == "interp" else self.lib.hg_solve_tsit5
         ts = _f64(np.asarray(t_save, dtype=np.float64)) if len(t_save) else None
         out = np.empty((len(t_save), 3 * self.N)) if len(t_save) else None
         stats = np.zeros(3, dtype=np.int64)
-        self._ck(self.lib.hg_solve_tsit5(self._h, float(t0), float(t1), float(dt), int(bool(adaptive)), float(abstol), float(reltol),
-                                         _p(ts), len(t_save), _p(out), _p(stats, L.c_i64p)))
+        self._ck(fn(self._h, float(t0), float(t1), float(dt), int(bool(adaptive)), float(abstol), float(reltol),
+                    _p(ts), len(t_save), _p(out), _p(stats, L.c_i64p)))
         return out, dict(accepted=int(stats[0]), rejected=int(stats[1]), rhs=int(stats[2]))
 
     def euler_adjoint(self, Q0, lam_T, dt, nsteps, params=None, active=None):

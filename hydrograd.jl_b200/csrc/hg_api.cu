@@ -793,10 +793,13 @@ int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps) {
 // drivers run by default: solve(prob, Tsit5(), adaptive=..., dt=dt, saveat=t_save; abstol=1e-6, reltol=1e-3)
 // (swe_2D_forward_simulation.jl:38-41, swe_2D_sensitivity.jl:38-43).  Device-resident: seven fused RHS launches per step
 // (six with FSAL), stage states by k_lincomb, the scaled error norm by a fixed-shape reduction; one 8-byte D2H per step
-// for the accept / reject decision.  Save times are tstops (the step is clipped to land on them, the controller's own
-// proposal is kept), not interpolated: OrdinaryDiffEq's dense-output polynomials are not restated.
-int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol, const double* t_save,
-                   int64_t n_save, double* Q_save, int64_t* stats) {
+// for the accept / reject decision.  Save times: dense = 0 treats them as tstops (the step is clipped to land on them, the
+// controller's own proposal is kept); dense = 1 is OrdinaryDiffEq's saveat: the steps ignore the save times and every
+// accepted step evaluates Tsit5's fourth-order dense output u + h sum_i b_i(theta) k_i at the save times it has passed
+// (one k_lincomb launch per save), copying the new state when a save time is the step end.
+namespace {
+int solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol, const double* t_save,
+                int64_t n_save, double* Q_save, int64_t* stats, bool dense) {
   if (!ctx || !(t1 > t0) || !(dt > 0.0) || n_save < 0 || (n_save > 0 && (!t_save || !Q_save))) return HG_ERR_ARG;
   if (adaptive && (!(abstol > 0.0) || !(reltol > 0.0))) { ctx->err = "hg_solve_tsit5: tolerances must be positive"; return HG_ERR_ARG; }
   if (!ctx->state_set) { ctx->err = "hg_solve_tsit5: no resident state"; return HG_ERR_STATE; }
@@ -831,7 +834,18 @@ int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptiv
     else { ctx->err = "hg_solve_tsit5: save time outside [t0, t1]"; return HG_ERR_ARG; }
   }
   std::sort(stops.begin(), stops.end());
+  std::vector<std::pair<double, int64_t>> pending;        // dense output: save times still ahead, ascending
+  if (dense) { pending.swap(stops); }
+  size_t next_save = 0;
   if (stops.empty() || stops.back().first < t1) stops.push_back({t1, -1});
+  // Tsit5Interp: b_i(theta) = theta (r_i1 + theta (r_i2 + theta (r_i3 + theta r_i4)))
+  static const double RI[7][4] = {{1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216},
+                                  {0.0, 0.13169999999999998, -0.2234, 0.1017},
+                                  {0.0, 3.9302962368947516, -5.941033872131505, 2.490627285651253},
+                                  {0.0, -12.411077166933676, 30.33818863028232, -16.548102889244902},
+                                  {0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928},
+                                  {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
+                                  {0.0, 1.5, -4.0, 2.5}};
   int64_t n_acc = 0, n_rej = 0, n_rhs = 0;
   double t = t0, dt_ctrl = dt, qold = qoldinit;
   double* k[7];
@@ -871,10 +885,19 @@ int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptiv
         accept = eest <= 1.0;
       }
       if (accept) {
+        const double tnew = (h == ts - t) ? ts : t + h;
+        for (; next_save < pending.size() && pending[next_save].first <= tnew; ++next_save) {
+          double* out = Q_save + (size_t)pending[next_save].second * 3 * ctx->N;
+          if (pending[next_save].first == tnew) { TRY(download3(ctx, d.ts_new.p, out)); continue; }
+          const double th = (pending[next_save].first - t) / h;
+          for (int m = 0; m < 7; ++m) coef[m] = h * (th * (RI[m][0] + th * (RI[m][1] + th * (RI[m][2] + th * RI[m][3]))));
+          TRY(hg::fused_lincomb(ctx, d.rk_tmp.p, d.Q.p, 7, k, coef));   // rk_tmp is free between steps
+          TRY(download3(ctx, d.rk_tmp.p, out));
+        }
         std::swap(d.Q.p, d.ts_new.p);            // the candidate becomes the state (equal sizes, like hg_step_euler's swap)
         std::swap(d.ts_k[0].p, d.ts_k[6].p);     // FSAL: k7 of this step is k1 of the next
         for (int m = 0; m < 7; ++m) k[m] = d.ts_k[m].p;
-        t += h;
+        t = tnew;
         ++n_acc;
         if (adaptive) {
           qold = std::max(eest, qoldinit);
@@ -893,6 +916,16 @@ int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptiv
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   if (stats) { stats[0] = n_acc; stats[1] = n_rej; stats[2] = n_rhs; }
   return check_err_flag(ctx);
+}
+}  // namespace
+
+int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol, const double* t_save,
+                   int64_t n_save, double* Q_save, int64_t* stats) {
+  return solve_tsit5(ctx, t0, t1, dt, adaptive, abstol, reltol, t_save, n_save, Q_save, stats, false);
+}
+int hg_solve_tsit5_dense(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol,
+                         const double* t_save, int64_t n_save, double* Q_save, int64_t* stats) {
+  return solve_tsit5(ctx, t0, t1, dt, adaptive, abstol, reltol, t_save, n_save, Q_save, stats, true);
 }
 
 int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double dt, int64_t nsteps,

@@ -169,15 +169,20 @@ end
 "custom_ODE_solve (ode_solvers/custom_ODE_solvers.jl:36-95) on the device; returns the 3N x nSaves matrix."
 # solve(prob, Tsit5(), adaptive=adaptive, dt=dt, saveat=t_save; abstol, reltol) with the state resident on the device
 # (swe_2D_forward_simulation.jl:38-41).  Returns the saved states as a 3N x length(t_save) matrix, like Array(sol).
+# dense=true (default): OrdinaryDiffEq's saveat (steps independent of t_save, Tsit5 dense output); dense=false: save times are stops.
 function solve_tsit5(ctx::Context, Q0::Vector{Float64}, tspan::Tuple{Float64,Float64}, dt::Float64, t_save::Vector{Float64};
-                     adaptive::Bool=true, abstol::Float64=1e-6, reltol::Float64=1e-3)
+                     adaptive::Bool=true, abstol::Float64=1e-6, reltol::Float64=1e-3, dense::Bool=true)
     n3 = length(Q0)
     out = Matrix{Float64}(undef, n3, length(t_save))
     stats = zeros(Int64, 3)
     GC.@preserve Q0 t_save out stats begin
         rc = ccall((:hg_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx.handle, Q0)
         rc == 0 || error(unsafe_string(ccall((:hg_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.handle)))
-        rc = ccall((:hg_solve_tsit5, LIB), Cint,
+        rc = dense ?
+            ccall((:hg_solve_tsit5_dense, LIB), Cint,
+                  (Ptr{Cvoid}, Float64, Float64, Float64, Int32, Float64, Float64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}),
+                  ctx.handle, tspan[1], tspan[2], dt, Int32(adaptive), abstol, reltol, t_save, length(t_save), out, stats) :
+            ccall((:hg_solve_tsit5, LIB), Cint,
                    (Ptr{Cvoid}, Float64, Float64, Float64, Int32, Float64, Float64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}),
                    ctx.handle, tspan[1], tspan[2], dt, Int32(adaptive), abstol, reltol, t_save, length(t_save), out, stats)
         rc == 0 || error(unsafe_string(ccall((:hg_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.handle)))

@@ -206,10 +206,19 @@ HG_API int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps);
  * t1 -- `solve(prob, Tsit5(), adaptive=..., dt=dt, saveat=t_save; abstol=1e-6, reltol=1e-3)` of
  * swe_2D_forward_simulation.jl:38-41 / swe_2D_sensitivity.jl:38-43 without a host round trip per stage.  dt is the initial
  * (adaptive) or the fixed step.  t_save[n_save] in [t0, t1] are stops at which the state is copied to Q_save[n_save][3N]
- * (reference order); OrdinaryDiffEq interpolates its saves instead, both agree within the integration tolerance.
+ * (reference order); OrdinaryDiffEq interpolates its saves instead (hg_solve_tsit5_dense), both agree within the
+ * integration tolerance.
  * stats[3] (may be NULL) = accepted steps, rejected steps, RHS evaluations. */
 HG_API int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol,
                           const double* t_save, int64_t n_save, double* Q_save, int64_t* stats);
+
+/* The same solve with OrdinaryDiffEq's saveat semantics (savevalues!, Tsit5's dense output `Tsit5Interp`): the steps do
+ * not stop at the save times (only t1 is a stop); after every accepted step [t, t + h] the fourth-order interpolant
+ * u + h sum_i b_i(theta) k_i, theta = (t_save - t) / h, is evaluated on the device for every save time the step has
+ * passed, and a save time equal to the step end copies the new state.  This reproduces the reference's step sequence
+ * (the step sizes do not depend on t_save); arguments as for hg_solve_tsit5. */
+HG_API int hg_solve_tsit5_dense(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol,
+                                const double* t_save, int64_t n_save, double* Q_save, int64_t* stats);
 
 /* Discrete adjoint of nsteps of hg_step_euler (what SciMLSensitivity + Zygote produce for the "customized" Euler
  * solver inside compute_loss_inversion, swe_2D_inversion.jl:339): given lambda_T = d loss / d Q(T) it returns

@@ -85,3 +85,32 @@ def test_adaptive_tsit5_follows_the_reference_transient(hg):
         assert stats["accepted"] > 50
         for got, want in zip(saves, ref):
             assert np.abs(got[:N] - want[:N]).max() < lim and np.abs(got[N:2 * N] - want[N:2 * N]).max() < lim
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_dense_output_saveat_matches_host(hg, adaptive):
+    """hg_solve_tsit5_dense = OrdinaryDiffEq's saveat: save times that are not step ends are interpolated with Tsit5's
+    dense output on the device, the step sequence is the one of a solve without save times.  Same algorithm on the host
+    (tsit5_ref.solve(saveat="interp")) with the oracle RHS."""
+    c = cases.load("oneD_bump_sens")
+    flat = R.flatten(c)
+    o = Oracle(flat)
+    p = np.array([0.03, 0.02, 0.03])
+    t1 = 6.0 if adaptive else 1.0
+    ts = [0.0, 0.137 * t1, t1 / 2, 0.9 * t1, t1]
+    args = (0.0, t1, 0.02 if adaptive else 0.01, adaptive, 1e-6, 1e-3)
+    ref_end, ref_saves, st = T.solve(lambda u: o.rhs(u, p, 2), c.Q0, *args, t_save=ts, saveat="interp")
+    _, _, st_free = T.solve(lambda u: o.rhs(u, p, 2), c.Q0, *args, t_save=[])
+    assert st == st_free
+    ctx = hg.Context(flat, tile_cells=128)
+    ctx.set_params(p, "ManningN")
+    ctx.set_state(c.Q0)
+    saves, stats = ctx.solve_tsit5(*args, t_save=ts, saveat="interp")
+    assert stats == st, (stats, st)
+    N = c.mesh.numOfCells
+    assert np.array_equal(saves[0], c.Q0)
+    tol = 2e-6 if adaptive else 1e-10                # see test_adaptive_tsit5_matches_host_controller for the adaptive bound
+    for got, want in zip(saves, ref_saves):
+        assert _scaled(got, want, N) <= tol
+    assert _scaled(ctx.get_state(), ref_end, N) <= tol
+    assert np.array_equal(saves[-1], ctx.get_state())            # a save at the step end is a copy, not an interpolation

@@ -208,3 +208,48 @@ def test_transient_of_reference_trajectory_with_tsit5(oracle_lib):
     for k, (got, want) in enumerate(zip(saves, ref)):
         lim = 4e-4 if idx[k] < 20 else 1e-5
         assert np.abs(got[:N] - want[:N]).max() < lim and np.abs(got[N:2 * N] - want[N:2 * N]).max() < lim, int(idx[k])
+
+
+def test_tsit5_dense_output_conditions():
+    """Tsit5's dense output b_i(theta) (OrdinaryDiffEq's Tsit5Interp, restated in tsit5_ref.INTERP): the continuous
+    order-4 conditions hold identically in theta (coefficient by coefficient), b_i(1) are the weights of the fifth-order
+    solution and b_i(0) = 0 -- the interpolant is the published one."""
+    from tests import tsit5_ref as T
+    A = np.zeros((7, 7))
+    for i, row in enumerate(T.A):
+        A[i, :len(row)] = row
+    c = np.array(T.C)
+    P = np.array(T.INTERP)                                       # b_i(theta) = sum_p P[i, p] theta^(p+1)
+    for w, power, val in ((np.ones(7), 1, 1.0), (c, 2, 1 / 2), (c ** 2, 3, 1 / 3), (A @ c, 3, 1 / 6), (c ** 3, 4, 1 / 4),
+                          (c * (A @ c), 4, 1 / 8), (A @ c ** 2, 4, 1 / 12), (A @ A @ c, 4, 1 / 24)):
+        want = np.zeros(4)
+        want[power - 1] = val
+        assert np.abs(P.T @ w - want).max() < 5e-14
+    assert np.abs(P.sum(1) - A[6]).max() < 5e-15
+    assert np.allclose(T.interp_weights(1.0), A[6], atol=5e-15) and T.interp_weights(0.0) == [0.0] * 7
+    # on u' = -u the interpolated saves have the dense output's O(h^5) local accuracy, and the step sequence does not
+    # depend on the save times (OrdinaryDiffEq's saveat semantics)
+    f = lambda u: -u
+    _, sv, st = T.solve(f, np.array([1.0]), 0.0, 2.0, 0.1, True, 1e-8, 1e-8, [0.3, 0.77, 1.234, 2.0], saveat="interp")
+    _, _, st0 = T.solve(f, np.array([1.0]), 0.0, 2.0, 0.1, True, 1e-8, 1e-8, [])
+    assert st == st0
+    for s, t in zip(sv, [0.3, 0.77, 1.234, 2.0]):
+        assert abs(s[0] - np.exp(-t)) < 2e-7
+
+
+def test_transient_of_reference_trajectory_with_dense_saveat(oracle_lib):
+    """As test_transient_of_reference_trajectory_with_tsit5, with OrdinaryDiffEq's saveat semantics (no stops, dense
+    output): this is the reference's own step sequence up to the starting guess of rounding."""
+    from tests import tsit5_ref as T
+    c = cases.load("oneD_bump_sens")
+    tj = np.load(cases.GOLD + "/oneD_bump_sens/trajectory.npz")
+    idx = tj["early_index"]
+    ref = tj["forward_simulation_results_early"]
+    o = Oracle(R.flatten(c))
+    p = np.array([0.03, 0.02, 0.03])
+    t_save = 2.0 * idx
+    N = 200
+    _, saves, st = T.solve(lambda u: o.rhs(u, p, 2), c.Q0, 0.0, float(t_save[-1]), 0.02, True, 1e-6, 1e-3, t_save, saveat="interp")
+    err = [max(np.abs(g[:N] - w[:N]).max(), np.abs(g[N:2 * N] - w[N:2 * N]).max()) for g, w in zip(saves, ref)]
+    print("dense saveat vs reference:", ["%.1e" % e for e in err], st)
+    assert len(saves) == len(ref) and max(err) < 1e-3

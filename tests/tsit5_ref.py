@@ -9,9 +9,13 @@ OrdinaryDiffEq itself unpinned).  Restated from its published form:
   * error estimate: utilde = dt * sum(btilde_i k_i), EEst = sqrt(mean((utilde / (abstol + max(|u_prev|, |u|) reltol))^2));
   * step-size control: OrdinaryDiffEq's PIController with the explicit-RK defaults beta2 = 2/(5 p), beta1 = 7/(10 p) (p = 5),
     gamma = 9/10, qmin = 1/5, qmax = 10, qoldinit = 1e-4; accept when EEst <= 1;
-  * saveat: OrdinaryDiffEq interpolates with Tsit5's dense output.  Here (and in hg_solve_tsit5) the save times are tstops --
-    the step is clipped to land on them and the controller's proposal is restored afterwards -- because the dense-output
-    polynomials are not restated.  Both are within the integration tolerance of each other.
+  * saveat: OrdinaryDiffEq does NOT stop at the save times; after every accepted step it evaluates Tsit5's fourth-order
+    dense output u(t + theta h) = u + h sum_i b_i(theta) k_i at the save times the step has passed (savevalues!), and
+    copies u when a save time coincides with the step end.  `saveat="interp"` (hg_solve_tsit5_dense) restates that; the
+    polynomials b_i(theta) below satisfy the continuous order-4 conditions identically in theta and b_i(1) = the weights
+    of the fifth-order solution (test_tsit5_dense_output_conditions).  `saveat="stop"` (hg_solve_tsit5) treats the save
+    times as tstops instead -- the step is clipped to land on them and the controller's proposal is restored afterwards.
+    Both are within the integration tolerance of each other; only "interp" reproduces OrdinaryDiffEq's step sequence.
 """
 import numpy as np
 
@@ -25,14 +29,29 @@ A = ((),
      (0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774))
 BTILDE = (-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, 0.5823571654525552,
           -0.45808210592918697, 0.015151515151515152)
+# dense output: b_i(theta) = sum_p INTERP[i][p] theta^(p+1)   (OrdinaryDiffEq's Tsit5Interp r_ip)
+INTERP = ((1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216),
+          (0.0, 0.13169999999999998, -0.2234, 0.1017),
+          (0.0, 3.9302962368947516, -5.941033872131505, 2.490627285651253),
+          (0.0, -12.411077166933676, 30.33818863028232, -16.548102889244902),
+          (0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928),
+          (0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661),
+          (0.0, 1.5, -4.0, 2.5))
 BETA2, BETA1, GAMMA, QMIN, QMAX, QOLDINIT = 2.0 / 25.0, 7.0 / 50.0, 0.9, 0.2, 10.0, 1e-4
 
 
-def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=()):
+def interp_weights(theta):
+    """b_i(theta), i = 1..7, evaluated by Horner like OrdinaryDiffEq's @evalpoly."""
+    return [theta * (r[0] + theta * (r[1] + theta * (r[2] + theta * r[3]))) for r in INTERP]
+
+
+def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(), saveat="stop"):
     """Returns (u(t1), [u(t) for t in t_save], stats).  rhs(u) -> du/dt (autonomous: the reference RHS ignores t)."""
+    assert saveat in ("stop", "interp")
     u = np.array(u0, dtype=np.float64)
     t = float(t0)
-    stops = sorted(set([float(x) for x in t_save if t0 < x <= t1] + [float(t1)]))
+    stops = sorted(set([float(x) for x in t_save if t0 < x <= t1 and saveat == "stop"] + [float(t1)]))
+    pending = sorted(float(x) for x in t_save if t0 < x <= t1) if saveat == "interp" else []
     saves = {}
     if any(float(x) == t0 for x in t_save):
         saves[float(t0)] = u.copy()
@@ -54,8 +73,21 @@ def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(
                     k[i] = rhs(y); n_rhs += 1
             unew = y
             k[6] = rhs(unew); n_rhs += 1
+            tnew = ts if h == ts - t else t + h
+
+            def dense_saves():
+                while pending and pending[0] <= tnew:
+                    s_ = pending.pop(0)
+                    if s_ == tnew:
+                        saves[s_] = unew.copy()
+                    else:
+                        v = u.copy()
+                        for b, kk in zip(interp_weights((s_ - t) / h), k):
+                            v += (h * b) * kk
+                        saves[s_] = v
             if not adaptive:
-                u, t, k[0] = unew, t + h, k[6]
+                dense_saves()
+                u, t, k[0] = unew, tnew, k[6]
                 n_acc += 1
                 continue
             ut = np.zeros_like(u)
@@ -69,7 +101,8 @@ def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(
                 q = q11 / qold ** BETA2
                 q = max(1.0 / QMAX, min(1.0 / QMIN, q / GAMMA))
             if eest <= 1.0:
-                u, t, k[0] = unew, t + h, k[6]
+                dense_saves()
+                u, t, k[0] = unew, tnew, k[6]
                 n_acc += 1
                 qold = max(eest, QOLDINIT)
                 prop = h / q
@@ -79,5 +112,6 @@ def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(
                 n_rej += 1
                 dt_ctrl = h / min(1.0 / QMIN, q11 / GAMMA)
         t = ts
-        saves[ts] = u.copy()
+        if saveat == "stop" or ts in [float(x) for x in t_save]:
+            saves.setdefault(ts, u.copy())
     return u, [saves[float(x)] for x in t_save if float(x) in saves], dict(accepted=n_acc, rejected=n_rej, rhs=n_rhs)
