@@ -12,9 +12,10 @@ c_i64p = C.POINTER(C.c_int64)
 c_f64p = C.POINTER(C.c_double)
 c_u8p = C.POINTER(C.c_uint8)
 
-PARAM_NONE, PARAM_ZB, PARAM_MANNING, PARAM_Q = 0, 1, 2, 3
-# active_param_name strings of the reference (application_commons.jl:9)
-ACTIVE_PARAM = {None: 0, "": 0, "none": 0, "zb": 1, "ManningN": 2, "Q": 3}
+PARAM_NONE, PARAM_ZB, PARAM_MANNING, PARAM_Q, PARAM_UDE = 0, 1, 2, 3, 4
+# active_param_name strings of the reference (application_commons.jl:9); "UDE" = settings.bPerform_UDE (params = NN parameters)
+ACTIVE_PARAM = {None: 0, "": 0, "none": 0, "zb": 1, "ManningN": 2, "Q": 3, "UDE": 4}
+UDE_MAX_HIDDEN, UDE_MAX_WIDTH = 3, 8
 ERR_NAMES = {1: "HG_ERR_ARG", 2: "HG_ERR_CUDA", 3: "HG_ERR_CONVEYANCE", 4: "HG_ERR_SOLVER", 5: "HG_ERR_STATE"}
 
 
@@ -42,6 +43,15 @@ class FieldsDesc(C.Structure):
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("tile_cells", C.c_int32), ("reorder", C.c_int32), ("strict", C.c_int32),
                 ("path", C.c_int32), ("reserved", C.c_int32 * 11)]
+
+
+class UdeDesc(C.Structure):
+    _fields_ = [("choice", C.c_int32), ("n_hidden", C.c_int32), ("width", C.c_int32 * UDE_MAX_HIDDEN),
+                ("activation", C.c_int32 * UDE_MAX_HIDDEN), ("layernorm", C.c_int32), ("ln_epsilon", C.c_double),
+                ("h_bounds", C.c_double * 2), ("umag_bounds", C.c_double * 2), ("ks_bounds", C.c_double * 2),
+                ("output_bounds", C.c_double * 2), ("n_params", C.c_int64),
+                ("off_weight", C.c_int64 * (UDE_MAX_HIDDEN + 1)), ("off_bias", C.c_int64 * (UDE_MAX_HIDDEN + 1)),
+                ("off_ln_scale", C.c_int64 * UDE_MAX_HIDDEN), ("off_ln_bias", C.c_int64 * UDE_MAX_HIDDEN)]
 
 
 # every symbol include/hydrograd_b200.h declares: name -> (restype, argtypes)
@@ -103,6 +113,7 @@ SYMBOLS = {
     "hg_plan_stats": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(BcDesc), C.POINTER(FieldsDesc), C.POINTER(Options),
                                 c_i64p, c_i64p]),
     "hg_flush_l2": (C.c_int, [_vp]),
+    "hg_set_ude_model": (C.c_int, [_vp, C.POINTER(UdeDesc), c_f64p]),
 }
 
 _lib = None

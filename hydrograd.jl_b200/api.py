@@ -192,6 +192,18 @@ class Context:
         ks = None if ks_cells is None else _f64(ks_cells)
         self._ck(self.lib.hg_set_manning_function(self._h, self.MANNING_TYPES[kind], _p(p), _p(ks)))
 
+    def set_ude_model(self, model, ks_cells=None):
+        """settings.bPerform_UDE with UDE_choice "ManningN_h" / "ManningN_h_Umag_ks" (semi_discretize_swe_2D.jl:165-178):
+        `model` is a hydrograd.jl_b200.ude.UDEModel (None clears it); afterwards params_vector with active = "UDE" is the
+        network's parameter vector, every RHS evaluates n = NN(h, |U|, ks) on the device and every VJP returns d/d theta."""
+        if model is None:
+            self._ck(self.lib.hg_set_ude_model(self._h, None, None))
+            return
+        ks = None if ks_cells is None else _f64(ks_cells)
+        if ks is not None and ks.size != self.N:
+            raise HydrogradError(1, f"ks_cells has length {ks.size}, expected {self.N}")
+        self._ck(self.lib.hg_set_ude_model(self._h, C.byref(model.desc), _p(ks)))
+
     # ---------------------------------------------------------------- adjoint on the resident state
     def set_lambda(self, lam):
         self._ck(self.lib.hg_set_lambda(self._h, _p(_f64(lam))))

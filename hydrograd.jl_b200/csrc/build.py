@@ -15,6 +15,7 @@ SOURCES = [
     ("hg_plain.cu", ["-fmad=false"]),      # reference evaluation order, no FMA contraction
     ("hg_fused.cu", []),
     ("hg_vjp.cu", []),
+    ("hg_ude.cu", []),
 ]
 
 
@@ -28,7 +29,7 @@ def _newer(target, deps):
 def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    hdrs = [os.path.join(HERE, "hg_ctx.h"), os.path.join(HERE, "hg_device.cuh"), os.path.join(PKG, "..", "include", "hydrograd_b200.h"), __file__]
+    hdrs = [os.path.join(HERE, "hg_ctx.h"), os.path.join(HERE, "hg_device.cuh"), os.path.join(HERE, "hg_ude.h"), os.path.join(PKG, "..", "include", "hydrograd_b200.h"), __file__]
     objs = []
     for src, extra in SOURCES:
         s = os.path.join(HERE, src)

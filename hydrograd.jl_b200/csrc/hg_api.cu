@@ -127,8 +127,16 @@ static int no_closure(hg_ctx* ctx, const char* what) {
 
 static int bind_params(hg_ctx* ctx, const double* params, int64_t np, int32_t active) {
   hg_ctx* x = ext(ctx);
-  if (active < HG_PARAM_NONE || active > HG_PARAM_Q) { ctx->err = "bad active_param"; return HG_ERR_ARG; }
-  const int64_t want = active == HG_PARAM_ZB ? ctx->N : active == HG_PARAM_MANNING ? ctx->n_mat : active == HG_PARAM_Q ? ctx->n_inletq : 0;
+  if (active < HG_PARAM_NONE || active > HG_PARAM_UDE) { ctx->err = "bad active_param"; return HG_ERR_ARG; }
+  if (active == HG_PARAM_UDE) {
+    if (!ctx->ude_set) { ctx->err = "active parameter UDE: no model (call hg_set_ude_model first)"; return HG_ERR_ARG; }
+    if (ctx->opt.path == 1) { ctx->err = "active parameter UDE needs the fused path (strict = 0)"; return HG_ERR_ARG; }
+  } else if (ctx->ude_set && active != HG_PARAM_NONE) {
+    ctx->err = "a UDE model is set: the active parameter must be UDE or NONE";
+    return HG_ERR_ARG;
+  }
+  const int64_t want = active == HG_PARAM_ZB ? ctx->N : active == HG_PARAM_MANNING ? ctx->n_mat : active == HG_PARAM_Q ? ctx->n_inletq :
+                       active == HG_PARAM_UDE ? ctx->ude.n_params : 0;
   if (active != HG_PARAM_NONE && (np != want || !params)) {
     ctx->err = "params_vector has length " + std::to_string(np) + ", expected " + std::to_string(want);
     return HG_ERR_ARG;
@@ -140,7 +148,9 @@ static int bind_params(hg_ctx* ctx, const double* params, int64_t np, int32_t ac
                     (np == 0 || std::memcmp(params, x->last_params.data(), np * 8) == 0);
   if (same) return HG_OK;
   // restore pristine fields if the previous binding overwrote them
-  if (x->last_active > HG_PARAM_NONE && ctx->opt.path != 1) TRY(upload_fields(ctx));
+  // (a new theta over an old theta has nothing to restore: the network rewrites ManningN_cells in every RHS anyway)
+  if (x->last_active > HG_PARAM_NONE && ctx->opt.path != 1 && !(active == HG_PARAM_UDE && x->last_active == HG_PARAM_UDE))
+    TRY(upload_fields(ctx));
   x->last_active = active;
   x->last_params.assign(params, params + np);
   ctx->active = active;
@@ -152,6 +162,11 @@ static int bind_params(hg_ctx* ctx, const double* params, int64_t np, int32_t ac
     return HG_OK;
   }
   hg::FusedDev& d = ctx->fd;
+  if (active == HG_PARAM_UDE) {   // theta stays in its own small buffer; n of every cell is re-evaluated from the state by each RHS
+    CK(ctx, cudaMemcpyAsync(d.ude_theta.p, x->last_params.data(), np * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return HG_OK;
+  }
   CK(ctx, cudaMemcpyAsync(d.params.p, params, np * 8, cudaMemcpyHostToDevice, ctx->stream));
   if (active == HG_PARAM_Q) {
     CK(ctx, cudaMemcpyAsync(d.Qin.p, d.params.p, np * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -361,6 +376,7 @@ int hg_set_manning_function(hg_ctx* ctx, int32_t type, const double* params, con
     if (type == HG_MANNING_SIGMOID && !(m.h_mid > 0.0)) { ctx->err = "hg_set_manning_function: h_mid must be positive"; return HG_ERR_ARG; }   // :176
     if (type == HG_MANNING_H_UMAG_KS && !ks_cells) { ctx->err = "hg_set_manning_function: ks_cells is NULL"; return HG_ERR_ARG; }
     if (ctx->active == HG_PARAM_MANNING) { ctx->err = "hg_set_manning_function: ManningN is the active parameter"; return HG_ERR_ARG; }
+    if (ctx->ude_set) { ctx->err = "hg_set_manning_function: a UDE model is set"; return HG_ERR_ARG; }
     const int64_t N = ctx->N;
     std::vector<double> ks(N, 1.0);
     if (ks_cells) ks.assign(ks_cells, ks_cells + N);
@@ -372,6 +388,38 @@ int hg_set_manning_function(hg_ctx* ctx, int32_t type, const double* params, con
     }
   }
   ctx->mfn = m;
+  return HG_OK;
+}
+
+int hg_set_ude_model(hg_ctx* ctx, const hg_ude_desc* desc, const double* ks_cells) {
+  if (!ctx) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!desc) {   // clear: un-bind theta (restores the frozen ManningN_cells)
+    if (ctx->active == HG_PARAM_UDE) TRY(bind_params(ctx, nullptr, 0, HG_PARAM_NONE));
+    ctx->ude_set = false;
+    return HG_OK;
+  }
+  if (ctx->opt.path == 1) { ctx->err = "hg_set_ude_model needs the fused path (strict = 0)"; return HG_ERR_ARG; }
+  if (ctx->mfn.type != HG_MANNING_CONSTANT) { ctx->err = "hg_set_ude_model: a variable Manning's n closure is set"; return HG_ERR_ARG; }
+  if (ctx->active != HG_PARAM_NONE && ctx->active != HG_PARAM_UDE) { ctx->err = "hg_set_ude_model: another parameter is active"; return HG_ERR_ARG; }
+  if (ctx->ens_members > 0) { ctx->err = "hg_set_ude_model: not available for ensembles"; return HG_ERR_ARG; }
+  hg::ude::Model m;
+  if (const char* why = hg::ude::make_model(desc, m)) { ctx->err = std::string("hg_set_ude_model: ") + why; return HG_ERR_ARG; }
+  if (m.ln_mode == HG_LN_WHOLE_ARRAY && ctx->n_halo > 0) {
+    ctx->err = "hg_set_ude_model: HG_LN_WHOLE_ARRAY needs statistics over all ranks; not available on multi-rank contexts";
+    return HG_ERR_ARG;
+  }
+  if (m.n_in == 3 && !ks_cells) { ctx->err = "hg_set_ude_model: ks_cells is NULL"; return HG_ERR_ARG; }
+  if (ctx->active == HG_PARAM_UDE) TRY(bind_params(ctx, nullptr, 0, HG_PARAM_NONE));   // theta of the previous model is void
+  if (m.n_in == 3) {
+    std::vector<double> ks(ks_cells, ks_cells + ctx->N);
+    TRY(upN(ctx, ctx->fd.ks, permuted(ks.data(), ctx->fh.perm), (size_t)ctx->fh.Ns));
+  }
+  ctx->ude = m;
+  TRY(hg::ude_prepare(ctx));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->ude_set = true;
   return HG_OK;
 }
 
@@ -491,7 +539,8 @@ int hg_rhs(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32
   if (!ctx || !Q || !dQdt) return HG_ERR_ARG;
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
-  if (ctx->opt.path != 1 && ctx->fh.n_chunks > 1 && ctx->n_halo == 0) return rhs_pipelined(ctx, Q, dQdt);
+  // (the UDE network may need whole-array statistics of the state before any tile can run: no chunked pipeline)
+  if (ctx->opt.path != 1 && ctx->fh.n_chunks > 1 && ctx->n_halo == 0 && ctx->active != HG_PARAM_UDE) return rhs_pipelined(ctx, Q, dQdt);
   TRY(hg_set_state(ctx, Q));
   TRY(hg_rhs_resident(ctx));
   return hg_get_rhs(ctx, dQdt);
@@ -561,7 +610,7 @@ int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   TRY(bind_params(ctx, params, np, active));
   if (ctx->active != HG_PARAM_NONE && !pbar) { ctx->err = "hg_rhs_vjp: pbar is NULL"; return HG_ERR_ARG; }
   hg::FusedDev& d = ctx->fd;
-  if (ctx->fh.n_chunks > 1 && ctx->n_halo == 0) {
+  if (ctx->fh.n_chunks > 1 && ctx->n_halo == 0 && ctx->active != HG_PARAM_UDE) {
     TRY(vjp_pipelined(ctx, Q, lambda, Qbar));
   } else {
     TRY(hg_set_state(ctx, Q));
@@ -606,6 +655,7 @@ int hg_vjp_resident_phase(hg_ctx* ctx, int32_t phase) {
   const hg::FusedHost& fh = ctx->fh;
   const int cfg = hg::fused_cfg_id(ctx);
   if (phase == 1) {
+    if (ctx->active == HG_PARAM_UDE) TRY(hg::ude_eval_n(ctx, d.Q.p));
     if (ctx->n_inletq > 0) hg::fused_inlet_coef(ctx, d.Q.p);
     return hg::fused_vjp_tiles(ctx, cfg, d.Q.p, d.lam.p, d.Qbar.p, d.band_order.p, 0, fh.n_interior_tiles);
   }
@@ -668,6 +718,7 @@ int hg_ensemble_alloc(hg_ctx* ctx, int64_t M, int32_t per_member_manning) {
   if (!ctx || M <= 0) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "ensembles need the fused path"; return HG_ERR_ARG; }
   TRY(no_closure(ctx, "hg_ensemble_alloc"));
+  if (ctx->ude_set) { ctx->err = "hg_ensemble_alloc: not available while a UDE model is set"; return HG_ERR_ARG; }
   if ((int64_t)ctx->fh.n_tiles * M >= ((int64_t)1 << 31)) { ctx->err = "too many members for one launch"; return HG_ERR_ARG; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   hg::FusedDev& d = ctx->fd;

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/hydrograd_b200.h"
+#include "hg_ude.h"
 
 namespace hg {
 
@@ -174,6 +175,7 @@ struct FusedDev {
   DBuf<double> rk_k, rk_acc, rk_tmp;                                   // RK4 stages
   DBuf<double> ts_k[7], ts_new, ts_part, ts_sum;                       // Tsit5 stages, candidate state, error-norm scratch
   DBuf<double> halo_send, halo_recv;                                    // [6 * n_halo_entries]
+  DBuf<double> ude_theta, ude_stats, ude_part;                          // UDE network: parameters, LayerNorm statistics, partial sums
   DBuf<int32_t> err;
 };
 
@@ -197,6 +199,8 @@ struct hg_ctx {
   bool lam_set = false;
   hg::Consts c{};
   hg::MannFn mfn{};
+  hg::ude::Model ude{};        // hg_set_ude_model
+  bool ude_set = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -259,4 +263,8 @@ int fused_err_blocks(const hg_ctx* ctx);
 int fused_err_norm(hg_ctx* ctx, const double* u, const double* unew, int n, const double* const* k, const double* coef, double abstol,
                    double reltol, double* d_part, double* d_sum);
 int fused_rhs_ensemble(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
+// UDE closure (hg_ude.cu)
+int ude_prepare(hg_ctx* ctx);
+int ude_eval_n(hg_ctx* ctx, const double* d_Q);
+int ude_adjoint(hg_ctx* ctx, const double* d_Q, double* d_Qbar);
 }  // namespace hg

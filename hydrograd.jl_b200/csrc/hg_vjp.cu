@@ -901,6 +901,9 @@ int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar) {
     }
   } else if (ctx->active == HG_PARAM_Q) {
     cudaMemcpyAsync(d.pbar.p, d.Qinbar.p, ctx->n_inletq * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+  } else if (ctx->active == HG_PARAM_UDE) {   // nbar is final here (friction + inlet conveyance): pull it back through the network
+    const int rc = ude_adjoint(ctx, d_Q, d_Qbar);
+    if (rc != HG_OK) return rc;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ctx->err = std::string("fused_vjp launch: ") + cudaGetErrorString(e); return HG_ERR_CUDA; }
@@ -910,6 +913,10 @@ int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar) {
 
 // Qbar (internal order, [3Ns]) and the parameter adjoint for the active parameter (pbar, device).
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar) {
+  if (ctx->active == HG_PARAM_UDE) {
+    const int rc0 = ude_eval_n(ctx, d_Q);
+    if (rc0 != HG_OK) return rc0;
+  }
   if (ctx->n_inletq > 0) fused_inlet_coef(ctx, d_Q);
   const int rc = fused_vjp_tiles(ctx, cfg_id, d_Q, d_lam, d_Qbar, nullptr, 0, -1);
   return rc != HG_OK ? rc : fused_vjp_finish(ctx, d_Q, d_Qbar);

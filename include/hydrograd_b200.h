@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 2
+#define HG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define HG_API __attribute__((visibility("default")))
@@ -46,7 +46,9 @@ enum {
   HG_PARAM_NONE = 0,     /* forward simulation: params_vector unused                          */
   HG_PARAM_ZB = 1,       /* "zb":       params = zb_cells[N]        -> update_bed_data        */
   HG_PARAM_MANNING = 2,  /* "ManningN": params = n per zone[n_mat]  -> n_cells = p[matID+1]   */
-  HG_PARAM_Q = 3         /* "Q":        params = inletQ_TotalQ[n_inletq]                      */
+  HG_PARAM_Q = 3,        /* "Q":        params = inletQ_TotalQ[n_inletq]                      */
+  HG_PARAM_UDE = 4       /* bPerform_UDE: params = the network parameters [hg_ude_desc.n_params] of the
+                            model set by hg_set_ude_model (semi_discretize_swe_2D.jl:165-178)  */
 };
 
 /* error codes */
@@ -169,6 +171,50 @@ HG_API int hg_set_fields(hg_ctx* ctx, const double* ManningN_cells, const double
  * (ks per material zone gathered through matID, process_ManningN_2D.jl:56-60).  Forward simulation only, like the
  * reference: the VJP / adjoint / ensemble entry points and active = HG_PARAM_MANNING return HG_ERR_ARG while a closure is set. */
 HG_API int hg_set_manning_function(hg_ctx* ctx, int32_t type, const double* params, const double* ks_cells);
+
+/* ---- UDE: Manning's n of every cell from a small neural network of the cell's own state, the reference's
+ * settings.bPerform_UDE with UDE_choice "ManningN_h" / "ManningN_h_Umag_ks" (semi_discretize_swe_2D.jl:165-178 ->
+ * update_ManningN_UDE, parameters/process_ManningN_2D.jl:216-272).  The network is the one create_NN_model builds
+ * (UDE/process_UDE.jl:2-65): per hidden layer Dense(in, width, activation) followed by LayerNorm(width), then
+ * Dense(in, 1) and the bounded output  n = lo + (hi - lo) sigmoid(z).  Inputs are (h, |U|, ks) of the clamped state,
+ * each mapped to [-1, 1] by 2 (x - lo) / (hi - lo) - 1 (process_ManningN_2D.jl:233-240).  Lux (third party, Lux = "1.2.3",
+ * Project.toml:88) is absent from this image, so its layers are restated from their published definitions:
+ *   Dense      y = activation(W x + b), W [out x in] column-major;
+ *   LayerNorm  y = (x - mean) / sqrt(var + epsilon) * scale + bias, var uncorrected, epsilon = 1f-5, scale / bias [width].
+ *              Which entries `mean` and `var` run over is Lux's `dims`: the reference passes none, and Lux's default
+ *              `dims = Colon()` is documented as "over the whole input array" -- every hidden unit of EVERY cell of the
+ *              batch (HG_LN_WHOLE_ARRAY; n of one cell then depends on all cells through two scalars per layer, which
+ *              the kernels obtain with deterministic reductions).  HG_LN_PER_CELL normalises over the hidden units of
+ *              each cell (Lux `dims = 1`, the textbook layer norm).  The shim picks the mode from the layer's `dims`.
+ * With active_param = HG_PARAM_UDE, params_vector is the flat parameter vector theta (a ComponentArray of the Lux
+ * parameters); the off_* fields say where each array starts in it, so any flattening order works.  The VJP then returns
+ * pbar = d(lambda . rhs)/d theta and Qbar includes the path through n(Q).  (UDE_choice "FlowResistance",
+ * semi_discretize_swe_2D.jl:517-532, is not built.) */
+#define HG_UDE_MAX_HIDDEN 3
+#define HG_UDE_MAX_WIDTH 8
+enum { HG_UDE_MANNING_H = 1, HG_UDE_MANNING_H_UMAG_KS = 2 };
+enum { HG_ACT_IDENTITY = 0, HG_ACT_RELU = 1, HG_ACT_LEAKYRELU = 2, HG_ACT_SIGMOID = 3, HG_ACT_TANH = 4, HG_ACT_SOFTPLUS = 5 };
+enum { HG_LN_NONE = 0, HG_LN_PER_CELL = 1, HG_LN_WHOLE_ARRAY = 2 };
+typedef struct {
+  int32_t choice;                            /* HG_UDE_MANNING_H (input h) or HG_UDE_MANNING_H_UMAG_KS (h, |U|, ks) */
+  int32_t n_hidden;                          /* hidden_layers: 1 .. HG_UDE_MAX_HIDDEN                               */
+  int32_t width[HG_UDE_MAX_HIDDEN];          /* units per hidden layer, 1 .. HG_UDE_MAX_WIDTH                       */
+  int32_t activation[HG_UDE_MAX_HIDDEN];     /* HG_ACT_* of each hidden Dense (get_activation, process_UDE.jl:91-105) */
+  int32_t layernorm;                         /* HG_LN_*                                                             */
+  double ln_epsilon;                         /* Lux default 1f-5 = 9.999999747378752e-06                            */
+  double h_bounds[2], umag_bounds[2], ks_bounds[2], output_bounds[2];   /* UDE_NN_config                           */
+  int64_t n_params;                          /* length of theta                                                     */
+  int64_t off_weight[HG_UDE_MAX_HIDDEN + 1]; /* 0-based offsets into theta; entry n_hidden = the output Dense       */
+  int64_t off_bias[HG_UDE_MAX_HIDDEN + 1];
+  int64_t off_ln_scale[HG_UDE_MAX_HIDDEN];   /* ignored with HG_LN_NONE                                             */
+  int64_t off_ln_bias[HG_UDE_MAX_HIDDEN];
+} hg_ude_desc;
+
+/* Sets (desc != NULL) or clears (desc == NULL) the UDE model.  ks_cells[N] (reference order) is needed by
+ * HG_UDE_MANNING_H_UMAG_KS (process_ManningN_2D.jl:48-60).  While a model is set, HG_PARAM_UDE is the only active
+ * parameter accepted besides NONE (which then evaluates the RHS with the bound ManningN_cells, no network).  Not
+ * available on the strict path, for ensembles, or -- HG_LN_WHOLE_ARRAY only -- on multi-rank contexts. */
+HG_API int hg_set_ude_model(hg_ctx* ctx, const hg_ude_desc* desc, const double* ks_cells);
 
 /* dQdt = swe_2d_rhs(Q, params, t)   -- host buffers, reference cell order.
  * semi_discretize_swe_2D.jl:18-277.  `t` is accepted and unused exactly like the reference.      */

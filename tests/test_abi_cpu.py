@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(hg):
     nm = subprocess.run(["nm", "-D", "--defined-only", hg._lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (hg_\w+)", nm))
     assert declared <= exported
-    assert lib.hg_abi_version() == 2
+    assert lib.hg_abi_version() == 3
 
 
 def test_no_cpu_fallback(hg):
