@@ -67,7 +67,8 @@ def _descs(f: dict):
     return mesh, bc, fields, keep
 
 
-def _options(lib, device=0, tile_cells=256, reorder=True, strict=False, path=0, threads=0, vjp_variant=0, prefetch=0, face_blocks=True):
+def _options(lib, device=0, tile_cells=256, reorder=True, strict=False, path=0, threads=0, vjp_variant=0, prefetch=0, face_blocks=True,
+             ude_generic=False):
     opt = L.Options()
     lib.hg_default_options(C.byref(opt))
     opt.device, opt.tile_cells, opt.reorder, opt.strict, opt.path = device, tile_cells, int(reorder), int(strict), path
@@ -75,6 +76,7 @@ def _options(lib, device=0, tile_cells=256, reorder=True, strict=False, path=0, 
     opt.reserved[2] = int(vjp_variant)
     opt.reserved[3] = int(prefetch)
     opt.reserved[4] = 0 if face_blocks else 1
+    opt.reserved[5] = 1 if ude_generic else 0
     return opt
 
 
@@ -99,11 +101,11 @@ class Context:
     (see INTEGRATION.md for how the Julia structs map onto them)."""
 
     def __init__(self, flat: dict, device=0, tile_cells=256, reorder=True, strict=False, path=0, threads=0, vjp_variant=0, prefetch=0,
-                 face_blocks=True):
+                 face_blocks=True, ude_generic=False):
         self.lib = L.load()
         self._h = C.c_void_p()
         mesh, bc, fields, keep = _descs(flat)
-        opt = _options(self.lib, device, tile_cells, reorder, strict, path, threads, vjp_variant, prefetch, face_blocks)
+        opt = _options(self.lib, device, tile_cells, reorder, strict, path, threads, vjp_variant, prefetch, face_blocks, ude_generic)
         rc = self.lib.hg_create(C.byref(self._h), C.byref(mesh), C.byref(bc), C.byref(fields), C.byref(opt))
         del keep            # the library copied what it needs (ownership rule of the ABI)
         if rc:

@@ -136,7 +136,7 @@ static int bind_params(hg_ctx* ctx, const double* params, int64_t np, int32_t ac
     return HG_ERR_ARG;
   }
   const int64_t want = active == HG_PARAM_ZB ? ctx->N : active == HG_PARAM_MANNING ? ctx->n_mat : active == HG_PARAM_Q ? ctx->n_inletq :
-                       active == HG_PARAM_UDE ? ctx->ude.n_params : 0;
+                       active == HG_PARAM_UDE ? ctx->ude_user_params : 0;
   if (active != HG_PARAM_NONE && (np != want || !params)) {
     ctx->err = "params_vector has length " + std::to_string(np) + ", expected " + std::to_string(want);
     return HG_ERR_ARG;
@@ -405,7 +405,8 @@ int hg_set_ude_model(hg_ctx* ctx, const hg_ude_desc* desc, const double* ks_cell
   if (ctx->active != HG_PARAM_NONE && ctx->active != HG_PARAM_UDE) { ctx->err = "hg_set_ude_model: another parameter is active"; return HG_ERR_ARG; }
   if (ctx->ens_members > 0) { ctx->err = "hg_set_ude_model: not available for ensembles"; return HG_ERR_ARG; }
   hg::ude::Model m;
-  if (const char* why = hg::ude::make_model(desc, m)) { ctx->err = std::string("hg_set_ude_model: ") + why; return HG_ERR_ARG; }
+  hg::ude::ThetaMap map;
+  if (const char* why = hg::ude::make_model(desc, m, map)) { ctx->err = std::string("hg_set_ude_model: ") + why; return HG_ERR_ARG; }
   if (m.ln_mode == HG_LN_WHOLE_ARRAY && ctx->n_halo > 0) {
     ctx->err = "hg_set_ude_model: HG_LN_WHOLE_ARRAY needs statistics over all ranks; not available on multi-rank contexts";
     return HG_ERR_ARG;
@@ -417,6 +418,8 @@ int hg_set_ude_model(hg_ctx* ctx, const hg_ude_desc* desc, const double* ks_cell
     TRY(upN(ctx, ctx->fd.ks, permuted(ks.data(), ctx->fh.perm), (size_t)ctx->fh.Ns));
   }
   ctx->ude = m;
+  ctx->ude_map = map;
+  ctx->ude_user_params = desc->n_params;
   TRY(hg::ude_prepare(ctx));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->ude_set = true;

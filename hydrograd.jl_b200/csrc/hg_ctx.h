@@ -200,6 +200,8 @@ struct hg_ctx {
   hg::Consts c{};
   hg::MannFn mfn{};
   hg::ude::Model ude{};        // hg_set_ude_model
+  hg::ude::ThetaMap ude_map{};
+  int64_t ude_user_params = 0; // length of the caller's theta
   bool ude_set = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -265,6 +267,7 @@ int fused_err_norm(hg_ctx* ctx, const double* u, const double* unew, int n, cons
 int fused_rhs_ensemble(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 // UDE closure (hg_ude.cu)
 int ude_prepare(hg_ctx* ctx);
+int ude_spec_id(const hg_ctx* ctx);
 int ude_eval_n(hg_ctx* ctx, const double* d_Q);
 int ude_adjoint(hg_ctx* ctx, const double* d_Q, double* d_Qbar);
 }  // namespace hg

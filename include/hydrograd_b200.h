@@ -134,7 +134,8 @@ typedef struct {
                                       reserved[1]: unused;
                                       reserved[2]: launch-shape variant of the VJP kernel (0 = default), tuning only;
                                       reserved[3]: L2 prefetch distance in tiles (0 = one residency ahead, -1 = off);
-                                      reserved[4]: 1 = do not regroup a tile's faces into bank-conflict-free blocks of 16 */
+                                      reserved[4]: 1 = do not regroup a tile's faces into bank-conflict-free blocks of 16;
+                                      reserved[5]: 1 = run the UDE network through the generic (run-time shape) kernels */
 } hg_options;
 
 /* Manning's n as a function of the state, the reference's forward-simulation option ManningN_option = "variable"

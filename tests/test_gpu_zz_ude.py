@@ -174,3 +174,26 @@ def test_ude_error_behaviour_and_clearing(hg):
     strict = hg.Context(flat, strict=True)
     with pytest.raises(hg.HydrogradError, match="fused path"):
         strict.set_ude_model(pm)
+
+
+@pytest.mark.parametrize("choice,ln", [("ManningN_h", "whole"), ("ManningN_h_Umag_ks", "whole"), ("ManningN_h", "cell"), ("ManningN_h_Umag_ks", "cell")])
+def test_ude_specialised_kernels_agree_with_the_generic_ones(hg, choice, ln):
+    """The shapes the reference ships run kernels with a compile-time network shape (tape in registers); hg_options.reserved[5]
+    forces the generic kernels.  Same arithmetic in the same order: agreement to rounding (FMA contraction may differ)."""
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    pm, om, th = _models(choice, [3, 3], ["tanh", "tanh"], ln, seed=5)
+    rng = np.random.default_rng(12)
+    ks = rng.uniform(0.02, 0.3, N)
+    Q = _state(flat, 2)
+    lam = rng.standard_normal(3 * N)
+    out = []
+    for generic in (False, True):
+        ctx = hg.Context(flat, tile_cells=128, ude_generic=generic)
+        ctx.set_ude_model(pm, ks)
+        dQ = ctx.rhs(Q, th, "UDE")
+        Qbar, tbar = ctx.rhs_vjp(Q, lam, th, "UDE")
+        out.append((dQ, Qbar, tbar))
+    for a, b in zip(*out):
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()

@@ -66,25 +66,39 @@ def _case(choice, hidden, acts, ln, N=57, seed=3):
     return pm, om, th, Q, hstill, ks, 1e-3
 
 
-@pytest.mark.parametrize("choice,hidden,acts,ln", CONFIGS)
-def test_network_values_match_the_restatement(host, choice, hidden, acts, ln):
+# which compile-time instantiation (hg_ude.h HG_UDE_SPECS) serves each configuration; 0 = generic
+SPEC = [1, 2, 4, 0, 0, 0]
+
+
+def test_spec_offsets_equal_the_canonical_layout(host):
+    assert host.ude_host_spec_check() == 0
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("k", range(len(CONFIGS)))
+def test_network_values_match_the_restatement(host, k, generic):
+    choice, hidden, acts, ln = CONFIGS[k]
     pm, om, th, Q, hstill, ks, hs = _case(choice, hidden, acts, ln)
     N = hstill.size
     n = np.empty(N)
-    assert host.ude_host_manning(C.byref(pm.desc), C.c_int64(N), _p(Q), _p(hstill), _p(ks), C.c_double(hs), _p(th), _p(n)) == 0
+    spec = C.c_int(-1)
+    assert host.ude_host_manning(C.byref(pm.desc), C.c_int64(N), _p(Q), _p(hstill), _p(ks), C.c_double(hs), _p(th), _p(n),
+                                 generic, C.byref(spec)) == 0
+    assert spec.value == (0 if generic else SPEC[k])
     ref = om.manning(Q, th, hstill, ks, hs)
     assert ref.min() > 0.02 and ref.max() < 0.06 and np.ptp(ref) > 1e-4
     assert np.abs(n - ref).max() <= 1e-13 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("generic", [0, 1])
 @pytest.mark.parametrize("choice,hidden,acts,ln", CONFIGS)
-def test_network_pullback_matches_complex_step(host, choice, hidden, acts, ln):
+def test_network_pullback_matches_complex_step(host, choice, hidden, acts, ln, generic):
     pm, om, th, Q, hstill, ks, hs = _case(choice, hidden, acts, ln)
     N = hstill.size
     nbar = np.random.default_rng(5).normal(size=N)
     Qb, tb = np.zeros(3 * N), np.zeros(pm.n_params)
     assert host.ude_host_pullback(C.byref(pm.desc), C.c_int64(N), _p(Q), _p(hstill), _p(ks), C.c_double(hs), _p(th), _p(nbar),
-                                  _p(Qb), _p(tb)) == 0
+                                  _p(Qb), _p(tb), generic) == 0
     Qr, tr = om.pullback(Q, th, hstill, ks, hs, nbar)
     assert np.abs(tr).max() > 1e-4 and np.abs(Qr).max() > 1e-5
     assert np.abs(tb - tr).max() <= 1e-11 * np.abs(tr).max()
@@ -102,7 +116,7 @@ def test_descriptor_validation(host):
         setattr(d, field, val)
         N = 4
         z = np.zeros(3 * N)
-        assert host.ude_host_manning(C.byref(d), C.c_int64(N), _p(z), _p(np.ones(N)), None, C.c_double(1e-3), _p(np.zeros(64)), _p(np.zeros(N))) == 1
+        assert host.ude_host_manning(C.byref(d), C.c_int64(N), _p(z), _p(np.ones(N)), None, C.c_double(1e-3), _p(np.zeros(64)), _p(np.zeros(N)), 0, None) == 1
     with pytest.raises(ValueError, match="Unsupported activation"):
         hude.UDEModel("ManningN_h", dict(hidden_layers=[3], activations=["gelu"], h_bounds=[0, 1], output_bounds=[0, 1]))
     with pytest.raises(ValueError, match="Unknown UDE choice"):
