@@ -21,10 +21,11 @@
 module HydrogradB200
 
 using ChainRulesCore
+import ComponentArrays                      # only set_ude_model needs it (offsets of the Lux parameter arrays)
 
 const LIB = get(ENV, "HYDROGRAD_B200_LIB", joinpath(@__DIR__, "..", "libhydrograd_b200.so"))
 
-const HG_PARAM = Dict("" => Int32(0), "zb" => Int32(1), "ManningN" => Int32(2), "Q" => Int32(3))
+const HG_PARAM = Dict("" => Int32(0), "zb" => Int32(1), "ManningN" => Int32(2), "Q" => Int32(3), "UDE" => Int32(4))
 
 # ---- mirrors of the C structs (field order and types must match hydrograd_b200.h) ----------------
 struct MeshDesc
@@ -202,6 +203,54 @@ function set_manning_function(ctx::Context, kind::String, params::Dict, ks_cells
                    ctx.handle, Int32(MANNING_TYPES[kind]), p, ks)
         rc == 0 || error(unsafe_string(ccall((:hg_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.handle)))
     end
+    return nothing
+end
+
+# ---- UDE: Manning's n from the Lux network (settings.bPerform_UDE, UDE_choice "ManningN_h" / "ManningN_h_Umag_ks") ----------------
+# mirror of hg_ude_desc (include/hydrograd_b200.h); HG_UDE_MAX_HIDDEN = 3
+struct UdeDesc
+    choice::Int32; n_hidden::Int32
+    width::NTuple{3,Int32}; activation::NTuple{3,Int32}
+    layernorm::Int32
+    ln_epsilon::Float64
+    h_bounds::NTuple{2,Float64}; umag_bounds::NTuple{2,Float64}; ks_bounds::NTuple{2,Float64}; output_bounds::NTuple{2,Float64}
+    n_params::Int64
+    off_weight::NTuple{4,Int64}; off_bias::NTuple{4,Int64}; off_ln_scale::NTuple{3,Int64}; off_ln_bias::NTuple{3,Int64}
+end
+const UDE_CHOICE = Dict("ManningN_h" => Int32(1), "ManningN_h_Umag_ks" => Int32(2))
+const UDE_ACT = Dict("relu" => Int32(1), "leakyrelu" => Int32(2), "sigmoid" => Int32(3), "tanh" => Int32(4), "softplus" => Int32(5))
+_pad(v, n, T) = ntuple(i -> i <= length(v) ? T(v[i]) : T(0), n)
+
+"""
+    set_ude_model(ctx, UDE_settings, ps::ComponentVector, ks_cells; layernorm_dims = Colon())
+
+After this call `params_vector` of `swe_2d_rhs` / `swe_2d_rhs_vjp` is the flat vector of `ps` (the ComponentArray of
+`Lux.setup(rng, ude_model)[1]`, UDE/process_UDE.jl:42) and Manning's n is evaluated by the network on the device
+(semi_discretize_swe_2D.jl:165-178).  Offsets are read from the axes of `ps`: Lux names the layers of
+`Chain(Dense, LayerNorm, Dense, LayerNorm, ..., Dense, wrapper)` layer_1, layer_2, ...; a Dense holds (weight, bias), a
+LayerNorm (bias, scale).  `layernorm_dims` is the `dims` field of the LayerNorm layers (`Colon()`, Lux's default, normalises
+over the whole width x N array).
+"""
+function set_ude_model(ctx::Context, us, ps, ks_cells::Union{Vector{Float64},Nothing}; layernorm_dims=Colon())
+    cfg = us.UDE_NN_config
+    hidden = Int.(cfg["hidden_layers"]); acts = String.(cfg["activations"])
+    L = length(hidden)
+    flat = collect(Float64, ps)                       # the same flattening `getdata(ps)` gives the optimiser
+    off(layer, field) = first(ComponentArrays.label2index(ps, "layer_$(layer).$(field)")) - 1     # 0-based start in `flat`
+    offw = [off(2l - 1, :weight) for l in 1:L]; offb = [off(2l - 1, :bias) for l in 1:L]
+    push!(offw, off(2L + 1, :weight)); push!(offb, off(2L + 1, :bias))
+    offg = [off(2l, :scale) for l in 1:L]; offbe = [off(2l, :bias) for l in 1:L]
+    b2(key) = haskey(cfg, key) ? (Float64(cfg[key][1]), Float64(cfg[key][2])) : (0.0, 1.0)
+    desc = UdeDesc(UDE_CHOICE[us.UDE_choice], Int32(L), _pad(hidden, 3, Int32), _pad([UDE_ACT[a] for a in acts], 3, Int32),
+                   layernorm_dims isa Colon ? Int32(2) : Int32(1), Float64(1.0f-5),
+                   b2("h_bounds"), b2("Umag_bounds"), b2("ks_bounds"), b2("output_bounds"), length(flat),
+                   _pad(offw, 4, Int64), _pad(offb, 4, Int64), _pad(offg, 3, Int64), _pad(offbe, 3, Int64))
+    ks = ks_cells === nothing ? Ptr{Float64}(C_NULL) : pointer(ks_cells)
+    GC.@preserve ks_cells begin
+        rc = ccall((:hg_set_ude_model, LIB), Cint, (Ptr{Cvoid}, Ref{UdeDesc}, Ptr{Float64}), ctx.handle, Ref(desc), ks)
+        _check(rc, ctx.handle)
+    end
+    ctx.active = HG_PARAM["UDE"]
     return nothing
 end
 
