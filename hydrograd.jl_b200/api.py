@@ -258,6 +258,14 @@ class Context:
     def step_rk4(self, dt, nsteps=1):
         self._ck(self.lib.hg_step_rk4(self._h, float(dt), int(nsteps)))
 
+    def step_ode_euler(self, dt, nsteps=1):
+        """solve(prob, Euler(), dt=dt) steps (swe_2D_forward_simulation.jl:41): no dry mask, unlike step_euler."""
+        self._ck(self.lib.hg_step_ode_euler(self._h, float(dt), int(nsteps)))
+
+    def step_ab3(self, dt, nsteps=1, restart=False):
+        """solve(prob, AB3(), dt=dt) steps (swe_2D_forward_simulation.jl:47); the multistep history persists between calls."""
+        self._ck(self.lib.hg_step_ab3(self._h, float(dt), int(nsteps), int(bool(restart))))
+
     def solve_tsit5(self, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(), saveat="stop"):
         """solve(prob, Tsit5(), adaptive=adaptive, dt=dt, saveat=t_save; abstol, reltol) on the resident state
         (swe_2D_forward_simulation.jl:38-41); returns (saved states [len(t_save), 3N], stats dict).

@@ -451,6 +451,7 @@ int hg_set_state(hg_ctx* ctx, const double* Q) {
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->state_set = true;
+  ctx->ab3_step = 1;   // a new state voids the multistep history of hg_step_ab3
   return HG_OK;
 }
 
@@ -809,6 +810,7 @@ int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
   if (!ctx->state_set) { ctx->err = "hg_step_euler: no resident state"; return HG_ERR_STATE; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   if (ctx->opt.path == 1) { ctx->err = "hg_step_euler needs the fused path (path=0)"; return HG_ERR_ARG; }
+  ctx->ab3_step = 1;   // another stepper moves the state: hg_step_ab3 starts again
   hg::FusedDev& d = ctx->fd;
   for (int64_t s = 0; s < nsteps; ++s) {
     TRY(hg::fused_rhs(ctx, d.Q.p, d.Q2.p, true, dt));
@@ -821,6 +823,7 @@ int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps) {
   if (!ctx || nsteps < 0) return HG_ERR_ARG;
   if (!ctx->state_set) { ctx->err = "hg_step_rk4: no resident state"; return HG_ERR_STATE; }
   if (ctx->opt.path == 1) { ctx->err = "hg_step_rk4 needs the fused path (path=0)"; return HG_ERR_ARG; }
+  ctx->ab3_step = 1;   // another stepper moves the state: hg_step_ab3 starts again
   CK(ctx, cudaSetDevice(ctx->opt.device));
   hg::FusedDev& d = ctx->fd;
   const size_t n = 3 * (size_t)ctx->fh.Ns;
@@ -839,6 +842,61 @@ int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps) {
     TRY(hg::fused_rhs(ctx, d.rk_tmp.p, d.rk_k.p, false, 0.0));
     TRY(hg::fused_axpy(ctx, nullptr, nullptr, d.rk_k.p, 0.0, d.rk_acc.p, d.rk_acc.p, dt / 6.0));
     TRY(hg::fused_axpy(ctx, d.Q.p, d.Q.p, d.rk_acc.p, 1.0, nullptr, nullptr, 0.0));
+  }
+  return HG_OK;
+}
+
+// OrdinaryDiffEq's `Euler()` (swe_2D_forward_simulation.jl:41, swe_2D_inversion.jl:272-273): u+ = u + dt f(u), WITHOUT the
+// dry mask of the customized stepper (that one is hg_step_euler).
+int hg_step_ode_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
+  if (!ctx || nsteps < 0) return HG_ERR_ARG;
+  if (!ctx->state_set) { ctx->err = "hg_step_ode_euler: no resident state"; return HG_ERR_STATE; }
+  if (ctx->opt.path == 1) { ctx->err = "hg_step_ode_euler needs the fused path (path=0)"; return HG_ERR_ARG; }
+  ctx->ab3_step = 1;   // another stepper moves the state: hg_step_ab3 starts again
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  for (int64_t s = 0; s < nsteps; ++s) {
+    TRY(hg::fused_rhs(ctx, d.Q.p, d.dQ.p, false, 0.0));
+    TRY(hg::fused_axpy(ctx, d.Q.p, d.Q.p, d.dQ.p, dt, nullptr, nullptr, 0.0));
+  }
+  return HG_OK;
+}
+
+// OrdinaryDiffEq's `AB3()` (swe_2D_forward_simulation.jl:46-47, swe_2D_inversion.jl:274-275): three-step Adams-Bashforth
+//   u+ = u + dt/12 (23 f_n - 16 f_{n-1} + 5 f_{n-2}),
+// the first two steps by Ralston's second-order method  u+ = u + dt/4 (k1 + 3 f(u + 2/3 dt k1))  (AB3ConstantCache's
+// perform_step!).  One RHS launch per step once started; the two older slopes stay resident between calls (ts_k[1], ts_k[2]).
+int hg_step_ab3(hg_ctx* ctx, double dt, int64_t nsteps, int32_t restart) {
+  if (!ctx || nsteps < 0) return HG_ERR_ARG;
+  if (!ctx->state_set) { ctx->err = "hg_step_ab3: no resident state"; return HG_ERR_STATE; }
+  if (ctx->opt.path == 1) { ctx->err = "hg_step_ab3 needs the fused path (path=0)"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  const size_t n3 = 3 * (size_t)ctx->fh.Ns;
+  for (int m = 0; m < 4; ++m)
+    if (d.ts_k[m].n != n3) { TRY(al(ctx, d.ts_k[m], n3)); restart = 1; }
+  if (d.rk_tmp.n != n3) TRY(al(ctx, d.rk_tmp, n3));
+  if (restart) ctx->ab3_step = 1;
+  for (int64_t s = 0; s < nsteps; ++s) {
+    double* k1 = d.ts_k[0].p;
+    TRY(hg::fused_rhs(ctx, d.Q.p, k1, false, 0.0));
+    if (ctx->ab3_step <= 2) {
+      const double* ks1[1] = {k1};
+      const double c1[1] = {2.0 / 3.0 * dt};
+      TRY(hg::fused_lincomb(ctx, d.rk_tmp.p, d.Q.p, 1, ks1, c1));
+      TRY(hg::fused_rhs(ctx, d.rk_tmp.p, d.ts_k[3].p, false, 0.0));
+      const double* ks2[2] = {k1, d.ts_k[3].p};
+      const double c2[2] = {dt / 4.0, 3.0 * dt / 4.0};
+      TRY(hg::fused_lincomb(ctx, d.Q.p, d.Q.p, 2, ks2, c2));
+      std::swap(d.ts_k[0].p, ctx->ab3_step == 1 ? d.ts_k[2].p : d.ts_k[1].p);   // f_0 -> k3, f_1 -> k2
+      ctx->ab3_step++;
+    } else {
+      const double* ks3[3] = {k1, d.ts_k[1].p, d.ts_k[2].p};
+      const double c3[3] = {23.0 * dt / 12.0, -16.0 * dt / 12.0, 5.0 * dt / 12.0};
+      TRY(hg::fused_lincomb(ctx, d.Q.p, d.Q.p, 3, ks3, c3));
+      std::swap(d.ts_k[1].p, d.ts_k[2].p);   // k3 <- k2 (the old k3 buffer becomes free)
+      std::swap(d.ts_k[0].p, d.ts_k[1].p);   // k2 <- k1
+    }
   }
   return HG_OK;
 }
@@ -900,6 +958,7 @@ int solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, 
                                   {0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928},
                                   {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
                                   {0.0, 1.5, -4.0, 2.5}};
+  ctx->ab3_step = 1;   // the stage buffers double as hg_step_ab3's history
   int64_t n_acc = 0, n_rej = 0, n_rhs = 0;
   double t = t0, dt_ctrl = dt, qold = qoldinit;
   double* k[7];

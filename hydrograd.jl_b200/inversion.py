@@ -78,3 +78,11 @@ def loss_and_gradient(ctx, flat, Q0, params, active_param_name, observed, dt, ns
     else:
         _, _, pbar = ctx.rk_adjoint(method, Q0, lam, dt, nsteps, params, active_param_name)
     return loss, parts, pbar + dp
+
+
+def compute_loss_UDE(ctx, flat, Q0, theta, observed, dt, nsteps, method="Tsit5", bWSE=True, buv=True):
+    """compute_loss_UDE (src/applications/UDE/swe_2D_UDE.jl:522-599) and its gradient with respect to the network parameters:
+    the same WSE / velocity mismatch terms as the inversion loss (UDE_bWSE_loss, UDE_b_uv_loss), no bound term.  The model must
+    have been set with ctx.set_ude_model; every RHS of the forward and adjoint sweeps re-evaluates n = NN_theta(state) on the
+    device.  Returns (loss_total, parts, d loss / d theta)."""
+    return loss_and_gradient(ctx, flat, Q0, theta, "UDE", observed, dt, nsteps, method=method, bWSE=bWSE, buv=buv)

@@ -249,6 +249,16 @@ HG_API int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps);
  * in swe_2D_forward_simulation.jl:44), four fused RHS launches + three axpy kernels per step, no host round trip.   */
 HG_API int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps);
 
+/* The other explicit fixed-step solvers the control files accept (forward_simulation_ode_solver / inversion ode_solver:
+ * swe_2D_forward_simulation.jl:40-47, swe_2D_inversion.jl:272-275), on the resident state:
+ *   hg_step_ode_euler  OrdinaryDiffEq's `Euler()`: u+ = u + dt f(u) -- no dry mask, unlike hg_step_euler;
+ *   hg_step_ab3        OrdinaryDiffEq's `AB3()`: u+ = u + dt/12 (23 f_n - 16 f_{n-1} + 5 f_{n-2}), started with two steps of
+ *                      Ralston's method u+ = u + dt/4 (k1 + 3 f(u + 2/3 dt k1)).  The two older slopes stay on the device
+ *                      between calls; restart != 0, hg_set_state or any other solver call starts the sequence again.
+ * (`Rosenbrock23()` / `TRBDF2()` are implicit and not built.) */
+HG_API int hg_step_ode_euler(hg_ctx* ctx, double dt, int64_t nsteps);
+HG_API int hg_step_ab3(hg_ctx* ctx, double dt, int64_t nsteps, int32_t restart);
+
 /* Tsit5 (adaptive with OrdinaryDiffEq's PI controller, or fixed-step when adaptive = 0) on the resident state from t0 to
  * t1 -- `solve(prob, Tsit5(), adaptive=..., dt=dt, saveat=t_save; abstol=1e-6, reltol=1e-3)` of
  * swe_2D_forward_simulation.jl:38-41 / swe_2D_sensitivity.jl:38-43 without a host round trip per stage.  dt is the initial
