@@ -191,6 +191,14 @@ function solve_tsit5(ctx::Context, Q0::Vector{Float64}, tspan::Tuple{Float64,Flo
     return out, (accepted=stats[1], rejected=stats[2], rhs=stats[3])
 end
 
+# solve(prob, Euler() / RK4() / AB3(), dt=dt, ...) of swe_2D_forward_simulation.jl:40-47 on the resident state (hg_set_state first)
+step_ode_euler(ctx::Context, dt::Float64, nsteps::Integer) =
+    _check(ccall((:hg_step_ode_euler, LIB), Cint, (Ptr{Cvoid}, Float64, Int64), ctx.handle, dt, nsteps), ctx.handle)
+step_rk4(ctx::Context, dt::Float64, nsteps::Integer) =
+    _check(ccall((:hg_step_rk4, LIB), Cint, (Ptr{Cvoid}, Float64, Int64), ctx.handle, dt, nsteps), ctx.handle)
+step_ab3(ctx::Context, dt::Float64, nsteps::Integer; restart::Bool=false) =
+    _check(ccall((:hg_step_ab3, LIB), Cint, (Ptr{Cvoid}, Float64, Int64, Int32), ctx.handle, dt, nsteps, Int32(restart)), ctx.handle)
+
 # forward_settings.ManningN_option == "variable" (semi_discretize_swe_2D.jl:140-149): select the closure once; every
 # following RHS / Euler step evaluates n(h) / n(h, |U|, ks) on the device.  kind = ManningN_function_type of the control file.
 const MANNING_TYPES = Dict("constant" => 0, "power_law" => 1, "sigmoid" => 2, "inverse" => 3, "h_Umag_ks" => 4)
