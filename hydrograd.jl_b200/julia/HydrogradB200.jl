@@ -39,6 +39,7 @@ struct BcDesc
     n_inletq::Int64; n_exith::Int64; n_wall::Int64; n_symm::Int64
     bc_ptr::Ptr{Int64}; ghost_ids::Ptr{Int64}; internal_cells::Ptr{Int64}
     outward_normals::Ptr{Float64}; face_lengths::Ptr{Float64}
+    n_halo::Int64; halo_flip::Ptr{UInt8}; halo_area::Ptr{Float64}      # multi-GPU extension: 0 / NULL for one GPU
 end
 struct FieldsDesc
     g::Float64; k_n::Float64; h_small::Float64
@@ -116,7 +117,7 @@ function _create(px, device::Int32, tile::Int32, strict::Bool)
         mesh = MeshDesc(N, m.numOfFaces, m.numOfAllBounaryFaces, ld, Int32(1), pointer(nfaces), pointer(cellfaces),
                         pointer(neigh), pointer(normals), pointer(isb), pointer(flen), pointer(areas), pointer(cent))
         bcd = BcDesc(bc.nInletQ_BCs, bc.nExitH_BCs, bc.nWall_BCs, bc.nSymm_BCs, pointer(ptr), pointer(gh), pointer(ic),
-                     pointer(bnorm), pointer(len))
+                     pointer(bnorm), pointer(len), 0, Ptr{UInt8}(C_NULL), Ptr{Float64}(C_NULL))
         fld = FieldsDesc(c.g, c.k_n, c.h_small, Base.unsafe_convert(Cstring, solver),
                          pointer(px.hstill), pointer(px.hstill_ghostCells), pointer(px.zb_cells), pointer(px.zb_ghostCells),
                          pointer(S0), pointer(px.ManningN_cells), pointer(matid), nmat,
@@ -144,6 +145,13 @@ function swe_2d_rhs(dQdt::Vector{Float64}, Q::Vector{Float64}, params_vector::Ve
     return dQdt
 end
 swe_2d_rhs(Q::Vector{Float64}, p::Vector{Float64}, t::Float64, ctx::Context) = swe_2d_rhs(similar(Q), Q, p, t, ctx)
+# Parameters that are not a plain Vector{Float64} (the ComponentVector of the UDE network, a view handed over by an optimiser)
+# are flattened first; the cotangent returned by the rrule below is projected back onto the caller's type by ChainRulesCore.
+_plain(p::Vector{Float64}) = p
+_plain(p::AbstractVector) = collect(Float64, p)
+swe_2d_rhs(dQdt::Vector{Float64}, Q::AbstractVector, p::AbstractVector, t::Real, ctx::Context) =
+    swe_2d_rhs(dQdt, _plain(Q), _plain(p), Float64(t), ctx)
+swe_2d_rhs(Q::AbstractVector, p::AbstractVector, t::Real, ctx::Context) = swe_2d_rhs(Vector{Float64}(undef, length(Q)), Q, p, t, ctx)
 
 "Vector-Jacobian product (Qbar, pbar) = (dRHS/dQ)' * lambda, (dRHS/dp)' * lambda -- what Zygote.pullback returns (debug_AD.jl:60,75)."
 function swe_2d_rhs_vjp(Q::Vector{Float64}, params_vector::Vector{Float64}, t::Float64, lambda::Vector{Float64}, ctx::Context)
@@ -158,11 +166,13 @@ function swe_2d_rhs_vjp(Q::Vector{Float64}, params_vector::Vector{Float64}, t::F
     return Qbar, pbar[1:length(params_vector)]
 end
 
-function ChainRulesCore.rrule(::typeof(swe_2d_rhs), Q::Vector{Float64}, p::Vector{Float64}, t::Float64, ctx::Context)
-    y = swe_2d_rhs(Q, p, t, ctx)
+function ChainRulesCore.rrule(::typeof(swe_2d_rhs), Q::AbstractVector, p::AbstractVector, t::Real, ctx::Context)
+    Qv, pv = _plain(Q), _plain(p)
+    y = swe_2d_rhs(Qv, pv, Float64(t), ctx)
+    project_Q, project_p = ProjectTo(Q), ProjectTo(p)      # e.g. back onto the ComponentVector of the network parameters
     function pullback(ybar)
-        Qbar, pbar = swe_2d_rhs_vjp(Q, p, t, collect(Float64, unthunk(ybar)), ctx)
-        return NoTangent(), Qbar, (ctx.active == 0 ? ZeroTangent() : pbar), NoTangent(), NoTangent()
+        Qbar, pbar = swe_2d_rhs_vjp(Qv, pv, Float64(t), collect(Float64, unthunk(ybar)), ctx)
+        return NoTangent(), project_Q(Qbar), (ctx.active == 0 ? ZeroTangent() : project_p(pbar)), NoTangent(), NoTangent()
     end
     return y, pullback
 end
