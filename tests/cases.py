@@ -13,11 +13,13 @@ _STEMS = {
     "oneD_uniform": "oneD_channel_uniform_flow_refined",
     "simple": "simple",
     "oneD_bump_sens": "oneD_channel_with_bump_refined",
+    "oneD_uniform_sens": "oneD_channel_uniform_flow_refined",
 }
 _IC = {
     "oneD_bump": ("constant", [0.33, 0.2, 0.0, 0.0]),          # run_control.json of the case
     "oneD_bump_sens": ("constant", [0.33, 0.2, 0.0, 0.0]),
     "oneD_uniform": ("constant", [3.857205, 3.0, 0.0, 0.0]),
+    "oneD_uniform_sens": ("constant", [3.857205, 3.0, 0.0, 0.0]),
     "simple": ("constant", [1.0, 0.5, 0.0, 0.0]),
 }
 _cache = {}

@@ -6,7 +6,9 @@ The GPU box has no /root/reference, so everything the tests need is copied / con
   <case>/*.srhgeom|.srhhydro|.srhmat     mesh inputs, copied verbatim
   <case>/truth.npz                       arrays of forward_simulation_solution_truth.json (float64, exact)
   <case>/ic.npz                          forward_simulation_initial_condition.json (Savannah)
-  oneD_bump_sens/trajectory.npz          columns 0, 50, 100 of the 3N x 101 sensitivity trajectory
+  oneD_*_sens/trajectory.npz             columns 0, 50, 100 and eight early columns of the 3N x 101 trajectory that
+                                         swe_2D_sensitivity.jl:60-70 saves (the VALUES of a ForwardDiff.Dual solve)
+  oneD_*_sens/sensitivity.npz            sensitivity_results.json: d Q(T) / d ManningN zones (ForwardDiff.jacobian of the solve)
 
 JSON numbers are written by the reference with 17 significant digits, so the float64 values round-trip exactly.
 """
@@ -25,6 +27,7 @@ CASES = {
     "oneD_uniform": ("forward_simulation/oneD_channel_uniform_flow", "oneD_channel_uniform_flow_refined"),
     "simple": ("inversion/bathymetry_inversion/simple", "simple"),
     "oneD_bump_sens": ("sensitivity_analysis/ManningN/oneD_channel_with_bump", "oneD_channel_with_bump_refined"),
+    "oneD_uniform_sens": ("sensitivity_analysis/ManningN/oneD_channel_uniform_flow", "oneD_channel_uniform_flow_refined"),
 }
 
 

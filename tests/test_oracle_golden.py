@@ -253,3 +253,80 @@ def test_transient_of_reference_trajectory_with_dense_saveat(oracle_lib):
     err = [max(np.abs(g[:N] - w[:N]).max(), np.abs(g[N:2 * N] - w[N:2 * N]).max()) for g, w in zip(saves, ref)]
     print("dense saveat vs reference:", ["%.1e" % e for e in err], st)
     assert len(saves) == len(ref) and max(err) < 1e-3
+
+
+def _dual_rhs(o, p, K):
+    """The RHS on a vector of ForwardDiff.Dual numbers, stored as [1 + K, 3N]: values and the K partials (one dual-number
+    pass of the oracle per partial)."""
+    def rhs(U):
+        out = np.empty_like(U)
+        for k in range(K):
+            e = np.zeros(K)
+            e[k] = 1.0
+            f, jv = o.jvp(U[0], U[1 + k], p, e, 2)
+            out[1 + k] = jv
+        out[0] = f
+        return out
+    return rhs
+
+
+@pytest.mark.parametrize("name,p,dt_save,early_tol", [("oneD_bump_sens", [0.03, 0.02, 0.03], 2.0, (1e-8, 3e-9)),
+                                                      ("oneD_uniform_sens", [0.03, 0.03], 1.0, (2e-10, 1e-9, 3e-9))])
+def test_reference_trajectory_hard_pin(oracle_lib, name, p, dt_save, early_tol):
+    """HARD pin of a1-a6 on the reference's own saved transients.  The trajectories in sensitivity_analysis/ManningN/*/
+    forward_simulation_results.json are the values of a ForwardDiff.Dual solve (ForwardDiff.jacobian around `solve`,
+    swe_2D_sensitivity.jl:34-80), so OrdinaryDiffEq's error estimate -- hence every step size -- includes the partials
+    (tsit5_ref.dual_norm).  Integrating the oracle RHS on values AND partials (dual-number JVP), with the restated Tsit5, PI
+    controller (DiffEqBase's Float32 `fastpow`) and dense-output saveat, reproduces the reference's saved states to
+    1e-11 ... 1e-9 over the first saves (~100 accepted steps x 7 stages of RHS calls on an evolving transient) and to 2e-6
+    over the first 12 saves; later the Float32 rounding of the controller's powers (exp2 of this platform vs Julia's) lets
+    the step sequences drift apart at the 1e-7 level.  Measured: bump 1.4e-9, 3.8e-10; uniform 1.4e-11, 8.9e-11, 3.0e-10."""
+    from tests import tsit5_ref as T
+    c = cases.load(name)
+    tj = np.load(cases.GOLD + f"/{name}/trajectory.npz")
+    idx, ref = tj["early_index"], tj["forward_simulation_results_early"]
+    assert np.array_equal(tj["forward_simulation_results"][0], c.Q0)             # the reference started from the same state
+    o = Oracle(R.flatten(c))
+    p = np.array(p)
+    K, N = p.size, c.mesh.numOfCells
+    U0 = np.zeros((1 + K, 3 * N))
+    U0[0] = c.Q0
+    n = int(np.searchsorted(idx, 12, side="right"))
+    ts = dt_save * idx[:n]
+    # (integrate a little past the last save: the solve's end point is a stop that the reference does not have there)
+    _, saves, st = T.solve(_dual_rhs(o, p, K), U0, 0.0, float(ts[-1]) + 3 * dt_save, 0.02, True, 1e-6, 1e-3, ts, saveat="interp",
+                           norm=T.dual_norm, pow="fastpow")
+    err = [max(np.abs(s[0][:N] - w[:N]).max(), np.abs(s[0][N:2 * N] - w[N:2 * N]).max()) for s, w in zip(saves, ref)]
+    print(name, "dual-norm Tsit5 vs the reference's saved trajectory:", ["%.1e" % e for e in err], st)
+    assert np.abs(ref[0][:N] - c.Q0[:N]).max() > 1e-3                             # a real transient
+    for e, tol in zip(err, early_tol):
+        assert e <= tol
+    assert max(err) <= 2e-6
+    # the same solve with a real-valued error norm (what a plain forward run would do) is three orders further away
+    _, saves_r, _ = T.solve(lambda u: o.rhs(u, p, 2), c.Q0, 0.0, float(ts[1]) + 3 * dt_save, 0.02, True, 1e-6, 1e-3, ts[:2], saveat="interp",
+                            pow="fastpow")
+    assert np.abs(saves_r[0][:N] - ref[0][:N]).max() > 100 * err[0]
+
+
+@pytest.mark.parametrize("name,p,t_end", [("oneD_bump_sens", [0.03, 0.02, 0.03], 200.0), ("oneD_uniform_sens", [0.03, 0.03], 100.0)])
+def test_reference_final_state_and_sensitivity_through_the_whole_run(oracle_lib, name, p, t_end):
+    """The whole reference run (2100 / 2800 accepted steps): final state within 5e-5 of the saved one and the partials at the
+    final time -- d Q(T) / d ManningN, what ForwardDiff.jacobian returns into sensitivity_results.json -- within 2e-5 of the
+    largest entry (measured 1e-5 / 3.5e-6): pins the dual-number derivative of the oracle through thousands of RHS calls."""
+    from tests import tsit5_ref as T
+    c = cases.load(name)
+    tj = np.load(cases.GOLD + f"/{name}/trajectory.npz")
+    S = np.load(cases.GOLD + f"/{name}/sensitivity.npz")["sensitivity_results"]
+    o = Oracle(R.flatten(c))
+    p = np.array(p)
+    K, N = p.size, c.mesh.numOfCells
+    S = S.reshape(K, 3 * N)
+    U0 = np.zeros((1 + K, 3 * N))
+    U0[0] = c.Q0
+    U, _, st = T.solve(_dual_rhs(o, p, K), U0, 0.0, t_end, 0.02, True, 1e-6, 1e-3, (), saveat="interp", norm=T.dual_norm, pow="fastpow")
+    assert st["accepted"] > 2000 and st["rejected"] < 30
+    final = tj["forward_simulation_results"][2]
+    assert np.abs(U[0][:2 * N] - final[:2 * N]).max() <= 5e-5
+    for k in range(K):
+        assert np.abs(U[1 + k] - S[k]).max() <= 2e-5 * max(np.abs(S).max(), 1e-30), k
+    assert np.abs(S).max() > 0.5

@@ -9,6 +9,13 @@ OrdinaryDiffEq itself unpinned).  Restated from its published form:
   * error estimate: utilde = dt * sum(btilde_i k_i), EEst = sqrt(mean((utilde / (abstol + max(|u_prev|, |u|) reltol))^2));
   * step-size control: OrdinaryDiffEq's PIController with the explicit-RK defaults beta2 = 2/(5 p), beta1 = 7/(10 p) (p = 5),
     gamma = 9/10, qmin = 1/5, qmax = 10, qoldinit = 1e-4; accept when EEst <= 1;
+    The two powers are evaluated by DiffEqBase's `fastpow` in the OrdinaryDiffEq generation the reference ran
+    (DifferentialEquations 7.15): Float32 arithmetic, log2 by a rational approximation on the significand (Goldberg's "fast
+    approximate logarithms", (x-1)(a(x-1)+b)/((x-1)+c) after reducing the significand to [0.75, 1.5)), then exp2 -- about
+    1e-5 relative error, i.e. step sizes that differ from the exact-power controller in the fifth digit.  `pow="fastpow"`
+    restates it; it is what makes the reference's saved trajectories reproducible to 1e-11 ... 1e-9 over the first saves
+    instead of 1e-9 ... 1e-7 (tests/test_oracle_golden.py::test_reference_trajectory_hard_pin).  `pow="exact"` (default, and what
+    hg_solve_tsit5 does) uses the correctly rounded power;
   * saveat: OrdinaryDiffEq does NOT stop at the save times; after every accepted step it evaluates Tsit5's fourth-order
     dense output u(t + theta h) = u + h sum_i b_i(theta) k_i at the save times the step has passed (savevalues!), and
     copies u when a save time coincides with the step end.  `saveat="interp"` (hg_solve_tsit5_dense) restates that; the
@@ -45,8 +52,44 @@ def interp_weights(theta):
     return [theta * (r[0] + theta * (r[1] + theta * (r[2] + theta * r[3]))) for r in INTERP]
 
 
-def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(), saveat="stop"):
+def fastpow(x, y):
+    """DiffEqBase.fastpow(x::Float64, y::Float64): Float32(x), Float32(y), fastlog2, exp2 (restated; see the header)."""
+    if x == 0.0:
+        return 0.0
+    f32 = np.float32
+    a, b, c = f32(0.338953), f32(2.198599), f32(1.523692)
+    ux = int(np.array([x], dtype=np.float32).view(np.uint32)[0])
+    ex = (ux & 0x7F800000) >> 23
+    if ux & 0x00400000:                      # significand >= 1.5: halve it (exponent field 126), compensate in the exponent
+        sig = np.array([(ux & 0x007FFFFF) | 0x3F000000], dtype=np.uint32).view(np.float32)[0]
+        fexp = f32(ex - 126)
+    else:
+        sig = np.array([(ux & 0x007FFFFF) | 0x3F800000], dtype=np.uint32).view(np.float32)[0]
+        fexp = f32(ex - 127)
+    sg = f32(sig - f32(1.0))
+    lg2 = f32(fexp + f32(f32(sg * f32(f32(a * sg) + b)) / f32(sg + c)))
+    return float(np.exp2(f32(f32(y) * lg2)))
+
+
+def default_norm(ut, u, unew, abstol, reltol):
+    """EEst of a real state: ODE_DEFAULT_NORM of calculate_residuals(utilde, uprev, u, abstol, reltol)."""
+    return float(np.sqrt(np.mean((ut / (abstol + np.maximum(np.abs(u), np.abs(unew)) * reltol)) ** 2)))
+
+
+def dual_norm(ut, u, unew, abstol, reltol):
+    """EEst when the state is a vector of ForwardDiff.Dual numbers (what ForwardDiff.jacobian over `solve` produces in
+    swe_2D_sensitivity.jl:34-80), stored here as an array of shape (1 + K, n): row 0 the values, rows 1..K the partials.
+    DiffEqBase's ForwardDiff rules: the internal norm of one Dual is sqrt(value^2 + sum(partials^2)), so the residual of
+    entry i is utilde_i / (abstol + max(|uprev_i|, |u_i|) reltol) with those norms in the (real) denominator, and the norm of
+    the residual vector is sqrt(sum over values AND partials of the squares / totallength) with totallength = n (1 + K)."""
+    den = abstol + np.maximum(np.sqrt((u * u).sum(0)), np.sqrt((unew * unew).sum(0))) * reltol
+    r = ut / den[None, :]
+    return float(np.sqrt((r * r).sum() / r.size))
+
+
+def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(), saveat="stop", norm=default_norm, pow="exact"):
     """Returns (u(t1), [u(t) for t in t_save], stats).  rhs(u) -> du/dt (autonomous: the reference RHS ignores t)."""
+    power = {"exact": lambda x, y: x ** y, "fastpow": fastpow}[pow]
     assert saveat in ("stop", "interp")
     u = np.array(u0, dtype=np.float64)
     t = float(t0)
@@ -93,12 +136,12 @@ def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(
             ut = np.zeros_like(u)
             for i in range(7):
                 ut += (h * BTILDE[i]) * k[i]
-            eest = float(np.sqrt(np.mean((ut / (abstol + np.maximum(np.abs(u), np.abs(unew)) * reltol)) ** 2)))
+            eest = norm(ut, u, unew, abstol, reltol)
             if eest == 0.0:
                 q11, q = 0.0, 1.0 / QMAX
             else:
-                q11 = eest ** BETA1
-                q = q11 / qold ** BETA2
+                q11 = power(eest, BETA1)
+                q = q11 / power(qold, BETA2)
                 q = max(1.0 / QMAX, min(1.0 / QMIN, q / GAMMA))
             if eest <= 1.0:
                 dense_saves()
