@@ -330,3 +330,43 @@ def test_reference_final_state_and_sensitivity_through_the_whole_run(oracle_lib,
     for k in range(K):
         assert np.abs(U[1 + k] - S[k]).max() <= 2e-5 * max(np.abs(S).max(), 1e-30), k
     assert np.abs(S).max() > 0.5
+
+
+def reference_step_sequence(name, p, dt_save, n_saves):
+    """The step sizes of the reference's sensitivity run, recovered by the Dual solve of test_reference_trajectory_hard_pin."""
+    from tests import tsit5_ref as T
+    c = cases.load(name)
+    o = Oracle(R.flatten(c))
+    p = np.array(p)
+    K, N = p.size, c.mesh.numOfCells
+    U0 = np.zeros((1 + K, 3 * N))
+    U0[0] = c.Q0
+    steps = []
+    T.solve(_dual_rhs(o, p, K), U0, 0.0, dt_save * (n_saves + 3), 0.02, True, 1e-6, 1e-3, (), saveat="interp", norm=T.dual_norm,
+            pow="fastpow", record=steps)
+    return steps
+
+
+def test_replaying_the_recovered_step_sequence_with_values_only(oracle_lib):
+    """The reference's saved values depend on the partials only through the step sizes: replaying the recovered (t, h)
+    sequence with a plain value-only Tsit5 step + dense output gives the same saves.  (This is the logic
+    tests/test_gpu_zz_reference_trajectory.py runs with the CUDA RHS in place of the oracle.)"""
+    from tests import tsit5_ref as T
+    name, p, dt_save = "oneD_uniform_sens", np.array([0.03, 0.03]), 1.0
+    c = cases.load(name)
+    N = c.mesh.numOfCells
+    ref = np.load(cases.GOLD + f"/{name}/trajectory.npz")["forward_simulation_results_early"]
+    o = Oracle(R.flatten(c))
+    steps = reference_step_sequence(name, p, dt_save, 3)
+    state = {"u": c.Q0.copy()}
+
+    def step(t0, t1, h, inside):
+        u, saves, st = T.solve(lambda v: o.rhs(v, p, 2), state["u"], t0, t1, h, adaptive=False, t_save=inside, saveat="interp")
+        assert st["accepted"] == 1
+        state["u"] = u
+        return saves
+
+    got = T.replay(step, steps, dt_save * np.array([1, 2, 3]))
+    assert len(got) == 3
+    for g, w, tol in zip(got, ref, (2e-10, 1e-9, 3e-9)):
+        assert max(np.abs(g[:N] - w[:N]).max(), np.abs(g[N:2 * N] - w[N:2 * N]).max()) <= tol

@@ -87,8 +87,10 @@ def dual_norm(ut, u, unew, abstol, reltol):
     return float(np.sqrt((r * r).sum() / r.size))
 
 
-def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(), saveat="stop", norm=default_norm, pow="exact"):
-    """Returns (u(t1), [u(t) for t in t_save], stats).  rhs(u) -> du/dt (autonomous: the reference RHS ignores t)."""
+def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(), saveat="stop", norm=default_norm, pow="exact",
+          record=None):
+    """Returns (u(t1), [u(t) for t in t_save], stats).  rhs(u) -> du/dt (autonomous: the reference RHS ignores t).
+    record: a list that receives (t, h) of every accepted step."""
     power = {"exact": lambda x, y: x ** y, "fastpow": fastpow}[pow]
     assert saveat in ("stop", "interp")
     u = np.array(u0, dtype=np.float64)
@@ -129,6 +131,8 @@ def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(
                             v += (h * b) * kk
                         saves[s_] = v
             if not adaptive:
+                if record is not None:
+                    record.append((t, h))
                 dense_saves()
                 u, t, k[0] = unew, tnew, k[6]
                 n_acc += 1
@@ -144,6 +148,8 @@ def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(
                 q = q11 / power(qold, BETA2)
                 q = max(1.0 / QMAX, min(1.0 / QMIN, q / GAMMA))
             if eest <= 1.0:
+                if record is not None:
+                    record.append((t, h))
                 dense_saves()
                 u, t, k[0] = unew, tnew, k[6]
                 n_acc += 1
@@ -158,3 +164,19 @@ def solve(rhs, u0, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(
         if saveat == "stop" or ts in [float(x) for x in t_save]:
             saves.setdefault(ts, u.copy())
     return u, [saves[float(x)] for x in t_save if float(x) in saves], dict(accepted=n_acc, rejected=n_rej, rhs=n_rhs)
+
+
+def replay(step, steps, t_save):
+    """Re-runs a recorded step sequence [(t, h)] with `step(t0, t1, h, saves_inside) -> [state at each save]` (one fixed
+    Tsit5 step from the current state, dense output at the save times inside it) and returns the saved states in order."""
+    pending = sorted(float(x) for x in t_save)
+    out = []
+    for t, h in steps:
+        t1 = t + h
+        inside = []
+        while pending and pending[0] <= t1:
+            inside.append(pending.pop(0))
+        out.extend(step(t, t1, h, inside))
+        if not pending:
+            break
+    return out
