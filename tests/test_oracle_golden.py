@@ -350,7 +350,7 @@ def reference_step_sequence(name, p, dt_save, n_saves):
 def test_replaying_the_recovered_step_sequence_with_values_only(oracle_lib):
     """The reference's saved values depend on the partials only through the step sizes: replaying the recovered (t, h)
     sequence with a plain value-only Tsit5 step + dense output gives the same saves.  (This is the logic
-    tests/test_gpu_zz_reference_trajectory.py runs with the CUDA RHS in place of the oracle.)"""
+    tests/test_gpu_zzz_reference_replay.py runs with the CUDA RHS in place of the oracle.)"""
     from tests import tsit5_ref as T
     name, p, dt_save = "oneD_uniform_sens", np.array([0.03, 0.03]), 1.0
     c = cases.load(name)
