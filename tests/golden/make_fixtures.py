@@ -8,6 +8,7 @@ The GPU box has no /root/reference, so everything the tests need is copied / con
   <case>/ic.npz                          forward_simulation_initial_condition.json (Savannah)
   oneD_*_sens/trajectory.npz             columns 0, 50, 100 and eight early columns of the 3N x 101 trajectory that
                                          swe_2D_sensitivity.jl:60-70 saves (the VALUES of a ForwardDiff.Dual solve)
+  savannah_sens/sensitivity.npz          sensitivity_results.json of sensitivity_analysis/ManningN/Savana_River (6 zones x 3N)
   oneD_*_sens/sensitivity.npz            sensitivity_results.json: d Q(T) / d ManningN zones (ForwardDiff.jacobian of the solve)
 
 JSON numbers are written by the reference with 17 significant digits, so the float64 values round-trip exactly.
@@ -50,8 +51,25 @@ def variable_n():
         np.savez_compressed(os.path.join(dst, "truth.npz"), **{k: np.array(v, dtype=np.float64) for k, v in d.items()})
 
 
+def savannah_sensitivity():
+    """sensitivity_results.json of the Savannah sensitivity run (same mesh / IC files as the forward case, byte-identical)."""
+    src = os.path.join(REF, "sensitivity_analysis/ManningN/Savana_River")
+    dst = os.path.join(HERE, "savannah_sens")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("savana_SI.srhgeom", "savana_SI.srhhydro", "savana_SI.srhmat", "forward_simulation_initial_condition.json"):
+        a = open(os.path.join(src, f), "rb").read()
+        b = open(os.path.join(REF, "forward_simulation/Savannah_River", f), "rb").read()
+        assert a == b, f
+    shutil.copyfile(os.path.join(src, "run_control.json"), os.path.join(dst, "run_control.json"))
+    os.chmod(os.path.join(dst, "run_control.json"), 0o644)
+    d = json.load(open(os.path.join(src, "sensitivity_results.json")))
+    np.savez_compressed(os.path.join(dst, "sensitivity.npz"),
+                        **{k: np.array(v, dtype=np.float64) for k, v in d.items() if not isinstance(v, str)})
+
+
 def main():
     variable_n()
+    savannah_sensitivity()
     for name, (rel, stem) in CASES.items():
         src = os.path.join(REF, rel)
         dst = os.path.join(HERE, name)

@@ -52,3 +52,31 @@ def test_device_replays_the_reference_run(hg, name, p, dt_save, early_tol):
     for e, tol in zip(err, early_tol):
         assert e <= tol
     assert max(err) <= 1e-5
+
+
+@pytest.mark.parametrize("variable_n", [False, True])
+def test_device_replays_the_savannah_forward_run(hg, variable_n):
+    """The reference's 200 s forward simulations on the Savannah River mesh (constant n, and Cheng's n(h, |U|, ks) evaluated
+    inside every RHS): the step sequence recovered on the host (tests/test_oracle_golden.py::
+    test_savannah_forward_run_reproduces_the_reference_final_state) replayed by the device, 202 fixed Tsit5 steps on the
+    resident state; the final state is compared with the reference's committed truth file.  Host figures: oracle 1.8e-9 /
+    1.0e-9, and 1e-12 relative noise on the RHS moves the replayed final state by 5e-10 (this run is not stability-limited)."""
+    from tests.test_oracle_golden import _savannah_ks_cells, savannah_forward_steps
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    t = cases.truth("savannah_ks" if variable_n else "savannah")
+    steps, u_host, _ = savannah_forward_steps(variable_n)
+    ctx = hg.Context(flat, tile_cells=128)
+    if variable_n:
+        ctx.set_manning_function("h_Umag_ks", ks_cells=_savannah_ks_cells())
+    ctx.set_state(c.Q0)
+    for t0, h in steps:
+        _, st = ctx.solve_tsit5(t0, t0 + h, h, adaptive=False)
+        assert st["accepted"] == 1
+    u = ctx.get_state()
+    den = u[:N] + flat["hstill"] + flat["h_small"]              # the reference saves u = q / (h + h_small)
+    err = (np.abs(u[:N] - t["xi_truth"]).max(), np.abs(u[N:2 * N] / den - t["u_truth"]).max(), np.abs(u[2 * N:] / den - t["v_truth"]).max())
+    print("device replay of the savannah forward run vs truth (xi, u, v):", ["%.1e" % e for e in err])
+    assert max(err) <= 1e-8
+    assert np.abs(u - u_host).max() <= 5e-9

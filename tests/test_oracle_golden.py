@@ -370,3 +370,81 @@ def test_replaying_the_recovered_step_sequence_with_values_only(oracle_lib):
     assert len(got) == 3
     for g, w, tol in zip(got, ref, (2e-10, 1e-9, 3e-9)):
         assert max(np.abs(g[:N] - w[:N]).max(), np.abs(g[N:2 * N] - w[N:2 * N]).max()) <= tol
+
+
+def _savannah_ks_cells():
+    import json
+    rc = json.load(open(os.path.join(cases.GOLD, "savannah_ks", "run_control.json")))
+    ks_zone = np.array(rc["forward_simulation_options"]["forward_simulation_ManningN_function_parameters"]["ks"])
+    return ks_zone[cases.load("savannah").matID]       # process_SRH_2D_input.jl:159-164, process_ManningN_2D.jl:56-60
+
+
+def savannah_forward_steps(variable_n):
+    """(oracle, recorded (t, h) of the accepted steps, final state) of the reference's Savannah forward simulation:
+    solve(prob, Tsit5(), adaptive=true, dt=0.02, saveat=...) over [0, 200] s (forward_simulation/Savannah_River*/run_control.json)
+    with a real-valued error norm and DiffEqBase's fastpow in the PI controller."""
+    from tests import tsit5_ref as T
+    c = cases.load("savannah")
+    o = Oracle(R.flatten(c))
+    if variable_n:
+        o.set_manning_function("h_Umag_ks", ks_cells=_savannah_ks_cells())
+    steps = []
+    try:
+        u, _, st = T.solve(lambda v: o.rhs(v), c.Q0, 0.0, 200.0, 0.02, True, 1e-6, 1e-3, (), saveat="interp", pow="fastpow", record=steps)
+    finally:
+        o.set_manning_function("constant")
+    return steps, u, st
+
+
+@pytest.mark.parametrize("variable_n", [False, True])
+def test_savannah_forward_run_reproduces_the_reference_final_state(oracle_lib, variable_n):
+    """HARD pin on the river mesh (1306 mixed triangles / quadrilaterals, six Manning zones, inlet-q / exit-h / walls, real
+    bathymetry): the reference's committed final state of its 200 s forward simulations -- xi_truth, u_truth, v_truth of
+    forward_simulation/Savannah_River (constant n) and Savannah_River_ManningN_ks_h_Umag (Cheng's n(h, |U|, ks) evaluated
+    inside every RHS, semi_discretize_swe_2D.jl:140-149) -- is reproduced by the oracle RHS under the restated adaptive Tsit5
+    to 2e-9 / 1e-9 after 202 accepted steps (1219 RHS calls).  With the exact power in the controller: 8e-8 / 1e-7."""
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    t = cases.truth("savannah_ks" if variable_n else "savannah")
+    steps, u, st = savannah_forward_steps(variable_n)
+    assert st["accepted"] > 150 and st["rejected"] <= 3
+    den = u[:N] + flat["hstill"] + flat["h_small"]              # the reference saves u = q / (h + h_small)
+    err = (np.abs(u[:N] - t["xi_truth"]).max(), np.abs(u[N:2 * N] / den - t["u_truth"]).max(), np.abs(u[2 * N:] / den - t["v_truth"]).max())
+    print("savannah forward run vs truth (xi, u, v):", ["%.1e" % e for e in err], st)
+    assert np.abs(u[:N] - c.Q0[:N]).max() > 1e-3                 # the state did move away from the initial condition
+    assert max(err) <= 1e-8
+
+
+def test_savannah_sensitivity_results_hard_pin(oracle_lib):
+    """d Q(T = 200 s) / d ManningN zones on the river mesh, `ForwardDiff.jacobian` of the adaptive solve
+    (sensitivity_analysis/ManningN/Savana_River/sensitivity_results.json): values and six partials carried by the oracle's
+    dual-number JVP through the restated Dual-norm Tsit5 agree with the reference to 4e-9 of the largest entry (entries up to
+    31.6; 202 accepted steps).  Pins the forward-mode derivative of a1-a7 -- friction, the inlet conveyance split through
+    n, the zone gather -- that the brute-force J^T lambda of the VJP tests is assembled from."""
+    from tests import tsit5_ref as T
+    c = cases.load("savannah")
+    o = Oracle(R.flatten(c))
+    z = np.load(os.path.join(cases.GOLD, "savannah_sens", "sensitivity.npz"))
+    p = z["params_vector"]
+    K, N = p.size, c.mesh.numOfCells
+    S = z["sensitivity_results"].reshape(K, 3 * N)
+    assert np.array_equal(p, c.ManningN_zone)
+    U0 = np.zeros((1 + K, 3 * N))
+    U0[0] = c.Q0
+
+    def rhs(U):
+        out = np.empty_like(U)
+        for k in range(K):
+            e = np.zeros(K)
+            e[k] = 1.0
+            f, jv = o.jvp(U[0], U[1 + k], p, e, 2, nthreads=0)
+            out[1 + k] = jv
+        out[0] = f
+        return out
+
+    U, _, st = T.solve(rhs, U0, 0.0, 200.0, 0.02, True, 1e-6, 1e-3, (), saveat="interp", norm=T.dual_norm, pow="fastpow")
+    err = [np.abs(U[1 + k] - S[k]).max() for k in range(K)]
+    print("savannah sensitivities vs reference:", ["%.1e" % e for e in err], "largest entry %.1f" % np.abs(S).max(), st)
+    assert np.abs(S).max() > 10.0 and np.abs(S[0]).max() == 0.0        # zone 0 (the default material) owns no cell
+    assert max(err) <= 2e-8 * np.abs(S).max()
