@@ -114,6 +114,8 @@ SYMBOLS = {
                                 c_i64p, c_i64p]),
     "hg_flush_l2": (C.c_int, [_vp]),
     "hg_set_ude_model": (C.c_int, [_vp, C.POINTER(UdeDesc), c_f64p]),
+    "hg_set_controller_pow": (C.c_int, [_vp, C.c_int32]),
+    "hg_fastpow": (C.c_double, [C.c_double, C.c_double]),
     "hg_step_ode_euler": (C.c_int, [_vp, C.c_double, C.c_int64]),
     "hg_step_ab3": (C.c_int, [_vp, C.c_double, C.c_int64, C.c_int32]),
 }

@@ -266,6 +266,10 @@ class Context:
         """solve(prob, AB3(), dt=dt) steps (swe_2D_forward_simulation.jl:47); the multistep history persists between calls."""
         self._ck(self.lib.hg_step_ab3(self._h, float(dt), int(nsteps), int(bool(restart))))
 
+    def set_controller_pow(self, mode):
+        """"exact" | "fastpow": how the PI controller of solve_tsit5 raises EEst and qold to their powers (hg_set_controller_pow)."""
+        self._ck(self.lib.hg_set_controller_pow(self._h, {"exact": 0, "fastpow": 1}[mode]))
+
     def solve_tsit5(self, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=(), saveat="stop"):
         """solve(prob, Tsit5(), adaptive=adaptive, dt=dt, saveat=t_save; abstol, reltol) on the resident state
         (swe_2D_forward_simulation.jl:38-41); returns (saved states [len(t_save), 3N], stats dict).

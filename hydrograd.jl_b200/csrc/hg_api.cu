@@ -901,6 +901,45 @@ int hg_step_ab3(hg_ctx* ctx, double dt, int64_t nsteps, int32_t restart) {
   return HG_OK;
 }
 
+// DiffEqBase.fastpow, the power OrdinaryDiffEq's PI controller used in the generation the reference ran (DifferentialEquations
+// 7.15): Float32 arithmetic, log2 from a rational approximation on the significand reduced to [0.75, 1.5) (Goldberg, "Fast
+// approximate logarithms", (s - 1)(a (s - 1) + b) / ((s - 1) + c)), then exp2.  ~1e-5 relative error -- enough to change
+// every step size in the fifth digit, which is why reproducing the reference's saved trajectories needs it.
+static float fastlog2f(float x) {
+  const float a = 0.338953f, b = 2.198599f, c = 1.523692f;
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  const int32_t ex = (int32_t)((u & 0x7F800000u) >> 23);
+  uint32_t u2;
+  float fexp;
+  if (u & 0x00400000u) {   // significand >= 1.5: halve it (exponent field 126) and compensate in the exponent
+    u2 = (u & 0x007FFFFFu) | 0x3F000000u;
+    fexp = (float)(ex - 126);
+  } else {
+    u2 = (u & 0x007FFFFFu) | 0x3F800000u;
+    fexp = (float)(ex - 127);
+  }
+  float sig;
+  std::memcpy(&sig, &u2, 4);
+  volatile float s = sig - 1.0f;                 // volatile: every operation rounded to Float32, no contraction
+  volatile float t1 = a * s;
+  volatile float t2 = t1 + b;
+  volatile float t3 = s * t2;
+  volatile float t4 = s + c;
+  volatile float t5 = t3 / t4;
+  return fexp + t5;
+}
+double hg_fastpow(double x, double y) {
+  if (x == 0.0) return 0.0;
+  volatile float e = (float)y * fastlog2f((float)x);
+  return (double)exp2f(e);
+}
+int hg_set_controller_pow(hg_ctx* ctx, int32_t mode) {
+  if (!ctx || mode < 0 || mode > 1) return HG_ERR_ARG;
+  ctx->controller_fastpow = mode == 1;
+  return HG_OK;
+}
+
 // Tsit5 (Tsitouras 2011) with OrdinaryDiffEq's PI step-size controller -- what the reference's forward and sensitivity
 // drivers run by default: solve(prob, Tsit5(), adaptive=..., dt=dt, saveat=t_save; abstol=1e-6, reltol=1e-3)
 // (swe_2D_forward_simulation.jl:38-41, swe_2D_sensitivity.jl:38-43).  Device-resident: seven fused RHS launches per step
@@ -991,8 +1030,8 @@ int solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, 
         if (!(eest == eest)) { ctx->err = "hg_solve_tsit5: the error estimate is NaN"; return HG_ERR_STATE; }
         if (eest == 0.0) { q11 = 0.0; q = 1.0 / qmax; }
         else {
-          q11 = std::pow(eest, beta1);
-          q = q11 / std::pow(qold, beta2);
+          q11 = ctx->controller_fastpow ? hg_fastpow(eest, beta1) : std::pow(eest, beta1);
+          q = q11 / (ctx->controller_fastpow ? hg_fastpow(qold, beta2) : std::pow(qold, beta2));
           q = std::max(1.0 / qmax, std::min(1.0 / qmin, q / gamma));
         }
         accept = eest <= 1.0;

@@ -182,7 +182,9 @@ end
 # (swe_2D_forward_simulation.jl:38-41).  Returns the saved states as a 3N x length(t_save) matrix, like Array(sol).
 # dense=true (default): OrdinaryDiffEq's saveat (steps independent of t_save, Tsit5 dense output); dense=false: save times are stops.
 function solve_tsit5(ctx::Context, Q0::Vector{Float64}, tspan::Tuple{Float64,Float64}, dt::Float64, t_save::Vector{Float64};
-                     adaptive::Bool=true, abstol::Float64=1e-6, reltol::Float64=1e-3, dense::Bool=true)
+                     adaptive::Bool=true, abstol::Float64=1e-6, reltol::Float64=1e-3, dense::Bool=true, fastpow::Bool=true)
+    # fastpow=true: the PI controller raises EEst / qold to their powers with DiffEqBase.fastpow like OrdinaryDiffEq did
+    _check(ccall((:hg_set_controller_pow, LIB), Cint, (Ptr{Cvoid}, Int32), ctx.handle, Int32(fastpow)), ctx.handle)
     n3 = length(Q0)
     out = Matrix{Float64}(undef, n3, length(t_save))
     stats = zeros(Int64, 3)

@@ -269,6 +269,13 @@ HG_API int hg_step_ab3(hg_ctx* ctx, double dt, int64_t nsteps, int32_t restart);
 HG_API int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol,
                           const double* t_save, int64_t n_save, double* Q_save, int64_t* stats);
 
+/* The powers EEst^beta1 and qold^beta2 of the PI controller: mode 0 (default) the correctly rounded pow; mode 1
+ * DiffEqBase's `fastpow` (Float32 rational-approximation log2 + exp2, ~1e-5 relative error), which OrdinaryDiffEq used in the
+ * generation the reference ran -- with it an adaptive solve follows OrdinaryDiffEq's own step sequence (the reference's
+ * committed Savannah forward runs are reproduced to 1e-9; with mode 0 to 1e-7).  hg_fastpow exposes the function. */
+HG_API int hg_set_controller_pow(hg_ctx* ctx, int32_t mode);
+HG_API double hg_fastpow(double x, double y);
+
 /* The same solve with OrdinaryDiffEq's saveat semantics (savevalues!, Tsit5's dense output `Tsit5Interp`): the steps do
  * not stop at the save times (only t1 is a stop); after every accepted step [t, t + h] the fourth-order interpolant
  * u + h sum_i b_i(theta) k_i, theta = (t_save - t) / h, is evaluated on the device for every save time the step has

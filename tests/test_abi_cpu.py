@@ -74,3 +74,24 @@ def test_synthetic_meshes_are_consistent():
     N = flat["n_cells"]
     rest = np.concatenate([np.full(N, 0.7), np.zeros(2 * N)])
     assert np.abs(Oracle(flat).rhs(rest)).max() < 1e-13                          # lake at rest
+
+
+def test_fastpow_of_the_library_is_the_restated_one(hg):
+    """hg_fastpow (the PI controller's power when hg_set_controller_pow(ctx, 1)) against tests/tsit5_ref.fastpow, the
+    restatement of DiffEqBase.fastpow that reproduces the reference's saved trajectories: same Float32 operations, so the
+    results agree to the last bit wherever glibc's exp2f and numpy's Float32 exp2 do -- they differ by one Float32 ulp in about a
+    fifth of the cases (neither is Julia's exp2 either: that last-ulp noise is what lets the restated step sequences drift away
+    from the reference's after ~100 steps)."""
+    from tests import tsit5_ref as T
+    lib = hg._lib.load()
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([np.exp(rng.uniform(np.log(1e-6), np.log(50.0), 4000)), [1e-4, 0.1875, 0.25, 0.5, 1.0, 1.5, 2.0]])
+    exact, worst = 0, 0.0
+    for x in xs:
+        for y in (7.0 / 50.0, 2.0 / 25.0):
+            a, b = lib.hg_fastpow(float(x), y), T.fastpow(float(x), y)
+            exact += a == b
+            worst = max(worst, abs(a - b) / b)
+            assert abs(a / x ** y - 1.0) < 2e-4                    # and it IS an approximation of the power
+    assert worst <= 1.3e-7 and exact >= 0.6 * 2 * xs.size
+    assert lib.hg_fastpow(0.0, 0.14) == 0.0

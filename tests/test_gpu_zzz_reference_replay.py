@@ -80,3 +80,33 @@ def test_device_replays_the_savannah_forward_run(hg, variable_n):
     print("device replay of the savannah forward run vs truth (xi, u, v):", ["%.1e" % e for e in err])
     assert max(err) <= 1e-8
     assert np.abs(u - u_host).max() <= 5e-9
+
+
+@pytest.mark.parametrize("variable_n", [False, True])
+def test_device_adaptive_solve_with_fastpow_lands_on_the_reference_final_state(hg, variable_n):
+    """No replay: the device's own adaptive Tsit5 (error norm reduced on the device, PI controller on the host) with
+    hg_set_controller_pow(ctx, 1) follows OrdinaryDiffEq's step sequence by itself and lands on the reference's committed
+    Savannah final states; with the exact power (the default) the same solve is ~1e-7 away (host figures 8e-8 / 1e-7)."""
+    from tests.test_oracle_golden import _savannah_ks_cells, savannah_forward_steps
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    t = cases.truth("savannah_ks" if variable_n else "savannah")
+    _, _, st_host = savannah_forward_steps(variable_n)
+    err = {}
+    for mode in ("fastpow", "exact"):
+        ctx = hg.Context(flat, tile_cells=128)
+        if variable_n:
+            ctx.set_manning_function("h_Umag_ks", ks_cells=_savannah_ks_cells())
+        ctx.set_controller_pow(mode)
+        ctx.set_state(c.Q0)
+        _, st = ctx.solve_tsit5(0.0, 200.0, 0.02, True, 1e-6, 1e-3)
+        u = ctx.get_state()
+        den = u[:N] + flat["hstill"] + flat["h_small"]
+        err[mode] = max(np.abs(u[:N] - t["xi_truth"]).max(), np.abs(u[N:2 * N] / den - t["u_truth"]).max(),
+                        np.abs(u[2 * N:] / den - t["v_truth"]).max())
+        if mode == "fastpow":
+            assert st == st_host, (st, st_host)
+    print("device adaptive solve vs the reference's final state:", {k: "%.1e" % v for k, v in err.items()})
+    assert err["fastpow"] <= 2e-8
+    assert err["exact"] <= 1e-6
