@@ -7,8 +7,8 @@ dense output).  The device RHS then has to reproduce the reference's saved state
 1e-5 through the first 12.  Both channel runs are stability-limited (the controller sits at a constant error estimate), so
 rounding-level differences in the RHS are amplified along the way: on the host, 1e-12 relative noise on the oracle RHS moves
 the replayed saves by 3e-10 ... 3e-9 early and up to 3e-6 later, which is what the tolerances leave room for (the oracle
-itself: 2e-11 ... 1e-9 early; CPU check of the replay logic: test_replaying_the_recovered_step_sequence_with_values_only).  (Written after the round's GPU budget was spent: not yet run
-on a B200; every device entry point it uses is exercised by tests/test_gpu_tsit5.py.)"""
+itself: 2e-11 ... 1e-9 early; CPU check of the replay logic: test_replaying_the_recovered_step_sequence_with_values_only).
+(Written after the round's GPU budget was spent: not yet run on a B200; every device entry point it uses is exercised by tests/test_gpu_tsit5.py.)"""
 import numpy as np
 import pytest
 
@@ -78,8 +78,8 @@ def test_device_replays_the_savannah_forward_run(hg, variable_n):
     den = u[:N] + flat["hstill"] + flat["h_small"]              # the reference saves u = q / (h + h_small)
     err = (np.abs(u[:N] - t["xi_truth"]).max(), np.abs(u[N:2 * N] / den - t["u_truth"]).max(), np.abs(u[2 * N:] / den - t["v_truth"]).max())
     print("device replay of the savannah forward run vs truth (xi, u, v):", ["%.1e" % e for e in err])
-    assert max(err) <= 1e-8
-    assert np.abs(u - u_host).max() <= 5e-9
+    assert max(err) <= 2e-8
+    assert np.abs(u - u_host).max() <= 2e-8
 
 
 @pytest.mark.parametrize("variable_n", [False, True])
