@@ -86,6 +86,9 @@ SYMBOLS = {
                                    c_f64p]),
     "hg_rk_adjoint": (C.c_int, [_vp, C.c_int32, c_f64p, c_f64p, C.c_int64, C.c_int32, C.c_double, C.c_int64, c_f64p, c_f64p, c_f64p,
                                 c_f64p]),
+    "hg_rk_adjoint_steps": (C.c_int, [_vp, C.c_int32, c_f64p, c_f64p, C.c_int64, C.c_int32, c_f64p, C.c_int64, c_f64p, c_f64p, c_f64p,
+                                      c_f64p]),
+    "hg_last_steps": (C.c_int, [_vp, c_f64p, C.c_int64, c_i64p]),
     "hg_custom_ode_solve": (C.c_int, [_vp, c_f64p, c_f64p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double,
                                       c_f64p, C.c_int64, c_i64p]),
     "hg_halo_info": (C.c_int, [_vp, c_i64p, c_i64p]),

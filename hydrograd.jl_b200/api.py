@@ -302,6 +302,23 @@ class Context:
                                         _p(_f64(lam_T)), _p(QT), _p(Q0bar), _p(pbar)))
         return QT, Q0bar, pbar[:n]
 
+    def rk_adjoint_steps(self, method, Q0, lam_T, steps, params=None, active=None):
+        """Discrete adjoint over the given step sizes (e.g. last_steps() of an adaptive solve): returns (Q_T, Q0bar, pbar)."""
+        p, n, a = self._params(params, active)
+        hs = _f64(steps)
+        QT, Q0bar, pbar = np.empty(3 * self.N), np.empty(3 * self.N), np.zeros(max(n, 1))
+        self._ck(self.lib.hg_rk_adjoint_steps(self._h, self.RK_METHODS[method], _p(_f64(Q0)), _p(p), n, a, _p(hs), hs.size,
+                                              _p(_f64(lam_T)), _p(QT), _p(Q0bar), _p(pbar)))
+        return QT, Q0bar, pbar[:n]
+
+    def last_steps(self):
+        """Accepted step sizes of the last solve_tsit5."""
+        n = C.c_int64(0)
+        self._ck(self.lib.hg_last_steps(self._h, None, 0, C.byref(n)))
+        h = np.empty(n.value)
+        self._ck(self.lib.hg_last_steps(self._h, _p(h), n.value, C.byref(n)))
+        return h
+
     def custom_ode_solve(self, Q0, params, active, t_start, t_end, dt):
         nsteps = int(np.floor((t_end - t_start) / dt + 1e-9)) + 1 if t_end >= t_start else 0
         sol = np.empty((max(nsteps, 1), 3 * self.N))   # row s = column s of the reference's 3N x nSaves `sol`

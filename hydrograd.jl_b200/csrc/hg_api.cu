@@ -998,6 +998,7 @@ int solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, 
                                   {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
                                   {0.0, 1.5, -4.0, 2.5}};
   ctx->ab3_step = 1;   // the stage buffers double as hg_step_ab3's history
+  ctx->last_steps.clear();
   int64_t n_acc = 0, n_rej = 0, n_rhs = 0;
   double t = t0, dt_ctrl = dt, qold = qoldinit;
   double* k[7];
@@ -1051,6 +1052,7 @@ int solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, 
         for (int m = 0; m < 7; ++m) k[m] = d.ts_k[m].p;
         t = tnew;
         ++n_acc;
+        ctx->last_steps.push_back(h);
         if (adaptive) {
           qold = std::max(eest, qoldinit);
           const double prop = h / q;
@@ -1166,9 +1168,9 @@ int rk_forward_step(hg_ctx* ctx, const RkTable& tb, double h, const double* un, 
 }
 }  // namespace
 
-int hg_rk_adjoint(hg_ctx* ctx, int32_t method, const double* Q0, const double* params, int64_t np, int32_t active, double dt,
-                  int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar) {
-  if (!ctx || !Q0 || !lambda_T || !Q0bar || nsteps < 1 || !(dt > 0.0) || method < 0 || method > 1) return HG_ERR_ARG;
+// hs[nsteps]: the step sizes (all equal for hg_rk_adjoint; the accepted steps of an adaptive solve for hg_rk_adjoint_steps)
+static int rk_adjoint_impl(hg_ctx* ctx, int32_t method, const double* Q0, const double* params, int64_t np, int32_t active,
+                           const double* hs, int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar) {
   if (ctx->opt.path == 1) { ctx->err = "hg_rk_adjoint needs the fused path"; return HG_ERR_ARG; }
   TRY(no_closure(ctx, "hg_rk_adjoint"));
   if (ctx->n_halo > 0) { ctx->err = "hg_rk_adjoint: multi-rank contexts are not supported"; return HG_ERR_ARG; }
@@ -1198,7 +1200,7 @@ int hg_rk_adjoint(hg_ctx* ctx, int32_t method, const double* Q0, const double* p
   TRY(hg_set_state(ctx, Q0));
   for (int64_t s = 0; s < nsteps; ++s) {
     if (s % C == 0) CK(ctx, cudaMemcpyAsync(ck.p + (s / C) * n3, d.Q.p, n3 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    TRY(rk_forward_step(ctx, tb, dt, d.Q.p, Y, K, d.Q2.p));
+    TRY(rk_forward_step(ctx, tb, hs[s], d.Q.p, Y, K, d.Q2.p));
     std::swap(d.Q.p, d.Q2.p);
   }
   if (Q_T) TRY(download3(ctx, d.Q.p, Q_T));
@@ -1210,9 +1212,10 @@ int hg_rk_adjoint(hg_ctx* ctx, int32_t method, const double* Q0, const double* p
   for (int64_t k = nck - 1; k >= 0; --k) {
     const int64_t s0 = k * C, s1 = std::min<int64_t>(nsteps, s0 + C);
     CK(ctx, cudaMemcpyAsync(seg.p, ck.p + k * n3, n3 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    for (int64_t s = s0; s < s1 - 1; ++s) TRY(rk_forward_step(ctx, tb, dt, seg.p + (s - s0) * n3, Y, K, seg.p + (s - s0 + 1) * n3));
+    for (int64_t s = s0; s < s1 - 1; ++s) TRY(rk_forward_step(ctx, tb, hs[s], seg.p + (s - s0) * n3, Y, K, seg.p + (s - s0 + 1) * n3));
     for (int64_t s = s1 - 1; s >= s0; --s) {
       const double* un = seg.p + (s - s0) * n3;
+      const double dt = hs[s];
       TRY(rk_forward_step(ctx, tb, dt, un, Y, K, d.Q2.p));                 // the step's stage states Y_1 .. Y_{s-1}
       for (int i = 0; i < tb.s; ++i) {                                     // kbar_i = h b_i lam
         const double* one[1] = {lam.p};
@@ -1232,6 +1235,29 @@ int hg_rk_adjoint(hg_ctx* ctx, int32_t method, const double* Q0, const double* p
   if (npar > 0) CK(ctx, cudaMemcpyAsync(pbar, pacc.p, npar * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   return check_err_flag(ctx);
+}
+
+int hg_rk_adjoint(hg_ctx* ctx, int32_t method, const double* Q0, const double* params, int64_t np, int32_t active, double dt,
+                  int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar) {
+  if (!ctx || !Q0 || !lambda_T || !Q0bar || nsteps < 1 || !(dt > 0.0) || method < 0 || method > 1) return HG_ERR_ARG;
+  const std::vector<double> hs((size_t)nsteps, dt);
+  return rk_adjoint_impl(ctx, method, Q0, params, np, active, hs.data(), nsteps, lambda_T, Q_T, Q0bar, pbar);
+}
+
+int hg_rk_adjoint_steps(hg_ctx* ctx, int32_t method, const double* Q0, const double* params, int64_t np, int32_t active,
+                        const double* h, int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar) {
+  if (!ctx || !Q0 || !lambda_T || !Q0bar || !h || nsteps < 1 || method < 0 || method > 1) return HG_ERR_ARG;
+  for (int64_t s = 0; s < nsteps; ++s)
+    if (!(h[s] > 0.0)) { ctx->err = "hg_rk_adjoint_steps: step sizes must be positive"; return HG_ERR_ARG; }
+  return rk_adjoint_impl(ctx, method, Q0, params, np, active, h, nsteps, lambda_T, Q_T, Q0bar, pbar);
+}
+
+int hg_last_steps(const hg_ctx* ctx, double* h, int64_t capacity, int64_t* n) {
+  if (!ctx || !n) return HG_ERR_ARG;
+  *n = (int64_t)ctx->last_steps.size();
+  if (h)
+    for (int64_t s = 0; s < std::min<int64_t>(capacity, *n); ++s) h[s] = ctx->last_steps[(size_t)s];
+  return HG_OK;
 }
 
 int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double t0,

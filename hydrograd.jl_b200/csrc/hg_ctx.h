@@ -204,6 +204,7 @@ struct hg_ctx {
   int64_t ude_user_params = 0; // length of the caller's theta
   bool ude_set = false;
   bool controller_fastpow = false;   // hg_set_controller_pow
+  std::vector<double> last_steps;    // accepted step sizes of the last hg_solve_tsit5 (hg_last_steps)
   int32_t ab3_step = 1;        // hg_step_ab3: 1, 2 = Ralston start-up steps, 3 = multistep formula
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -274,6 +274,23 @@ function set_ude_model(ctx::Context, us, ps, ks_cells::Union{Vector{Float64},Not
     return nothing
 end
 
+# Gradient of  lambda_T . Q(T)  through the adaptive Tsit5 solve that just ran on ctx (solve_tsit5): discrete adjoint over its
+# accepted steps (step sizes are constants of the differentiation).  Returns (Q_T, dL/dQ0, dL/dparams).
+function tsit5_adjoint(ctx::Context, Q0::Vector{Float64}, params_vector::Vector{Float64}, lambda_T::Vector{Float64})
+    n = Ref{Int64}(0)
+    _check(ccall((:hg_last_steps, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ref{Int64}), ctx.handle, C_NULL, 0, n), ctx.handle)
+    h = Vector{Float64}(undef, n[])
+    QT = similar(Q0); Q0bar = similar(Q0); pbar = zeros(max(length(params_vector), 1))
+    np = ctx.active == 0 ? 0 : length(params_vector)
+    GC.@preserve h Q0 params_vector lambda_T QT Q0bar pbar begin
+        _check(ccall((:hg_last_steps, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ref{Int64}), ctx.handle, h, length(h), n), ctx.handle)
+        _check(ccall((:hg_rk_adjoint_steps, LIB), Cint,
+                     (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                     ctx.handle, Int32(1), Q0, params_vector, np, ctx.active, h, length(h), lambda_T, QT, Q0bar, pbar), ctx.handle)
+    end
+    return QT, Q0bar, pbar[1:length(params_vector)]
+end
+
 function custom_ODE_solve(Q0::Vector{Float64}, params_vector::Vector{Float64}, tspan::Tuple{Float64,Float64}, dt::Float64, ctx::Context)
     nsave = length(tspan[1]:dt:tspan[2])
     sol = Matrix{Float64}(undef, 3 * ctx.N, nsave)

@@ -299,6 +299,15 @@ HG_API int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params,
 HG_API int hg_rk_adjoint(hg_ctx* ctx, int32_t method, const double* Q0, const double* params, int64_t np, int32_t active,
                          double dt, int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar);
 
+/* The same discrete adjoint over a GIVEN sequence of step sizes h[nsteps] -- in particular the accepted steps of an adaptive
+ * solve, which hg_last_steps returns after hg_solve_tsit5(_dense): the gradient of the reference's default integrator
+ * (`solve(prob, Tsit5(), adaptive=true, ...; sensealg=...)`, swe_2D_inversion.jl:339) with the step sizes held constant, as
+ * every discretise-then-differentiate adjoint does.  hg_last_steps: n receives the number of accepted steps, h (may be NULL)
+ * the first min(capacity, n) of them. */
+HG_API int hg_rk_adjoint_steps(hg_ctx* ctx, int32_t method, const double* Q0, const double* params, int64_t np, int32_t active,
+                               const double* h, int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar);
+HG_API int hg_last_steps(const hg_ctx* ctx, double* h, int64_t capacity, int64_t* n);
+
 /* custom_ODE_solve (custom_ODE_solvers.jl:36-95): steps over t_start:dt:t_end, saving every
  * state; sol is [3N x n_saves] column-major, n_saves_capacity columns available; *n_saves out.   */
 HG_API int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params,

@@ -110,3 +110,35 @@ def test_device_adaptive_solve_with_fastpow_lands_on_the_reference_final_state(h
     print("device adaptive solve vs the reference's final state:", {k: "%.1e" % v for k, v in err.items()})
     assert err["fastpow"] <= 2e-8
     assert err["exact"] <= 1e-6
+
+
+def test_device_adjoint_through_the_reference_run_matches_its_sensitivities(hg):
+    """The device's REVERSE mode against the reference's published sensitivities.  sensitivity_results.json of the Savannah
+    case is d Q(200 s) / d ManningN (ForwardDiff through the adaptive solve, step sizes plain Float64: constants of the
+    differentiation).  The discrete adjoint of the same step sequence (hg_rk_adjoint_steps: checkpointed reverse sweep, one
+    hand-written VJP launch per Tsit5 stage, 202 steps) must return pbar = S lambda for any cotangent lambda of the final state."""
+    from tests.test_oracle_golden import savannah_sensitivity_solve
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    U, S, st, steps = savannah_sensitivity_solve()
+    hs = np.array([h for _, h in steps])
+    assert hs.size == st["accepted"] and abs(hs.sum() - 200.0) < 1e-9
+    rng = np.random.default_rng(3)
+    lam = rng.standard_normal(3 * N)
+    ctx = hg.Context(flat, tile_cells=128)
+    QT, Q0bar, pbar = ctx.rk_adjoint_steps("Tsit5", c.Q0, lam, hs, c.ManningN_zone, "ManningN")
+    assert np.abs(QT - U[0]).max() <= 2e-8                                # the forward sweep lands on the host's final state
+    want = S @ lam
+    scale = np.abs(S * lam[None, :]).sum(1)
+    print("device adjoint vs reference sensitivities:", ["%.1e" % (abs(a - b) / max(sc, 1e-300)) for a, b, sc in zip(pbar, want, scale)])
+    assert pbar[0] == 0.0 and want[0] == 0.0                              # zone 0 (default material) owns no cell
+    for k in range(1, S.shape[0]):
+        assert abs(pbar[k] - want[k]) <= 1e-6 * scale[k], k
+    # and the adaptive device solve hands out its own accepted steps for the same purpose
+    ctx.set_controller_pow("fastpow")
+    ctx.set_params(c.ManningN_zone, "ManningN")
+    ctx.set_state(c.Q0)
+    _, st_dev = ctx.solve_tsit5(0.0, 200.0, 0.02, True, 1e-6, 1e-3)
+    h_dev = ctx.last_steps()
+    assert h_dev.size == st_dev["accepted"] and abs(h_dev.sum() - 200.0) < 1e-9 and h_dev[0] == 0.02

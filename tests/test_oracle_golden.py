@@ -416,12 +416,9 @@ def test_savannah_forward_run_reproduces_the_reference_final_state(oracle_lib, v
     assert max(err) <= 1e-8
 
 
-def test_savannah_sensitivity_results_hard_pin(oracle_lib):
-    """d Q(T = 200 s) / d ManningN zones on the river mesh, `ForwardDiff.jacobian` of the adaptive solve
-    (sensitivity_analysis/ManningN/Savana_River/sensitivity_results.json): values and six partials carried by the oracle's
-    dual-number JVP through the restated Dual-norm Tsit5 agree with the reference to 4e-9 of the largest entry (entries up to
-    31.6; 202 accepted steps).  Pins the forward-mode derivative of a1-a7 -- friction, the inlet conveyance split through
-    n, the zone gather -- that the brute-force J^T lambda of the VJP tests is assembled from."""
+def savannah_sensitivity_solve():
+    """The reference's Savannah sensitivity run restated: values and six partials through the Dual-norm Tsit5.  Returns
+    (U[1 + K, 3N] at T = 200 s, the reference's sensitivity_results as [K, 3N], stats, recorded accepted steps [(t, h)])."""
     from tests import tsit5_ref as T
     c = cases.load("savannah")
     o = Oracle(R.flatten(c))
@@ -443,7 +440,19 @@ def test_savannah_sensitivity_results_hard_pin(oracle_lib):
         out[0] = f
         return out
 
-    U, _, st = T.solve(rhs, U0, 0.0, 200.0, 0.02, True, 1e-6, 1e-3, (), saveat="interp", norm=T.dual_norm, pow="fastpow")
+    steps = []
+    U, _, st = T.solve(rhs, U0, 0.0, 200.0, 0.02, True, 1e-6, 1e-3, (), saveat="interp", norm=T.dual_norm, pow="fastpow", record=steps)
+    return U, S, st, steps
+
+
+def test_savannah_sensitivity_results_hard_pin(oracle_lib):
+    """d Q(T = 200 s) / d ManningN zones on the river mesh, `ForwardDiff.jacobian` of the adaptive solve
+    (sensitivity_analysis/ManningN/Savana_River/sensitivity_results.json): values and six partials carried by the oracle's
+    dual-number JVP through the restated Dual-norm Tsit5 agree with the reference to 4e-9 of the largest entry (entries up to
+    31.6; 202 accepted steps).  Pins the forward-mode derivative of a1-a7 -- friction, the inlet conveyance split through
+    n, the zone gather -- that the brute-force J^T lambda of the VJP tests is assembled from."""
+    U, S, st, _ = savannah_sensitivity_solve()
+    K = S.shape[0]
     err = [np.abs(U[1 + k] - S[k]).max() for k in range(K)]
     print("savannah sensitivities vs reference:", ["%.1e" % e for e in err], "largest entry %.1f" % np.abs(S).max(), st)
     assert np.abs(S).max() > 10.0 and np.abs(S[0]).max() == 0.0        # zone 0 (the default material) owns no cell
