@@ -8,10 +8,15 @@
 //
 // PARITY PINNING: the reference cannot be executed here (Julia is absent from this image and from
 // the GPU box).  The setup side (zb, S0) and the friction formula are pinned bit-exactly / to
-// <= 6e-16 against the reference's committed truth JSONs (tests/test_oracle_golden.py); a single
-// swe_2d_rhs call and its derivative are pinned by NO reference fixture ("parity unpinned" for
-// a2/a3/a5/a12 in SURVEY.md section 8c) beyond the soft steady-state check on the committed
-// sensitivity trajectory.
+// <= 6e-16 against the reference's committed truth JSONs (tests/test_oracle_golden.py).  No reference
+// fixture holds the output of a SINGLE swe_2d_rhs call, but the committed results
+// of the reference's adaptive Tsit5 runs do pin this RHS and its forward-mode derivative once the solve is
+// restated the way it was produced (tests/tsit5_ref.py: Dual-aware error norm, DiffEqBase fastpow, dense
+// output): the saved channel transients are reproduced to 1e-11 ... 1e-9, the final states of the 200 s
+// Savannah River runs to 1e-9 and their ManningN sensitivities to 2.5e-9 (test_reference_trajectory_hard_pin,
+// test_savannah_forward_run_reproduces_the_reference_final_state, test_savannah_sensitivity_results_hard_pin).
+// Branches those runs do not reach (symmetry boundaries, some wet/dry fronts, the zb and Q parameter paths)
+// remain pinned by construction only.
 //
 // Reference files followed (relative to /root/reference/src):
 //   fvm/discretization/semi_discretize_swe_2D.jl          18-277, 281-434, 449-559
