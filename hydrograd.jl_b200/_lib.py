@@ -54,6 +54,10 @@ class UdeDesc(C.Structure):
                 ("off_ln_scale", C.c_int64 * UDE_MAX_HIDDEN), ("off_ln_bias", C.c_int64 * UDE_MAX_HIDDEN)]
 
 
+class NamedArray(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", c_f64p)]
+
+
 # every symbol include/hydrograd_b200.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 SYMBOLS = {
@@ -121,6 +125,25 @@ SYMBOLS = {
     "hg_fastpow": (C.c_double, [C.c_double, C.c_double]),
     "hg_step_ode_euler": (C.c_int, [_vp, C.c_double, C.c_int64]),
     "hg_step_ab3": (C.c_int, [_vp, C.c_double, C.c_int64, C.c_int32]),
+    "hg_format_f64": (C.c_int, [C.c_double, C.c_int32, C.c_char_p, C.c_int64]),
+    "hg_json_open": (C.c_int, [C.POINTER(_vp), C.c_char_p, C.c_int32, C.c_char_p, C.c_int64]),
+    "hg_json_error": (C.c_char_p, [_vp]),
+    "hg_json_key": (C.c_int, [_vp, C.c_char_p]),
+    "hg_json_begin_array": (C.c_int, [_vp]),
+    "hg_json_end_array": (C.c_int, [_vp]),
+    "hg_json_numbers": (C.c_int, [_vp, c_f64p, C.c_int64]),
+    "hg_json_number": (C.c_int, [_vp, C.c_double]),
+    "hg_json_string": (C.c_int, [_vp, C.c_char_p]),
+    "hg_json_close": (C.c_int, [_vp, C.c_int32]),
+    "hg_write_vtk_2d": (C.c_int, [C.c_char_p, C.c_int64, c_f64p, C.c_int64, C.c_int64, C.c_int32, c_i64p, c_i64p, C.c_char_p,
+                                  C.c_char_p, C.c_double, C.POINTER(NamedArray), C.c_int64, C.POINTER(NamedArray), C.c_int64,
+                                  C.c_char_p, C.c_int64]),
+    "hg_forward_truth_fields": (C.c_int, [C.c_int64, c_f64p, c_f64p, c_f64p, c_f64p, C.c_double, C.c_double, C.c_double,
+                                          c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "hg_manning_function_cells": (C.c_int, [C.c_int32, c_f64p, C.c_int64, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "hg_dry_wet_flags": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, c_i64p, c_i64p, c_i64p, c_u8p, C.c_int64, c_f64p, c_f64p,
+                                   C.c_double, c_u8p, c_u8p, c_u8p]),
+    "hg_total_water_volume": (C.c_double, [C.c_int64, c_f64p, c_f64p]),
 }
 
 _lib = None

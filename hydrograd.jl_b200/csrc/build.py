@@ -11,6 +11,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 SOURCES = [
     ("hg_host.cpp", []),
     ("hg_srh.cpp", []),
+    ("hg_results.cpp", []),
     ("hg_api.cu", []),
     ("hg_plain.cu", ["-fmad=false"]),      # reference evaluation order, no FMA contraction
     ("hg_fused.cu", []),

@@ -364,6 +364,56 @@ HG_API void hg_case_free(hg_case* c);
 HG_API int hg_case_dims(const hg_case* c, int64_t* dims /* [16] */);
 HG_API int hg_case_array(const hg_case* c, const char* name, const void** ptr, int64_t* count, int32_t* dtype /* 0 f64, 1 i64, 2 u8 */);
 
+/* ---- results writers and the derived fields of the forward driver, host only (csrc/hg_results.cpp): the output side
+ * of the path.  Replaces, for callers without the Julia package, postprocess_forward_simulation_results_swe_2D
+ * (applications/forward_simulation/process_forward_simulation_results_2D.jl:4-86), swe_2D_save_results_SciML and
+ * export_to_vtk_2D (utilities/swe_2D_tools.jl:10-98, 145-214), and the JSON3.pretty calls of the sensitivity driver
+ * (applications/sensitivity/swe_2D_sensitivity.jl:70,90).  Files are byte-compatible with the reference's: numbers are
+ * formatted the way Julia prints a Float64 (shortest round-trip digits, Base.Ryu.writeshortest's layout), and in JSON the
+ * way JSON3.pretty leaves them (whole values as integers).                                                        */
+enum { HG_FMT_JULIA = 0, HG_FMT_JSON3 = 1 };
+/* formats x into out (cap >= 32), NUL-terminated; returns the length, -1 on a bad argument */
+HG_API int hg_format_f64(double x, int32_t style, char* out, int64_t cap);
+
+/* streaming JSON3.pretty writer of one top-level object: key, then a number / string / (nested) array of numbers */
+typedef struct hg_json hg_json;
+/* style HG_FMT_JSON3: numbers as JSON3.pretty (JSON3 1.14) leaves them -- whole values as integers, except in arrays
+ * whose first element is not whole; HG_FMT_JULIA: every number as Julia prints a Float64 */
+HG_API int hg_json_open(hg_json** out, const char* path, int32_t style, char* err, int64_t errlen);
+HG_API const char* hg_json_error(const hg_json* w);
+HG_API int hg_json_key(hg_json* w, const char* key);
+HG_API int hg_json_begin_array(hg_json* w);
+HG_API int hg_json_end_array(hg_json* w);
+HG_API int hg_json_numbers(hg_json* w, const double* x, int64_t n);   /* n elements of the open array; NaN / Inf refused like JSON3 */
+HG_API int hg_json_number(hg_json* w, double x);
+HG_API int hg_json_string(hg_json* w, const char* value);
+HG_API int hg_json_close(hg_json* w, int32_t trailing_newline);       /* always frees w                                */
+
+typedef struct {
+  const char* name;
+  const double* data;   /* scalars: [n_cells]; vectors: n_cells x 2 column-major (hcat(x, y))                          */
+} hg_named_array;
+/* export_to_vtk_2D: node_xyz [n_nodes][3] (x y z per node), cell_nodes N x ld column-major with ids from index_base,
+ * FIELD block only when field_name is not empty.                                                                  */
+HG_API int hg_write_vtk_2d(const char* path, int64_t n_nodes, const double* node_xyz, int64_t n_cells, int64_t ld, int32_t index_base,
+                    const int64_t* cell_nodes, const int64_t* cell_nnodes, const char* field_name, const char* field_type,
+                    double field_value, const hg_named_array* scalars, int64_t n_scalars, const hg_named_array* vectors,
+                    int64_t n_vectors, char* err, int64_t errlen);
+/* xi, wse, h, u, v, friction_x/y of a saved state Q[3N] (any output may be NULL) */
+HG_API int hg_forward_truth_fields(int64_t N, const double* Q, const double* hstill, const double* wstill, const double* ManningN_cells,
+                            double g, double k_n, double h_small, double* xi, double* wse, double* h, double* u, double* v,
+                            double* friction_x, double* friction_y);
+/* update_ManningN_forward_simulation on the host: n and the closures' diagnostics h/ks, f, Re (NULL to skip) */
+HG_API int hg_manning_function_cells(int32_t type, const double* params, int64_t N, const double* h, const double* umag, const double* ks,
+                              double* n, double* h_ks, double* f, double* Re);
+/* process_dry_wet_flags (fvm/discretization/process_dry_wet.jl:2-35), read by the VTK file only */
+HG_API int hg_dry_wet_flags(int64_t N, int64_t ld, int32_t index_base, const int64_t* cell_nfaces, const int64_t* cell_faces,
+                     const int64_t* cell_neighbors, const uint8_t* face_is_boundary, int64_t n_faces, const double* h,
+                     const double* zb_cells, double h_small, uint8_t* b_dry_wet, uint8_t* adjacent_to_dry_land,
+                     uint8_t* adjacent_to_high_dry_land);
+/* swe_2D_calc_total_water_volume: pairwise sum(h .* cell_areas) */
+HG_API double hg_total_water_volume(int64_t N, const double* h, const double* cell_areas);
+
 /* ---- timing hooks used by bench.py (device time of the last N launches, CUDA events on the
  * ctx stream) and introspection for the roofline arithmetic.                                     */
 HG_API int hg_time_rhs(hg_ctx* ctx, int32_t n_launches, int32_t fused_euler, double dt, float* ms_total);

@@ -67,9 +67,31 @@ def savannah_sensitivity():
                         **{k: np.array(v, dtype=np.float64) for k, v in d.items() if not isinstance(v, str)})
 
 
+def json_digests():
+    """sha256 / length of the reference's own JSON outputs whose VALUES the fixtures hold completely: the byte-level pins of
+    the results writer (tests/test_results_cpu.py rewrites them from truth.npz / sensitivity.npz and compares digests)."""
+    import hashlib
+    files = {name: os.path.join(REF, rel, "forward_simulation_solution_truth.json") for name, (rel, _) in CASES.items()}
+    files.update({name: os.path.join(REF, rel, "forward_simulation_solution_truth.json") for name, rel in VARIABLE_N.items()})
+    out = {}
+    for name, path in sorted(files.items()):
+        if os.path.exists(path) and os.path.exists(os.path.join(HERE, name, "truth.npz")):
+            raw = open(path, "rb").read()
+            out[name + "/truth"] = dict(sha256=hashlib.sha256(raw).hexdigest(), bytes=len(raw), keys=list(json.loads(raw).keys()))
+    for name, rel in (("savannah_sens", "sensitivity_analysis/ManningN/Savana_River"),
+                      ("oneD_bump_sens", CASES["oneD_bump_sens"][0]), ("oneD_uniform_sens", CASES["oneD_uniform_sens"][0])):
+        raw = open(os.path.join(REF, rel, "sensitivity_results.json"), "rb").read()
+        d = json.loads(raw)
+        out[name + "/sensitivity"] = dict(sha256=hashlib.sha256(raw).hexdigest(), bytes=len(raw), keys=list(d.keys()),
+                                          parameter_name=d["parameter_name"])
+    with open(os.path.join(HERE, "json_digests.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
     variable_n()
     savannah_sensitivity()
+    json_digests()
     for name, (rel, stem) in CASES.items():
         src = os.path.join(REF, rel)
         dst = os.path.join(HERE, name)

@@ -18,7 +18,7 @@ HEADER = open(os.path.join(ROOT, "include", "hydrograd_b200.h")).read()
 JULIA = open(os.path.join(ROOT, "hydrograd.jl_b200", "julia", "HydrogradB200.jl")).read()
 MACROS = {k: int(v) for k, v in re.findall(r"#define\s+(HG_UDE_MAX_\w+)\s+(\d+)", HEADER)}
 STRUCTS = {"hg_mesh_desc": L.MeshDesc, "hg_bc_desc": L.BcDesc, "hg_fields_desc": L.FieldsDesc, "hg_options": L.Options,
-           "hg_ude_desc": L.UdeDesc}
+           "hg_ude_desc": L.UdeDesc, "hg_named_array": L.NamedArray}
 P = C.POINTER
 i32p, f32p = P(C.c_int32), P(C.c_float)
 
@@ -35,6 +35,7 @@ def _c_type(t):
     table = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double, "float": C.c_float, "uint8_t": C.c_uint8,
              "double *": L.c_f64p, "int64_t *": L.c_i64p, "int32_t *": i32p, "float *": f32p, "uint8_t *": L.c_u8p, "char *": C.c_char_p,
              "void *": C.c_void_p, "hg_ctx *": C.c_void_p, "hg_case *": C.c_void_p, "hg_ctx * *": P(C.c_void_p), "hg_case * *": P(C.c_void_p),
+             "hg_json *": C.c_void_p, "hg_json * *": P(C.c_void_p),
              "void * *": P(C.c_void_p), "double * *": P(L.c_f64p)}
     if t in table:
         return table[t]
