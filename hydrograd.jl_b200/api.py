@@ -156,6 +156,17 @@ class Context:
         self._ck(self.lib.hg_rhs_vjp(self._h, _p(Q), _p(p), n, a, float(t), _p(lam), _p(Qbar), _p(pbar), _p(nbar)))
         return (Qbar, pbar[:n], nbar) if want_ncell_bar else (Qbar, pbar[:n])
 
+    def rhs_jvp(self, Q, v, params=None, active=None, pdot=None, t=0.0, want_rhs=True):
+        """Forward mode on a strict context: (dQdt, J_Q v + J_p pdot) -- one partial of a ForwardDiff.Dual pass (hg_rhs_jvp)."""
+        p, n, a = self._params(params, active)
+        pd = _f64(pdot) if pdot is not None else None
+        if pd is not None and pd.size != n:
+            raise ValueError(f"pdot has length {pd.size}, expected {n}")
+        out = np.empty(3 * self.N) if want_rhs else None
+        jv = np.empty(3 * self.N)
+        self._ck(self.lib.hg_rhs_jvp(self._h, _p(_f64(Q)), _p(p), n, a, float(t), _p(_f64(v)), _p(pd), _p(out), _p(jv)))
+        return (out, jv) if want_rhs else jv
+
     def rhs_vjp_into(self, Q, lam, Qbar_out):
         """hg_rhs_vjp with no active parameter into a caller-owned (e.g. pinned) buffer."""
         self._ck(self.lib.hg_rhs_vjp(self._h, _p(_f64(Q)), None, 0, 0, 0.0, _p(_f64(lam)), _p(Qbar_out), None, None))

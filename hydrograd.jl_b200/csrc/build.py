@@ -14,6 +14,7 @@ SOURCES = [
     ("hg_results.cpp", []),
     ("hg_api.cu", []),
     ("hg_plain.cu", ["-fmad=false"]),      # reference evaluation order, no FMA contraction
+    ("hg_jvp.cu", ["-fmad=false"]),        # forward mode on the plain tables, same arithmetic rules
     ("hg_fused.cu", []),
     ("hg_vjp.cu", []),
     ("hg_ude.cu", []),
@@ -30,7 +31,7 @@ def _newer(target, deps):
 def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    hdrs = [os.path.join(HERE, "hg_ctx.h"), os.path.join(HERE, "hg_device.cuh"), os.path.join(HERE, "hg_ude.h"), os.path.join(PKG, "..", "include", "hydrograd_b200.h"), __file__]
+    hdrs = [os.path.join(HERE, "hg_ctx.h"), os.path.join(HERE, "hg_device.cuh"), os.path.join(HERE, "hg_ude.h"), os.path.join(HERE, "hg_jvp_impl.h"), os.path.join(PKG, "..", "include", "hydrograd_b200.h"), __file__]
     objs = []
     for src, extra in SOURCES:
         s = os.path.join(HERE, src)

@@ -632,6 +632,38 @@ int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   return check_err_flag(ctx);
 }
 
+// Forward mode: dQdt (optional) and dQdt_dot = J_Q(Q, p) v + J_p(Q, p) pdot, what a ForwardDiff.Dual pass through swe_2d_rhs
+// carries (one partial per call).  Runs on the plain tables (reference evaluation order, hg_jvp.cu): the context must be
+// created with strict = 1 / path = 1.  The state-dependent Manning closures and the UDE network have no forward mode here.
+int hg_rhs_jvp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32_t active, double t, const double* v,
+               const double* pdot, double* dQdt, double* dQdt_dot) {
+  (void)t;
+  if (!ctx || !Q || !v || !dQdt_dot) return HG_ERR_ARG;
+  if (ctx->opt.path != 1) { ctx->err = "hg_rhs_jvp needs the plain path (strict = 1)"; return HG_ERR_ARG; }
+  TRY(no_closure(ctx, "hg_rhs_jvp"));
+  if (active == HG_PARAM_UDE) { ctx->err = "hg_rhs_jvp: the UDE network has no forward mode"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  TRY(bind_params(ctx, params, np, active));
+  hg::PlainDev& p = ctx->pd;
+  const size_t n3 = 3 * (size_t)ctx->N;
+  if (p.V.n != n3) { TRY(al(ctx, p.V, n3)); TRY(al(ctx, p.dQd, n3)); }
+  const int64_t npar = ctx->active == HG_PARAM_NONE ? 0 : ctx->n_params;
+  const double* d_pdot = nullptr;
+  if (pdot && npar > 0) {
+    if (p.pdot.n < (size_t)npar) TRY(al(ctx, p.pdot, (size_t)npar));
+    CK(ctx, cudaMemcpyAsync(p.pdot.p, pdot, npar * 8, cudaMemcpyHostToDevice, ctx->stream));
+    d_pdot = p.pdot.p;
+  }
+  CK(ctx, cudaMemcpyAsync(p.Q.p, Q, n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(p.V.p, v, n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->state_set = true;
+  TRY(hg::plain_jvp(ctx, p.Q.p, p.V.p, d_pdot, dQdt ? p.dQ.p : nullptr, p.dQd.p));
+  if (dQdt) CK(ctx, cudaMemcpyAsync(dQdt, p.dQ.p, n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dQdt_dot, p.dQd.p, n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_err_flag(ctx);
+}
+
 int hg_set_lambda(hg_ctx* ctx, const double* lambda) {
   if (!ctx || !lambda) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "hg_set_lambda needs the fused path"; return HG_ERR_ARG; }

@@ -112,6 +112,8 @@ struct PlainDev {
   DBuf<double> ks;                    // [N] roughness height (variable Manning's n)
   DBuf<double> hstill_g, zb_g;        // [B] GHOST order (as passed in)
   DBuf<double> gh, gqx, gqy, gxi;     // [B] ghost states, ghost order
+  DBuf<double> gh_d, gqx_d, gqy_d, gxi_d;  // [B] their tangents (forward mode, hg_jvp.cu)
+  DBuf<double> V, dQd, pdot;          // [3N], [3N], [np]: tangent of the state, of the RHS, of the parameters
   DBuf<double> Qin, wse;              // [n_inletq], [n_exith]
   DBuf<double> Q, dQ, params;         // [3N], [3N], [np]
   DBuf<int32_t> err;                  // device error flag
@@ -239,6 +241,8 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
 
 // plain path launchers (hg_plain.cu)
 int plain_rhs(hg_ctx* ctx, const double* dQ_in_Q, double* d_out);
+// forward mode on the plain tables (hg_jvp.cu)
+int plain_jvp(hg_ctx* ctx, const double* d_Q, const double* d_V, const double* d_pdot, double* d_out, double* d_out_dot);
 // fused path launchers (hg_fused.cu)
 int fused_rhs(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 int fused_rhs_tiles(hg_ctx* ctx, const double* d_Q, double* d_out, int32_t tile_base, int32_t n_tiles);

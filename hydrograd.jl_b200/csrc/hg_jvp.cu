@@ -1,0 +1,78 @@
+// Forward mode of the RHS on the device (hg_rhs_jvp): dQ/dt and J_Q v + J_p pdot in one sweep of dual-number arithmetic -- the
+// counterpart of ForwardDiff.Dual flowing through swe_2d_rhs (swe_2D_sensitivity.jl:34-80; the ForwardDiffSensitivity /
+// ForwardSensitivity inversion options, solve_swe_2D.jl:230-235).  The arithmetic is hg_jvp_impl.h (shared with the g++ CPU
+// check); this file is the launch structure, the same two launches as the strict path (hg_plain.cu), whose tables it uses:
+//   k_jvp_ghost   one block: inlet-q conveyance coefficients (values and tangents) into shared memory, then one boundary
+//                 entry per thread -> ghost states and their tangents
+//   k_jvp_cell    one thread per cell: every face of the cell from its own side, reference summation order
+// Compiled with -fmad=false like hg_plain.cu, so the values it returns are those of the strict path.
+#include "hg_ctx.h"
+#include "hg_jvp_impl.h"
+
+namespace hg {
+namespace {
+static_assert((int)jvp::kInletQ == (int)BC_INLETQ && (int)jvp::kExitH == (int)BC_EXITH && (int)jvp::kWall == (int)BC_WALL &&
+                  (int)jvp::kSymm == (int)BC_SYMM, "BcType");
+static_assert((int)jvp::kParamZb == (int)HG_PARAM_ZB && (int)jvp::kParamManning == (int)HG_PARAM_MANNING &&
+                  (int)jvp::kParamQ == (int)HG_PARAM_Q, "HG_PARAM_*");
+constexpr int kMaxInlets = 64;
+
+__global__ void __launch_bounds__(256) k_jvp_ghost(jvp::Args a) {
+  __shared__ double coef_v[kMaxInlets], coef_d[kMaxInlets];
+  for (int32_t k = threadIdx.x; k < a.n_inlet; k += blockDim.x) {
+    const jvp::Dual c = jvp::inlet_coef<jvp::Dual>(a, k);
+    coef_v[k] = c.v; coef_d[k] = c.d;
+  }
+  __syncthreads();
+  for (int32_t e = threadIdx.x; e < a.B; e += blockDim.x) {
+    const bool inlet = a.bc_type[e] == jvp::kInletQ;
+    const int32_t k = a.bc_group[e];
+    jvp::ghost_entry<jvp::Dual>(a, e, inlet ? jvp::mk(coef_v[k], coef_d[k]) : jvp::mk(0.0, 0.0));
+  }
+}
+
+__global__ void __launch_bounds__(128) k_jvp_cell(jvp::Args a) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.N) jvp::cell<jvp::Dual>(a, i);
+}
+}  // namespace
+
+// d_V [3N], d_pdot [n_params] or nullptr, d_out [3N] or nullptr, d_out_dot [3N]; reference cell order throughout
+int plain_jvp(hg_ctx* ctx, const double* d_Q, const double* d_V, const double* d_pdot, double* d_out, double* d_out_dot) {
+  PlainDev& p = ctx->pd;
+  if (ctx->n_inletq > kMaxInlets) { ctx->err = "plain path supports at most 64 inlet-q boundaries"; return HG_ERR_ARG; }
+  const size_t B = (size_t)std::max<int64_t>(ctx->B, 1);
+  if (p.gh_d.n != B) {
+    cudaError_t e = p.gh_d.alloc(B);
+    if (e == cudaSuccess) e = p.gqx_d.alloc(B);
+    if (e == cudaSuccess) e = p.gqy_d.alloc(B);
+    if (e == cudaSuccess) e = p.gxi_d.alloc(B);
+    if (e != cudaSuccess) { ctx->err = std::string("plain_jvp: ") + cudaGetErrorString(e); return HG_ERR_CUDA; }
+  }
+  jvp::Args a;
+  a.N = (int32_t)ctx->N; a.B = (int32_t)ctx->B; a.n_inlet = (int32_t)ctx->n_inletq; a.active = ctx->active;
+  a.g = ctx->c.g; a.k_n = ctx->c.k_n; a.h_small = ctx->c.h_small;
+  a.cf_ptr = p.cf_ptr.p; a.cf_nb = p.cf_nb.p; a.cf_nx = p.cf_nx.p; a.cf_ny = p.cf_ny.p; a.cf_len = p.cf_len.p;
+  a.area = p.area.p; a.hstill = p.hstill.p; a.zb = p.zb.p; a.S0x = p.S0x.p; a.S0y = p.S0y.p; a.mann = p.mann.p;
+  a.matid = p.matid.p;
+  a.bc_type = p.bc_type.p; a.bc_group = p.bc_group.p; a.bc_ghost = p.bc_ghost.p; a.bc_cell = p.bc_cell.p;
+  a.inlet_ptr = p.inlet_ptr.p;
+  a.bc_nx = p.bc_nx.p; a.bc_ny = p.bc_ny.p; a.bc_l53 = p.bc_l53.p; a.bc_l23 = p.bc_l23.p;
+  a.hstill_g = p.hstill_g.p; a.zb_g = p.zb_g.p;
+  a.gh = p.gh.p; a.gqx = p.gqx.p; a.gqy = p.gqy.p; a.gxi = p.gxi.p;
+  a.gh_d = p.gh_d.p; a.gqx_d = p.gqx_d.p; a.gqy_d = p.gqy_d.p; a.gxi_d = p.gxi_d.p;
+  a.Qin = p.Qin.p; a.wse = p.wse.p; a.Q = d_Q; a.V = d_V; a.params = p.params.p; a.pdot = d_pdot;
+  a.dQ = d_out; a.dQ_d = d_out_dot; a.err = p.err.p;
+  if (ctx->B > 0) {
+    k_jvp_ghost<<<1, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+  }
+  const int threads = 128;
+  k_jvp_cell<<<(unsigned)((ctx->N + threads - 1) / threads), threads, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = std::string("plain_jvp launch: ") + cudaGetErrorString(e); return HG_ERR_CUDA; }
+  return HG_OK;
+}
+
+}  // namespace hg

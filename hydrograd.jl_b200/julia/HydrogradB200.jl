@@ -15,12 +15,15 @@
 # `swe_2d_rhs` keeps the reference signature (semi_discretize_swe_2D.jl:18-19) with the context in
 # place of p_extra.  The ChainRulesCore.rrule below makes Zygote / ZygoteVJP-based SciMLSensitivity
 # adjoints use the hand-written CUDA VJP (hg_rhs_vjp) instead of differentiating through the RHS.
-# Forward-mode callers (ForwardDiff.Dual state, e.g. ForwardDiffSensitivity) cannot be served by a
-# Float64 kernel: `swe_2d_rhs` has no method for Dual and the driver must pick an adjoint sensealg
-# such as InterpolatingAdjoint(autojacvec=ZygoteVJP()).
+# Forward-mode callers (ForwardDiff.Dual state and / or parameters: ForwardDiff.jacobian around the solve in
+# swe_2D_sensitivity.jl:80, the ForwardDiffSensitivity / ForwardSensitivity inversion options) are served by the
+# Dual methods of `swe_2d_rhs` below: values and partials are split, every partial goes through the device's
+# forward mode (hg_rhs_jvp, one call per partial) and the Duals are reassembled.  That entry point runs on the plain
+# tables, so such drivers create the context with `strict=true`; a fused forward-mode kernel is the next step.
 module HydrogradB200
 
 using ChainRulesCore
+import ForwardDiff
 import ComponentArrays                      # only set_ude_model needs it (offsets of the Lux parameter arrays)
 
 const LIB = get(ENV, "HYDROGRAD_B200_LIB", joinpath(@__DIR__, "..", "libhydrograd_b200.so"))
@@ -152,6 +155,45 @@ _plain(p::AbstractVector) = collect(Float64, p)
 swe_2d_rhs(dQdt::Vector{Float64}, Q::AbstractVector, p::AbstractVector, t::Real, ctx::Context) =
     swe_2d_rhs(dQdt, _plain(Q), _plain(p), Float64(t), ctx)
 swe_2d_rhs(Q::AbstractVector, p::AbstractVector, t::Real, ctx::Context) = swe_2d_rhs(Vector{Float64}(undef, length(Q)), Q, p, t, ctx)
+
+"""
+    swe_2d_rhs_jvp(Q, params_vector, t, v, pdot, ctx) -> (dQdt, J_Q v + J_p pdot)
+
+One forward-mode pass of the device RHS (hg_rhs_jvp); `ctx` must have been created with `strict=true`.
+"""
+function swe_2d_rhs_jvp(Q::Vector{Float64}, params_vector::Vector{Float64}, t::Float64, v::Vector{Float64}, pdot::Vector{Float64}, ctx::Context)
+    dQdt = similar(Q); jv = similar(Q)
+    np = ctx.active == 0 ? 0 : length(params_vector)
+    GC.@preserve Q params_vector v pdot dQdt jv begin
+        rc = ccall((:hg_rhs_jvp, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   ctx.handle, Q, params_vector, np, ctx.active, t, v, (np == 0 ? C_NULL : pointer(pdot)), dQdt, jv)
+        _check(rc, ctx.handle)
+    end
+    return dQdt, jv
+end
+
+# ForwardDiff.Dual state and / or parameters (same tag on both when both are Dual): one device pass per partial
+_vals(x::AbstractVector{<:ForwardDiff.Dual}) = collect(Float64, ForwardDiff.value.(x))
+_vals(x::AbstractVector) = _plain(x)
+_part(x::AbstractVector{<:ForwardDiff.Dual}, k) = collect(Float64, ForwardDiff.partials.(x, k))
+_part(x::AbstractVector, k) = zeros(length(x))
+function _rhs_dual(::Type{ForwardDiff.Dual{Tg,V,NP}}, Q::AbstractVector, p::AbstractVector, t::Real, ctx::Context) where {Tg,V,NP}
+    Qv, pv = _vals(Q), _vals(p)
+    y = Vector{Float64}(undef, length(Qv))
+    cols = ntuple(NP) do k
+        y_k, jv = swe_2d_rhs_jvp(Qv, pv, Float64(t), _part(Q, k), _part(p, k), ctx)
+        copyto!(y, y_k)
+        jv
+    end
+    return [ForwardDiff.Dual{Tg}(y[i], ForwardDiff.Partials(ntuple(k -> cols[k][i], NP))) for i in eachindex(y)]
+end
+swe_2d_rhs(Q::AbstractVector{D}, p::AbstractVector, t::Real, ctx::Context) where {D<:ForwardDiff.Dual} = _rhs_dual(D, Q, p, t, ctx)
+swe_2d_rhs(Q::AbstractVector{<:AbstractFloat}, p::AbstractVector{D}, t::Real, ctx::Context) where {D<:ForwardDiff.Dual} = _rhs_dual(D, Q, p, t, ctx)
+function swe_2d_rhs(dQdt::AbstractVector{D}, Q::AbstractVector, p::AbstractVector, t::Real, ctx::Context) where {D<:ForwardDiff.Dual}
+    dQdt .= _rhs_dual(D, Q, p, t, ctx)                     # in-place twin (bInPlaceODE, solve_swe_2D.jl:230-235)
+    return dQdt
+end
 
 "Vector-Jacobian product (Qbar, pbar) = (dRHS/dQ)' * lambda, (dRHS/dp)' * lambda -- what Zygote.pullback returns (debug_AD.jl:60,75)."
 function swe_2d_rhs_vjp(Q::Vector{Float64}, params_vector::Vector{Float64}, t::Float64, lambda::Vector{Float64}, ctx::Context)

@@ -231,6 +231,12 @@ HG_API int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_
                double* ncell_bar);
 
 /* ---- device-resident state (no host round trip per stage) ---------------------------------- */
+/* Forward mode: dQdt_dot = J_Q v + J_p pdot (and dQdt when not NULL) -- one partial of a ForwardDiff.Dual pass through
+ * swe_2d_rhs (swe_2D_sensitivity.jl:80 wraps the whole solve in ForwardDiff.jacobian; ForwardDiffSensitivity /
+ * ForwardSensitivity of solve_swe_2D.jl:230-235).  v[3N]; pdot[n_params] or NULL (zero).  Needs a context created with
+ * strict = 1 (plain tables, reference evaluation order); no state-dependent Manning closure, no UDE network.            */
+HG_API int hg_rhs_jvp(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params, int32_t active_param, double t,
+               const double* v, const double* pdot, double* dQdt, double* dQdt_dot);
 HG_API int hg_set_state(hg_ctx* ctx, const double* Q);          /* host [3N] -> device                  */
 HG_API int hg_get_state(hg_ctx* ctx, double* Q);                /* device -> host [3N]                  */
 HG_API int hg_set_params(hg_ctx* ctx, const double* params, int64_t n_params, int32_t active_param);

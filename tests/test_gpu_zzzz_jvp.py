@@ -1,0 +1,96 @@
+"""Forward mode on the device (hg_rhs_jvp, hg_jvp.cu) against the oracle's dual-number pass -- the ForwardDiff.Dual semantics the
+reference's sensitivity driver and its ForwardDiffSensitivity inversion option rely on.  The arithmetic is the same source as
+tests/test_jvp_cpu.py checks on the host; this file covers the kernels' launch structure through the C ABI.  (Written after the
+round's GPU budget was spent: not yet run on a B200; sorts last.)"""
+import numpy as np
+import pytest
+
+import _pkg
+from oracle import srh2d_ref as R
+from oracle.oracle import Oracle
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+ACTIVE = {None: 0, "zb": 1, "ManningN": 2, "Q": 3}
+
+
+@pytest.fixture(scope="module")
+def hg():
+    return _pkg.load()
+
+
+def _params(c, flat, mode):
+    if mode == "ManningN":
+        return np.asarray(c.ManningN_zone, dtype=np.float64).copy()
+    if mode == "zb":
+        return np.asarray(c.zb_cells, dtype=np.float64).copy()
+    if mode == "Q":
+        return np.asarray(flat["inletQ_TotalQ"], dtype=np.float64).copy()
+    return None
+
+
+@pytest.mark.parametrize("name", ["simple", "oneD_bump", "savannah"])
+@pytest.mark.parametrize("mode", [None, "ManningN", "zb", "Q"])
+def test_device_forward_mode_matches_the_oracle(hg, name, mode):
+    c = cases.load(name)
+    flat = R.flatten(c)
+    if mode == "Q" and flat["n_inletq"] == 0:
+        pytest.skip("no inlet-q boundary")
+    N = c.mesh.numOfCells
+    o = Oracle(flat)
+    ctx = hg.Context(flat, strict=True)
+    rng = np.random.default_rng(21)
+    p = _params(c, flat, mode)
+    for seed in (0, 2):
+        Q = cases.random_state(c, seed) if seed else c.Q0
+        v = rng.standard_normal(3 * N)
+        pdot = rng.standard_normal(p.size) if p is not None else None
+        dQ, jv = ctx.rhs_jvp(Q, v, p, mode, pdot)
+        ref, ref_jv = o.jvp(Q, v, p, pdot, ACTIVE[mode])
+        sc = cases.flux_scale(c, Q)
+        assert (np.abs(dQ - ref) <= 1e-12 * sc).all()
+        assert np.abs(jv - ref_jv).max() <= 1e-11 * np.abs(ref_jv).max(), (name, mode, seed)
+        strict = ctx.rhs(Q, p, mode)                       # the values are those of the strict path (same operations)
+        assert (np.abs(dQ - strict) <= 1e-14 * sc).all()
+        print(name, mode, seed, "values equal to the strict path bit for bit:", bool(np.array_equal(dQ, strict)),
+              " tangent rel. err %.1e" % (np.abs(jv - ref_jv).max() / np.abs(ref_jv).max()))
+        only = ctx.rhs_jvp(Q, v, p, mode, pdot, want_rhs=False)
+        assert np.array_equal(only, jv)
+
+
+def test_device_forward_mode_is_the_transpose_of_the_vjp_kernel(hg):
+    """<lambda, J v> (forward mode, strict context) = <J^T lambda, v> (hand-written VJP kernel, fused context): the two
+    derivative kernels of the library against each other on a synthetic mesh with dry cells."""
+    from hydrograd_jl_b200 import synthetic as S
+    flat, Q0 = S.river(64, 40)
+    N = flat["n_cells"]
+    rng = np.random.default_rng(4)
+    Q = cases.random_state_flat(flat, 7, dry_frac=0.03)
+    p = np.linspace(0.02, 0.05, int(flat["n_mat"]))
+    v, lam, pdot = rng.standard_normal(3 * N), rng.standard_normal(3 * N), rng.standard_normal(p.size)
+    fwd = hg.Context(flat, strict=True)
+    rev = hg.Context(flat)
+    _, jv = fwd.rhs_jvp(Q, v, p, "ManningN", pdot)
+    Qbar, pbar = rev.rhs_vjp(Q, lam, p, "ManningN")[:2]
+    lhs, rhs = lam @ jv, Qbar @ v + pbar @ pdot
+    assert abs(lhs - rhs) <= 1e-10 * np.abs(lam * jv).sum()
+
+
+def test_forward_mode_error_behaviour(hg):
+    c = cases.load("oneD_bump")
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    fused = hg.Context(flat)
+    with pytest.raises(hg.HydrogradError) as e:
+        fused.rhs_jvp(c.Q0, np.ones(3 * N))
+    assert "plain path" in str(e.value)
+    ctx = hg.Context(flat, strict=True)
+    with pytest.raises(hg.HydrogradError):
+        ctx.rhs_jvp(c.Q0, np.ones(3 * N), np.array([0.03]), "ManningN")            # wrong parameter length
+    dry = c.Q0.copy()
+    dry[:N] = -flat["hstill"] + 1e-4
+    with pytest.raises(hg.HydrogradError) as e:
+        ctx.rhs_jvp(dry, np.ones(3 * N))
+    assert e.value.code == 3                                                          # inlet conveyance assert (bc_2D.jl:678-680)
+    dQ, jv = ctx.rhs_jvp(c.Q0, np.zeros(3 * N))                                       # the context is usable afterwards
+    assert not jv.any() and np.isfinite(dQ).all()
