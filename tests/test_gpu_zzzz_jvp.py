@@ -94,3 +94,23 @@ def test_forward_mode_error_behaviour(hg):
     assert e.value.code == 3                                                          # inlet conveyance assert (bc_2D.jl:678-680)
     dQ, jv = ctx.rhs_jvp(c.Q0, np.zeros(3 * N))                                       # the context is usable afterwards
     assert not jv.any() and np.isfinite(dQ).all()
+
+
+def test_device_forward_mode_reproduces_the_reference_sensitivities(hg):
+    """The reference's Savannah sensitivity run -- ForwardDiff.jacobian of the adaptive Tsit5 solve, d Q(200 s) / d ManningN --
+    with every Dual pass done by the device: values and six partials, hg_rhs_jvp per partial and stage, Dual-aware error norm
+    and fastpow controller on the host (tests/tsit5_ref.py).  Compared with the reference's committed sensitivity_results.json
+    (host build of the same source: 2.5e-9 of the largest entry, tests/test_jvp_cpu.py; tolerance here as for the other replays
+    of tests/test_gpu_zzz_reference_replay.py)."""
+    from tests.test_oracle_golden import savannah_sensitivity_solve
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    ctx = hg.Context(flat, strict=True)
+
+    def jvp(Q, V, p, pdot):
+        return ctx.rhs_jvp(Q, V, p, "ManningN", pdot)
+
+    U, S, st, _ = savannah_sensitivity_solve(jvp)
+    err = [np.abs(U[1 + k] - S[k]).max() for k in range(S.shape[0])]
+    print("savannah sensitivities, device forward mode vs reference:", ["%.1e" % e for e in err], st)
+    assert max(err) <= 1e-5 * np.abs(S).max()

@@ -84,46 +84,58 @@ def plain_tables(flat):
     return t
 
 
-def run_host(host, flat, Q, V=None, params=None, pdot=None, active=0, dual=True):
-    N, B = flat["n_cells"], flat["n_ghost"]
-    t = plain_tables(flat)
-    keep = []
+class HostJvp:
+    """hg::jvp::Args for one mesh, filled once; call(...) runs the g++ build of hg_jvp_impl.h."""
 
-    def d(x):
+    def __init__(self, host, flat):
+        self.host, self.flat = host, flat
+        N, B = flat["n_cells"], flat["n_ghost"]
+        self.N = N
+        t = plain_tables(flat)
+        self.keep = []
+        a = self.a = Args()
+        a.N, a.B, a.n_inlet = N, B, flat["n_inletq"]
+        a.g, a.k_n, a.h_small = flat["g"], flat["k_n"], flat["h_small"]
+        for k in ("cf_ptr", "cf_nb", "bc_type", "bc_group", "bc_ghost", "bc_cell", "inlet_ptr"):
+            setattr(a, k, self.i(t[k]))
+        for k in ("cf_nx", "cf_ny", "cf_len", "bc_nx", "bc_ny", "bc_l53", "bc_l23"):
+            setattr(a, k, self.d(t[k]))
+        S0 = np.asarray(flat["S0_cells"], dtype=np.float64)
+        a.area, a.hstill, a.zb, a.S0x, a.S0y, a.mann = (self.d(flat["cell_areas"]), self.d(flat["hstill"]), self.d(flat["zb_cells"]),
+                                                         self.d(S0[:N]), self.d(S0[N:]), self.d(flat["ManningN_cells"]))
+        a.matid = self.i(np.asarray(flat["matID_cells"]) if "matID_cells" in flat else np.zeros(N))
+        a.hstill_g, a.zb_g = self.d(flat["hstill_ghost"]), self.d(flat["zb_ghost"])
+        for k in ("gh", "gqx", "gqy", "gxi", "gh_d", "gqx_d", "gqy_d", "gxi_d"):
+            setattr(a, k, self.d(np.zeros(max(B, 1))))
+        a.Qin = self.d(flat["inletQ_TotalQ"] if flat["n_inletq"] else np.zeros(1))
+        a.wse = self.d(flat["exitH_WSE"] if flat["n_exith"] else np.zeros(1))
+        self.err = np.zeros(1, dtype=np.int32)
+        a.err = self.err.ctypes.data_as(i32p)
+
+    def d(self, x):
         x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
-        keep.append(x)
+        self.keep.append(x)
         return x.ctypes.data_as(f64p)
 
-    def i(x):
+    def i(self, x):
         x = np.ascontiguousarray(np.asarray(x, dtype=np.int32))
-        keep.append(x)
+        self.keep.append(x)
         return x.ctypes.data_as(i32p)
 
-    a = Args()
-    a.N, a.B, a.n_inlet, a.active = N, B, flat["n_inletq"], active
-    a.g, a.k_n, a.h_small = flat["g"], flat["k_n"], flat["h_small"]
-    for k in ("cf_ptr", "cf_nb", "bc_type", "bc_group", "bc_ghost", "bc_cell", "inlet_ptr"):
-        setattr(a, k, i(t[k]))
-    for k in ("cf_nx", "cf_ny", "cf_len", "bc_nx", "bc_ny", "bc_l53", "bc_l23"):
-        setattr(a, k, d(t[k]))
-    S0 = np.asarray(flat["S0_cells"], dtype=np.float64)
-    a.area, a.hstill, a.zb, a.S0x, a.S0y, a.mann = d(flat["cell_areas"]), d(flat["hstill"]), d(flat["zb_cells"]), d(S0[:N]), d(S0[N:]), d(flat["ManningN_cells"])
-    a.matid = i(np.asarray(flat["matID_cells"]) if "matID_cells" in flat else np.zeros(N))
-    a.hstill_g, a.zb_g = d(flat["hstill_ghost"]), d(flat["zb_ghost"])
-    gh = [np.zeros(max(B, 1)) for _ in range(8)]
-    for k, g in zip(("gh", "gqx", "gqy", "gxi", "gh_d", "gqx_d", "gqy_d", "gxi_d"), gh):
-        setattr(a, k, d(g))
-    a.Qin, a.wse = d(flat["inletQ_TotalQ"] if flat["n_inletq"] else np.zeros(1)), d(flat["exitH_WSE"] if flat["n_exith"] else np.zeros(1))
-    a.Q = d(Q)
-    a.V = d(V) if V is not None else None
-    a.params = d(params) if params is not None else None
-    a.pdot = d(pdot) if pdot is not None else None
-    out, out_d = np.zeros(3 * N), np.zeros(3 * N)
-    a.dQ, a.dQ_d = out.ctypes.data_as(f64p), out_d.ctypes.data_as(f64p)
-    err = np.zeros(1, dtype=np.int32)
-    a.err = err.ctypes.data_as(i32p)
-    rc = host.jvp_host(C.byref(a), int(dual))
-    return out, out_d, rc
+    def __call__(self, Q, V=None, params=None, pdot=None, active=0, dual=True):
+        a = self.a
+        hold = [np.ascontiguousarray(x, dtype=np.float64) if x is not None else None for x in (Q, V, params, pdot)]
+        a.active = active
+        a.Q, a.V, a.params, a.pdot = [x.ctypes.data_as(f64p) if x is not None else None for x in hold]
+        out, out_d = np.zeros(3 * self.N), np.zeros(3 * self.N)
+        a.dQ, a.dQ_d = out.ctypes.data_as(f64p), out_d.ctypes.data_as(f64p)
+        self.err[0] = 0
+        rc = self.host.jvp_host(C.byref(a), int(dual))
+        return out, out_d, rc
+
+
+def run_host(host, flat, Q, V=None, params=None, pdot=None, active=0, dual=True):
+    return HostJvp(host, flat)(Q, V, params, pdot, active, dual)
 
 
 def _flat(name):
@@ -190,3 +202,22 @@ def test_conveyance_assert_is_reported(host):
     Q[:N] = -flat["hstill"] + 1e-4          # everything dry: the inlet's conveyance is 0 (bc_2D.jl:678-680)
     _, _, rc = run_host(host, flat, Q, np.ones(3 * N))
     assert rc == 3
+
+
+def test_reference_sensitivity_run_through_the_forward_mode_source(host):
+    """The reference's Savannah sensitivity run (ForwardDiff.jacobian of the adaptive solve: values and six partials through the
+    Dual-norm Tsit5, 202 accepted steps x 7 stages x 6 partials) carried by the g++ build of hg_jvp_impl.h -- the source the
+    device kernels are compiled from -- lands on the reference's committed sensitivity_results.json."""
+    from tests.test_oracle_golden import savannah_sensitivity_solve
+    c, flat = _flat("savannah")
+    run = HostJvp(host, flat)
+
+    def jvp(Q, V, p, pdot):
+        f, jv, rc = run(Q, V, p, pdot, 2)
+        assert rc == 0
+        return f, jv
+
+    U, S, st, _ = savannah_sensitivity_solve(jvp)
+    err = [np.abs(U[1 + k] - S[k]).max() for k in range(S.shape[0])]
+    print("savannah sensitivities through hg_jvp_impl.h vs reference:", ["%.1e" % e for e in err], st)
+    assert st["accepted"] > 150 and max(err) <= 2e-8 * np.abs(S).max()

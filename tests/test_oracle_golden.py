@@ -416,9 +416,10 @@ def test_savannah_forward_run_reproduces_the_reference_final_state(oracle_lib, v
     assert max(err) <= 1e-8
 
 
-def savannah_sensitivity_solve():
+def savannah_sensitivity_solve(jvp=None):
     """The reference's Savannah sensitivity run restated: values and six partials through the Dual-norm Tsit5.  Returns
-    (U[1 + K, 3N] at T = 200 s, the reference's sensitivity_results as [K, 3N], stats, recorded accepted steps [(t, h)])."""
+    (U[1 + K, 3N] at T = 200 s, the reference's sensitivity_results as [K, 3N], stats, recorded accepted steps [(t, h)]).
+    jvp(Q, V, p, pdot) -> (f, J_Q V + J_p pdot) replaces the oracle's dual pass (the device's or the host build of its source)."""
     from tests import tsit5_ref as T
     c = cases.load("savannah")
     o = Oracle(R.flatten(c))
@@ -435,7 +436,7 @@ def savannah_sensitivity_solve():
         for k in range(K):
             e = np.zeros(K)
             e[k] = 1.0
-            f, jv = o.jvp(U[0], U[1 + k], p, e, 2, nthreads=0)
+            f, jv = o.jvp(U[0], U[1 + k], p, e, 2, nthreads=0) if jvp is None else jvp(U[0], U[1 + k], p, e)
             out[1 + k] = jv
         out[0] = f
         return out
