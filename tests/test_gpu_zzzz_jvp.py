@@ -41,7 +41,7 @@ def test_device_forward_mode_matches_the_oracle(hg, name, mode):
     ctx = hg.Context(flat, strict=True)
     rng = np.random.default_rng(21)
     p = _params(c, flat, mode)
-    for seed in (0, 2):
+    for seed in (0, 1):
         Q = cases.random_state(c, seed) if seed else c.Q0
         v = rng.standard_normal(3 * N)
         pdot = rng.standard_normal(p.size) if p is not None else None
