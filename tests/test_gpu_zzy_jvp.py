@@ -1,7 +1,7 @@
 """Forward mode on the device (hg_rhs_jvp, hg_jvp.cu) against the oracle's dual-number pass -- the ForwardDiff.Dual semantics the
 reference's sensitivity driver and its ForwardDiffSensitivity inversion option rely on.  The arithmetic is the same source as
 tests/test_jvp_cpu.py checks on the host; this file covers the kernels' launch structure through the C ABI.  (Written after the
-round's GPU budget was spent: not yet run on a B200; sorts last.)"""
+round's GPU budget was spent: not yet run on a B200; sorts after the tests that have run, before the replays.)"""
 import numpy as np
 import pytest
 

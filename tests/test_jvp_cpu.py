@@ -1,7 +1,7 @@
 """CPU check of the forward-mode (JVP) arithmetic: hydrograd.jl_b200/csrc/hg_jvp_impl.h -- the very source the CUDA kernels of
 hg_jvp.cu are compiled from -- built by g++ (tests/jvp_host.cpp) and compared with the oracle: values against its RHS, tangents
 against its dual-number pass, for every active parameter, with dry cells and wet/dry fronts.  The launch structure of the
-kernels is covered by tests/test_gpu_zzzz_jvp.py."""
+kernels is covered by tests/test_gpu_zzy_jvp.py."""
 import ctypes as C
 import os
 import subprocess

@@ -53,6 +53,34 @@ def test_julia_float_layout(res):
         assert len(s.replace("-", "").replace(".", "").split("e")[0].strip("0")) <= len(repr(float(x)).replace("-", "").replace(".", "").split("e")[0].strip("0"))
 
 
+def _canon(txt):
+    """(digits without leading / trailing zeros, decimal exponent of the first digit) of a positive decimal literal"""
+    from decimal import Decimal
+    sign, digits, exp = Decimal(txt).as_tuple()
+    d = "".join(map(str, digits)).lstrip("0")
+    e = exp + len(d) - 1 if d else 0
+    return d.rstrip("0"), e
+
+
+def test_shortest_digits_agree_with_python_repr_on_random_bit_patterns(res):
+    """Both Julia (Ryu) and Python (repr) print the shortest decimal string that round-trips, the closest one when several
+    exist: same digits and exponent, only the layout differs.  2e4 random bit patterns over the whole exponent range incl.
+    subnormals, and neighbours of powers of ten and two."""
+    rng = np.random.default_rng(7)
+    bits = rng.integers(0, 0x7FF0000000000000, 20000, dtype=np.int64)
+    xs = list(bits.view(np.float64)) + [10.0 ** k for k in range(-300, 300, 7)] + [np.nextafter(10.0 ** k, 0) for k in range(-20, 22)] + \
+        [2.0 ** k for k in range(-1074, 1023, 11)] + [np.nextafter(2.0 ** k, np.inf) for k in range(-60, 60)]
+    for x in xs:
+        x = float(x)
+        if x == 0.0:
+            continue
+        s = res.format_float(x)
+        assert float(s) == x
+        assert _canon(s.replace("e", "E")) == _canon(repr(x)), (x, s, repr(x))
+        pt = _canon(s.replace("e", "E"))[1] + 1
+        assert ("e" in s) == (not (-4 < pt <= 6)), (x, s)
+
+
 def _digests():
     return json.load(open(os.path.join(cases.GOLD, "json_digests.json")))
 
