@@ -167,6 +167,16 @@ class Context:
         self._ck(self.lib.hg_rhs_jvp(self._h, _p(_f64(Q)), _p(p), n, a, float(t), _p(_f64(v)), _p(pd), _p(out), _p(jv)))
         return (out, jv) if want_rhs else jv
 
+    def solve_tsit5_sens(self, Q0, params, active, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3):
+        """The reference's sensitivity driver (ForwardDiff.jacobian around the Tsit5 solve, swe_2D_sensitivity.jl:34-80) on a
+        strict context: returns (Q(t1) [3N], S [n_params, 3N] with S[k] = dQ(t1)/dp_k, stats)."""
+        p, n, a = self._params(params, active)
+        QT, S = np.empty(3 * self.N), np.empty((max(n, 1), 3 * self.N))
+        stats = np.zeros(3, dtype=np.int64)
+        self._ck(self.lib.hg_solve_tsit5_sens(self._h, _p(_f64(Q0)), _p(p), n, a, float(t0), float(t1), float(dt), int(bool(adaptive)),
+                                              float(abstol), float(reltol), _p(QT), _p(S), _p(stats, L.c_i64p)))
+        return QT, S[:n], dict(accepted=int(stats[0]), rejected=int(stats[1]), rhs=int(stats[2]))
+
     def rhs_vjp_into(self, Q, lam, Qbar_out):
         """hg_rhs_vjp with no active parameter into a caller-owned (e.g. pinned) buffer."""
         self._ck(self.lib.hg_rhs_vjp(self._h, _p(_f64(Q)), None, 0, 0, 0.0, _p(_f64(lam)), _p(Qbar_out), None, None))

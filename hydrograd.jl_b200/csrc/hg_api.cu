@@ -664,6 +664,120 @@ int hg_rhs_jvp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   return check_err_flag(ctx);
 }
 
+// Forward sensitivity solve: the reference's sensitivity driver on the device.  swe_2D_sensitivity.jl:34-80 wraps
+// solve(prob, Tsit5(), adaptive=..., dt=dt; abstol, reltol) in ForwardDiff.jacobian, i.e. the state is a vector of Duals with
+// one partial per parameter: values and partials advance together, the error estimate -- hence every step size -- includes
+// the partials (DiffEqBase's norm of Dual numbers).  Here: U = [Q; dQ/dp_1; ...; dQ/dp_K] resident on the device, each Tsit5
+// stage = K forward-mode sweeps (plain_jvp, the first one also delivers the values), the Dual-aware norm reduced on the
+// device, the PI controller on the host (powers per hg_set_controller_pow).  Plain tables: the context needs strict = 1.
+int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double t0, double t1,
+                        double dt, int32_t adaptive, double abstol, double reltol, double* Q_T, double* S, int64_t* stats) {
+  if (!ctx || !Q0 || !S || !(t1 > t0) || !(dt > 0.0)) return HG_ERR_ARG;
+  if (adaptive && (!(abstol > 0.0) || !(reltol > 0.0))) { ctx->err = "hg_solve_tsit5_sens: tolerances must be positive"; return HG_ERR_ARG; }
+  if (ctx->opt.path != 1) { ctx->err = "hg_solve_tsit5_sens needs the plain path (strict = 1)"; return HG_ERR_ARG; }
+  TRY(no_closure(ctx, "hg_solve_tsit5_sens"));
+  if (active != HG_PARAM_ZB && active != HG_PARAM_MANNING && active != HG_PARAM_Q) {
+    ctx->err = "hg_solve_tsit5_sens: the active parameter must be zb, ManningN or Q";
+    return HG_ERR_ARG;
+  }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  TRY(bind_params(ctx, params, np, active));
+  const int64_t K = ctx->n_params;
+  if (K < 1) { ctx->err = "hg_solve_tsit5_sens: no parameters"; return HG_ERR_ARG; }
+  static const double A[7][6] = {
+      {0, 0, 0, 0, 0, 0},
+      {0.161, 0, 0, 0, 0, 0},
+      {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+      {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+      {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+      {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+      {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+  static const double BT[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                               0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
+  const double beta2 = 2.0 / 25.0, beta1 = 7.0 / 50.0, gamma = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
+  const int64_t n3 = 3 * ctx->N, rows = 1 + K, len = rows * n3;
+  hg::DBuf<double> U, Unew, Y, kb[7], E, part, sum;
+  CK(ctx, U.alloc((size_t)len)); CK(ctx, Unew.alloc((size_t)len)); CK(ctx, Y.alloc((size_t)len));
+  for (int m = 0; m < 7; ++m) CK(ctx, kb[m].alloc((size_t)len));
+  CK(ctx, E.alloc((size_t)(K * K)));
+  CK(ctx, part.alloc((size_t)hg::sens_err_blocks(n3))); CK(ctx, sum.alloc(1));
+  {
+    std::vector<double> eye((size_t)(K * K), 0.0);
+    for (int64_t k = 0; k < K; ++k) eye[(size_t)(k * K + k)] = 1.0;
+    CK(ctx, cudaMemcpyAsync(E.p, eye.data(), eye.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  CK(ctx, cudaMemsetAsync(U.p, 0, (size_t)len * 8, ctx->stream));           // the partials start at zero (Q0 does not depend on p)
+  CK(ctx, cudaMemcpyAsync(U.p, Q0, (size_t)n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  // d/dt of the augmented state: row 0 = f(Q, p), row k = J_Q U_k + J_p e_k
+  auto rhs_aug = [&](const double* u, double* du) -> int {
+    for (int64_t k = 0; k < K; ++k)
+      TRY(hg::plain_jvp(ctx, u, u + (1 + k) * n3, E.p + k * K, k == 0 ? du : nullptr, du + (1 + k) * n3));
+    return HG_OK;
+  };
+  double* u = U.p;
+  double* unew = Unew.p;
+  double* k[7];
+  for (int m = 0; m < 7; ++m) k[m] = kb[m].p;
+  int64_t n_acc = 0, n_rej = 0, n_rhs = 0;
+  double t = t0, dt_ctrl = dt, qold = qoldinit;
+  ctx->last_steps.clear();
+  TRY(rhs_aug(u, k[0]));
+  ++n_rhs;
+  while (t < t1) {
+    double h = std::min(dt_ctrl, t1 - t);
+    const bool clipped = h < dt_ctrl;
+    if (t1 - (t + h) < 1e-12 * std::max(1.0, std::fabs(t1))) h = t1 - t;
+    double coef[7];
+    for (int i = 1; i < 7; ++i) {
+      for (int j = 0; j < i; ++j) coef[j] = h * A[i][j];
+      double* y = i < 6 ? Y.p : unew;
+      TRY(hg::sens_lincomb(ctx, len, y, u, i, k, coef));
+      TRY(rhs_aug(y, k[i]));
+      ++n_rhs;
+    }
+    bool accept = true;
+    double q = 1.0, q11 = 0.0, eest = 0.0;
+    if (adaptive) {
+      for (int m = 0; m < 7; ++m) coef[m] = h * BT[m];
+      TRY(hg::sens_err_norm(ctx, n3, (int)rows, u, unew, 7, k, coef, abstol, reltol, part.p, sum.p));
+      double ssum = 0.0;
+      CK(ctx, cudaMemcpyAsync(&ssum, sum.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      eest = std::sqrt(ssum / (double)len);
+      if (!(eest == eest)) { ctx->err = "hg_solve_tsit5_sens: the error estimate is NaN"; return HG_ERR_STATE; }
+      if (eest == 0.0) { q11 = 0.0; q = 1.0 / qmax; }
+      else {
+        q11 = ctx->controller_fastpow ? hg_fastpow(eest, beta1) : std::pow(eest, beta1);
+        q = q11 / (ctx->controller_fastpow ? hg_fastpow(qold, beta2) : std::pow(qold, beta2));
+        q = std::max(1.0 / qmax, std::min(1.0 / qmin, q / gamma));
+      }
+      accept = eest <= 1.0;
+    }
+    if (accept) {
+      std::swap(u, unew);
+      std::swap(k[0], k[6]);                       // FSAL
+      t = (h == t1 - t) ? t1 : t + h;
+      ++n_acc;
+      ctx->last_steps.push_back(h);
+      if (adaptive) {
+        qold = std::max(eest, qoldinit);
+        const double prop = h / q;
+        dt_ctrl = clipped ? std::max(prop, dt_ctrl) : prop;
+      }
+    } else {
+      ++n_rej;
+      dt_ctrl = h / std::min(1.0 / qmin, q11 / gamma);
+      if (!(dt_ctrl > 1e-14 * std::max(1.0, std::fabs(t)))) { ctx->err = "hg_solve_tsit5_sens: step size underflow"; return HG_ERR_STATE; }
+    }
+  }
+  if (Q_T) CK(ctx, cudaMemcpyAsync(Q_T, u, (size_t)n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(S, u + n3, (size_t)(K * n3) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) { stats[0] = n_acc; stats[1] = n_rej; stats[2] = n_rhs; }
+  return check_err_flag(ctx);
+}
+
 int hg_set_lambda(hg_ctx* ctx, const double* lambda) {
   if (!ctx || !lambda) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "hg_set_lambda needs the fused path"; return HG_ERR_ARG; }

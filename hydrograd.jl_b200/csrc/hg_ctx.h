@@ -243,6 +243,10 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
 int plain_rhs(hg_ctx* ctx, const double* dQ_in_Q, double* d_out);
 // forward mode on the plain tables (hg_jvp.cu)
 int plain_jvp(hg_ctx* ctx, const double* d_Q, const double* d_V, const double* d_pdot, double* d_out, double* d_out_dot);
+int sens_lincomb(hg_ctx* ctx, int64_t len, double* y, const double* x, int n, const double* const* k, const double* coef);
+int sens_err_blocks(int64_t n3);
+int sens_err_norm(hg_ctx* ctx, int64_t n3, int rows, const double* u, const double* unew, int n, const double* const* k,
+                  const double* coef, double abstol, double reltol, double* d_part, double* d_sum);
 // fused path launchers (hg_fused.cu)
 int fused_rhs(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 int fused_rhs_tiles(hg_ctx* ctx, const double* d_Q, double* d_out, int32_t tile_base, int32_t n_tiles);

@@ -35,7 +35,92 @@ __global__ void __launch_bounds__(128) k_jvp_cell(jvp::Args a) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < a.N) jvp::cell<jvp::Dual>(a, i);
 }
+
+// ---- small kernels of the forward-sensitivity solve (hg_solve_tsit5_sens): the augmented state is U[(1 + K)][3N],
+// row 0 the values, row k the partial with respect to parameter k
+struct Comb {
+  const double* k[7];
+  double c[7];
+  int n;
+};
+__global__ void k_sens_lincomb(int64_t len, double* __restrict__ y, const double* __restrict__ x, Comb cb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  double v = x[i];
+  for (int m = 0; m < cb.n; ++m) v += cb.c[m] * cb.k[m][i];
+  y[i] = v;
+}
+constexpr int kErrBlock = 256;
+// DiffEqBase's norm for Dual states: residual of entry i over abstol + max(|u_i|, |unew_i|) reltol with |.| the norm of the
+// Dual (values and partials), squares summed over values AND partials.  One entry per thread, fixed-shape tree per block.
+__global__ void __launch_bounds__(kErrBlock) k_sens_err_partial(int64_t n3, int rows, const double* __restrict__ u,
+                                                                const double* __restrict__ unew, Comb cb, double abstol,
+                                                                double reltol, double* __restrict__ part) {
+  __shared__ double sh[kErrBlock];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (i < n3) {
+    double nu = 0.0, nn = 0.0;
+    for (int r = 0; r < rows; ++r) {
+      const double a = u[r * n3 + i], b = unew[r * n3 + i];
+      nu += a * a; nn += b * b;
+    }
+    const double den = abstol + fmax(sqrt(nu), sqrt(nn)) * reltol;
+    for (int r = 0; r < rows; ++r) {
+      double ut = 0.0;
+      for (int m = 0; m < cb.n; ++m) ut += cb.c[m] * cb.k[m][r * n3 + i];
+      const double q = ut / den;
+      acc += q * q;
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = kErrBlock / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(kErrBlock) k_sens_err_final(int nblocks, const double* __restrict__ part, double* __restrict__ out) {
+  __shared__ double sh[kErrBlock];
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += kErrBlock) acc += part[b];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = kErrBlock / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+int launch_ok(hg_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); return HG_ERR_CUDA; }
+  return HG_OK;
+}
 }  // namespace
+
+int sens_lincomb(hg_ctx* ctx, int64_t len, double* y, const double* x, int n, const double* const* k, const double* coef) {
+  Comb cb;
+  cb.n = n;
+  for (int m = 0; m < 7; ++m) { cb.k[m] = m < n ? k[m] : nullptr; cb.c[m] = m < n ? coef[m] : 0.0; }
+  k_sens_lincomb<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(len, y, x, cb);
+  ctx->launches++;
+  return launch_ok(ctx, "sens_lincomb");
+}
+int sens_err_blocks(int64_t n3) { return (int)((n3 + kErrBlock - 1) / kErrBlock); }
+// sum over values and partials of the squared scaled residuals -> d_sum[0]
+int sens_err_norm(hg_ctx* ctx, int64_t n3, int rows, const double* u, const double* unew, int n, const double* const* k,
+                  const double* coef, double abstol, double reltol, double* d_part, double* d_sum) {
+  Comb cb;
+  cb.n = n;
+  for (int m = 0; m < 7; ++m) { cb.k[m] = m < n ? k[m] : nullptr; cb.c[m] = m < n ? coef[m] : 0.0; }
+  const int nb = sens_err_blocks(n3);
+  k_sens_err_partial<<<nb, kErrBlock, 0, ctx->stream>>>(n3, rows, u, unew, cb, abstol, reltol, d_part);
+  k_sens_err_final<<<1, kErrBlock, 0, ctx->stream>>>(nb, d_part, d_sum);
+  ctx->launches += 2;
+  return launch_ok(ctx, "sens_err_norm");
+}
 
 // d_V [3N], d_pdot [n_params] or nullptr, d_out [3N] or nullptr, d_out_dot [3N]; reference cell order throughout
 int plain_jvp(hg_ctx* ctx, const double* d_Q, const double* d_V, const double* d_pdot, double* d_out, double* d_out_dot) {

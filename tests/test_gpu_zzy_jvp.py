@@ -114,3 +114,33 @@ def test_device_forward_mode_reproduces_the_reference_sensitivities(hg):
     err = [np.abs(U[1 + k] - S[k]).max() for k in range(S.shape[0])]
     print("savannah sensitivities, device forward mode vs reference:", ["%.1e" % e for e in err], st)
     assert max(err) <= 1e-5 * np.abs(S).max()
+
+
+def test_device_resident_sensitivity_solve_reproduces_the_reference(hg):
+    """hg_solve_tsit5_sens: the same run in ONE call -- augmented state [Q; dQ/dp_1..6] resident on the device, K forward-mode
+    sweeps per Tsit5 stage, Dual-aware error norm reduced on the device, fastpow PI controller -- against the reference's
+    committed sensitivity_results.json and against the host restatement's step count (202 accepted, 1 rejected)."""
+    import os
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    z = np.load(os.path.join(cases.GOLD, "savannah_sens", "sensitivity.npz"))
+    p = z["params_vector"]
+    S_ref = z["sensitivity_results"].reshape(p.size, 3 * N)
+    ctx = hg.Context(flat, strict=True)
+    ctx.set_controller_pow("fastpow")
+    QT, S, st = ctx.solve_tsit5_sens(c.Q0, p, "ManningN", 0.0, 200.0, 0.02, True, 1e-6, 1e-3)
+    err = [np.abs(S[k] - S_ref[k]).max() for k in range(p.size)]
+    print("device-resident sensitivity solve vs reference:", ["%.1e" % e for e in err], st)
+    assert abs(st["accepted"] - 202) <= 10 and st["rejected"] <= 6
+    assert max(err) <= 1e-5 * np.abs(S_ref).max()
+    t = cases.truth("savannah")                                   # the values ride along: the forward run's final state
+    assert np.abs(QT[:N] - t["xi_truth"]).max() <= 5e-3           # (that file comes from the plain forward run, other steps: 7.5e-4 on the host)
+    h = ctx.last_steps()
+    assert h.size == st["accepted"] and abs(h.sum() - 200.0) < 1e-9
+    # fixed-step mode and the other parameters: finite, right shapes; Q: linear dependence -> S p = dQ/dlog-scale check by FD
+    pQ = np.asarray(flat["inletQ_TotalQ"], dtype=np.float64)
+    Q1, SQ, _ = ctx.solve_tsit5_sens(c.Q0, pQ, "Q", 0.0, 1.0, 0.05, False)
+    Q2, _, _ = ctx.solve_tsit5_sens(c.Q0, pQ * (1 + 1e-6), "Q", 0.0, 1.0, 0.05, False)
+    fd = (Q2 - Q1) / 1e-6
+    assert np.abs(SQ.T @ pQ - fd).max() <= 1e-4 * max(np.abs(fd).max(), 1e-12)
