@@ -10,6 +10,7 @@ the library (csrc/hg_results.cpp), byte-compatible with the files t
   postprocess_forward_simulation_results_swe_2D     applications/forward_simulation/process_forward_simulation_results_2D.jl:4-86
   swe_2D_save_results_SciML                         utilities/swe_2D_tools.jl:10-98
   save_sensitivity_results                          applications/sensitivity/swe_2D_sensitivity.jl:60-72, 84-95
+  postprocess_sensitivity_results_swe_2D            applications/sensitivity/process_sensitivity_results_2D.jl:4-80
 
 Host only (file output is I/O bound); the states come from the device integrators (Context.solve_tsit5 / custom_ode_solve).
 """
@@ -33,6 +34,7 @@ TRUTH_KEYS = ("wstill_truth", "Re_cells_truth", "friction_y_truth", "xi_truth", 
               "zb_cell_truth", "friction_factor_cells_truth", "friction_x_truth", "u_truth", "hstill_truth")
 SENSITIVITY_KEYS = ("params_vector", "parameter_name", "sensitivity_results")
 FORWARD_RESULTS_KEYS = ("forward_simulation_results", "zb_cells", "wstill", "hstill")
+SENSITIVITY_PARAM_KEYS = ("dh_dparam", "parameter_name", "parameter_value", "dhv_dparam", "dhu_dparam")
 
 
 def _f64(a):
@@ -300,3 +302,27 @@ def save_sensitivity_results(case_path, pred_array=None, zb_cells=None, wstill=N
         write_json_pretty(os.path.join(case_path, "sensitivity_results.json"),
                           {"params_vector": _f64(params_vector), "parameter_name": str(parameter_name),
                            "sensitivity_results": _f64(sensitivity).ravel(order="F")})
+
+
+
+def postprocess_sensitivity_results_swe_2D(flat, sensitivity, params_vector, active_param_name, case_path, write_vtk=True):
+    """Per parameter i: sensitivity_results_<name>_<i>.json (dh / dhu / dhv _dparam, parameter_name, parameter_value) and the
+    .vtk with the three scalars (process_sensitivity_results_2D.jl:33-78).  sensitivity: [3N, n_params], the reference's layout
+    (hg_solve_tsit5_sens returns its transpose)."""
+    S = np.asarray(sensitivity, dtype=np.float64)
+    N = int(flat["n_cells"])
+    p = _f64(params_vector)
+    if S.shape != (3 * N, p.size):
+        raise ValueError(f"sensitivity has shape {S.shape}, expected {(3 * N, p.size)}")
+    for i in range(1, p.size + 1):
+        dh, dhu, dhv = (np.ascontiguousarray(S[k * N:(k + 1) * N, i - 1]) for k in range(3))
+        if write_vtk:
+            ld = int(flat["ld"])
+            export_to_vtk_2D(os.path.join(case_path, f"sensitivity_results_{active_param_name}_{i}.vtk"),
+                             _f64(flat["node_coords"]).reshape(-1, 3), _i64(flat["cell_nodes"]).reshape(ld, N).T, _i64(flat["cell_nfaces"]),
+                             "parameter_number", "integer", i, [dh, dhu, dhv], ["dh_dparam", "dhu_dparam", "dhv_dparam"], [], [],
+                             index_base=int(flat.get("index_base", 1)))
+        vals = {"dh_dparam": dh, "parameter_name": f"{active_param_name}_{i}", "parameter_value": float(p[i - 1]), "dhv_dparam": dhv,
+                "dhu_dparam": dhu}
+        write_json_pretty(os.path.join(case_path, f"sensitivity_results_{active_param_name}_{i}.json"),
+                          {k: vals[k] for k in SENSITIVITY_PARAM_KEYS})

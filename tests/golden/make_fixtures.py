@@ -84,6 +84,13 @@ def json_digests():
         d = json.loads(raw)
         out[name + "/sensitivity"] = dict(sha256=hashlib.sha256(raw).hexdigest(), bytes=len(raw), keys=list(d.keys()),
                                           parameter_name=d["parameter_name"])
+        # per-parameter files of postprocess_sensitivity_results_swe_2D (derived from the same matrix)
+        k = 1
+        while os.path.exists(os.path.join(REF, rel, f"sensitivity_results_ManningN_{k}.json")):
+            raw = open(os.path.join(REF, rel, f"sensitivity_results_ManningN_{k}.json"), "rb").read()
+            out[f"{name}/sensitivity_ManningN_{k}"] = dict(sha256=hashlib.sha256(raw).hexdigest(), bytes=len(raw),
+                                                         keys=list(json.loads(raw).keys()))
+            k += 1
     with open(os.path.join(HERE, "json_digests.json"), "w") as f:
         json.dump(out, f, indent=1)
 

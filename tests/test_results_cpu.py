@@ -113,6 +113,26 @@ def test_sensitivity_json_is_reproduced_byte_for_byte(res, name, tmp_path):
     assert _sha(tmp_path / "sensitivity_results.json") == (d["sha256"], d["bytes"])
 
 
+@pytest.mark.parametrize("name", ["savannah_sens", "oneD_bump_sens", "oneD_uniform_sens"])
+def test_per_parameter_sensitivity_files_are_reproduced_byte_for_byte(res, name, tmp_path):
+    """postprocess_sensitivity_results_swe_2D: sensitivity_results_ManningN_<i>.json of the reference, from the matrix."""
+    dg = _digests()
+    z = np.load(os.path.join(cases.GOLD, name, "sensitivity.npz"))
+    p = z["params_vector"]
+    S = z["sensitivity_results"].reshape(p.size, -1).T                     # [3N, n_params]
+    res.postprocess_sensitivity_results_swe_2D({"n_cells": S.shape[0] // 3}, S, p, "ManningN", tmp_path, write_vtk=False)
+    n = 0
+    for i in range(1, p.size + 1):
+        d = dg.get(f"{name}/sensitivity_ManningN_{i}")
+        if d is None:
+            continue
+        out = tmp_path / f"sensitivity_results_ManningN_{i}.json"
+        assert list(json.load(open(out)).keys()) == d["keys"] == list(res.SENSITIVITY_PARAM_KEYS)
+        assert _sha(out) == (d["sha256"], d["bytes"]), i
+        n += 1
+    assert n >= 2
+
+
 def test_json3_integer_quirk_follows_the_first_element(res, tmp_path):
     """JSON3.pretty prints whole values as integers unless the array starts with a non-whole number: zb_cells (0.0 first) ->
     "0", the zero discharges inside forward_simulation_results (0.13 first) -> "0.0" -- both in the reference's
