@@ -329,3 +329,37 @@ def test_postprocess_writes_the_truth_file_of_the_reference(res, tmp_path):
         assert np.array_equal(a, out[k])
     for k in ("zb_cell_truth", "S0_cells_truth", "hstill_truth", "wstill_truth", "xi_truth", "ManningN_cells_truth"):
         assert np.array_equal(np.asarray(d[k]), t[k]), k               # geometry from the product reader: to the bit
+
+
+def _case_dir(tmp_path, name, res):
+    """A case directory like the reference's examples/SWE_2D/forward_simulation/<case>: the committed inputs + run_control.json
+    (+ the initial-condition file, rewritten from the fixture with the 'julia' number style of the original)."""
+    import shutil
+    src = os.path.join(cases.GOLD, name)
+    dst = tmp_path / name
+    shutil.copytree(src, dst)
+    ic = os.path.join(src, "ic.npz")
+    if os.path.exists(ic):
+        z = np.load(ic)
+        res.write_json_pretty(dst / "forward_simulation_initial_condition.json", {k: z[k] for k in z.files}, style="julia")
+    return str(dst)
+
+
+def test_forward_driver_reads_the_case_and_refuses_to_run_without_a_gpu(res, tmp_path):
+    """run_forward_case up to the device: run_control.json, SRH-2D files and the initial condition are read by the product
+    code; without a CUDA device the driver fails loudly (no CPU fallback).  The full run is tests/test_gpu_zzz_forward_driver.py."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    hg = _pkg.load()
+    from hydrograd_jl_b200 import forward
+    for name in ("savannah", "oneD_bump"):
+        with pytest.raises(hg.HydrogradError) as e:
+            forward.run_forward_case(_case_dir(tmp_path, name, res))
+        assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+    d = _case_dir(tmp_path / "x", "oneD_bump", res)
+    rc = json.load(open(os.path.join(d, "run_control.json")))
+    rc["control_variables"]["bPerform_Forward_Simulation"] = False
+    json.dump(rc, open(os.path.join(d, "run_control.json"), "w"))
+    with pytest.raises(ValueError):
+        forward.run_forward_case(d)
