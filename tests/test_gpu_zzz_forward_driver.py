@@ -66,3 +66,23 @@ def test_forward_case_with_state_dependent_manning(mods, tmp_path):
     for k, tol in (("ManningN_cells_truth", 1e-4), ("h_ks_cells_truth", 1e-4), ("friction_factor_cells_truth", 1e-3), ("Re_cells_truth", 1e-3)):
         a, b = np.asarray(got[k]), t[k]
         assert np.abs(a - b).max() <= tol * np.abs(b).max(), k
+
+
+def test_sensitivity_case_end_to_end(mods, tmp_path):
+    """sensitivity_analysis/ManningN/Savana_River in one call: run_control.json -> hg_solve_tsit5_sens -> sensitivity_results.json
+    and the six per-parameter files, against the reference's committed matrix."""
+    import shutil
+    hg, forward, results = mods
+    from hydrograd_jl_b200 import sensitivity
+    d = _case_dir(tmp_path, "savannah", results)
+    shutil.copyfile(os.path.join(cases.GOLD, "savannah_sens", "run_control.json"), os.path.join(d, "run_control.json"))
+    out = sensitivity.run_sensitivity_case(d, write_vtk=True)
+    z = np.load(os.path.join(cases.GOLD, "savannah_sens", "sensitivity.npz"))
+    assert np.array_equal(out["params_vector"], z["params_vector"])
+    got = json.load(open(os.path.join(d, "sensitivity_results.json")))
+    assert list(got.keys()) == list(results.SENSITIVITY_KEYS) and got["parameter_name"] == "ManningN"
+    a, b = np.asarray(got["sensitivity_results"], dtype=np.float64), z["sensitivity_results"]
+    print("sensitivity driver vs the reference's file: %.1e of %.1f" % (np.abs(a - b).max(), np.abs(b).max()), out["stats"])
+    assert a.shape == b.shape and np.abs(a - b).max() <= 1e-5 * np.abs(b).max()
+    for i in range(1, 7):
+        assert os.path.exists(os.path.join(d, f"sensitivity_results_ManningN_{i}.json")) and os.path.exists(os.path.join(d, f"sensitivity_results_ManningN_{i}.vtk"))

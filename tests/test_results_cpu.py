@@ -363,3 +363,22 @@ def test_forward_driver_reads_the_case_and_refuses_to_run_without_a_gpu(res, tmp
     json.dump(rc, open(os.path.join(d, "run_control.json"), "w"))
     with pytest.raises(ValueError):
         forward.run_forward_case(d)
+
+
+def test_sensitivity_driver_reads_the_case_and_refuses_to_run_without_a_gpu(res, tmp_path):
+    import shutil
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    hg = _pkg.load()
+    from hydrograd_jl_b200 import sensitivity
+    d = _case_dir(tmp_path, "savannah", res)
+    shutil.copyfile(os.path.join(cases.GOLD, "savannah_sens", "run_control.json"), os.path.join(d, "run_control.json"))
+    with pytest.raises(hg.HydrogradError) as e:
+        sensitivity.run_sensitivity_case(d)
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+    rc = json.load(open(os.path.join(d, "run_control.json")))
+    flat = {"n_cells": 5}
+    opts = rc["sensitivity_analysis_options"]
+    assert np.array_equal(sensitivity._params_vector(opts, "ManningN", flat, d), [0.02, 0.04, 0.05, 0.03, 0.045, 0.05])
+    assert np.array_equal(sensitivity._params_vector(opts, "zb", flat, d), np.zeros(5))
