@@ -27,7 +27,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -122,7 +124,14 @@ bool write_items(FILE* f, int64_t n, size_t reserve_per_item, F one) {
     if (T == 1) work(0);
     else {
       std::vector<std::thread> th;
-      for (unsigned t = 0; t < T; ++t) th.emplace_back(work, t);
+      th.reserve(T);
+      for (unsigned t = 0; t < T; ++t) {
+        try {
+          th.emplace_back(work, t);
+        } catch (const std::system_error&) {     // no more threads: format this chunk here
+          work(t);
+        }
+      }
       for (auto& x : th) x.join();
     }
     for (unsigned t = 0; t < T; ++t)
@@ -245,28 +254,33 @@ int hg_json_end_array(hg_json* w) {
 }
 
 int hg_json_numbers(hg_json* w, const double* x, int64_t n) {
-  if (!w || n < 0 || (n > 0 && !x)) return HG_ERR_ARG;
-  if (w->first.empty()) { w->err = "hg_json_numbers: no open array"; return HG_ERR_STATE; }
-  for (int64_t i = 0; i < n; ++i)
-    if (!std::isfinite(x[i])) {          // JSON3: "NaN not allowed to be written in JSON spec"
-      char b[24];
-      b[format_julia(x[i], b)] = 0;
-      w->err = std::string(b) + " not allowed to be written in JSON spec (element " + std::to_string(i + 1) + ")";
-      return HG_ERR_ARG;
-    }
-  if (n == 0) return HG_OK;
-  const bool was_first = w->first.back();
-  w->first.back() = false;
-  const int st = w->number_style(x[0]);
-  const std::string pad((size_t)w->depth * 4, ' ');
-  const bool ok = write_items(w->f, n, pad.size() + 26, [&](int64_t i, std::string& s) {
-    s += (i == 0 && was_first) ? "\n" : ",\n";
-    s += pad;
-    char b[32];
-    s.append(b, (size_t)format_any(x[i], st, b));
-  });
-  if (!ok) { w->err = "hg_json: write failed"; w->failed = true; return HG_ERR_ARG; }
-  return HG_OK;
+  try {
+    if (!w || n < 0 || (n > 0 && !x)) return HG_ERR_ARG;
+    if (w->first.empty()) { w->err = "hg_json_numbers: no open array"; return HG_ERR_STATE; }
+    for (int64_t i = 0; i < n; ++i)
+      if (!std::isfinite(x[i])) {          // JSON3: "NaN not allowed to be written in JSON spec"
+        char b[24];
+        b[format_julia(x[i], b)] = 0;
+        w->err = std::string(b) + " not allowed to be written in JSON spec (element " + std::to_string(i + 1) + ")";
+        return HG_ERR_ARG;
+      }
+    if (n == 0) return HG_OK;
+    const bool was_first = w->first.back();
+    w->first.back() = false;
+    const int st = w->number_style(x[0]);
+    const std::string pad((size_t)w->depth * 4, ' ');
+    const bool ok = write_items(w->f, n, pad.size() + 26, [&](int64_t i, std::string& s) {
+      s += (i == 0 && was_first) ? "\n" : ",\n";
+      s += pad;
+      char b[32];
+      s.append(b, (size_t)format_any(x[i], st, b));
+    });
+    if (!ok) { w->err = "hg_json: write failed"; w->failed = true; return HG_ERR_ARG; }
+    return HG_OK;
+  } catch (const std::exception& e) {
+    if (w) w->err = std::string("hg_json_numbers: ") + e.what();
+    return HG_ERR_ARG;
+  }
 }
 
 int hg_json_number(hg_json* w, double x) {
@@ -308,88 +322,93 @@ int hg_write_vtk_2d(const char* path, int64_t n_nodes, const double* node_xyz, i
                     const int64_t* cell_nodes, const int64_t* cell_nnodes, const char* field_name, const char* field_type,
                     double field_value, const hg_named_array* scalars, int64_t n_scalars, const hg_named_array* vectors,
                     int64_t n_vectors, char* err, int64_t errlen) {
-  if (!path || n_nodes < 0 || n_cells < 0 || ld < 1 || (n_nodes > 0 && !node_xyz) || (n_cells > 0 && (!cell_nodes || !cell_nnodes)) ||
-      n_scalars < 0 || n_vectors < 0 || (n_scalars > 0 && !scalars) || (n_vectors > 0 && !vectors) || !field_name || !field_type) {
-    set_err(err, errlen, "hg_write_vtk_2d: bad argument");
-    return HG_ERR_ARG;
-  }
-  for (int64_t c = 0; c < n_cells; ++c) {
-    if (cell_nnodes[c] < 0 || cell_nnodes[c] > ld) { set_err(err, errlen, "hg_write_vtk_2d: node count of cell " + std::to_string(c + 1) + " out of range"); return HG_ERR_ARG; }
-    for (int64_t j = 0; j < cell_nnodes[c]; ++j) {
-      const int64_t id = cell_nodes[c + n_cells * j] - index_base;
-      if (id < 0 || id >= n_nodes) { set_err(err, errlen, "hg_write_vtk_2d: node id of cell " + std::to_string(c + 1) + " out of range"); return HG_ERR_ARG; }
+  try {
+    if (!path || n_nodes < 0 || n_cells < 0 || ld < 1 || (n_nodes > 0 && !node_xyz) || (n_cells > 0 && (!cell_nodes || !cell_nnodes)) ||
+        n_scalars < 0 || n_vectors < 0 || (n_scalars > 0 && !scalars) || (n_vectors > 0 && !vectors) || !field_name || !field_type) {
+      set_err(err, errlen, "hg_write_vtk_2d: bad argument");
+      return HG_ERR_ARG;
     }
-  }
-  for (int64_t k = 0; k < n_scalars + n_vectors; ++k) {
-    const hg_named_array& a = k < n_scalars ? scalars[k] : vectors[k - n_scalars];
-    if (!a.name || (n_cells > 0 && !a.data)) { set_err(err, errlen, "hg_write_vtk_2d: field without name or data"); return HG_ERR_ARG; }
-  }
-  FILE* f = std::fopen(path, "wb");
-  if (!f) { set_err(err, errlen, std::string("hg_write_vtk_2d: cannot open ") + path); return HG_ERR_ARG; }
-  bool ok = true;
-  std::string hd = "# vtk DataFile Version 2.0\n2D Unstructured Mesh\nASCII\nDATASET UNSTRUCTURED_GRID\n";
-  if (field_name[0]) {
-    hd += "FIELD FieldData 1\n";
-    hd += std::string(field_name) + " 1 1 " + field_type + "\n";
-    char b[32];
-    // the reference passes the save index (an Int); a Float64 value would print the Julia way
-    const int n = (std::strcmp(field_type, "integer") == 0 && field_value == std::nearbyint(field_value)) ? format_json3(field_value, b) : format_julia(field_value, b);
-    hd.append(b, (size_t)n);
-    hd += "\n";
-  }
-  hd += "POINTS " + std::to_string(n_nodes) + " double\n";
-  ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
-  // nodeCoordinates is n_nodes x 3; rows as the reader keeps them (x y z per node)
-  ok = ok && write_items(f, n_nodes, 80, [&](int64_t i, std::string& s) {
-    char b[32];
-    for (int k = 0; k < 3; ++k) {
-      s.append(b, (size_t)format_julia(node_xyz[3 * i + k], b));
-      s += k < 2 ? ' ' : '\n';
+    for (int64_t c = 0; c < n_cells; ++c) {
+      if (cell_nnodes[c] < 0 || cell_nnodes[c] > ld) { set_err(err, errlen, "hg_write_vtk_2d: node count of cell " + std::to_string(c + 1) + " out of range"); return HG_ERR_ARG; }
+      for (int64_t j = 0; j < cell_nnodes[c]; ++j) {
+        const int64_t id = cell_nodes[c + n_cells * j] - index_base;
+        if (id < 0 || id >= n_nodes) { set_err(err, errlen, "hg_write_vtk_2d: node id of cell " + std::to_string(c + 1) + " out of range"); return HG_ERR_ARG; }
+      }
     }
-  });
-  int64_t total = 0;
-  for (int64_t c = 0; c < n_cells; ++c) total += cell_nnodes[c] + 1;
-  hd = "CELLS " + std::to_string(n_cells) + " " + std::to_string(total) + "\n";
-  ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
-  ok = ok && write_items(f, n_cells, 64, [&](int64_t c, std::string& s) {
-    s += std::to_string(cell_nnodes[c]);
-    s += ' ';                                            // "$(length(cell)) $(join(cell .- 1, ' '))": the blank stays for an empty cell
-    for (int64_t j = 0; j < cell_nnodes[c]; ++j) {
-      if (j) s += ' ';
-      s += std::to_string(cell_nodes[c + n_cells * j] - index_base);   // VTK ids are 0-based
+    for (int64_t k = 0; k < n_scalars + n_vectors; ++k) {
+      const hg_named_array& a = k < n_scalars ? scalars[k] : vectors[k - n_scalars];
+      if (!a.name || (n_cells > 0 && !a.data)) { set_err(err, errlen, "hg_write_vtk_2d: field without name or data"); return HG_ERR_ARG; }
     }
-    s += '\n';
-  });
-  hd = "CELL_TYPES " + std::to_string(n_cells) + "\n";
-  ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
-  ok = ok && write_items(f, n_cells, 2, [&](int64_t, std::string& s) { s += "7\n"; });     // VTK_POLYGON
-  hd = "CELL_DATA " + std::to_string(n_cells) + "\n";
-  ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
-  for (int64_t k = 0; k < n_scalars && ok; ++k) {
-    hd = std::string("SCALARS ") + scalars[k].name + " double 1\nLOOKUP_TABLE default\n";
-    ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
-    const double* x = scalars[k].data;
-    ok = ok && write_items(f, n_cells, 26, [&](int64_t i, std::string& s) {
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { set_err(err, errlen, std::string("hg_write_vtk_2d: cannot open ") + path); return HG_ERR_ARG; }
+    bool ok = true;
+    std::string hd = "# vtk DataFile Version 2.0\n2D Unstructured Mesh\nASCII\nDATASET UNSTRUCTURED_GRID\n";
+    if (field_name[0]) {
+      hd += "FIELD FieldData 1\n";
+      hd += std::string(field_name) + " 1 1 " + field_type + "\n";
       char b[32];
-      s.append(b, (size_t)format_julia(x[i], b));
+      // the reference passes the save index (an Int); a Float64 value would print the Julia way
+      const int n = (std::strcmp(field_type, "integer") == 0 && field_value == std::nearbyint(field_value)) ? format_json3(field_value, b) : format_julia(field_value, b);
+      hd.append(b, (size_t)n);
+      hd += "\n";
+    }
+    hd += "POINTS " + std::to_string(n_nodes) + " double\n";
+    ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
+    // nodeCoordinates is n_nodes x 3; rows as the reader keeps them (x y z per node)
+    ok = ok && write_items(f, n_nodes, 80, [&](int64_t i, std::string& s) {
+      char b[32];
+      for (int k = 0; k < 3; ++k) {
+        s.append(b, (size_t)format_julia(node_xyz[3 * i + k], b));
+        s += k < 2 ? ' ' : '\n';
+      }
+    });
+    int64_t total = 0;
+    for (int64_t c = 0; c < n_cells; ++c) total += cell_nnodes[c] + 1;
+    hd = "CELLS " + std::to_string(n_cells) + " " + std::to_string(total) + "\n";
+    ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
+    ok = ok && write_items(f, n_cells, 64, [&](int64_t c, std::string& s) {
+      s += std::to_string(cell_nnodes[c]);
+      s += ' ';                                            // "$(length(cell)) $(join(cell .- 1, ' '))": the blank stays for an empty cell
+      for (int64_t j = 0; j < cell_nnodes[c]; ++j) {
+        if (j) s += ' ';
+        s += std::to_string(cell_nodes[c + n_cells * j] - index_base);   // VTK ids are 0-based
+      }
       s += '\n';
     });
-  }
-  for (int64_t k = 0; k < n_vectors && ok; ++k) {
-    hd = std::string("VECTORS ") + vectors[k].name + " double\n";
+    hd = "CELL_TYPES " + std::to_string(n_cells) + "\n";
     ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
-    const double* x = vectors[k].data;                     // n_cells x 2, column-major (hcat(u, v))
-    ok = ok && write_items(f, n_cells, 56, [&](int64_t i, std::string& s) {
-      char b[32];
-      s.append(b, (size_t)format_julia(x[i], b));
-      s += ' ';
-      s.append(b, (size_t)format_julia(x[i + n_cells], b));
-      s += " 0.0\n";
-    });
+    ok = ok && write_items(f, n_cells, 2, [&](int64_t, std::string& s) { s += "7\n"; });     // VTK_POLYGON
+    hd = "CELL_DATA " + std::to_string(n_cells) + "\n";
+    ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
+    for (int64_t k = 0; k < n_scalars && ok; ++k) {
+      hd = std::string("SCALARS ") + scalars[k].name + " double 1\nLOOKUP_TABLE default\n";
+      ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
+      const double* x = scalars[k].data;
+      ok = ok && write_items(f, n_cells, 26, [&](int64_t i, std::string& s) {
+        char b[32];
+        s.append(b, (size_t)format_julia(x[i], b));
+        s += '\n';
+      });
+    }
+    for (int64_t k = 0; k < n_vectors && ok; ++k) {
+      hd = std::string("VECTORS ") + vectors[k].name + " double\n";
+      ok = ok && std::fwrite(hd.data(), 1, hd.size(), f) == hd.size();
+      const double* x = vectors[k].data;                     // n_cells x 2, column-major (hcat(u, v))
+      ok = ok && write_items(f, n_cells, 56, [&](int64_t i, std::string& s) {
+        char b[32];
+        s.append(b, (size_t)format_julia(x[i], b));
+        s += ' ';
+        s.append(b, (size_t)format_julia(x[i + n_cells], b));
+        s += " 0.0\n";
+      });
+    }
+    if (std::fclose(f) != 0) ok = false;
+    if (!ok) { set_err(err, errlen, std::string("hg_write_vtk_2d: write failed: ") + path); return HG_ERR_ARG; }
+    return HG_OK;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, std::string("hg_write_vtk_2d: ") + e.what());
+    return HG_ERR_ARG;
   }
-  if (std::fclose(f) != 0) ok = false;
-  if (!ok) { set_err(err, errlen, std::string("hg_write_vtk_2d: write failed: ") + path); return HG_ERR_ARG; }
-  return HG_OK;
 }
 
 // ---------------------------------------------------------------- derived fields of the forward driver
