@@ -22,6 +22,7 @@
 // Formatting runs in parallel chunks (std::thread) into per-chunk buffers that are written in order: the reference's
 // println-per-value loop is the bottleneck of its output on large meshes, 10^8 numbers should take seconds.
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
@@ -112,14 +113,19 @@ bool write_items(FILE* f, int64_t n, size_t reserve_per_item, F one) {
   const unsigned T = n_threads_for(n);
   const int64_t per_round = (int64_t)T * 262144;       // bounds the memory of the chunk buffers
   std::vector<std::string> buf(T);
+  std::atomic<bool> failed{false};
   for (int64_t base = 0; base < n; base += per_round) {
     const int64_t m = std::min(per_round, n - base), chunk = (m + T - 1) / T;
     auto work = [&](unsigned t) {
-      std::string& s = buf[t];
-      s.clear();
-      const int64_t a = base + (int64_t)t * chunk, b = std::min(base + m, a + chunk);
-      if (a < b) s.reserve((size_t)(b - a) * reserve_per_item);
-      for (int64_t i = a; i < b; ++i) one(i, s);
+      try {                                       // an exception must not leave a worker thread
+        std::string& s = buf[t];
+        s.clear();
+        const int64_t a = base + (int64_t)t * chunk, b = std::min(base + m, a + chunk);
+        if (a < b) s.reserve((size_t)(b - a) * reserve_per_item);
+        for (int64_t i = a; i < b; ++i) one(i, s);
+      } catch (...) {
+        failed.store(true);
+      }
     };
     if (T == 1) work(0);
     else {
@@ -134,6 +140,7 @@ bool write_items(FILE* f, int64_t n, size_t reserve_per_item, F one) {
       }
       for (auto& x : th) x.join();
     }
+    if (failed.load()) return false;
     for (unsigned t = 0; t < T; ++t)
       if (!buf[t].empty() && std::fwrite(buf[t].data(), 1, buf[t].size(), f) != buf[t].size()) return false;
   }
