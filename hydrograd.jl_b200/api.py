@@ -159,21 +159,27 @@ class Context:
     def rhs_jvp(self, Q, v, params=None, active=None, pdot=None, t=0.0, want_rhs=True):
         """Forward mode on a strict context: (dQdt, J_Q v + J_p pdot) -- one partial of a ForwardDiff.Dual pass (hg_rhs_jvp)."""
         p, n, a = self._params(params, active)
+        Q, v = _f64(Q), _f64(v)
+        if Q.size != 3 * self.N or v.size != 3 * self.N:
+            raise HydrogradError(1, f"Q / v have lengths {Q.size} / {v.size}, expected {3 * self.N}")
         pd = _f64(pdot) if pdot is not None else None
         if pd is not None and pd.size != n:
             raise ValueError(f"pdot has length {pd.size}, expected {n}")
         out = np.empty(3 * self.N) if want_rhs else None
         jv = np.empty(3 * self.N)
-        self._ck(self.lib.hg_rhs_jvp(self._h, _p(_f64(Q)), _p(p), n, a, float(t), _p(_f64(v)), _p(pd), _p(out), _p(jv)))
+        self._ck(self.lib.hg_rhs_jvp(self._h, _p(Q), _p(p), n, a, float(t), _p(v), _p(pd), _p(out), _p(jv)))
         return (out, jv) if want_rhs else jv
 
     def solve_tsit5_sens(self, Q0, params, active, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3):
         """The reference's sensitivity driver (ForwardDiff.jacobian around the Tsit5 solve, swe_2D_sensitivity.jl:34-80) on a
         strict context: returns (Q(t1) [3N], S [n_params, 3N] with S[k] = dQ(t1)/dp_k, stats)."""
         p, n, a = self._params(params, active)
+        Q0 = _f64(Q0)
+        if Q0.size != 3 * self.N:
+            raise HydrogradError(1, f"Q0 has length {Q0.size}, expected {3 * self.N}")
         QT, S = np.empty(3 * self.N), np.empty((max(n, 1), 3 * self.N))
         stats = np.zeros(3, dtype=np.int64)
-        self._ck(self.lib.hg_solve_tsit5_sens(self._h, _p(_f64(Q0)), _p(p), n, a, float(t0), float(t1), float(dt), int(bool(adaptive)),
+        self._ck(self.lib.hg_solve_tsit5_sens(self._h, _p(Q0), _p(p), n, a, float(t0), float(t1), float(dt), int(bool(adaptive)),
                                               float(abstol), float(reltol), _p(QT), _p(S), _p(stats, L.c_i64p)))
         return QT, S[:n], dict(accepted=int(stats[0]), rejected=int(stats[1]), rhs=int(stats[2]))
 
