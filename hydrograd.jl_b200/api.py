@@ -170,6 +170,20 @@ class Context:
         self._ck(self.lib.hg_rhs_jvp(self._h, _p(Q), _p(p), n, a, float(t), _p(v), _p(pd), _p(out), _p(jv)))
         return (out, jv) if want_rhs else jv
 
+    def rhs_jvp_multi(self, Q, V, params=None, active=None, Pdot=None, t=0.0):
+        """K directions in one call (a ForwardDiff chunk): V [K, 3N], Pdot [K, n_params] or None -> (dQdt, JV [K, 3N])."""
+        p, n, a = self._params(params, active)
+        Q, V = _f64(Q), _f64(V)
+        if V.ndim != 2 or Q.size != 3 * self.N or V.shape[1] != 3 * self.N:
+            raise HydrogradError(1, f"Q / V have shapes {Q.shape} / {V.shape}, expected ({3 * self.N},) / (K, {3 * self.N})")
+        K = V.shape[0]
+        Pd = _f64(Pdot) if Pdot is not None and n > 0 else None
+        if Pd is not None and Pd.shape != (K, n):
+            raise ValueError(f"Pdot has shape {Pd.shape}, expected {(K, n)}")
+        out, JV = np.empty(3 * self.N), np.empty((K, 3 * self.N))
+        self._ck(self.lib.hg_rhs_jvp_multi(self._h, _p(Q), _p(p), n, a, float(t), K, _p(V), _p(Pd), _p(out), _p(JV)))
+        return out, JV
+
     def solve_tsit5_sens(self, Q0, params, active, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3):
         """The reference's sensitivity driver (ForwardDiff.jacobian around the Tsit5 solve, swe_2D_sensitivity.jl:34-80) on a
         strict context: returns (Q(t1) [3N], S [n_params, 3N] with S[k] = dQ(t1)/dp_k, stats)."""

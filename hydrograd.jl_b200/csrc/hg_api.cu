@@ -664,6 +664,38 @@ int hg_rhs_jvp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   return check_err_flag(ctx);
 }
 
+// K directions in one call (a ForwardDiff chunk: Dual{Tag, Float64, K}): Q is uploaded once, the K sweeps run back to back
+// on the stream, one download.  V[K][3N], Pdot[K][n_params] or NULL, JV[K][3N].
+int hg_rhs_jvp_multi(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32_t active, double t, int64_t K,
+                     const double* V, const double* Pdot, double* dQdt, double* JV) {
+  (void)t;
+  if (!ctx || !Q || !V || !JV || K < 1) return HG_ERR_ARG;
+  if (ctx->opt.path != 1) { ctx->err = "hg_rhs_jvp_multi needs the plain path (strict = 1)"; return HG_ERR_ARG; }
+  TRY(no_closure(ctx, "hg_rhs_jvp_multi"));
+  if (active == HG_PARAM_UDE) { ctx->err = "hg_rhs_jvp_multi: the UDE network has no forward mode"; return HG_ERR_ARG; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  TRY(bind_params(ctx, params, np, active));
+  hg::PlainDev& p = ctx->pd;
+  const size_t n3 = 3 * (size_t)ctx->N;
+  const int64_t npar = ctx->active == HG_PARAM_NONE ? 0 : ctx->n_params;
+  hg::DBuf<double> dV, dJ, dP;
+  CK(ctx, dV.alloc((size_t)K * n3)); CK(ctx, dJ.alloc((size_t)K * n3));
+  const bool with_p = Pdot && npar > 0;
+  if (with_p) {
+    CK(ctx, dP.alloc((size_t)(K * npar)));
+    CK(ctx, cudaMemcpyAsync(dP.p, Pdot, (size_t)(K * npar) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(ctx, cudaMemcpyAsync(p.Q.p, Q, n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dV.p, V, (size_t)K * n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->state_set = true;
+  for (int64_t k = 0; k < K; ++k)
+    TRY(hg::plain_jvp(ctx, p.Q.p, dV.p + k * n3, with_p ? dP.p + k * npar : nullptr, (k == 0 && dQdt) ? p.dQ.p : nullptr, dJ.p + k * n3));
+  if (dQdt) CK(ctx, cudaMemcpyAsync(dQdt, p.dQ.p, n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(JV, dJ.p, (size_t)K * n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_err_flag(ctx);
+}
+
 // Forward sensitivity solve: the reference's sensitivity driver on the device.  swe_2D_sensitivity.jl:34-80 wraps
 // solve(prob, Tsit5(), adaptive=..., dt=dt; abstol, reltol) in ForwardDiff.jacobian, i.e. the state is a vector of Duals with
 // one partial per parameter: values and partials advance together, the error estimate -- hence every step size -- includes

@@ -180,13 +180,20 @@ _part(x::AbstractVector{<:ForwardDiff.Dual}, k) = collect(Float64, ForwardDiff.p
 _part(x::AbstractVector, k) = zeros(length(x))
 function _rhs_dual(::Type{ForwardDiff.Dual{Tg,V,NP}}, Q::AbstractVector, p::AbstractVector, t::Real, ctx::Context) where {Tg,V,NP}
     Qv, pv = _vals(Q), _vals(p)
-    y = Vector{Float64}(undef, length(Qv))
-    cols = ntuple(NP) do k
-        y_k, jv = swe_2d_rhs_jvp(Qv, pv, Float64(t), _part(Q, k), _part(p, k), ctx)
-        copyto!(y, y_k)
-        jv
+    n3 = length(Qv); np = ctx.active == 0 ? 0 : length(pv)
+    y = Vector{Float64}(undef, n3)
+    Vm = Matrix{Float64}(undef, n3, NP); Pm = Matrix{Float64}(undef, max(np, 1), NP); JV = Matrix{Float64}(undef, n3, NP)
+    for k in 1:NP                                          # column k = partial k (the C layout [K][3N] is this matrix)
+        Vm[:, k] .= _part(Q, k)
+        np > 0 && (Pm[1:np, k] .= _part(p, k))
     end
-    return [ForwardDiff.Dual{Tg}(y[i], ForwardDiff.Partials(ntuple(k -> cols[k][i], NP))) for i in eachindex(y)]
+    GC.@preserve Qv pv Vm Pm y JV begin
+        rc = ccall((:hg_rhs_jvp_multi, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   ctx.handle, Qv, pv, np, ctx.active, Float64(t), NP, Vm, (np == 0 ? C_NULL : pointer(Pm)), y, JV)
+        _check(rc, ctx.handle)
+    end
+    return [ForwardDiff.Dual{Tg}(y[i], ForwardDiff.Partials(ntuple(k -> JV[i, k], NP))) for i in eachindex(y)]
 end
 swe_2d_rhs(Q::AbstractVector{D}, p::AbstractVector, t::Real, ctx::Context) where {D<:ForwardDiff.Dual} = _rhs_dual(D, Q, p, t, ctx)
 swe_2d_rhs(Q::AbstractVector{<:AbstractFloat}, p::AbstractVector{D}, t::Real, ctx::Context) where {D<:ForwardDiff.Dual} = _rhs_dual(D, Q, p, t, ctx)

@@ -237,6 +237,9 @@ HG_API int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_
  * strict = 1 (plain tables, reference evaluation order); no state-dependent Manning closure, no UDE network.            */
 HG_API int hg_rhs_jvp(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params, int32_t active_param, double t,
                const double* v, const double* pdot, double* dQdt, double* dQdt_dot);
+/* K directions at once (one ForwardDiff chunk): V[K][3N], Pdot[K][n_params] or NULL, JV[K][3N]; dQdt may be NULL */
+HG_API int hg_rhs_jvp_multi(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params, int32_t active_param, double t,
+                     int64_t K, const double* V, const double* Pdot, double* dQdt, double* JV);
 /* Forward sensitivity solve = the reference's sensitivity driver (swe_2D_sensitivity.jl:34-80: ForwardDiff.jacobian around
  * solve(prob, Tsit5(), adaptive, dt; abstol, reltol)) on the device: values and one partial per entry of the active
  * parameter (zb, ManningN or Q) advance together, the error estimate includes the partials like DiffEqBase's norm of Dual

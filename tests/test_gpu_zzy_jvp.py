@@ -56,6 +56,13 @@ def test_device_forward_mode_matches_the_oracle(hg, name, mode):
               " tangent rel. err %.1e" % (np.abs(jv - ref_jv).max() / np.abs(ref_jv).max()))
         only = ctx.rhs_jvp(Q, v, p, mode, pdot, want_rhs=False)
         assert np.array_equal(only, jv)
+        # a chunk of three directions in one call (hg_rhs_jvp_multi): the same sweeps, the same bits
+        V3 = np.stack([v, -2.0 * v, rng.standard_normal(3 * N)])
+        P3 = np.stack([pdot, -2.0 * pdot, rng.standard_normal(p.size)]) if p is not None else None
+        dQm, JV = ctx.rhs_jvp_multi(Q, V3, p, mode, P3)
+        assert np.array_equal(dQm, dQ) and np.array_equal(JV[0], jv)
+        assert np.abs(JV[1] + 2.0 * jv).max() <= 1e-12 * np.abs(jv).max()
+        assert np.array_equal(JV[2], ctx.rhs_jvp(Q, V3[2], p, mode, None if P3 is None else P3[2], want_rhs=False))
 
 
 def test_device_forward_mode_is_the_transpose_of_the_vjp_kernel(hg):
