@@ -75,7 +75,7 @@ SYMBOLS = {
     "hg_rhs_jvp": (C.c_int, [_vp, c_f64p, c_f64p, C.c_int64, C.c_int32, C.c_double, c_f64p, c_f64p, c_f64p, c_f64p]),
     "hg_rhs_jvp_multi": (C.c_int, [_vp, c_f64p, c_f64p, C.c_int64, C.c_int32, C.c_double, C.c_int64, c_f64p, c_f64p, c_f64p, c_f64p]),
     "hg_solve_tsit5_sens": (C.c_int, [_vp, c_f64p, c_f64p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32,
-                                      C.c_double, C.c_double, c_f64p, c_f64p, c_i64p]),
+                                      C.c_double, C.c_double, c_f64p, C.c_int64, c_f64p, c_f64p, c_f64p, c_i64p]),
     "hg_set_state": (C.c_int, [_vp, c_f64p]),
     "hg_get_state": (C.c_int, [_vp, c_f64p]),
     "hg_set_params": (C.c_int, [_vp, c_f64p, C.c_int64, C.c_int32]),

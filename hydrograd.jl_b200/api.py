@@ -184,18 +184,22 @@ class Context:
         self._ck(self.lib.hg_rhs_jvp_multi(self._h, _p(Q), _p(p), n, a, float(t), K, _p(V), _p(Pd), _p(out), _p(JV)))
         return out, JV
 
-    def solve_tsit5_sens(self, Q0, params, active, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3):
+    def solve_tsit5_sens(self, Q0, params, active, t0, t1, dt, adaptive=True, abstol=1e-6, reltol=1e-3, t_save=()):
         """The reference's sensitivity driver (ForwardDiff.jacobian around the Tsit5 solve, swe_2D_sensitivity.jl:34-80) on a
-        strict context: returns (Q(t1) [3N], S [n_params, 3N] with S[k] = dQ(t1)/dp_k, stats)."""
+        strict context: returns (Q(t1) [3N], S [n_params, 3N] with S[k] = dQ(t1)/dp_k, stats); with t_save also the values at
+        the save times [len(t_save), 3N] (dense output), stored in stats["saves"]."""
         p, n, a = self._params(params, active)
         Q0 = _f64(Q0)
         if Q0.size != 3 * self.N:
             raise HydrogradError(1, f"Q0 has length {Q0.size}, expected {3 * self.N}")
         QT, S = np.empty(3 * self.N), np.empty((max(n, 1), 3 * self.N))
         stats = np.zeros(3, dtype=np.int64)
+        ts = _f64(np.asarray(t_save, dtype=np.float64)) if len(t_save) else None
+        saves = np.empty((len(t_save), 3 * self.N)) if len(t_save) else None
         self._ck(self.lib.hg_solve_tsit5_sens(self._h, _p(Q0), _p(p), n, a, float(t0), float(t1), float(dt), int(bool(adaptive)),
-                                              float(abstol), float(reltol), _p(QT), _p(S), _p(stats, L.c_i64p)))
-        return QT, S[:n], dict(accepted=int(stats[0]), rejected=int(stats[1]), rhs=int(stats[2]))
+                                              float(abstol), float(reltol), _p(ts), len(t_save), _p(saves), _p(QT), _p(S),
+                                              _p(stats, L.c_i64p)))
+        return QT, S[:n], dict(accepted=int(stats[0]), rejected=int(stats[1]), rhs=int(stats[2]), saves=saves)
 
     def rhs_vjp_into(self, Q, lam, Qbar_out):
         """hg_rhs_vjp with no active parameter into a caller-owned (e.g. pinned) buffer."""

@@ -703,8 +703,9 @@ int hg_rhs_jvp_multi(hg_ctx* ctx, const double* Q, const double* params, int64_t
 // stage = K forward-mode sweeps (plain_jvp, the first one also delivers the values), the Dual-aware norm reduced on the
 // device, the PI controller on the host (powers per hg_set_controller_pow).  Plain tables: the context needs strict = 1.
 int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int64_t np, int32_t active, double t0, double t1,
-                        double dt, int32_t adaptive, double abstol, double reltol, double* Q_T, double* S, int64_t* stats) {
-  if (!ctx || !Q0 || !S || !(t1 > t0) || !(dt > 0.0)) return HG_ERR_ARG;
+                        double dt, int32_t adaptive, double abstol, double reltol, const double* t_save, int64_t n_save,
+                        double* Q_save, double* Q_T, double* S, int64_t* stats) {
+  if (!ctx || !Q0 || !S || !(t1 > t0) || !(dt > 0.0) || n_save < 0 || (n_save > 0 && (!t_save || !Q_save))) return HG_ERR_ARG;
   if (adaptive && (!(abstol > 0.0) || !(reltol > 0.0))) { ctx->err = "hg_solve_tsit5_sens: tolerances must be positive"; return HG_ERR_ARG; }
   if (ctx->opt.path != 1) { ctx->err = "hg_solve_tsit5_sens needs the plain path (strict = 1)"; return HG_ERR_ARG; }
   TRY(no_closure(ctx, "hg_solve_tsit5_sens"));
@@ -739,6 +740,23 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
     CK(ctx, cudaMemcpyAsync(E.p, eye.data(), eye.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  // saveat = t_save of the driver (swe_2D_sensitivity.jl:38-43): the VALUES at the save times by Tsit5's dense output, steps
+  // independent of the save times (what forward_simulation_results.json holds)
+  std::vector<std::pair<double, int64_t>> pending;
+  for (int64_t i = 0; i < n_save; ++i) {
+    if (t_save[i] == t0) std::memcpy(Q_save + (size_t)i * n3, Q0, (size_t)n3 * 8);
+    else if (t_save[i] > t0 && t_save[i] <= t1) pending.push_back({t_save[i], i});
+    else { ctx->err = "hg_solve_tsit5_sens: save time outside [t0, t1]"; return HG_ERR_ARG; }
+  }
+  std::sort(pending.begin(), pending.end());
+  size_t next_save = 0;
+  static const double RI[7][4] = {{1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216},
+                                  {0.0, 0.13169999999999998, -0.2234, 0.1017},
+                                  {0.0, 3.9302962368947516, -5.941033872131505, 2.490627285651253},
+                                  {0.0, -12.411077166933676, 30.33818863028232, -16.548102889244902},
+                                  {0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928},
+                                  {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
+                                  {0.0, 1.5, -4.0, 2.5}};
   CK(ctx, cudaMemsetAsync(U.p, 0, (size_t)len * 8, ctx->stream));           // the partials start at zero (Q0 does not depend on p)
   CK(ctx, cudaMemcpyAsync(U.p, Q0, (size_t)n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
   // d/dt of the augmented state: row 0 = f(Q, p), row k = J_Q U_k + J_p e_k
@@ -787,9 +805,22 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
       accept = eest <= 1.0;
     }
     if (accept) {
+      const double tnew = (h == t1 - t) ? t1 : t + h;
+      for (; next_save < pending.size() && pending[next_save].first <= tnew; ++next_save) {
+        double* out = Q_save + (size_t)pending[next_save].second * n3;
+        if (pending[next_save].first == tnew) {
+          CK(ctx, cudaMemcpyAsync(out, unew, (size_t)n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {                                   // row 0 of u + h sum_i b_i(theta) k_i (Y is free between steps)
+          const double th = (pending[next_save].first - t) / h;
+          for (int m = 0; m < 7; ++m) coef[m] = h * (th * (RI[m][0] + th * (RI[m][1] + th * (RI[m][2] + th * RI[m][3]))));
+          TRY(hg::sens_lincomb(ctx, n3, Y.p, u, 7, k, coef));
+          CK(ctx, cudaMemcpyAsync(out, Y.p, (size_t)n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+      }
       std::swap(u, unew);
       std::swap(k[0], k[6]);                       // FSAL
-      t = (h == t1 - t) ? t1 : t + h;
+      t = tnew;
       ++n_acc;
       ctx->last_steps.push_back(h);
       if (adaptive) {

@@ -227,25 +227,26 @@ function ChainRulesCore.rrule(::typeof(swe_2d_rhs), Q::AbstractVector, p::Abstra
 end
 
 """
-    sensitivity_tsit5(ctx, Q0, params_vector, tspan, dt; adaptive, abstol, reltol, fastpow) -> (Q_T, sensitivity)
+    sensitivity_tsit5(ctx, Q0, params_vector, tspan, dt; t_save, adaptive, abstol, reltol, fastpow) -> (Q_T, sensitivity, pred)
 
 The whole sensitivity driver in one call (swe_2D_sensitivity.jl:34-80: `ForwardDiff.jacobian(forward_simulation, params_vector)`
 with `solve(prob, Tsit5(), ...)` inside): `sensitivity` is the 3N x length(params_vector) Jacobian of the final state.
 `ctx` must have been created with `strict=true`.
 """
 function sensitivity_tsit5(ctx::Context, Q0::Vector{Float64}, params_vector::Vector{Float64}, tspan::Tuple{Float64,Float64}, dt::Float64;
-                           adaptive::Bool=true, abstol::Float64=1e-6, reltol::Float64=1e-3, fastpow::Bool=true)
+                           t_save::Vector{Float64}=Float64[], adaptive::Bool=true, abstol::Float64=1e-6, reltol::Float64=1e-3, fastpow::Bool=true)
     _check(ccall((:hg_set_controller_pow, LIB), Cint, (Ptr{Cvoid}, Int32), ctx.handle, Int32(fastpow)), ctx.handle)
     QT = similar(Q0); S = Matrix{Float64}(undef, length(Q0), length(params_vector)); stats = zeros(Int64, 3)
-    GC.@preserve Q0 params_vector QT S stats begin
+    pred = Matrix{Float64}(undef, length(Q0), length(t_save))        # Array(pred) of the driver: values at the save times
+    GC.@preserve Q0 params_vector t_save pred QT S stats begin
         rc = ccall((:hg_solve_tsit5_sens, LIB), Cint,
                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64, Float64, Float64, Int32, Float64, Float64,
-                    Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                    Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
                    ctx.handle, Q0, params_vector, length(params_vector), ctx.active, tspan[1], tspan[2], dt, Int32(adaptive),
-                   abstol, reltol, QT, S, stats)
+                   abstol, reltol, t_save, length(t_save), pred, QT, S, stats)
         _check(rc, ctx.handle)
     end
-    return QT, S            # column k of S = row k of the C layout: d Q(T) / d p_k
+    return QT, S, pred      # column k of S = row k of the C layout: d Q(T) / d p_k
 end
 
 "custom_ODE_solve (ode_solvers/custom_ODE_solvers.jl:36-95) on the device; returns the 3N x nSaves matrix."

@@ -4,7 +4,8 @@
                                     swe_2D_sensitivity (applications/sensitivity/swe_2D_sensitivity.jl:2-99): the active parameter
                                     and its values from run_control.json (parameters/process_model_parameters_2D.jl:93-127),
                                     ForwardDiff.jacobian of the adaptive Tsit5 solve = hg_solve_tsit5_sens (values and one partial
-                                    per parameter on the device, Dual-aware error norm), then sensitivity_results.json and the
+                                    per parameter on the device, Dual-aware error norm), then forward_simulation_results.json (the
+                                    values at the save times), sensitivity_results.json and the
                                     per-parameter JSON / VTK files (process_sensitivity_results_2D.jl:4-80).
 
 Only the keys this driver reads are interpreted.  Forward mode runs on the plain tables: the context is created with strict = 1.
@@ -60,8 +61,15 @@ def run_sensitivity_case(case_path, out_path=None, device=0, write_vtk=True, con
     ctx = Context(flat, device=device, strict=True)
     ctx.set_controller_pow(controller_pow)
     t0, t1 = (float(v) for v in ts["tspan"])
-    QT, S, stats = ctx.solve_tsit5_sens(Q0, p, active, t0, t1, float(ts["dt"]), bool(ode.get("ode_solver_adaptive", True)), 1e-6, 1e-3)
+    n_save = int(ode.get("ode_solver_nSave", 0))
+    t_save = t0 + (t1 - t0) / n_save * np.arange(n_save + 1) if n_save > 0 else np.zeros(0)      # t_start:dt_save:t_end
+    if n_save > 0:
+        t_save[-1] = min(t_save[-1], t1)
+    QT, S, stats = ctx.solve_tsit5_sens(Q0, p, active, t0, t1, float(ts["dt"]), bool(ode.get("ode_solver_adaptive", True)), 1e-6, 1e-3,
+                                        t_save=t_save)
     sens = np.ascontiguousarray(S.T)                                  # [3N, n_params], the reference's Jacobian layout
-    results.save_sensitivity_results(out_path, sensitivity=sens, parameter_name=active, params_vector=p)
+    pred = stats.pop("saves")
+    results.save_sensitivity_results(out_path, pred_array=None if pred is None else pred.T, zb_cells=flat["zb_cells"], wstill=wstill,
+                                     hstill=flat["hstill"], sensitivity=sens, parameter_name=active, params_vector=p)
     results.postprocess_sensitivity_results_swe_2D(flat, sens, p, active, out_path, write_vtk=write_vtk)
-    return dict(Q_T=QT, sensitivity=sens, params_vector=p, stats=stats, flat=flat)
+    return dict(Q_T=QT, sensitivity=sens, params_vector=p, stats=stats, flat=flat, pred=pred, t_save=t_save)

@@ -243,12 +243,14 @@ HG_API int hg_rhs_jvp_multi(hg_ctx* ctx, const double* Q, const double* params, 
 /* Forward sensitivity solve = the reference's sensitivity driver (swe_2D_sensitivity.jl:34-80: ForwardDiff.jacobian around
  * solve(prob, Tsit5(), adaptive, dt; abstol, reltol)) on the device: values and one partial per entry of the active
  * parameter (zb, ManningN or Q) advance together, the error estimate includes the partials like DiffEqBase's norm of Dual
- * numbers, PI controller with the powers of hg_set_controller_pow.  Q_T[3N] (may be NULL); S[n_params][3N], row k =
+ * numbers, PI controller with the powers of hg_set_controller_pow.  t_save[n_save] / Q_save[n_save][3N] (n_save may be 0):
+ * the VALUES at the driver's save times by Tsit5's dense output, i.e. the columns of forward_simulation_results.json
+ * (swe_2D_sensitivity.jl:60-72).  Q_T[3N] (may be NULL); S[n_params][3N], row k =
  * d Q(t1) / d p_k (the transpose of the reference's 3N x n_params Jacobian = its column-major JSON layout); stats =
  * {accepted, rejected, augmented RHS evaluations}; hg_last_steps afterwards gives the accepted steps.  strict = 1 only.   */
 HG_API int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params, int32_t active_param,
-                        double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol, double* Q_T,
-                        double* S, int64_t* stats);
+                        double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol, const double* t_save,
+                        int64_t n_save, double* Q_save, double* Q_T, double* S, int64_t* stats);
 HG_API int hg_set_state(hg_ctx* ctx, const double* Q);          /* host [3N] -> device                  */
 HG_API int hg_get_state(hg_ctx* ctx, double* Q);                /* device -> host [3N]                  */
 HG_API int hg_set_params(hg_ctx* ctx, const double* params, int64_t n_params, int32_t active_param);

@@ -86,3 +86,32 @@ def test_sensitivity_case_end_to_end(mods, tmp_path):
     assert a.shape == b.shape and np.abs(a - b).max() <= 1e-5 * np.abs(b).max()
     for i in range(1, 7):
         assert os.path.exists(os.path.join(d, f"sensitivity_results_ManningN_{i}.json")) and os.path.exists(os.path.join(d, f"sensitivity_results_ManningN_{i}.vtk"))
+
+
+@pytest.mark.parametrize("name,early_tol", [("oneD_uniform_sens", (2e-6, 2e-5)), ("oneD_bump_sens", (1e-6, 1e-5))])
+def test_channel_sensitivity_case_reproduces_the_saved_trajectory(mods, tmp_path, name, early_tol):
+    """The reference's channel sensitivity cases in one call: the VALUES of the Dual solve at the save times
+    (forward_simulation_results.json -- the file the hard pins of tests/test_oracle_golden.py are made against) and
+    d Q(T) / d ManningN (sensitivity_results.json), from the device-resident solve.  The runs are stability-limited (see
+    tests/test_gpu_zzz_reference_replay.py): early saves tight, the final time as loose as the host restatement needs x 10."""
+    hg, forward, results = mods
+    from hydrograd_jl_b200 import sensitivity
+    d = _case_dir(tmp_path, name, results)
+    out = sensitivity.run_sensitivity_case(d, write_vtk=False)
+    N = out["flat"]["n_cells"]
+    tj = np.load(os.path.join(cases.GOLD, name, "trajectory.npz"))
+    got = json.load(open(os.path.join(d, "forward_simulation_results.json")))
+    assert list(got.keys()) == list(results.FORWARD_RESULTS_KEYS)
+    pred = np.asarray(got["forward_simulation_results"], dtype=np.float64).reshape(101, 3 * N)      # column-major 3N x 101
+    assert np.array_equal(pred[0], tj["forward_simulation_results"][0])                              # the initial condition
+    idx, ref = tj["early_index"], tj["forward_simulation_results_early"]
+    err = [max(np.abs(pred[i][:N] - w[:N]).max(), np.abs(pred[i][N:2 * N] - w[N:2 * N]).max()) for i, w in zip(idx[:2], ref[:2])]
+    fin = np.abs(pred[100][:2 * N] - tj["forward_simulation_results"][2][:2 * N]).max()
+    z = np.load(os.path.join(cases.GOLD, name, "sensitivity.npz"))
+    S_ref = z["sensitivity_results"].reshape(z["params_vector"].size, 3 * N)
+    es = np.abs(out["sensitivity"].T - S_ref).max() / np.abs(S_ref).max()
+    print(name, "early saves", ["%.1e" % e for e in err], "final %.1e" % fin, "sensitivities %.1e" % es, out["stats"])
+    for e, tol in zip(err, early_tol):
+        assert e <= tol
+    assert fin <= 5e-4 and es <= 2e-4
+    assert np.array_equal(np.asarray(got["zb_cells"], dtype=np.float64), tj["zb_cells"]) and np.array_equal(np.asarray(got["hstill"]), tj["hstill"])
