@@ -123,7 +123,8 @@ class CpuSample:
         self.n = flat["n_cells"]
         self.threads = threads or self.o.max_threads()
         self.v = np.ones_like(self.Q0)
-        self.o.rhs(self.Q0, nthreads=self.threads)          # first touch
+        self.o.rhs(self.Q0, nthreads=self.threads)          # first touch (both passes: the CPU side is timed warm)
+        self.o.jvp(self.Q0, self.v, nthreads=self.threads)
 
     def step(self, reps=1):
         """(seconds per RHS, seconds per derivative pass), mean of reps"""
