@@ -221,3 +221,27 @@ def test_reference_sensitivity_run_through_the_forward_mode_source(host):
     err = [np.abs(U[1 + k] - S[k]).max() for k in range(S.shape[0])]
     print("savannah sensitivities through hg_jvp_impl.h vs reference:", ["%.1e" % e for e in err], st)
     assert st["accepted"] > 150 and max(err) <= 2e-8 * np.abs(S).max()
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("mode", ["ManningN", "Q", "zb"])
+def test_forward_mode_on_random_meshes_with_symmetry_and_two_inlets(host, tmp_path, seed, mode):
+    """Boundary types the reference's fixtures do not contain (symmetry, two inlet-q node strings, corner cells with two boundary
+    types, the default-wall rule) on random mixed tri / quad meshes, thin-film states: values and tangents against the oracle."""
+    from tests.test_srh_reader_cpu import _write_random_case
+    _write_random_case(str(tmp_path), seed)
+    c = R.load_case(str(tmp_path), "rnd.srhhydro", ("constant", [3.0, 2.0, 0.1, 0.0]))
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    o = Oracle(flat)
+    rng = np.random.default_rng(seed)
+    Q = cases.random_state_flat(flat, seed + 5, dry_frac=0.08)
+    p = {"ManningN": np.asarray(c.ManningN_zone, dtype=np.float64), "Q": np.asarray(flat["inletQ_TotalQ"], dtype=np.float64),
+         "zb": np.asarray(c.zb_cells, dtype=np.float64)}[mode].copy()
+    V, pdot = rng.standard_normal(3 * N), rng.standard_normal(p.size)
+    dQ, dQd, rc = run_host(host, flat, Q, V, p, pdot, ACTIVE[mode])
+    assert rc == 0
+    ref, ref_d = o.jvp(Q, V, p, pdot, ACTIVE[mode])
+    assert (np.abs(dQ - ref) <= 1e-13 * cases.flat_scale(flat, Q)).all()
+    assert np.abs(dQd - ref_d).max() <= 1e-12 * np.abs(ref_d).max()
+    assert flat["n_symm"] == 1 and flat["n_inletq"] == 2
