@@ -59,7 +59,10 @@ def loss_terms(Q_T, params, observed, flat, active_param_name, bWSE=True, buv=Tr
 
 def loss_and_gradient(ctx, flat, Q0, params, active_param_name, observed, dt, nsteps, method="Euler", **kw):
     """One optimiser iteration's work: forward sweep, loss, discrete adjoint sweep -> (loss, parts, d loss/d params).
-    method: "Euler" (the reference's customized solver, custom_ODE_solvers.jl), "RK4" or "Tsit5" (fixed-step SciML solvers)."""
+    method: "Euler" (the reference's customized solver, custom_ODE_solvers.jl), "RK4" or "Tsit5" (fixed-step SciML solvers), or
+    "Tsit5_adaptive" -- the configuration of the reference's inversion cases (inversion_ode_solver_options: Tsit5(), adaptive):
+    adaptive solve over [0, dt * nsteps] with initial step dt, then the discrete adjoint over the accepted steps, whose sizes are
+    constants of the differentiation exactly as for ForwardDiff through the reference's solve (hg_last_steps + hg_rk_adjoint_steps)."""
     # the terminal cotangent needs Q(T) first, so run forward once; the adjoint call repeats the forward sweep with checkpoints
     ctx.set_params(params, active_param_name)
     ctx.set_state(Q0)
@@ -69,12 +72,17 @@ def loss_and_gradient(ctx, flat, Q0, params, active_param_name, observed, dt, ns
         ctx.step_rk4(dt, nsteps)
     elif method == "Tsit5":
         ctx.solve_tsit5(0.0, dt * nsteps, dt, adaptive=False)
+    elif method == "Tsit5_adaptive":
+        ctx.solve_tsit5(0.0, dt * nsteps, dt, adaptive=True, abstol=1e-6, reltol=1e-3)
+        steps = ctx.last_steps()
     else:
         raise ValueError(f"unknown method {method}")
     Q_T = ctx.get_state()
     loss, parts, lam, dp = loss_terms(Q_T, params, observed, flat, active_param_name, **kw)
     if method == "Euler":
         _, _, pbar = ctx.euler_adjoint(Q0, lam, dt, nsteps, params, active_param_name)
+    elif method == "Tsit5_adaptive":
+        _, _, pbar = ctx.rk_adjoint_steps("Tsit5", Q0, lam, steps, params, active_param_name)
     else:
         _, _, pbar = ctx.rk_adjoint(method, Q0, lam, dt, nsteps, params, active_param_name)
     return loss, parts, pbar + dp

@@ -149,6 +149,37 @@ def test_strict_path_replays_the_channel_runs_through_the_host_integrator(hg):
             assert e <= tol
 
 
+def test_inversion_gradient_of_the_adaptive_run_against_the_reference_sensitivities(hg):
+    """One iteration's work of the reference's Savannah ManningN inversion in its own configuration (adaptive Tsit5 over 200 s):
+    inversion.loss_and_gradient(method="Tsit5_adaptive") -- adaptive device solve, discrete adjoint over its accepted steps --
+    must return d loss / d ManningN = S lambda + direct terms, with S the reference's committed sensitivities of the same run
+    and lambda the loss cotangent at the final state."""
+    from hydrograd_jl_b200 import inversion as inv
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    z = np.load(cases.GOLD + "/savannah_sens/sensitivity.npz")
+    p = z["params_vector"]
+    S = z["sensitivity_results"].reshape(p.size, 3 * N)
+    t = cases.truth("savannah")
+    rng = np.random.default_rng(8)
+    obs = dict(WSE_truth=t["wse_truth"] + 0.05 * rng.standard_normal(N), u_truth=t["u_truth"] * 1.1, v_truth=t["v_truth"] * 0.9,
+               zb_cell_truth=t["zb_cell_truth"])
+    bound = (np.full(p.size, 0.025), np.full(p.size, 0.06))           # the first zone value (0.02) is out of bounds
+    ctx = hg.Context(flat, tile_cells=128)
+    ctx.set_controller_pow("fastpow")
+    loss, parts, grad = inv.loss_and_gradient(ctx, flat, c.Q0, p, "ManningN", obs, 0.02, 10000, method="Tsit5_adaptive", bound=bound)
+    QT = ctx.get_state()
+    _, _, lam, dp = inv.loss_terms(QT, p, obs, flat, "ManningN", bound=bound)
+    want = S @ lam + dp
+    scale = np.abs(S * lam[None, :]).sum(1) + np.abs(dp)
+    print("inversion gradient vs reference sensitivities:", ["%.1e" % (abs(a - b) / max(s_, 1e-300)) for a, b, s_ in zip(grad, want, scale)],
+          "loss %.3e" % loss, parts)
+    assert loss > 0 and parts["bound"] > 0 and dp[0] != 0.0
+    for k in range(p.size):
+        assert abs(grad[k] - want[k]) <= 1e-4 * max(scale[k], 1e-300), k
+
+
 # last: the stability-limited channel runs amplify rounding differences the most (module docstring)
 @pytest.mark.parametrize("name,p,dt_save,early_tol", [("oneD_uniform_sens", [0.03, 0.03], 1.0, (2e-6, 2e-5)),
                                                       ("oneD_bump_sens", [0.03, 0.02, 0.03], 2.0, (1e-6, 1e-5))])
