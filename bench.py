@@ -148,6 +148,12 @@ def cpu_sample(cells_m=2.0, reps=3, threads=0, seed=1234):
     return {"value": c.n / (dt_rhs + dt_jvp), "rhs_only": c.n / dt_rhs, "cores": c.threads, "sample": c.describe(reps)}
 
 
+def workload_text(cells_millions):
+    """config.workload, shared by both arms (the reference arm times a bounded sample of this workload)"""
+    return (f"C3 synthetic {cells_millions:.1f}M-cell meandering river per GPU (mixed tri/quad, 6 Manning "
+            "zones, inlet-Q/exit-H/walls); step = one fused fp64 RHS + one hand-written VJP of the resident state")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path.  Hydrograd.jl is Julia-only and Julia is not in this image, so
     this times the oracle port (C++ restatement, reference evaluation order) on all host cores."""
@@ -169,7 +175,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3 synthetic meandering-river mesh, fp64 RHS, bounded CPU sample", "sample": sample},
+            "config": {"workload": workload_text(args.cells_m), "sample": sample,
+                       "note": "CPU arm: one RHS + one forward-mode derivative pass of the C++ port of the reference algorithm "
+                               "(the cheapest derivative pass the reference's AD performs), bounded sample of the same mesh family"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "rhs_only": val_rhs},
             "rhs": {"value": val_rhs, "unit": UNIT},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -431,8 +439,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C3 synthetic {N / 1e6:.1f}M-cell meandering river per GPU (mixed tri/quad, 6 Manning "
-                                       "zones, inlet-Q/exit-H/walls); step = one fused fp64 RHS + one hand-written VJP of the resident state",
+                "config": {"workload": workload_text(N / 1e6),
                            "cells_per_gpu": N, "faces_per_gpu": F, "tile_cells": args.tile, "n_tiles": st["n_tiles"],
                            "l2": "inputs (state + mesh tables >> 126 MB L2) larger than L2, no flush needed",
                            "parallelism": (f"rcb-slab x{world}, one-layer halo, NCCL send/recv per step" + (" overlapped with the tiles without halo faces" if args.overlap else "")) if world > 1 else "single GPU"},
