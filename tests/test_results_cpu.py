@@ -382,3 +382,32 @@ def test_sensitivity_driver_reads_the_case_and_refuses_to_run_without_a_gpu(res,
     opts = rc["sensitivity_analysis_options"]
     assert np.array_equal(sensitivity._params_vector(opts, "ManningN", flat, d), [0.02, 0.04, 0.05, 0.03, 0.045, 0.05])
     assert np.array_equal(sensitivity._params_vector(opts, "zb", flat, d), np.zeros(5))
+
+
+def test_written_json_parses_back_to_the_same_values(res, tmp_path):
+    """Structure fuzz: nested / ragged / empty arrays, scalars, strings with quotes, backslashes, control characters and UTF-8 --
+    whatever is written must be valid JSON that parses back to the same values (numbers exactly)."""
+    rng = np.random.default_rng(3)
+
+    def rand_array(depth):
+        if depth == 0 or rng.random() < 0.4:
+            n = int(rng.integers(0, 6))
+            return [float(x) for x in np.round(rng.standard_normal(n) * 10.0 ** rng.integers(-8, 8), int(rng.integers(0, 12)))]
+        return [rand_array(depth - 1) for _ in range(int(rng.integers(0, 4)))]
+
+    for trial in range(20):
+        obj = {f"key {trial}.{k}": rand_array(3) for k in range(4)}
+        obj["name"] = 'zone "A"\\B\n\ttab \x01 é 水'
+        obj["scalar"] = float(rng.standard_normal())
+        obj["whole"] = 7.0
+        for style in ("JSON3", "julia"):
+            res.write_json_pretty(tmp_path / "f.json", obj, style=style)
+            back = json.load(open(tmp_path / "f.json", encoding="utf-8"))
+            assert list(back.keys()) == list(obj.keys())
+
+            def same(a, b):
+                if isinstance(a, list):
+                    return isinstance(b, list) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+                return a == b
+            for k in obj:
+                assert same(obj[k], back[k]), (k, obj[k], back[k])
