@@ -56,13 +56,27 @@ def test_device_forward_mode_matches_the_oracle(hg, name, mode):
               " tangent rel. err %.1e" % (np.abs(jv - ref_jv).max() / np.abs(ref_jv).max()))
         only = ctx.rhs_jvp(Q, v, p, mode, pdot, want_rhs=False)
         assert np.array_equal(only, jv)
-        # a chunk of three directions in one call (hg_rhs_jvp_multi): the same sweeps, the same bits
-        V3 = np.stack([v, -2.0 * v, rng.standard_normal(3 * N)])
-        P3 = np.stack([pdot, -2.0 * pdot, rng.standard_normal(p.size)]) if p is not None else None
-        dQm, JV = ctx.rhs_jvp_multi(Q, V3, p, mode, P3)
-        assert np.array_equal(dQm, dQ) and np.array_equal(JV[0], jv)
-        assert np.abs(JV[1] + 2.0 * jv).max() <= 1e-12 * np.abs(jv).max()
-        assert np.array_equal(JV[2], ctx.rhs_jvp(Q, V3[2], p, mode, None if P3 is None else P3[2], want_rhs=False))
+
+
+@pytest.mark.parametrize("mode", [None, "ManningN", "zb", "Q"])
+def test_chunk_of_directions_in_one_call(hg, mode):
+    """hg_rhs_jvp_multi (a ForwardDiff chunk): the same sweeps as K single calls, the same bits."""
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    N = c.mesh.numOfCells
+    ctx = hg.Context(flat, strict=True)
+    rng = np.random.default_rng(22)
+    p = _params(c, flat, mode)
+    Q = cases.random_state(c, 1)
+    v = rng.standard_normal(3 * N)
+    pdot = rng.standard_normal(p.size) if p is not None else None
+    dQ, jv = ctx.rhs_jvp(Q, v, p, mode, pdot)
+    V3 = np.stack([v, -2.0 * v, rng.standard_normal(3 * N)])
+    P3 = np.stack([pdot, -2.0 * pdot, rng.standard_normal(p.size)]) if p is not None else None
+    dQm, JV = ctx.rhs_jvp_multi(Q, V3, p, mode, P3)
+    assert np.array_equal(dQm, dQ) and np.array_equal(JV[0], jv)
+    assert np.abs(JV[1] + 2.0 * jv).max() <= 1e-12 * np.abs(jv).max()
+    assert np.array_equal(JV[2], ctx.rhs_jvp(Q, V3[2], p, mode, None if P3 is None else P3[2], want_rhs=False))
 
 
 def test_device_forward_mode_is_the_transpose_of_the_vjp_kernel(hg):
