@@ -91,9 +91,12 @@ def run_forward_case(case_path, out_path=None, device=0, write_vtk=True, control
             adaptive = bool(fs.get("forward_simulation_adaptive", True)) if ode == "Tsit5()" else True
             ctx.set_controller_pow(controller_pow)
             states, stats = ctx.solve_tsit5(t0, t1, dt, adaptive, 1e-6, 1e-3, t_save=t_save, saveat="interp")
-    elif solver == "customized":
-        states = ctx.custom_ode_solve(Q0, None, None, t0, t1, dt).T          # [n_saves, 3N]
-        t_save = t0 + dt * np.arange(states.shape[0])
+    elif solver == "customized":                              # swe_2D_forward_simulation.jl:71-90: Euler loop, VTK only, no truth file
+        sol = ctx.custom_ode_solve(Q0, None, None, t0, t1, dt)                # [3N, n_saves], every step saved
+        if write_vtk:
+            results.swe_2D_save_results_custom(flat, sol, out_path)
+        return dict(states=np.ascontiguousarray(sol.T), t_save=t0 + dt * np.arange(sol.shape[1]), stats=dict(accepted=sol.shape[1] - 1, rejected=0),
+                    truth=None, flat=flat)
     else:
         raise ValueError("Wrong solver choice. Supported solvers: SciML, customized. No forward simulation is performed.")
     truth = results.postprocess_forward_simulation_results_swe_2D(

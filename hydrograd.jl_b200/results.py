@@ -8,7 +8,8 @@ the library (csrc/hg_results.cpp), byte-compatible with the files t
   process_dry_wet_flags                             fvm/discretization/process_dry_wet.jl:2-35
   swe_2D_calc_total_water_volume                    utilities/swe_2D_tools.jl:4-7
   postprocess_forward_simulation_results_swe_2D     applications/forward_simulation/process_forward_simulation_results_2D.jl:4-86
-  swe_2D_save_results_SciML                         utilities/swe_2D_tools.jl:10-98
+  swe_2D_save_results_SciML                         utilities/swe_2D_tools.jl:10-90
+  swe_2D_save_results_custom                        utilities/swe_2D_tools.jl:92-141
   save_sensitivity_results                          applications/sensitivity/swe_2D_sensitivity.jl:60-72, 84-95
   postprocess_sensitivity_results_swe_2D            applications/sensitivity/process_sensitivity_results_2D.jl:4-80
 
@@ -287,6 +288,33 @@ def swe_2D_save_results_SciML(flat, states, save_path, wstill, friction_x_truth,
         fo.write("total_water_volume\n")
         for v in volumes:
             fo.write(format_float(v) + "\n")
+    return volumes
+
+
+def swe_2D_save_results_custom(flat, sol, save_path):
+    """utilities/swe_2D_tools.jl:92-141, what the forward driver writes after the customized Euler solver: one VTK per column of
+    `sol` ([3N, n_saves], the layout custom_ODE_solve returns) with the scalars h, hu, hv, zb_cell, WSE and the vector U.
+    Faithful to the reference, including that it reads the first block of the state as the depth (it is xi = h - hstill): the
+    file labels xi as "h", divides by it for U and adds zb to it for "WSE".  Returns the "volumes" sum(xi .* areas) it computes
+    (the reference does not write them: its CSV block is commented out)."""
+    sol = np.asarray(sol, dtype=np.float64)
+    N, ld = int(flat["n_cells"]), int(flat["ld"])
+    if sol.ndim != 2 or sol.shape[0] != 3 * N:
+        raise ValueError(f"sol has shape {sol.shape}, expected ({3 * N}, n_saves)")
+    xyz = _f64(flat["node_coords"]).reshape(-1, 3)
+    cn = _i64(flat["cell_nodes"]).reshape(ld, N).T
+    cnt = _i64(flat["cell_nfaces"])
+    zb = _f64(flat["zb_cells"])
+    volumes = []
+    for index in range(1, sol.shape[1] + 1):
+        Q = np.ascontiguousarray(sol[:, index - 1])
+        first, hu, hv = Q[:N], Q[N:2 * N], Q[2 * N:]
+        volumes.append(swe_2D_calc_total_water_volume(first, flat["cell_areas"]))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            U = np.stack([hu / first, hv / first], axis=1)
+        export_to_vtk_2D(os.path.join(save_path, "forward_simulation_results_%04d.vtk" % index), xyz, cn, cnt,
+                         "forward_simulation_saved_index", "integer", index, [first, hu, hv, zb, first + zb],
+                         ["h", "hu", "hv", "zb_cell", "WSE"], [U], ["U"], index_base=int(flat.get("index_base", 1)))
     return volumes
 
 

@@ -411,3 +411,25 @@ def test_written_json_parses_back_to_the_same_values(res, tmp_path):
                 return a == b
             for k in obj:
                 assert same(obj[k], back[k]), (k, obj[k], back[k])
+
+
+def test_custom_solver_results_writer(res, tmp_path):
+    """swe_2D_save_results_custom: five scalars + U per saved column, the first state block labelled "h" as in the reference."""
+    from hydrograd_jl_b200 import srh2d
+    flat = srh2d.process_SRH_2D_input(os.path.join(cases.GOLD, "simple"), "simple.srhhydro")
+    Q0 = srh2d.setup_initial_condition(flat, 1.0, 0.5, 0.1, 0.0)
+    N = flat["n_cells"]
+    sol = np.stack([Q0, Q0 * 1.01], axis=1)
+    vol = res.swe_2D_save_results_custom(flat, sol, tmp_path)
+    assert vol[0] == pytest.approx((Q0[:N] * flat["cell_areas"]).sum(), rel=1e-14)
+    lines = open(tmp_path / "forward_simulation_results_0002.vtk").read().split("\n")
+    assert lines[6] == "2"
+    heads = [l for l in lines if l.startswith(("SCALARS", "VECTORS"))]
+    assert heads == ["SCALARS h double 1", "SCALARS hu double 1", "SCALARS hv double 1", "SCALARS zb_cell double 1", "SCALARS WSE double 1",
+                     "VECTORS U double"]
+    i = lines.index("SCALARS h double 1")
+    assert lines[i + 2] == res.format_float(sol[0, 1])
+    j = lines.index("VECTORS U double")
+    assert lines[j + 1] == f"{res.format_float(sol[N, 1] / sol[0, 1])} {res.format_float(sol[2 * N, 1] / sol[0, 1])} 0.0"
+    with pytest.raises(ValueError):
+        res.swe_2D_save_results_custom(flat, sol[:5], tmp_path)
