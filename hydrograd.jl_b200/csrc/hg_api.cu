@@ -927,9 +927,21 @@ int hg_set_stream(hg_ctx* ctx, void* cuda_stream) {
 }
 
 // ---------------------------------------------------------------- parameter ensembles
+// Multi-rank contexts (n_halo > 0): every RHS needs fresh halo states.  An entry point that loops the RHS without an
+// exchange between steps / stages would read stale halo data, so it refuses unless the library owns the exchange.
+static int need_exchange_guard(hg_ctx* ctx, const char* who, bool loops) {
+  if (ctx->n_halo > 0 && loops && !hg_comm_ready(ctx)) {
+    ctx->err = std::string(who) + ": multi-rank context without a library-owned halo exchange (hg_comm_connect) -- "
+               "this entry point evaluates the RHS more than once per call and would read stale halo states";
+    return HG_ERR_ARG;
+  }
+  return HG_OK;
+}
+
 int hg_ensemble_alloc(hg_ctx* ctx, int64_t M, int32_t per_member_manning) {
   if (!ctx || M <= 0) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "ensembles need the fused path"; return HG_ERR_ARG; }
+  if (ctx->n_halo > 0) { ctx->err = "hg_ensemble_alloc: ensembles shard by member, not by domain -- multi-rank (halo) contexts are not supported"; return HG_ERR_ARG; }
   TRY(no_closure(ctx, "hg_ensemble_alloc"));
   if (ctx->ude_set) { ctx->err = "hg_ensemble_alloc: not available while a UDE model is set"; return HG_ERR_ARG; }
   if ((int64_t)ctx->fh.n_tiles * M >= ((int64_t)1 << 31)) { ctx->err = "too many members for one launch"; return HG_ERR_ARG; }
@@ -1019,6 +1031,7 @@ int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
   if (!ctx->state_set) { ctx->err = "hg_step_euler: no resident state"; return HG_ERR_STATE; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   if (ctx->opt.path == 1) { ctx->err = "hg_step_euler needs the fused path (path=0)"; return HG_ERR_ARG; }
+  TRY(need_exchange_guard(ctx, "hg_step_euler", nsteps > 1));
   ctx->ab3_step = 1;   // another stepper moves the state: hg_step_ab3 starts again
   hg::FusedDev& d = ctx->fd;
   for (int64_t s = 0; s < nsteps; ++s) {
@@ -1032,6 +1045,7 @@ int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps) {
   if (!ctx || nsteps < 0) return HG_ERR_ARG;
   if (!ctx->state_set) { ctx->err = "hg_step_rk4: no resident state"; return HG_ERR_STATE; }
   if (ctx->opt.path == 1) { ctx->err = "hg_step_rk4 needs the fused path (path=0)"; return HG_ERR_ARG; }
+  TRY(need_exchange_guard(ctx, "hg_step_rk4", true));
   ctx->ab3_step = 1;   // another stepper moves the state: hg_step_ab3 starts again
   CK(ctx, cudaSetDevice(ctx->opt.device));
   hg::FusedDev& d = ctx->fd;
@@ -1061,6 +1075,7 @@ int hg_step_ode_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
   if (!ctx || nsteps < 0) return HG_ERR_ARG;
   if (!ctx->state_set) { ctx->err = "hg_step_ode_euler: no resident state"; return HG_ERR_STATE; }
   if (ctx->opt.path == 1) { ctx->err = "hg_step_ode_euler needs the fused path (path=0)"; return HG_ERR_ARG; }
+  TRY(need_exchange_guard(ctx, "hg_step_ode_euler", nsteps > 1));
   ctx->ab3_step = 1;   // another stepper moves the state: hg_step_ab3 starts again
   CK(ctx, cudaSetDevice(ctx->opt.device));
   hg::FusedDev& d = ctx->fd;
@@ -1079,6 +1094,7 @@ int hg_step_ab3(hg_ctx* ctx, double dt, int64_t nsteps, int32_t restart) {
   if (!ctx || nsteps < 0) return HG_ERR_ARG;
   if (!ctx->state_set) { ctx->err = "hg_step_ab3: no resident state"; return HG_ERR_STATE; }
   if (ctx->opt.path == 1) { ctx->err = "hg_step_ab3 needs the fused path (path=0)"; return HG_ERR_ARG; }
+  TRY(need_exchange_guard(ctx, "hg_step_ab3", true));
   CK(ctx, cudaSetDevice(ctx->opt.device));
   hg::FusedDev& d = ctx->fd;
   const size_t n3 = 3 * (size_t)ctx->fh.Ns;
@@ -1477,6 +1493,7 @@ int hg_custom_ode_solve(hg_ctx* ctx, const double* Q0, const double* params, int
   const int64_t nsteps = t1 < t0 ? 0 : (int64_t)std::floor((t1 - t0) / dt + 1e-9) + 1;
   *n_saves = nsteps;
   if (cap < nsteps) { ctx->err = "hg_custom_ode_solve: sol has room for " + std::to_string(cap) + " of " + std::to_string(nsteps) + " saves"; return HG_ERR_ARG; }
+  TRY(need_exchange_guard(ctx, "hg_custom_ode_solve", nsteps > 1));
   TRY(bind_params(ctx, params, np, active));
   TRY(hg_set_state(ctx, Q0));
   for (int64_t s = 0; s < nsteps; ++s) {

@@ -218,6 +218,8 @@ struct hg_ctx {
   hg::BcHost bch;
   hg::PlainDev pd;
   hg::FusedHost fh;
+  int32_t fh_force_nf = 0;     // build_tiles: face slots per cell of the attempt being built (4 or 8)
+  struct hg_comm* comm = nullptr;   // library-owned halo exchange (hg_comm.cu); null = the caller moves halo_send -> halo_recv
   hg::FusedDev fd;
   double* h_pinned = nullptr;  // staging [6N] pinned host memory
   size_t h_pinned_bytes = 0;
@@ -229,6 +231,8 @@ struct hg_ctx {
   int32_t last_active = -1;
   std::vector<int32_t> matid_ref;
 };
+
+inline bool hg_comm_ready(const hg_ctx* ctx) { return ctx->comm != nullptr; }
 
 namespace hg {
 // host-side builder (hg_host.cpp)

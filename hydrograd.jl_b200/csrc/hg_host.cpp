@@ -51,6 +51,8 @@ int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg
   const int64_t nbc = b->n_inletq + b->n_exith + b->n_wall + b->n_symm + b->n_halo;
   ctx->n_halo = b->n_halo;
   if (b->n_halo < 0 || (b->n_halo > 0 && (!b->halo_flip || !b->halo_area))) HG_FAIL(ctx, HG_ERR_ARG, "halo boundary data missing");
+  if (b->n_halo > 0 && ctx->opt.path == 1)
+    HG_FAIL(ctx, HG_ERR_ARG, "multi-rank contexts (n_halo > 0) need the fused path: the plain / strict path has no halo boundaries");
   if (b->n_inletq < 0 || b->n_exith < 0 || b->n_wall < 0 || b->n_symm < 0) HG_FAIL(ctx, HG_ERR_ARG, "negative boundary count");
   if (B > 0 && (!b->bc_ptr || !b->ghost_ids || !b->internal_cells || !b->outward_normals))
     HG_FAIL(ctx, HG_ERR_ARG, "null boundary array");
@@ -233,13 +235,17 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
   int32_t maxnf = 0;
   for (int64_t i = 0; i < ctx->N; ++i) maxnf = std::max(maxnf, cf_ptr[i + 1] - cf_ptr[i]);
   if (maxnf > 4) want = 128;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    ctx->opt.tile_cells = want;
+  // attempts: the requested tile size, then T = 128 with the slot count the mesh needs (4 for triangles / quadrilaterals),
+  // then T = 128 with the roomy 8-slot configuration
+  const int32_t try_T[3] = {want, 128, 128};
+  const int32_t try_nf[3] = {maxnf <= 4 ? 4 : 8, maxnf <= 4 ? 4 : 8, 8};
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if (attempt > 0 && try_T[attempt] == try_T[attempt - 1] && try_nf[attempt] == try_nf[attempt - 1]) continue;
+    ctx->opt.tile_cells = try_T[attempt];
+    ctx->fh_force_nf = try_nf[attempt];
     int rc = build_tiles_T(ctx, m, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
     if (rc != HG_OK) return rc;
     if (fused_config_ok(ctx)) return HG_OK;
-    if (want == 128) break;
-    want = 128;
   }
   HG_FAIL(ctx, HG_ERR_ARG, "mesh does not fit the compiled tile configurations (tile needs %d local cells, %d faces): "
           "renumber the mesh for locality or pass cell_centroids", ctx->fh.max_local, ctx->fh.max_faces);
@@ -256,7 +262,7 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
   int32_t maxnf = 0;
   for (int64_t i = 0; i < N; ++i) maxnf = std::max(maxnf, cf_ptr[i + 1] - cf_ptr[i]);
   fh.max_cell_faces = maxnf;
-  fh.NF = (maxnf <= 4 && T != 128) ? 4 : 8;
+  fh.NF = ctx->fh_force_nf ? ctx->fh_force_nf : (maxnf <= 4 ? 4 : 8);
   const int32_t NF = fh.NF;
   if (maxnf > 8) HG_FAIL(ctx, HG_ERR_ARG, "cells with %d faces are not supported (max 8 = gMax_Nodes_per_Element)", maxnf);
   fh.Ns = ((N + 15) / 16) * 16 + 16;  // slack: the last tile's TMA copy may read one element past N

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <dirent.h>
 #include <fstream>
 #include <map>
 #include <sstream>
@@ -55,6 +56,26 @@ std::string lower(std::string s) {
   for (auto& c : s) c = (char)std::tolower((unsigned char)c);
   return s;
 }
+// The reference's committed control files were written on a case-insensitive file system: e.g.
+// examples/SWE_2D/forward_simulation/Savannah_River_ManningN_ks_h_Umag/run_control.json:5 names `Savana_SI.srhhydro`
+// while the file is `savana_SI.srhhydro`.  If the exact name is absent, take the unique case-folded match of its directory.
+std::string resolve_path(const std::string& path) {
+  {
+    std::ifstream f(path);
+    if (f) return path;
+  }
+  const std::string dir = dir_of(path);
+  const size_t k = path.find_last_of('/');
+  const std::string want = lower(k == std::string::npos ? path : path.substr(k + 1));
+  std::string found;
+  int hits = 0;
+  if (DIR* d = opendir(dir.c_str())) {
+    while (dirent* e = readdir(d))
+      if (lower(e->d_name) == want) { found = e->d_name; ++hits; }
+    closedir(d);
+  }
+  return hits == 1 ? dir + "/" + found : path;
+}
 inline uint64_t key(int64_t a, int64_t b) { return ((uint64_t)std::min(a, b) << 32) | (uint64_t)std::max(a, b); }
 
 int fail(hg_case* c, const std::string& m) {
@@ -62,7 +83,8 @@ int fail(hg_case* c, const std::string& m) {
   return HG_ERR_ARG;
 }
 
-int load(hg_case* cs, const std::string& hydro_path) {
+int load(hg_case* cs, const std::string& hydro_path_in) {
+  const std::string hydro_path = resolve_path(hydro_path_in);
   // ---- srhhydro
   std::map<int64_t, double> mann;
   std::map<int64_t, std::string> bc;
@@ -91,7 +113,7 @@ int load(hg_case* cs, const std::string& hydro_path) {
   std::vector<double> xyz;
   std::map<int64_t, std::vector<int64_t>> nstr;
   {
-    std::ifstream f(dir + "/" + grid);
+    std::ifstream f(resolve_path(dir + "/" + grid));
     if (!f) return fail(cs, "cannot open " + dir + "/" + grid);
     std::string line;
     int64_t cur = -1;
@@ -271,7 +293,7 @@ int load(hg_case* cs, const std::string& hydro_path) {
   // ---- materials: first zone containing the cell, 0 = default (process_SRH_2D_input.jl:136-153)
   auto& matid = cs->i64["matID_cells"]; matid.assign(N, 0);
   {
-    std::ifstream f(dir + "/" + matf);
+    std::ifstream f(resolve_path(dir + "/" + matf));
     if (!f) return fail(cs, "SRHMAT file " + dir + "/" + matf + " does not exist");
     std::vector<char> set(N, 0);
     std::string line;

@@ -117,7 +117,7 @@ def extract_local(flat, part, rank, Q=None, gid=None):
     nb = o_neigh[ci, cj]
     nbr_rank = part[nb]
     neighbors = sorted(set(int(r) for r in nbr_rank))
-    h_ic, h_n, h_len, h_flip, h_area, h_nb, h_counts = [], [], [], [], [], [], []
+    h_ic, h_j, h_n, h_len, h_flip, h_area, h_nb, h_counts = [], [], [], [], [], [], [], []
     flen = np.asarray(flat["face_lengths"])
     area = np.asarray(flat["cell_areas"])
     for q in neighbors:
@@ -126,7 +126,7 @@ def extract_local(flat, part, rank, Q=None, gid=None):
         ga, gb = gid[own[c]], gid[r]
         order = np.lexsort((np.maximum(ga, gb), np.minimum(ga, gb)))
         c, j, r, ga, gb = c[order], j[order], r[order], ga[order], gb[order]
-        h_ic.append(c); h_n.append(o_norm[c, j]); h_len.append(flen[o_faces[c, j]])
+        h_ic.append(c); h_j.append(j); h_n.append(o_norm[c, j]); h_len.append(flen[o_faces[c, j]])
         h_flip.append((gb < ga).astype(np.uint8)); h_area.append(area[r]); h_nb.append(r)
         h_counts.append(c.size)
         ptr.append(ptr[-1] + c.size)
@@ -143,7 +143,7 @@ def extract_local(flat, part, rank, Q=None, gid=None):
     l_neigh[o_isb] = old2new[o_neigh[o_isb]]
     off = n_phys
     for k, q in enumerate(neighbors):
-        l_neigh[h_ic[k], _slot_of(cut, nbr_rank, ci, cj, q, h_ic[k], h_nb[k], o_neigh)] = off + np.arange(h_counts[k])
+        l_neigh[h_ic[k], h_j[k]] = off + np.arange(h_counts[k])    # the cut slot itself, never a boundary slot whose ghost id collides
         off += h_counts[k]
     # ---- local faces
     used = np.unique(o_faces[o_valid])
@@ -187,14 +187,6 @@ def extract_local(flat, part, rank, Q=None, gid=None):
         Q = np.asarray(Q)
         info["Q"] = np.concatenate([Q[:N][own], Q[N:2 * N][own], Q[2 * N:][own]])
     return loc, info
-
-
-def _slot_of(cut, nbr_rank, ci, cj, q, cells, nbs, o_neigh):
-    """Slot j of each (owned cell, remote neighbour) pair, in the sorted entry order."""
-    out = np.empty(cells.size, dtype=np.int64)
-    for i, (c, r) in enumerate(zip(cells, nbs)):
-        out[i] = np.nonzero(o_neigh[c] == r)[0][0]
-    return out
 
 
 class HaloExchanger:

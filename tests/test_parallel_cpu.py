@@ -159,3 +159,46 @@ def test_partition_keeps_inlets_whole():
         cnt = np.bincount(pr, minlength=Pn)
         assert cnt.max() - cnt.min() <= 2 + g.size
         assert sum(P.extract_local(flat, pr, r, Q0)[0]["n_inletq"] for r in range(Pn)) == 1
+
+
+def test_cut_slot_is_not_confused_with_a_colliding_ghost_id():
+    """Ghost ids (boundary slots) and cell ids (interior slots) of the neighbour table share the range 0..; a boundary
+    cell whose ghost id equals the global id of its remote neighbour must still get the halo ghost in the CUT slot and
+    keep its physical ghost (round-1 advice: the slot search matched the boundary slot first)."""
+    flat, Q0 = S.dam_break(24)
+    flat = dict(flat)
+    N, ld, base = flat["n_cells"], flat["ld"], flat["index_base"]
+    neigh = np.asarray(flat["cell_neighbors"]).copy().reshape(ld, N)
+    faces = np.abs(np.asarray(flat["cell_faces"]).reshape(ld, N)) - base
+    isb = np.asarray(flat["face_is_boundary"]).astype(bool)
+    nf = np.asarray(flat["cell_nfaces"])
+    B = flat["n_ghost"]
+    # a boundary cell c whose boundary slot comes BEFORE an interior slot holding a neighbour r < B
+    pick = None
+    for c in range(N):
+        js = [j for j in range(nf[c]) if isb[faces[j, c]]]
+        ks = [j for j in range(nf[c]) if not isb[faces[j, c]] and neigh[j, c] - base < B]
+        if js and ks and js[0] < ks[-1]:
+            pick = (c, js[0], ks[-1]); break
+    assert pick is not None
+    c, jb, ji = pick
+    g, r = int(neigh[jb, c]) - base, int(neigh[ji, c]) - base
+    # renumber the ghosts: swap ids g and r, so that cell c's ghost id equals its neighbour's cell id
+    swap = np.arange(B); swap[g], swap[r] = r, g
+    bslots = np.zeros((ld, N), dtype=bool)
+    for cc in range(N):
+        for j in range(nf[cc]):
+            bslots[j, cc] = isb[faces[j, cc]]
+    neigh[bslots] = swap[neigh[bslots] - base] + base
+    flat["cell_neighbors"] = neigh.ravel()
+    flat["bc_ghost_ids"] = swap[np.asarray(flat["bc_ghost_ids"]) - base] + base
+    for k in ("hstill_ghost", "zb_ghost"):
+        a = np.asarray(flat[k]).copy(); a[[g, r]] = a[[r, g]]; flat[k] = a
+    assert neigh[jb, c] == neigh[ji, c]
+    part = np.zeros(N, dtype=np.int32); part[r] = 1          # the colliding neighbour lives on the other rank
+    loc, info = P.extract_local(flat, part, 0, Q0)
+    lc = int(np.nonzero(info["own"] == c)[0][0])
+    ln = np.asarray(loc["cell_neighbors"]).reshape(ld, loc["n_cells"])
+    n_phys = loc["n_ghost"] - sum(info["counts"])
+    assert ln[jb, lc] < n_phys <= ln[ji, lc]                  # physical ghost kept, halo ghost in the cut slot
+    assert hg.plan_stats(loc, tile_cells=128)["n_tiles"] >= 1

@@ -157,3 +157,17 @@ def test_cpp_reader_matches_reference_builder_on_random_meshes(tmp_path, seed):
         assert np.array_equal(np.asarray(t["zb_ghost"])[g - 1], np.asarray(t["zb_cells"])[np.asarray(t["bc_internal_cells"]) - 1])
     Q0 = srh2d.setup_initial_condition(got, 3.0, 2.0, 0.1, 0.0)
     assert np.array_equal(Q0, c.Q0) and np.array_equal(got["hstill"], c.hstill)
+
+
+def test_case_folded_file_names_resolve():
+    """The reference's own control file names `Savana_SI.srhhydro` for the file `savana_SI.srhhydro`
+    (examples/SWE_2D/forward_simulation/Savannah_River_ManningN_ks_h_Umag/run_control.json:5): the reader falls back to
+    the unique case-folded match of the directory, for the .srhhydro itself and for the files it names."""
+    d = os.path.join(cases.GOLD, "savannah")
+    a = srh2d.process_SRH_2D_input(d, "savana_SI.srhhydro")
+    b = srh2d.process_SRH_2D_input(d, "Savana_SI.SRHhydro")
+    for k in ("cell_areas", "zb_cells", "cellFacesList"):
+        if k in a and k in b:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]))
+    with pytest.raises(Exception):
+        srh2d.process_SRH_2D_input(d, "no_such_case.srhhydro")
