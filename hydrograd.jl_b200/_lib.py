@@ -117,6 +117,7 @@ SYMBOLS = {
     "hg_case_free": (None, [_vp]),
     "hg_case_dims": (C.c_int, [_vp, c_i64p]),
     "hg_case_array": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), c_i64p, C.POINTER(C.c_int32)]),
+    "hg_debug_math": (C.c_int, [_vp, C.c_int32, C.c_int64, c_f64p, c_f64p]),
     "hg_time_rhs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "hg_time_vjp": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_float)]),
     "hg_kernel_launches": (C.c_int64, [_vp]),

@@ -408,6 +408,14 @@ class Context:
         self._ck(self.lib.hg_time_vjp(self._h, int(n_launches), C.byref(ms)))
         return ms.value
 
+    def debug_math(self, kind, x):
+        """The kernels' branch-free fp64 helpers evaluated on the device (accuracy probe): kind 0 = 1/x, 1 = x^-1/2, 2 = sqrt,
+        3 = sqrt(x^2 + eps), 4 = x^(-7/3)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        self._ck(self.lib.hg_debug_math(self._h, int(kind), x.size, _p(x), _p(out)))
+        return out
+
     def kernel_launches(self):
         return int(self.lib.hg_kernel_launches(self._h))
 

@@ -1569,6 +1569,18 @@ int hg_plan_stats(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_de
   return HG_OK;
 }
 
+int hg_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* x, double* out) {
+  if (!ctx || !x || !out || n <= 0 || kind < 0 || kind > 4) return HG_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::DBuf<double> dx, dy;
+  CK(ctx, dx.alloc((size_t)n)); CK(ctx, dy.alloc((size_t)n));
+  CK(ctx, cudaMemcpyAsync(dx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TRY(hg::fused_debug_math(ctx, kind, n, dx.p, dy.p));
+  CK(ctx, cudaMemcpyAsync(out, dy.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return HG_OK;
+}
+
 int hg_flush_l2(hg_ctx* ctx) {
   if (!ctx) return HG_ERR_ARG;
   CK(ctx, cudaSetDevice(ctx->opt.device));

@@ -279,6 +279,7 @@ int fused_lincomb(hg_ctx* ctx, double* y, const double* x, int n, const double* 
 int fused_err_blocks(const hg_ctx* ctx);
 int fused_err_norm(hg_ctx* ctx, const double* u, const double* unew, int n, const double* const* k, const double* coef, double abstol,
                    double reltol, double* d_part, double* d_sum);
+int fused_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* d_x, double* d_out);
 int fused_rhs_ensemble(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 // UDE closure (hg_ude.cu)
 int ude_prepare(hg_ctx* ctx);

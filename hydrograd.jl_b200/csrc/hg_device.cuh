@@ -41,51 +41,53 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Manning's n), so the IEEE special-case slow paths of '/', sqrt() and cbrt() are dead weight: each costs
 // a branch + call sequence per use.  These are the same MUFU seed + Newton refinements, straight-line;
 // results are within 1-2 ulp of the correctly rounded value (parity budget is 1e-12).
+// The MUFU seeds read only the high word of the argument (MUFU.RCP64H / RSQ64H: ~2^-20 relative error), so ONE third-order
+// step (error -> ~e^3 = 2^-60) reaches full precision where two quadratic steps (2^-40, 2^-80) were needed: fewer fp64-pipe
+// instructions and a shorter dependency chain.  Accuracy is measured on the device by tests/test_gpu_parity.py::test_fast_math.
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // MUFU.RCP64H, ~20 bits
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // MUFU.RCP64H
+  const double e = fma(-x, r, 1.0);                        // 1/x = r / (1 - e) = r (1 + e + e^2 + ...)
+  return fma(r, fma(e, e, e), r);
 }
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double r;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); // MUFU.RSQ64H, ~20 bits
-  const double hx = 0.5 * x;
-  double e = fma(-hx * r, r, 0.5);
-  r = fma(r, e, r);
-  e = fma(-hx * r, r, 0.5);
-  r = fma(r, e, r);
-  return r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); // MUFU.RSQ64H
+  const double e = fma(-(x * r), r, 1.0);                  // x^(-1/2) = r (1 - e)^(-1/2) = r (1 + e/2 + 3 e^2/8 + ...)
+  return fma(r * e, fma(0.375, e, 0.5), r);
 }
 __device__ __forceinline__ double fast_sqrt(double x) {   // x > 0
   const double r = fast_rsqrt(x);
-  double s = x * r;
-  const double e = fma(-s, s, x);
-  return fma(e, 0.5 * r, s);
+  const double s = x * r;
+  return fma(fma(-s, s, x), 0.5 * r, s);                   // one correction: correctly rounded but for rare ties
 }
-// x^(-7/3) for x > 0: w = x^(-1/3) from a float seed + two division-free Newton steps (w <- w (4 - x w^3)/3)
+// w = x^(-1/3) for x > 0: float seed (~2^-21) + ONE third-order step, w <- w (1 + e/3 + 2 e^2/9), e = 1 - x w^3.
+// x^(-7/3) = w^7 (friction, semi_discretize_swe_2D.jl:544-547) and 1/x = w^3 both come from it.
+__device__ __forceinline__ double rcbrt_pos(double x) {
+  const double w = (double)exp2f(-0.33333334f * log2f((float)x));
+  const double e = fma(-x, w * w * w, 1.0);
+  return fma(w * e, fma(0.2222222222222222, e, 0.3333333333333333), w);
+}
 __device__ __forceinline__ double pow_m73(double x) {
-  double w = (double)exp2f(-0.33333334f * log2f((float)x));
-  double t = w * w * w;
-  w = w * fma(-x, t, 4.0) * 0.3333333333333333;
-  t = w * w * w;
-  w = w * fma(-x, t, 4.0) * 0.3333333333333333;
+  const double w = rcbrt_pos(x);
   const double w2 = w * w, w4 = w2 * w2;
   return w4 * w2 * w;
 }
-
-__device__ __forceinline__ double smooth_abs(double x) { return fast_sqrt(fma(x, x, EPS)); }
+// smooth |x| = sqrt(x^2 + eps) (utilities/smooth_functions.jl), three per face: y * rsqrt(y) without the correction step,
+// <= 1 ulp (rounding of r and of the product)
+__device__ __forceinline__ double smooth_abs(double x) {
+  const double y = fma(x, x, EPS);
+  return y * fast_rsqrt(y);
+}
 
 struct Side {
   double xi, h, hu, hv, zb, u, v, s, P;
 };
 
-// Riemann_2D_Roe, face-once form.  Returns the flux along the face normal (outward for L).
+// Riemann_2D_Roe, face-once form.  Returns (flux along the face normal, outward for L) * len.  The 1/2 of the Roe average
+// of the two physical fluxes rides in the length factor (scaling by 2 is exact, so the bits are those of 0.5*(..)*len).
 // zbL/zbR point at the bed elevations; they are only read on the (rare) faces with a dry side.
-__device__ __forceinline__ void roe_flux(Side L, Side R, const double* zbL, const double* zbR, double nx, double ny,
+__device__ __forceinline__ void roe_flux(Side L, Side R, const double* zbL, const double* zbR, double nx, double ny, double len,
                                          double g, double hmin, double& o0, double& o1, double& o2) {
   const bool dryL = L.h <= hmin, dryR = R.h <= hmin;
   if (dryL || dryR) {
@@ -100,18 +102,17 @@ __device__ __forceinline__ void roe_flux(Side L, Side R, const double* zbL, cons
       const double hp = W.h + EPS;
       const double p = 0.5 * g * hp * hp;
       const double un = W.u * nx + W.v * ny;
-      o0 = W.hu * nx + W.hv * ny;
-      o1 = W.hu * un + p * nx;
-      o2 = W.hv * un + p * ny;
+      o0 = (W.hu * nx + W.hv * ny) * len;
+      o1 = (W.hu * un + p * nx) * len;
+      o2 = (W.hv * un + p * ny) * len;
       return;
     }
   }
-  const double hRoe = 0.5 * (L.h + R.h);                       // :91 arithmetic mean
   const double rs = fast_rcp(L.s + R.s);
   const double uRoe = (L.s * L.u + R.s * R.u) * rs;
   const double vRoe = (L.s * L.v + R.s * R.v) * rs;
   const double un = uRoe * nx + vRoe * ny;
-  const double c2 = fma(g, hRoe, EPS);
+  const double c2 = fma(0.5 * g, L.h + R.h, EPS);             // g hRoe + eps, hRoe = (hL + hR)/2 (:91 arithmetic mean)
   const double rc = fast_rsqrt(c2);
   const double c = c2 * rc;                                    // sqrt(g hRoe + eps)
   const double k = 0.5 * rc;                                   // 1/(2c)
@@ -126,9 +127,10 @@ __device__ __forceinline__ void roe_flux(Side L, Side R, const double* zbL, cons
   const double y3 = -nx * z1 + vRoe * zs + ny * zd;
   const double unL = L.u * nx + L.v * ny, unR = R.u * nx + R.v * ny;
   const double ps = L.P + R.P;
-  o0 = 0.5 * ((L.hu * nx + L.hv * ny) + (R.hu * nx + R.hv * ny) - y1);  // :121-133
-  o1 = 0.5 * (L.hu * unL + R.hu * unR + ps * nx - y2);
-  o2 = 0.5 * (L.hv * unL + R.hv * unR + ps * ny - y3);
+  const double hl = 0.5 * len;
+  o0 = ((L.hu * nx + L.hv * ny) + (R.hu * nx + R.hv * ny) - y1) * hl;  // :121-133
+  o1 = (L.hu * unL + R.hu * unR + ps * nx - y2) * hl;
+  o2 = (L.hv * unL + R.hv * unR + ps * ny - y3) * hl;
 }
 
 __device__ __forceinline__ void derive(Side& s, double hst, double g) {
@@ -168,6 +170,8 @@ struct TileCfg {
   X(2, 256, 352, 580, 4, 256, 3)      \
   X(4, 512, 672, 1124, 4, 384, 2)     \
   X(3, 512, 672, 1124, 4, 256, 2)     \
+  X(12, 224, 304, 504, 4, 128, 5)     \
+  X(13, 224, 304, 504, 4, 160, 5)     \
   X(9, 192, 264, 436, 4, 160, 6)      \
   X(8, 192, 264, 436, 4, 128, 6)      \
   X(6, 128, 192, 324, 4, 128, 8)      \

@@ -51,8 +51,7 @@ struct Adj {
 __device__ __forceinline__ void sabs_r(double x, double& A, double& r) {  // A = sqrt(x^2+eps), r = 1/A
   const double y = fma(x, x, EPS);
   r = fast_rsqrt(y);
-  A = y * r;
-  A = fma(fma(-A, A, y), 0.5 * r, A);
+  A = y * r;                                                              // same rounding as dev::smooth_abs
 }
 
 // Reverse sweep of the face flux, main (both sides wet) branch only: straight-line code.
@@ -179,56 +178,53 @@ struct FaceCore {
   double ab, bb, Sb;            // adjoints of a, b, S
 };
 __device__ __forceinline__ void roe_adj_core(double xiL, double hL, double uL, double vL, double sL, double xiR, double hR,
-                                             double uR, double vR, double sR, double nx, double ny, double g, double f0b,
-                                             double f1b, double f2b, FaceCore& o) {
-  const double hRoe = 0.5 * (hL + hR);
+                                             double uR, double vR, double sR, double nx, double ny, double g, double b0,
+                                             double b1, double b2, FaceCore& o) {
+  // (b0, b1, b2) = 0.5 * adjoint of the flux = (mu_R - mu_L) * (len/2), formed by the caller
+  const double gh = 0.5 * g;
   const double rs = fast_rcp(sL + sR);
-  const double a_ = sL * uL + sR * uR, b_ = sL * vL + sR * vR;
+  const double a_ = fma(sL, uL, sR * uR), b_ = fma(sL, vL, sR * vR);
   const double uRoe = a_ * rs, vRoe = b_ * rs;
-  const double un = uRoe * nx + vRoe * ny;
-  const double c2 = fma(g, hRoe, EPS);
+  const double un = fma(uRoe, nx, vRoe * ny);
+  const double c2 = fma(gh, hL + hR, EPS);                        // g hRoe + eps
   const double rc = fast_rsqrt(c2);
   const double c = c2 * rc, k = 0.5 * rc;
-  const double d1 = xiR - xiL, d2 = __dmul_rn(hR, uR) - __dmul_rn(hL, uL), d3 = __dmul_rn(hR, vR) - __dmul_rn(hL, vL);
-  const double t1 = uRoe * ny - vRoe * nx;
-  const double w1 = -t1 * d1 + ny * d2 - nx * d3;
-  const double e_ = un * d1 - (nx * d2 + ny * d3);
-  const double m = k * e_;
-  const double w2 = 0.5 * d1 + m, w3 = 0.5 * d1 - m;
+  const double d1 = xiR - xiL, d2 = fma(hR, uR, -(hL * uL)), d3 = fma(hR, vR, -(hL * vL));
+  const double t1 = fma(uRoe, ny, -(vRoe * nx));
+  const double nd = fma(nx, d2, ny * d3);
+  const double w1 = fma(ny, d2, -fma(nx, d3, t1 * d1));
+  const double e_ = fma(un, d1, -nd);
+  const double hd1 = 0.5 * d1, m = k * e_;
+  const double w2 = hd1 + m, w3 = hd1 - m;
   const double l2 = un - c, l3 = un + c;
   double A1, A2, A3, r1, r2, r3;
   sabs_r(un, A1, r1); sabs_r(l2, A2, r2); sabs_r(l3, A3, r3);
   const double z2 = A2 * w2, z3 = A3 * w3;
   const double zs = z2 + z3;
   // ---- reverse
-  const double b0 = 0.5 * f0b, b1 = 0.5 * f1b, b2 = 0.5 * f2b;
-  const double z1b = nx * b2 - ny * b1;                       // y = R_mat z, ybar = -b
-  const double zsb = -(b0 + uRoe * b1 + vRoe * b2);
-  const double zdb = -(nx * b1 + ny * b2);
-  double uRoeb = -zs * b1, vRoeb = -zs * b2;
-  double cb = zdb * (z3 - z2);
-  const double z3b = zsb + c * zdb, z2b = zsb - c * zdb;
+  const double z1b = fma(nx, b2, -(ny * b1));                 // y = R_mat z, ybar = -b
+  const double zsb = -fma(vRoe, b2, fma(uRoe, b1, b0));
+  const double zdb = -fma(nx, b1, ny * b2);
+  const double czd = c * zdb;
+  const double z3b = zsb + czd, z2b = zsb - czd;
+  const double q1 = z1b * r1, q2 = z2b * r2, q3 = z3b * r3;   // d sqrt(x^2+eps)/dx = x / sqrt(..)
   const double w1b = z1b * A1, w2b = z2b * A2, w3b = z3b * A3;
-  const double l1b = z1b * w1 * un * r1, l2b = z2b * w2 * l2 * r2, l3b = z3b * w3 * l3 * r3;   // d sqrt(x^2+eps)/dx = x / sqrt(..)
-  double unb = l1b + l2b + l3b;
-  cb += l3b - l2b;
-  double d1b = 0.5 * (w2b + w3b);
+  const double l1b = q1 * w1 * un, l2b = q2 * w2 * l2, l3b = q3 * w3 * l3;
   const double mb = w2b - w3b;
   const double kb = mb * e_, eb = mb * k;
-  unb += eb * d1;
-  d1b += eb * un;
-  const double t1b = -w1b * d1;
-  d1b -= w1b * t1;
-  uRoeb += t1b * ny + unb * nx;
-  vRoeb += unb * ny - t1b * nx;
-  const double c2b = cb * k - 2.0 * kb * k * k * k;             // c = sqrt(c2), k = 1/(2 sqrt(c2))
+  const double cb = fma(zdb, z3 - z2, l3b - l2b);
+  const double unb = fma(eb, d1, l1b + l2b + l3b);
+  const double t1b = -(w1b * d1);
+  const double uRoeb = fma(unb, nx, fma(t1b, ny, -(zs * b1)));
+  const double vRoeb = fma(unb, ny, -fma(t1b, nx, zs * b2));
+  const double c2b = k * fma(-2.0 * kb, k * k, cb);            // c = sqrt(c2), k = 1/(2 sqrt(c2))
   o.b0 = b0; o.b1 = b1; o.b2 = b2;
-  o.d1b = d1b;
-  o.d2b = w1b * ny - eb * nx;
-  o.d3b = -w1b * nx - eb * ny;
-  o.hh = 0.5 * g * c2b;
+  o.d1b = fma(0.5, w2b + w3b, fma(eb, un, -(w1b * t1)));
+  o.d2b = fma(w1b, ny, -(eb * nx));
+  o.d3b = -fma(w1b, nx, eb * ny);
+  o.hh = gh * c2b;
   o.ab = uRoeb * rs; o.bb = vRoeb * rs;
-  o.Sb = -(uRoeb * a_ + vRoeb * b_) * rs * rs;
+  o.Sb = -fma(o.ab, uRoe, o.bb * vRoe);                        // -(uRoeb a + vRoeb b) rs^2 with a rs = uRoe
 }
 // One side's (xi, q_x, q_y) adjoints from the core: the per-side part of the sweep (physical flux, jumps, Roe
 // weights) composed with the transpose of u = hu/h, v = hv/h, s = sqrt(h+eps), P(xi).  sgn = -1 for L, +1 for R.
@@ -520,8 +516,8 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
       }
       return;
     }
-    const double nx = sm.o[0][f], ny = sm.o[1][f], len = sm.o[2][f];
-    const double f0b = (sm.m0[lR] - sm.m0[lL]) * len, f1b = (sm.m1[lR] - sm.m1[lL]) * len, f2b = (sm.m2[lR] - sm.m2[lL]) * len;
+    const double nx = sm.o[0][f], ny = sm.o[1][f], hl = 0.5 * sm.o[2][f];
+    const double f0b = (sm.m0[lR] - sm.m0[lL]) * hl, f1b = (sm.m1[lR] - sm.m1[lL]) * hl, f2b = (sm.m2[lR] - sm.m2[lL]) * hl;
     FaceCore k;
     roe_adj_core(sm.xi[lL], hL, sm.u[lL], sm.v[lL], sm.s[lL], sm.xi[lR], hR, sm.u[lR], sm.v[lR], sm.s[lR], nx, ny, g,
                  f0b, f1b, f2b, k);
@@ -554,8 +550,8 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
         one_face(fB, bL, bR, hBL, hBR);
         continue;
       }
-      const double nxA = sm.o[0][fA], nyA = sm.o[1][fA], lenA = sm.o[2][fA];
-      const double nxB = sm.o[0][fB], nyB = sm.o[1][fB], lenB = sm.o[2][fB];
+      const double nxA = sm.o[0][fA], nyA = sm.o[1][fA], lenA = 0.5 * sm.o[2][fA];   // half lengths: the 1/2 of the Roe average
+      const double nxB = sm.o[0][fB], nyB = sm.o[1][fB], lenB = 0.5 * sm.o[2][fB];
       FaceCore kA, kB;
       roe_adj_core(sm.xi[aL], hAL, sm.u[aL], sm.v[aL], sm.s[aL], sm.xi[aR], hAR, sm.u[aR], sm.v[aR], sm.s[aR], nxA, nyA, g,
                    (sm.m0[aR] - sm.m0[aL]) * lenA, (sm.m1[aR] - sm.m1[aL]) * lenA, (sm.m2[aR] - sm.m2[aL]) * lenA, kA);
@@ -611,14 +607,16 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     const double y = fma(qx, qx, fma(qy, qy, EPS));
     const double rm = fast_rsqrt(y);
     const double mag = y * rm;
-    const double C = kfr * n * n * pow_m73(h + hs);
+    const double w = rcbrt_pos(h + hs), w2 = w * w, w3 = w2 * w;   // (h+hs)^(-1/3): w^7 = (h+hs)^(-7/3), w^3 = 1/(h+hs)
+    const double C = kfr * n * n * (w3 * w3 * w);
     const double fxb = -lam1, fyb = -lam2;
-    const double cross = C * qx * qy * rm;
-    const double dqx = fxb * (C * mag + C * qx * qx * rm) + fyb * cross;
-    const double dqy = fyb * (C * mag + C * qy * qy * rm) + fxb * cross;
-    const double D = (fxb * qx + fyb * qy) * C * mag;      // fxb*fx + fyb*fy
+    const double Cm = C * mag, Cr = C * rm;
+    const double lq = fma(fxb, qx, fyb * qy);             // fbar . q
+    const double dqx = fma(fxb, Cm, Cr * qx * lq);        // fbar_x C m + C q_x (fbar . q) / m
+    const double dqy = fma(fyb, Cm, Cr * qy * lq);
+    const double D = lq * Cm;                              // fxb*fx + fyb*fy
     // -(7/3) D / (h+hs): through h = xi + hstill (a wet cell is unclamped); bed slope: g xi S0 . lambda
-    const double dxi = -(7.0 / 3.0) * D * fast_rcp(h + hs) + g * (sm.sx[l] * lam1 + sm.sy[l] * lam2);
+    const double dxi = fma(-(7.0 / 3.0) * D, w3, g * fma(sm.sx[l], lam1, sm.sy[l] * lam2));
     CellOut o;
     o.xib = wet ? xib + dxi : xib;
     o.qxb = wet ? qxb + dqx : qxb;
@@ -788,6 +786,10 @@ VjpKernel vjp_pick(int v) {
     // measured at 16M cells (ms): 128x3 two faces per trip 0.92 | 192x3 one face 1.02 | 160x3 two faces 1.14 (spills)
     if (v == 1) return vjp_mk<T, ML, MF, NF, 192, 3, 1>();
     if (v == 2) return vjp_mk<T, ML, MF, NF, 160, 3, 2>();
+    return vjp_mk<T, ML, MF, NF, 128, 3, 2>();
+  } else if constexpr (T == 224) {
+    // <= 512 interior faces per tile: the face phase is exactly two two-face trips of 128 threads (T = 256 needs a third, mostly empty one)
+    if (v == 1) return vjp_mk<T, ML, MF, NF, 160, 3, 1>();
     return vjp_mk<T, ML, MF, NF, 128, 3, 2>();
   } else if constexpr (T == 192) {
     // 96x4 two faces per trip 0.91 | 128x4 one face 0.96 | 128x4 two faces 1.07 (spills)

@@ -447,6 +447,9 @@ HG_API int hg_mesh_stats(const hg_ctx* ctx, int64_t* n_cells, int64_t* n_faces, 
  * [N]) receives the internal->reference cell permutation.                                          */
 HG_API int hg_plan_stats(const hg_mesh_desc* mesh, const hg_bc_desc* bc, const hg_fields_desc* fields,
                   const hg_options* opt, int64_t* stats, int64_t* perm_out);
+/* Accuracy probe of the kernels' branch-free fp64 helpers (hg_device.cuh): out[i] = f(x[i]) evaluated on the device,
+ * kind 0 = 1/x, 1 = 1/sqrt(x), 2 = sqrt(x), 3 = sqrt(x^2 + eps) (smooth abs), 4 = x^(-7/3); x > 0, host pointers.          */
+HG_API int hg_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* x, double* out);
 /* write 256 MiB of device scratch (L2 flush between timed iterations)                             */
 HG_API int hg_flush_l2(hg_ctx* ctx);
 
