@@ -16,7 +16,7 @@ PARAM_NONE, PARAM_ZB, PARAM_MANNING, PARAM_Q, PARAM_UDE = 0, 1, 2, 3, 4
 # active_param_name strings of the reference (application_commons.jl:9); "UDE" = settings.bPerform_UDE (params = NN parameters)
 ACTIVE_PARAM = {None: 0, "": 0, "none": 0, "zb": 1, "ManningN": 2, "Q": 3, "UDE": 4}
 UDE_MAX_HIDDEN, UDE_MAX_WIDTH = 3, 8
-ERR_NAMES = {1: "HG_ERR_ARG", 2: "HG_ERR_CUDA", 3: "HG_ERR_CONVEYANCE", 4: "HG_ERR_SOLVER", 5: "HG_ERR_STATE"}
+ERR_NAMES = {1: "HG_ERR_ARG", 2: "HG_ERR_CUDA", 3: "HG_ERR_CONVEYANCE", 4: "HG_ERR_SOLVER", 5: "HG_ERR_STATE", 6: "HG_ERR_COMM"}
 
 
 class MeshDesc(C.Structure):
@@ -117,6 +117,12 @@ SYMBOLS = {
     "hg_case_free": (None, [_vp]),
     "hg_case_dims": (C.c_int, [_vp, c_i64p]),
     "hg_case_array": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), c_i64p, C.POINTER(C.c_int32)]),
+    "hg_comm_export": (C.c_int, [_vp, C.c_void_p]),
+    "hg_comm_connect": (C.c_int, [_vp, C.c_int64, C.c_void_p, c_i64p, c_i64p]),
+    "hg_comm_init_shm": (C.c_int, [_vp, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "hg_comm_set_auto": (C.c_int, [_vp, C.c_int32]),
+    "hg_comm_exchange": (C.c_int, [_vp, C.c_int32]),
+    "hg_comm_disconnect": (C.c_int, [_vp]),
     "hg_debug_math": (C.c_int, [_vp, C.c_int32, C.c_int64, c_f64p, c_f64p]),
     "hg_time_rhs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "hg_time_vjp": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_float)]),

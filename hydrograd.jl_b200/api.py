@@ -279,6 +279,33 @@ class Context:
         self._ck(self.lib.hg_halo_buffers(self._h, C.byref(s), C.byref(r), C.byref(n)))
         return C.cast(s, C.c_void_p).value, C.cast(r, C.c_void_p).value, n.value
 
+    # library-owned exchange over NVLink peer memory (hg_comm.cu); parallel.connect_contexts / connect_ranks wire it up
+    COMM_HANDLE_BYTES = 128
+
+    def comm_export(self):
+        buf = C.create_string_buffer(self.COMM_HANDLE_BYTES)
+        self._ck(self.lib.hg_comm_export(self._h, buf))
+        return buf.raw
+
+    def comm_connect(self, handles, entry_offsets, flag_indices):
+        blob = b"".join(handles)
+        off = np.ascontiguousarray(entry_offsets, dtype=np.int64)
+        idx = np.ascontiguousarray(flag_indices, dtype=np.int64)
+        self._ck(self.lib.hg_comm_connect(self._h, len(handles), blob, _p(off, L.c_i64p), _p(idx, L.c_i64p)))
+
+    def comm_init_shm(self, job_name, rank, world, neighbor_ranks):
+        nb = (C.c_int32 * len(neighbor_ranks))(*[int(r) for r in neighbor_ranks])
+        self._ck(self.lib.hg_comm_init_shm(self._h, job_name.encode(), int(rank), int(world), nb))
+
+    def comm_set_auto(self, on=True):
+        self._ck(self.lib.hg_comm_set_auto(self._h, int(on)))
+
+    def comm_exchange(self, with_lambda=False):
+        self._ck(self.lib.hg_comm_exchange(self._h, int(with_lambda)))
+
+    def comm_disconnect(self):
+        self._ck(self.lib.hg_comm_disconnect(self._h))
+
     def halo_pack(self, with_lambda=False):
         self._ck(self.lib.hg_halo_pack(self._h, int(with_lambda)))
 

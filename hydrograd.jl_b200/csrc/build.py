@@ -18,6 +18,7 @@ SOURCES = [
     ("hg_fused.cu", []),
     ("hg_vjp.cu", []),
     ("hg_ude.cu", []),
+    ("hg_comm.cu", []),
 ]
 
 

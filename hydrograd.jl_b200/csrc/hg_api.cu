@@ -72,6 +72,7 @@ int check_err_flag(hg_ctx* ctx) {
   if (h != 0) {
     CK(ctx, cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
     if (h == HG_ERR_CONVEYANCE) ctx->err = "Total cross-sectional conveyance for an inlet-q boundary is not positive";
+    else if (h == HG_ERR_COMM) ctx->err = "halo exchange: a neighbour's push did not arrive within the time-out (exchanges are collective: every rank must issue the same sequence of RHS / VJP calls)";
     else ctx->err = "device-side error flag " + std::to_string(h);
     return h;
   }
@@ -201,6 +202,7 @@ void hg_destroy(hg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->opt.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  hg_comm_disconnect(ctx);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);

@@ -52,6 +52,14 @@ struct Consts {
   double g, k_n, h_small;
 };
 
+// what a consumer kernel needs to wait for the halo of this exchange (library-owned transport); n = 0: nothing to wait for
+struct CommWait {
+  const unsigned long long* flags = nullptr;   // local flag lines, 16 u64 apart
+  unsigned long long epoch = 0;
+  int32_t n = 0, from = 0;                     // neighbours; first CTA index (band order) that touches halo faces
+  int32_t* err = nullptr;
+};
+
 // state-dependent Manning's n (hg_set_manning_function); type 0 = off
 struct MannFn {
   int32_t type = 0;
@@ -188,6 +196,22 @@ struct Frozen {
 
 }  // namespace hg
 
+// library-owned halo exchange (hg_comm.cu)
+struct hg_comm {
+  int32_t n = 0;                          // neighbours (= halo boundaries of the context)
+  int64_t stride = 0, flags_off = 0;      // doubles per parity buffer; byte offset of the flag lines
+  size_t bytes = 0;
+  void* buf = nullptr;                    // one cudaMalloc: recv[0] | recv[1] | one 128-byte flag line per neighbour
+  double* recv[2] = {nullptr, nullptr};
+  unsigned long long* flags = nullptr;    // written by the peers: epoch of the last completed push
+  hg::DBuf<double*> d_dst0, d_dst1;       // [n] where this rank's block k lands in peer k's parity buffer 0 / 1
+  hg::DBuf<unsigned long long*> d_flag;   // [n] this rank's flag line at peer k
+  hg::DBuf<int32_t> d_ptr;                // [n+1] entry ranges of the blocks
+  std::vector<void*> opened;              // cudaIpcOpenMemHandle mappings
+  unsigned long long epoch = 0;           // exchanges issued so far
+  bool connected = false, auto_exchange = true, pushed = false;
+};
+
 struct hg_ctx {
   hg_options opt{};
   int64_t N = 0, F = 0, B = 0, sumnf = 0;
@@ -219,7 +243,7 @@ struct hg_ctx {
   hg::PlainDev pd;
   hg::FusedHost fh;
   int32_t fh_force_nf = 0;     // build_tiles: face slots per cell of the attempt being built (4 or 8)
-  struct hg_comm* comm = nullptr;   // library-owned halo exchange (hg_comm.cu); null = the caller moves halo_send -> halo_recv
+  hg_comm* comm = nullptr;   // library-owned halo exchange (hg_comm.cu); null = the caller moves halo_send -> halo_recv
   hg::FusedDev fd;
   double* h_pinned = nullptr;  // staging [6N] pinned host memory
   size_t h_pinned_bytes = 0;
@@ -232,7 +256,7 @@ struct hg_ctx {
   std::vector<int32_t> matid_ref;
 };
 
-inline bool hg_comm_ready(const hg_ctx* ctx) { return ctx->comm != nullptr; }
+inline bool hg_comm_ready(const hg_ctx* ctx) { return ctx->comm != nullptr && ctx->comm->connected; }
 
 namespace hg {
 // host-side builder (hg_host.cpp)
@@ -268,7 +292,7 @@ void fused_inlet_coef(hg_ctx* ctx, const double* d_Q);
 int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);
 int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar, const int32_t* tile_order,
-                    int32_t tile_base, int32_t n_run);
+                    int32_t tile_base, int32_t n_run, bool use_comm = false);
 int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar);
 int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 int fused_halo_pack(hg_ctx* ctx, bool with_lambda);
@@ -279,6 +303,8 @@ int fused_lincomb(hg_ctx* ctx, double* y, const double* x, int n, const double* 
 int fused_err_blocks(const hg_ctx* ctx);
 int fused_err_norm(hg_ctx* ctx, const double* u, const double* unew, int n, const double* const* k, const double* coef, double abstol,
                    double reltol, double* d_part, double* d_sum);
+// library-owned halo exchange (hg_comm.cu): push d_Q (and d_lam) of the cut cells into the neighbours' receive buffers
+int comm_push(hg_ctx* ctx, const double* d_Q, const double* d_lam);
 int fused_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* d_x, double* d_out);
 int fused_rhs_ensemble(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
 // UDE closure (hg_ude.cu)

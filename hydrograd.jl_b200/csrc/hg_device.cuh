@@ -36,6 +36,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+// ---------------------------------------------------------------- library-owned halo exchange: consumer side
+// Thread k < w.n of a band tile's CTA waits until neighbour k has published this exchange's epoch (hg_comm.cu); the
+// block barrier that follows phase 1 hands the acquired view to the rest of the CTA.  Gives up after ~4 s (a peer that
+// never pushed: mismatched call sequences) by raising the device error flag instead of hanging the GPU.
+__device__ __forceinline__ void comm_wait(const CommWait& w, int tid) {
+  if (tid >= w.n) return;
+  const unsigned long long* f = w.flags + (size_t)tid * 16;
+  unsigned long long v, t0 = 0, t;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v >= w.epoch) return;
+    if ((it & 255u) == 255u) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) { atomicExch(w.err, HG_ERR_COMM); return; }
+    }
+    __nanosleep(64);
+  }
+}
+
 // ---------------------------------------------------------------- branch-free fp64 helpers
 // Every argument on this path is a positive normal number (h >= h_small, x^2 + eps, g h + eps, areas,
 // Manning's n), so the IEEE special-case slow paths of '/', sqrt() and cbrt() are dead weight: each costs

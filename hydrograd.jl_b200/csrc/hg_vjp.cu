@@ -42,6 +42,7 @@ struct VjpArgs {
   const double *Q, *lam;
   double *Qbar, *nbar, *s0bar;          // [3Ns], [Ns], [2Ns]
   double *ent_c, *ent_n, *ent_z;        // per boundary entry: inlet coef adjoint share, n adjoint, zb adjoint
+  CommWait cw;                          // library-owned halo exchange: CTAs >= cw.from wait for the neighbours' pushes
 };
 
 struct Adj {
@@ -331,11 +332,11 @@ __device__ __forceinline__ void vjp_boundary_face(Smem& sm, const VjpArgs& a, in
     } else {
       // remote cell: state and cotangent arrived through the halo buffers; its own adjoint is computed by its owner
       const int32_t off = a.halo_off[e], n = a.halo_cnt[e];
-      const double xr = a.halo_recv[off], qxr = a.halo_recv[off + n], qyr = a.halo_recv[off + 2 * n];
+      const double xr = __ldcg(a.halo_recv + off), qxr = __ldcg(a.halo_recv + off + n), qyr = __ldcg(a.halo_recv + off + 2 * n);
       const double rAr = fast_rcp(a.bc_l23[e]);          // remote cell area rides in l23
       // mu_remote is a rounded product exactly like an in-tile cell's (no FMA contraction with the sum)
-      f0b += __dmul_rn(a.halo_recv[off + 3 * n], rAr); f1b += __dmul_rn(a.halo_recv[off + 4 * n], rAr);
-      f2b += __dmul_rn(a.halo_recv[off + 5 * n], rAr);
+      f0b += __dmul_rn(__ldcg(a.halo_recv + off + 3 * n), rAr); f1b += __dmul_rn(__ldcg(a.halo_recv + off + 4 * n), rAr);
+      f2b += __dmul_rn(__ldcg(a.halo_recv + off + 5 * n), rAr);
       const double hr = xr + hstg;
       const bool dryr = hr <= hs;
       R.h = dryr ? hs : hr; R.hu = dryr ? 0.0 : qxr; R.hv = dryr ? 0.0 : qyr; R.xi = xr;
@@ -473,6 +474,7 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     if (p0.w > 0) bulk_prefetch_l2(a.halo + p0.z, (uint32_t)((p0.w + 3) & ~3) * 4u);
     if (!a.tile_order && wp + a.prefetch < a.n_run) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tile_desc + (size_t)(wp + a.prefetch) * kTileDesc));
   }
+  if (a.cw.n > 0 && (int)blockIdx.x >= a.cw.from) comm_wait(a.cw, tid);   // band tile: phase 2b reads what the neighbours push
   mbar_wait(sm.bar, 0);
 
   // ---- phase 1: owned cells, in place
@@ -721,12 +723,50 @@ __global__ void __launch_bounds__(kZoneBlock) k_zone_partial(int32_t N, int32_t 
     __syncthreads();
   }
 }
-__global__ void k_zone_final(int32_t nblocks, int32_t n_mat, const double* __restrict__ part, double* __restrict__ pbar) {
-  const int32_t z = blockIdx.x * blockDim.x + threadIdx.x;
-  if (z >= n_mat) return;
+// few zones (the reference's cases have 1-6 Manning zones): ONE pass over the chunk with a register accumulator per zone,
+// then a fixed-shape reduction per zone (warp shuffles, then the 8 warp sums in order) -- 12 B per cell, bandwidth-bound
+template <int NZ>
+__global__ void __launch_bounds__(kZoneBlock) k_zone_partial_few(int32_t N, int32_t n_mat, const int32_t* __restrict__ matid,
+                                                                 const double* __restrict__ nbar, double* __restrict__ part) {
+  __shared__ double ws[kZoneBlock / 32][NZ];
+  const int32_t b0 = blockIdx.x * kZoneChunk;
+  double acc[NZ];
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) acc[z] = 0.0;
+  for (int32_t i = b0 + threadIdx.x; i < min(N, b0 + kZoneChunk); i += kZoneBlock) {
+    const int32_t m = matid[i];
+    const double v = nbar[i];
+#pragma unroll
+    for (int z = 0; z < NZ; ++z) acc[z] += (m == z) ? v : 0.0;
+  }
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) {
+    double v = acc[z];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5][z] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_mat) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kZoneBlock / 32; ++w) v += ws[w][threadIdx.x];
+    part[(size_t)blockIdx.x * n_mat + threadIdx.x] = v;
+  }
+}
+// one CTA per zone: 256 strided sums over the blocks' partials in block order, then a fixed tree
+__global__ void __launch_bounds__(256) k_zone_final(int32_t nblocks, int32_t n_mat, const double* __restrict__ part, double* __restrict__ pbar) {
+  __shared__ double red[256];
+  const int32_t z = blockIdx.x;
   double acc = 0.0;
-  for (int32_t b = 0; b < nblocks; ++b) acc += part[(size_t)b * n_mat + z];
-  pbar[z] = acc;
+  for (int32_t b = threadIdx.x; b < nblocks; b += 256) acc += part[(size_t)b * n_mat + z];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) pbar[z] = red[0];
 }
 
 // zbar (reference order) = (update_bed_data)^T S0bar + exit-h entries.  Transposed Green-Gauss as a gather:
@@ -830,7 +870,7 @@ int fused_vjp_prepare(hg_ctx* ctx, int cfg_id) {
 // The tile kernel over the tiles tile_order[tile_base .. tile_base + n_run) (tile_order NULL: all tiles, identity).
 // The inlet coefficients must be current (fused_inlet_coef).
 int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar, const int32_t* tile_order,
-                    int32_t tile_base, int32_t n_run) {
+                    int32_t tile_base, int32_t n_run, bool use_comm) {
   FusedDev& d = ctx->fd;
   const FusedHost& fh = ctx->fh;
   if (n_run == 0) return HG_OK;
@@ -846,6 +886,12 @@ int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_
   a.wse = d.wse.p; a.Q = d_Q; a.lam = d_lam; a.Qbar = d_Qbar; a.nbar = d.nbar.p; a.s0bar = d.s0bar.p;
   a.ent_c = d.ent_c.p; a.ent_n = d.ent_n.p; a.ent_z = d.ent_z.p;
   a.tile_order = tile_order; a.tile_base = tile_base;
+  if (use_comm) {   // library-owned exchange (see launch_rhs)
+    const hg_comm* cm = ctx->comm;
+    a.tile_order = d.band_order.p; a.tile_base = 0; n_run = fh.n_tiles;
+    a.halo_recv = cm->recv[cm->epoch & 1];
+    a.cw.flags = cm->flags; a.cw.epoch = cm->epoch; a.cw.n = cm->n; a.cw.from = fh.n_interior_tiles; a.cw.err = d.err.p;
+  }
   const unsigned grid = (unsigned)(n_run >= 0 ? n_run : fh.n_tiles);
   a.n_run = (int32_t)grid;
   const VjpKernel kk = vjp_kernel(cfg_id, ctx->opt.reserved[2]);
@@ -885,9 +931,12 @@ int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar) {
     if (d.zone_part.n < (size_t)nblocks * ctx->n_mat) {
       if (d.zone_part.alloc((size_t)nblocks * ctx->n_mat) != cudaSuccess) { ctx->err = "cudaMalloc(zone_part)"; return HG_ERR_CUDA; }
     }
-    k_zone_partial<<<nblocks, kZoneBlock, kZoneBlock * sizeof(double), ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid.p,
-                                                                                      d.nbar.p, d.zone_part.p);
-    k_zone_final<<<(unsigned)((ctx->n_mat + 63) / 64), 64, 0, ctx->stream>>>(nblocks, (int32_t)ctx->n_mat, d.zone_part.p, d.pbar.p);
+    if (ctx->n_mat <= 8)
+      k_zone_partial_few<8><<<nblocks, kZoneBlock, 0, ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid.p, d.nbar.p, d.zone_part.p);
+    else
+      k_zone_partial<<<nblocks, kZoneBlock, kZoneBlock * sizeof(double), ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid.p,
+                                                                                        d.nbar.p, d.zone_part.p);
+    k_zone_final<<<(unsigned)ctx->n_mat, 256, 0, ctx->stream>>>(nblocks, (int32_t)ctx->n_mat, d.zone_part.p, d.pbar.p);
     ctx->launches += 2;
   } else if (ctx->active == HG_PARAM_ZB) {
     PlainDev& p = ctx->pd;
@@ -920,7 +969,20 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
     if (rc0 != HG_OK) return rc0;
   }
   if (ctx->n_inletq > 0) fused_inlet_coef(ctx, d_Q);
-  const int rc = fused_vjp_tiles(ctx, cfg_id, d_Q, d_lam, d_Qbar, nullptr, 0, -1);
+  bool use_comm = false;
+  if (hg_comm_ready(ctx)) {   // the adjoint of a cut face needs the remote cell's state AND cotangent
+    hg_comm* cm = ctx->comm;
+    if (cm->auto_exchange) {
+      const int rc0 = comm_push(ctx, d_Q, d_lam);
+      if (rc0 != HG_OK) return rc0;
+    } else if (!cm->pushed) {
+      ctx->err = "halo exchange: auto mode is off and hg_comm_exchange(with_lambda = 1) was not called before this evaluation";
+      return HG_ERR_STATE;
+    }
+    cm->pushed = false;
+    use_comm = true;
+  }
+  const int rc = fused_vjp_tiles(ctx, cfg_id, d_Q, d_lam, d_Qbar, nullptr, 0, -1, use_comm);
   return rc != HG_OK ? rc : fused_vjp_finish(ctx, d_Q, d_Qbar);
 }
 

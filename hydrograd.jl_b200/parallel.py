@@ -234,3 +234,43 @@ def attach_exchanger(ctx, ranks, group=None):
     if torch.cuda.current_stream().cuda_stream != 0:
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     return HaloExchanger(send, recv, ranks, counts, group)
+
+
+# ---------------------------------------------------------------- library-owned exchange (hg_comm.cu): wiring only
+def _peer_tables(rank, neighbors, tables):
+    """For each neighbour q of `rank`: (entries before rank's block in q's boundary list, index of rank in q's list).
+    tables[q] = (neighbors_q, counts_q)."""
+    off, idx = [], []
+    for q in neighbors:
+        nb_q, cnt_q = tables[q]
+        j = list(nb_q).index(rank)
+        off.append(int(sum(cnt_q[:j])))
+        idx.append(j)
+    return off, idx
+
+
+def connect_contexts(ctxs, infos):
+    """Several rank contexts living in THIS process (one host process driving several GPUs, or emulated ranks on one
+    device): exchange the handles directly.  infos[r] = the info dict of extract_local for rank r."""
+    handles = [c.comm_export() if info["neighbors"] else None for c, info in zip(ctxs, infos)]
+    tables = {r: (info["neighbors"], info["counts"]) for r, info in enumerate(infos)}
+    for r, (c, info) in enumerate(zip(ctxs, infos)):
+        if not info["neighbors"]:
+            continue
+        off, idx = _peer_tables(r, info["neighbors"], tables)
+        c.comm_connect([handles[q] for q in info["neighbors"]], off, idx)
+
+
+def connect_ranks(ctx, info, group=None):
+    """One process per GPU (torchrun): all-gather the handles and neighbour tables over torch.distributed (plumbing; the
+    data path afterwards is peer stores over NVLink, no NCCL)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    mine = (ctx.comm_export() if info["neighbors"] else None, list(info["neighbors"]), [int(c) for c in info["counts"]])
+    everyone = [None] * dist.get_world_size(group)
+    dist.all_gather_object(everyone, mine, group=group)
+    if info["neighbors"]:
+        tables = {q: (e[1], e[2]) for q, e in enumerate(everyone)}
+        off, idx = _peer_tables(rank, info["neighbors"], tables)
+        ctx.comm_connect([everyone[q][0] for q in info["neighbors"]], off, idx)
+    dist.barrier(group)

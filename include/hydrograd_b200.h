@@ -58,7 +58,8 @@ enum {
   HG_ERR_CUDA = 2,        /* CUDA runtime failure or no sm_100 device                          */
   HG_ERR_CONVEYANCE = 3,  /* inlet-q total conveyance <= 1e-10 (bc_2D.jl:678-680 assert)       */
   HG_ERR_SOLVER = 4,      /* unknown Riemann solver (semi_discretize_swe_2D.jl:356-361)        */
-  HG_ERR_STATE = 5        /* call sequence error (e.g. device state never set)                 */
+  HG_ERR_STATE = 5,       /* call sequence error (e.g. device state never set)                 */
+  HG_ERR_COMM = 6         /* library-owned halo exchange: a neighbour's push did not arrive in time */
 };
 
 /* ---- mesh_2D (src/meshes/mesh_2D.jl:2-71): the fields swe_2d_rhs reads, flattened. -------------
@@ -348,6 +349,27 @@ HG_API int hg_set_stream(hg_ctx* ctx, void* cuda_stream);
 /* resident cotangent for hg_vjp_resident / hg_time_vjp */
 HG_API int hg_set_lambda(hg_ctx* ctx, const double* lambda);
 HG_API int hg_vjp_resident(hg_ctx* ctx);
+
+/* ---- library-owned halo exchange over NVLink peer memory (hg_comm.cu): replaces the caller-side NCCL send/recv.
+ * Each rank exports a handle of its receive block, collects its neighbours' handles by whatever messaging the host has
+ * (MPI, Distributed.jl, torch.distributed: plumbing only) and connects; or lets hg_comm_init_shm do the rendezvous through
+ * POSIX shared memory (one process per GPU on one box, no messaging layer needed).  Ranks living in ONE process (one host
+ * process driving several GPUs) connect the same way -- peer access instead of CUDA IPC.  Once connected, every resident RHS /
+ * VJP / stepper call pushes the cut cells' states (and cotangents) straight into the neighbours' buffers and the tile kernel
+ * itself waits for the halo only in the tiles that touch it: calls are COLLECTIVE (same sequence on every rank).
+ *   peer_handles        [n_neighbors * HG_COMM_HANDLE_BYTES], neighbour k = k-th halo boundary of this context
+ *   peer_entry_offset   [n_neighbors] halo entries that precede THIS rank's block in neighbour k's own boundary list
+ *   peer_flag_index     [n_neighbors] index of THIS rank in neighbour k's neighbour list                                  */
+#define HG_COMM_HANDLE_BYTES 128
+HG_API int hg_comm_export(hg_ctx* ctx, void* handle /* [HG_COMM_HANDLE_BYTES] */);
+HG_API int hg_comm_connect(hg_ctx* ctx, int64_t n_neighbors, const void* peer_handles, const int64_t* peer_entry_offset,
+                           const int64_t* peer_flag_index);
+HG_API int hg_comm_init_shm(hg_ctx* ctx, const char* job_name, int32_t rank, int32_t world, const int32_t* neighbor_ranks /* [n_neighbors] */);
+/* auto (default 1): every resident RHS / VJP evaluation starts with an exchange of the state it evaluates.  auto = 0: the
+ * caller issues hg_comm_exchange itself (several contexts of ONE process on ONE device must push all before any consumes). */
+HG_API int hg_comm_set_auto(hg_ctx* ctx, int32_t on);
+HG_API int hg_comm_exchange(hg_ctx* ctx, int32_t with_lambda);
+HG_API int hg_comm_disconnect(hg_ctx* ctx);   /* call after a barrier: peers must not push any more */
 
 /* Multi-GPU overlap of the halo exchange with the tiles that need no remote cell.  phase 1: everything that does not
  * touch a halo face (launch it right after hg_halo_pack, while the exchange is in flight on another stream); phase 2: the

@@ -15,19 +15,23 @@ lam = np.random.default_rng(0).standard_normal(3 * N)
 p = np.array([0.02, 0.04, 0.05, 0.03, 0.045, 0.05])[:flat["n_mat"]]
 print("N", N, "rhs B/cell", Brhs / N, "vjp B/cell", Bvjp / N, flush=True)
 res = []
-for tile, threads, var in [(256, 0, 0), (256, 128, 0), (224, 0, 0), (224, 160, 1), (192, 0, 0)]:
+CFG = [(256, 0, 0), (256, 128, 0), (192, 0, 0)] if len(sys.argv) < 3 else [tuple(int(v) for v in c.split(",")) for c in sys.argv[2:]]
+for tile, threads, var in CFG:
     t0 = time.time()
     ctx = hg.Context(flat, tile_cells=tile, threads=threads, vjp_variant=var)
     tc = time.time() - t0
-    ctx.set_state(Q0); ctx.set_lambda(lam); ctx.set_params(p, "ManningN")
+    ctx.set_state(Q0); ctx.set_lambda(lam)
     ctx.time_rhs(5); ctx.time_vjp(5)
+    tv0 = min(ctx.time_vjp(20) / 20 for _ in range(3))      # no active parameter: the tile kernel + inlet follow-ups only
+    ctx.set_params(p, "ManningN")
+    ctx.time_vjp(5)
     tr = min(ctx.time_rhs(20) / 20 for _ in range(3))
     tv = min(ctx.time_vjp(20) / 20 for _ in range(3))
     # sustained: ~1.5 s of back-to-back launches each
     nr = int(1500 / tr / 2); ctx.time_rhs(nr); trs = ctx.time_rhs(nr) / nr
     nv = int(1500 / tv / 2); ctx.time_vjp(nv); tvs = ctx.time_vjp(nv) / nv
     r = dict(tile=tile, threads=threads, vjp_variant=var, create_s=round(tc, 1), rhs_ms=round(tr, 4), rhs_frac=round(Brhs / tr / 1e6 / PEAK, 3),
-             vjp_ms=round(tv, 4), vjp_frac=round(Bvjp / tv / 1e6 / PEAK, 3), rhs_sust_ms=round(trs, 4), rhs_sust_frac=round(Brhs / trs / 1e6 / PEAK, 3),
+             vjp_noparam_ms=round(tv0, 4), vjp_ms=round(tv, 4), vjp_frac=round(Bvjp / tv / 1e6 / PEAK, 3), rhs_sust_ms=round(trs, 4), rhs_sust_frac=round(Brhs / trs / 1e6 / PEAK, 3),
              vjp_sust_ms=round(tvs, 4), vjp_sust_frac=round(Bvjp / tvs / 1e6 / PEAK, 3))
     print(json.dumps(r), flush=True)
     res.append(r)
