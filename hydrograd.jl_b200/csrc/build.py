@@ -9,7 +9,7 @@ OUT = os.path.join(PKG, "libhydrograd_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 SOURCES = [
-    ("hg_host.cpp", []),
+    ("hg_host.cpp", ["-Xcompiler", "-fopenmp"]),     # the tile builder runs on all host cores
     ("hg_srh.cpp", []),
     ("hg_results.cpp", []),
     ("hg_api.cu", []),
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
             print(" ".join(cmd), flush=True)
             subprocess.run(cmd, check=True)
     if force or _newer(OUT, objs):
-        cmd = ["nvcc"] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + objs
+        cmd = ["nvcc"] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + objs + ["-lgomp"]
         print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
     return OUT

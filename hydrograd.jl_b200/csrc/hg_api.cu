@@ -314,6 +314,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(al(ctx, d.pbar, npar)); TRY(al(ctx, d.ent_c, std::max<int64_t>(B, 1))); TRY(al(ctx, d.ent_n, std::max<int64_t>(B, 1)));
     TRY(al(ctx, d.ent_z, std::max<int64_t>(B, 1))); TRY(al(ctx, d.ent_h, std::max<int64_t>(B, 1)));
     TRY(al(ctx, d.Qinbar, std::max<int64_t>(ctx->n_inletq, 1))); TRY(al(ctx, d.inlet_A, std::max<int64_t>(ctx->n_inletq, 1)));
+    TRY(al(ctx, d.nbcorr, std::max<int64_t>((int64_t)h.bcell_ref.size(), 1)));
     {
       std::vector<int32_t> bcell_int(h.bcell_ref.size());
       for (size_t q = 0; q < bcell_int.size(); ++q) bcell_int[q] = fh.iperm[h.bcell_ref[q]];

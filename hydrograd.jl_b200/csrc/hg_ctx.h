@@ -178,7 +178,7 @@ struct FusedDev {
   DBuf<double> inlet_coef;                         // [n_inletq]  Q_k / total_A
   DBuf<double> Qin, wse;
   DBuf<double> Q, Q2, dQ, lam, Qbar, stage, params, pbar, nbar, s0bar;  // state-like: [3*Ns]
-  DBuf<double> ent_c, ent_n, ent_z, ent_h, Qinbar, inlet_A, zone_part;   // VJP: per boundary entry / per inlet
+  DBuf<double> ent_c, ent_n, ent_z, ent_h, Qinbar, inlet_A, zone_part, nbcorr;   // VJP: per boundary entry / per inlet
   DBuf<int32_t> bcell, bcell_ref, bcell_ptr, bcell_ent;                 // boundary-adjacent cells -> their entries
   DBuf<int32_t> halo_off, halo_cnt;                                     // [B]
   DBuf<double> ens_Q, ens_Q2, ens_mann, ens_Qin, ens_coef, ens_A;       // parameter ensembles: [M][...]
@@ -292,7 +292,7 @@ void fused_inlet_coef(hg_ctx* ctx, const double* d_Q);
 int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);
 int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar, const int32_t* tile_order,
-                    int32_t tile_base, int32_t n_run, bool use_comm = false);
+                    int32_t tile_base, int32_t n_run, bool use_comm = false, bool pdl = false);
 int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar);
 int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 int fused_halo_pack(hg_ctx* ctx, bool with_lambda);

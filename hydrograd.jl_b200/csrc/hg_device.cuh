@@ -36,6 +36,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The tile kernels are launched as programmatic dependents of the small single-CTA kernel that precedes them
+// (k_inlet_coef: the boundary-wide conveyance sum): it releases its dependents at once, the tile kernel runs beside it, and
+// only the threads that evaluate an inlet-q face wait for its result.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- library-owned halo exchange: consumer side
 // Thread k < w.n of a band tile's CTA waits until neighbour k has published this exchange's epoch (hg_comm.cu); the
 // block barrier that follows phase 1 hands the acquired view to the rest of the CTA.  Gives up after ~4 s (a peer that

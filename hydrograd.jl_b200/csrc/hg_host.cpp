@@ -7,6 +7,7 @@
 // This replaces the per-call Dict / Vector-of-Vector lookups of compute_inviscid_fluxes
 // (semi_discretize_swe_2D.jl:286-330) with one O(N log N) preprocessing step at hg_create.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -25,9 +26,21 @@ namespace hg {
     return (code);                                    \
   } while (0)
 
+// HG_DEBUG_TIMING=1: wall time of the host-side preprocessing stages on stderr
+struct StageTimer {
+  const char* what;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit StageTimer(const char* w) : what(w) {}
+  ~StageTimer() {
+    if (getenv("HG_DEBUG_TIMING"))
+      fprintf(stderr, "[hg] %-28s %8.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+
 int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f,
                std::vector<int32_t>& cf_ptr, std::vector<int32_t>& cf_nb, std::vector<double>& cf_nx,
                std::vector<double>& cf_ny, std::vector<double>& cf_len, std::vector<int32_t>& cf_face) {
+  StageTimer timer("build_host");
   if (!m || !b || !f) HG_FAIL(ctx, HG_ERR_ARG, "null descriptor");
   const int64_t N = m->n_cells, F = m->n_faces, B = m->n_ghost, ld = m->ld, base = m->index_base;
   if (N <= 0 || F <= 0 || B < 0 || ld <= 0) HG_FAIL(ctx, HG_ERR_ARG, "bad sizes N=%ld F=%ld B=%ld ld=%ld", (long)N, (long)F, (long)B, (long)ld);
@@ -69,19 +82,28 @@ int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg
   const int64_t S = cf_ptr[N];
   ctx->sumnf = S;
   cf_nb.resize(S); cf_nx.resize(S); cf_ny.resize(S); cf_len.resize(S); cf_face.resize(S);
+  int64_t bad_cell = -1, bad_face = -1;
+  int bad_kind = 0;   // 1 face id, 2 ghost id, 3 neighbour id
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < N; ++i) {
     for (int64_t j = 0; j < cf_ptr[i + 1] - cf_ptr[i]; ++j) {
       int64_t fv = m->cell_faces[i + N * j];
       int64_t fid = (fv < 0 ? -fv : fv) - base;
-      if (fid < 0 || fid >= F) HG_FAIL(ctx, HG_ERR_ARG, "cell %ld face %ld: face id out of range", (long)i, (long)j);
+      int kind = 0;
       int64_t nb = m->cell_neighbors[i + N * j] - base;
       int64_t k = cf_ptr[i] + j;
-      if (m->face_is_boundary[fid]) {
-        if (nb < 0 || nb >= B) HG_FAIL(ctx, HG_ERR_ARG, "cell %ld face %ld: ghost id out of range", (long)i, (long)j);
-        cf_nb[k] = (int32_t)(N + nb);
+      if (fid < 0 || fid >= F) kind = 1;
+      else if (m->face_is_boundary[fid]) {
+        if (nb < 0 || nb >= B) kind = 2;
+        else cf_nb[k] = (int32_t)(N + nb);
       } else {
-        if (nb < 0 || nb >= N || nb == i) HG_FAIL(ctx, HG_ERR_ARG, "cell %ld face %ld: neighbour id out of range", (long)i, (long)j);
-        cf_nb[k] = (int32_t)nb;
+        if (nb < 0 || nb >= N || nb == i) kind = 3;
+        else cf_nb[k] = (int32_t)nb;
+      }
+      if (kind) {
+#pragma omp critical(hg_csr_fail)
+        if (bad_cell < 0 || i < bad_cell) { bad_cell = i; bad_face = j; bad_kind = kind; }
+        continue;
       }
       cf_nx[k] = m->cell_normals[i + N * (j + ld * 0)];
       cf_ny[k] = m->cell_normals[i + N * (j + ld * 1)];
@@ -89,6 +111,9 @@ int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg
       cf_face[k] = (int32_t)fid;
     }
   }
+  if (bad_cell >= 0)
+    HG_FAIL(ctx, HG_ERR_ARG, "cell %ld face %ld: %s id out of range", (long)bad_cell, (long)bad_face,
+            bad_kind == 1 ? "face" : bad_kind == 2 ? "ghost" : "neighbour");
 
   // ---- boundary entries in processing order
   BcHost& h = ctx->bch;
@@ -181,12 +206,12 @@ struct Rcb {
   const double* cy;
   int32_t T;
   std::vector<int32_t>& idx;
-  std::vector<int32_t>& tile0;
+  bool ok = true;   // every leaf starts at a multiple of T
   void run(int64_t lo, int64_t hi) {
     const int64_t n = hi - lo;
     if (n <= T) {
       std::sort(idx.begin() + lo, idx.begin() + hi);
-      tile0.push_back((int32_t)lo);
+      if (lo % T != 0) ok = false;
       return;
     }
     double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
@@ -200,8 +225,17 @@ struct Rcb {
     std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [key](int32_t a, int32_t b) {
       return key[a] < key[b] || (key[a] == key[b] && a < b);
     });
-    run(lo, mid);
-    run(mid, hi);
+    // the two halves are independent (disjoint index ranges): OpenMP tasks down to ~64K cells
+    if (n > 65536) {
+#pragma omp task shared(idx)
+      run(lo, mid);
+#pragma omp task shared(idx)
+      run(mid, hi);
+#pragma omp taskwait
+    } else {
+      run(lo, mid);
+      run(mid, hi);
+    }
   }
 };
 }  // namespace
@@ -271,11 +305,12 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
   fh.perm.resize(N);
   std::iota(fh.perm.begin(), fh.perm.end(), 0);
   if (ctx->opt.reorder && m->cell_centroids) {
-    std::vector<int32_t> leaves;
-    Rcb r{m->cell_centroids, m->cell_centroids + N, T, fh.perm, leaves};
+    StageTimer timer("rcb renumbering");
+    Rcb r{m->cell_centroids, m->cell_centroids + N, T, fh.perm};
+#pragma omp parallel
+#pragma omp single
     r.run(0, N);
-    for (size_t k = 0; k < leaves.size(); ++k)
-      if (leaves[k] != (int64_t)k * T) HG_FAIL(ctx, HG_ERR_ARG, "internal error: RCB leaf %zu starts at %d", k, leaves[k]);
+    if (!r.ok) HG_FAIL(ctx, HG_ERR_ARG, "internal error: an RCB leaf does not start at a multiple of the tile size");
   }
   fh.n_tiles = (int32_t)((N + T - 1) / T);
   fh.iperm.resize(N);
@@ -284,17 +319,30 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
   std::vector<int32_t> ghost_entry(B);
   for (int64_t e = 0; e < B; ++e) ghost_entry[ctx->bch.ghost[e]] = (int32_t)e;
 
-  std::vector<int32_t> stamp(N, -1), loc(N, 0), fstamp(F, -1), floc(F, 0);
   fh.tile_desc.assign((size_t)fh.n_tiles * kTileDesc, 0);
   fh.cf_idx.assign((size_t)fh.n_tiles * T * NF, 0);
-  fh.halo.reserve(N / 4);
-  fh.face_lr.reserve(ctx->sumnf / 2 + ctx->sumnf / 8);
 
+  // Every tile is built independently (OpenMP) into its own TileOut with tile-local scratch -- a cell is "in the tile" iff
+  // its internal id lies in [c0, c1), halo cells and face ids are looked up in small sorted lists -- and the per-tile pieces
+  // are concatenated afterwards at offsets from a prefix sum: same tables as a serial pass, in a fraction of the time.
+  struct TileOut {
+    std::vector<int32_t> halo, bface_e;
+    std::vector<uint32_t> face_lr;
+    std::vector<double> nx, ny, len;
+    int32_t nh = 0, nint = 0, nf = 0, nfp = 0, max_local = 0;
+  };
+  std::vector<TileOut> outs(fh.n_tiles);
+  int first_err = HG_OK;
+  std::string first_msg;
+  auto tile_fail = [&](int code, const std::string& msg) {
+#pragma omp critical(hg_tile_fail)
+    if (first_err == HG_OK) { first_err = code; first_msg = msg; }
+  };
+  StageTimer tiles_timer("tile tables");
+#pragma omp parallel for schedule(dynamic, 16)
   for (int32_t t = 0; t < fh.n_tiles; ++t) {
+    TileOut& o = outs[t];
     const int32_t c0 = t * T, c1 = (int32_t)std::min<int64_t>(N, (int64_t)c0 + T), nc = c1 - c0, ncp = (nc + 1) & ~1;
-    int32_t nloc = ncp;
-    for (int32_t c = c0; c < c1; ++c) { stamp[c] = t; loc[c] = c - c0; }
-    const size_t face_base = fh.face_lr.size(), halo_base = fh.halo.size(), bf_base = fh.bface_e.size();
     // pass 0: the one-layer halo, in ascending internal order (so that the indirect loads of neighbouring lanes
     // fall into the same sectors wherever the neighbouring tiles' cells are contiguous)
     for (int32_t c = c0; c < c1; ++c) {
@@ -302,36 +350,46 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
       for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
         if (cf_nb[k] >= N) continue;
         const int32_t cn = fh.iperm[cf_nb[k]];
-        if (stamp[cn] != t) { stamp[cn] = t; fh.halo.push_back(cn); }
+        if (cn < c0 || cn >= c1) o.halo.push_back(cn);
       }
     }
-    std::sort(fh.halo.begin() + halo_base, fh.halo.end());
-    for (size_t q = halo_base; q < fh.halo.size(); ++q) loc[fh.halo[q]] = nloc++;
+    std::sort(o.halo.begin(), o.halo.end());
+    o.halo.erase(std::unique(o.halo.begin(), o.halo.end()), o.halo.end());
+    o.nh = (int32_t)o.halo.size();
+    const int32_t nloc = ncp + o.nh;
+    auto loc = [&](int32_t c) {   // tile-local index of an owned or halo cell
+      return (c >= c0 && c < c1) ? c - c0 : ncp + (int32_t)(std::lower_bound(o.halo.begin(), o.halo.begin() + o.nh, c) - o.halo.begin());
+    };
     // pass A: interior faces, found by the first owned cell (internal order) that sees them ...
     struct TF { int32_t lL, lR, fid; double nx, ny, len; };
     std::vector<TF> tf;
-    for (int32_t c = c0; c < c1; ++c) {
+    bool bad = false;
+    for (int32_t c = c0; c < c1 && !bad; ++c) {
       const int32_t r = fh.perm[c];
       for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
         if (cf_nb[k] >= N) continue;
         const int32_t fid = cf_face[k];
-        if (fstamp[fid] == t) continue;
         const int32_t rn = cf_nb[k], cn = fh.iperm[rn];
+        if (cn >= c0 && cn < c) continue;   // both cells owned: the face was taken when the smaller internal id saw it
         // canonical orientation: L = smaller REFERENCE id, normal taken from the L cell's own table
         int32_t lL, lR; double nx, ny;
         if (r < rn) {
-          lL = loc[c]; lR = loc[cn]; nx = cf_nx[k]; ny = cf_ny[k];
+          lL = loc(c); lR = loc(cn); nx = cf_nx[k]; ny = cf_ny[k];
         } else {
-          lL = loc[cn]; lR = loc[c];
+          lL = loc(cn); lR = loc(c);
           int32_t kk = -1;
           for (int32_t q = cf_ptr[rn]; q < cf_ptr[rn + 1]; ++q) if (cf_face[q] == fid) { kk = q; break; }
-          if (kk < 0 || cf_nb[kk] != r) HG_FAIL(ctx, HG_ERR_ARG, "face %d: cells %d and %d disagree on adjacency", fid, r, rn);
+          if (kk < 0 || cf_nb[kk] != r) {
+            tile_fail(HG_ERR_ARG, "face " + std::to_string(fid) + ": cells " + std::to_string(r) + " and " + std::to_string(rn) + " disagree on adjacency");
+            bad = true;
+            break;
+          }
           nx = cf_nx[kk]; ny = cf_ny[kk];
         }
-        fstamp[fid] = t;
         tf.push_back({lL, lR, fid, nx, ny, cf_len[k]});
       }
     }
+    if (bad) continue;
     // ... then ordered by (lR - lL, lL): faces with the same index offset are consecutive, so a warp's L reads
     // and R reads of the cell arrays in shared memory each hit consecutive addresses (no bank conflicts), and so
     // do the per-cell flux gathers of phase 3.  Evaluation order per cell is unaffected (bitwise same result).
@@ -403,41 +461,46 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
       }
       fprintf(stderr, "[hg] tile %d: %zu interior faces, half-warp gather wavefronts L %.2f R %.2f\n", t, tf.size(), wl / nb, wr / nb);
     }
+    std::vector<std::pair<int32_t, int32_t>> floc;   // (face id, tile-local face index), sorted by face id below
+    floc.reserve(tf.size() + 16);
     for (const TF& f : tf) {
-      floc[f.fid] = (int32_t)(fh.face_lr.size() - face_base);
-      fh.face_lr.push_back((uint32_t)f.lL | ((uint32_t)f.lR << 16));
-      fh.face_nx.push_back(f.nx); fh.face_ny.push_back(f.ny); fh.face_len.push_back(f.len);
+      floc.push_back({f.fid, (int32_t)o.face_lr.size()});
+      o.face_lr.push_back((uint32_t)f.lL | ((uint32_t)f.lR << 16));
+      o.nx.push_back(f.nx); o.ny.push_back(f.ny); o.len.push_back(f.len);
     }
-    const int32_t nint = (int32_t)(fh.face_lr.size() - face_base);
+    o.nint = (int32_t)o.face_lr.size();
     // pass B: boundary faces (their ghost state is evaluated on the fly from the owned internal cell)
     for (int32_t c = c0; c < c1; ++c) {
       const int32_t r = fh.perm[c];
       for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
         if (cf_nb[k] < N) continue;
-        const int32_t fid = cf_face[k];
-        fstamp[fid] = t; floc[fid] = (int32_t)(fh.face_lr.size() - face_base);
-        fh.face_lr.push_back((uint32_t)loc[c] | (0xFFFFu << 16));
-        fh.bface_e.push_back(ghost_entry[cf_nb[k] - N]);
-        fh.face_nx.push_back(cf_nx[k]); fh.face_ny.push_back(cf_ny[k]); fh.face_len.push_back(cf_len[k]);
+        floc.push_back({cf_face[k], (int32_t)o.face_lr.size()});
+        o.face_lr.push_back((uint32_t)(c - c0) | (0xFFFFu << 16));
+        o.bface_e.push_back(ghost_entry[cf_nb[k] - N]);
+        o.nx.push_back(cf_nx[k]); o.ny.push_back(cf_ny[k]); o.len.push_back(cf_len[k]);
       }
     }
-    const int32_t nf = (int32_t)(fh.face_lr.size() - face_base);
-    if (nloc >= 0xFFFF || nf >= 0x8000) HG_FAIL(ctx, HG_ERR_ARG, "tile %d too large (local cells %d, faces %d)", t, nloc, nf);
-    while ((fh.face_lr.size() - face_base) % 4) {  // zero-length padding faces keep the segments 16-byte sized
-      fh.face_lr.push_back(0u); fh.face_nx.push_back(1.0); fh.face_ny.push_back(0.0); fh.face_len.push_back(0.0);
+    o.nf = (int32_t)o.face_lr.size();
+    if (nloc >= 0xFFFF || o.nf >= 0x8000) {
+      tile_fail(HG_ERR_ARG, "tile " + std::to_string(t) + " too large (local cells " + std::to_string(nloc) + ", faces " + std::to_string(o.nf) + ")");
+      continue;
     }
-    const int32_t nfp = (int32_t)(fh.face_lr.size() - face_base);
+    while (o.face_lr.size() % 4) {  // zero-length padding faces keep the segments 16-byte sized
+      o.face_lr.push_back(0u); o.nx.push_back(1.0); o.ny.push_back(0.0); o.len.push_back(0.0);
+    }
+    o.nfp = (int32_t)o.face_lr.size();
+    std::sort(floc.begin(), floc.end());
     // pass C: NF slots per cell, local face ids in the reference's face order with the side bit; unused
     // slots point at the zero-flux slot nfp (adding 0.0 last leaves the left-to-right sum unchanged)
     uint16_t* slots = &fh.cf_idx[(size_t)t * T * NF];
-    for (int32_t l = 0; l < T * NF; ++l) slots[l] = (uint16_t)nfp;
+    for (int32_t l = 0; l < T * NF; ++l) slots[l] = (uint16_t)o.nfp;
     for (int32_t c = c0; c < c1; ++c) {
       const int32_t r = fh.perm[c];
       int32_t j = 0;
       for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k, ++j) {
-        const int32_t lf = floc[cf_face[k]];
-        const uint32_t lr = fh.face_lr[face_base + lf];
-        const bool on_right = (cf_nb[k] < N) && ((int32_t)(lr >> 16) == loc[c]);
+        const int32_t lf = std::lower_bound(floc.begin(), floc.end(), std::make_pair(cf_face[k], (int32_t)-1))->second;
+        const uint32_t lr = o.face_lr[lf];
+        const bool on_right = (cf_nb[k] < N) && ((int32_t)(lr >> 16) == c - c0);
         slots[(c - c0) * NF + j] = (uint16_t)(lf | (on_right ? 0x8000 : 0));
       }
     }
@@ -460,14 +523,39 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
         }
       fprintf(stderr, "[hg] tile %d: phase-3 slot gather wavefronts per half-warp %.2f\n", t, w / std::max(ng, 1));
     }
-    const int32_t nh = (int32_t)(fh.halo.size() - halo_base);
-    while ((fh.halo.size() - halo_base) % 4) fh.halo.push_back(0);
-    int32_t* d = &fh.tile_desc[(size_t)t * kTileDesc];
-    d[0] = c0; d[1] = nc; d[2] = (int32_t)halo_base; d[3] = nh; d[4] = (int32_t)face_base; d[5] = nf; d[6] = nfp;
-    d[7] = 0; d[8] = 0; d[9] = nint; d[10] = (int32_t)bf_base; d[11] = 0;
-    fh.max_local = std::max(fh.max_local, ncp + nh);
-    fh.max_faces = std::max(fh.max_faces, nfp);
-    fh.max_halo = std::max(fh.max_halo, nh);
+    while (o.halo.size() % 4) o.halo.push_back(0);
+    o.max_local = ncp + o.nh;
+  }
+  if (first_err != HG_OK) { ctx->err = first_msg; return first_err; }
+  // ---- concatenate at prefix-sum offsets
+  {
+    std::vector<size_t> fb(fh.n_tiles + 1, 0), hb(fh.n_tiles + 1, 0), bb(fh.n_tiles + 1, 0);
+    for (int32_t t = 0; t < fh.n_tiles; ++t) {
+      fb[t + 1] = fb[t] + outs[t].face_lr.size(); hb[t + 1] = hb[t] + outs[t].halo.size(); bb[t + 1] = bb[t] + outs[t].bface_e.size();
+    }
+    fh.face_lr.resize(fb.back()); fh.face_nx.resize(fb.back()); fh.face_ny.resize(fb.back()); fh.face_len.resize(fb.back());
+    fh.halo.resize(hb.back()); fh.bface_e.resize(bb.back());
+    if (fb.back() >= ((size_t)1 << 31) || hb.back() >= ((size_t)1 << 31)) HG_FAIL(ctx, HG_ERR_ARG, "tile tables exceed 32-bit offsets");
+#pragma omp parallel for schedule(static)
+    for (int32_t t = 0; t < fh.n_tiles; ++t) {
+      TileOut& o = outs[t];
+      std::copy(o.face_lr.begin(), o.face_lr.end(), fh.face_lr.begin() + fb[t]);
+      std::copy(o.nx.begin(), o.nx.end(), fh.face_nx.begin() + fb[t]);
+      std::copy(o.ny.begin(), o.ny.end(), fh.face_ny.begin() + fb[t]);
+      std::copy(o.len.begin(), o.len.end(), fh.face_len.begin() + fb[t]);
+      std::copy(o.halo.begin(), o.halo.end(), fh.halo.begin() + hb[t]);
+      std::copy(o.bface_e.begin(), o.bface_e.end(), fh.bface_e.begin() + bb[t]);
+      const int32_t c0 = t * T, nc = (int32_t)std::min<int64_t>(N, (int64_t)c0 + T) - c0;
+      int32_t* d = &fh.tile_desc[(size_t)t * kTileDesc];
+      d[0] = c0; d[1] = nc; d[2] = (int32_t)hb[t]; d[3] = o.nh; d[4] = (int32_t)fb[t]; d[5] = o.nf; d[6] = o.nfp;
+      d[7] = 0; d[8] = 0; d[9] = o.nint; d[10] = (int32_t)bb[t]; d[11] = 0;
+      TileOut().halo.swap(o.halo);   // (the locals go out of scope with `outs`; nothing else to free early)
+    }
+    for (int32_t t = 0; t < fh.n_tiles; ++t) {
+      fh.max_local = std::max(fh.max_local, outs[t].max_local);
+      fh.max_faces = std::max(fh.max_faces, outs[t].nfp);
+      fh.max_halo = std::max(fh.max_halo, outs[t].nh);
+    }
   }
   fh.max_local = (fh.max_local + 1) & ~1;
   // ---- multi-GPU overlap: a tile belongs to the band if one of its boundary faces is a halo face

@@ -43,7 +43,10 @@ struct VjpArgs {
   double *Qbar, *nbar, *s0bar;          // [3Ns], [Ns], [2Ns]
   double *ent_c, *ent_n, *ent_z;        // per boundary entry: inlet coef adjoint share, n adjoint, zb adjoint
   CommWait cw;                          // library-owned halo exchange: CTAs >= cw.from wait for the neighbours' pushes
+  const int32_t* matid;                 // fused Manning-zone reduction (active parameter ManningN, <= kZoneFused zones):
+  double* zone_part;                    // [n_tiles][kZoneFused] per-tile sums of nbar by zone; NULL = off
 };
+constexpr int kZoneFused = 8;
 
 struct Adj {
   double xi, h, u, v, s, P;   // adjoints of the staged per-cell variables (hu = h*u, hv = h*v folded in)
@@ -253,6 +256,7 @@ struct __align__(16) VjpSmem {
   double area[T], mann[T], sx[T], sy[T];
   uint32_t lr[MF];
   uint16_t cf[T * NF];
+  double zs[16][kZoneFused];                              // per-warp zone sums of nbar (fused Manning-zone reduction)
 };
 
 // adjoints of one side's staged variables (xi, h, u, v, s, P) -> adjoints of its raw state (xi, q_x, q_y): the
@@ -318,7 +322,8 @@ __device__ __forceinline__ void vjp_boundary_face(Smem& sm, const VjpArgs& a, in
     if (ty == BC_INLETQ) {
       wet = L.h > hs ? 1.0 : 0.0;
       mannc = sm.mann[lL];
-      vn = a.inlet_coef[kgrp] * a.bc_l23[e] / mannc;
+      pdl_wait();                                // coef comes from k_inlet_coef, which may still be running (PDL)
+      vn = __ldcg(a.inlet_coef + kgrp) * a.bc_l23[e] / mannc;
       R.h = L.h; R.hu = -L.h * vn * bnx * wet; R.hv = -L.h * vn * bny * wet;
     } else if (ty == BC_EXITH) {
       const double hg = a.wse[kgrp] - zbl;
@@ -628,6 +633,22 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     o.s0y = wet ? g * xi * lam2 : 0.0;
     return o;
   };
+  // fused Manning-zone reduction: the warp adds up nbar zone by zone (zones are spatially contiguous: almost always one
+  // pass), lane 0 accumulates into its warp's row; fixed order, no atomics
+  const int warp = tid >> 5, lane = tid & 31;
+  auto zone_add = [&](int32_t z, double v, bool valid) {
+    unsigned rem = __ballot_sync(0xffffffffu, valid);
+    while (rem) {
+      const int leader = __ffs(rem) - 1;
+      const int32_t zl = __shfl_sync(0xffffffffu, z, leader);
+      const bool mine = valid && z == zl;
+      double sacc = mine ? v : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+      if (lane == 0) sm.zs[warp][zl] += sacc;
+      rem &= ~__ballot_sync(0xffffffffu, mine);
+    }
+  };
   auto cell_store = [&](int32_t l, const CellOut& o) {
     const int32_t gi = c0 + l;
     a.Qbar[gi] = o.xib;
@@ -636,16 +657,42 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     a.nbar[gi] = o.nb;
     if (a.want_s0) { a.s0bar[gi] = o.s0x; a.s0bar[Ns + gi] = o.s0y; }
   };
+  const bool zones = a.zone_part != nullptr;
+  if (zones && lane < kZoneFused) sm.zs[warp][lane] = 0.0;   // own row of the warp: no barrier needed
+  if (zones) __syncwarp();
   if constexpr (FPT == 1) {
-    for (int32_t l = tid; l < nc; l += kThreads) cell_store(l, cell_adj(l));
+    for (int32_t l0 = 0; l0 < nc; l0 += kThreads) {          // whole warps take every trip (the zone sums shuffle)
+      const int32_t l = l0 + tid;
+      const bool valid = l < nc;
+      CellOut o = {0, 0, 0, 0, 0, 0};
+      if (valid) { o = cell_adj(l); cell_store(l, o); }
+      if (zones) zone_add(valid ? __ldg(a.matid + c0 + l) : 0, o.nb, valid);
+    }
   } else {
-    for (int32_t l = tid; l < nc; l += 2 * kThreads) {
-      if (l + kThreads < nc) {
-        const CellOut o1 = cell_adj(l), o2 = cell_adj(l + kThreads);
-        cell_store(l, o1); cell_store(l + kThreads, o2);
-      } else {
-        cell_store(l, cell_adj(l));
+    for (int32_t l0 = 0; l0 < nc; l0 += 2 * kThreads) {
+      const int32_t l = l0 + tid, l2 = l + kThreads;
+      const bool v1 = l < nc, v2 = l2 < nc;
+      CellOut o1 = {0, 0, 0, 0, 0, 0}, o2 = {0, 0, 0, 0, 0, 0};
+      if (v2) {
+        o1 = cell_adj(l); o2 = cell_adj(l2);
+        cell_store(l, o1); cell_store(l2, o2);
+      } else if (v1) {
+        o1 = cell_adj(l);
+        cell_store(l, o1);
       }
+      if (zones) {
+        zone_add(v1 ? __ldg(a.matid + c0 + l) : 0, o1.nb, v1);
+        zone_add(v2 ? __ldg(a.matid + c0 + l2) : 0, o2.nb, v2);
+      }
+    }
+  }
+  if (zones) {
+    __syncthreads();
+    if (tid < kZoneFused) {
+      double acc = 0.0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) acc += sm.zs[w][tid];
+      a.zone_part[(size_t)t * kZoneFused + tid] = acc;
     }
   }
 }
@@ -690,7 +737,8 @@ __global__ void __launch_bounds__(256) k_inlet_adj(Consts c, const int32_t* inle
 // One thread per boundary-adjacent cell: add its entries' contributions in fixed order (deterministic).
 __global__ void k_bc_scatter(int32_t nbcell, const int32_t* __restrict__ bcell, const int32_t* __restrict__ bcell_ptr,
                              const int32_t* __restrict__ bcell_ent, const int32_t* __restrict__ bc_type,
-                             const double* __restrict__ ent_h, const double* __restrict__ ent_n, double* Qbar, double* nbar) {
+                             const double* __restrict__ ent_h, const double* __restrict__ ent_n, double* Qbar, double* nbar,
+                             double* __restrict__ nbcorr) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nbcell) return;
   const int32_t c = bcell[i];
@@ -701,6 +749,7 @@ __global__ void k_bc_scatter(int32_t nbcell, const int32_t* __restrict__ bcell, 
   }
   Qbar[c] += hb;   // inlet cells that receive this are wet, hence unclamped: xi_bar += h_bar
   nbar[c] += nb;
+  nbcorr[i] = nb;  // what the fused zone sums of the tile kernel have not seen
 }
 
 // pbar_z = sum_{cells of zone z} nbar  (process_ManningN_2D.jl:88 transposed): two fixed-shape stages
@@ -723,43 +772,16 @@ __global__ void __launch_bounds__(kZoneBlock) k_zone_partial(int32_t N, int32_t 
     __syncthreads();
   }
 }
-// few zones (the reference's cases have 1-6 Manning zones): ONE pass over the chunk with a register accumulator per zone,
-// then a fixed-shape reduction per zone (warp shuffles, then the 8 warp sums in order) -- 12 B per cell, bandwidth-bound
-template <int NZ>
-__global__ void __launch_bounds__(kZoneBlock) k_zone_partial_few(int32_t N, int32_t n_mat, const int32_t* __restrict__ matid,
-                                                                 const double* __restrict__ nbar, double* __restrict__ part) {
-  __shared__ double ws[kZoneBlock / 32][NZ];
-  const int32_t b0 = blockIdx.x * kZoneChunk;
-  double acc[NZ];
-#pragma unroll
-  for (int z = 0; z < NZ; ++z) acc[z] = 0.0;
-  for (int32_t i = b0 + threadIdx.x; i < min(N, b0 + kZoneChunk); i += kZoneBlock) {
-    const int32_t m = matid[i];
-    const double v = nbar[i];
-#pragma unroll
-    for (int z = 0; z < NZ; ++z) acc[z] += (m == z) ? v : 0.0;
-  }
-#pragma unroll
-  for (int z = 0; z < NZ; ++z) {
-    double v = acc[z];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5][z] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < n_mat) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < kZoneBlock / 32; ++w) v += ws[w][threadIdx.x];
-    part[(size_t)blockIdx.x * n_mat + threadIdx.x] = v;
-  }
-}
 // one CTA per zone: 256 strided sums over the blocks' partials in block order, then a fixed tree
-__global__ void __launch_bounds__(256) k_zone_final(int32_t nblocks, int32_t n_mat, const double* __restrict__ part, double* __restrict__ pbar) {
+// (+ the inlet-coupling corrections of the boundary-adjacent cells when the partials come from the tile kernel)
+__global__ void __launch_bounds__(256) k_zone_final(int32_t nblocks, int32_t stride, const double* __restrict__ part, double* __restrict__ pbar,
+                                                    int32_t nbcell, const int32_t* __restrict__ bcell, const int32_t* __restrict__ matid,
+                                                    const double* __restrict__ nbcorr) {
   __shared__ double red[256];
   const int32_t z = blockIdx.x;
   double acc = 0.0;
-  for (int32_t b = threadIdx.x; b < nblocks; b += 256) acc += part[(size_t)b * n_mat + z];
+  for (int32_t b = threadIdx.x; b < nblocks; b += 256) acc += part[(size_t)b * stride + z];
+  for (int32_t i = threadIdx.x; i < nbcell; i += 256) acc += (matid[bcell[i]] == z) ? nbcorr[i] : 0.0;
   red[threadIdx.x] = acc;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -870,7 +892,7 @@ int fused_vjp_prepare(hg_ctx* ctx, int cfg_id) {
 // The tile kernel over the tiles tile_order[tile_base .. tile_base + n_run) (tile_order NULL: all tiles, identity).
 // The inlet coefficients must be current (fused_inlet_coef).
 int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar, const int32_t* tile_order,
-                    int32_t tile_base, int32_t n_run, bool use_comm) {
+                    int32_t tile_base, int32_t n_run, bool use_comm, bool pdl) {
   FusedDev& d = ctx->fd;
   const FusedHost& fh = ctx->fh;
   if (n_run == 0) return HG_OK;
@@ -885,6 +907,14 @@ int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_
   a.halo_off = d.halo_off.p; a.halo_cnt = d.halo_cnt.p; a.halo_recv = d.halo_recv.p;
   a.wse = d.wse.p; a.Q = d_Q; a.lam = d_lam; a.Qbar = d_Qbar; a.nbar = d.nbar.p; a.s0bar = d.s0bar.p;
   a.ent_c = d.ent_c.p; a.ent_n = d.ent_n.p; a.ent_z = d.ent_z.p;
+  a.matid = nullptr; a.zone_part = nullptr;
+  if (ctx->active == HG_PARAM_MANNING && ctx->n_mat <= kZoneFused && d.matid.p) {   // zone sums of nbar inside the tile kernel
+    if (d.zone_part.n < (size_t)fh.n_tiles * kZoneFused && d.zone_part.alloc((size_t)fh.n_tiles * kZoneFused) != cudaSuccess) {
+      ctx->err = "cudaMalloc(zone_part)";
+      return HG_ERR_CUDA;
+    }
+    a.matid = d.matid.p; a.zone_part = d.zone_part.p;
+  }
   a.tile_order = tile_order; a.tile_base = tile_base;
   if (use_comm) {   // library-owned exchange (see launch_rhs)
     const hg_comm* cm = ctx->comm;
@@ -900,7 +930,13 @@ int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_
     const int r3 = ctx->opt.reserved[3];
     a.prefetch = r3 < 0 ? 0 : (r3 > 0 ? r3 : ctx->n_sm * kk.ctas_per_sm);
     void* kargs[] = {(void*)&a};
-    const cudaError_t le = cudaLaunchKernel(kk.fn, dim3(grid), dim3((unsigned)kk.threads), kargs, (size_t)kk.smem, ctx->stream);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3((unsigned)kk.threads); lc.dynamicSmemBytes = (size_t)kk.smem; lc.stream = ctx->stream;
+    cudaLaunchAttribute pdl_attr[1];   // programmatic dependent of the k_inlet_coef launched just before (hg_device.cuh)
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = pdl_attr; lc.numAttrs = pdl ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelExC(&lc, kk.fn, kargs);
     if (le != cudaSuccess) { ctx->err = std::string("fused_vjp launch: ") + cudaGetErrorString(le); return HG_ERR_CUDA; }
   }
   ctx->launches++;
@@ -921,23 +957,28 @@ int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar) {
     if (ctx->nbcell > 0) {
       k_bc_scatter<<<(unsigned)((ctx->nbcell + th - 1) / th), th, 0, ctx->stream>>>((int32_t)ctx->nbcell, d.bcell.p, d.bcell_ptr.p,
                                                                                  d.bcell_ent.p, d.bc_type.p, d.ent_h.p,
-                                                                                 d.ent_n.p, d_Qbar, d.nbar.p);
+                                                                                 d.ent_n.p, d_Qbar, d.nbar.p, d.nbcorr.p);
       ctx->launches++;
     }
   }
   // ---- parameter adjoints
   if (ctx->active == HG_PARAM_MANNING) {
-    const int nblocks = (int)((ctx->N + kZoneChunk - 1) / kZoneChunk);
-    if (d.zone_part.n < (size_t)nblocks * ctx->n_mat) {
-      if (d.zone_part.alloc((size_t)nblocks * ctx->n_mat) != cudaSuccess) { ctx->err = "cudaMalloc(zone_part)"; return HG_ERR_CUDA; }
-    }
-    if (ctx->n_mat <= 8)
-      k_zone_partial_few<8><<<nblocks, kZoneBlock, 0, ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid.p, d.nbar.p, d.zone_part.p);
-    else
+    const bool corr = ctx->n_inletq > 0 && ctx->nbcell > 0;
+    if (ctx->n_mat <= kZoneFused && d.matid.p) {
+      // the tile kernel left per-tile zone sums; add the inlet-coupling corrections of the boundary-adjacent cells
+      k_zone_final<<<(unsigned)ctx->n_mat, 256, 0, ctx->stream>>>(fh.n_tiles, kZoneFused, d.zone_part.p, d.pbar.p, corr ? (int32_t)ctx->nbcell : 0,
+                                                                  d.bcell.p, d.matid.p, d.nbcorr.p);
+      ctx->launches++;
+    } else {
+      const int nblocks = (int)((ctx->N + kZoneChunk - 1) / kZoneChunk);
+      if (d.zone_part.n < (size_t)nblocks * ctx->n_mat) {
+        if (d.zone_part.alloc((size_t)nblocks * ctx->n_mat) != cudaSuccess) { ctx->err = "cudaMalloc(zone_part)"; return HG_ERR_CUDA; }
+      }
       k_zone_partial<<<nblocks, kZoneBlock, kZoneBlock * sizeof(double), ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid.p,
                                                                                         d.nbar.p, d.zone_part.p);
-    k_zone_final<<<(unsigned)ctx->n_mat, 256, 0, ctx->stream>>>(nblocks, (int32_t)ctx->n_mat, d.zone_part.p, d.pbar.p);
-    ctx->launches += 2;
+      k_zone_final<<<(unsigned)ctx->n_mat, 256, 0, ctx->stream>>>(nblocks, (int32_t)ctx->n_mat, d.zone_part.p, d.pbar.p, 0, nullptr, nullptr, nullptr);
+      ctx->launches += 2;
+    }
   } else if (ctx->active == HG_PARAM_ZB) {
     PlainDev& p = ctx->pd;
     k_zb_bar<<<(unsigned)((ctx->N + th - 1) / th), th, 0, ctx->stream>>>((int32_t)ctx->N, fh.Ns, d.iperm.p, p.cf_ptr.p, p.cf_nb.p,
@@ -968,7 +1009,6 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
     const int rc0 = ude_eval_n(ctx, d_Q);
     if (rc0 != HG_OK) return rc0;
   }
-  if (ctx->n_inletq > 0) fused_inlet_coef(ctx, d_Q);
   bool use_comm = false;
   if (hg_comm_ready(ctx)) {   // the adjoint of a cut face needs the remote cell's state AND cotangent
     hg_comm* cm = ctx->comm;
@@ -982,7 +1022,9 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
     cm->pushed = false;
     use_comm = true;
   }
-  const int rc = fused_vjp_tiles(ctx, cfg_id, d_Q, d_lam, d_Qbar, nullptr, 0, -1, use_comm);
+  const bool pdl = ctx->n_inletq > 0;   // the conveyance sum last: the tile kernel is its programmatic dependent
+  if (pdl) fused_inlet_coef(ctx, d_Q);
+  const int rc = fused_vjp_tiles(ctx, cfg_id, d_Q, d_lam, d_Qbar, nullptr, 0, -1, use_comm, pdl);
   return rc != HG_OK ? rc : fused_vjp_finish(ctx, d_Q, d_Qbar);
 }
 
