@@ -4,11 +4,17 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells-m M]
 
 A "step" is one pass of the hot path over the whole mesh: one fused RHS evaluation (swe_2d_rhs,
-semi_discretize_swe_2D.jl:18-277) of the resident state -- plus, once the adjoint kernel is enabled
-(--vjp), one VJP of the same call.  Workload at every N: config C3, the synthetic ~16M-cell
-meandering river per GPU (6 Manning zones, inlet-Q / exit-H / walls), i.e. WEAK scaling: rank r owns
-slab r of a river N times as long.  All inputs (5.6 GB of state + mesh tables) are far larger than the
-126 MB L2, so no flush is needed between iterations (config.l2 says so).
+semi_discretize_swe_2D.jl:18-277) of the resident state plus one hand-written VJP of the same call with the Manning
+zone values as the active parameter (BASELINE config C4: Qbar AND pbar are inside the step).  Workload at every N:
+config C3, the synthetic ~16M-cell meandering river per GPU (6 Manning zones, inlet-Q / exit-H / walls), i.e. WEAK
+scaling: rank r owns slab r of a river N times as long.  All inputs (5.6 GB of state + mesh tables) are far larger
+than the 126 MB L2, so no flush is needed between iterations (config.l2 says so).  At N > 1 the halo moves through the
+library's own transport (hg_comm.cu: peer stores over NVLink, consumed inside the one tile-kernel launch);
+--transport nccl selects the round-1 pack -> NCCL send/recv -> kernel sequence for comparison.
+
+Extra keys (same JSON line): `sustained` (seconds of back-to-back steps, with roofline fractions), `c2` (1M-cell dam
+break, fused Euler steps) and `c5` (128-member parameter ensemble on a 1M-cell mesh) at N = 1; `strong` (the 16M-cell
+river split over the N GPUs) at N > 1.
 
 Printed JSON keys follow the driver contract; see DESIGN.md section "Measurement" for the arithmetic:
   value      cell-updates/s, inputs resident in HBM, CUDA-event time of K steps (max over ranks)
@@ -94,6 +100,10 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
+TRAFFIC_SOURCE = ("static: dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture of this kernel on the 16M-cell "
+                  "river (profiles/traffic.json), scaled per cell -- not measured in this run")
+
+
 def measured_traffic(kernel, N):
     """DRAM bytes per launch from the committed `ncu --set full` capture of the same kernel (profiles/), scaled per cell."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -106,6 +116,13 @@ def measured_traffic(kernel, N):
 def algorithmic_bytes(N, F, sum_nf):
     """compulsory traffic with every array touched once, int32 indices, fp64 data."""
     return 100 * N + 32 * F + 4 * sum_nf
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class CpuSample:
@@ -121,7 +138,8 @@ class CpuSample:
         flat, self.Q0 = S.river(self.ni, 1000, seed=seed)
         self.o = Oracle(flat)
         self.n = flat["n_cells"]
-        self.threads = threads or self.o.max_threads()
+        # torchrun exports OMP_NUM_THREADS=1 to every rank: ask the OS which cores this process may run on instead
+        self.threads = threads or host_threads()
         self.v = np.ones_like(self.Q0)
         self.o.rhs(self.Q0, nthreads=self.threads)          # first touch (both passes: the CPU side is timed warm)
         self.o.jvp(self.Q0, self.v, nthreads=self.threads)
@@ -185,6 +203,43 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def side_configs(hg, S, device, peak):
+    """BASELINE configs C2 and C5 on one GPU (extra keys of the N = 1 line).  Small meshes: built, timed and freed."""
+    out = {}
+    # ---- C2: 1M-cell dam break, forward run with the customized Euler stepper fused into the RHS kernel
+    flat, Q0 = S.dam_break(953)
+    N, F, sn = flat["n_cells"], flat["n_faces"], int(flat["cell_nfaces"].sum())
+    ctx = hg.Context(flat, device=device)
+    ctx.set_state(Q0)
+    dt = 1e-4
+    ctx.time_rhs(50, True, dt)
+    ms = min(ctx.time_rhs(200, True, dt) / 200 for _ in range(3))
+    ab = algorithmic_bytes(N, F, sn)
+    out["c2"] = {"workload": f"C2 synthetic {N / 1e6:.2f}M-cell unstructured dam break (mixed tri/quad, walls), forward run: fused RHS + Euler update per step",
+                 "cells": N, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "value": N / (ms * 1e-3), "unit": UNIT,
+                 "roofline_frac": ab / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": ab,
+                 "l2": f"working set {ab / 1e6:.0f} MB vs 126 MB L2: partly L2-resident, no flush between steps (steady state of a forward run)"}
+    del ctx
+    # ---- C5: parameter ensemble, 128 members per GPU (1024 over 8 GPUs: members shard with no communication)
+    flat, Q0 = S.river(909, 1000)
+    N = flat["n_cells"]
+    M = 128
+    ctx = hg.Context(flat, device=device)
+    ctx.ensemble_alloc(M, per_member_manning=True)
+    rng = np.random.default_rng(1234)
+    for m in range(M):
+        ctx.ensemble_set_member(m, Q0, S.RIVER_N_ZONES[:flat["n_mat"]] * (1 + 0.2 * rng.uniform(-1, 1, flat["n_mat"])), "ManningN")
+    ctx.time_ensemble(3, dt)
+    ms = min(ctx.time_ensemble(10, dt) / 10 for _ in range(2))
+    bpmc = (48.0 * M + 132.0) / M          # SURVEY 8d: state in + out per member, mesh / bed tables once per tile
+    out["c5"] = {"workload": f"C5 ensemble of {M} Manning-n parameter sets on a {N / 1e6:.2f}M-cell river (per GPU; x8 GPUs = 1024 members), fused Euler step of all members per launch",
+                 "members": M, "cells": N, "ms_per_step": ms, "value": M * N / (ms * 1e-3), "unit": "member-cell-updates/s",
+                 "bytes_per_member_cell": bpmc, "roofline_frac": bpmc * M * N / (ms * 1e-3) / 1e9 / peak,
+                 "note": "bound by the fp64 / shared-memory work of the tile kernel, not by HBM (the mesh blocks of a tile are shared by the members through L2)"}
+    del ctx
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,11 +250,14 @@ def main():
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the fused kernel (tuning)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--overlap", action="store_true", help="multi-GPU: run the tiles without halo faces while the halo is exchanged on a second stream "
-                    "(hg_*_resident_phase).  Measured slower at 16M cells/GPU (exchange ~25 us; two launches + NCCL beside the kernel cost more): off by default")
+    ap.add_argument("--transport", default="ipc", choices=["ipc", "nccl"],
+                    help="multi-GPU halo transport: ipc = the library's own peer stores over NVLink (hg_comm.cu), nccl = pack -> NCCL send/recv -> kernel")
+    ap.add_argument("--overlap", action="store_true", help="nccl transport only: run the tiles without halo faces while the halo is exchanged on a second stream "
+                    "(hg_*_resident_phase); measured slower than the serial sequence in round 1")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--sustained-s", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` key (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs: the launch list then holds the timed region only)")
+    ap.add_argument("--no-side", action="store_true", help="skip the c2 / c5 / strong extra keys")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -228,85 +286,28 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
 
-    # ---- workload: slab `rank` of a river `world` times as long (weak scaling).  The slab decomposition is what
-    # recursive coordinate bisection yields for this elongated domain; each rank generates its slab plus one
-    # column on each cut side and extracts its local mesh (owned cells + halo boundaries) with the general
-    # partitioner code (hydrograd.jl_b200/parallel.py).
     from hydrograd_jl_b200 import parallel as PAR
-    ni = int(args.cells_m * 1e6 / 1.1 / 1000)
-    t0 = time.time()
-    if world == 1:
-        flat, Q0 = S.river(ni, 1000)
-        ranks = []
-    else:
-        lo = rank * ni - (1 if rank > 0 else 0)
-        hi = (rank + 1) * ni + (1 if rank < world - 1 else 0)
-        gflat, gQ = S.river(hi - lo, 1000, i0=lo, ni_total=world * ni)
-        # owner of every cell of the extended slab, from the stream-wise column of its centroid's quad
-        col = S.cell_columns(gflat, hi - lo, 1000)
-        part = np.full(gflat["n_cells"], rank, dtype=np.int32)
-        if rank > 0:
-            part[col == 0] = rank - 1
-        if rank < world - 1:
-            part[col == (hi - lo - 1)] = rank + 1
-        flat, info = PAR.extract_local(gflat, part, rank, gQ)
-        Q0, ranks = info["Q"], info["neighbors"]
-        del gflat, gQ
-    N, F = flat["n_cells"], flat["n_faces"]
-    log(f"[rank {rank}] mesh: N={N} F={F} ({time.time() - t0:.1f}s)")
-    t0 = time.time()
-    ctx = hg.Context(flat, device=local, tile_cells=args.tile, threads=args.threads)
-    st = ctx.mesh_stats()
-    log(f"[rank {rank}] context: {st} ({time.time() - t0:.1f}s)")
-    ctx.set_state(Q0)
-    rng = np.random.default_rng(99 + rank)
-    ctx.set_lambda(rng.standard_normal(3 * N))
-    # one explicit (non-default) stream for everything: pack kernel, NCCL transfers, RHS / VJP kernels, timing events
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    ex = PAR.attach_exchanger(ctx, ranks) if world > 1 else None
+    peak, peak_src = measured_peak()
+    p_zones = S.RIVER_N_ZONES.copy()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # multi-GPU step: pack the halo, exchange it on a second stream (NCCL send/recv over NVLink) WHILE the tiles without halo
-    # faces run, then the band of tiles with halo faces once the received block is complete
-    comm = torch.cuda.Stream() if ex is not None else None
-    ev_pack, ev_recv = torch.cuda.Event(), torch.cuda.Event()
+    def allmax(x):
+        if dist is None:
+            return x
+        tt = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
-    def overlapped(pack_lambda, run):
-        ctx.halo_pack(pack_lambda)
-        ev_pack.record(stream)
-        comm.wait_event(ev_pack)
-        with torch.cuda.stream(comm):
-            ex.exchange(pack_lambda)
-            ev_recv.record(comm)
-        run(1)
-        stream.wait_event(ev_recv)
-        run(2)
-
-    def rhs_step():
-        if ex is None:
-            ctx.rhs_resident()
-        elif not args.overlap:
-            ctx.halo_pack(False)
-            ex.exchange(False)
-            ctx.rhs_resident()
-        else:
-            overlapped(False, ctx.rhs_resident)
-
-    def vjp_step():
-        if ex is None:
-            ctx.vjp_resident()
-        elif not args.overlap:
-            ctx.halo_pack(True)
-            ex.exchange(True)
-            ctx.vjp_resident()
-        else:
-            overlapped(True, ctx.vjp_resident)
+    def allsum(x):
+        if dist is None:
+            return x
+        tt = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt)
+        return float(tt.item())
 
     def timed(fn, n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,12 +318,102 @@ def main():
         e1.synchronize()
         return e0.elapsed_time(e1)
 
-    def allmax(x):
-        if dist is None:
-            return x
-        tt = torch.tensor([x], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+    # one explicit (non-default) stream for everything: halo push / pack kernel, NCCL transfers, RHS / VJP kernels, timing events
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+
+    class Slab:
+        """Slab `rank` of a river of world * ni columns: mesh, context, halo transport, step functions."""
+
+        def __init__(self, ni):
+            t0 = time.time()
+            if world == 1:
+                flat, Q0 = S.river(ni, 1000)
+                info = {"neighbors": [], "counts": []}
+            else:
+                # the slab decomposition is what recursive coordinate bisection yields for this elongated domain; each rank
+                # generates its slab plus one column on each cut side and extracts its local mesh (owned cells + halo
+                # boundaries) with the general partitioner code (hydrograd.jl_b200/parallel.py)
+                lo = rank * ni - (1 if rank > 0 else 0)
+                hi = (rank + 1) * ni + (1 if rank < world - 1 else 0)
+                gflat, gQ = S.river(hi - lo, 1000, i0=lo, ni_total=world * ni)
+                col = S.cell_columns(gflat, hi - lo, 1000)
+                part = np.full(gflat["n_cells"], rank, dtype=np.int32)
+                if rank > 0:
+                    part[col == 0] = rank - 1
+                if rank < world - 1:
+                    part[col == (hi - lo - 1)] = rank + 1
+                flat, info = PAR.extract_local(gflat, part, rank, gQ)
+                Q0 = info["Q"]
+                del gflat, gQ
+            self.N, self.F, self.Q0, self.info = flat["n_cells"], flat["n_faces"], Q0, info
+            log(f"[rank {rank}] mesh: N={self.N} F={self.F} ({time.time() - t0:.1f}s)")
+            t0 = time.time()
+            self.ctx = ctx = hg.Context(flat, device=local, tile_cells=args.tile, threads=args.threads)
+            self.st = ctx.mesh_stats()
+            self.create_s = time.time() - t0
+            log(f"[rank {rank}] context: {self.st} ({self.create_s:.1f}s)")
+            ctx.set_state(Q0)
+            ctx.set_lambda(np.random.default_rng(99 + rank).standard_normal(3 * self.N))
+            ctx.set_params(p_zones[:flat["n_mat"]], "ManningN")     # C4: the Manning-n gradient is part of the VJP step
+            ctx.set_stream(stream.cuda_stream)
+            self.transport, self.ex = "none", None
+            if world > 1:
+                self.transport = args.transport
+                if self.transport == "ipc":
+                    ok = 1.0
+                    try:
+                        PAR.connect_ranks(ctx, info)
+                    except Exception as e:  # noqa: BLE001 -- e.g. CUDA IPC not permitted in this container
+                        log(f"[rank {rank}] library-owned transport unavailable ({e}); falling back to NCCL send/recv")
+                        ok = 0.0
+                    if allsum(ok) < world:      # all ranks or none
+                        if ok:
+                            ctx.comm_disconnect()
+                        self.transport = "nccl (ipc unavailable)"
+                if self.transport != "ipc":
+                    self.ex = PAR.attach_exchanger(ctx, info["neighbors"])
+                    self.comm, self.ev_pack, self.ev_recv = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
+
+        def _overlapped(self, pack_lambda, run):
+            self.ctx.halo_pack(pack_lambda)
+            self.ev_pack.record(stream)
+            self.comm.wait_event(self.ev_pack)
+            with torch.cuda.stream(self.comm):
+                self.ex.exchange(pack_lambda)
+                self.ev_recv.record(self.comm)
+            run(1)
+            stream.wait_event(self.ev_recv)
+            run(2)
+
+        def rhs_step(self):
+            ctx = self.ctx
+            if self.ex is None:
+                ctx.rhs_resident()            # multi-rank: the halo push is part of the call (auto exchange)
+            elif not args.overlap:
+                ctx.halo_pack(False); self.ex.exchange(False); ctx.rhs_resident()
+            else:
+                self._overlapped(False, ctx.rhs_resident)
+
+        def vjp_step(self):
+            ctx = self.ctx
+            if self.ex is None:
+                ctx.vjp_resident()
+            elif not args.overlap:
+                ctx.halo_pack(True); self.ex.exchange(True); ctx.vjp_resident()
+            else:
+                self._overlapped(True, ctx.vjp_resident)
+
+        def close(self):
+            barrier()
+            if self.transport == "ipc":
+                self.ctx.comm_disconnect()
+            self.ctx.close()
+
+    ni = int(args.cells_m * 1e6 / 1.1 / 1000)
+    sl = Slab(ni)
+    ctx, N, F, st, Q0 = sl.ctx, sl.N, sl.F, sl.st, sl.Q0
+    rhs_step, vjp_step = sl.rhs_step, sl.vjp_step
 
     # ---- warm-up, then exactly K timed steps; CUDA events on the stream every kernel and transfer is ordered on
     W = max(args.warmup, 3)
@@ -339,16 +430,14 @@ def main():
     clocks = sampler.stop()
     ctx.sync()
     ms, ms_vjp = allmax(ms), allmax(ms_vjp)
-    if dist is not None:
-        tn = torch.tensor([N], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tn)
-        N_total = int(tn.item())
-    else:
-        N_total = N
+    N_total = int(allsum(float(N)))
     ms_rhs_step = ms / args.steps
     ms_vjp_step = ms_vjp / args.steps
     ms_per_step = ms_rhs_step + ms_vjp_step
     value = N_total / (ms_per_step * 1e-3)
+
+    abytes = algorithmic_bytes(N, F, st["sum_cell_faces"])
+    vbytes = abytes + 32 * N          # SURVEY 8(d): RHS inputs re-read + lambda (24 B) + Qbar (24 B) + nbar (8 B) - dQ (24 B)
 
     # ---- sustained regime (single GPU): ~2 s of alternating steps back to back.  The K timed steps above last a few tens
     # of milliseconds -- the same "burst" regime the HBM peak in MEASURED_PEAKS.json was measured in (best of 10 copies);
@@ -365,23 +454,22 @@ def main():
         n_done = (n_pairs // 20) * 20
         c2 = s2.stop()
         sustained = {"rhs_ms": t_r / n_done, "vjp_ms": t_v / n_done, "value": N_total / ((t_r + t_v) / n_done * 1e-3), "unit": UNIT,
+                     "rhs_roofline_frac": abytes / (t_r / n_done * 1e-3) / 1e9 / peak,
+                     "vjp_roofline_frac": vbytes / (t_v / n_done * 1e-3) / 1e9 / peak,
                      "steps": n_done, "clocks": c2}
 
     # ---- roofline of the dominant kernel (k_fused_rhs): algorithmic bytes / measured launch time
-    peak, peak_src = measured_peak()
-    abytes = algorithmic_bytes(N, F, st["sum_cell_faces"])
     achieved = abytes / (ms_rhs_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": measured_traffic("k_fused_rhs", N), "kernel": "k_fused_rhs", "algorithmic_bytes_per_launch": abytes,
-                "bytes_per_cell": abytes / N, "peak_source": peak_src, "ms_per_launch": ms_rhs_step}
-    vbytes = abytes + 32 * N          # SURVEY 8(d): RHS inputs re-read + lambda (24 B) + Qbar (24 B) + nbar (8 B) - dQ (24 B)
+                "traffic": measured_traffic("k_fused_rhs", N), "traffic_source": TRAFFIC_SOURCE, "kernel": "k_fused_rhs",
+                "algorithmic_bytes_per_launch": abytes, "bytes_per_cell": abytes / N, "peak_source": peak_src, "ms_per_launch": ms_rhs_step}
     vach = vbytes / (ms_vjp_step * 1e-3) / 1e9
     roofline_vjp = {"bound": "hbm", "achieved": vach, "peak": peak, "unit": "GB/s", "frac": vach / peak, "traffic": measured_traffic("k_fused_vjp", N),
-                    "kernel": "k_fused_vjp", "algorithmic_bytes_per_launch": vbytes, "bytes_per_cell": vbytes / N,
-                    "ms_per_launch": ms_vjp_step}
+                    "traffic_source": TRAFFIC_SOURCE, "kernel": "k_fused_vjp + parameter follow-ups (active parameter ManningN: Qbar and pbar)",
+                    "algorithmic_bytes_per_launch": vbytes, "bytes_per_cell": vbytes / N, "ms_per_launch": ms_vjp_step}
 
     # ---- end to end through the host-buffer ABI (pinned host memory; H2D + D2H inside the timed region): at N = 1
-    # this is exactly hg_rhs; at N > 1 the same three stages with the halo exchange in between
+    # this is exactly hg_rhs / hg_rhs_vjp (three-stream pipeline); at N > 1 upload, halo push + kernel, download per rank
     e2e = None
     if not args.no_e2e:
         hQ = torch.empty(3 * N, dtype=torch.float64).pin_memory()
@@ -391,18 +479,20 @@ def main():
         hQ.numpy()[:] = Q0
         hL.numpy()[:] = 1.0
         out, outb = hD.numpy(), hB.numpy()
+        pz = p_zones[:len(p_zones)]
+        pbar_host = np.zeros(pz.size)
 
         def e2e_rhs():
-            if ex is None:
-                ctx.rhs(hQ.numpy(), out=out)
+            if world == 1:
+                ctx.rhs(hQ.numpy(), pz, "ManningN", out=out)
             else:
                 ctx.set_state(hQ.numpy())
                 rhs_step()
                 ctx.get_rhs(out=out)
 
         def e2e_vjp():
-            if ex is None:
-                ctx.rhs_vjp_into(hQ.numpy(), hL.numpy(), outb)
+            if world == 1:
+                ctx.rhs_vjp_into(hQ.numpy(), hL.numpy(), outb, pz, "ManningN", pbar_host)
             else:
                 ctx.set_state(hQ.numpy())
                 ctx.set_lambda(hL.numpy())
@@ -426,8 +516,12 @@ def main():
         e2e = {"value": N_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 72 * N, "d2h_bytes_per_step": 48 * N,
                "ms_per_step": e2e_s * 1e3, "rhs_ms": e2e_rhs_s * 1e3, "vjp_ms": e2e_vjp_s * 1e3,
                "rhs_only": N_total / e2e_rhs_s,
-               "what": "one RHS + one VJP through pinned host buffers (hg_rhs: H2D state, kernel, D2H dQdt; hg_rhs_vjp: H2D state "
-                       "and lambda, kernel, D2H Qbar), chunked over three streams"}
+               "pcie_gbs_per_gpu": {"rhs_h2d": 24 * N / e2e_rhs_s / 1e9, "rhs_d2h": 24 * N / e2e_rhs_s / 1e9,
+                                    "vjp_h2d": 48 * N / e2e_vjp_s / 1e9, "vjp_d2h": 24 * N / e2e_vjp_s / 1e9,
+                                    "note": "bytes of each direction over the whole call time (the directions overlap at N = 1)"},
+               "what": ("one RHS + one VJP through pinned host buffers (hg_rhs: H2D state, kernel, D2H dQdt; hg_rhs_vjp: H2D state "
+                        "and lambda, kernel, D2H Qbar), chunked over three streams") if world == 1 else
+                       "per rank: hg_set_state (H2D) -> halo push + tile kernel -> hg_get_rhs / hg_get_vjp (D2H); all ranks share one host's PCIe / pinned memory"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -435,21 +529,55 @@ def main():
         cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"], "rhs_only": c["rhs_only"],
                "note": "C++ oracle port of the reference algorithm (OpenMP); Hydrograd.jl itself cannot run here (no Julia)"}
 
+    # ---- extra records: C2 / C5 on one GPU; strong scaling (the 16M-cell river split over the GPUs) at N > 1
+    side, strong = {}, None
+    create_s = sl.create_s
+    transport = sl.transport
+    if not args.no_side:
+        if world == 1:
+            sl.close()
+            del sl, ctx
+            side = side_configs(hg, S, local, peak)
+        else:
+            sl.close()
+            del sl, ctx
+            s2 = Slab(max(8, ni // world))
+            timed(s2.rhs_step, W); timed(s2.vjp_step, W)
+            barrier()
+            m_r = allmax(timed(s2.rhs_step, args.steps)) / args.steps
+            barrier()
+            m_v = allmax(timed(s2.vjp_step, args.steps)) / args.steps
+            Ns_total = int(allsum(float(s2.N)))
+            strong = {"workload": f"the {Ns_total / 1e6:.1f}M-cell C3 river split into {world} slabs ({s2.N / 1e6:.2f}M cells per GPU)",
+                      "cells_total": Ns_total, "rhs_ms": m_r, "vjp_ms": m_v, "ms_per_step": m_r + m_v,
+                      "value": Ns_total / ((m_r + m_v) * 1e-3), "unit": UNIT, "transport": s2.transport,
+                      "note": "strong-scaling record: compare with the N = 1 line's ms_per_step on the same total mesh"}
+            s2.close()
+
     if rank == 0:
+        par = "single GPU"
+        if world > 1:
+            par = (f"rcb-slab x{world}, one-layer halo, " +
+                   ("library-owned transport: peer stores over NVLink + epoch flags, consumed by the band tiles of the single tile-kernel launch"
+                    if transport == "ipc" else "pack -> NCCL send/recv -> kernel per step" + (" overlapped with the tiles without halo faces" if args.overlap else "")))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_text(N / 1e6),
                            "cells_per_gpu": N, "faces_per_gpu": F, "tile_cells": args.tile, "n_tiles": st["n_tiles"],
                            "l2": "inputs (state + mesh tables >> 126 MB L2) larger than L2, no flush needed",
-                           "parallelism": (f"rcb-slab x{world}, one-layer halo, NCCL send/recv per step" + (" overlapped with the tiles without halo faces" if args.overlap else "")) if world > 1 else "single GPU"},
+                           "parallelism": par, "transport": transport, "hg_create_s": create_s},
                 "roofline": roofline, "roofline_vjp": roofline_vjp,
                 "rhs": {"value": N_total / (ms_rhs_step * 1e-3), "unit": UNIT, "ms": ms_rhs_step},
                 "vjp": {"value": N_total / (ms_vjp_step * 1e-3), "unit": UNIT, "ms": ms_vjp_step},
                 "sustained": sustained, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        line.update(side)
+        if strong is not None:
+            line["strong"] = strong
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -201,9 +201,10 @@ class Context:
                                               _p(stats, L.c_i64p)))
         return QT, S[:n], dict(accepted=int(stats[0]), rejected=int(stats[1]), rhs=int(stats[2]), saves=saves)
 
-    def rhs_vjp_into(self, Q, lam, Qbar_out):
-        """hg_rhs_vjp with no active parameter into a caller-owned (e.g. pinned) buffer."""
-        self._ck(self.lib.hg_rhs_vjp(self._h, _p(_f64(Q)), None, 0, 0, 0.0, _p(_f64(lam)), _p(Qbar_out), None, None))
+    def rhs_vjp_into(self, Q, lam, Qbar_out, params=None, active=None, pbar_out=None):
+        """hg_rhs_vjp into caller-owned (e.g. pinned) buffers; pbar_out [n_params] when a parameter is active."""
+        p, n, a = self._params(params, active)
+        self._ck(self.lib.hg_rhs_vjp(self._h, _p(_f64(Q)), _p(p), n, a, 0.0, _p(_f64(lam)), _p(Qbar_out), _p(pbar_out) if n else None, None))
 
     def get_vjp_into(self, Qbar_out):
         self._ck(self.lib.hg_get_vjp(self._h, _p(Qbar_out), None, None))

@@ -283,7 +283,11 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(up(ctx, d.face_nx, fh.face_nx)); TRY(up(ctx, d.face_ny, fh.face_ny)); TRY(up(ctx, d.face_len, fh.face_len));
     TRY(upN(ctx, d.area, permuted(area.data(), fh.perm), Ns)); TRY(upN(ctx, d.hstill, permuted(hstill.data(), fh.perm), Ns));
     TRY(al(ctx, d.zb, Ns)); TRY(al(ctx, d.S0x, Ns)); TRY(al(ctx, d.S0y, Ns)); TRY(al(ctx, d.mann, Ns));
-    if (!x->matid_ref.empty()) TRY(up(ctx, d.matid, permuted(x->matid_ref.data(), fh.perm)));
+    if (!x->matid_ref.empty()) {
+      auto mid = permuted(x->matid_ref.data(), fh.perm);
+      mid.resize((size_t)fh.n_tiles * fh.T, 0);   // whole tiles: the VJP kernel prefetches the next tile's block into L2
+      TRY(up(ctx, d.matid, mid));
+    }
     std::vector<int32_t> bc_cell(B);
     std::vector<double> bhst(B);
     for (int64_t e = 0; e < B; ++e) { bc_cell[e] = fh.iperm[h.cell_ref[e]]; bhst[e] = h.hstill_g[e]; }
@@ -314,7 +318,6 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(al(ctx, d.pbar, npar)); TRY(al(ctx, d.ent_c, std::max<int64_t>(B, 1))); TRY(al(ctx, d.ent_n, std::max<int64_t>(B, 1)));
     TRY(al(ctx, d.ent_z, std::max<int64_t>(B, 1))); TRY(al(ctx, d.ent_h, std::max<int64_t>(B, 1)));
     TRY(al(ctx, d.Qinbar, std::max<int64_t>(ctx->n_inletq, 1))); TRY(al(ctx, d.inlet_A, std::max<int64_t>(ctx->n_inletq, 1)));
-    TRY(al(ctx, d.nbcorr, std::max<int64_t>((int64_t)h.bcell_ref.size(), 1)));
     {
       std::vector<int32_t> bcell_int(h.bcell_ref.size());
       for (size_t q = 0; q < bcell_int.size(); ++q) bcell_int[q] = fh.iperm[h.bcell_ref[q]];

@@ -178,7 +178,7 @@ struct FusedDev {
   DBuf<double> inlet_coef;                         // [n_inletq]  Q_k / total_A
   DBuf<double> Qin, wse;
   DBuf<double> Q, Q2, dQ, lam, Qbar, stage, params, pbar, nbar, s0bar;  // state-like: [3*Ns]
-  DBuf<double> ent_c, ent_n, ent_z, ent_h, Qinbar, inlet_A, zone_part, nbcorr;   // VJP: per boundary entry / per inlet
+  DBuf<double> ent_c, ent_n, ent_z, ent_h, Qinbar, inlet_A, zone_part, zone_part2;   // VJP: per boundary entry / per inlet
   DBuf<int32_t> bcell, bcell_ref, bcell_ptr, bcell_ent;                 // boundary-adjacent cells -> their entries
   DBuf<int32_t> halo_off, halo_cnt;                                     // [B]
   DBuf<double> ens_Q, ens_Q2, ens_mann, ens_Qin, ens_coef, ens_A;       // parameter ensembles: [M][...]

@@ -113,13 +113,15 @@ struct Side {
 
 // Riemann_2D_Roe, face-once form.  Returns (flux along the face normal, outward for L) * len.  The 1/2 of the Roe average
 // of the two physical fluxes rides in the length factor (scaling by 2 is exact, so the bits are those of 0.5*(..)*len).
-// zbL/zbR point at the bed elevations; they are only read on the (rare) faces with a dry side.
-__device__ __forceinline__ void roe_flux(Side L, Side R, const double* zbL, const double* zbR, double nx, double ny, double len,
+// zbL() / zbR() fetch the bed elevations; they are only called on the (rare) faces with a dry side, so the bed is never
+// staged: it stays in global memory.
+template <class ZL, class ZR>
+__device__ __forceinline__ void roe_flux(Side L, Side R, ZL zbL, ZR zbR, double nx, double ny, double len,
                                          double g, double hmin, double& o0, double& o1, double& o2) {
   const bool dryL = L.h <= hmin, dryR = R.h <= hmin;
   if (dryL || dryR) {
     if (dryL && dryR) { o0 = o1 = o2 = 0.0; return; }         // swe_2D_solvers.jl:16
-    L.zb = *zbL; R.zb = *zbR;
+    L.zb = zbL(); R.zb = zbR();
     if ((L.h + L.zb) < (R.zb + hmin) && dryR) {                // :23 wall-like: mirror L into R
       R.h = L.h; R.hu = -L.hu; R.hv = -L.hv; R.u = -L.u; R.v = -L.v; R.s = L.s;
     } else if ((R.h + R.zb) < (L.zb + hmin) && dryL) {         // :39
@@ -175,7 +177,7 @@ __device__ __forceinline__ void derive(Side& s, double hst, double g) {
 template <int T_, int ML_, int MF_, int NF_, int THREADS_, int MINB_>
 struct TileCfg {
   static constexpr int T = T_, ML = ML_, MF = MF_, NF = NF_, THREADS = THREADS_, MINB = MINB_;
-  static constexpr int kSmem = 16 + 8 * (7 * ML + 3 * MF + 4 * T) + 4 * MF + 2 * T * NF;
+  static constexpr int kSmem = 16 + 8 * (6 * ML + 3 * MF + 4 * T) + 4 * MF + 2 * T * NF;
   // half as many threads as cells: every thread owns exactly two cells and ~four faces, processed pairwise
   static constexpr bool kDual = 2 * THREADS_ <= T_;
 };
@@ -186,11 +188,12 @@ struct TileCfg {
 
 // X-macro over the compiled configurations, in priority order: (id, T, ML, MF, NF, THREADS, MINB).
 // MINB CTAs/SM is what the shared-memory footprint allows; THREADS keeps MINB*THREADS*regs <= 64K.
-// Measured on B200 (4M-cell river, ms per RHS): T=256/160 thr/5 CTAs 0.174, T=192/160/6 0.176,
-// T=256/192/4 0.184, T=512/384/2 0.195.
+// Measured on B200 (round 1, 4M-cell river, ms per RHS): T=256/160 thr/5 CTAs 0.174, T=192/160/6 0.176,
+// T=256/192/4 0.184, T=512/384/2 0.195.  Round 2 (16M cells, after the leaner arithmetic): T=256/128 thr/5 CTAs with two
+// faces / cells per trip 0.531-0.538 (sustained 0.625-0.636) vs T=256/160 0.543-0.553 (0.646-0.659); T=224 0.56, T=192 0.67.
 #define HG_TILE_CONFIGS(X)            \
-  X(7, 256, 336, 564, 4, 160, 5)      \
   X(10, 256, 336, 564, 4, 128, 5)     \
+  X(7, 256, 336, 564, 4, 160, 5)      \
   X(11, 256, 336, 564, 4, 128, 4)     \
   X(1, 256, 352, 580, 4, 192, 4)      \
   X(0, 256, 352, 580, 4, 128, 4)      \

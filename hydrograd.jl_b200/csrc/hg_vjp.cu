@@ -43,10 +43,7 @@ struct VjpArgs {
   double *Qbar, *nbar, *s0bar;          // [3Ns], [Ns], [2Ns]
   double *ent_c, *ent_n, *ent_z;        // per boundary entry: inlet coef adjoint share, n adjoint, zb adjoint
   CommWait cw;                          // library-owned halo exchange: CTAs >= cw.from wait for the neighbours' pushes
-  const int32_t* matid;                 // fused Manning-zone reduction (active parameter ManningN, <= kZoneFused zones):
-  double* zone_part;                    // [n_tiles][kZoneFused] per-tile sums of nbar by zone; NULL = off
 };
-constexpr int kZoneFused = 8;
 
 struct Adj {
   double xi, h, u, v, s, P;   // adjoints of the staged per-cell variables (hu = h*u, hv = h*v folded in)
@@ -256,7 +253,6 @@ struct __align__(16) VjpSmem {
   double area[T], mann[T], sx[T], sy[T];
   uint32_t lr[MF];
   uint16_t cf[T * NF];
-  double zs[16][kZoneFused];                              // per-warp zone sums of nbar (fused Manning-zone reduction)
 };
 
 // adjoints of one side's staged variables (xi, h, u, v, s, P) -> adjoints of its raw state (xi, q_x, q_y): the
@@ -633,22 +629,6 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     o.s0y = wet ? g * xi * lam2 : 0.0;
     return o;
   };
-  // fused Manning-zone reduction: the warp adds up nbar zone by zone (zones are spatially contiguous: almost always one
-  // pass), lane 0 accumulates into its warp's row; fixed order, no atomics
-  const int warp = tid >> 5, lane = tid & 31;
-  auto zone_add = [&](int32_t z, double v, bool valid) {
-    unsigned rem = __ballot_sync(0xffffffffu, valid);
-    while (rem) {
-      const int leader = __ffs(rem) - 1;
-      const int32_t zl = __shfl_sync(0xffffffffu, z, leader);
-      const bool mine = valid && z == zl;
-      double sacc = mine ? v : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
-      if (lane == 0) sm.zs[warp][zl] += sacc;
-      rem &= ~__ballot_sync(0xffffffffu, mine);
-    }
-  };
   auto cell_store = [&](int32_t l, const CellOut& o) {
     const int32_t gi = c0 + l;
     a.Qbar[gi] = o.xib;
@@ -657,42 +637,16 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     a.nbar[gi] = o.nb;
     if (a.want_s0) { a.s0bar[gi] = o.s0x; a.s0bar[Ns + gi] = o.s0y; }
   };
-  const bool zones = a.zone_part != nullptr;
-  if (zones && lane < kZoneFused) sm.zs[warp][lane] = 0.0;   // own row of the warp: no barrier needed
-  if (zones) __syncwarp();
   if constexpr (FPT == 1) {
-    for (int32_t l0 = 0; l0 < nc; l0 += kThreads) {          // whole warps take every trip (the zone sums shuffle)
-      const int32_t l = l0 + tid;
-      const bool valid = l < nc;
-      CellOut o = {0, 0, 0, 0, 0, 0};
-      if (valid) { o = cell_adj(l); cell_store(l, o); }
-      if (zones) zone_add(valid ? __ldg(a.matid + c0 + l) : 0, o.nb, valid);
-    }
+    for (int32_t l = tid; l < nc; l += kThreads) cell_store(l, cell_adj(l));
   } else {
-    for (int32_t l0 = 0; l0 < nc; l0 += 2 * kThreads) {
-      const int32_t l = l0 + tid, l2 = l + kThreads;
-      const bool v1 = l < nc, v2 = l2 < nc;
-      CellOut o1 = {0, 0, 0, 0, 0, 0}, o2 = {0, 0, 0, 0, 0, 0};
-      if (v2) {
-        o1 = cell_adj(l); o2 = cell_adj(l2);
-        cell_store(l, o1); cell_store(l2, o2);
-      } else if (v1) {
-        o1 = cell_adj(l);
-        cell_store(l, o1);
+    for (int32_t l = tid; l < nc; l += 2 * kThreads) {
+      if (l + kThreads < nc) {
+        const CellOut o1 = cell_adj(l), o2 = cell_adj(l + kThreads);
+        cell_store(l, o1); cell_store(l + kThreads, o2);
+      } else {
+        cell_store(l, cell_adj(l));
       }
-      if (zones) {
-        zone_add(v1 ? __ldg(a.matid + c0 + l) : 0, o1.nb, v1);
-        zone_add(v2 ? __ldg(a.matid + c0 + l2) : 0, o2.nb, v2);
-      }
-    }
-  }
-  if (zones) {
-    __syncthreads();
-    if (tid < kZoneFused) {
-      double acc = 0.0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) acc += sm.zs[w][tid];
-      a.zone_part[(size_t)t * kZoneFused + tid] = acc;
     }
   }
 }
@@ -708,8 +662,23 @@ __global__ void __launch_bounds__(256) k_inlet_adj(Consts c, const int32_t* inle
   __shared__ double red[256];
   __shared__ double sAbar;
   const int k = blockIdx.x;
+  const int32_t e0 = inlet_ptr[k], e1 = inlet_ptr[k + 1];
+  // the per-entry gathers (cell id -> depth, n) do not depend on the reduction: issue them first, so that their latency
+  // (two dependent global accesses) overlaps the tree instead of following it
+  constexpr int KM = 4;                          // entries per thread kept in registers (inlets of up to 1024 faces)
+  double hh[KM], nn[KM], ll[KM];
   double acc = 0.0;
-  for (int32_t e = inlet_ptr[k] + threadIdx.x; e < inlet_ptr[k + 1]; e += 256) acc += ent_c[e];
+#pragma unroll
+  for (int j = 0; j < KM; ++j) {
+    const int32_t e = e0 + threadIdx.x + j * 256;
+    hh[j] = 0.0; nn[j] = 1.0; ll[j] = 0.0;
+    if (e < e1) {
+      const int32_t ci = bc_cell[e];
+      hh[j] = Q[ci] + hstill[ci]; nn[j] = mann[ci]; ll[j] = bc_l53[e];
+      acc += ent_c[e];
+    }
+  }
+  for (int32_t e = e0 + threadIdx.x + KM * 256; e < e1; e += 256) acc += ent_c[e];
   red[threadIdx.x] = acc;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -724,7 +693,16 @@ __global__ void __launch_bounds__(256) k_inlet_adj(Consts c, const int32_t* inle
   }
   __syncthreads();
   const double Abar = sAbar;
-  for (int32_t e = inlet_ptr[k] + threadIdx.x; e < inlet_ptr[k + 1]; e += 256) {
+#pragma unroll
+  for (int j = 0; j < KM; ++j) {
+    const int32_t e = e0 + threadIdx.x + j * 256;
+    if (e < e1) {
+      const bool wet = hh[j] > c.h_small;
+      ent_h[e] = wet ? Abar * ll[j] / nn[j] : 0.0;
+      ent_n[e] += wet ? -Abar * ll[j] * hh[j] / (nn[j] * nn[j]) : 0.0;
+    }
+  }
+  for (int32_t e = e0 + threadIdx.x + KM * 256; e < e1; e += 256) {
     const int32_t ci = bc_cell[e];
     const double h = Q[ci] + hstill[ci];
     const bool wet = h > c.h_small;
@@ -737,8 +715,7 @@ __global__ void __launch_bounds__(256) k_inlet_adj(Consts c, const int32_t* inle
 // One thread per boundary-adjacent cell: add its entries' contributions in fixed order (deterministic).
 __global__ void k_bc_scatter(int32_t nbcell, const int32_t* __restrict__ bcell, const int32_t* __restrict__ bcell_ptr,
                              const int32_t* __restrict__ bcell_ent, const int32_t* __restrict__ bc_type,
-                             const double* __restrict__ ent_h, const double* __restrict__ ent_n, double* Qbar, double* nbar,
-                             double* __restrict__ nbcorr) {
+                             const double* __restrict__ ent_h, const double* __restrict__ ent_n, double* Qbar, double* nbar) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nbcell) return;
   const int32_t c = bcell[i];
@@ -749,7 +726,6 @@ __global__ void k_bc_scatter(int32_t nbcell, const int32_t* __restrict__ bcell, 
   }
   Qbar[c] += hb;   // inlet cells that receive this are wet, hence unclamped: xi_bar += h_bar
   nbar[c] += nb;
-  nbcorr[i] = nb;  // what the fused zone sums of the tile kernel have not seen
 }
 
 // pbar_z = sum_{cells of zone z} nbar  (process_ManningN_2D.jl:88 transposed): two fixed-shape stages
@@ -772,16 +748,12 @@ __global__ void __launch_bounds__(kZoneBlock) k_zone_partial(int32_t N, int32_t 
     __syncthreads();
   }
 }
-// one CTA per zone: 256 strided sums over the blocks' partials in block order, then a fixed tree
-// (+ the inlet-coupling corrections of the boundary-adjacent cells when the partials come from the tile kernel)
-__global__ void __launch_bounds__(256) k_zone_final(int32_t nblocks, int32_t stride, const double* __restrict__ part, double* __restrict__ pbar,
-                                                    int32_t nbcell, const int32_t* __restrict__ bcell, const int32_t* __restrict__ matid,
-                                                    const double* __restrict__ nbcorr) {
+// (many zones: one CTA per zone over the chunk partials of k_zone_partial)
+__global__ void __launch_bounds__(256) k_zone_final_many(int32_t nblocks, int32_t n_mat, const double* __restrict__ part, double* __restrict__ pbar) {
   __shared__ double red[256];
   const int32_t z = blockIdx.x;
   double acc = 0.0;
-  for (int32_t b = threadIdx.x; b < nblocks; b += 256) acc += part[(size_t)b * stride + z];
-  for (int32_t i = threadIdx.x; i < nbcell; i += 256) acc += (matid[bcell[i]] == z) ? nbcorr[i] : 0.0;
+  for (int32_t b = threadIdx.x; b < nblocks; b += 256) acc += part[(size_t)b * n_mat + z];
   red[threadIdx.x] = acc;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -789,6 +761,70 @@ __global__ void __launch_bounds__(256) k_zone_final(int32_t nblocks, int32_t str
     __syncthreads();
   }
   if (threadIdx.x == 0) pbar[z] = red[0];
+}
+// Few zones (the reference's cases have 1-6): ONE launch straight from nbar + matid (12 B per cell, bandwidth-bound).
+// A fixed grid of CTAs strides over the cells with four independent loads in flight per thread and one register
+// accumulator per zone; per-CTA sums go to part2[cta][.]; the CTA that finishes last (ticket counter) adds part2 in a fixed
+// shape (256 strided sums in CTA order, then a tree) and writes pbar.  Every order is fixed: bit-reproducible.
+constexpr int kZoneFew = 8, kZoneGrid = 148 * 8;
+template <int NZ>
+__global__ void __launch_bounds__(256) k_zone_reduce(int32_t N, int32_t n_mat, const int32_t* __restrict__ matid, const double* __restrict__ nbar,
+                                                     double* __restrict__ part2, unsigned int* __restrict__ ticket, double* __restrict__ pbar) {
+  __shared__ double ws[8][NZ];
+  __shared__ double red[256];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[NZ];
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) acc[z] = 0.0;
+  const int32_t stride = gridDim.x * 256;
+  for (int32_t i = blockIdx.x * 256 + threadIdx.x; i < N; i += 4 * stride) {
+    int32_t m[4];
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int32_t j = i + k * stride;
+      m[k] = j < N ? __ldg(matid + j) : -1;
+      v[k] = j < N ? __ldg(nbar + j) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int z = 0; z < NZ; ++z) acc[z] += (m[k] == z) ? v[k] : 0.0;
+  }
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) {
+    double v = acc[z];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) ws[warp][z] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NZ) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += ws[w][threadIdx.x];
+    part2[(size_t)blockIdx.x * NZ + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int z = 0; z < n_mat; ++z) {
+    double v = 0.0;
+    for (unsigned c = threadIdx.x; c < gridDim.x; c += 256) v += __ldcg(part2 + (size_t)c * NZ + z);
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) pbar[z] = red[0];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *ticket = 0;   // ready for the next launch
 }
 
 // zbar (reference order) = (update_bed_data)^T S0bar + exit-h entries.  Transposed Green-Gauss as a gather:
@@ -907,14 +943,6 @@ int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_
   a.halo_off = d.halo_off.p; a.halo_cnt = d.halo_cnt.p; a.halo_recv = d.halo_recv.p;
   a.wse = d.wse.p; a.Q = d_Q; a.lam = d_lam; a.Qbar = d_Qbar; a.nbar = d.nbar.p; a.s0bar = d.s0bar.p;
   a.ent_c = d.ent_c.p; a.ent_n = d.ent_n.p; a.ent_z = d.ent_z.p;
-  a.matid = nullptr; a.zone_part = nullptr;
-  if (ctx->active == HG_PARAM_MANNING && ctx->n_mat <= kZoneFused && d.matid.p) {   // zone sums of nbar inside the tile kernel
-    if (d.zone_part.n < (size_t)fh.n_tiles * kZoneFused && d.zone_part.alloc((size_t)fh.n_tiles * kZoneFused) != cudaSuccess) {
-      ctx->err = "cudaMalloc(zone_part)";
-      return HG_ERR_CUDA;
-    }
-    a.matid = d.matid.p; a.zone_part = d.zone_part.p;
-  }
   a.tile_order = tile_order; a.tile_base = tile_base;
   if (use_comm) {   // library-owned exchange (see launch_rhs)
     const hg_comm* cm = ctx->comm;
@@ -957,17 +985,20 @@ int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar) {
     if (ctx->nbcell > 0) {
       k_bc_scatter<<<(unsigned)((ctx->nbcell + th - 1) / th), th, 0, ctx->stream>>>((int32_t)ctx->nbcell, d.bcell.p, d.bcell_ptr.p,
                                                                                  d.bcell_ent.p, d.bc_type.p, d.ent_h.p,
-                                                                                 d.ent_n.p, d_Qbar, d.nbar.p, d.nbcorr.p);
+                                                                                 d.ent_n.p, d_Qbar, d.nbar.p);
       ctx->launches++;
     }
   }
   // ---- parameter adjoints
   if (ctx->active == HG_PARAM_MANNING) {
-    const bool corr = ctx->n_inletq > 0 && ctx->nbcell > 0;
-    if (ctx->n_mat <= kZoneFused && d.matid.p) {
-      // the tile kernel left per-tile zone sums; add the inlet-coupling corrections of the boundary-adjacent cells
-      k_zone_final<<<(unsigned)ctx->n_mat, 256, 0, ctx->stream>>>(fh.n_tiles, kZoneFused, d.zone_part.p, d.pbar.p, corr ? (int32_t)ctx->nbcell : 0,
-                                                                  d.bcell.p, d.matid.p, d.nbcorr.p);
+    if (ctx->n_mat <= kZoneFew) {
+      if (d.zone_part2.n < (size_t)kZoneGrid * kZoneFew + 2) {
+        if (d.zone_part2.alloc((size_t)kZoneGrid * kZoneFew + 2) != cudaSuccess) { ctx->err = "cudaMalloc(zone_part2)"; return HG_ERR_CUDA; }
+        cudaMemsetAsync(d.zone_part2.p + (size_t)kZoneGrid * kZoneFew, 0, 16, ctx->stream);   // the ticket counter
+      }
+      unsigned int* ticket = reinterpret_cast<unsigned int*>(d.zone_part2.p + (size_t)kZoneGrid * kZoneFew);
+      const unsigned g2 = (unsigned)std::min<int64_t>(kZoneGrid, (ctx->N + 1023) / 1024);
+      k_zone_reduce<kZoneFew><<<g2, 256, 0, ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid.p, d.nbar.p, d.zone_part2.p, ticket, d.pbar.p);
       ctx->launches++;
     } else {
       const int nblocks = (int)((ctx->N + kZoneChunk - 1) / kZoneChunk);
@@ -976,7 +1007,7 @@ int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar) {
       }
       k_zone_partial<<<nblocks, kZoneBlock, kZoneBlock * sizeof(double), ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid.p,
                                                                                         d.nbar.p, d.zone_part.p);
-      k_zone_final<<<(unsigned)ctx->n_mat, 256, 0, ctx->stream>>>(nblocks, (int32_t)ctx->n_mat, d.zone_part.p, d.pbar.p, 0, nullptr, nullptr, nullptr);
+      k_zone_final_many<<<(unsigned)ctx->n_mat, 256, 0, ctx->stream>>>(nblocks, (int32_t)ctx->n_mat, d.zone_part.p, d.pbar.p);
       ctx->launches += 2;
     }
   } else if (ctx->active == HG_PARAM_ZB) {
