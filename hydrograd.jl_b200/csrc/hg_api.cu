@@ -299,7 +299,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(al(ctx, d.Q, 3 * Ns)); TRY(al(ctx, d.Q2, 3 * Ns)); TRY(al(ctx, d.dQ, 3 * Ns)); TRY(al(ctx, d.stage, 3 * N));
     TRY(al(ctx, d.params, npar)); TRY(al(ctx, d.err, 1));
     TRY(up(ctx, d.tile_order, fh.tile_order));
-    TRY(up(ctx, d.band_order, fh.band_order));
+    TRY(up(ctx, d.band_order, fh.band_order)); TRY(up(ctx, d.comm_order, fh.comm_order));
     if (fh.n_chunks > 1) {
       TRY(al(ctx, d.stage_out, 3 * N));
       CK(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));

@@ -56,7 +56,7 @@ struct Consts {
 struct CommWait {
   const unsigned long long* flags = nullptr;   // local flag lines, 16 u64 apart
   unsigned long long epoch = 0;
-  int32_t n = 0, from = 0;                     // neighbours; first CTA index (band order) that touches halo faces
+  int32_t n = 0, from = 0, to = 0;             // neighbours; CTA index range [from, to) of the band (tiles with halo faces)
   int32_t* err = nullptr;
 };
 
@@ -161,10 +161,12 @@ struct FusedHost {
   // multi-GPU overlap: tiles without halo-boundary faces first (they can run while the halo is in flight), then the band
   std::vector<int32_t> band_order;   // [n_tiles]
   int32_t n_interior_tiles = 0;
+  std::vector<int32_t> comm_order;   // [n_tiles] library-owned transport: interior tiles, band in the middle, interior tiles
+  int32_t comm_band0 = 0;            // first band position in comm_order
 };
 
 struct FusedDev {
-  DBuf<int32_t> perm, iperm, tile_desc, halo, bface_e, tile_order, band_order;
+  DBuf<int32_t> perm, iperm, tile_desc, halo, bface_e, tile_order, band_order, comm_order;
   DBuf<double> stage_out, stage_lam;
   DBuf<uint32_t> face_lr;
   DBuf<uint16_t> cf_idx;

@@ -570,6 +570,12 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
       (is_band ? band : fh.band_order).push_back(t);
     }
     fh.n_interior_tiles = (int32_t)fh.band_order.size();
+    // library-owned transport (one launch): the band sits in the MIDDLE of the order -- the neighbours' pushes land a few
+    // microseconds after the launch starts, so the band tiles never wait there, and their slower halo faces are not the tail
+    fh.comm_band0 = fh.n_interior_tiles / 2;
+    fh.comm_order.assign(fh.band_order.begin(), fh.band_order.begin() + fh.comm_band0);
+    fh.comm_order.insert(fh.comm_order.end(), band.begin(), band.end());
+    fh.comm_order.insert(fh.comm_order.end(), fh.band_order.begin() + fh.comm_band0, fh.band_order.end());
     fh.band_order.insert(fh.band_order.end(), band.begin(), band.end());
   }
   // ---- stages of the host-buffer pipeline

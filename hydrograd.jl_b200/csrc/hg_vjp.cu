@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     if (p0.w > 0) bulk_prefetch_l2(a.halo + p0.z, (uint32_t)((p0.w + 3) & ~3) * 4u);
     if (!a.tile_order && wp + a.prefetch < a.n_run) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tile_desc + (size_t)(wp + a.prefetch) * kTileDesc));
   }
-  if (a.cw.n > 0 && (int)blockIdx.x >= a.cw.from) comm_wait(a.cw, tid);   // band tile: phase 2b reads what the neighbours push
+  if (a.cw.n > 0 && (int)blockIdx.x >= a.cw.from && (int)blockIdx.x < a.cw.to) comm_wait(a.cw, tid);   // band tile: phase 2b reads what the neighbours push
   mbar_wait(sm.bar, 0);
 
   // ---- phase 1: owned cells, in place
@@ -946,9 +946,10 @@ int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_
   a.tile_order = tile_order; a.tile_base = tile_base;
   if (use_comm) {   // library-owned exchange (see launch_rhs)
     const hg_comm* cm = ctx->comm;
-    a.tile_order = d.band_order.p; a.tile_base = 0; n_run = fh.n_tiles;
+    a.tile_order = d.comm_order.p; a.tile_base = 0; n_run = fh.n_tiles;
     a.halo_recv = cm->recv[cm->epoch & 1];
-    a.cw.flags = cm->flags; a.cw.epoch = cm->epoch; a.cw.n = cm->n; a.cw.from = fh.n_interior_tiles; a.cw.err = d.err.p;
+    a.cw.flags = cm->flags; a.cw.epoch = cm->epoch; a.cw.n = cm->n; a.cw.err = d.err.p;
+    a.cw.from = fh.comm_band0; a.cw.to = fh.comm_band0 + (fh.n_tiles - fh.n_interior_tiles);
   }
   const unsigned grid = (unsigned)(n_run >= 0 ? n_run : fh.n_tiles);
   a.n_run = (int32_t)grid;
