@@ -198,6 +198,7 @@ struct TileCfg {
   X(1, 256, 352, 580, 4, 192, 4)      \
   X(0, 256, 352, 580, 4, 128, 4)      \
   X(2, 256, 352, 580, 4, 256, 3)      \
+  X(14, 384, 480, 872, 4, 192, 3)     \
   X(4, 512, 672, 1124, 4, 384, 2)     \
   X(3, 512, 672, 1124, 4, 256, 2)     \
   X(12, 224, 304, 504, 4, 128, 5)     \

@@ -96,7 +96,7 @@ def test_tiling_and_ordering_do_not_change_bits(hg):
     Q = cases.random_state_flat(flat, 11)
     base = hg.Context(flat, tile_cells=512, reorder=True).rhs(Q)
     for tile, reorder, threads in ((128, True, 0), (256, True, 128), (256, True, 256), (512, False, 384), (128, False, 0),
-                                  (256, True, 1010), (256, True, 1011), (512, True, 256), (224, True, 0), (224, True, 160)):   # two-faces-per-trip configurations
+                                  (256, True, 1010), (256, True, 1011), (512, True, 256), (224, True, 0), (224, True, 160), (384, True, 0)):   # two-faces-per-trip configurations
         got = hg.Context(flat, tile_cells=tile, reorder=reorder, threads=threads).rhs(Q)
         assert np.array_equal(base, got), (tile, reorder, threads)
 

@@ -104,7 +104,7 @@ def test_vjp_launch_shapes_agree(hg):
     lam = np.random.default_rng(8).standard_normal(Q.size)
     p = np.full(flat["n_mat"], 0.035)
     base = None
-    for tile, variant in ((256, 0), (256, 1), (256, 2), (224, 0), (224, 1), (192, 0), (192, 1), (192, 2), (128, 0), (512, 0)):
+    for tile, variant in ((256, 0), (256, 1), (256, 2), (384, 0), (384, 1), (224, 0), (224, 1), (192, 0), (192, 1), (192, 2), (128, 0), (512, 0)):
         Qbar, pbar = hg.Context(flat, tile_cells=tile, vjp_variant=variant).rhs_vjp(Q, lam, p, "ManningN")
         if base is None:
             base = (Qbar, pbar)
