@@ -694,8 +694,8 @@ int hg_rhs_jvp_multi(hg_ctx* ctx, const double* Q, const double* params, int64_t
   CK(ctx, cudaMemcpyAsync(p.Q.p, Q, n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaMemcpyAsync(dV.p, V, (size_t)K * n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
   ctx->state_set = true;
-  for (int64_t k = 0; k < K; ++k)
-    TRY(hg::plain_jvp(ctx, p.Q.p, dV.p + k * n3, with_p ? dP.p + k * npar : nullptr, (k == 0 && dQdt) ? p.dQ.p : nullptr, dJ.p + k * n3));
+  // all K directions in one pair of launches
+  TRY(hg::plain_jvp_batch(ctx, p.Q.p, dV.p, (int64_t)n3, with_p ? dP.p : nullptr, npar, dQdt ? p.dQ.p : nullptr, dJ.p, K));
   if (dQdt) CK(ctx, cudaMemcpyAsync(dQdt, p.dQ.p, n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaMemcpyAsync(JV, dJ.p, (size_t)K * n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -767,9 +767,8 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
   CK(ctx, cudaMemcpyAsync(U.p, Q0, (size_t)n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
   // d/dt of the augmented state: row 0 = f(Q, p), row k = J_Q U_k + J_p e_k
   auto rhs_aug = [&](const double* u, double* du) -> int {
-    for (int64_t k = 0; k < K; ++k)
-      TRY(hg::plain_jvp(ctx, u, u + (1 + k) * n3, E.p + k * K, k == 0 ? du : nullptr, du + (1 + k) * n3));
-    return HG_OK;
+    // the K partials in one pair of launches (row k of the augmented state is direction k; pdot = e_k)
+    return hg::plain_jvp_batch(ctx, u, u + n3, (int64_t)n3, E.p, K, du, du + n3, K);
   };
   double* u = U.p;
   double* unew = Unew.p;

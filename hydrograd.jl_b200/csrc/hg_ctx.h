@@ -120,7 +120,8 @@ struct PlainDev {
   DBuf<double> ks;                    // [N] roughness height (variable Manning's n)
   DBuf<double> hstill_g, zb_g;        // [B] GHOST order (as passed in)
   DBuf<double> gh, gqx, gqy, gxi;     // [B] ghost states, ghost order
-  DBuf<double> gh_d, gqx_d, gqy_d, gxi_d;  // [B] their tangents (forward mode, hg_jvp.cu)
+  DBuf<double> gh_d, gqx_d, gqy_d, gxi_d;  // [K][B] their tangents (forward mode, hg_jvp.cu), one copy per direction of a batch
+  DBuf<double> jgh, jgqx, jgqy, jgxi;      // [K][B] ghost values of the forward-mode sweeps (per direction: no write sharing)
   DBuf<double> V, dQd, pdot;          // [3N], [3N], [np]: tangent of the state, of the RHS, of the parameters
   DBuf<double> Qin, wse;              // [n_inletq], [n_exith]
   DBuf<double> Q, dQ, params;         // [3N], [3N], [np]
@@ -273,6 +274,8 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
 int plain_rhs(hg_ctx* ctx, const double* dQ_in_Q, double* d_out);
 // forward mode on the plain tables (hg_jvp.cu)
 int plain_jvp(hg_ctx* ctx, const double* d_Q, const double* d_V, const double* d_pdot, double* d_out, double* d_out_dot);
+int plain_jvp_batch(hg_ctx* ctx, const double* d_Q, const double* d_V, int64_t sV, const double* d_pdot, int64_t sP, double* d_out,
+                    double* d_out_dot, int64_t K);
 int sens_lincomb(hg_ctx* ctx, int64_t len, double* y, const double* x, int n, const double* const* k, const double* coef);
 int sens_err_blocks(int64_t n3);
 int sens_err_norm(hg_ctx* ctx, int64_t n3, int rows, const double* u, const double* unew, int n, const double* const* k,

@@ -17,7 +17,24 @@ static_assert((int)jvp::kParamZb == (int)HG_PARAM_ZB && (int)jvp::kParamManning 
                   (int)jvp::kParamQ == (int)HG_PARAM_Q, "HG_PARAM_*");
 constexpr int kMaxInlets = 64;
 
-__global__ void __launch_bounds__(256) k_jvp_ghost(jvp::Args a) {
+// K directions per launch: blockIdx.y selects the direction, i.e. the rows of V / pdot / the outputs and its own copy of the
+// ghost buffers (strides in doubles; every direction recomputes the values -- the path is launch-bound on the meshes it
+// serves, so K directions cost two launches instead of 2 K)
+struct Batch {
+  int64_t sV, sP, sB;
+};
+__device__ __forceinline__ void select_direction(jvp::Args& a, const Batch& b) {
+  const int64_t y = blockIdx.y;
+  if (a.V) a.V += y * b.sV;
+  if (a.pdot) a.pdot += y * b.sP;
+  a.dQ_d += y * b.sV;
+  a.gh += y * b.sB; a.gqx += y * b.sB; a.gqy += y * b.sB; a.gxi += y * b.sB;
+  a.gh_d += y * b.sB; a.gqx_d += y * b.sB; a.gqy_d += y * b.sB; a.gxi_d += y * b.sB;
+  if (y > 0) a.dQ = nullptr;     // the values are delivered once
+}
+
+__global__ void __launch_bounds__(256) k_jvp_ghost(jvp::Args a, const Batch b) {
+  select_direction(a, b);
   __shared__ double coef_v[kMaxInlets], coef_d[kMaxInlets];
   for (int32_t k = threadIdx.x; k < a.n_inlet; k += blockDim.x) {
     const jvp::Dual c = jvp::inlet_coef<jvp::Dual>(a, k);
@@ -31,7 +48,8 @@ __global__ void __launch_bounds__(256) k_jvp_ghost(jvp::Args a) {
   }
 }
 
-__global__ void __launch_bounds__(128) k_jvp_cell(jvp::Args a) {
+__global__ void __launch_bounds__(128) k_jvp_cell(jvp::Args a, const Batch b) {
+  select_direction(a, b);
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < a.N) jvp::cell<jvp::Dual>(a, i);
 }
@@ -122,16 +140,23 @@ int sens_err_norm(hg_ctx* ctx, int64_t n3, int rows, const double* u, const doub
   return launch_ok(ctx, "sens_err_norm");
 }
 
-// d_V [3N], d_pdot [n_params] or nullptr, d_out [3N] or nullptr, d_out_dot [3N]; reference cell order throughout
-int plain_jvp(hg_ctx* ctx, const double* d_Q, const double* d_V, const double* d_pdot, double* d_out, double* d_out_dot) {
+// K directions in one pair of launches: d_V [K][3N] (row stride sV; NULL = zero), d_pdot [K][n_params] (row stride sP) or
+// nullptr, d_out [3N] or nullptr (values, once), d_out_dot [K][3N] (row stride sV); reference cell order throughout
+int plain_jvp_batch(hg_ctx* ctx, const double* d_Q, const double* d_V, int64_t sV, const double* d_pdot, int64_t sP, double* d_out,
+                    double* d_out_dot, int64_t K) {
   PlainDev& p = ctx->pd;
   if (ctx->n_inletq > kMaxInlets) { ctx->err = "plain path supports at most 64 inlet-q boundaries"; return HG_ERR_ARG; }
+  if (K < 1 || K > 65535) { ctx->err = "plain_jvp: number of directions out of range"; return HG_ERR_ARG; }
   const size_t B = (size_t)std::max<int64_t>(ctx->B, 1);
-  if (p.gh_d.n != B) {
-    cudaError_t e = p.gh_d.alloc(B);
-    if (e == cudaSuccess) e = p.gqx_d.alloc(B);
-    if (e == cudaSuccess) e = p.gqy_d.alloc(B);
-    if (e == cudaSuccess) e = p.gxi_d.alloc(B);
+  if (p.gh_d.n < B * (size_t)K) {     // one copy of the ghost buffers per direction
+    cudaError_t e = p.gh_d.alloc(B * K);
+    if (e == cudaSuccess) e = p.gqx_d.alloc(B * K);
+    if (e == cudaSuccess) e = p.gqy_d.alloc(B * K);
+    if (e == cudaSuccess) e = p.gxi_d.alloc(B * K);
+    if (e == cudaSuccess) e = p.jgh.alloc(B * K);
+    if (e == cudaSuccess) e = p.jgqx.alloc(B * K);
+    if (e == cudaSuccess) e = p.jgqy.alloc(B * K);
+    if (e == cudaSuccess) e = p.jgxi.alloc(B * K);
     if (e != cudaSuccess) { ctx->err = std::string("plain_jvp: ") + cudaGetErrorString(e); return HG_ERR_CUDA; }
   }
   jvp::Args a;
@@ -144,20 +169,25 @@ int plain_jvp(hg_ctx* ctx, const double* d_Q, const double* d_V, const double* d
   a.inlet_ptr = p.inlet_ptr.p;
   a.bc_nx = p.bc_nx.p; a.bc_ny = p.bc_ny.p; a.bc_l53 = p.bc_l53.p; a.bc_l23 = p.bc_l23.p;
   a.hstill_g = p.hstill_g.p; a.zb_g = p.zb_g.p;
-  a.gh = p.gh.p; a.gqx = p.gqx.p; a.gqy = p.gqy.p; a.gxi = p.gxi.p;
+  a.gh = p.jgh.p; a.gqx = p.jgqx.p; a.gqy = p.jgqy.p; a.gxi = p.jgxi.p;
   a.gh_d = p.gh_d.p; a.gqx_d = p.gqx_d.p; a.gqy_d = p.gqy_d.p; a.gxi_d = p.gxi_d.p;
   a.Qin = p.Qin.p; a.wse = p.wse.p; a.Q = d_Q; a.V = d_V; a.params = p.params.p; a.pdot = d_pdot;
   a.dQ = d_out; a.dQ_d = d_out_dot; a.err = p.err.p;
+  const Batch b{sV, sP, (int64_t)B};
   if (ctx->B > 0) {
-    k_jvp_ghost<<<1, 256, 0, ctx->stream>>>(a);
+    k_jvp_ghost<<<dim3(1, (unsigned)K), 256, 0, ctx->stream>>>(a, b);
     ctx->launches++;
   }
   const int threads = 128;
-  k_jvp_cell<<<(unsigned)((ctx->N + threads - 1) / threads), threads, 0, ctx->stream>>>(a);
+  k_jvp_cell<<<dim3((unsigned)((ctx->N + threads - 1) / threads), (unsigned)K), threads, 0, ctx->stream>>>(a, b);
   ctx->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ctx->err = std::string("plain_jvp launch: ") + cudaGetErrorString(e); return HG_ERR_CUDA; }
   return HG_OK;
+}
+
+int plain_jvp(hg_ctx* ctx, const double* d_Q, const double* d_V, const double* d_pdot, double* d_out, double* d_out_dot) {
+  return plain_jvp_batch(ctx, d_Q, d_V, 0, d_pdot, 0, d_out, d_out_dot, 1);
 }
 
 }  // namespace hg
