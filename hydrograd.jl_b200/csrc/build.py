@@ -11,6 +11,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 SOURCES = [
     ("hg_host.cpp", ["-Xcompiler", "-fopenmp"]),     # the tile builder runs on all host cores
     ("hg_srh.cpp", []),
+    ("hg_partition.cpp", []),
     ("hg_results.cpp", []),
     ("hg_api.cu", []),
     ("hg_plain.cu", ["-fmad=false"]),      # reference evaluation order, no FMA contraction
@@ -32,7 +33,7 @@ def _newer(target, deps):
 def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    hdrs = [os.path.join(HERE, "hg_ctx.h"), os.path.join(HERE, "hg_device.cuh"), os.path.join(HERE, "hg_ude.h"), os.path.join(HERE, "hg_jvp_impl.h"), os.path.join(PKG, "..", "include", "hydrograd_b200.h"), __file__]
+    hdrs = [os.path.join(HERE, "hg_ctx.h"), os.path.join(HERE, "hg_device.cuh"), os.path.join(HERE, "hg_ude.h"), os.path.join(HERE, "hg_jvp_impl.h"), os.path.join(HERE, "hg_case.h"), os.path.join(PKG, "..", "include", "hydrograd_b200.h"), __file__]
     objs = []
     for src, extra in SOURCES:
         s = os.path.join(HERE, src)

@@ -26,13 +26,7 @@
 
 #include "../../include/hydrograd_b200.h"
 
-struct hg_case {
-  std::map<std::string, std::vector<double>> f64;
-  std::map<std::string, std::vector<int64_t>> i64;
-  std::map<std::string, std::vector<uint8_t>> u8;
-  int64_t dims[16] = {0};
-  std::string err;
-};
+#include "hg_case.h"
 
 namespace {
 constexpr int LD = 8;  // gMax_Nodes_per_Element

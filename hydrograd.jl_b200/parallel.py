@@ -25,7 +25,27 @@ def inlet_cell_groups(flat):
 
 
 def rcb_partition(cx, cy, P, keep_together=None):
-    """Recursive coordinate bisection: split the longer extent at the weighted median until P parts exist.
+    """Recursive coordinate bisection (hg_partition_rcb, csrc/hg_partition.cpp): split the longer extent at the weighted
+    median until P parts exist; `keep_together` = list of cell-id arrays (e.g. inlet_cell_groups(flat)) that are moved as a
+    whole to the rank owning most of them."""
+    import ctypes as C
+    from . import _lib as L
+    lib = L.load()
+    cx = np.ascontiguousarray(cx, dtype=np.float64)
+    cy = np.ascontiguousarray(cy, dtype=np.float64)
+    groups = [np.asarray(g, dtype=np.int64) for g in (keep_together or [])]
+    gptr = np.concatenate([[0], np.cumsum([g.size for g in groups])]).astype(np.int64)
+    gcells = np.ascontiguousarray(np.concatenate(groups) if groups else np.zeros(1, dtype=np.int64), dtype=np.int64)
+    part = np.zeros(cx.size, dtype=np.int32)
+    rc = lib.hg_partition_rcb(cx.size, cx.ctypes.data_as(L.c_f64p), cy.ctypes.data_as(L.c_f64p), int(P), len(groups),
+                              gptr.ctypes.data_as(L.c_i64p), gcells.ctypes.data_as(L.c_i64p), part.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc:
+        raise ValueError(f"hg_partition_rcb failed ({rc})")
+    return part
+
+
+def rcb_partition_reference(cx, cy, P, keep_together=None):
+    """numpy twin of hg_partition_rcb (tests compare the two): split the longer extent at the weighted median until P parts exist.
 
     `keep_together`: list of cell-id arrays (e.g. inlet_cell_groups(flat)); after the bisection every group is moved as a
     whole to the rank that already owns most of it (ties: the lowest rank).  An inlet is a few hundred cells, so the load
@@ -65,7 +85,64 @@ def _tables(flat):
 
 
 def extract_local(flat, part, rank, Q=None, gid=None):
-    """Rank-local flat mesh (index_base 0).  `gid` are the global cell ids of `flat`'s cells (default: identity);
+    """Rank-local flat mesh (index_base 0) through hg_partition_extract (csrc/hg_partition.cpp).  `gid` are the global cell ids
+    of `flat`'s cells (default: identity); they only define the canonical face orientation / ordering and must be consistent
+    across ranks.  Returns (local_flat, info); info = dict(own=global-row indices of the owned cells, neighbors=[rank...],
+    counts=[entries per neighbour], halo_cells, halo_remote, Q=local state)."""
+    import ctypes as C
+    from . import _lib as L
+    from .api import _descs
+    lib = L.load()
+    mesh, bc, fields, keep = _descs(flat)
+    part32 = np.ascontiguousarray(part, dtype=np.int32)
+    g = None if gid is None else np.ascontiguousarray(gid, dtype=np.int64)
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib.hg_partition_extract(C.byref(h), C.byref(mesh), C.byref(bc), C.byref(fields), part32.ctypes.data_as(C.POINTER(C.c_int32)),
+                                  int(rank), None if g is None else g.ctypes.data_as(L.c_i64p), err, 512)
+    if rc:
+        msg = err.value.decode()
+        raise (NotImplementedError if "split across ranks" in msg else ValueError)(msg)
+    try:
+        dims = np.zeros(16, dtype=np.int64)
+        lib.hg_case_dims(h, dims.ctypes.data_as(L.c_i64p))
+        dts = {0: (np.float64, C.c_double), 1: (np.int64, C.c_int64), 2: (np.uint8, C.c_uint8)}
+
+        def arr(name, default_dtype=np.float64):
+            ptr, cnt, dt = C.c_void_p(), C.c_int64(0), C.c_int32(0)
+            if lib.hg_case_array(h, name.encode(), C.byref(ptr), C.byref(cnt), C.byref(dt)):
+                return None
+            npt, ct = dts[dt.value]
+            if cnt.value == 0:
+                return np.zeros(0, dtype=npt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(cnt.value,)).astype(npt, copy=True)
+
+        loc = dict(n_cells=int(dims[0]), n_faces=int(dims[1]), n_ghost=int(dims[2]), ld=int(dims[3]), index_base=0,
+                   n_inletq=int(dims[5]), n_exith=int(dims[6]), n_wall=int(dims[7]), n_symm=int(dims[8]), n_mat=int(dims[9]),
+                   n_halo=int(dims[10]), g=flat["g"], k_n=flat["k_n"], h_small=flat["h_small"])
+        for name in ("cell_nfaces", "cell_faces", "cell_neighbors", "cell_normals", "face_is_boundary", "face_lengths", "cell_areas",
+                     "cell_centroids", "bc_ptr", "bc_ghost_ids", "bc_internal_cells", "bc_normals", "bc_lengths", "halo_flip",
+                     "halo_area", "hstill", "hstill_ghost", "zb_cells", "zb_ghost", "S0_cells", "ManningN_cells", "matID_cells",
+                     "inletQ_TotalQ", "exitH_WSE"):
+            loc[name] = arr(name)
+        for k in ("bc_lengths", "halo_flip", "halo_area", "hstill_ghost", "zb_ghost", "inletQ_TotalQ", "exitH_WSE"):
+            if loc[k] is None:
+                loc[k] = np.zeros(0, dtype=np.uint8 if k == "halo_flip" else np.float64)
+        info = dict(own=arr("own"), neighbors=[int(r) for r in arr("neighbors")], counts=[int(c) for c in arr("counts")],
+                    halo_remote=arr("halo_remote") if arr("halo_remote") is not None else np.zeros(0, dtype=np.int64),
+                    halo_cells=arr("halo_cells") if arr("halo_cells") is not None else np.zeros(0, dtype=np.int64))
+    finally:
+        lib.hg_case_free(h)
+    del keep
+    if Q is not None:
+        Q = np.asarray(Q)
+        N, own = int(flat["n_cells"]), info["own"]
+        info["Q"] = np.concatenate([Q[:N][own], Q[N:2 * N][own], Q[2 * N:][own]])
+    return loc, info
+
+
+def extract_local_reference(flat, part, rank, Q=None, gid=None):
+    """numpy twin of hg_partition_extract (tests compare the two).  Rank-local flat mesh (index_base 0).  `gid` are the global cell ids of `flat`'s cells (default: identity);
     they only define the canonical face orientation / ordering and must be consistent across ranks.
 
     Returns (local_flat, info); info = dict(own=global-row indices of the owned cells, neighbors=[rank...],

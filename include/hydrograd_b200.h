@@ -406,6 +406,22 @@ HG_API void hg_case_free(hg_case* c);
 HG_API int hg_case_dims(const hg_case* c, int64_t* dims /* [16] */);
 HG_API int hg_case_array(const hg_case* c, const char* name, const void** ptr, int64_t* count, int32_t* dtype /* 0 f64, 1 i64, 2 u8 */);
 
+/* ---- domain decomposition for multi-GPU runs, host only (csrc/hg_partition.cpp; no counterpart in the reference, which is a
+ * single serial process).  hg_partition_rcb: recursive coordinate bisection of the centroids into P parts; cell groups
+ * (group_ptr [n_groups+1] into group_cells, 0-based ids; e.g. the cells of each inlet-q boundary) are moved as a whole to the
+ * rank owning most of them.  hg_partition_extract: the rank-local mesh of `rank` as an hg_case (free with hg_case_free) whose
+ * arrays carry the names of the descriptor fields they feed -- cell_nfaces cell_faces cell_neighbors bc_ptr bc_ghost_ids
+ * bc_internal_cells matID_cells (int64), cell_normals face_lengths cell_areas cell_centroids bc_normals bc_lengths halo_area
+ * hstill hstill_ghost zb_cells zb_ghost S0_cells ManningN_cells inletQ_TotalQ exitH_WSE (float64), face_is_boundary halo_flip
+ * (uint8), 0-based ids -- plus own (global ids of the owned cells), neighbors (ranks, = halo boundaries in order), counts
+ * (entries per neighbour), halo_cells (local cell of every halo entry), halo_remote (global id of its remote cell).
+ * dims = {N, F, B, ld, index_base, n_inletq, n_exith, n_wall, n_symm, n_mat, n_halo, n_halo_entries}.  `gid` (optional) are the
+ * global ids of the input cells when the input is itself a piece of a larger mesh.                                     */
+HG_API int hg_partition_rcb(int64_t n_cells, const double* cx, const double* cy, int32_t n_parts, int64_t n_groups,
+                            const int64_t* group_ptr, const int64_t* group_cells, int32_t* part /* [n_cells] out */);
+HG_API int hg_partition_extract(hg_case** out, const hg_mesh_desc* mesh, const hg_bc_desc* bc, const hg_fields_desc* fields,
+                                const int32_t* part, int32_t rank, const int64_t* gid, char* err, int64_t errlen);
+
 /* ---- results writers and the derived fields of the forward driver, host only (csrc/hg_results.cpp): the output side
  * of the path.  Replaces, for callers without the Julia package, postprocess_forward_simulation_results_swe_2D
  * (applications/forward_simulation/process_forward_simulation_results_2D.jl:4-86), swe_2D_save_results_SciML and

@@ -202,3 +202,40 @@ def test_cut_slot_is_not_confused_with_a_colliding_ghost_id():
     n_phys = loc["n_ghost"] - sum(info["counts"])
     assert ln[jb, lc] < n_phys <= ln[ji, lc]                  # physical ghost kept, halo ghost in the cut slot
     assert hg.plan_stats(loc, tile_cells=128)["n_tiles"] >= 1
+
+
+@pytest.mark.parametrize("case", ["dam", "river_inlet", "river_slab_gid"])
+def test_native_partitioner_matches_the_numpy_twin(case):
+    """hg_partition_rcb / hg_partition_extract (C++, what a non-Python host calls) against the numpy statements of the same
+    rules: identical parts, identical local tables (ids, orders, flip flags, fields), for RCB with kept-together inlets, for
+    slabs, and with explicit global ids."""
+    if case == "dam":
+        flat, Q0 = S.dam_break(40); Pn = 4
+    else:
+        flat, Q0 = S.river(60, 48); Pn = 3 if case == "river_slab_gid" else 4
+    N = flat["n_cells"]
+    cx, cy = flat["cell_centroids"][:N], flat["cell_centroids"][N:]
+    groups = P.inlet_cell_groups(flat)
+    gid = None
+    if case == "river_slab_gid":
+        part = (np.arange(N) * Pn // N).astype(np.int32)
+        gid = np.random.default_rng(1).permutation(N).astype(np.int64) + 5     # any injective map is a valid set of global ids
+    else:
+        part = P.rcb_partition(cx, cy, Pn, keep_together=groups)
+        ref = P.rcb_partition_reference(cx, cy, Pn, keep_together=groups)
+        assert np.array_equal(part, ref)
+        for Pk in (2, 3, 5, 8):
+            assert np.array_equal(P.rcb_partition(cx, cy, Pk), P.rcb_partition_reference(cx, cy, Pk)), Pk
+    for r in range(Pn):
+        a, ia = P.extract_local(flat, part, r, Q0, gid=gid)
+        b, ib = P.extract_local_reference(flat, part, r, Q0, gid=gid)
+        for k in b:
+            if b[k] is None:
+                assert a.get(k) is None or np.size(a[k]) == 0, k
+            elif isinstance(b[k], np.ndarray):
+                assert np.array_equal(np.asarray(a[k]), b[k]), (k, r)
+            else:
+                assert a[k] == b[k], (k, r)
+        for k in ("own", "halo_remote", "halo_cells", "Q"):
+            assert np.array_equal(ia[k], ib[k]), (k, r)
+        assert ia["neighbors"] == ib["neighbors"] and ia["counts"] == ib["counts"]
