@@ -114,7 +114,7 @@ SYMBOLS = {
     "hg_ensemble_get_member": (C.c_int, [_vp, C.c_int64, C.c_int32, c_f64p]),
     "hg_time_ensemble": (C.c_int, [_vp, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "hg_partition_rcb": (C.c_int, [C.c_int64, c_f64p, c_f64p, C.c_int32, C.c_int64, c_i64p, c_i64p, C.POINTER(C.c_int32)]),
-    "hg_partition_extract": (C.c_int, [C.POINTER(_vp), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, c_i64p,
+    "hg_partition_extract": (C.c_int, [C.POINTER(_vp), C.POINTER(MeshDesc), C.POINTER(BcDesc), C.POINTER(FieldsDesc), C.POINTER(C.c_int32), C.c_int32, c_i64p,
                                        C.c_char_p, C.c_int64]),
     "hg_case_load_srh2d": (C.c_int, [C.POINTER(_vp), C.c_char_p, C.c_char_p, C.c_int64]),
     "hg_case_free": (None, [_vp]),
