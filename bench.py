@@ -482,8 +482,10 @@ def main():
         pz = p_zones[:len(p_zones)]
         pbar_host = np.zeros(pz.size)
 
+        host_api = world == 1 or sl.transport == "ipc"    # hg_rhs / hg_rhs_vjp with host pointers: the three-stream pipeline
+
         def e2e_rhs():
-            if world == 1:
+            if host_api:
                 ctx.rhs(hQ.numpy(), pz, "ManningN", out=out)
             else:
                 ctx.set_state(hQ.numpy())
@@ -491,7 +493,7 @@ def main():
                 ctx.get_rhs(out=out)
 
         def e2e_vjp():
-            if world == 1:
+            if host_api:
                 ctx.rhs_vjp_into(hQ.numpy(), hL.numpy(), outb, pz, "ManningN", pbar_host)
             else:
                 ctx.set_state(hQ.numpy())
@@ -520,8 +522,10 @@ def main():
                                     "vjp_h2d": 48 * N / e2e_vjp_s / 1e9, "vjp_d2h": 24 * N / e2e_vjp_s / 1e9,
                                     "note": "bytes of each direction over the whole call time (the directions overlap at N = 1)"},
                "what": ("one RHS + one VJP through pinned host buffers (hg_rhs: H2D state, kernel, D2H dQdt; hg_rhs_vjp: H2D state "
-                        "and lambda, kernel, D2H Qbar), chunked over three streams") if world == 1 else
-                       "per rank: hg_set_state (H2D) -> halo push + tile kernel -> hg_get_rhs / hg_get_vjp (D2H); all ranks share one host's PCIe / pinned memory"}
+                        "and lambda, kernel, D2H Qbar), chunked over three streams" +
+                        ("; per rank, the cut cells are pushed to the neighbours once the last chunk has landed; all ranks share one host's PCIe / pinned memory" if world > 1 else ""))
+                       if host_api else
+                       "per rank: hg_set_state (H2D) -> pack + NCCL send/recv + tile kernel -> hg_get_rhs / hg_get_vjp (D2H); all ranks share one host's PCIe / pinned memory"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -526,8 +526,10 @@ static int rhs_pipelined(hg_ctx* ctx, const double* Q, double* dQdt) {
     const int64_t r0 = s * csz, r1 = std::min<int64_t>(N, r0 + csz);
     CK(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[s], 0));
     TRY(hg::fused_permute_range(ctx, true, d.stage.p, d.Q.p, r0, r1));
+    const bool band = s == K - 1 && hg_comm_ready(ctx);   // multi-rank: the whole state has landed -- push the cut cells, the last stage holds the band
+    if (band) { TRY(hg::comm_push(ctx, d.Q.p, nullptr)); ctx->comm->pushed = false; }
     if (s == K - 1 && ctx->n_inletq > 0) hg::fused_inlet_coef(ctx, d.Q.p);
-    TRY(hg::fused_rhs_tiles(ctx, d.Q.p, d.dQ.p, fh.stage_ptr[s], fh.stage_ptr[s + 1] - fh.stage_ptr[s]));
+    TRY(hg::fused_rhs_tiles(ctx, d.Q.p, d.dQ.p, fh.stage_ptr[s], fh.stage_ptr[s + 1] - fh.stage_ptr[s], band));
     for (int c = 0; c < K; ++c) {
       if (fh.chunk_done[c] != s) continue;
       const int64_t q0 = c * csz, q1 = std::min<int64_t>(N, q0 + csz);
@@ -550,7 +552,7 @@ int hg_rhs(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
   // (the UDE network may need whole-array statistics of the state before any tile can run: no chunked pipeline)
-  if (ctx->opt.path != 1 && ctx->fh.n_chunks > 1 && ctx->n_halo == 0 && ctx->active != HG_PARAM_UDE) return rhs_pipelined(ctx, Q, dQdt);
+  if (ctx->opt.path != 1 && ctx->fh.n_chunks > 1 && (ctx->n_halo == 0 || hg_comm_ready(ctx)) && ctx->active != HG_PARAM_UDE) return rhs_pipelined(ctx, Q, dQdt);
   TRY(hg_set_state(ctx, Q));
   TRY(hg_rhs_resident(ctx));
   return hg_get_rhs(ctx, dQdt);
@@ -591,8 +593,10 @@ static int vjp_pipelined(hg_ctx* ctx, const double* Q, const double* lambda, dou
     CK(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[s], 0));
     TRY(hg::fused_permute_range(ctx, true, d.stage.p, d.Q.p, r0, r1));
     TRY(hg::fused_permute_range(ctx, true, d.stage_lam.p, d.lam.p, r0, r1));
+    const bool band = s == K - 1 && hg_comm_ready(ctx);
+    if (band) { TRY(hg::comm_push(ctx, d.Q.p, d.lam.p)); ctx->comm->pushed = false; }
     if (s == K - 1 && ctx->n_inletq > 0) hg::fused_inlet_coef(ctx, d.Q.p);
-    TRY(hg::fused_vjp_tiles(ctx, cfg, d.Q.p, d.lam.p, d.Qbar.p, d.tile_order.p, fh.stage_ptr[s], fh.stage_ptr[s + 1] - fh.stage_ptr[s]));
+    TRY(hg::fused_vjp_tiles(ctx, cfg, d.Q.p, d.lam.p, d.Qbar.p, d.tile_order.p, fh.stage_ptr[s], fh.stage_ptr[s + 1] - fh.stage_ptr[s], band ? 2 : 0));
     if (s == K - 1) TRY(hg::fused_vjp_finish(ctx, d.Q.p, d.Qbar.p));
     for (int c = 0; c < K; ++c) {
       if (fh.chunk_done[c] != s) continue;
@@ -620,7 +624,7 @@ int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   TRY(bind_params(ctx, params, np, active));
   if (ctx->active != HG_PARAM_NONE && !pbar) { ctx->err = "hg_rhs_vjp: pbar is NULL"; return HG_ERR_ARG; }
   hg::FusedDev& d = ctx->fd;
-  if (ctx->fh.n_chunks > 1 && ctx->n_halo == 0 && ctx->active != HG_PARAM_UDE) {
+  if (ctx->fh.n_chunks > 1 && (ctx->n_halo == 0 || hg_comm_ready(ctx)) && ctx->active != HG_PARAM_UDE) {
     TRY(vjp_pipelined(ctx, Q, lambda, Qbar));
   } else {
     TRY(hg_set_state(ctx, Q));

@@ -282,7 +282,7 @@ int sens_err_norm(hg_ctx* ctx, int64_t n3, int rows, const double* u, const doub
                   const double* coef, double abstol, double reltol, double* d_part, double* d_sum);
 // fused path launchers (hg_fused.cu)
 int fused_rhs(hg_ctx* ctx, const double* d_Q, double* d_out, bool euler, double dt);
-int fused_rhs_tiles(hg_ctx* ctx, const double* d_Q, double* d_out, int32_t tile_base, int32_t n_tiles);
+int fused_rhs_tiles(hg_ctx* ctx, const double* d_Q, double* d_out, int32_t tile_base, int32_t n_tiles, bool with_band = false);
 int fused_rhs_phase(hg_ctx* ctx, const double* d_Q, double* d_out, int phase);
 int fused_permute_range(hg_ctx* ctx, bool to_internal, const double* src, double* dst, int64_t r0, int64_t r1);
 int fused_smem_bytes(const hg_ctx* ctx);
@@ -297,7 +297,7 @@ void fused_inlet_coef(hg_ctx* ctx, const double* d_Q);
 int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);
 int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar, const int32_t* tile_order,
-                    int32_t tile_base, int32_t n_run, bool use_comm = false, bool pdl = false);
+                    int32_t tile_base, int32_t n_run, int comm_mode = 0, bool pdl = false);
 int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar);
 int fused_nbar_to_ref(hg_ctx* ctx, double* d_dst);
 int fused_halo_pack(hg_ctx* ctx, bool with_lambda);

@@ -589,9 +589,10 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
       int32_t st = 0;
       for (int32_t c = d[0]; c < d[0] + d[1]; ++c) st = std::max(st, (int32_t)(fh.perm[c] / csz));
       for (int32_t q = d[2]; q < d[2] + d[3]; ++q) st = std::max(st, (int32_t)(fh.perm[fh.halo[q]] / csz));
-      // tiles with inlet-q faces wait for the boundary-wide conveyance sum, i.e. for the last chunk
+      // tiles with inlet-q faces wait for the boundary-wide conveyance sum, i.e. for the last chunk; so do the tiles with halo
+      // faces (multi-rank contexts: the neighbours push their cut cells once their own last chunk has landed)
       for (int32_t q = 0; q < d[5] - d[9]; ++q)
-        if (ctx->bch.type[fh.bface_e[d[10] + q]] == BC_INLETQ) st = K - 1;
+        if (ctx->bch.type[fh.bface_e[d[10] + q]] == BC_INLETQ || ctx->bch.type[fh.bface_e[d[10] + q]] == BC_HALO) st = K - 1;
       tstage[t] = st;
     }
     fh.tile_order.resize(fh.n_tiles);

@@ -932,7 +932,7 @@ int fused_vjp_prepare(hg_ctx* ctx, int cfg_id) {
 // The tile kernel over the tiles tile_order[tile_base .. tile_base + n_run) (tile_order NULL: all tiles, identity).
 // The inlet coefficients must be current (fused_inlet_coef).
 int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar, const int32_t* tile_order,
-                    int32_t tile_base, int32_t n_run, bool use_comm, bool pdl) {
+                    int32_t tile_base, int32_t n_run, int comm_mode, bool pdl) {
   FusedDev& d = ctx->fd;
   const FusedHost& fh = ctx->fh;
   if (n_run == 0) return HG_OK;
@@ -948,12 +948,16 @@ int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_
   a.wse = d.wse.p; a.Q = d_Q; a.lam = d_lam; a.Qbar = d_Qbar; a.nbar = d.nbar.p; a.s0bar = d.s0bar.p;
   a.ent_c = d.ent_c.p; a.ent_n = d.ent_n.p; a.ent_z = d.ent_z.p;
   a.tile_order = tile_order; a.tile_base = tile_base;
-  if (use_comm) {   // library-owned exchange (see launch_rhs)
+  if (comm_mode) {   // library-owned exchange (see launch_rhs): 1 = the whole mesh in one launch, 2 = a pipeline stage with the band
     const hg_comm* cm = ctx->comm;
-    a.tile_order = d.comm_order.p; a.tile_base = 0; n_run = fh.n_tiles;
     a.halo_recv = cm->recv[cm->epoch & 1];
     a.cw.flags = cm->flags; a.cw.epoch = cm->epoch; a.cw.n = cm->n; a.cw.err = d.err.p;
-    a.cw.from = fh.comm_band0; a.cw.to = fh.comm_band0 + (fh.n_tiles - fh.n_interior_tiles);
+    if (comm_mode == 1) {
+      a.tile_order = d.comm_order.p; a.tile_base = 0; n_run = fh.n_tiles;
+      a.cw.from = fh.comm_band0; a.cw.to = fh.comm_band0 + (fh.n_tiles - fh.n_interior_tiles);
+    } else {
+      a.cw.from = 0; a.cw.to = n_run >= 0 ? n_run : fh.n_tiles;
+    }
   }
   const unsigned grid = (unsigned)(n_run >= 0 ? n_run : fh.n_tiles);
   a.n_run = (int32_t)grid;
@@ -1045,7 +1049,7 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
     const int rc0 = ude_eval_n(ctx, d_Q);
     if (rc0 != HG_OK) return rc0;
   }
-  bool use_comm = false;
+  int use_comm = 0;
   if (hg_comm_ready(ctx)) {   // the adjoint of a cut face needs the remote cell's state AND cotangent
     hg_comm* cm = ctx->comm;
     if (cm->auto_exchange) {
@@ -1056,7 +1060,7 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
       return HG_ERR_STATE;
     }
     cm->pushed = false;
-    use_comm = true;
+    use_comm = 1;
   }
   const bool pdl = ctx->n_inletq > 0;   // the conveyance sum last: the tile kernel is its programmatic dependent
   if (pdl) fused_inlet_coef(ctx, d_Q);

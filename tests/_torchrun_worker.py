@@ -53,6 +53,27 @@ def main():
         out["ipc_euler_bitwise"] = bool(np.array_equal(ctx.get_state(), pick(ref_Q5)))
         dist.barrier()
         ctx.comm_disconnect()
+        # ---- host-buffer calls on a mesh large enough for the three-stream pipeline (>= 1M cells per rank): hg_rhs / hg_rhs_vjp
+        # push the cut cells once the last chunk has landed; the band tiles run in the last stage
+        bflat, bQ = S.river(2100, 1000)
+        bN = bflat["n_cells"]
+        bpart = (np.arange(bN) * world // bN).astype(np.int32)
+        blam = np.random.default_rng(5).standard_normal(3 * bN)
+        big = hg.Context(bflat, device=dev)
+        bref = big.rhs(bQ)
+        bbar, _ = big.rhs_vjp(bQ, blam)
+        del big
+        bloc, binfo = P.extract_local(bflat, bpart, rank, bQ)
+        bown = binfo["own"]
+        bpick = lambda v: np.concatenate([v[k * bN + bown] for k in range(3)])
+        bctx = hg.Context(bloc, device=dev)
+        P.connect_ranks(bctx, binfo)
+        out["pipe_rhs_bitwise"] = bool(np.array_equal(bctx.rhs(binfo["Q"]), bpick(bref)))
+        got_bar, _ = bctx.rhs_vjp(binfo["Q"], bpick(blam))
+        out["pipe_vjp_err"] = float(np.abs(got_bar - bpick(bbar)).max() / np.abs(bbar).max())
+        dist.barrier()
+        bctx.comm_disconnect()
+        del bctx
         # ---- NCCL send/recv path (needs one GPU per rank)
         if one_gpu_each:
             ctx2 = hg.Context(loc, device=dev, tile_cells=128)
@@ -68,7 +89,8 @@ def main():
     except Exception as e:  # noqa: BLE001
         out["ok"] = False
         out["error"] = repr(e)
-    print("WORKER " + json.dumps(out), flush=True)
+    with open(os.path.join(os.environ["HG_WORKER_OUT"], f"rank{rank}.json"), "w") as fh:   # (stdout of the ranks interleaves)
+        json.dump(out, fh)
     dist.barrier()
     dist.destroy_process_group()
 

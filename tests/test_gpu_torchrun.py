@@ -13,18 +13,19 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_ranks_match_single_context():
+def test_two_ranks_match_single_context(tmp_path):
     port = 29600 + (os.getpid() % 300)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "_torchrun_worker.py")]
-    env = dict(os.environ, OMP_NUM_THREADS="4")
+    env = dict(os.environ, OMP_NUM_THREADS="4", HG_WORKER_OUT=str(tmp_path))
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
-    res = [json.loads(l.split("WORKER ", 1)[1]) for l in r.stdout.splitlines() if "WORKER " in l]
+    res = [json.load(open(tmp_path / f)) for f in sorted(os.listdir(tmp_path)) if f.startswith("rank")]
     assert r.returncode == 0 and len(res) == 2, r.stdout[-2000:] + r.stderr[-3000:]
     print(res)
     for o in res:
         assert o["ok"], o
         assert o["ipc_rhs_bitwise"] and o["ipc_euler_bitwise"], o
         assert o["ipc_vjp_err"] <= 1e-13, o
+        assert o["pipe_rhs_bitwise"] and o["pipe_vjp_err"] <= 1e-13, o
         if o["one_gpu_each"]:
             assert o["nccl_rhs_bitwise"] and o["nccl_vjp_err"] <= 1e-13, o
