@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(512) k_comm_push(int32_t e0, int64_t Ns, const
                                                    const int32_t* __restrict__ ptr, const double* __restrict__ Q,
                                                    const double* __restrict__ lam, double* const* __restrict__ dst,
                                                    unsigned long long* const* __restrict__ flag, unsigned long long epoch) {
+  dev::pdl_launch_dependents();   // the consumer kernel (a programmatic dependent) may start: it needs the PEERS' pushes, not this one
   const int k = blockIdx.x;
   const int32_t p0 = ptr[k], n = ptr[k + 1] - p0;
   double* out = dst[k];

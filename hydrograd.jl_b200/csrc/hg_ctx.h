@@ -292,7 +292,7 @@ int fused_permute(hg_ctx* ctx, bool to_internal, const double* src, double* dst)
 int fused_bind_manning(hg_ctx* ctx, const double* d_params);
 int fused_bind_zb(hg_ctx* ctx, const double* d_params_ref);
 int fused_cfg_id(const hg_ctx* ctx);
-void fused_inlet_coef(hg_ctx* ctx, const double* d_Q);
+void fused_inlet_coef(hg_ctx* ctx, const double* d_Q, bool after_push = false);
 // fused VJP (hg_vjp.cu)
 int fused_vjp_prepare(hg_ctx* ctx, int cfg_id);
 int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, double* d_Qbar);

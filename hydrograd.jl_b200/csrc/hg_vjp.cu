@@ -1062,8 +1062,9 @@ int fused_vjp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_lam, d
     cm->pushed = false;
     use_comm = 1;
   }
-  const bool pdl = ctx->n_inletq > 0;   // the conveyance sum last: the tile kernel is its programmatic dependent
-  if (pdl) fused_inlet_coef(ctx, d_Q);
+  // the conveyance sum last: the tile kernel is its (or the halo push's) programmatic dependent
+  const bool pdl = ctx->n_inletq > 0 || use_comm == 1;
+  if (ctx->n_inletq > 0) fused_inlet_coef(ctx, d_Q, use_comm == 1 && ctx->comm->auto_exchange);
   const int rc = fused_vjp_tiles(ctx, cfg_id, d_Q, d_lam, d_Qbar, nullptr, 0, -1, use_comm, pdl);
   return rc != HG_OK ? rc : fused_vjp_finish(ctx, d_Q, d_Qbar);
 }
