@@ -277,6 +277,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     hg::FusedHost& fh = ctx->fh;
     hg::FusedDev& d = ctx->fd;
     const size_t Ns = (size_t)fh.Ns;
+    hg::StageTimer up_timer("device tables (alloc+H2D)");
     TRY(up(ctx, d.perm, fh.perm)); TRY(up(ctx, d.iperm, fh.iperm)); TRY(up(ctx, d.tile_desc, fh.tile_desc));
     TRY(up(ctx, d.halo, fh.halo)); TRY(up(ctx, d.bface_e, fh.bface_e));
     TRY(up(ctx, d.face_lr, fh.face_lr)); TRY(up(ctx, d.cf_idx, fh.cf_idx));
@@ -325,6 +326,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
       TRY(up(ctx, d.bcell_ptr, h.bcell_ptr)); TRY(up(ctx, d.bcell_ent, h.bcell_ent));
     }
     // the plain CSR in reference order is kept for update_bed_data when zb is the active parameter
+    hg::StageTimer csr_timer("plain CSR (alloc+H2D)");
     hg::PlainDev& p = ctx->pd;
     TRY(up(ctx, p.cf_ptr, cf_ptr)); TRY(up(ctx, p.cf_nb, cf_nb));
     TRY(up(ctx, p.cf_nx, cf_nx)); TRY(up(ctx, p.cf_ny, cf_ny)); TRY(up(ctx, p.cf_len, cf_len));

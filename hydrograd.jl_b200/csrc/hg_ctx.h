@@ -3,8 +3,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -12,6 +14,17 @@
 #include "hg_ude.h"
 
 namespace hg {
+
+// HG_DEBUG_TIMING=1: wall time of the host-side preprocessing stages on stderr
+struct StageTimer {
+  const char* what;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit StageTimer(const char* w) : what(w) {}
+  ~StageTimer() {
+    if (getenv("HG_DEBUG_TIMING"))
+      fprintf(stderr, "[hg] %-28s %8.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
 
 constexpr double EPS = 2.220446049250313e-16;  // eps(Float64) of utilities/smooth_functions.jl
 

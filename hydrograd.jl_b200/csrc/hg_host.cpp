@@ -7,7 +7,6 @@
 // This replaces the per-call Dict / Vector-of-Vector lookups of compute_inviscid_fluxes
 // (semi_discretize_swe_2D.jl:286-330) with one O(N log N) preprocessing step at hg_create.
 #include <algorithm>
-#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -25,17 +24,6 @@ namespace hg {
     (ctx)->err = _b;                                  \
     return (code);                                    \
   } while (0)
-
-// HG_DEBUG_TIMING=1: wall time of the host-side preprocessing stages on stderr
-struct StageTimer {
-  const char* what;
-  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  explicit StageTimer(const char* w) : what(w) {}
-  ~StageTimer() {
-    if (getenv("HG_DEBUG_TIMING"))
-      fprintf(stderr, "[hg] %-28s %8.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-  }
-};
 
 int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f,
                std::vector<int32_t>& cf_ptr, std::vector<int32_t>& cf_nb, std::vector<double>& cf_nx,
@@ -169,15 +157,23 @@ int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg
   // ---- per cell-face: where the same face sits in the neighbour's list (transposed Green-Gauss of the VJP)
   h.cf_rev.assign(S, -1);
   {
-    std::vector<int32_t> first(F, -1);
-    for (int64_t k = 0; k < S; ++k) {
-      if (cf_nb[k] >= N) continue;
-      const int32_t fid = cf_face[k];
-      if (first[fid] < 0) first[fid] = (int32_t)k;
-      else { h.cf_rev[k] = first[fid]; h.cf_rev[first[fid]] = (int32_t)k; }
-    }
-    for (int64_t k = 0; k < S; ++k)
-      if (cf_nb[k] < N && h.cf_rev[k] < 0) HG_FAIL(ctx, HG_ERR_ARG, "interior face %d is listed by one cell only", cf_face[k]);
+    // for every interior cell-face: the position of the same face in the neighbour's list (scan of <= ld entries), in parallel
+    int64_t bad = -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i)
+      for (int32_t k = cf_ptr[i]; k < cf_ptr[i + 1]; ++k) {
+        const int32_t nb = cf_nb[k];
+        if (nb >= N) continue;
+        int32_t kk = -1;
+        for (int32_t q = cf_ptr[nb]; q < cf_ptr[nb + 1]; ++q)
+          if (cf_face[q] == cf_face[k] && cf_nb[q] == (int32_t)i) { kk = q; break; }
+        if (kk < 0) {
+#pragma omp critical(hg_cfrev_fail)
+          if (bad < 0 || k < bad) bad = k;
+        }
+        h.cf_rev[k] = kk;
+      }
+    if (bad >= 0) HG_FAIL(ctx, HG_ERR_ARG, "interior face %d is listed by one cell only", cf_face[bad]);
   }
   // ---- distinct boundary-adjacent cells -> their boundary entries (deterministic scatter of BC adjoints)
   {
