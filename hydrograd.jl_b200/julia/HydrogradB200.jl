@@ -60,6 +60,11 @@ mutable struct Context
     handle::Ptr{Cvoid}
     N::Int
     active::Int32
+    function Context(h::Ptr{Cvoid}, N::Int, active::Int32)
+        ctx = new(h, N, active)
+        finalizer(c -> (c.handle != C_NULL && ccall((:hg_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle); c.handle = C_NULL), ctx)
+        return ctx
+    end
     function Context(p_extra; device::Integer=0, tile_cells::Integer=512, strict::Bool=false)
         h = _create(p_extra, Int32(device), Int32(tile_cells), strict)
         ctx = new(h, p_extra.my_mesh_2D.numOfCells, HG_PARAM[p_extra.active_param_name])
@@ -68,12 +73,27 @@ mutable struct Context
     end
 end
 
+# a context around an already created handle (multi-GPU rank contexts)
+_wrap(h::Ptr{Cvoid}, N::Int, active::Int32) = Context(h, N, active)
+
 _err(h) = unsafe_string(ccall((:hg_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
 _check(rc, h) = rc == 0 ? nothing : error("hydrograd_b200 error $rc: " * _err(h))
 
 # Flatten mesh_2D / BoundaryConditions2D / SWE2D_Extra_Parameters (no copies of the big matrices that
 # are already dense: cellFacesList, cellNodesCount, face_lengths, cell_areas, cell_centroids, S0_cells).
 function _create(px, device::Int32, tile::Int32, strict::Bool)
+    handle = Ref{Ptr{Cvoid}}(C_NULL)
+    _with_descs(px) do mesh, bcd, fld
+        opt = Ref(Options(device, tile, Int32(1), Int32(strict), Int32(0), ntuple(_ -> Int32(0), 11)))
+        rc = ccall((:hg_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{MeshDesc}, Ref{BcDesc}, Ref{FieldsDesc}, Ref{Options}),
+                   handle, Ref(mesh), Ref(bcd), Ref(fld), opt)
+        _check(rc, C_NULL)
+    end
+    return handle[]
+end
+
+# f(mesh::MeshDesc, bc::BcDesc, fields::FieldsDesc) is called while every array the descriptors point at is kept alive
+function _with_descs(f, px)
     m  = px.my_mesh_2D
     bc = px.boundary_conditions
     N, ld = m.numOfCells, size(m.cellFacesList, 2)
@@ -115,7 +135,6 @@ function _create(px, device::Int32, tile::Int32, strict::Bool)
     nmat = length(px.srh_all_Dict["srhhydro_ManningsN"])
     c = px.swe_2D_constants
     solver = c.RiemannSolver
-    handle = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve neigh normals isb ptr gh ic bnorm len cellfaces nfaces flen areas cent S0 matid solver px begin
         mesh = MeshDesc(N, m.numOfFaces, m.numOfAllBounaryFaces, ld, Int32(1), pointer(nfaces), pointer(cellfaces),
                         pointer(neigh), pointer(normals), pointer(isb), pointer(flen), pointer(areas), pointer(cent))
@@ -125,12 +144,114 @@ function _create(px, device::Int32, tile::Int32, strict::Bool)
                          pointer(px.hstill), pointer(px.hstill_ghostCells), pointer(px.zb_cells), pointer(px.zb_ghostCells),
                          pointer(S0), pointer(px.ManningN_cells), pointer(matid), nmat,
                          pointer(px.inletQ_TotalQ), pointer(px.exitH_WSE))
-        opt = Ref(Options(device, tile, Int32(1), Int32(strict), Int32(0), ntuple(_ -> Int32(0), 11)))
-        rc = ccall((:hg_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{MeshDesc}, Ref{BcDesc}, Ref{FieldsDesc}, Ref{Options}),
-                   handle, Ref(mesh), Ref(bcd), Ref(fld), opt)
-        _check(rc, C_NULL)
+        return f(mesh, bcd, fld)
     end
-    return handle[]
+end
+
+# ---------------------------------------------------------------- multi-GPU: one host process, one context per device
+# Partition (recursive coordinate bisection, every inlet-q boundary kept on one rank), rank-local meshes with halo
+# boundaries, one context per device, contexts connected through the library's own NVLink transport (hg_comm_*): after
+# that every resident call (set_state / step_euler / rhs_resident ...) on the rank contexts exchanges its halo on the device.
+# No counterpart in the reference (a single serial process); nothing here needs Python or NCCL.
+mutable struct MultiContext
+    ctxs::Vector{Context}
+    own::Vector{Vector{Int64}}          # 1-based global ids of every rank's cells, in the rank's local order
+    neighbors::Vector{Vector{Int64}}    # ranks (0-based) behind the halo boundaries of every rank, in order
+    counts::Vector{Vector{Int64}}       # entries per halo boundary
+end
+
+function _case_array(cs::Ptr{Cvoid}, name::String)
+    ptr = Ref{Ptr{Cvoid}}(C_NULL); cnt = Ref{Int64}(0); dt = Ref{Int32}(0)
+    rc = ccall((:hg_case_array, LIB), Cint, (Ptr{Cvoid}, Cstring, Ref{Ptr{Cvoid}}, Ref{Int64}, Ref{Int32}), cs, name, ptr, cnt, dt)
+    rc == 0 || return nothing
+    T = dt[] == 0 ? Float64 : dt[] == 1 ? Int64 : UInt8
+    return cnt[] == 0 ? T[] : copy(unsafe_wrap(Array, Ptr{T}(ptr[]), cnt[]))
+end
+
+function MultiContext(p_extra; device_ids::Vector{<:Integer}, tile_cells::Integer=256)
+    P = length(device_ids)
+    m, bc = p_extra.my_mesh_2D, p_extra.boundary_conditions
+    N = m.numOfCells
+    cx, cy = Vector{Float64}(m.cell_centroids[:, 1]), Vector{Float64}(m.cell_centroids[:, 2])
+    groups = [unique(Int64.(bc.inletQ_internalCellIDs[k]) .- 1) for k in 1:bc.nInletQ_BCs]     # 0-based cell ids
+    gptr = Int64[0; cumsum(length.(groups))]; gcells = isempty(groups) ? Int64[0] : vcat(groups...)
+    part = Vector{Int32}(undef, N)
+    _check(ccall((:hg_partition_rcb, LIB), Cint, (Int64, Ptr{Float64}, Ptr{Float64}, Int32, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}),
+                 N, cx, cy, Int32(P), length(groups), gptr, gcells, part), C_NULL)
+    ctxs = Context[]; own = Vector{Int64}[]; nbs = Vector{Int64}[]; cnts = Vector{Int64}[]
+    _with_descs(p_extra) do mesh, bcd, fld
+        for r in 0:P-1
+            cs = Ref{Ptr{Cvoid}}(C_NULL); err = zeros(UInt8, 512)
+            rc = ccall((:hg_partition_extract, LIB), Cint,
+                       (Ref{Ptr{Cvoid}}, Ref{MeshDesc}, Ref{BcDesc}, Ref{FieldsDesc}, Ptr{Int32}, Int32, Ptr{Int64}, Ptr{UInt8}, Int64),
+                       cs, Ref(mesh), Ref(bcd), Ref(fld), part, Int32(r), C_NULL, err, 512)
+            rc == 0 || error("hg_partition_extract: " * unsafe_string(pointer(err)))
+            A = Dict(k => _case_array(cs[], k) for k in ("cell_nfaces", "cell_faces", "cell_neighbors", "cell_normals", "face_is_boundary",
+                     "face_lengths", "cell_areas", "cell_centroids", "bc_ptr", "bc_ghost_ids", "bc_internal_cells", "bc_normals", "bc_lengths",
+                     "halo_flip", "halo_area", "hstill", "hstill_ghost", "zb_cells", "zb_ghost", "S0_cells", "ManningN_cells", "matID_cells",
+                     "inletQ_TotalQ", "exitH_WSE", "own", "neighbors", "counts"))
+            dims = zeros(Int64, 16)
+            ccall((:hg_case_dims, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), cs[], dims)
+            ccall((:hg_case_free, LIB), Cvoid, (Ptr{Cvoid},), cs[])
+            solver = p_extra.swe_2D_constants.RiemannSolver
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            GC.@preserve A solver begin
+                pp(k, T) = (A[k] === nothing || isempty(A[k])) ? Ptr{T}(C_NULL) : pointer(A[k])
+                lm = MeshDesc(dims[1], dims[2], dims[3], dims[4], Int32(0), pp("cell_nfaces", Int64), pp("cell_faces", Int64),
+                              pp("cell_neighbors", Int64), pp("cell_normals", Float64), pp("face_is_boundary", UInt8),
+                              pp("face_lengths", Float64), pp("cell_areas", Float64), pp("cell_centroids", Float64))
+                lb = BcDesc(dims[6], dims[7], dims[8], dims[9], pp("bc_ptr", Int64), pp("bc_ghost_ids", Int64), pp("bc_internal_cells", Int64),
+                            pp("bc_normals", Float64), pp("bc_lengths", Float64), dims[11], pp("halo_flip", UInt8), pp("halo_area", Float64))
+                lf = FieldsDesc(fld.g, fld.k_n, fld.h_small, Base.unsafe_convert(Cstring, solver), pp("hstill", Float64),
+                                pp("hstill_ghost", Float64), pp("zb_cells", Float64), pp("zb_ghost", Float64), pp("S0_cells", Float64),
+                                pp("ManningN_cells", Float64), pp("matID_cells", Int64), dims[10], pp("inletQ_TotalQ", Float64), pp("exitH_WSE", Float64))
+                opt = Ref(Options(Int32(device_ids[r + 1]), Int32(tile_cells), Int32(1), Int32(0), Int32(0), ntuple(_ -> Int32(0), 11)))
+                _check(ccall((:hg_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{MeshDesc}, Ref{BcDesc}, Ref{FieldsDesc}, Ref{Options}),
+                             h, Ref(lm), Ref(lb), Ref(lf), opt), C_NULL)
+            end
+            push!(ctxs, _wrap(h[], Int(dims[1]), HG_PARAM[p_extra.active_param_name]))
+            push!(own, A["own"] .+ 1); push!(nbs, A["neighbors"]); push!(cnts, A["counts"])
+        end
+    end
+    # handles of every rank, then each rank connects to its neighbours: where its block lands in the neighbour's receive
+    # buffer (entries before it in the neighbour's list) and which of the neighbour's flag lines is its own
+    handles = [(b = zeros(UInt8, 128); isempty(nbs[r]) || _check(ccall((:hg_comm_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), ctxs[r].handle, b), ctxs[r].handle); b) for r in 1:P]
+    for r in 1:P
+        isempty(nbs[r]) && continue
+        blob = vcat((handles[q + 1] for q in nbs[r])...)
+        off = Int64[]; idx = Int64[]
+        for q in nbs[r]
+            j = findfirst(==(r - 1), nbs[q + 1])
+            push!(off, sum(cnts[q + 1][1:j-1]; init = 0)); push!(idx, j - 1)
+        end
+        _check(ccall((:hg_comm_connect, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{UInt8}, Ptr{Int64}, Ptr{Int64}),
+                     ctxs[r].handle, length(nbs[r]), blob, off, idx), ctxs[r].handle)
+    end
+    return MultiContext(ctxs, own, nbs, cnts)
+end
+
+# state in / out of the rank contexts (global vectors of length 3N, the reference's layout)
+function set_state(mc::MultiContext, Q::Vector{Float64})
+    N = length(Q) ÷ 3
+    for (c, o) in zip(mc.ctxs, mc.own)
+        q = vcat(Q[o], Q[N .+ o], Q[2N .+ o])
+        _check(ccall((:hg_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), c.handle, q), c.handle)
+    end
+end
+function step_euler(mc::MultiContext, dt::Float64, nsteps::Integer)      # launches are asynchronous: the ranks run side by side
+    for c in mc.ctxs
+        _check(ccall((:hg_step_euler, LIB), Cint, (Ptr{Cvoid}, Float64, Int64), c.handle, dt, Int64(nsteps)), c.handle)
+    end
+end
+function get_state(mc::MultiContext, N::Integer)
+    Q = zeros(3N)
+    for (c, o) in zip(mc.ctxs, mc.own)
+        q = zeros(3 * c.N)
+        _check(ccall((:hg_get_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), c.handle, q), c.handle)
+        n = c.N
+        Q[o] = q[1:n]; Q[N .+ o] = q[n+1:2n]; Q[2N .+ o] = q[2n+1:3n]
+    end
+    return Q
 end
 
 """
