@@ -127,6 +127,7 @@ SYMBOLS = {
     "hg_comm_exchange": (C.c_int, [_vp, C.c_int32]),
     "hg_comm_disconnect": (C.c_int, [_vp]),
     "hg_debug_math": (C.c_int, [_vp, C.c_int32, C.c_int64, c_f64p, c_f64p]),
+    "hg_time_jvp": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "hg_time_rhs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "hg_time_vjp": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_float)]),
     "hg_kernel_launches": (C.c_int64, [_vp]),

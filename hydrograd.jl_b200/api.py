@@ -431,6 +431,11 @@ class Context:
         self._ck(self.lib.hg_time_rhs(self._h, int(n_launches), int(fused_euler), float(dt), C.byref(ms)))
         return ms.value
 
+    def time_jvp(self, n_directions, n_launches):
+        ms = C.c_float(0)
+        self._ck(self.lib.hg_time_jvp(self._h, int(n_directions), int(n_launches), C.byref(ms)))
+        return ms.value
+
     def time_vjp(self, n_launches):
         ms = C.c_float(0)
         self._ck(self.lib.hg_time_vjp(self._h, int(n_launches), C.byref(ms)))

@@ -18,6 +18,7 @@ SOURCES = [
     ("hg_jvp.cu", ["-fmad=false"]),        # forward mode on the plain tables, same arithmetic rules
     ("hg_fused.cu", []),
     ("hg_vjp.cu", []),
+    ("hg_fjvp.cu", []),
     ("hg_ude.cu", []),
     ("hg_comm.cu", []),
 ]

@@ -647,15 +647,40 @@ int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
 // Forward mode: dQdt (optional) and dQdt_dot = J_Q(Q, p) v + J_p(Q, p) pdot, what a ForwardDiff.Dual pass through swe_2d_rhs
 // carries (one partial per call).  Runs on the plain tables (reference evaluation order, hg_jvp.cu): the context must be
 // created with strict = 1 / path = 1.  The state-dependent Manning closures and the UDE network have no forward mode here.
+// Forward mode on a fused (non-strict) context: the tile kernel of hg_fjvp.cu, K directions per launch.  Host vectors in the
+// reference's order; V [K][3N], Pdot [K][np] or NULL, dQdt [3N] or NULL, JV [K][3N].
+static int fused_jvp_host(hg_ctx* ctx, const double* Q, int64_t K, const double* V, const double* Pdot, double* dQdt, double* JV) {
+  hg::FusedDev& d = ctx->fd;
+  const int64_t N = ctx->N;
+  const size_t Ns3 = 3 * (size_t)ctx->fh.Ns;
+  const int64_t npar = ctx->active == HG_PARAM_NONE ? 0 : ctx->n_params;
+  if (d.j_V.n < (size_t)K * Ns3) { TRY(al(ctx, d.j_V, (size_t)K * Ns3)); TRY(al(ctx, d.j_out, (size_t)K * Ns3)); }
+  TRY(hg_set_state(ctx, Q));
+  for (int64_t k = 0; k < K; ++k) {
+    CK(ctx, cudaMemcpyAsync(d.stage.p, V + k * 3 * N, 3 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(hg::fused_permute(ctx, true, d.stage.p, d.j_V.p + k * Ns3));
+  }
+  const double* d_pdot = nullptr;
+  if (Pdot && npar > 0) {
+    if (d.j_pdot.n < (size_t)(K * npar)) TRY(al(ctx, d.j_pdot, (size_t)(K * npar)));
+    CK(ctx, cudaMemcpyAsync(d.j_pdot.p, Pdot, (size_t)(K * npar) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    d_pdot = d.j_pdot.p;
+  }
+  TRY(hg::fused_jvp(ctx, hg::fused_cfg_id(ctx), d.Q.p, d.j_V.p, d_pdot, dQdt ? d.dQ.p : nullptr, d.j_out.p, K));
+  if (dQdt) TRY(download3(ctx, d.dQ.p, dQdt));
+  for (int64_t k = 0; k < K; ++k) TRY(download3(ctx, d.j_out.p + k * Ns3, JV + k * 3 * N));
+  return check_err_flag(ctx);
+}
+
 int hg_rhs_jvp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32_t active, double t, const double* v,
                const double* pdot, double* dQdt, double* dQdt_dot) {
   (void)t;
   if (!ctx || !Q || !v || !dQdt_dot) return HG_ERR_ARG;
-  if (ctx->opt.path != 1) { ctx->err = "hg_rhs_jvp needs the plain path (strict = 1)"; return HG_ERR_ARG; }
   TRY(no_closure(ctx, "hg_rhs_jvp"));
   if (active == HG_PARAM_UDE) { ctx->err = "hg_rhs_jvp: the UDE network has no forward mode"; return HG_ERR_ARG; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
+  if (ctx->opt.path != 1) return fused_jvp_host(ctx, Q, 1, v, pdot, dQdt, dQdt_dot);   // fused tile kernel (hg_fjvp.cu)
   hg::PlainDev& p = ctx->pd;
   const size_t n3 = 3 * (size_t)ctx->N;
   if (p.V.n != n3) { TRY(al(ctx, p.V, n3)); TRY(al(ctx, p.dQd, n3)); }
@@ -682,11 +707,11 @@ int hg_rhs_jvp_multi(hg_ctx* ctx, const double* Q, const double* params, int64_t
                      const double* V, const double* Pdot, double* dQdt, double* JV) {
   (void)t;
   if (!ctx || !Q || !V || !JV || K < 1) return HG_ERR_ARG;
-  if (ctx->opt.path != 1) { ctx->err = "hg_rhs_jvp_multi needs the plain path (strict = 1)"; return HG_ERR_ARG; }
   TRY(no_closure(ctx, "hg_rhs_jvp_multi"));
   if (active == HG_PARAM_UDE) { ctx->err = "hg_rhs_jvp_multi: the UDE network has no forward mode"; return HG_ERR_ARG; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
+  if (ctx->opt.path != 1) return fused_jvp_host(ctx, Q, K, V, Pdot, dQdt, JV);   // fused tile kernel (hg_fjvp.cu), K directions per launch
   hg::PlainDev& p = ctx->pd;
   const size_t n3 = 3 * (size_t)ctx->N;
   const int64_t npar = ctx->active == HG_PARAM_NONE ? 0 : ctx->n_params;
@@ -719,7 +744,9 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
                         double* Q_save, double* Q_T, double* S, int64_t* stats) {
   if (!ctx || !Q0 || !S || !(t1 > t0) || !(dt > 0.0) || n_save < 0 || (n_save > 0 && (!t_save || !Q_save))) return HG_ERR_ARG;
   if (adaptive && (!(abstol > 0.0) || !(reltol > 0.0))) { ctx->err = "hg_solve_tsit5_sens: tolerances must be positive"; return HG_ERR_ARG; }
-  if (ctx->opt.path != 1) { ctx->err = "hg_solve_tsit5_sens needs the plain path (strict = 1)"; return HG_ERR_ARG; }
+  // strict contexts: forward mode on the plain tables (reference operation order); fused contexts: the tile kernel of
+  // hg_fjvp.cu -- the same solver around either, the augmented state in the context's own cell order
+  const bool fused = ctx->opt.path != 1;
   TRY(no_closure(ctx, "hg_solve_tsit5_sens"));
   if (active != HG_PARAM_ZB && active != HG_PARAM_MANNING && active != HG_PARAM_Q) {
     ctx->err = "hg_solve_tsit5_sens: the active parameter must be zb, ManningN or Q";
@@ -740,10 +767,20 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
   static const double BT[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
                                0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
   const double beta2 = 2.0 / 25.0, beta1 = 7.0 / 50.0, gamma = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
-  const int64_t n3 = 3 * ctx->N, rows = 1 + K, len = rows * n3;
+  const int64_t n3h = 3 * ctx->N;                                   // a row on the host (reference order)
+  const int64_t n3 = fused ? 3 * ctx->fh.Ns : n3h, rows = 1 + K, len = rows * n3;   // a row on the device (fused: padded internal order; the padding stays zero)
+  const int cfg = fused ? hg::fused_cfg_id(ctx) : 0;
+  auto fetch3 = [&](const double* d_row, double* host) -> int {     // one row of the augmented state -> host, reference order
+    if (fused) return download3(ctx, d_row, host);
+    CK(ctx, cudaMemcpyAsync(host, d_row, (size_t)n3h * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return HG_OK;
+  };
   hg::DBuf<double> U, Unew, Y, kb[7], E, part, sum;
   CK(ctx, U.alloc((size_t)len)); CK(ctx, Unew.alloc((size_t)len)); CK(ctx, Y.alloc((size_t)len));
   for (int m = 0; m < 7; ++m) CK(ctx, kb[m].alloc((size_t)len));
+  CK(ctx, cudaMemsetAsync(Unew.p, 0, (size_t)len * 8, ctx->stream)); CK(ctx, cudaMemsetAsync(Y.p, 0, (size_t)len * 8, ctx->stream));
+  for (int m = 0; m < 7; ++m) CK(ctx, cudaMemsetAsync(kb[m].p, 0, (size_t)len * 8, ctx->stream));
   CK(ctx, E.alloc((size_t)(K * K)));
   CK(ctx, part.alloc((size_t)hg::sens_err_blocks(n3))); CK(ctx, sum.alloc(1));
   {
@@ -756,7 +793,7 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
   // independent of the save times (what forward_simulation_results.json holds)
   std::vector<std::pair<double, int64_t>> pending;
   for (int64_t i = 0; i < n_save; ++i) {
-    if (t_save[i] == t0) std::memcpy(Q_save + (size_t)i * n3, Q0, (size_t)n3 * 8);
+    if (t_save[i] == t0) std::memcpy(Q_save + (size_t)i * n3h, Q0, (size_t)n3h * 8);
     else if (t_save[i] > t0 && t_save[i] <= t1) pending.push_back({t_save[i], i});
     else { ctx->err = "hg_solve_tsit5_sens: save time outside [t0, t1]"; return HG_ERR_ARG; }
   }
@@ -770,10 +807,17 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
                                   {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
                                   {0.0, 1.5, -4.0, 2.5}};
   CK(ctx, cudaMemsetAsync(U.p, 0, (size_t)len * 8, ctx->stream));           // the partials start at zero (Q0 does not depend on p)
-  CK(ctx, cudaMemcpyAsync(U.p, Q0, (size_t)n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (fused) {
+    CK(ctx, cudaMemcpyAsync(ctx->fd.stage.p, Q0, (size_t)n3h * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(hg::fused_permute(ctx, true, ctx->fd.stage.p, U.p));
+    ctx->state_set = false;     // the resident state buffer is not what this solve integrates
+  } else {
+    CK(ctx, cudaMemcpyAsync(U.p, Q0, (size_t)n3h * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
   // d/dt of the augmented state: row 0 = f(Q, p), row k = J_Q U_k + J_p e_k
   auto rhs_aug = [&](const double* u, double* du) -> int {
-    // the K partials in one pair of launches (row k of the augmented state is direction k; pdot = e_k)
+    // the K partials in one launch (pair): row k of the augmented state is direction k; pdot = e_k
+    if (fused) return hg::fused_jvp(ctx, cfg, u, u + n3, E.p, du, du + n3, K);
     return hg::plain_jvp_batch(ctx, u, u + n3, (int64_t)n3, E.p, K, du, du + n3, K);
   };
   double* u = U.p;
@@ -805,7 +849,7 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
       double ssum = 0.0;
       CK(ctx, cudaMemcpyAsync(&ssum, sum.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
       CK(ctx, cudaStreamSynchronize(ctx->stream));
-      eest = std::sqrt(ssum / (double)len);
+      eest = std::sqrt(ssum / (double)(rows * n3h));
       if (!(eest == eest)) { ctx->err = "hg_solve_tsit5_sens: the error estimate is NaN"; return HG_ERR_STATE; }
       if (eest == 0.0) { q11 = 0.0; q = 1.0 / qmax; }
       else {
@@ -818,16 +862,15 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
     if (accept) {
       const double tnew = (h == t1 - t) ? t1 : t + h;
       for (; next_save < pending.size() && pending[next_save].first <= tnew; ++next_save) {
-        double* out = Q_save + (size_t)pending[next_save].second * n3;
+        double* out = Q_save + (size_t)pending[next_save].second * n3h;
         if (pending[next_save].first == tnew) {
-          CK(ctx, cudaMemcpyAsync(out, unew, (size_t)n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+          TRY(fetch3(unew, out));
         } else {                                   // row 0 of u + h sum_i b_i(theta) k_i (Y is free between steps)
           const double th = (pending[next_save].first - t) / h;
           for (int m = 0; m < 7; ++m) coef[m] = h * (th * (RI[m][0] + th * (RI[m][1] + th * (RI[m][2] + th * RI[m][3]))));
           TRY(hg::sens_lincomb(ctx, n3, Y.p, u, 7, k, coef));
-          CK(ctx, cudaMemcpyAsync(out, Y.p, (size_t)n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+          TRY(fetch3(Y.p, out));
         }
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
       }
       std::swap(u, unew);
       std::swap(k[0], k[6]);                       // FSAL
@@ -845,9 +888,8 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
       if (!(dt_ctrl > 1e-14 * std::max(1.0, std::fabs(t)))) { ctx->err = "hg_solve_tsit5_sens: step size underflow"; return HG_ERR_STATE; }
     }
   }
-  if (Q_T) CK(ctx, cudaMemcpyAsync(Q_T, u, (size_t)n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(ctx, cudaMemcpyAsync(S, u + n3, (size_t)(K * n3) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (Q_T) TRY(fetch3(u, Q_T));
+  for (int64_t kk = 0; kk < K; ++kk) TRY(fetch3(u + (1 + kk) * n3, S + (size_t)kk * n3h));
   if (stats) { stats[0] = n_acc; stats[1] = n_rej; stats[2] = n_rhs; }
   return check_err_flag(ctx);
 }
@@ -1523,6 +1565,37 @@ int hg_time_rhs(hg_ctx* ctx, int32_t n, int32_t fused_euler, double dt, float* m
     if (fused_euler) TRY(hg_step_euler(ctx, dt, 1));
     else TRY(hg_rhs_resident(ctx));
   }
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return check_err_flag(ctx);
+}
+
+// device time of n launches of the fused forward-mode kernel with K directions each (tangents = the resident cotangent
+// buffer's content replicated; Manning zones as directions when they are the active parameter)
+int hg_time_jvp(hg_ctx* ctx, int32_t K, int32_t n, float* ms) {
+  if (!ctx || !ms || n <= 0 || K <= 0) return HG_ERR_ARG;
+  if (ctx->opt.path == 1) { ctx->err = "hg_time_jvp needs the fused path"; return HG_ERR_ARG; }
+  if (!ctx->state_set || !ctx->lam_set) { ctx->err = "hg_time_jvp: state or lambda not set"; return HG_ERR_STATE; }
+  CK(ctx, cudaSetDevice(ctx->opt.device));
+  hg::FusedDev& d = ctx->fd;
+  const size_t Ns3 = 3 * (size_t)ctx->fh.Ns;
+  if (d.j_V.n < (size_t)K * Ns3) { TRY(al(ctx, d.j_V, (size_t)K * Ns3)); TRY(al(ctx, d.j_out, (size_t)K * Ns3)); }
+  for (int32_t k = 0; k < K; ++k) CK(ctx, cudaMemcpyAsync(d.j_V.p + k * Ns3, d.lam.p, Ns3 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  const int64_t npar = ctx->active == HG_PARAM_NONE ? 0 : ctx->n_params;
+  const double* d_pdot = nullptr;
+  if (npar > 0) {
+    std::vector<double> pd((size_t)(K * npar), 0.0);
+    for (int64_t k = 0; k < K; ++k) pd[(size_t)(k * npar + (k % npar))] = 1.0;
+    if (d.j_pdot.n < pd.size()) TRY(al(ctx, d.j_pdot, pd.size()));
+    CK(ctx, cudaMemcpyAsync(d.j_pdot.p, pd.data(), pd.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    d_pdot = d.j_pdot.p;
+  }
+  const int cfg = hg::fused_cfg_id(ctx);
+  TRY(hg::fused_jvp(ctx, cfg, d.Q.p, d.j_V.p, d_pdot, d.dQ.p, d.j_out.p, K));   // warm
+  CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int i = 0; i < n; ++i) TRY(hg::fused_jvp(ctx, cfg, d.Q.p, d.j_V.p, d_pdot, d.dQ.p, d.j_out.p, K));
   CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   CK(ctx, cudaEventSynchronize(ctx->ev1));
   CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));

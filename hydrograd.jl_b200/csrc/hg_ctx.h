@@ -201,6 +201,7 @@ struct FusedDev {
   DBuf<double> rk_k, rk_acc, rk_tmp;                                   // RK4 stages
   DBuf<double> ts_k[7], ts_new, ts_part, ts_sum;                       // Tsit5 stages, candidate state, error-norm scratch
   DBuf<double> halo_send, halo_recv;                                    // [6 * n_halo_entries]
+  DBuf<double> j_V, j_out, j_pdot, j_p0, j_p1, j_p2, j_coef;             // fused forward mode (hg_fjvp.cu): tangents in / out, parameter tangents
   DBuf<double> ude_theta, ude_stats, ude_part;                          // UDE network: parameters, LayerNorm statistics, partial sums
   DBuf<int32_t> err;
 };
@@ -258,6 +259,7 @@ struct hg_ctx {
   hg::BcHost bch;
   hg::PlainDev pd;
   hg::FusedHost fh;
+  bool fjvp_ready = false;     // hg_fjvp.cu: kernel attributes set
   int32_t fh_force_nf = 0;     // build_tiles: face slots per cell of the attempt being built (4 or 8)
   hg_comm* comm = nullptr;   // library-owned halo exchange (hg_comm.cu); null = the caller moves halo_send -> halo_recv
   hg::FusedDev fd;
@@ -321,6 +323,9 @@ int fused_lincomb(hg_ctx* ctx, double* y, const double* x, int n, const double* 
 int fused_err_blocks(const hg_ctx* ctx);
 int fused_err_norm(hg_ctx* ctx, const double* u, const double* unew, int n, const double* const* k, const double* coef, double abstol,
                    double reltol, double* d_part, double* d_sum);
+// fused forward mode (hg_fjvp.cu)
+int fused_jvp(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_V, const double* d_pdot, double* d_out, double* d_out_d, int64_t K);
+int fused_bed_from(hg_ctx* ctx, const double* d_zb_ref, double* d_zb, double* d_S0x, double* d_S0y);
 // library-owned halo exchange (hg_comm.cu): push d_Q (and d_lam) of the cut cells into the neighbours' receive buffers
 int comm_push(hg_ctx* ctx, const double* d_Q, const double* d_lam);
 int fused_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* d_x, double* d_out);

@@ -234,8 +234,9 @@ HG_API int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_
 /* ---- device-resident state (no host round trip per stage) ---------------------------------- */
 /* Forward mode: dQdt_dot = J_Q v + J_p pdot (and dQdt when not NULL) -- one partial of a ForwardDiff.Dual pass through
  * swe_2d_rhs (swe_2D_sensitivity.jl:80 wraps the whole solve in ForwardDiff.jacobian; ForwardDiffSensitivity /
- * ForwardSensitivity of solve_swe_2D.jl:230-235).  v[3N]; pdot[n_params] or NULL (zero).  Needs a context created with
- * strict = 1 (plain tables, reference evaluation order); no state-dependent Manning closure, no UDE network.            */
+ * ForwardSensitivity of solve_swe_2D.jl:230-235).  v[3N]; pdot[n_params] or NULL (zero).  Fused contexts run the forward-mode
+ * tile kernel (hg_fjvp.cu: each face once on the staged tile, K directions per launch); contexts created with strict = 1 run
+ * on the plain tables in the reference's evaluation order.  No state-dependent Manning closure, no UDE network, one GPU.   */
 HG_API int hg_rhs_jvp(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params, int32_t active_param, double t,
                const double* v, const double* pdot, double* dQdt, double* dQdt_dot);
 /* K directions at once (one ForwardDiff chunk): V[K][3N], Pdot[K][n_params] or NULL, JV[K][3N]; dQdt may be NULL */
@@ -248,7 +249,8 @@ HG_API int hg_rhs_jvp_multi(hg_ctx* ctx, const double* Q, const double* params, 
  * the VALUES at the driver's save times by Tsit5's dense output, i.e. the columns of forward_simulation_results.json
  * (swe_2D_sensitivity.jl:60-72).  Q_T[3N] (may be NULL); S[n_params][3N], row k =
  * d Q(t1) / d p_k (the transpose of the reference's 3N x n_params Jacobian = its column-major JSON layout); stats =
- * {accepted, rejected, augmented RHS evaluations}; hg_last_steps afterwards gives the accepted steps.  strict = 1 only.   */
+ * {accepted, rejected, augmented RHS evaluations}; hg_last_steps afterwards gives the accepted steps.  Fused and strict
+ * contexts (the K partials of a stage go through one launch of the respective forward-mode kernel).                         */
 HG_API int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params, int32_t active_param,
                         double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol, const double* t_save,
                         int64_t n_save, double* Q_save, double* Q_T, double* S, int64_t* stats);
@@ -476,6 +478,7 @@ HG_API double hg_total_water_volume(int64_t N, const double* h, const double* ce
  * ctx stream) and introspection for the roofline arithmetic.                                     */
 HG_API int hg_time_rhs(hg_ctx* ctx, int32_t n_launches, int32_t fused_euler, double dt, float* ms_total);
 HG_API int hg_time_vjp(hg_ctx* ctx, int32_t n_launches, float* ms_total);
+HG_API int hg_time_jvp(hg_ctx* ctx, int32_t n_directions, int32_t n_launches, float* ms_total);   /* fused forward-mode kernel */
 HG_API int64_t hg_kernel_launches(const hg_ctx* ctx);            /* kernels launched so far             */
 HG_API int hg_mesh_stats(const hg_ctx* ctx, int64_t* n_cells, int64_t* n_faces, int64_t* sum_cell_faces,
                   int64_t* n_tiles, int64_t* device_bytes);

@@ -108,7 +108,7 @@ def _jl_type(t):
     t = t.strip()
     table = {"Int64": C.c_int64, "Int32": C.c_int32, "Float64": C.c_double, "Cint": C.c_int, "Cstring": C.c_char_p, "Cvoid": None,
              "Ptr{Int64}": L.c_i64p, "Ptr{Float64}": L.c_f64p, "Ptr{UInt8}": L.c_u8p, "Ptr{Cvoid}": C.c_void_p,
-             "Ref{Int64}": L.c_i64p, "Ref{Ptr{Cvoid}}": P(C.c_void_p),
+             "Ref{Int64}": L.c_i64p, "Ref{Int32}": P(C.c_int32), "Ptr{Int32}": P(C.c_int32), "Ref{Ptr{Cvoid}}": P(C.c_void_p),
              "Ref{MeshDesc}": P(L.MeshDesc), "Ref{BcDesc}": P(L.BcDesc), "Ref{FieldsDesc}": P(L.FieldsDesc), "Ref{Options}": P(L.Options),
              "Ref{UdeDesc}": P(L.UdeDesc)}
     if t in table:
@@ -170,5 +170,6 @@ def test_julia_ccalls_match_the_prototypes():
         seen.add(name)
     # the shim binds the whole drop-in path
     for must in ("hg_create", "hg_destroy", "hg_last_error", "hg_rhs", "hg_rhs_vjp", "hg_custom_ode_solve", "hg_solve_tsit5_dense",
-                 "hg_set_manning_function", "hg_set_ude_model", "hg_set_state", "hg_step_ab3"):
+                 "hg_set_manning_function", "hg_set_ude_model", "hg_set_state", "hg_step_ab3",
+                 "hg_partition_rcb", "hg_partition_extract", "hg_comm_export", "hg_comm_connect", "hg_step_euler", "hg_get_state"):
         assert must in seen, must
