@@ -22,6 +22,34 @@
 namespace hg {
 namespace ude {
 
+// Reciprocal, reciprocal square root and tanh of the per-cell arithmetic.  On the device: the branch-free MUFU-seed + one
+// third-order step of the RHS kernels (hg_device.cuh; arguments here are positive normals: depths, 1 + exp(.), variances +
+// eps) and tanh from ONE expm1 and one reciprocal -- the closure is bound by the fp64 pipe, and the library's `/`, `sqrt` and
+// `tanh` each cost a branchy slow path.  On the host (the g++ check of tests/ude_host.cpp): the plain expressions.
+#if defined(__CUDA_ARCH__)
+HG_HD double u_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+}
+HG_HD double u_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-(x * r), r, 1.0);
+  return fma(r * e, fma(0.375, e, 0.5), r);
+}
+HG_HD double u_tanh(double z) {
+  const double e = expm1(-2.0 * fabs(z));          // in (-1, 0]: tanh|z| = -e / (2 + e), no cancellation near 0
+  const double t = -e * u_rcp(2.0 + e);
+  return z < 0.0 ? -t : t;
+}
+#else
+HG_HD double u_rcp(double x) { return 1.0 / x; }
+HG_HD double u_rsqrt(double x) { return 1.0 / sqrt(x); }
+HG_HD double u_tanh(double z) { return tanh(z); }
+#endif
+
 constexpr int MAXH = HG_UDE_MAX_HIDDEN, MAXW = HG_UDE_MAX_WIDTH;
 constexpr int MAXP = 3 * MAXW + 3 * MAXW + (MAXH - 1) * (MAXW * MAXW + 3 * MAXW) + MAXW + 1;   // 233 with 3 x 8
 
@@ -120,14 +148,15 @@ HG_HD void inputs(const Model& m, double xi, double qx, double qy, double hst, d
   const double h0 = xi + hst;
   in.dry = h0 <= hs;
   in.h = in.dry ? hs : h0;
-  in.u = in.dry ? 0.0 : qx / in.h;
-  in.v = in.dry ? 0.0 : qy / in.h;
+  const double rh = u_rcp(in.h);
+  in.u = in.dry ? 0.0 : qx * rh;
+  in.v = in.dry ? 0.0 : qy * rh;
   in.umag = sqrt(in.u * in.u + in.v * in.v);
-  in.x[0] = 2.0 * (in.h - m.in_lo[0]) / m.in_den[0] - 1.0;
+  in.x[0] = 2.0 * (in.h - m.in_lo[0]) * u_rcp(m.in_den[0]) - 1.0;
   in.x[1] = in.x[2] = 0.0;
   if (s_nin<S>(m) == 3) {
-    in.x[1] = 2.0 * (in.umag - m.in_lo[1]) / m.in_den[1] - 1.0;
-    in.x[2] = 2.0 * (ks - m.in_lo[2]) / m.in_den[2] - 1.0;
+    in.x[1] = 2.0 * (in.umag - m.in_lo[1]) * u_rcp(m.in_den[1]) - 1.0;
+    in.x[2] = 2.0 * (ks - m.in_lo[2]) * u_rcp(m.in_den[2]) - 1.0;
   }
 }
 // transpose of the above: the clamp is a constant selector (a clamped cell passes nothing back, like every other clamp of
@@ -136,13 +165,14 @@ template <class S>
 HG_HD void inputs_adj(const Model& m, const Inputs& in, const double* xbar, double& xib, double& qxb, double& qyb) {
   xib = qxb = qyb = 0.0;
   if (in.dry) return;
-  double hb = xbar[0] * (2.0 / m.in_den[0]);
+  double hb = xbar[0] * (2.0 * u_rcp(m.in_den[0]));
   if (s_nin<S>(m) == 3 && in.umag > 0.0) {
-    const double Ub = xbar[1] * (2.0 / m.in_den[1]);
-    const double ub = Ub * in.u / in.umag, vb = Ub * in.v / in.umag;
-    qxb = ub / in.h;
-    qyb = vb / in.h;
-    hb -= (ub * in.u + vb * in.v) / in.h;
+    const double Ub = xbar[1] * (2.0 * u_rcp(m.in_den[1]));
+    const double rU = u_rcp(in.umag), rh = u_rcp(in.h);
+    const double ub = Ub * in.u * rU, vb = Ub * in.v * rU;
+    qxb = ub * rh;
+    qyb = vb * rh;
+    hb -= (ub * in.u + vb * in.v) * rh;
   }
   xib = hb;
 }
@@ -151,8 +181,8 @@ HG_HD double act_fwd(int a, double z) {
   switch (a) {
     case HG_ACT_RELU: return z > 0.0 ? z : 0.0;
     case HG_ACT_LEAKYRELU: return z > 0.0 ? z : 0.01 * z;
-    case HG_ACT_SIGMOID: return 1.0 / (1.0 + exp(-z));
-    case HG_ACT_TANH: return tanh(z);
+    case HG_ACT_SIGMOID: return u_rcp(1.0 + exp(-z));
+    case HG_ACT_TANH: return u_tanh(z);
     case HG_ACT_SOFTPLUS: return log1p(exp(-fabs(z))) + (z > 0.0 ? z : 0.0);
     default: return z;
   }
@@ -164,7 +194,7 @@ HG_HD double act_der(int a, double z, double y) {
     case HG_ACT_LEAKYRELU: return z > 0.0 ? 1.0 : 0.01;
     case HG_ACT_SIGMOID: return y * (1.0 - y);
     case HG_ACT_TANH: return 1.0 - y * y;
-    case HG_ACT_SOFTPLUS: return 1.0 / (1.0 + exp(-z));
+    case HG_ACT_SOFTPLUS: return u_rcp(1.0 + exp(-z));
     default: return 1.0;
   }
 }
@@ -218,12 +248,13 @@ HG_HD double forward(const Model& m, const double* th, const double* x, const do
           HG_UNROLL
           for (int j = 0; j < MAXW; ++j)
             if (j < W) mu += t.y[l][j];
-          mu /= W;
+          const double rW = 1.0 / W;      // (compile-time for the specialised shapes)
+          mu *= rW;
           double var = 0.0;
           HG_UNROLL
           for (int j = 0; j < MAXW; ++j)
             if (j < W) var += (t.y[l][j] - mu) * (t.y[l][j] - mu);
-          rstd = 1.0 / sqrt(var / W + m.eps);
+          rstd = u_rsqrt(var * rW + m.eps);
         } else {
           mu = stats[2 * l];
           rstd = stats[2 * l + 1];
@@ -253,7 +284,7 @@ HG_HD double forward(const Model& m, const double* th, const double* x, const do
         if (i < W) zo += w[i] * t.a[l][i];
     }
   }
-  t.s = 1.0 / (1.0 + exp(-zo));
+  t.s = u_rcp(1.0 + exp(-zo));
   return m.out_lo + m.out_span * t.s;
 }
 
