@@ -458,6 +458,17 @@ def main():
                      "vjp_roofline_frac": vbytes / (t_v / n_done * 1e-3) / 1e9 / peak,
                      "steps": n_done, "clocks": c2}
 
+    # ---- forward mode (the reference's sensitivity / ForwardDiff paths): the fused forward-mode tile kernel, six directions
+    # (one per Manning zone) per launch
+    jvp = None
+    if world == 1 and not args.no_side:
+        Kd = 6
+        ctx.time_jvp(Kd, 1)
+        ms_j = min(ctx.time_jvp(Kd, 3) / 3 for _ in range(2))
+        jbytes = abytes + Kd * 56 * N     # tile tables + state once per tile (the K CTAs of a tile share them through L2); per direction 24 B in, 24 B out, 8 B parameter tangent
+        jvp = {"kernel": "k_fused_jvp", "directions": Kd, "ms_per_launch": ms_j, "value": Kd * N / (ms_j * 1e-3), "unit": "direction-cell-updates/s",
+               "roofline_frac": jbytes / (ms_j * 1e-3) / 1e9 / peak, "note": "values + six tangents (dQ/dt and J_Q v + J_p e_k per Manning zone); bound by the fp64 pipe (dual-number Roe flux), not by HBM"}
+
     # ---- roofline of the dominant kernel (k_fused_rhs): algorithmic bytes / measured launch time
     achieved = abytes / (ms_rhs_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -575,6 +586,8 @@ def main():
                 "rhs": {"value": N_total / (ms_rhs_step * 1e-3), "unit": UNIT, "ms": ms_rhs_step},
                 "vjp": {"value": N_total / (ms_vjp_step * 1e-3), "unit": UNIT, "ms": ms_vjp_step},
                 "sustained": sustained, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        if jvp is not None:
+            line["jvp"] = jvp
         line.update(side)
         if strong is not None:
             line["strong"] = strong
