@@ -398,10 +398,19 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     // per half-warp, so the 12 (RHS) / 22 (VJP) per-side gathers of the face phase become conflict-free.  Greedy
     // decomposition of the bipartite multigraph (bank of L) x (bank of R) into matchings; leftovers fill the tail.
     if (ctx->opt.reserved[4] == 0 && tf.size() >= 32) {
-      // cell[bL][bR]: the faces with that pair of banks in their original order; cnt = how many are still unplaced
-      std::vector<int32_t> cell[16][16];
-      int head[16][16] = {}, cnt[16][16] = {};
-      for (int32_t k = 0; k < (int32_t)tf.size(); ++k) { cell[tf[k].lL & 15][tf[k].lR & 15].push_back(k); ++cnt[tf[k].lL & 15][tf[k].lR & 15]; }
+      // bucket (bL, bR): the faces with that pair of banks in their original order (one counting sort into a flat array --
+      // 256 small vectors per tile were 16M allocations on a 16M-cell mesh); cnt = how many are still unplaced
+      int head[16][16] = {}, cnt[16][16] = {}, off[16][16];
+      for (int32_t k = 0; k < (int32_t)tf.size(); ++k) ++cnt[tf[k].lL & 15][tf[k].lR & 15];
+      {
+        int run = 0;
+        for (int l = 0; l < 16; ++l) for (int r = 0; r < 16; ++r) { off[l][r] = run; run += cnt[l][r]; }
+      }
+      std::vector<int32_t> bucket(tf.size());
+      {
+        int fill[16][16] = {};
+        for (int32_t k = 0; k < (int32_t)tf.size(); ++k) { const int l = tf[k].lL & 15, r = tf[k].lR & 15; bucket[off[l][r] + fill[l][r]++] = k; }
+      }
       std::vector<TF> out;
       out.reserve(tf.size());
       size_t left = tf.size();
@@ -422,7 +431,7 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
         for (int l = 0; l < 16; ++l) {
           const int r = matchL[l];
           if (r < 0) continue;
-          out.push_back(tf[cell[l][r][head[l][r]++]]);
+          out.push_back(tf[bucket[off[l][r] + head[l][r]++]]);
           --cnt[l][r]; ++useL[l]; ++useR[r];
           ++npick;
         }
@@ -436,7 +445,7 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
               const int cost = 64 * std::max(useL[l], useR[r]) + 4 * (useL[l] + useR[r]) - std::min(cnt[l][r], 3);
               if (cost < best) { best = cost; bl = l; br = r; }
             }
-          out.push_back(tf[cell[bl][br][head[bl][br]++]]);
+          out.push_back(tf[bucket[off[bl][br] + head[bl][br]++]]);
           --cnt[bl][br]; ++useL[bl]; ++useR[br];
           ++npick;
         }
