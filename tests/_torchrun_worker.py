@@ -51,6 +51,13 @@ def main():
         out["ipc_vjp_err"] = float(np.abs(bar - pick(ref_bar)).max() / np.abs(ref_bar).max())
         ctx.step_euler(1e-3, 5)          # five exchanges inside one call
         out["ipc_euler_bitwise"] = bool(np.array_equal(ctx.get_state(), pick(ref_Q5)))
+        # the other resident steppers loop the RHS too (four exchanges per RK4 step, one or two per AB3 step)
+        single.set_state(Q0); single.step_rk4(1e-3, 3); ref_rk = single.get_state()
+        ctx.set_state(info["Q"]); ctx.step_rk4(1e-3, 3)
+        out["ipc_rk4_bitwise"] = bool(np.array_equal(ctx.get_state(), pick(ref_rk)))
+        single.set_state(Q0); single.step_ab3(1e-3, 4); ref_ab = single.get_state()
+        ctx.set_state(info["Q"]); ctx.step_ab3(1e-3, 4)
+        out["ipc_ab3_bitwise"] = bool(np.array_equal(ctx.get_state(), pick(ref_ab)))
         dist.barrier()
         ctx.comm_disconnect()
         # ---- host-buffer calls on a mesh large enough for the three-stream pipeline (>= 1M cells per rank): hg_rhs / hg_rhs_vjp
@@ -67,7 +74,8 @@ def main():
         bown = binfo["own"]
         bpick = lambda v: np.concatenate([v[k * bN + bown] for k in range(3)])
         bctx = hg.Context(bloc, device=dev)
-        P.connect_ranks(bctx, binfo)
+        # this context is wired by the library's own rendezvous (POSIX shared memory): what a host without a messaging layer uses
+        bctx.comm_init_shm("t" + os.path.basename(os.environ["HG_WORKER_OUT"]) + os.environ.get("MASTER_PORT", "0"), rank, world, binfo["neighbors"])
         out["pipe_rhs_bitwise"] = bool(np.array_equal(bctx.rhs(binfo["Q"]), bpick(bref)))
         got_bar, _ = bctx.rhs_vjp(binfo["Q"], bpick(blam))
         out["pipe_vjp_err"] = float(np.abs(got_bar - bpick(bbar)).max() / np.abs(bbar).max())

@@ -24,7 +24,7 @@ def test_two_ranks_match_single_context(tmp_path):
     print(res)
     for o in res:
         assert o["ok"], o
-        assert o["ipc_rhs_bitwise"] and o["ipc_euler_bitwise"], o
+        assert o["ipc_rhs_bitwise"] and o["ipc_euler_bitwise"] and o["ipc_rk4_bitwise"] and o["ipc_ab3_bitwise"], o
         assert o["ipc_vjp_err"] <= 1e-13, o
         assert o["pipe_rhs_bitwise"] and o["pipe_vjp_err"] <= 1e-13, o
         if o["one_gpu_each"]:
