@@ -35,15 +35,22 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(HERE, "hg_ctx.h"), os.path.join(HERE, "hg_device.cuh"), os.path.join(HERE, "hg_ude.h"), os.path.join(HERE, "hg_jvp_impl.h"), os.path.join(HERE, "hg_case.h"), os.path.join(PKG, "..", "include", "hydrograd_b200.h"), __file__]
-    objs = []
+    objs, cmds = [], []
     for src, extra in SOURCES:
         s = os.path.join(HERE, src)
         o = os.path.join(objdir, src.rsplit(".", 1)[0] + ".o")
         objs.append(o)
         if force or _newer(o, [s] + hdrs):
-            cmd = ["nvcc"] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", s, "-o", o]
+            cmds.append(["nvcc"] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", s, "-o", o])
+    if cmds:   # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             print(" ".join(cmd), flush=True)
             subprocess.run(cmd, check=True)
+
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as ex:
+            list(ex.map(run, cmds))
     if force or _newer(OUT, objs):
         cmd = ["nvcc"] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + objs + ["-lgomp"]
         print(" ".join(cmd), flush=True)
