@@ -288,6 +288,11 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
       auto mid = permuted(x->matid_ref.data(), fh.perm);
       mid.resize((size_t)fh.n_tiles * fh.T, 0);   // whole tiles: the VJP kernel prefetches the next tile's block into L2
       TRY(up(ctx, d.matid, mid));
+      if (ctx->n_mat <= 255) {
+        std::vector<uint8_t> m8(mid.size());
+        for (size_t q = 0; q < mid.size(); ++q) m8[q] = (uint8_t)mid[q];
+        TRY(up(ctx, d.matid8, m8));
+      }
     }
     std::vector<int32_t> bc_cell(B);
     std::vector<double> bhst(B);

@@ -134,6 +134,7 @@ int hg_comm_connect(hg_ctx* ctx, int64_t n_neighbors, const void* peer_handles, 
   int rc = comm_alloc(ctx);
   if (rc != HG_OK) return rc;
   hg_comm* cm = ctx->comm;
+  if (cm->connected) { ctx->err = "hg_comm_connect: already connected (hg_comm_disconnect first)"; return HG_ERR_STATE; }
   if (n_neighbors != cm->n) { ctx->err = "hg_comm_connect: the context has " + std::to_string(cm->n) + " halo boundaries"; return HG_ERR_ARG; }
   if (cudaSetDevice(ctx->opt.device) != cudaSuccess) { ctx->err = "cudaSetDevice"; return HG_ERR_CUDA; }
   std::vector<double*> dst0(cm->n), dst1(cm->n);

@@ -188,6 +188,7 @@ struct FusedDev {
   DBuf<double> area, hstill, zb, S0x, S0y, mann;  // [Ns] internal order
   DBuf<double> ks;                                // [Ns] roughness height (variable Manning's n)
   DBuf<int32_t> matid;
+  DBuf<uint8_t> matid8;                           // the same zone ids in one byte each (few zones: the zone reduction of the VJP reads these)
   DBuf<int32_t> bc_type, bc_group, bc_cell;        // [B] entry order, internal cell ids
   DBuf<double> bc_nx, bc_ny, bc_l53, bc_l23, bc_hstill, bc_zb;
   DBuf<int32_t> inlet_ptr;

@@ -762,16 +762,15 @@ __global__ void __launch_bounds__(256) k_zone_final_many(int32_t nblocks, int32_
   }
   if (threadIdx.x == 0) pbar[z] = red[0];
 }
-// Few zones (the reference's cases have 1-6): ONE launch straight from nbar + matid (12 B per cell, bandwidth-bound).
+// Few zones (the reference's cases have 1-6): ONE launch straight from nbar + one-byte zone ids (9 B per cell, bandwidth-bound).
 // A fixed grid of CTAs strides over the cells with four independent loads in flight per thread and one register
 // accumulator per zone; per-CTA sums go to part2[cta][.]; the CTA that finishes last (ticket counter) adds part2 in a fixed
 // shape (256 strided sums in CTA order, then a tree) and writes pbar.  Every order is fixed: bit-reproducible.
 constexpr int kZoneFew = 8, kZoneGrid = 148 * 8;
 template <int NZ>
-__global__ void __launch_bounds__(256) k_zone_reduce(int32_t N, int32_t n_mat, const int32_t* __restrict__ matid, const double* __restrict__ nbar,
+__global__ void __launch_bounds__(256) k_zone_reduce(int32_t N, int32_t n_mat, const uint8_t* __restrict__ matid, const double* __restrict__ nbar,
                                                      double* __restrict__ part2, unsigned int* __restrict__ ticket, double* __restrict__ pbar) {
   __shared__ double ws[8][NZ];
-  __shared__ double red[256];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc[NZ];
@@ -784,7 +783,7 @@ __global__ void __launch_bounds__(256) k_zone_reduce(int32_t N, int32_t n_mat, c
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int32_t j = i + k * stride;
-      m[k] = j < N ? __ldg(matid + j) : -1;
+      m[k] = j < N ? (int32_t)__ldg(matid + j) : -1;
       v[k] = j < N ? __ldg(nbar + j) : 0.0;
     }
 #pragma unroll
@@ -812,17 +811,28 @@ __global__ void __launch_bounds__(256) k_zone_reduce(int32_t N, int32_t n_mat, c
   __syncthreads();
   if (!last) return;
   __threadfence();
-  for (int z = 0; z < n_mat; ++z) {
+  // the last CTA: every thread adds its strided share of the CTAs' sums for ALL zones (fixed order), then ONE shuffle +
+  // shared-memory reduction for all zones at once
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) acc[z] = 0.0;
+  for (unsigned c = threadIdx.x; c < gridDim.x; c += 256) {
+#pragma unroll
+    for (int z = 0; z < NZ; ++z) acc[z] += __ldcg(part2 + (size_t)c * NZ + z);
+  }
+  __syncthreads();                      // ws is reused
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) {
+    double v = acc[z];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) ws[warp][z] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_mat) {
     double v = 0.0;
-    for (unsigned c = threadIdx.x; c < gridDim.x; c += 256) v += __ldcg(part2 + (size_t)c * NZ + z);
-    red[threadIdx.x] = v;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-      if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) pbar[z] = red[0];
-    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += ws[w][threadIdx.x];
+    pbar[threadIdx.x] = v;
   }
   if (threadIdx.x == 0) *ticket = 0;   // ready for the next launch
 }
@@ -1007,7 +1017,7 @@ int fused_vjp_finish(hg_ctx* ctx, const double* d_Q, double* d_Qbar) {
       }
       unsigned int* ticket = reinterpret_cast<unsigned int*>(d.zone_part2.p + (size_t)kZoneGrid * kZoneFew);
       const unsigned g2 = (unsigned)std::min<int64_t>(kZoneGrid, (ctx->N + 1023) / 1024);
-      k_zone_reduce<kZoneFew><<<g2, 256, 0, ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid.p, d.nbar.p, d.zone_part2.p, ticket, d.pbar.p);
+      k_zone_reduce<kZoneFew><<<g2, 256, 0, ctx->stream>>>((int32_t)ctx->N, (int32_t)ctx->n_mat, d.matid8.p, d.nbar.p, d.zone_part2.p, ticket, d.pbar.p);
       ctx->launches++;
     } else {
       const int nblocks = (int)((ctx->N + kZoneChunk - 1) / kZoneChunk);
