@@ -68,11 +68,12 @@ def _descs(f: dict):
 
 
 def _options(lib, device=0, tile_cells=256, reorder=True, strict=False, path=0, threads=0, vjp_variant=0, prefetch=0, face_blocks=True,
-             ude_generic=False):
+             ude_generic=False, pipeline_chunks=0):
     opt = L.Options()
     lib.hg_default_options(C.byref(opt))
     opt.device, opt.tile_cells, opt.reorder, opt.strict, opt.path = device, tile_cells, int(reorder), int(strict), path
     opt.reserved[0] = threads
+    opt.reserved[1] = int(pipeline_chunks)
     opt.reserved[2] = int(vjp_variant)
     opt.reserved[3] = int(prefetch)
     opt.reserved[4] = 0 if face_blocks else 1
@@ -101,11 +102,11 @@ class Context:
     (see INTEGRATION.md for how the Julia structs map onto them)."""
 
     def __init__(self, flat: dict, device=0, tile_cells=256, reorder=True, strict=False, path=0, threads=0, vjp_variant=0, prefetch=0,
-                 face_blocks=True, ude_generic=False):
+                 face_blocks=True, ude_generic=False, pipeline_chunks=0):
         self.lib = L.load()
         self._h = C.c_void_p()
         mesh, bc, fields, keep = _descs(flat)
-        opt = _options(self.lib, device, tile_cells, reorder, strict, path, threads, vjp_variant, prefetch, face_blocks, ude_generic)
+        opt = _options(self.lib, device, tile_cells, reorder, strict, path, threads, vjp_variant, prefetch, face_blocks, ude_generic, pipeline_chunks)
         rc = self.lib.hg_create(C.byref(self._h), C.byref(mesh), C.byref(bc), C.byref(fields), C.byref(opt))
         del keep            # the library copied what it needs (ownership rule of the ABI)
         if rc:

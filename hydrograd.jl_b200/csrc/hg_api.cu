@@ -511,6 +511,18 @@ int hg_get_rhs(hg_ctx* ctx, double* dQ) {
   return check_err_flag(ctx);
 }
 
+// rows [r0, r1) of the three components of a [3][N] vector in ONE strided copy (beyond the 2 GiB pitch limit of
+// cudaMemcpy2D -- more than 268M cells -- component by component)
+static cudaError_t copy3_rows(double* dst, const double* src, int64_t N, int64_t r0, int64_t r1, cudaMemcpyKind kind, cudaStream_t s) {
+  if ((size_t)N * 8 < ((size_t)1 << 31))
+    return cudaMemcpy2DAsync(dst + r0, (size_t)N * 8, src + r0, (size_t)N * 8, (size_t)(r1 - r0) * 8, 3, kind, s);
+  for (int q = 0; q < 3; ++q) {
+    const cudaError_t e = cudaMemcpyAsync(dst + q * N + r0, src + q * N + r0, (size_t)(r1 - r0) * 8, kind, s);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 // Host-buffer RHS as a three-stream pipeline: the state arrives over PCIe in reference-order chunks (s_in); after each
 // chunk the compute stream scatters it into the internal order and runs every tile whose cells and halo have landed;
 // finished chunks of dQdt are gathered back and leave on s_out while later chunks are still arriving.  PCIe is full
@@ -525,8 +537,7 @@ static int rhs_pipelined(hg_ctx* ctx, const double* Q, double* dQdt) {
   CK(ctx, cudaStreamSynchronize(sc));
   for (int c = 0; c < K; ++c) {
     const int64_t r0 = c * csz, r1 = std::min<int64_t>(N, r0 + csz);
-    for (int q = 0; q < 3; ++q)
-      CK(ctx, cudaMemcpyAsync(d.stage.p + q * N + r0, Q + q * N + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    CK(ctx, copy3_rows(d.stage.p, Q, N, r0, r1, cudaMemcpyHostToDevice, ctx->s_in));
     CK(ctx, cudaEventRecord(ctx->ev_in[c], ctx->s_in));
   }
   for (int s = 0; s < K; ++s) {
@@ -543,8 +554,7 @@ static int rhs_pipelined(hg_ctx* ctx, const double* Q, double* dQdt) {
       TRY(hg::fused_permute_range(ctx, false, d.dQ.p, d.stage_out.p, q0, q1));
       CK(ctx, cudaEventRecord(ctx->ev_cmp[c], sc));
       CK(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[c], 0));
-      for (int q = 0; q < 3; ++q)
-        CK(ctx, cudaMemcpyAsync(dQdt + q * N + q0, d.stage_out.p + q * N + q0, (q1 - q0) * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+      CK(ctx, copy3_rows(dQdt, d.stage_out.p, N, q0, q1, cudaMemcpyDeviceToHost, ctx->s_out));
     }
   }
   CK(ctx, cudaStreamSynchronize(ctx->s_out));
@@ -589,10 +599,8 @@ static int vjp_pipelined(hg_ctx* ctx, const double* Q, const double* lambda, dou
   CK(ctx, cudaStreamSynchronize(sc));
   for (int c = 0; c < K; ++c) {
     const int64_t r0 = c * csz, r1 = std::min<int64_t>(N, r0 + csz);
-    for (int q = 0; q < 3; ++q) {
-      CK(ctx, cudaMemcpyAsync(d.stage.p + q * N + r0, Q + q * N + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-      CK(ctx, cudaMemcpyAsync(d.stage_lam.p + q * N + r0, lambda + q * N + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-    }
+    CK(ctx, copy3_rows(d.stage.p, Q, N, r0, r1, cudaMemcpyHostToDevice, ctx->s_in));
+    CK(ctx, copy3_rows(d.stage_lam.p, lambda, N, r0, r1, cudaMemcpyHostToDevice, ctx->s_in));
     CK(ctx, cudaEventRecord(ctx->ev_in[c], ctx->s_in));
   }
   for (int s = 0; s < K; ++s) {
@@ -611,8 +619,7 @@ static int vjp_pipelined(hg_ctx* ctx, const double* Q, const double* lambda, dou
       TRY(hg::fused_permute_range(ctx, false, d.Qbar.p, d.stage_out.p, q0, q1));
       CK(ctx, cudaEventRecord(ctx->ev_cmp[c], sc));
       CK(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[c], 0));
-      for (int q = 0; q < 3; ++q)
-        CK(ctx, cudaMemcpyAsync(Qbar + q * N + q0, d.stage_out.p + q * N + q0, (q1 - q0) * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+      CK(ctx, copy3_rows(Qbar, d.stage_out.p, N, q0, q1, cudaMemcpyDeviceToHost, ctx->s_out));
     }
   }
   CK(ctx, cudaStreamSynchronize(ctx->s_out));

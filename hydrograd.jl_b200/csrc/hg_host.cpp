@@ -585,7 +585,8 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
   }
   // ---- stages of the host-buffer pipeline
   {
-    const int32_t K = N >= (1 << 20) ? (int32_t)std::min<int64_t>(32, std::max<int64_t>(8, N >> 19)) : 1;   // ~0.5M cells (12 MB) per chunk
+    int32_t K = N >= (1 << 20) ? (int32_t)std::min<int64_t>(32, std::max<int64_t>(8, N >> 19)) : 1;   // ~0.5M cells (12 MB) per chunk
+    if (ctx->opt.reserved[1] > 0) K = (int32_t)std::min<int64_t>(ctx->opt.reserved[1], std::max<int64_t>(1, N / 1024));   // tuning override
     fh.n_chunks = K;
     const int64_t csz = (N + K - 1) / K;
     std::vector<int32_t> tstage(fh.n_tiles, 0);

@@ -132,7 +132,7 @@ typedef struct {
   int32_t strict;                  /* 1 = reference evaluation order, no FMA contraction         */
   int32_t path;                    /* 0 = fused tile kernel, 1 = plain 3-kernel path (ghost/face/cell) */
   int32_t reserved[11];            /* reserved[0]: threads per CTA of the fused kernel (0 = default), tuning only;
-                                      reserved[1]: unused;
+                                      reserved[1]: chunks of the host-buffer pipeline of hg_rhs / hg_rhs_vjp (0 = default), tuning only;
                                       reserved[2]: launch-shape variant of the VJP kernel (0 = default), tuning only;
                                       reserved[3]: L2 prefetch distance in tiles (0 = one residency ahead, -1 = off);
                                       reserved[4]: 1 = do not regroup a tile's faces into bank-conflict-free blocks of 16;
