@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libhydrograd_b200.so")
 
 c_i64p = C.POINTER(C.c_int64)
 c_f64p = C.POINTER(C.c_double)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int64, C.c_void_p)
 c_u8p = C.POINTER(C.c_uint8)
 
 PARAM_NONE, PARAM_ZB, PARAM_MANNING, PARAM_Q, PARAM_UDE = 0, 1, 2, 3, 4
@@ -126,6 +127,7 @@ SYMBOLS = {
     "hg_comm_set_auto": (C.c_int, [_vp, C.c_int32]),
     "hg_comm_exchange": (C.c_int, [_vp, C.c_int32]),
     "hg_comm_disconnect": (C.c_int, [_vp]),
+    "hg_comm_set_allreduce": (C.c_int, [_vp, ALLREDUCE_FN, C.c_void_p]),
     "hg_debug_math": (C.c_int, [_vp, C.c_int32, C.c_int64, c_f64p, c_f64p]),
     "hg_time_jvp": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "hg_time_rhs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_float)]),

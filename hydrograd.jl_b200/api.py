@@ -305,6 +305,17 @@ class Context:
     def comm_exchange(self, with_lambda=False):
         self._ck(self.lib.hg_comm_exchange(self._h, int(with_lambda)))
 
+    def comm_set_allreduce(self, fn):
+        """fn(numpy view of the doubles to sum over ranks, in place).  Needed by adaptive solves on multi-rank contexts."""
+        def cb(ptr, n, _user):
+            try:
+                fn(np.ctypeslib.as_array(ptr, shape=(n,)))
+                return 0
+            except Exception:  # noqa: BLE001 -- never raise through the C boundary
+                return 1
+        self._allreduce_cb = L.ALLREDUCE_FN(cb)          # keep the trampoline alive as long as the context
+        self._ck(self.lib.hg_comm_set_allreduce(self._h, self._allreduce_cb, None))
+
     def comm_disconnect(self):
         self._ck(self.lib.hg_comm_disconnect(self._h))
 

@@ -1245,7 +1245,13 @@ int solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, 
   if (adaptive && (!(abstol > 0.0) || !(reltol > 0.0))) { ctx->err = "hg_solve_tsit5: tolerances must be positive"; return HG_ERR_ARG; }
   if (!ctx->state_set) { ctx->err = "hg_solve_tsit5: no resident state"; return HG_ERR_STATE; }
   if (ctx->opt.path == 1) { ctx->err = "hg_solve_tsit5 needs the fused path (path=0)"; return HG_ERR_ARG; }
-  if (ctx->n_halo > 0) { ctx->err = "hg_solve_tsit5: multi-rank contexts are not supported"; return HG_ERR_ARG; }
+  // multi-rank contexts: the stages exchange their halos through the library transport; the adaptive controller needs the
+  // error norm of the WHOLE mesh, i.e. a sum over ranks -- done on the host by the caller's all-reduce (hg_comm_set_allreduce)
+  if (ctx->n_halo > 0 && !hg_comm_ready(ctx)) { ctx->err = "hg_solve_tsit5: multi-rank context without a library-owned halo exchange (hg_comm_connect)"; return HG_ERR_ARG; }
+  if (ctx->n_halo > 0 && adaptive && !ctx->allreduce) {
+    ctx->err = "hg_solve_tsit5: an adaptive solve on a multi-rank context needs hg_comm_set_allreduce (the error norm is a sum over ranks)";
+    return HG_ERR_ARG;
+  }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   static const double A[7][6] = {
       {0, 0, 0, 0, 0, 0},
@@ -1317,7 +1323,9 @@ int solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, 
         double sum = 0.0;
         CK(ctx, cudaMemcpyAsync(&sum, d.ts_sum.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
-        eest = std::sqrt(sum / (3.0 * (double)ctx->N));
+        double tot[2] = {sum, 3.0 * (double)ctx->N};
+        if (ctx->n_halo > 0 && ctx->allreduce(tot, 2, ctx->allreduce_user) != 0) { ctx->err = "hg_solve_tsit5: the caller's all-reduce failed"; return HG_ERR_STATE; }
+        eest = std::sqrt(tot[0] / tot[1]);
         if (!(eest == eest)) { ctx->err = "hg_solve_tsit5: the error estimate is NaN"; return HG_ERR_STATE; }
         if (eest == 0.0) { q11 = 0.0; q = 1.0 / qmax; }
         else {
@@ -1377,7 +1385,9 @@ int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params, int64_
   if (!ctx || !Q0 || !lambda_T || !Q0bar || nsteps < 1 || !(dt > 0.0)) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "hg_euler_adjoint needs the fused path"; return HG_ERR_ARG; }
   TRY(no_closure(ctx, "hg_euler_adjoint"));
-  if (ctx->n_halo > 0) { ctx->err = "hg_euler_adjoint: multi-rank contexts are not supported"; return HG_ERR_ARG; }
+  // multi-rank contexts: every RHS / VJP of the sweeps exchanges state (and cotangent) halos through the library transport;
+  // Q0bar covers the owned cells, pbar is this rank's partial sum (the caller adds the ranks' pbar in rank order)
+  if (ctx->n_halo > 0 && !hg_comm_ready(ctx)) { ctx->err = "hg_euler_adjoint: multi-rank context without a library-owned halo exchange (hg_comm_connect)"; return HG_ERR_ARG; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
   if (ctx->active != HG_PARAM_NONE && !pbar) { ctx->err = "hg_euler_adjoint: pbar is NULL"; return HG_ERR_ARG; }
@@ -1463,7 +1473,7 @@ static int rk_adjoint_impl(hg_ctx* ctx, int32_t method, const double* Q0, const 
                            const double* hs, int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar) {
   if (ctx->opt.path == 1) { ctx->err = "hg_rk_adjoint needs the fused path"; return HG_ERR_ARG; }
   TRY(no_closure(ctx, "hg_rk_adjoint"));
-  if (ctx->n_halo > 0) { ctx->err = "hg_rk_adjoint: multi-rank contexts are not supported"; return HG_ERR_ARG; }
+  if (ctx->n_halo > 0 && !hg_comm_ready(ctx)) { ctx->err = "hg_rk_adjoint: multi-rank context without a library-owned halo exchange (hg_comm_connect)"; return HG_ERR_ARG; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
   if (ctx->active != HG_PARAM_NONE && !pbar) { ctx->err = "hg_rk_adjoint: pbar is NULL"; return HG_ERR_ARG; }

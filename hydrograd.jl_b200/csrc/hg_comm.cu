@@ -182,6 +182,12 @@ int hg_comm_set_auto(hg_ctx* ctx, int32_t on) {
   return HG_OK;
 }
 
+int hg_comm_set_allreduce(hg_ctx* ctx, hg_allreduce_fn fn, void* user) {
+  if (!ctx) return HG_ERR_ARG;
+  ctx->allreduce = fn; ctx->allreduce_user = user;
+  return HG_OK;
+}
+
 int hg_comm_exchange(hg_ctx* ctx, int32_t with_lambda) {
   if (!ctx) return HG_ERR_ARG;
   if (!ctx->state_set || (with_lambda && !ctx->lam_set)) { ctx->err = "hg_comm_exchange: state or lambda not set"; return HG_ERR_STATE; }

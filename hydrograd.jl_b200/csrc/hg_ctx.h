@@ -262,7 +262,9 @@ struct hg_ctx {
   hg::FusedHost fh;
   bool fjvp_ready = false;     // hg_fjvp.cu: kernel attributes set
   int32_t fh_force_nf = 0;     // build_tiles: face slots per cell of the attempt being built (4 or 8)
-  hg_comm* comm = nullptr;   // library-owned halo exchange (hg_comm.cu); null = the caller moves halo_send -> halo_recv
+  hg_comm* comm = nullptr;
+  hg_allreduce_fn allreduce = nullptr;   // sum over ranks on the host (adaptive solves on multi-rank contexts), hg_comm_set_allreduce
+  void* allreduce_user = nullptr;   // library-owned halo exchange (hg_comm.cu); null = the caller moves halo_send -> halo_recv
   hg::FusedDev fd;
   double* h_pinned = nullptr;  // staging [6N] pinned host memory
   size_t h_pinned_bytes = 0;

@@ -351,3 +351,17 @@ def connect_ranks(ctx, info, group=None):
         off, idx = _peer_tables(rank, info["neighbors"], tables)
         ctx.comm_connect([everyone[q][0] for q in info["neighbors"]], off, idx)
     dist.barrier(group)
+
+
+def attach_allreduce(ctx, group=None):
+    """Sum over ranks for the global scalars of adaptive solves (hg_comm_set_allreduce) through torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+
+    def allreduce(buf):
+        t = torch.tensor(buf, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, group=group)
+        buf[:] = t.cpu().numpy()
+
+    ctx.comm_set_allreduce(allreduce)

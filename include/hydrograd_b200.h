@@ -288,7 +288,9 @@ HG_API int hg_step_ab3(hg_ctx* ctx, double dt, int64_t nsteps, int32_t restart);
  * (adaptive) or the fixed step.  t_save[n_save] in [t0, t1] are stops at which the state is copied to Q_save[n_save][3N]
  * (reference order); OrdinaryDiffEq interpolates its saves instead (hg_solve_tsit5_dense), both agree within the
  * integration tolerance.
- * stats[3] (may be NULL) = accepted steps, rejected steps, RHS evaluations. */
+ * stats[3] (may be NULL) = accepted steps, rejected steps, RHS evaluations.
+ * Multi-rank contexts (after hg_comm_connect / hg_comm_init_shm): collective, every stage exchanges halos; an adaptive
+ * solve additionally needs hg_comm_set_allreduce (the error norm is summed over ranks), HG_ERR_ARG without it. */
 HG_API int hg_solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, double abstol, double reltol,
                           const double* t_save, int64_t n_save, double* Q_save, int64_t* stats);
 
@@ -311,7 +313,9 @@ HG_API int hg_solve_tsit5_dense(hg_ctx* ctx, double t0, double t1, double dt, in
  * solver inside compute_loss_inversion, swe_2D_inversion.jl:339): given lambda_T = d loss / d Q(T) it returns
  * Q0bar = d loss / d Q0 [3N] and pbar = d loss / d params [n_params] (NULL when active_param = NONE).  The forward
  * sweep keeps sqrt(nsteps)-spaced checkpoints on the device, the reverse sweep recomputes each segment and calls the
- * VJP kernel once per step; the dry mask of custom_ODE_update_cells is a constant selector, like every other clamp. */
+ * VJP kernel once per step; the dry mask of custom_ODE_update_cells is a constant selector, like every other clamp.
+ * Multi-rank contexts with a connected transport (also hg_rk_adjoint / hg_rk_adjoint_steps): collective; Q0bar covers the
+ * owned cells and pbar is this rank's partial sum -- add the ranks' pbar in a fixed order. */
 HG_API int hg_euler_adjoint(hg_ctx* ctx, const double* Q0, const double* params, int64_t n_params, int32_t active_param,
                      double dt, int64_t nsteps, const double* lambda_T, double* Q_T, double* Q0bar, double* pbar);
 
@@ -372,6 +376,12 @@ HG_API int hg_comm_init_shm(hg_ctx* ctx, const char* job_name, int32_t rank, int
 HG_API int hg_comm_set_auto(hg_ctx* ctx, int32_t on);
 HG_API int hg_comm_exchange(hg_ctx* ctx, int32_t with_lambda);
 HG_API int hg_comm_disconnect(hg_ctx* ctx);   /* call after a barrier: peers must not push any more */
+/* Host-side sum over ranks for the few scalars that are global: the error norm of an adaptive hg_solve_tsit5 on a
+ * multi-rank context (two doubles per step).  fn adds inout[0..n) over all ranks in place and returns 0 (MPI_Allreduce,
+ * torch.distributed.all_reduce, Distributed.jl ...).  Everything else -- fixed-step solvers, the time adjoints -- needs no
+ * global sum: Q0bar covers the owned cells, pbar is the rank's partial sum.                                              */
+typedef int (*hg_allreduce_fn)(double* inout, int64_t n, void* user);
+HG_API int hg_comm_set_allreduce(hg_ctx* ctx, hg_allreduce_fn fn, void* user);
 
 /* Multi-GPU overlap of the halo exchange with the tiles that need no remote cell.  phase 1: everything that does not
  * touch a halo face (launch it right after hg_halo_pack, while the exchange is in flight on another stream); phase 2: the

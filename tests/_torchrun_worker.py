@@ -58,6 +58,30 @@ def main():
         single.set_state(Q0); single.step_ab3(1e-3, 4); ref_ab = single.get_state()
         ctx.set_state(info["Q"]); ctx.step_ab3(1e-3, 4)
         out["ipc_ab3_bitwise"] = bool(np.array_equal(ctx.get_state(), pick(ref_ab)))
+        # adaptive Tsit5: the stages exchange halos inside the call; the error norm is the one global scalar (host all-reduce).
+        # Its sum runs in another order than on one context, so the steps agree to rounding, not bitwise
+        P.attach_allreduce(ctx)
+        single.set_state(Q0); _, st1 = single.solve_tsit5(0.0, 0.05, 1e-3, adaptive=True, abstol=1e-8, reltol=1e-6); ref_ts = single.get_state()
+        ctx.set_state(info["Q"]); _, st2 = ctx.solve_tsit5(0.0, 0.05, 1e-3, adaptive=True, abstol=1e-8, reltol=1e-6)
+        out["ipc_tsit5_counts"] = [st1["accepted"], st1["rejected"], st2["accepted"], st2["rejected"]]
+        out["ipc_tsit5_err"] = float(np.abs(ctx.get_state() - pick(ref_ts)).max() / np.abs(ref_ts).max())
+        single.set_state(Q0); single.solve_tsit5(0.0, 4e-3, 1e-3, adaptive=False); ref_tf = single.get_state()
+        ctx.set_state(info["Q"]); ctx.solve_tsit5(0.0, 4e-3, 1e-3, adaptive=False)
+        out["ipc_tsit5_fixed_bitwise"] = bool(np.array_equal(ctx.get_state(), pick(ref_tf)))
+        # time adjoints: every RHS / VJP of the forward and reverse sweeps exchanges state / cotangent halos; Q0bar covers the
+        # owned cells, pbar is the rank's partial sum
+        par = dict(params=S.RIVER_N_ZONES.copy(), active="ManningN")
+        def summed(v):
+            t = torch.tensor(v, dtype=torch.float64, device="cuda" if one_gpu_each else "cpu"); dist.all_reduce(t); return t.cpu().numpy()
+        for name, run in (("euler", lambda c, q, l: c.euler_adjoint(q, l, 1e-3, 6, **par)),
+                          ("rk4", lambda c, q, l: c.rk_adjoint("RK4", q, l, 1e-3, 3, **par)),
+                          ("tsit5", lambda c, q, l: c.rk_adjoint("Tsit5", q, l, 1e-3, 3, **par))):
+            rQT, rbar, rp = run(single, Q0, lam)
+            gQT, gbar, gp = run(ctx, info["Q"], pick(lam))
+            out[f"adj_{name}_state_bitwise"] = bool(np.array_equal(gQT, pick(rQT)))
+            out[f"adj_{name}_q0bar_err"] = float(np.abs(gbar - pick(rbar)).max() / np.abs(rbar).max())
+            if rp.size:
+                out[f"adj_{name}_pbar_err"] = float(np.abs(summed(gp) - rp).max() / max(np.abs(rp).max(), 1e-300))
         dist.barrier()
         ctx.comm_disconnect()
         # ---- host-buffer calls on a mesh large enough for the three-stream pipeline (>= 1M cells per rank): hg_rhs / hg_rhs_vjp

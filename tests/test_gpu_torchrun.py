@@ -26,6 +26,10 @@ def test_two_ranks_match_single_context(tmp_path):
         assert o["ok"], o
         assert o["ipc_rhs_bitwise"] and o["ipc_euler_bitwise"] and o["ipc_rk4_bitwise"] and o["ipc_ab3_bitwise"], o
         assert o["ipc_vjp_err"] <= 1e-13, o
+        a1, r1, a2, r2 = o["ipc_tsit5_counts"]
+        assert (a1, r1) == (a2, r2) and a1 > 3 and o["ipc_tsit5_err"] <= 1e-11 and o["ipc_tsit5_fixed_bitwise"], o
+        for name in ("euler", "rk4", "tsit5"):
+            assert o[f"adj_{name}_state_bitwise"] and o[f"adj_{name}_q0bar_err"] <= 1e-12 and o[f"adj_{name}_pbar_err"] <= 1e-12, o
         assert o["pipe_rhs_bitwise"] and o["pipe_vjp_err"] <= 1e-13, o
         if o["one_gpu_each"]:
             assert o["nccl_rhs_bitwise"] and o["nccl_vjp_err"] <= 1e-13, o
