@@ -8,6 +8,7 @@ PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libhydrograd_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+COMMON += os.environ.get("HG_NVCC_EXTRA", "").split()   # experiment builds (e.g. -DHG_PHASE_CLOCKS); empty for the product
 SOURCES = [
     ("hg_host.cpp", ["-Xcompiler", "-fopenmp"]),     # the tile builder runs on all host cores
     ("hg_srh.cpp", []),

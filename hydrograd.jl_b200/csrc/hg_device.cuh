@@ -16,6 +16,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// raise the barrier's pending byte count WITHOUT arriving: lets a thread start copies before it knows the total
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -24,6 +28,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // L2 prefetch of a contiguous block (16-byte aligned, size a multiple of 16): nothing is written on the SM
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// L2 prefetch of [p, p + bytes) by one warp through the load/store path (prefetch.global.L2, one 64-byte chunk per lane and
+// trip).  The copy engine's cp.async.bulk.prefetch.L2 would take one of its operation slots per row, and that engine -- one
+// per SM, ~100 cycles per operation under load -- is what the tile kernels run out of first.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void warp_prefetch_l2(const void* p, uint32_t bytes, int lane) {
+  const char* c = static_cast<const char*>(p);
+  for (uint32_t off = (uint32_t)lane * 64u; off < bytes + 64u; off += 2048u) prefetch_l2(c + min(off, bytes - 1u));
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -201,6 +213,7 @@ struct TileCfg {
   X(14, 384, 480, 872, 4, 192, 3)     \
   X(4, 512, 672, 1124, 4, 384, 2)     \
   X(3, 512, 672, 1124, 4, 256, 2)     \
+  X(15, 240, 320, 536, 4, 128, 5)     \
   X(12, 224, 304, 504, 4, 128, 5)     \
   X(13, 224, 304, 504, 4, 160, 5)     \
   X(9, 192, 264, 436, 4, 160, 6)      \

@@ -261,7 +261,7 @@ int build_tiles(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& 
                 const std::vector<int32_t>& cf_nb, const std::vector<double>& cf_nx, const std::vector<double>& cf_ny,
                 const std::vector<double>& cf_len, const std::vector<int32_t>& cf_face) {
   int32_t want = ctx->opt.tile_cells > 0 ? ctx->opt.tile_cells : 256;
-  if (want != 128 && want != 192 && want != 224 && want != 256 && want != 384 && want != 512) HG_FAIL(ctx, HG_ERR_ARG, "tile_cells must be 128, 192, 224, 256, 384 or 512");
+  if (want != 128 && want != 192 && want != 224 && want != 240 && want != 256 && want != 384 && want != 512) HG_FAIL(ctx, HG_ERR_ARG, "tile_cells must be 128, 192, 224, 240, 256, 384 or 512");
   int32_t maxnf = 0;
   for (int64_t i = 0; i < ctx->N; ++i) maxnf = std::max(maxnf, cf_ptr[i + 1] - cf_ptr[i]);
   if (maxnf > 4) want = 128;

@@ -389,6 +389,12 @@ __device__ __forceinline__ void vjp_boundary_face(Smem& sm, const VjpArgs& a, in
 
 // The common path needs ~90 registers; TH x MB is picked per tile size so that MB CTAs fit next to each other in
 // shared memory and TH*MB*regs <= 64K (vjp_pick below).
+#ifdef HG_PHASE_CLOCKS   // experiment builds only: where a CTA's lifetime goes (thread 0's clock at the phase boundaries)
+__device__ unsigned long long g_phase_clk[8];
+#define PHASE_MARK(i) do { if (tid == 0) { const long long c_ = clock64(); atomicAdd(&g_phase_clk[i], (unsigned long long)(c_ - pc_)); pc_ = c_; } } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
 template <int T, int ML, int MF, int NF, int TH, int MB, int FPT>
 __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ VjpArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -397,24 +403,24 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
   constexpr int kThreads = TH;
 
   const int tid = threadIdx.x;
+#ifdef HG_PHASE_CLOCKS
+  long long pc_ = clock64();
+#endif
   const int t = a.tile_order ? __ldg(a.tile_order + a.tile_base + (int)blockIdx.x) : (int)blockIdx.x;
   const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc));
   const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 1);
   const int4 d2 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)t * kTileDesc) + 2);
-  const int32_t c0 = d0.x, nc = d0.y, hp = d0.z, nh = d0.w;
-  const int32_t fp = d1.x, nf = d1.y, nfp = d1.z;
-  const int32_t nint = d2.y, bfp = d2.z;
+  // Tiles are runs of T cells (build_tiles_T), so the cell range needs no descriptor: the per-cell rows are copied while
+  // the descriptor is still on its way from L2 (~600 cycles); only the face rows and the halo list wait for it.
+  const int32_t c0 = t * T, nc = min(T, a.N - c0);
   const int32_t ncp = (nc + 1) & ~1;
   const double g = a.c.g, hs = a.c.h_small;
   const int64_t Ns = a.Ns;
-  // bed elevation of a tile-local cell: only the (rare) faces with a dry side and boundary faces read it
-  auto zb_local = [&](int32_t l) { return a.zb[l < ncp ? c0 + l : __ldg(a.halo + hp + (l - ncp))]; };
-
   if (tid == 0) mbar_init(sm.bar, 1);
   __syncthreads();
   if (tid == 0) {
-    const uint32_t cb = (uint32_t)ncp * 8u, fb = (uint32_t)nfp * 8u;
-    mbar_expect_tx(sm.bar, 11u * cb + 3u * fb + (uint32_t)nfp * 4u + (uint32_t)(T * NF) * 2u);
+    const uint32_t cb = (uint32_t)ncp * 8u;
+    mbar_expect_tx_only(sm.bar, 11u * cb + (uint32_t)(T * NF) * 2u);
     bulk_g2s(sm.xi, a.Q + c0, cb, sm.bar);
     bulk_g2s(sm.u, a.Q + Ns + c0, cb, sm.bar);             // raw q_x; u replaces it in place
     bulk_g2s(sm.v, a.Q + 2 * Ns + c0, cb, sm.bar);         // raw q_y
@@ -422,16 +428,34 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     bulk_g2s(sm.m0, a.lam + c0, cb, sm.bar);
     bulk_g2s(sm.m1, a.lam + Ns + c0, cb, sm.bar);
     bulk_g2s(sm.m2, a.lam + 2 * Ns + c0, cb, sm.bar);
-    bulk_g2s(sm.o[0], a.face_nx + fp, fb, sm.bar);
-    bulk_g2s(sm.o[1], a.face_ny + fp, fb, sm.bar);
-    bulk_g2s(sm.o[2], a.face_len + fp, fb, sm.bar);
-    bulk_g2s(sm.lr, a.face_lr + fp, (uint32_t)nfp * 4u, sm.bar);
     bulk_g2s(sm.area, a.area + c0, cb, sm.bar);
     bulk_g2s(sm.mann, a.mann + c0, cb, sm.bar);
     bulk_g2s(sm.sx, a.S0x + c0, cb, sm.bar);
     bulk_g2s(sm.sy, a.S0y + c0, cb, sm.bar);
     bulk_g2s(sm.cf, a.cf_idx + (size_t)t * (T * NF), (uint32_t)(T * NF) * 2u, sm.bar);
   }
+  const int32_t hp = d0.z, nh = d0.w;
+  const int32_t fp = d1.x, nf = d1.y, nfp = d1.z;
+  const int32_t nint = d2.y, bfp = d2.z;
+  // bed elevation of a tile-local cell: only the (rare) faces with a dry side and boundary faces read it
+  auto zb_local = [&](int32_t l) { return a.zb[l < ncp ? c0 + l : __ldg(a.halo + hp + (l - ncp))]; };
+
+  // first trip of the halo gathers, part 1: the cell id
+  const int32_t hgi = tid < nh ? __ldg(a.halo + hp + tid) : -1;
+  PHASE_MARK(0);   // cell-row copies issued, descriptor here
+  // The bulk copies are all issued by one thread.  Measured (scripts/micro/bulk_issue.cu, profiles/round2_bulk_issue_micro.txt):
+  // a cp.async.bulk costs its thread ~48 cycles on an idle SM and ~100 under this kernel's load, the copy engine serialises
+  // them whoever issues (sixteen lanes of one instruction: 4800 cycles; four warps with four copies each: 1200 cycles per
+  // warp), and the engine's L2 prefetches queue behind the same port.
+  if (tid == 0) {
+    const uint32_t fb = (uint32_t)nfp * 8u;
+    mbar_expect_tx(sm.bar, 3u * fb + (uint32_t)nfp * 4u);   // the barrier's only arrival
+    bulk_g2s(sm.o[0], a.face_nx + fp, fb, sm.bar);
+    bulk_g2s(sm.o[1], a.face_ny + fp, fb, sm.bar);
+    bulk_g2s(sm.o[2], a.face_len + fp, fb, sm.bar);
+    bulk_g2s(sm.lr, a.face_lr + fp, (uint32_t)nfp * 4u, sm.bar);
+  }
+  PHASE_MARK(7);   // issue of the bulk copies (thread 0)
   // clamp + derived values + the factors of the derived map's transpose, for local cell l
   auto stage_cell = [&](int32_t l, double xi, double qx, double qy, double hst) {
     const double h0 = xi + hst;
@@ -446,19 +470,25 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     sm.h[l] = h; sm.u[l] = dry ? 0.0 : qx * rh; sm.v[l] = dry ? 0.0 : qy * rh; sm.s[l] = s;
     sm.sg[l] = s * rh; sm.rs2[l] = 0.5 * r; sm.dP[l] = g * (xe + hst);
   };
-  // halo cells: state + lambda/area
-  for (int32_t k = tid; k < nh; k += kThreads) {
-    const int32_t gi = __ldg(a.halo + hp + k);
-    const double xi = a.Q[gi], qx = a.Q[Ns + gi], qy = a.Q[2 * Ns + gi];
-    const double hst = a.hstill[gi];
-    const double rA = fast_rcp(a.area[gi]);
-    const double l0 = a.lam[gi], l1 = a.lam[Ns + gi], l2 = a.lam[2 * Ns + gi];
+  // halo cells (state + lambda / area), the only indirect reads: two dependent trips to L2 / HBM.  The values of the first
+  // trip (nh <= kThreads on all but ragged tilings) are only LOADED here; they are consumed after the owned cells of phase 1,
+  // whose bulk copies need one trip, so the gather latency passes behind that work instead of idling the CTA.
+  double hx = 0.0, hqx = 0.0, hqy = 0.0, hhst = 0.0, hA = 1.0, hl0 = 0.0, hl1 = 0.0, hl2 = 0.0;
+  if (hgi >= 0) {
+    hx = a.Q[hgi]; hqx = a.Q[Ns + hgi]; hqy = a.Q[2 * Ns + hgi];
+    hhst = a.hstill[hgi]; hA = a.area[hgi];
+    hl0 = a.lam[hgi]; hl1 = a.lam[Ns + hgi]; hl2 = a.lam[2 * Ns + hgi];
+  }
+  auto stage_halo = [&](int32_t k, double xi, double qx, double qy, double hst, double A, double l0, double l1, double l2) {
+    const double rA = fast_rcp(A);
     const int32_t l = ncp + k;
     sm.xi[l] = xi;
     stage_cell(l, xi, qx, qy, hst);
     sm.m0[l] = l0 * rA; sm.m1[l] = l1 * rA; sm.m2[l] = l2 * rA;
-  }
+  };
   if (a.prefetch > 0 && tid == kThreads - 1 && (int)blockIdx.x + a.prefetch < a.n_run) {
+    // L2 prefetch of the tile one residency ahead.  (Through the load/store path instead -- a warp of prefetch.global.L2 per
+    // row -- the kernel takes 1.13 ms instead of 0.81: the issuing warp stalls ~4500 cycles and holds up its CTA.)
     const int32_t wp = (int)blockIdx.x + a.prefetch;
     const int32_t tp = a.tile_order ? __ldg(a.tile_order + a.tile_base + wp) : wp;
     const int4 p0 = __ldg(reinterpret_cast<const int4*>(a.tile_desc + (size_t)tp * kTileDesc));
@@ -475,8 +505,10 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
     if (p0.w > 0) bulk_prefetch_l2(a.halo + p0.z, (uint32_t)((p0.w + 3) & ~3) * 4u);
     if (!a.tile_order && wp + a.prefetch < a.n_run) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tile_desc + (size_t)(wp + a.prefetch) * kTileDesc));
   }
+  PHASE_MARK(1);   // bulk copies and halo gathers issued (+ prefetch)
   if (a.cw.n > 0 && (int)blockIdx.x >= a.cw.from && (int)blockIdx.x < a.cw.to) comm_wait(a.cw, tid);   // band tile: phase 2b reads what the neighbours push
   mbar_wait(sm.bar, 0);
+  PHASE_MARK(2);   // wait for the bulk copies
 
   // ---- phase 1: owned cells, in place
   auto own_cell = [&](int32_t l) {
@@ -502,7 +534,14 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
       }
     }
   }
+  // the halo cells loaded above
+  if (hgi >= 0) stage_halo(tid, hx, hqx, hqy, hhst, hA, hl0, hl1, hl2);
+  for (int32_t k = tid + kThreads; k < nh; k += kThreads) {   // ragged tilings: further trips
+    const int32_t gi = __ldg(a.halo + hp + k);
+    stage_halo(k, a.Q[gi], a.Q[Ns + gi], a.Q[2 * Ns + gi], a.hstill[gi], a.area[gi], a.lam[gi], a.lam[Ns + gi], a.lam[2 * Ns + gi]);
+  }
   __syncthreads();
+  PHASE_MARK(3);   // phase 1 + halo cells
 
   // ---- phase 2a: interior faces, common cases only.  Both sides wet: straight-line sweep with the derived map's
   // transpose folded in algebraically (roe_adj_core + fold_core_side, ~90 registers); both dry: zero flux, zero
@@ -571,10 +610,12 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
       sm.o[3][fB] = xB; sm.o[4][fB] = qxB; sm.o[5][fB] = qyB;
     }
   }
+  PHASE_MARK(4);   // phase 2a (thread 0's own faces)
   // ---- phase 2b: boundary faces (physical boundaries and halo faces)
   for (int32_t f = nint + tid; f < nf; f += kThreads) vjp_boundary_face(sm, a, f, nint, bfp, c0);
   if (tid < 6) sm.o[tid][nfp] = 0.0;   // the zero slot of unused cf entries
   __syncthreads();
+  PHASE_MARK(5);   // phase 2b + waiting for the slowest warp of phase 2
 
   // ---- phase 3: per-cell gather of the face adjoints (L or R side of each face) + source adjoint
   const double kfr = g / (a.c.k_n * a.c.k_n);
@@ -649,6 +690,7 @@ __global__ void __launch_bounds__(TH, MB) k_fused_vjp(const __grid_constant__ Vj
       }
     }
   }
+  PHASE_MARK(6);   // phase 3
 }
 
 // ---------------------------------------------------------------- boundary-wide couplings of the inlet-q split
@@ -899,7 +941,7 @@ VjpKernel vjp_pick(int v) {
     // fewer, larger tiles (measured at 16M cells: 0.89 ms vs 0.82 ms for T = 256 -- two CTAs per SM hide less latency)
     if (v == 1) return vjp_mk<T, ML, MF, NF, 256, 2, 1>();
     return vjp_mk<T, ML, MF, NF, 192, 2, 2>();
-  } else if constexpr (T == 224) {
+  } else if constexpr (T == 224 || T == 240) {
     // <= 512 interior faces per tile: the face phase is exactly two two-face trips of 128 threads (T = 256 needs a third, mostly empty one)
     if (v == 1) return vjp_mk<T, ML, MF, NF, 160, 3, 1>();
     return vjp_mk<T, ML, MF, NF, 128, 3, 2>();
@@ -987,6 +1029,21 @@ int fused_vjp_tiles(hg_ctx* ctx, int cfg_id, const double* d_Q, const double* d_
     if (le != cudaSuccess) { ctx->err = std::string("fused_vjp launch: ") + cudaGetErrorString(le); return HG_ERR_CUDA; }
   }
   ctx->launches++;
+#ifdef HG_PHASE_CLOCKS
+  {
+    static int n_launch = 0;
+    if (++n_launch % 40 == 0) {
+      unsigned long long h[8];
+      cudaStreamSynchronize(ctx->stream);
+      cudaMemcpyFromSymbol(h, g_phase_clk, sizeof(h));
+      const double den = 40.0 * (double)grid;
+      fprintf(stderr, "[phase clocks / tile] desc %.0f  issue %.0f  copy wait %.0f  phase1+halo %.0f  phase2a %.0f  phase2b+sync %.0f  phase3 %.0f  (bulk-copy issue %.0f)\n",
+              h[0] / den, h[1] / den, h[2] / den, h[3] / den, h[4] / den, h[5] / den, h[6] / den, h[7] / den);
+      memset(h, 0, sizeof(h));
+      cudaMemcpyToSymbol(g_phase_clk, h, sizeof(h));
+    }
+  }
+#endif
   return HG_OK;
 }
 
