@@ -14,7 +14,7 @@ SOURCES = [
     ("hg_srh.cpp", []),
     ("hg_partition.cpp", []),
     ("hg_results.cpp", []),
-    ("hg_api.cu", []),
+    ("hg_api.cu", ["-Xcompiler", "-fopenmp"]),       # hg_create permutes the per-cell fields on all host cores
     ("hg_plain.cu", ["-fmad=false"]),      # reference evaluation order, no FMA contraction
     ("hg_jvp.cu", ["-fmad=false"]),        # forward mode on the plain tables, same arithmetic rules
     ("hg_fused.cu", []),

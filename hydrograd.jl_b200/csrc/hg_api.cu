@@ -60,7 +60,9 @@ int upN(hg_ctx* ctx, hg::DBuf<T>& b, const std::vector<T>& h, size_t padded) {
 template <class T>
 std::vector<T> permuted(const T* src, const std::vector<int32_t>& perm) {
   std::vector<T> o(perm.size());
-  for (size_t i = 0; i < perm.size(); ++i) o[i] = src[perm[i]];
+  const int64_t n = (int64_t)perm.size();
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) o[i] = src[perm[i]];
   return o;
 }
 
@@ -216,6 +218,7 @@ void hg_destroy(hg_ctx* ctx) {
 }
 
 static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f) {
+  hg::StageTimer whole_timer("hg_create (all of the above)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     ctx->err = "no CUDA device available (this library has no CPU fallback)";
@@ -229,10 +232,13 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     ctx->err = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this build is sm_100a only";
     return HG_ERR_CUDA;
   }
-  CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  ctx->own_stream = ctx->stream;
-  CK(ctx, cudaEventCreate(&ctx->ev0));
-  CK(ctx, cudaEventCreate(&ctx->ev1));
+  {
+    hg::StageTimer cuda_timer("cuda context + stream");
+    CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = ctx->stream;
+    CK(ctx, cudaEventCreate(&ctx->ev0));
+    CK(ctx, cudaEventCreate(&ctx->ev1));
+  }
 
   std::vector<int32_t> cf_ptr, cf_nb, cf_face;
   std::vector<double> cf_nx, cf_ny, cf_len;
@@ -240,22 +246,37 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
   const int64_t N = ctx->N, B = ctx->B;
   hg_ctx* x = ext(ctx);
   Frozen& fr = x->fr;
-  fr.mann_ref.assign(f->ManningN_cells, f->ManningN_cells + N);
-  fr.zb_ref.assign(f->zb_cells, f->zb_cells + N);
-  fr.S0_ref.assign(f->S0_cells, f->S0_cells + 2 * N);
-  fr.zbg_ghost.assign(f->zb_ghost, f->zb_ghost + B);
+  hg::StageTimer* frozen_timer = new hg::StageTimer("frozen field copies");
+#pragma omp parallel sections   // ~0.8 GB of host copies on a 16M-cell mesh: one thread per field
+  {
+#pragma omp section
+    fr.mann_ref.assign(f->ManningN_cells, f->ManningN_cells + N);
+#pragma omp section
+    fr.zb_ref.assign(f->zb_cells, f->zb_cells + N);
+#pragma omp section
+    fr.S0_ref.assign(f->S0_cells, f->S0_cells + 2 * N);
+#pragma omp section
+    fr.zbg_ghost.assign(f->zb_ghost, f->zb_ghost + B);
+  }
   fr.Qin.assign(f->inletQ_TotalQ, f->inletQ_TotalQ + ctx->n_inletq);
   fr.wse.assign(f->exitH_WSE, f->exitH_WSE + ctx->n_exith);
   if (f->matID_cells) {
     x->matid_ref.resize(N);
+    const int64_t nmat = std::max<int64_t>(f->n_mat, 1);
+    int bad_id = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad_id)
     for (int64_t i = 0; i < N; ++i) {
-      if (f->matID_cells[i] < 0 || f->matID_cells[i] >= std::max<int64_t>(f->n_mat, 1)) { ctx->err = "matID_cells out of range"; return HG_ERR_ARG; }
+      bad_id |= (f->matID_cells[i] < 0 || f->matID_cells[i] >= nmat) ? 1 : 0;
       x->matid_ref[i] = (int32_t)f->matID_cells[i];
     }
+    if (bad_id) { ctx->err = "matID_cells out of range"; return HG_ERR_ARG; }
   }
+  delete frozen_timer;
   const hg::BcHost& h = ctx->bch;
   const size_t npar = (size_t)std::max<int64_t>(std::max<int64_t>(N, ctx->n_mat), std::max<int64_t>(ctx->n_inletq, 1));
-  std::vector<double> hstill(f->hstill, f->hstill + N), area(m->cell_areas, m->cell_areas + N);
+  std::vector<double> hstill, area;   // host copies only where a table is uploaded in reference order
+  if (ctx->opt.path == 1) hstill.assign(f->hstill, f->hstill + N);
+  area.assign(m->cell_areas, m->cell_areas + N);
 
   if (ctx->opt.path == 1) {
     hg::PlainDev& p = ctx->pd;
@@ -282,7 +303,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(up(ctx, d.halo, fh.halo)); TRY(up(ctx, d.bface_e, fh.bface_e));
     TRY(up(ctx, d.face_lr, fh.face_lr)); TRY(up(ctx, d.cf_idx, fh.cf_idx));
     TRY(up(ctx, d.face_nx, fh.face_nx)); TRY(up(ctx, d.face_ny, fh.face_ny)); TRY(up(ctx, d.face_len, fh.face_len));
-    TRY(upN(ctx, d.area, permuted(area.data(), fh.perm), Ns)); TRY(upN(ctx, d.hstill, permuted(hstill.data(), fh.perm), Ns));
+    TRY(upN(ctx, d.area, permuted(m->cell_areas, fh.perm), Ns)); TRY(upN(ctx, d.hstill, permuted(f->hstill, fh.perm), Ns));
     TRY(al(ctx, d.zb, Ns)); TRY(al(ctx, d.S0x, Ns)); TRY(al(ctx, d.S0y, Ns)); TRY(al(ctx, d.mann, Ns));
     if (!x->matid_ref.empty()) {
       auto mid = permuted(x->matid_ref.data(), fh.perm);
@@ -339,7 +360,10 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     TRY(hg::fused_prepare(ctx));
     TRY(hg::fused_vjp_prepare(ctx, hg::fused_cfg_id(ctx)));
   }
-  TRY(upload_fields(ctx));
+  {
+    hg::StageTimer fields_timer("fields (permute+H2D)");
+    TRY(upload_fields(ctx));
+  }
   return HG_OK;
 }
 

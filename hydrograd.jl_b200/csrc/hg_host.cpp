@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <omp.h>
 
 #include "hg_ctx.h"
 
@@ -69,7 +70,20 @@ int build_host(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg
   }
   const int64_t S = cf_ptr[N];
   ctx->sumnf = S;
-  cf_nb.resize(S); cf_nx.resize(S); cf_ny.resize(S); cf_len.resize(S); cf_face.resize(S);
+  // (value-initialising ~2 GB of tables on a 16M-cell mesh costs a second on one thread: one thread per table)
+#pragma omp parallel sections
+  {
+#pragma omp section
+    cf_nb.resize(S);
+#pragma omp section
+    cf_nx.resize(S);
+#pragma omp section
+    cf_ny.resize(S);
+#pragma omp section
+    cf_len.resize(S);
+#pragma omp section
+    cf_face.resize(S);
+  }
   int64_t bad_cell = -1, bad_face = -1;
   int bad_kind = 0;   // 1 face id, 2 ghost id, 3 neighbour id
 #pragma omp parallel for schedule(static)
@@ -237,17 +251,21 @@ struct Rcb {
 }  // namespace
 
 // Kuhn's augmenting path on the 16 x 16 bank graph: L bank l looks for an R bank, preferring the pair with most faces left
-static bool bank_augment(int l, bool* seen, int* matchR, int* matchL, const int (*cnt)[16]) {
-  int cand[16], nc = 0;
-  for (int r = 0; r < 16; ++r) if (cnt[l][r] > 0 && !seen[r]) cand[nc++] = r;
-  std::sort(cand, cand + nc, [&](int x, int y) { return cnt[l][x] > cnt[l][y]; });
-  for (int k = 0; k < nc; ++k) {
-    const int r = cand[k];
-    if (seen[r]) continue;
-    seen[r] = true;
-    if (matchR[r] < 0 || bank_augment(matchR[r], seen, matchR, matchL, cnt)) { matchR[r] = l; matchL[l] = r; return true; }
+static bool bank_augment(int l, uint32_t& seen, const uint32_t* adj, int* matchR, int* matchL, const int (*cnt)[16]) {
+  // adj[l]: bit r set while faces (l, r) are left.  Candidates = the R banks unseen on entry, visited by (faces left desc,
+  // bank asc); `seen` only grows, so picking the best still-unseen one each time visits them in exactly that order without
+  // building and sorting a list.  The bank graph is sparse (two or three R banks per L bank), hence the bit masks.
+  const uint32_t cand = adj[l] & ~seen;
+  for (;;) {
+    int r = -1;
+    for (uint32_t q = cand & ~seen; q; q &= q - 1) {
+      const int b = __builtin_ctz(q);
+      if (r < 0 || cnt[l][b] > cnt[l][r]) r = b;
+    }
+    if (r < 0) return false;
+    seen |= 1u << r;
+    if (matchR[r] < 0 || bank_augment(matchR[r], seen, adj, matchR, matchL, cnt)) { matchR[r] = l; matchL[l] = r; return true; }
   }
-  return false;
 }
 
 static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<int32_t>& cf_ptr,
@@ -310,13 +328,14 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
   }
   fh.n_tiles = (int32_t)((N + T - 1) / T);
   fh.iperm.resize(N);
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < N; ++i) fh.iperm[fh.perm[i]] = (int32_t)i;
 
   std::vector<int32_t> ghost_entry(B);
   for (int64_t e = 0; e < B; ++e) ghost_entry[ctx->bch.ghost[e]] = (int32_t)e;
 
   fh.tile_desc.assign((size_t)fh.n_tiles * kTileDesc, 0);
-  fh.cf_idx.assign((size_t)fh.n_tiles * T * NF, 0);
+  fh.cf_idx.assign((size_t)fh.n_tiles * T * NF, (uint16_t)0xFFFFu);   // "unset": pass C replaces what is left by the zero-flux slot
 
   // Every tile is built independently (OpenMP) into its own TileOut with tile-local scratch -- a cell is "in the tile" iff
   // its internal id lies in [c0, c1), halo cells and face ids are looked up in small sorted lists -- and the per-tile pieces
@@ -335,8 +354,20 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     if (first_err == HG_OK) { first_err = code; first_msg = msg; }
   };
   StageTimer tiles_timer("tile tables");
-#pragma omp parallel for schedule(dynamic, 16)
+  double TT[6] = {0, 0, 0, 0, 0, 0};   // thread-seconds per stage of the tile loop (printed with HG_DEBUG_TIMING)
+  // sA / sB: the gather-map slots (local cell * NF + position in the cell's face list) of the one or two OWNED cells of the
+  // face -- pass C fills them once the face's place in the tile is known
+  struct TF { int32_t lL, lR, fid, sA, sB; double nx, ny, len; };
+#pragma omp parallel
+  {
+  // per-thread scratch, reused from tile to tile (the allocator was a quarter of this loop)
+  std::vector<TF> tf, sorted, out;
+  std::vector<uint64_t> key;
+  std::vector<int32_t> bucket;
+#pragma omp for schedule(dynamic, 16)
   for (int32_t t = 0; t < fh.n_tiles; ++t) {
+    double tt0 = omp_get_wtime(), tt1;
+#define TTM(i) do { tt1 = omp_get_wtime(); _Pragma("omp atomic") TT[i] += tt1 - tt0; tt0 = tt1; } while (0)
     TileOut& o = outs[t];
     const int32_t c0 = t * T, c1 = (int32_t)std::min<int64_t>(N, (int64_t)c0 + T), nc = c1 - c0, ncp = (nc + 1) & ~1;
     // pass 0: the one-layer halo, in ascending internal order (so that the indirect loads of neighbouring lanes
@@ -356,9 +387,9 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     auto loc = [&](int32_t c) {   // tile-local index of an owned or halo cell
       return (c >= c0 && c < c1) ? c - c0 : ncp + (int32_t)(std::lower_bound(o.halo.begin(), o.halo.begin() + o.nh, c) - o.halo.begin());
     };
+    TTM(0);
     // pass A: interior faces, found by the first owned cell (internal order) that sees them ...
-    struct TF { int32_t lL, lR, fid; double nx, ny, len; };
-    std::vector<TF> tf;
+    tf.clear();
     bool bad = false;
     for (int32_t c = c0; c < c1 && !bad; ++c) {
       const int32_t r = fh.perm[c];
@@ -369,34 +400,43 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
         if (cn >= c0 && cn < c) continue;   // both cells owned: the face was taken when the smaller internal id saw it
         // canonical orientation: L = smaller REFERENCE id, normal taken from the L cell's own table
         int32_t lL, lR; double nx, ny;
-        if (r < rn) {
-          lL = loc(c); lR = loc(cn); nx = cf_nx[k]; ny = cf_ny[k];
-        } else {
-          lL = loc(cn); lR = loc(c);
-          int32_t kk = -1;
+        const bool cn_owned = cn >= c0 && cn < c1;
+        int32_t kk = -1;   // the face in the neighbour's own list
+        if (r > rn || cn_owned) {
           for (int32_t q = cf_ptr[rn]; q < cf_ptr[rn + 1]; ++q) if (cf_face[q] == fid) { kk = q; break; }
           if (kk < 0 || cf_nb[kk] != r) {
             tile_fail(HG_ERR_ARG, "face " + std::to_string(fid) + ": cells " + std::to_string(r) + " and " + std::to_string(rn) + " disagree on adjacency");
             bad = true;
             break;
           }
-          nx = cf_nx[kk]; ny = cf_ny[kk];
         }
-        tf.push_back({lL, lR, fid, nx, ny, cf_len[k]});
+        if (r < rn) {
+          lL = loc(c); lR = loc(cn); nx = cf_nx[k]; ny = cf_ny[k];
+        } else {
+          lL = loc(cn); lR = loc(c); nx = cf_nx[kk]; ny = cf_ny[kk];
+        }
+        tf.push_back({lL, lR, fid, (c - c0) * NF + (k - cf_ptr[r]), cn_owned ? (cn - c0) * NF + (kk - cf_ptr[rn]) : -1, nx, ny, cf_len[k]});
       }
     }
     if (bad) continue;
+    TTM(1);
     // ... then ordered by (lR - lL, lL): faces with the same index offset are consecutive, so a warp's L reads
     // and R reads of the cell arrays in shared memory each hit consecutive addresses (no bank conflicts), and so
     // do the per-cell flux gathers of phase 3.  Evaluation order per cell is unaffected (bitwise same result).
-    std::sort(tf.begin(), tf.end(), [](const TF& x, const TF& y) {
-      const int32_t dx = x.lR - x.lL, dy = y.lR - y.lL;
-      return dx != dy ? dx < dy : x.lL < y.lL;
-    });
+    {   // (sorting 64-bit keys and permuting once is twice as fast as sorting the records with a comparator)
+      key.resize(tf.size());
+      for (size_t k = 0; k < tf.size(); ++k)
+        key[k] = ((uint64_t)(uint32_t)(tf[k].lR - tf[k].lL + 0x10000) << 40) | ((uint64_t)(uint32_t)tf[k].lL << 20) | (uint64_t)k;
+      std::sort(key.begin(), key.end());
+      sorted.resize(tf.size());
+      for (size_t k = 0; k < tf.size(); ++k) sorted[k] = tf[key[k] & 0xFFFFFu];
+      tf.swap(sorted);
+    }
     // ... and regrouped into aligned blocks of 16 whose L cells fall into 16 distinct shared-memory banks
     // (8-byte banks: local index mod 16) and whose R cells do too: a 64-bit shared-memory load of a warp is served
     // per half-warp, so the 12 (RHS) / 22 (VJP) per-side gathers of the face phase become conflict-free.  Greedy
     // decomposition of the bipartite multigraph (bank of L) x (bank of R) into matchings; leftovers fill the tail.
+    TTM(2);
     if (ctx->opt.reserved[4] == 0 && tf.size() >= 32) {
       // bucket (bL, bR): the faces with that pair of banks in their original order (one counting sort into a flat array --
       // 256 small vectors per tile were 16M allocations on a 16M-cell mesh); cnt = how many are still unplaced
@@ -406,33 +446,36 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
         int run = 0;
         for (int l = 0; l < 16; ++l) for (int r = 0; r < 16; ++r) { off[l][r] = run; run += cnt[l][r]; }
       }
-      std::vector<int32_t> bucket(tf.size());
+      bucket.resize(tf.size());
       {
         int fill[16][16] = {};
         for (int32_t k = 0; k < (int32_t)tf.size(); ++k) { const int l = tf[k].lL & 15, r = tf[k].lR & 15; bucket[off[l][r] + fill[l][r]++] = k; }
       }
-      std::vector<TF> out;
+      out.clear();
       out.reserve(tf.size());
       size_t left = tf.size();
+      int degL[16] = {};   // unplaced faces per L bank
+      uint32_t adj[16] = {};
+      for (int l = 0; l < 16; ++l) for (int r = 0; r < 16; ++r) { degL[l] += cnt[l][r]; if (cnt[l][r] > 0) adj[l] |= 1u << r; }
       while (left > 0) {
         // maximum bipartite matching L banks -> R banks over the unplaced faces (Kuhn's augmenting paths, 16 x 16)
-        int matchR[16], matchL[16], degL[16] = {}, order[16];
+        int matchR[16], matchL[16], order[16];
         std::fill(matchR, matchR + 16, -1);
         std::fill(matchL, matchL + 16, -1);
-        for (int l = 0; l < 16; ++l) for (int r = 0; r < 16; ++r) degL[l] += cnt[l][r];
         std::iota(order, order + 16, 0);
         std::stable_sort(order, order + 16, [&](int x, int y) { return degL[x] > degL[y]; });   // fullest banks first
         for (int ol = 0; ol < 16; ++ol) {
           if (degL[order[ol]] == 0) continue;
-          bool seen[16] = {};
-          bank_augment(order[ol], seen, matchR, matchL, cnt);
+          uint32_t seen = 0;
+          bank_augment(order[ol], seen, adj, matchR, matchL, cnt);
         }
         int npick = 0, useL[16] = {}, useR[16] = {};
         for (int l = 0; l < 16; ++l) {
           const int r = matchL[l];
           if (r < 0) continue;
           out.push_back(tf[bucket[off[l][r] + head[l][r]++]]);
-          --cnt[l][r]; ++useL[l]; ++useR[r];
+          if (--cnt[l][r] == 0) adj[l] &= ~(1u << r);
+          --degL[l]; ++useL[l]; ++useR[r];
           ++npick;
         }
         // incomplete matching (only near the end of a tile): fill the block with the faces that add the fewest conflicts
@@ -446,7 +489,8 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
               if (cost < best) { best = cost; bl = l; br = r; }
             }
           out.push_back(tf[bucket[off[bl][br] + head[bl][br]++]]);
-          --cnt[bl][br]; ++useL[bl]; ++useR[br];
+          if (--cnt[bl][br] == 0) adj[bl] &= ~(1u << br);
+          --degL[bl]; ++useL[bl]; ++useR[br];
           ++npick;
         }
         left -= npick;
@@ -466,10 +510,17 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
       }
       fprintf(stderr, "[hg] tile %d: %zu interior faces, half-warp gather wavefronts L %.2f R %.2f\n", t, tf.size(), wl / nb, wr / nb);
     }
-    std::vector<std::pair<int32_t, int32_t>> floc;   // (face id, tile-local face index), sorted by face id below
-    floc.reserve(tf.size() + 16);
+    TTM(3);
+    // pass C (fused into the emission of the faces): NF slots per cell, local face ids in the reference's face order with the
+    // side bit (set when the cell is the R side); unused slots point at the zero-flux slot nfp (adding 0.0 last leaves the
+    // left-to-right sum unchanged)
+    uint16_t* slots = &fh.cf_idx[(size_t)t * T * NF];
+    const size_t nface_max = tf.size() + (size_t)nc * NF + 4;
+    o.face_lr.reserve(nface_max); o.nx.reserve(nface_max); o.ny.reserve(nface_max); o.len.reserve(nface_max);
     for (const TF& f : tf) {
-      floc.push_back({f.fid, (int32_t)o.face_lr.size()});
+      const int32_t lf = (int32_t)o.face_lr.size();
+      slots[f.sA] = (uint16_t)(lf | (f.lR == f.sA / NF ? 0x8000 : 0));
+      if (f.sB >= 0) slots[f.sB] = (uint16_t)(lf | (f.lR == f.sB / NF ? 0x8000 : 0));
       o.face_lr.push_back((uint32_t)f.lL | ((uint32_t)f.lR << 16));
       o.nx.push_back(f.nx); o.ny.push_back(f.ny); o.len.push_back(f.len);
     }
@@ -479,7 +530,7 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
       const int32_t r = fh.perm[c];
       for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k) {
         if (cf_nb[k] < N) continue;
-        floc.push_back({cf_face[k], (int32_t)o.face_lr.size()});
+        slots[(c - c0) * NF + (k - cf_ptr[r])] = (uint16_t)o.face_lr.size();
         o.face_lr.push_back((uint32_t)(c - c0) | (0xFFFFu << 16));
         o.bface_e.push_back(ghost_entry[cf_nb[k] - N]);
         o.nx.push_back(cf_nx[k]); o.ny.push_back(cf_ny[k]); o.len.push_back(cf_len[k]);
@@ -494,21 +545,8 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
       o.face_lr.push_back(0u); o.nx.push_back(1.0); o.ny.push_back(0.0); o.len.push_back(0.0);
     }
     o.nfp = (int32_t)o.face_lr.size();
-    std::sort(floc.begin(), floc.end());
-    // pass C: NF slots per cell, local face ids in the reference's face order with the side bit; unused
-    // slots point at the zero-flux slot nfp (adding 0.0 last leaves the left-to-right sum unchanged)
-    uint16_t* slots = &fh.cf_idx[(size_t)t * T * NF];
-    for (int32_t l = 0; l < T * NF; ++l) slots[l] = (uint16_t)o.nfp;
-    for (int32_t c = c0; c < c1; ++c) {
-      const int32_t r = fh.perm[c];
-      int32_t j = 0;
-      for (int32_t k = cf_ptr[r]; k < cf_ptr[r + 1]; ++k, ++j) {
-        const int32_t lf = std::lower_bound(floc.begin(), floc.end(), std::make_pair(cf_face[k], (int32_t)-1))->second;
-        const uint32_t lr = o.face_lr[lf];
-        const bool on_right = (cf_nb[k] < N) && ((int32_t)(lr >> 16) == c - c0);
-        slots[(c - c0) * NF + j] = (uint16_t)(lf | (on_right ? 0x8000 : 0));
-      }
-    }
+    for (int32_t l = 0; l < T * NF; ++l)
+      if (slots[l] == 0xFFFFu) slots[l] = (uint16_t)o.nfp;
     if (getenv("HG_DEBUG_TILES") && t == fh.n_tiles / 2) {
       // average wavefronts of a half-warp's gather of one flux row at slot j (1 = conflict-free; same face = broadcast)
       double w = 0; int ng = 0;
@@ -530,16 +568,29 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     }
     while (o.halo.size() % 4) o.halo.push_back(0);
     o.max_local = ncp + o.nh;
+    TTM(4);
   }
+  }   // omp parallel
+  if (getenv("HG_DEBUG_TIMING")) fprintf(stderr, "[hg] tile stages (thread-seconds): halo %.2f passA %.2f sort %.2f banks %.2f rest %.2f\n", TT[0], TT[1], TT[2], TT[3], TT[4]);
   if (first_err != HG_OK) { ctx->err = first_msg; return first_err; }
   // ---- concatenate at prefix-sum offsets
   {
+    StageTimer cat_timer("  concatenate");
     std::vector<size_t> fb(fh.n_tiles + 1, 0), hb(fh.n_tiles + 1, 0), bb(fh.n_tiles + 1, 0);
     for (int32_t t = 0; t < fh.n_tiles; ++t) {
       fb[t + 1] = fb[t] + outs[t].face_lr.size(); hb[t + 1] = hb[t] + outs[t].halo.size(); bb[t + 1] = bb[t] + outs[t].bface_e.size();
     }
-    fh.face_lr.resize(fb.back()); fh.face_nx.resize(fb.back()); fh.face_ny.resize(fb.back()); fh.face_len.resize(fb.back());
-    fh.halo.resize(hb.back()); fh.bface_e.resize(bb.back());
+#pragma omp parallel sections
+    {
+#pragma omp section
+      { fh.face_lr.resize(fb.back()); fh.halo.resize(hb.back()); fh.bface_e.resize(bb.back()); }
+#pragma omp section
+      fh.face_nx.resize(fb.back());
+#pragma omp section
+      fh.face_ny.resize(fb.back());
+#pragma omp section
+      fh.face_len.resize(fb.back());
+    }
     if (fb.back() >= ((size_t)1 << 31) || hb.back() >= ((size_t)1 << 31)) HG_FAIL(ctx, HG_ERR_ARG, "tile tables exceed 32-bit offsets");
 #pragma omp parallel for schedule(static)
     for (int32_t t = 0; t < fh.n_tiles; ++t) {
@@ -563,8 +614,17 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     }
   }
   fh.max_local = (fh.max_local + 1) & ~1;
+  if (getenv("HG_DEBUG_FINGERPRINT")) {   // fingerprint of the tile tables (to check that a change of the builder leaves them as they were)
+    auto fnv = [](const void* p, size_t n) { uint64_t h = 1469598103934665603ull; const unsigned char* c = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; } return h; };
+    fprintf(stderr, "[hg] tile tables fingerprint: lr %016llx cf %016llx halo %016llx nx %016llx len %016llx desc %016llx bface %016llx\n",
+            (unsigned long long)fnv(fh.face_lr.data(), fh.face_lr.size() * 4), (unsigned long long)fnv(fh.cf_idx.data(), fh.cf_idx.size() * 2),
+            (unsigned long long)fnv(fh.halo.data(), fh.halo.size() * 4), (unsigned long long)fnv(fh.face_nx.data(), fh.face_nx.size() * 8),
+            (unsigned long long)fnv(fh.face_len.data(), fh.face_len.size() * 8), (unsigned long long)fnv(fh.tile_desc.data(), fh.tile_desc.size() * 4),
+            (unsigned long long)fnv(fh.bface_e.data(), fh.bface_e.size() * 4));
+  }
   // ---- multi-GPU overlap: a tile belongs to the band if one of its boundary faces is a halo face
   {
+    StageTimer band_timer("  band order");
     std::vector<int32_t> band;
     fh.band_order.clear();
     for (int32_t t = 0; t < fh.n_tiles; ++t) {
@@ -585,11 +645,13 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
   }
   // ---- stages of the host-buffer pipeline
   {
+    StageTimer stage_timer("  pipeline stages");
     int32_t K = N >= (1 << 20) ? (int32_t)std::min<int64_t>(32, std::max<int64_t>(8, N >> 19)) : 1;   // ~0.5M cells (12 MB) per chunk
     if (ctx->opt.reserved[1] > 0) K = (int32_t)std::min<int64_t>(ctx->opt.reserved[1], std::max<int64_t>(1, N / 1024));   // tuning override
     fh.n_chunks = K;
     const int64_t csz = (N + K - 1) / K;
     std::vector<int32_t> tstage(fh.n_tiles, 0);
+#pragma omp parallel for schedule(static)
     for (int32_t t = 0; t < fh.n_tiles; ++t) {
       const int32_t* d = &fh.tile_desc[(size_t)t * kTileDesc];
       int32_t st = 0;
@@ -608,9 +670,11 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     for (int32_t t = 0; t < fh.n_tiles; ++t) fh.stage_ptr[tstage[t] + 1]++;
     for (int32_t k = 0; k < K; ++k) fh.stage_ptr[k + 1] += fh.stage_ptr[k];
     fh.chunk_done.assign(K, 0);
-    for (int64_t r = 0; r < N; ++r) {
-      const int32_t c = (int32_t)(r / csz), t = fh.iperm[r] / T;
-      fh.chunk_done[c] = std::max(fh.chunk_done[c], tstage[t]);
+#pragma omp parallel for schedule(static)
+    for (int32_t c = 0; c < K; ++c) {
+      int32_t done = 0;
+      for (int64_t r = c * csz; r < std::min<int64_t>(N, (c + 1) * csz); ++r) done = std::max(done, tstage[fh.iperm[r] / T]);
+      fh.chunk_done[c] = done;
     }
   }
   if (fh.halo.empty()) fh.halo.push_back(0);

@@ -1,13 +1,7 @@
 #!/bin/bash
-# one-off experiment driver: parity subset + timings with the product build, A/B against libhg_rhsA.so, phase clocks
+# full device suite + create-time breakdown + microbenchmark
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vjp.py tests/test_gpu_multirank.py -m gpu -x -q -p no:cacheprovider > gpurun_out/exp_tests.log 2>&1
-tail -3 gpurun_out/exp_tests.log | cut -c1-300
-cp hydrograd.jl_b200/libhydrograd_b200.so /tmp/libB.so
-for v in B A B A; do
-  if [ $v = A ]; then cp hydrograd.jl_b200/libhg_rhsA.so hydrograd.jl_b200/libhydrograd_b200.so; else cp /tmp/libB.so hydrograd.jl_b200/libhydrograd_b200.so; fi
-  echo "variant $v"; timeout 300 python scripts/tune_r2.py 16 256,0,0 2>&1 | tail -1 | cut -c1-400
-done | tee gpurun_out/exp_ab.log
-cp hydrograd.jl_b200/libhg_clk.so hydrograd.jl_b200/libhydrograd_b200.so
-timeout 400 python scripts/phase_clocks.py 16 256 > gpurun_out/exp_clocks.log 2>&1
-tail -3 gpurun_out/exp_clocks.log | cut -c1-300
+bash scripts/gpu_suite.sh
+HG_DEBUG_TIMING=1 timeout 300 python scripts/tune_r2.py 16 256,0,0 > gpurun_out/exp_create.log 2>&1
+grep "hg\]" gpurun_out/exp_create.log | head -12; tail -1 gpurun_out/exp_create.log | cut -c1-400
+timeout 120 ./hydrograd.jl_b200/bulk_issue_micro > gpurun_out/bulk_issue.txt 2>&1; tail -3 gpurun_out/bulk_issue.txt
