@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <utility>
+#include <thread>
 #include <vector>
 #include <memory>
 #include <mutex>
@@ -219,12 +220,35 @@ void hg_destroy(hg_ctx* ctx) {
 
 static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f) {
   hg::StageTimer whole_timer("hg_create (all of the above)");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+  // Driver initialisation (~0.6 s in a cold process) and the device's primary context are brought up on a helper thread
+  // while this one validates and preprocesses the mesh; the guard joins it on every way out.  Descriptor errors are
+  // therefore reported before a missing device is.
+  struct Warm {
+    int ndev = 0;
+    cudaError_t status = cudaSuccess;
+    std::thread th;
+    explicit Warm(int dev) {
+      th = std::thread([this, dev] {
+        status = cudaGetDeviceCount(&ndev);
+        if (status == cudaSuccess && dev >= 0 && dev < ndev && cudaSetDevice(dev) == cudaSuccess) cudaFree(nullptr);
+      });
+    }
+    void join() { if (th.joinable()) th.join(); }
+    ~Warm() { join(); }
+  } warm(ctx->opt.device);
+
+  std::vector<int32_t> cf_ptr, cf_nb, cf_face;
+  std::vector<double> cf_nx, cf_ny, cf_len;
+  TRY(hg::build_host(ctx, m, b, f, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face));
+  {
+    hg::StageTimer cuda_timer("cuda init (what the mesh checks did not hide)");
+    warm.join();
+  }
+  if (warm.status != cudaSuccess || warm.ndev == 0) {
     ctx->err = "no CUDA device available (this library has no CPU fallback)";
     return HG_ERR_CUDA;
   }
-  if (ctx->opt.device < 0 || ctx->opt.device >= ndev) { ctx->err = "bad device ordinal"; return HG_ERR_ARG; }
+  if (ctx->opt.device < 0 || ctx->opt.device >= warm.ndev) { ctx->err = "bad device ordinal"; return HG_ERR_ARG; }
   CK(ctx, cudaSetDevice(ctx->opt.device));
   cudaDeviceProp prop;
   CK(ctx, cudaGetDeviceProperties(&prop, ctx->opt.device));
@@ -232,17 +256,11 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     ctx->err = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this build is sm_100a only";
     return HG_ERR_CUDA;
   }
-  {
-    hg::StageTimer cuda_timer("cuda context + stream");
-    CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    ctx->own_stream = ctx->stream;
-    CK(ctx, cudaEventCreate(&ctx->ev0));
-    CK(ctx, cudaEventCreate(&ctx->ev1));
-  }
+  CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = ctx->stream;
+  CK(ctx, cudaEventCreate(&ctx->ev0));
+  CK(ctx, cudaEventCreate(&ctx->ev1));
 
-  std::vector<int32_t> cf_ptr, cf_nb, cf_face;
-  std::vector<double> cf_nx, cf_ny, cf_len;
-  TRY(hg::build_host(ctx, m, b, f, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face));
   const int64_t N = ctx->N, B = ctx->B;
   hg_ctx* x = ext(ctx);
   Frozen& fr = x->fr;
