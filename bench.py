@@ -267,6 +267,10 @@ def main():
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
 
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; hg_create's mesh preprocessing is OpenMP (setup, not in
+    # any timed region): give each rank its share of the host cores before the library's OpenMP runtime reads the variable
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
     import torch
     import _pkg
     hg = _pkg.load()
