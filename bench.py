@@ -440,6 +440,8 @@ def main():
     ms_per_step = ms_rhs_step + ms_vjp_step
     value = N_total / (ms_per_step * 1e-3)
 
+    uncoupled = None
+
     abytes = algorithmic_bytes(N, F, st["sum_cell_faces"])
     vbytes = abytes + 32 * N          # RHS inputs re-read + lambda (24 B) + Qbar (24 B) + nbar (8 B) - dQ (24 B)
 
@@ -558,6 +560,21 @@ def main():
             del sl, ctx
             side = side_configs(hg, S, local, peak)
         else:
+            # what the halo exchange costs ON THESE BOARDS: the same launches with the library's transport disconnected (no
+            # push, no waiting; the halo faces read stale values -- a timing probe, not a result).  Boards differ by a few per
+            # cent and a multi-GPU step is the max over ranks, so this ratio -- not the comparison with a single-GPU run on
+            # another board -- isolates the cost of the exchange.
+            if sl.transport == "ipc":
+                barrier()
+                ctx.comm_disconnect()
+                timed(ctx.rhs_resident, W); timed(ctx.vjp_resident, W)
+                barrier()
+                u_r = timed(ctx.rhs_resident, args.steps)
+                barrier()
+                u_v = timed(ctx.vjp_resident, args.steps)
+                u_ms = (allmax(u_r) + allmax(u_v)) / args.steps
+                uncoupled = {"ms_per_step": u_ms, "same_board_efficiency": u_ms / ms_per_step,
+                             "note": "identical work without the halo push / wait on the same GPUs (stale halos: timing probe only)"}
             sl.close()
             del sl, ctx
             s2 = Slab(max(8, ni // world))
@@ -595,6 +612,8 @@ def main():
         line.update(side)
         if strong is not None:
             line["strong"] = strong
+        if uncoupled is not None:
+            line["uncoupled"] = uncoupled
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if dist is not None:
