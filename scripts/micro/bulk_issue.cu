@@ -1,5 +1,6 @@
 // Microbenchmark: what does a thread pay to issue N cp.async.bulk copies of 2 KB, and when does the data land?
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/bulk_issue scripts/micro/bulk_issue.cu && gpurun_out/bulk_issue
+// build here (no GPU needed), run on the box:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o hydrograd.jl_b200/bulk_issue_micro scripts/micro/bulk_issue.cu
+// (the executable travels with the snapshot; it is git-ignored)
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
