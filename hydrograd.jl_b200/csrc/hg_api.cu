@@ -264,7 +264,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
   const int64_t N = ctx->N, B = ctx->B;
   hg_ctx* x = ext(ctx);
   Frozen& fr = x->fr;
-  hg::StageTimer* frozen_timer = new hg::StageTimer("frozen field copies");
+  auto frozen_timer = std::make_unique<hg::StageTimer>("frozen field copies");
 #pragma omp parallel sections   // ~0.8 GB of host copies on a 16M-cell mesh: one thread per field
   {
 #pragma omp section
@@ -289,7 +289,7 @@ static int create_impl(hg_ctx* ctx, const hg_mesh_desc* m, const hg_bc_desc* b, 
     }
     if (bad_id) { ctx->err = "matID_cells out of range"; return HG_ERR_ARG; }
   }
-  delete frozen_timer;
+  frozen_timer.reset();
   const hg::BcHost& h = ctx->bch;
   const size_t npar = (size_t)std::max<int64_t>(std::max<int64_t>(N, ctx->n_mat), std::max<int64_t>(ctx->n_inletq, 1));
   std::vector<double> hstill, area;   // host copies only where a table is uploaded in reference order
