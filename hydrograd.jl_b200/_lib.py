@@ -133,6 +133,7 @@ SYMBOLS = {
     "hg_time_rhs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "hg_time_vjp": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_float)]),
     "hg_kernel_launches": (C.c_int64, [_vp]),
+    "hg_state_generation": (C.c_int64, [_vp]),
     "hg_mesh_stats": (C.c_int, [_vp, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p]),
     "hg_plan_stats": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(BcDesc), C.POINTER(FieldsDesc), C.POINTER(Options),
                                 c_i64p, c_i64p]),

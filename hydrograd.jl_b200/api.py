@@ -149,7 +149,11 @@ class Context:
         return out
 
     def rhs_vjp(self, Q, lam, params=None, active=None, t=0.0, want_ncell_bar=False):
-        Q, lam = _f64(Q), _f64(lam)
+        """hg_rhs_vjp.  Q = None: at the resident state (the one the last rhs / set_state call uploaded; see
+        state_generation) -- only the cotangent crosses PCIe."""
+        Q, lam = (_f64(Q) if Q is not None else None), _f64(lam)
+        if lam.size != 3 * self.N or (Q is not None and Q.size != 3 * self.N):
+            raise HydrogradError(1, f"Q / lambda must have length {3 * self.N}")
         p, n, a = self._params(params, active)
         Qbar = np.empty(3 * self.N)
         pbar = np.zeros(max(n, 1))
@@ -205,7 +209,12 @@ class Context:
     def rhs_vjp_into(self, Q, lam, Qbar_out, params=None, active=None, pbar_out=None):
         """hg_rhs_vjp into caller-owned (e.g. pinned) buffers; pbar_out [n_params] when a parameter is active."""
         p, n, a = self._params(params, active)
-        self._ck(self.lib.hg_rhs_vjp(self._h, _p(_f64(Q)), _p(p), n, a, 0.0, _p(_f64(lam)), _p(Qbar_out), _p(pbar_out) if n else None, None))
+        Q = _f64(Q) if Q is not None else None      # None: the resident state (hg_rhs_vjp with Q = NULL)
+        self._ck(self.lib.hg_rhs_vjp(self._h, _p(Q), _p(p), n, a, 0.0, _p(_f64(lam)), _p(Qbar_out), _p(pbar_out) if n else None, None))
+
+    def state_generation(self):
+        """Changes whenever the resident state changes (hg_state_generation)."""
+        return int(self.lib.hg_state_generation(self._h))
 
     def get_vjp_into(self, Qbar_out):
         self._ck(self.lib.hg_get_vjp(self._h, _p(Qbar_out), None, None))
@@ -526,6 +535,21 @@ def swe_2d_rhs(dQdt, Q, params_vector, t, p_extra: SWE2D_Extra_Parameters):
         p_extra.ctx.rhs(Q, params_vector, p_extra.active_param_name, t, out=dQdt)
         return dQdt
     return p_extra.ctx.rhs(Q, params_vector, p_extra.active_param_name, t)
+
+
+def swe_2d_rhs_pullback(Q, params_vector, t, p_extra: SWE2D_Extra_Parameters):
+    """`y, back = Zygote.pullback(Q -> swe_2d_rhs(Q, p, t, extra), Q)` (debug_AD.jl:60,75; what ZygoteVJP / the shim's
+    `rrule` do per adjoint stage): returns (dQdt, back) with back(lam) -> (Qbar, pbar).  The primal's state stays on the
+    device, so the pullback uploads only the cotangent as long as nothing has moved the state in between."""
+    ctx = p_extra.ctx
+    dQdt = ctx.rhs(Q, params_vector, p_extra.active_param_name, t)
+    gen = ctx.state_generation()
+
+    def back(lam):
+        same = ctx.state_generation() == gen
+        return ctx.rhs_vjp(None if same else Q, lam, params_vector, p_extra.active_param_name, t)
+
+    return dQdt, back
 
 
 def custom_ODE_solve(ode_f, Q0, params_vector, swe2d_extra_params: SWE2D_Extra_Parameters):

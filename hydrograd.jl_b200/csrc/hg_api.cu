@@ -200,6 +200,7 @@ const char* hg_last_error(const hg_ctx* ctx) {
 }
 int64_t hg_n_cells(const hg_ctx* ctx) { return ctx ? ctx->N : 0; }
 int64_t hg_kernel_launches(const hg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t hg_state_generation(const hg_ctx* ctx) { return ctx ? (int64_t)ctx->state_gen : -1; }
 
 void hg_destroy(hg_ctx* ctx) {
   if (!ctx) return;
@@ -506,6 +507,7 @@ int hg_set_state(hg_ctx* ctx, const double* Q) {
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->state_set = true;
+  ctx->state_gen++;
   ctx->ab3_step = 1;   // a new state voids the multistep history of hg_step_ab3
   return HG_OK;
 }
@@ -602,6 +604,8 @@ static int rhs_pipelined(hg_ctx* ctx, const double* Q, double* dQdt) {
   CK(ctx, cudaStreamSynchronize(ctx->s_out));
   CK(ctx, cudaStreamSynchronize(sc));
   ctx->state_set = true;
+  ctx->state_gen++;
+  ctx->ab3_step = 1;
   return check_err_flag(ctx);
 }
 
@@ -641,14 +645,14 @@ static int vjp_pipelined(hg_ctx* ctx, const double* Q, const double* lambda, dou
   CK(ctx, cudaStreamSynchronize(sc));
   for (int c = 0; c < K; ++c) {
     const int64_t r0 = c * csz, r1 = std::min<int64_t>(N, r0 + csz);
-    CK(ctx, copy3_rows(d.stage.p, Q, N, r0, r1, cudaMemcpyHostToDevice, ctx->s_in));
+    if (Q) CK(ctx, copy3_rows(d.stage.p, Q, N, r0, r1, cudaMemcpyHostToDevice, ctx->s_in));   // NULL: the resident state
     CK(ctx, copy3_rows(d.stage_lam.p, lambda, N, r0, r1, cudaMemcpyHostToDevice, ctx->s_in));
     CK(ctx, cudaEventRecord(ctx->ev_in[c], ctx->s_in));
   }
   for (int s = 0; s < K; ++s) {
     const int64_t r0 = s * csz, r1 = std::min<int64_t>(N, r0 + csz);
     CK(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[s], 0));
-    TRY(hg::fused_permute_range(ctx, true, d.stage.p, d.Q.p, r0, r1));
+    if (Q) TRY(hg::fused_permute_range(ctx, true, d.stage.p, d.Q.p, r0, r1));
     TRY(hg::fused_permute_range(ctx, true, d.stage_lam.p, d.lam.p, r0, r1));
     const bool band = s == K - 1 && hg_comm_ready(ctx);
     if (band) { TRY(hg::comm_push(ctx, d.Q.p, d.lam.p)); ctx->comm->pushed = false; }
@@ -665,7 +669,7 @@ static int vjp_pipelined(hg_ctx* ctx, const double* Q, const double* lambda, dou
     }
   }
   CK(ctx, cudaStreamSynchronize(ctx->s_out));
-  ctx->state_set = true;
+  if (Q) { ctx->state_set = true; ctx->state_gen++; ctx->ab3_step = 1; }
   ctx->lam_set = true;
   return HG_OK;
 }
@@ -673,8 +677,11 @@ static int vjp_pipelined(hg_ctx* ctx, const double* Q, const double* lambda, dou
 int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, int32_t active, double t, const double* lambda,
                double* Qbar, double* pbar, double* ncell_bar) {
   (void)t;
-  if (!ctx || !Q || !lambda || !Qbar) return HG_ERR_ARG;
+  if (!ctx || !lambda || !Qbar) return HG_ERR_ARG;
   if (ctx->opt.path == 1) { ctx->err = "hg_rhs_vjp needs the fused path (strict = 0)"; return HG_ERR_ARG; }
+  // Q = NULL: the pullback of a forward call whose state is still on the device (Zygote's pullback closes over the primal
+  // of its forward pass; hg_state_generation tells the caller whether anything has moved the state since)
+  if (!Q && !ctx->state_set) { ctx->err = "hg_rhs_vjp: Q is NULL and no state is resident (call hg_rhs or hg_set_state first)"; return HG_ERR_STATE; }
   TRY(no_closure(ctx, "hg_rhs_vjp"));
   CK(ctx, cudaSetDevice(ctx->opt.device));
   TRY(bind_params(ctx, params, np, active));
@@ -683,7 +690,7 @@ int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   if (ctx->fh.n_chunks > 1 && (ctx->n_halo == 0 || hg_comm_ready(ctx)) && ctx->active != HG_PARAM_UDE) {
     TRY(vjp_pipelined(ctx, Q, lambda, Qbar));
   } else {
-    TRY(hg_set_state(ctx, Q));
+    if (Q) TRY(hg_set_state(ctx, Q));
     TRY(set_lambda(ctx, lambda));
     TRY(hg::fused_vjp(ctx, hg::fused_cfg_id(ctx), d.Q.p, d.lam.p, d.Qbar.p));
     TRY(download3(ctx, d.Qbar.p, Qbar));
@@ -748,6 +755,7 @@ int hg_rhs_jvp(hg_ctx* ctx, const double* Q, const double* params, int64_t np, i
   CK(ctx, cudaMemcpyAsync(p.Q.p, Q, n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaMemcpyAsync(p.V.p, v, n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
   ctx->state_set = true;
+  ctx->state_gen++;
   TRY(hg::plain_jvp(ctx, p.Q.p, p.V.p, d_pdot, dQdt ? p.dQ.p : nullptr, p.dQd.p));
   if (dQdt) CK(ctx, cudaMemcpyAsync(dQdt, p.dQ.p, n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaMemcpyAsync(dQdt_dot, p.dQd.p, n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -779,6 +787,7 @@ int hg_rhs_jvp_multi(hg_ctx* ctx, const double* Q, const double* params, int64_t
   CK(ctx, cudaMemcpyAsync(p.Q.p, Q, n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaMemcpyAsync(dV.p, V, (size_t)K * n3 * 8, cudaMemcpyHostToDevice, ctx->stream));
   ctx->state_set = true;
+  ctx->state_gen++;
   // all K directions in one pair of launches
   TRY(hg::plain_jvp_batch(ctx, p.Q.p, dV.p, (int64_t)n3, with_p ? dP.p : nullptr, npar, dQdt ? p.dQ.p : nullptr, dJ.p, K));
   if (dQdt) CK(ctx, cudaMemcpyAsync(dQdt, p.dQ.p, n3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -865,6 +874,7 @@ int hg_solve_tsit5_sens(hg_ctx* ctx, const double* Q0, const double* params, int
     CK(ctx, cudaMemcpyAsync(ctx->fd.stage.p, Q0, (size_t)n3h * 8, cudaMemcpyHostToDevice, ctx->stream));
     TRY(hg::fused_permute(ctx, true, ctx->fd.stage.p, U.p));
     ctx->state_set = false;     // the resident state buffer is not what this solve integrates
+    ctx->state_gen++;
   } else {
     CK(ctx, cudaMemcpyAsync(U.p, Q0, (size_t)n3h * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
@@ -1140,6 +1150,7 @@ int hg_step_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
   if (ctx->opt.path == 1) { ctx->err = "hg_step_euler needs the fused path (path=0)"; return HG_ERR_ARG; }
   TRY(need_exchange_guard(ctx, "hg_step_euler", nsteps > 1));
   ctx->ab3_step = 1;   // another stepper moves the state: hg_step_ab3 starts again
+  ctx->state_gen++;
   hg::FusedDev& d = ctx->fd;
   for (int64_t s = 0; s < nsteps; ++s) {
     TRY(hg::fused_rhs(ctx, d.Q.p, d.Q2.p, true, dt));
@@ -1154,6 +1165,7 @@ int hg_step_rk4(hg_ctx* ctx, double dt, int64_t nsteps) {
   if (ctx->opt.path == 1) { ctx->err = "hg_step_rk4 needs the fused path (path=0)"; return HG_ERR_ARG; }
   TRY(need_exchange_guard(ctx, "hg_step_rk4", true));
   ctx->ab3_step = 1;   // another stepper moves the state: hg_step_ab3 starts again
+  ctx->state_gen++;
   CK(ctx, cudaSetDevice(ctx->opt.device));
   hg::FusedDev& d = ctx->fd;
   const size_t n = 3 * (size_t)ctx->fh.Ns;
@@ -1184,6 +1196,7 @@ int hg_step_ode_euler(hg_ctx* ctx, double dt, int64_t nsteps) {
   if (ctx->opt.path == 1) { ctx->err = "hg_step_ode_euler needs the fused path (path=0)"; return HG_ERR_ARG; }
   TRY(need_exchange_guard(ctx, "hg_step_ode_euler", nsteps > 1));
   ctx->ab3_step = 1;   // another stepper moves the state: hg_step_ab3 starts again
+  ctx->state_gen++;
   CK(ctx, cudaSetDevice(ctx->opt.device));
   hg::FusedDev& d = ctx->fd;
   for (int64_t s = 0; s < nsteps; ++s) {
@@ -1209,6 +1222,7 @@ int hg_step_ab3(hg_ctx* ctx, double dt, int64_t nsteps, int32_t restart) {
     if (d.ts_k[m].n != n3) { TRY(al(ctx, d.ts_k[m], n3)); restart = 1; }
   if (d.rk_tmp.n != n3) TRY(al(ctx, d.rk_tmp, n3));
   if (restart) ctx->ab3_step = 1;
+  ctx->state_gen++;
   for (int64_t s = 0; s < nsteps; ++s) {
     double* k1 = d.ts_k[0].p;
     TRY(hg::fused_rhs(ctx, d.Q.p, k1, false, 0.0));
@@ -1286,6 +1300,7 @@ int solve_tsit5(hg_ctx* ctx, double t0, double t1, double dt, int32_t adaptive, 
   if (!ctx || !(t1 > t0) || !(dt > 0.0) || n_save < 0 || (n_save > 0 && (!t_save || !Q_save))) return HG_ERR_ARG;
   if (adaptive && (!(abstol > 0.0) || !(reltol > 0.0))) { ctx->err = "hg_solve_tsit5: tolerances must be positive"; return HG_ERR_ARG; }
   if (!ctx->state_set) { ctx->err = "hg_solve_tsit5: no resident state"; return HG_ERR_STATE; }
+  ctx->state_gen++;
   if (ctx->opt.path == 1) { ctx->err = "hg_solve_tsit5 needs the fused path (path=0)"; return HG_ERR_ARG; }
   // multi-rank contexts: the stages exchange their halos through the library transport; the adaptive controller needs the
   // error norm of the WHOLE mesh, i.e. a sum over ranks -- done on the host by the caller's all-reduce (hg_comm_set_allreduce)

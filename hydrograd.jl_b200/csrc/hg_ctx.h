@@ -255,6 +255,7 @@ struct hg_ctx {
   std::string err;
   int64_t launches = 0;
   bool state_set = false;
+  uint64_t state_gen = 0;      // bumped whenever the resident state changes (hg_state_generation): lets a pullback reuse the state of its forward call
   int32_t active = HG_PARAM_NONE;
   int64_t n_params = 0;
   hg::BcHost bch;

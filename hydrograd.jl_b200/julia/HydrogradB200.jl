@@ -324,24 +324,33 @@ function swe_2d_rhs(dQdt::AbstractVector{D}, Q::AbstractVector, p::AbstractVecto
 end
 
 "Vector-Jacobian product (Qbar, pbar) = (dRHS/dQ)' * lambda, (dRHS/dp)' * lambda -- what Zygote.pullback returns (debug_AD.jl:60,75)."
-function swe_2d_rhs_vjp(Q::Vector{Float64}, params_vector::Vector{Float64}, t::Float64, lambda::Vector{Float64}, ctx::Context)
+function swe_2d_rhs_vjp(Q::Vector{Float64}, params_vector::Vector{Float64}, t::Float64, lambda::Vector{Float64}, ctx::Context;
+                        state_resident::Bool=false)
     Qbar = similar(Q); pbar = zeros(max(length(params_vector), 1))
     np = ctx.active == 0 ? 0 : length(params_vector)
     GC.@preserve Q params_vector lambda Qbar pbar begin
+        # state_resident: Q is what the last forward call uploaded and nothing has moved it since -- pass NULL, only lambda is copied
+        Qptr = state_resident ? Ptr{Float64}(C_NULL) : pointer(Q)
         rc = ccall((:hg_rhs_vjp, LIB), Cint,
                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                   ctx.handle, Q, params_vector, np, ctx.active, t, lambda, Qbar, pbar, C_NULL)
+                   ctx.handle, Qptr, params_vector, np, ctx.active, t, lambda, Qbar, pbar, C_NULL)
         _check(rc, ctx.handle)
     end
     return Qbar, pbar[1:length(params_vector)]
 end
 
+"Changes whenever the state resident on the device changes (uploads, steppers, solves)."
+state_generation(ctx::Context) = ccall((:hg_state_generation, LIB), Int64, (Ptr{Cvoid},), ctx.handle)
+
 function ChainRulesCore.rrule(::typeof(swe_2d_rhs), Q::AbstractVector, p::AbstractVector, t::Real, ctx::Context)
     Qv, pv = _plain(Q), _plain(p)
     y = swe_2d_rhs(Qv, pv, Float64(t), ctx)
+    gen = state_generation(ctx)                            # the primal's state stays on the device ...
     project_Q, project_p = ProjectTo(Q), ProjectTo(p)      # e.g. back onto the ComponentVector of the network parameters
     function pullback(ybar)
-        Qbar, pbar = swe_2d_rhs_vjp(Qv, pv, Float64(t), collect(Float64, unthunk(ybar)), ctx)
+        # ... so a pullback called before anything else touches the context (ZygoteVJP calls it at once) ships only the cotangent
+        Qbar, pbar = swe_2d_rhs_vjp(Qv, pv, Float64(t), collect(Float64, unthunk(ybar)), ctx;
+                                    state_resident = state_generation(ctx) == gen)
         return NoTangent(), project_Q(Qbar), (ctx.active == 0 ? ZeroTangent() : project_p(pbar)), NoTangent(), NoTangent()
     end
     return y, pullback

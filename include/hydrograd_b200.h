@@ -226,7 +226,12 @@ HG_API int hg_rhs(hg_ctx* ctx, const double* Q, const double* params, int64_t n_
 /* Vector-Jacobian product of the same call: Qbar = (d rhs/dQ)^T lambda  [3N],
  * pbar = (d rhs/dparams)^T lambda  [n_params] (NULL allowed when active_param = NONE),
  * ncell_bar (optional, may be NULL) = d(lambda . rhs)/d ManningN_cells  [N]  (UDE hook).
- * Replaces Zygote.pullback on swe_2d_rhs (debug_AD.jl:60,75; swe_2D_inversion.jl:339).           */
+ * Replaces Zygote.pullback on swe_2d_rhs (debug_AD.jl:60,75; swe_2D_inversion.jl:339).
+ * Q = NULL: differentiate at the state that is resident on the device -- the one the last hg_rhs / hg_set_state call put
+ * there.  That is the shape of a Zygote pullback: `y, back = Zygote.pullback(swe_2d_rhs, Q, p)` evaluates the primal
+ * once (hg_rhs uploads Q) and `back(lambda)` needs only the cotangent, so the pullback ships 24 instead of 48 bytes per
+ * cell over PCIe.  hg_state_generation guards the reuse: read it after the forward call, pass Q = NULL only while it is
+ * unchanged (HG_ERR_STATE when nothing is resident).                                               */
 HG_API int hg_rhs_vjp(hg_ctx* ctx, const double* Q, const double* params, int64_t n_params,
                int32_t active_param, double t, const double* lambda, double* Qbar, double* pbar,
                double* ncell_bar);
@@ -490,6 +495,10 @@ HG_API int hg_time_rhs(hg_ctx* ctx, int32_t n_launches, int32_t fused_euler, dou
 HG_API int hg_time_vjp(hg_ctx* ctx, int32_t n_launches, float* ms_total);
 HG_API int hg_time_jvp(hg_ctx* ctx, int32_t n_directions, int32_t n_launches, float* ms_total);   /* fused forward-mode kernel */
 HG_API int64_t hg_kernel_launches(const hg_ctx* ctx);            /* kernels launched so far             */
+/* A counter that changes whenever the resident state changes (uploads by hg_rhs / hg_rhs_vjp / hg_set_state / the forward-
+ * mode calls, every stepper, solve and time adjoint).  Equal values before and after = the state of the earlier call is
+ * still on the device, so hg_rhs_vjp may be called with Q = NULL.  -1 for a NULL context.                             */
+HG_API int64_t hg_state_generation(const hg_ctx* ctx);
 HG_API int hg_mesh_stats(const hg_ctx* ctx, int64_t* n_cells, int64_t* n_faces, int64_t* sum_cell_faces,
                   int64_t* n_tiles, int64_t* device_bytes);
 /* Host-only: run the hg_create preprocessing (validation, renumbering, tiling) WITHOUT touching a GPU

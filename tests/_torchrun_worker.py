@@ -103,6 +103,10 @@ def main():
         out["pipe_rhs_bitwise"] = bool(np.array_equal(bctx.rhs(binfo["Q"]), bpick(bref)))
         got_bar, _ = bctx.rhs_vjp(binfo["Q"], bpick(blam))
         out["pipe_vjp_err"] = float(np.abs(got_bar - bpick(bbar)).max() / np.abs(bbar).max())
+        # the pullback of a forward call: Q = None reuses the state hg_rhs uploaded (only lambda crosses PCIe) -- same bits
+        bctx.rhs(binfo["Q"])
+        got_bar2, _ = bctx.rhs_vjp(None, bpick(blam))
+        out["pipe_vjp_resident_state_bitwise"] = bool(np.array_equal(got_bar2, got_bar))
         dist.barrier()
         bctx.comm_disconnect()
         del bctx

@@ -31,5 +31,6 @@ def test_two_ranks_match_single_context(tmp_path):
         for name in ("euler", "rk4", "tsit5"):
             assert o[f"adj_{name}_state_bitwise"] and o[f"adj_{name}_q0bar_err"] <= 1e-12 and o[f"adj_{name}_pbar_err"] <= 1e-12, o
         assert o["pipe_rhs_bitwise"] and o["pipe_vjp_err"] <= 1e-13, o
+        assert o["pipe_vjp_resident_state_bitwise"], o
         if o["one_gpu_each"]:
             assert o["nccl_rhs_bitwise"] and o["nccl_vjp_err"] <= 1e-13, o
