@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+#include <cstdio>
 #include <utility>
 #include <thread>
 #include <vector>
@@ -555,17 +557,35 @@ int hg_get_rhs(hg_ctx* ctx, double* dQ) {
   return check_err_flag(ctx);
 }
 
-// rows [r0, r1) of the three components of a [3][N] vector in ONE strided copy (beyond the 2 GiB pitch limit of
-// cudaMemcpy2D -- more than 268M cells -- component by component)
-static cudaError_t copy3_rows(double* dst, const double* src, int64_t N, int64_t r0, int64_t r1, cudaMemcpyKind kind, cudaStream_t s) {
-  if ((size_t)N * 8 < ((size_t)1 << 31))
-    return cudaMemcpy2DAsync(dst + r0, (size_t)N * 8, src + r0, (size_t)N * 8, (size_t)(r1 - r0) * 8, 3, kind, s);
+// ---- chunk geometry of the host-buffer pipeline (tables: build_tiles in hg_host.cpp, fh.chunk_cells = nominal rows per chunk)
+// Rows [r0, r1) of chunk c for the component whose HOST address is hrow: the boundaries are shifted per component so that every
+// host address a copy starts at is a multiple of 256 bytes (the caller's [3N] layout gives the components arbitrary offsets).
+static inline void chunk_rows(const double* hrow, int c, int K, int64_t csz, int64_t N, int64_t& r0, int64_t& r1) {
+  const int64_t sh = (int64_t)((reinterpret_cast<uintptr_t>(hrow) >> 3) & (uintptr_t)(hg::kPipeAlign - 1));
+  r0 = c == 0 ? 0 : std::min<int64_t>(N, std::max<int64_t>(0, (int64_t)c * csz - sh));
+  r1 = c == K - 1 ? N : std::min<int64_t>(N, std::max<int64_t>(0, (int64_t)(c + 1) * csz - sh));
+  if (r0 > r1) r0 = r1;
+}
+// chunk c of a [3][N] vector between `host` and the device staging buffer (same row offsets on both sides)
+static cudaError_t copy3_chunk(double* dst, const double* src, const double* host, int64_t N, int c, int K, int64_t csz,
+                               cudaMemcpyKind kind, cudaStream_t s) {
   for (int q = 0; q < 3; ++q) {
+    int64_t r0, r1;
+    chunk_rows(host + q * N, c, K, csz, N, r0, r1);
+    if (r1 <= r0) continue;
     const cudaError_t e = cudaMemcpyAsync(dst + q * N + r0, src + q * N + r0, (size_t)(r1 - r0) * 8, kind, s);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
+// rows every component has landed once chunk c has arrived, whatever the shifts: [0, landed_rows(c))
+static inline int64_t landed_rows(int c, int K, int64_t csz, int64_t N) {
+  return c < 0 ? 0 : c >= K - 1 ? N : std::max<int64_t>(0, std::min<int64_t>(N, (int64_t)(c + 1) * csz - hg::kPipeAlign));
+}
+// rows result chunk c may take, whatever the shifts: [result_lo(c), result_hi(c)) (neighbouring chunks overlap by kPipeAlign rows;
+// those are gathered twice, with the same finished values)
+static inline int64_t result_lo(int c, int64_t csz, int64_t N) { return std::min<int64_t>(N, std::max<int64_t>(0, (int64_t)c * csz - hg::kPipeAlign)); }
+static inline int64_t result_hi(int c, int K, int64_t csz, int64_t N) { return c == K - 1 ? N : std::min<int64_t>(N, (int64_t)(c + 1) * csz); }
 
 // Host-buffer RHS as a three-stream pipeline: the state arrives over PCIe in reference-order chunks (s_in); after each
 // chunk the compute stream scatters it into the internal order and runs every tile whose cells and halo have landed;
@@ -576,33 +596,55 @@ static int rhs_pipelined(hg_ctx* ctx, const double* Q, double* dQdt) {
   hg::FusedDev& d = ctx->fd;
   const hg::FusedHost& fh = ctx->fh;
   const int K = fh.n_chunks;
-  const int64_t N = ctx->N, csz = (N + K - 1) / K;
+  const int64_t N = ctx->N, csz = fh.chunk_cells;
   cudaStream_t sc = ctx->stream;
   CK(ctx, cudaStreamSynchronize(sc));
+  // HG_DEBUG_PIPE=1: when did every chunk land, every stage finish, every result chunk leave (ms after the first copy started)
+  static const bool trace = std::getenv("HG_DEBUG_PIPE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  if (trace) {
+    tev.resize(3 * (size_t)K + 1);
+    for (auto& e : tev) CK(ctx, cudaEventCreate(&e));
+    CK(ctx, cudaEventRecord(tev[3 * (size_t)K], ctx->s_in));
+  }
   for (int c = 0; c < K; ++c) {
-    const int64_t r0 = c * csz, r1 = std::min<int64_t>(N, r0 + csz);
-    CK(ctx, copy3_rows(d.stage.p, Q, N, r0, r1, cudaMemcpyHostToDevice, ctx->s_in));
+    CK(ctx, copy3_chunk(d.stage.p, Q, Q, N, c, K, csz, cudaMemcpyHostToDevice, ctx->s_in));
     CK(ctx, cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+    if (trace) CK(ctx, cudaEventRecord(tev[c], ctx->s_in));
   }
   for (int s = 0; s < K; ++s) {
-    const int64_t r0 = s * csz, r1 = std::min<int64_t>(N, r0 + csz);
+    const int64_t r0 = landed_rows(s - 1, K, csz, N), r1 = landed_rows(s, K, csz, N);
     CK(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[s], 0));
     TRY(hg::fused_permute_range(ctx, true, d.stage.p, d.Q.p, r0, r1));
     const bool band = s == K - 1 && hg_comm_ready(ctx);   // multi-rank: the whole state has landed -- push the cut cells, the last stage holds the band
     if (band) { TRY(hg::comm_push(ctx, d.Q.p, nullptr)); ctx->comm->pushed = false; }
     if (s == K - 1 && ctx->n_inletq > 0) hg::fused_inlet_coef(ctx, d.Q.p);
     TRY(hg::fused_rhs_tiles(ctx, d.Q.p, d.dQ.p, fh.stage_ptr[s], fh.stage_ptr[s + 1] - fh.stage_ptr[s], band));
+    if (trace) CK(ctx, cudaEventRecord(tev[K + s], sc));
     for (int c = 0; c < K; ++c) {
       if (fh.chunk_done[c] != s) continue;
-      const int64_t q0 = c * csz, q1 = std::min<int64_t>(N, q0 + csz);
+      const int64_t q0 = result_lo(c, csz, N), q1 = result_hi(c, K, csz, N);
+      if (q1 <= q0) continue;
       TRY(hg::fused_permute_range(ctx, false, d.dQ.p, d.stage_out.p, q0, q1));
       CK(ctx, cudaEventRecord(ctx->ev_cmp[c], sc));
       CK(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[c], 0));
-      CK(ctx, copy3_rows(dQdt, d.stage_out.p, N, q0, q1, cudaMemcpyDeviceToHost, ctx->s_out));
+      CK(ctx, copy3_chunk(dQdt, d.stage_out.p, dQdt, N, c, K, csz, cudaMemcpyDeviceToHost, ctx->s_out));
+      if (trace) CK(ctx, cudaEventRecord(tev[2 * (size_t)K + c], ctx->s_out));
     }
   }
   CK(ctx, cudaStreamSynchronize(ctx->s_out));
   CK(ctx, cudaStreamSynchronize(sc));
+  if (trace) {
+    fprintf(stderr, "[hg pipe] rhs, %d chunks: chunk / landed / stage done / result left (after stage) [ms]\n", K);
+    for (int c = 0; c < K; ++c) {
+      float a = 0, b = 0, o = 0;
+      cudaEventElapsedTime(&a, tev[3 * (size_t)K], tev[c]);
+      cudaEventElapsedTime(&b, tev[3 * (size_t)K], tev[K + c]);
+      if (result_hi(c, K, csz, N) > result_lo(c, csz, N)) cudaEventElapsedTime(&o, tev[3 * (size_t)K], tev[2 * (size_t)K + c]);
+      fprintf(stderr, "[hg pipe] %3d %8.3f %8.3f %8.3f (%d)\n", c, a, b, o, fh.chunk_done[c]);
+    }
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
   ctx->state_set = true;
   ctx->state_gen++;
   ctx->ab3_step = 1;
@@ -638,19 +680,18 @@ static int vjp_pipelined(hg_ctx* ctx, const double* Q, const double* lambda, dou
   hg::FusedDev& d = ctx->fd;
   const hg::FusedHost& fh = ctx->fh;
   const int K = fh.n_chunks;
-  const int64_t N = ctx->N, csz = (N + K - 1) / K;
+  const int64_t N = ctx->N, csz = fh.chunk_cells;
   cudaStream_t sc = ctx->stream;
   if (d.stage_lam.n < (size_t)(3 * N)) CK(ctx, d.stage_lam.alloc(3 * N));
   const int cfg = hg::fused_cfg_id(ctx);
   CK(ctx, cudaStreamSynchronize(sc));
   for (int c = 0; c < K; ++c) {
-    const int64_t r0 = c * csz, r1 = std::min<int64_t>(N, r0 + csz);
-    if (Q) CK(ctx, copy3_rows(d.stage.p, Q, N, r0, r1, cudaMemcpyHostToDevice, ctx->s_in));   // NULL: the resident state
-    CK(ctx, copy3_rows(d.stage_lam.p, lambda, N, r0, r1, cudaMemcpyHostToDevice, ctx->s_in));
+    if (Q) CK(ctx, copy3_chunk(d.stage.p, Q, Q, N, c, K, csz, cudaMemcpyHostToDevice, ctx->s_in));   // NULL: the resident state
+    CK(ctx, copy3_chunk(d.stage_lam.p, lambda, lambda, N, c, K, csz, cudaMemcpyHostToDevice, ctx->s_in));
     CK(ctx, cudaEventRecord(ctx->ev_in[c], ctx->s_in));
   }
   for (int s = 0; s < K; ++s) {
-    const int64_t r0 = s * csz, r1 = std::min<int64_t>(N, r0 + csz);
+    const int64_t r0 = landed_rows(s - 1, K, csz, N), r1 = landed_rows(s, K, csz, N);
     CK(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[s], 0));
     if (Q) TRY(hg::fused_permute_range(ctx, true, d.stage.p, d.Q.p, r0, r1));
     TRY(hg::fused_permute_range(ctx, true, d.stage_lam.p, d.lam.p, r0, r1));
@@ -661,11 +702,12 @@ static int vjp_pipelined(hg_ctx* ctx, const double* Q, const double* lambda, dou
     if (s == K - 1) TRY(hg::fused_vjp_finish(ctx, d.Q.p, d.Qbar.p));
     for (int c = 0; c < K; ++c) {
       if (fh.chunk_done[c] != s) continue;
-      const int64_t q0 = c * csz, q1 = std::min<int64_t>(N, q0 + csz);
+      const int64_t q0 = result_lo(c, csz, N), q1 = result_hi(c, K, csz, N);
+      if (q1 <= q0) continue;
       TRY(hg::fused_permute_range(ctx, false, d.Qbar.p, d.stage_out.p, q0, q1));
       CK(ctx, cudaEventRecord(ctx->ev_cmp[c], sc));
       CK(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[c], 0));
-      CK(ctx, copy3_rows(Qbar, d.stage_out.p, N, q0, q1, cudaMemcpyDeviceToHost, ctx->s_out));
+      CK(ctx, copy3_chunk(Qbar, d.stage_out.p, Qbar, N, c, K, csz, cudaMemcpyDeviceToHost, ctx->s_out));
     }
   }
   CK(ctx, cudaStreamSynchronize(ctx->s_out));

@@ -155,6 +155,12 @@ struct PlainDev {
 //                                       tile's zero-flux slot (index nfp)
 // Local cell index space of a tile: owned cells 0..nc-1, halo cells ncp.. (ncp = nc rounded up to 2).
 constexpr int kTileDesc = 12;  // ints per tile: c0 nc hp nh fp nf nfp (unused) (unused) nint bfp (pad)
+// Host-buffer pipeline: the rows of a chunk start at HOST addresses that are multiples of 256 bytes (32 doubles).  The caller's
+// [3N] vectors have an arbitrary N, so each component's chunk boundaries are shifted by up to kPipeAlign - 1 cells; the stage
+// tables are built with that margin and do not depend on the pointers.  Misaligned rows cost ~20 % of the duplex PCIe rate
+// (scripts/micro/pcie_pipeline.cu: 35.6 -> 44.2 GB/s per direction).
+constexpr int64_t kPipeAlign = 32;
+
 struct FusedHost {
   int32_t n_tiles = 0, T = 0, NF = 4, max_local = 0, max_faces = 0, max_halo = 0, max_cell_faces = 0;
   int64_t Ns = 0;                    // padded component stride of cell-indexed arrays
@@ -169,6 +175,7 @@ struct FusedHost {
   // host-buffer pipeline (hg_rhs): reference-order chunks arrive one by one over PCIe; a tile can run once the
   // chunks holding its cells and halo cells have landed; a chunk can leave once its tiles are done
   int32_t n_chunks = 1;
+  int64_t chunk_cells = 0;           // nominal rows per chunk, a multiple of kPipeAlign (see chunk_rows in hg_api.cu)
   std::vector<int32_t> tile_order;   // tiles sorted by the stage at which they become ready
   std::vector<int32_t> stage_ptr;    // [n_chunks+1] ranges of tile_order
   std::vector<int32_t> chunk_done;   // [n_chunks] stage after which every cell of the chunk has been computed

@@ -649,14 +649,19 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
     int32_t K = N >= (1 << 20) ? (int32_t)std::min<int64_t>(32, std::max<int64_t>(8, N >> 19)) : 1;   // ~0.5M cells (12 MB) per chunk
     if (ctx->opt.reserved[1] > 0) K = (int32_t)std::min<int64_t>(ctx->opt.reserved[1], std::max<int64_t>(1, N / 1024));   // tuning override
     fh.n_chunks = K;
-    const int64_t csz = (N + K - 1) / K;
+    // chunk c nominally holds the reference rows [c csz, (c+1) csz); a component whose host address needs a shift sh < kPipeAlign
+    // moves rows [c csz - sh, (c+1) csz - sh).  So after chunk c every component has landed rows < (c+1) csz - kPipeAlign (all of
+    // them after the last chunk), and result chunk c can take rows from c csz - kPipeAlign on.
+    const int64_t csz = K > 1 ? ((N + K - 1) / K + kPipeAlign - 1) / kPipeAlign * kPipeAlign : N;
+    fh.chunk_cells = csz;
+    auto stage_of_row = [&](int64_t r) { return (int32_t)std::min<int64_t>(K - 1, (r + kPipeAlign) / csz); };
     std::vector<int32_t> tstage(fh.n_tiles, 0);
 #pragma omp parallel for schedule(static)
     for (int32_t t = 0; t < fh.n_tiles; ++t) {
       const int32_t* d = &fh.tile_desc[(size_t)t * kTileDesc];
       int32_t st = 0;
-      for (int32_t c = d[0]; c < d[0] + d[1]; ++c) st = std::max(st, (int32_t)(fh.perm[c] / csz));
-      for (int32_t q = d[2]; q < d[2] + d[3]; ++q) st = std::max(st, (int32_t)(fh.perm[fh.halo[q]] / csz));
+      for (int32_t c = d[0]; c < d[0] + d[1]; ++c) st = std::max(st, stage_of_row(fh.perm[c]));
+      for (int32_t q = d[2]; q < d[2] + d[3]; ++q) st = std::max(st, stage_of_row(fh.perm[fh.halo[q]]));
       // tiles with inlet-q faces wait for the boundary-wide conveyance sum, i.e. for the last chunk; so do the tiles with halo
       // faces (multi-rank contexts: the neighbours push their cut cells once their own last chunk has landed)
       for (int32_t q = 0; q < d[5] - d[9]; ++q)
@@ -673,7 +678,8 @@ static int build_tiles_T(hg_ctx* ctx, const hg_mesh_desc* m, const std::vector<i
 #pragma omp parallel for schedule(static)
     for (int32_t c = 0; c < K; ++c) {
       int32_t done = 0;
-      for (int64_t r = c * csz; r < std::min<int64_t>(N, (c + 1) * csz); ++r) done = std::max(done, tstage[fh.iperm[r] / T]);
+      const int64_t hi = c == K - 1 ? N : std::min<int64_t>(N, (c + 1) * csz);
+      for (int64_t r = std::max<int64_t>(0, c * csz - kPipeAlign); r < hi; ++r) done = std::max(done, tstage[fh.iperm[r] / T]);
       fh.chunk_done[c] = done;
     }
   }
