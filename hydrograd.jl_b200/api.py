@@ -97,6 +97,25 @@ def plan_stats(flat: dict, tile_cells=256, reorder=True, want_perm=False):
     return (out, perm) if want_perm else out
 
 
+def plan_pipeline(flat: dict, tile_cells=256, reorder=True, pipeline_chunks=0):
+    """Host-only: stage tables of the host-buffer pipeline (hg_plan_pipeline): dict(n_chunks, chunk_cells, n_tiles, tile_cells,
+    margin, tile_stage [n_tiles], chunk_done [n_chunks])."""
+    lib = L.load()
+    mesh, bc, fields, keep = _descs(flat)
+    opt = _options(lib, 0, tile_cells, reorder, pipeline_chunks=pipeline_chunks)
+    hdr = np.zeros(5, dtype=np.int64)
+    i32p = C.POINTER(C.c_int32)
+    rc = lib.hg_plan_pipeline(C.byref(mesh), C.byref(bc), C.byref(fields), C.byref(opt), _p(hdr, L.c_i64p), None, None)
+    if rc:
+        raise HydrogradError(rc, (lib.hg_last_error(None) or b"").decode())
+    ts, cd = np.zeros(int(hdr[2]), dtype=np.int32), np.zeros(int(hdr[0]), dtype=np.int32)
+    rc = lib.hg_plan_pipeline(C.byref(mesh), C.byref(bc), C.byref(fields), C.byref(opt), _p(hdr, L.c_i64p), _p(ts, i32p), _p(cd, i32p))
+    if rc:
+        raise HydrogradError(rc, (lib.hg_last_error(None) or b"").decode())
+    return dict(n_chunks=int(hdr[0]), chunk_cells=int(hdr[1]), n_tiles=int(hdr[2]), tile_cells=int(hdr[3]), margin=int(hdr[4]),
+                tile_stage=ts, chunk_done=cd)
+
+
 class Context:
     """Owns one hg_ctx (one mesh on one GPU).  `flat` holds the flat tables of include/hydrograd_b200.h
     (see INTEGRATION.md for how the Julia structs map onto them)."""

@@ -1774,6 +1774,29 @@ int hg_plan_stats(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_de
   return HG_OK;
 }
 
+// Host-only: the stage tables of the host-buffer pipeline for this mesh (no GPU touched).  header = {n_chunks, rows per chunk,
+// n_tiles, tile_cells, alignment margin in rows}; tile_stage[n_tiles] (may be NULL) = the stage a tile runs in, i.e. the chunk
+// after which all its cells and halo cells have landed; chunk_done[n_chunks] (may be NULL) = the stage after which result
+// chunk c may leave.  The CPU tests check both against the mesh adjacency.
+int hg_plan_pipeline(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, const hg_options* opt, int64_t* header,
+                     int32_t* tile_stage, int32_t* chunk_done) {
+  if (!header) return HG_ERR_ARG;
+  std::unique_ptr<hg_ctx> ctx(new hg_ctx());
+  if (opt) ctx->opt = *opt; else hg_default_options(&ctx->opt);
+  std::vector<int32_t> cf_ptr, cf_nb, cf_face;
+  std::vector<double> cf_nx, cf_ny, cf_len;
+  int rc = hg::build_host(ctx.get(), m, b, f, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
+  if (rc == HG_OK) rc = hg::build_tiles(ctx.get(), m, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
+  if (rc != HG_OK) { set_global_err(ctx->err); return rc; }
+  const hg::FusedHost& fh = ctx->fh;
+  header[0] = fh.n_chunks; header[1] = fh.chunk_cells; header[2] = fh.n_tiles; header[3] = fh.T; header[4] = hg::kPipeAlign;
+  if (tile_stage)
+    for (int32_t s = 0; s < fh.n_chunks; ++s)
+      for (int32_t k = fh.stage_ptr[s]; k < fh.stage_ptr[s + 1]; ++k) tile_stage[fh.tile_order[k]] = s;
+  if (chunk_done) for (int32_t c = 0; c < fh.n_chunks; ++c) chunk_done[c] = fh.chunk_done[c];
+  return HG_OK;
+}
+
 int hg_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* x, double* out) {
   if (!ctx || !x || !out || n <= 0 || kind < 0 || kind > 4) return HG_ERR_ARG;
   CK(ctx, cudaSetDevice(ctx->opt.device));

@@ -507,6 +507,12 @@ HG_API int hg_mesh_stats(const hg_ctx* ctx, int64_t* n_cells, int64_t* n_faces, 
  * [N]) receives the internal->reference cell permutation.                                          */
 HG_API int hg_plan_stats(const hg_mesh_desc* mesh, const hg_bc_desc* bc, const hg_fields_desc* fields,
                   const hg_options* opt, int64_t* stats, int64_t* perm_out);
+/* Host-only: the stage tables of the host-buffer pipeline (hg_rhs / hg_rhs_vjp with host pointers on >= 1M cells) for this mesh.
+ * header[5] = n_chunks, nominal rows per chunk, n_tiles, tile_cells, alignment margin in rows; tile_stage[n_tiles] (may be NULL)
+ * = the chunk after which a tile's cells and halo have all landed; chunk_done[n_chunks] (may be NULL) = the stage after which
+ * result chunk c may leave.  opt->reserved[1] > 0 overrides the chunk count (tuning).                                    */
+HG_API int hg_plan_pipeline(const hg_mesh_desc* mesh, const hg_bc_desc* bc, const hg_fields_desc* fields, const hg_options* opt,
+                     int64_t* header, int32_t* tile_stage, int32_t* chunk_done);
 /* Accuracy probe of the kernels' branch-free fp64 helpers (hg_device.cuh): out[i] = f(x[i]) evaluated on the device,
  * kind 0 = 1/x, 1 = 1/sqrt(x), 2 = sqrt(x), 3 = sqrt(x^2 + eps) (smooth abs), 4 = x^(-7/3); x > 0, host pointers.          */
 HG_API int hg_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* x, double* out);

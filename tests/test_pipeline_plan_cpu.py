@@ -1,0 +1,59 @@
+"""Stage tables of the host-buffer pipeline (hg_rhs / hg_rhs_vjp with host pointers on >= 1M cells), checked on the CPU against
+the mesh adjacency.  Chunk c of a component whose host address needs a shift sh < margin moves the reference rows
+[c csz - sh, (c+1) csz - sh) (every copy then starts at a multiple of 256 bytes), so:
+  * a tile may run in stage s only if all its cells AND their face neighbours lie below (s+1) csz - margin (or s is the last stage);
+  * result chunk c takes rows from c csz - margin on and may leave after stage chunk_done[c] only if every tile owning one of
+    those rows has run by then."""
+import numpy as np
+import pytest
+
+import _pkg
+
+
+@pytest.fixture(scope="module")
+def hg():
+    return _pkg.load()
+
+
+def _needed_stage(rows, K, csz, margin):
+    return np.minimum(K - 1, (rows + margin) // csz)
+
+
+@pytest.mark.parametrize("chunks", [0, 5, 64])
+def test_stage_tables_respect_the_shifted_chunk_boundaries(hg, chunks):
+    from hydrograd_jl_b200 import synthetic as S
+    flat, _ = S.river(1000, 1050)
+    N, ld = int(flat["n_cells"]), int(flat["ld"])
+    assert N >= 1 << 20
+    plan = hg.plan_pipeline(flat, pipeline_chunks=chunks)
+    _, perm = hg.plan_stats(flat, want_perm=True)          # internal -> reference cell id
+    K, csz, T, margin = plan["n_chunks"], plan["chunk_cells"], plan["tile_cells"], plan["margin"]
+    assert K == (chunks or 8) and margin == 32 and csz % margin == 0 and K * csz >= N and (K - 1) * csz < N
+    assert plan["n_tiles"] == (N + T - 1) // T
+    tile_of_row = np.empty(N, dtype=np.int64)
+    tile_of_row[perm] = np.arange(N) // T                    # tile that owns reference row r
+    # rows a tile needs: its own cells and their face neighbours (boundary faces have ghosts, not rows)
+    nf = np.asarray(flat["cell_nfaces"])
+    neigh = np.asarray(flat["cell_neighbors"]).reshape(ld, N).T - int(flat["index_base"])
+    faces = np.asarray(flat["cell_faces"]).reshape(ld, N).T
+    isb = np.asarray(flat["face_is_boundary"]).astype(bool)
+    need = _needed_stage(np.arange(N), K, csz, margin)       # stage at which a row has landed for every component
+    tile_need = np.zeros(plan["n_tiles"], dtype=np.int64)
+    np.maximum.at(tile_need, tile_of_row, need)
+    for j in range(ld):
+        valid = (j < nf)
+        fid = np.abs(faces[:, j]) - (1 if int(flat["index_base"]) == 1 else 0)
+        interior = valid & ~isb[np.where(valid, fid, 0)]
+        rows = np.nonzero(interior)[0]
+        np.maximum.at(tile_need, tile_of_row[rows], need[neigh[rows, j]])
+    ts = plan["tile_stage"].astype(np.int64)
+    assert (ts >= tile_need).all()                            # never before its inputs
+    # the only tiles held back are those with inlet-q faces (boundary-wide conveyance sum): they wait for the last chunk
+    late = np.nonzero(ts > tile_need)[0]
+    ptr = np.asarray(flat["bc_ptr"])
+    inlet_cells = np.asarray(flat["bc_internal_cells"])[:ptr[int(flat["n_inletq"])]] - int(flat["index_base"])
+    assert set(late) <= set(tile_of_row[inlet_cells]) and (ts[late] == K - 1).all()
+    # results: chunk c needs every row in [c csz - margin, (c+1) csz) (to N for the last chunk) computed
+    for c in range(K):
+        lo, hi = max(0, c * csz - margin), (N if c == K - 1 else min(N, (c + 1) * csz))
+        assert plan["chunk_done"][c] == ts[tile_of_row[lo:hi]].max()
