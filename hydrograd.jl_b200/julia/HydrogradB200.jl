@@ -65,7 +65,7 @@ mutable struct Context
         finalizer(c -> (c.handle != C_NULL && ccall((:hg_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle); c.handle = C_NULL), ctx)
         return ctx
     end
-    function Context(p_extra; device::Integer=0, tile_cells::Integer=512, strict::Bool=false)
+    function Context(p_extra; device::Integer=0, tile_cells::Integer=256, strict::Bool=false)
         h = _create(p_extra, Int32(device), Int32(tile_cells), strict)
         ctx = new(h, p_extra.my_mesh_2D.numOfCells, HG_PARAM[p_extra.active_param_name])
         finalizer(c -> (c.handle != C_NULL && ccall((:hg_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle); c.handle = C_NULL), ctx)
