@@ -139,6 +139,7 @@ SYMBOLS = {
                                 c_i64p, c_i64p]),
     "hg_plan_pipeline": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(BcDesc), C.POINTER(FieldsDesc), C.POINTER(Options),
                                    c_i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "hg_debug_chunk_rows": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_i64p, c_i64p]),
     "hg_flush_l2": (C.c_int, [_vp]),
     "hg_set_ude_model": (C.c_int, [_vp, C.POINTER(UdeDesc), c_f64p]),
     "hg_set_controller_pow": (C.c_int, [_vp, C.c_int32]),

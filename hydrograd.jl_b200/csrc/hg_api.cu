@@ -1797,6 +1797,15 @@ int hg_plan_pipeline(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields
   return HG_OK;
 }
 
+// Host-only: the rows [r0, r1) chunk c of a component moves when that component's row 0 sits at host address host_addr -- the
+// geometry hg_rhs / hg_rhs_vjp use (chunk_rows above), exposed so that the CPU tests can check coverage, alignment and the
+// margins the stage tables assume.
+int hg_debug_chunk_rows(uint64_t host_addr, int32_t c, int32_t K, int64_t rows_per_chunk, int64_t N, int64_t* r0, int64_t* r1) {
+  if (!r0 || !r1 || K < 1 || c < 0 || c >= K || rows_per_chunk < 1 || N < 1) return HG_ERR_ARG;
+  chunk_rows(reinterpret_cast<const double*>(static_cast<uintptr_t>(host_addr)), c, K, rows_per_chunk, N, *r0, *r1);
+  return HG_OK;
+}
+
 int hg_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* x, double* out) {
   if (!ctx || !x || !out || n <= 0 || kind < 0 || kind > 4) return HG_ERR_ARG;
   CK(ctx, cudaSetDevice(ctx->opt.device));

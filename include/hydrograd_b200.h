@@ -513,6 +513,9 @@ HG_API int hg_plan_stats(const hg_mesh_desc* mesh, const hg_bc_desc* bc, const h
  * result chunk c may leave.  opt->reserved[1] > 0 overrides the chunk count (tuning).                                    */
 HG_API int hg_plan_pipeline(const hg_mesh_desc* mesh, const hg_bc_desc* bc, const hg_fields_desc* fields, const hg_options* opt,
                      int64_t* header, int32_t* tile_stage, int32_t* chunk_done);
+/* Host-only: rows [r0, r1) that chunk c (of K, nominal size rows_per_chunk) of a [N] component moves when the component starts at
+ * host address host_addr: boundaries are shifted so that every copy starts at a multiple of 256 bytes (test hook). */
+HG_API int hg_debug_chunk_rows(uint64_t host_addr, int32_t c, int32_t K, int64_t rows_per_chunk, int64_t N, int64_t* r0, int64_t* r1);
 /* Accuracy probe of the kernels' branch-free fp64 helpers (hg_device.cuh): out[i] = f(x[i]) evaluated on the device,
  * kind 0 = 1/x, 1 = 1/sqrt(x), 2 = sqrt(x), 3 = sqrt(x^2 + eps) (smooth abs), 4 = x^(-7/3); x > 0, host pointers.          */
 HG_API int hg_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* x, double* out);

@@ -57,3 +57,32 @@ def test_stage_tables_respect_the_shifted_chunk_boundaries(hg, chunks):
     for c in range(K):
         lo, hi = max(0, c * csz - margin), (N if c == K - 1 else min(N, (c + 1) * csz))
         assert plan["chunk_done"][c] == ts[tile_of_row[lo:hi]].max()
+
+
+def test_chunk_rows_cover_the_vector_at_aligned_host_addresses(hg):
+    """hg_debug_chunk_rows = the geometry the copies use: for any host address of a component, the K chunks tile [0, N) without
+    gaps, every interior boundary is a multiple of 256 bytes in HOST address, chunk c has landed at least the rows the stage
+    tables count on ((c+1) csz - margin) and never reaches beyond the rows result chunk c gathers."""
+    import ctypes as C
+    lib = hg._lib.load()
+    rng = np.random.default_rng(3)
+    r0, r1 = C.c_int64(), C.c_int64()
+    margin = 32
+    for N, K in [(15998186, 30), (1 << 20, 8), (1050000, 8), (1234567, 64), (4096, 4), (100000, 97)]:
+        csz = ((N + K - 1) // K + margin - 1) // margin * margin if K > 1 else N
+        for addr in [0x7F0000000000, 0x7F0000000008, 0x7F00000000F8] + [int(a) * 8 for a in rng.integers(1 << 20, 1 << 40, 5)]:
+            prev = 0
+            for c in range(K):
+                assert lib.hg_debug_chunk_rows(addr, c, K, csz, N, C.byref(r0), C.byref(r1)) == 0
+                a, b = r0.value, r1.value
+                assert 0 <= a <= b <= N
+                if b > a:
+                    assert a == prev
+                    prev = b
+                    if c > 0:
+                        assert (addr + 8 * a) % 256 == 0
+                    assert max(0, c * csz - margin) <= a and b <= (N if c == K - 1 else min(N, (c + 1) * csz))
+                landed = N if c == K - 1 else max(0, min(N, (c + 1) * csz - margin))
+                assert prev >= landed
+            assert prev == N
+    assert lib.hg_debug_chunk_rows(0, 3, 3, 32, 100, C.byref(r0), C.byref(r1)) != 0      # c out of range
