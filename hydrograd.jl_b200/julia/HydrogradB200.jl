@@ -18,8 +18,10 @@
 # Forward-mode callers (ForwardDiff.Dual state and / or parameters: ForwardDiff.jacobian around the solve in
 # swe_2D_sensitivity.jl:80, the ForwardDiffSensitivity / ForwardSensitivity inversion options) are served by the
 # Dual methods of `swe_2d_rhs` below: values and partials are split, every partial goes through the device's
-# forward mode (hg_rhs_jvp, one call per partial) and the Duals are reassembled.  That entry point runs on the plain
-# tables, so such drivers create the context with `strict=true`; a fused forward-mode kernel is the next step.
+# forward mode (hg_rhs_jvp_multi: one upload of the state, all partials of a chunk in one launch) and the Duals are
+# reassembled.  A default context runs the fused forward-mode tile kernel; with `strict=true` the calls run on the plain
+# tables in the reference's evaluation order.  The rrule's pullback reuses the state its forward call left on the device
+# (hg_rhs_vjp with Q = NULL while hg_state_generation is unchanged), so an adjoint stage uploads only the cotangent.
 module HydrogradB200
 
 using ChainRulesCore
