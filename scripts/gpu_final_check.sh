@@ -1,5 +1,6 @@
 #!/bin/bash
-# Last call of a round: the whole device suite, the smoke entry, then the default bench line (N = 1).
+# The whole device suite with its printed figures kept (profiles/roundN_gpu_tests_full.log is a copy of gpurun_out/gpu_full.log),
+# the smoke entry, then the default bench line (N = 1): the last call of a round.
 mkdir -p gpurun_out
 timeout 240 python -m pytest tests -m gpu -q -x -s -p no:cacheprovider --tb=short --durations=10 > gpurun_out/gpu_full.log 2>&1
 echo "exit $?" >> gpurun_out/gpu_full.log
