@@ -32,7 +32,7 @@ def _c_type(t):
     t = " ".join(t.replace("*", " * ").split())
     const = t.startswith("const ")
     t = t[6:] if const else t
-    table = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double, "float": C.c_float, "uint8_t": C.c_uint8,
+    table = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double, "float": C.c_float, "uint8_t": C.c_uint8, "uint64_t": C.c_uint64,
              "double *": L.c_f64p, "int64_t *": L.c_i64p, "int32_t *": i32p, "float *": f32p, "uint8_t *": L.c_u8p, "char *": C.c_char_p,
              "void *": C.c_void_p, "hg_ctx *": C.c_void_p, "hg_case *": C.c_void_p, "hg_ctx * *": P(C.c_void_p), "hg_case * *": P(C.c_void_p),
              "hg_json *": C.c_void_p, "hg_json * *": P(C.c_void_p),
