@@ -1,0 +1,108 @@
+"""Cross-check of the primary oracle (oracle/swe_oracle.cpp, scalar-expanded C++) against a second restatement written
+independently from the Julia source in its own shapes (oracle/rhs_literal.py: 3x3 matrices for the Roe dissipation, per-boundary
+vectors + update_1d_array for the ghosts, the comprehension of compute_inviscid_fluxes).  Two routes from the same source that
+agree to rounding on fuzzed states pin what the reference's committed trajectories do not reach: every wet/dry branch of the
+Roe flux, symmetry boundaries, several inlets, and the zb / ManningN / Q parameter bindings."""
+import numpy as np
+import pytest
+
+from oracle import rhs_literal as LIT
+from oracle import srh2d_ref as R
+from oracle.oracle import Oracle
+from tests import cases
+from tests.test_srh_reader_cpu import _write_random_case
+
+MODES = ((None, "", 0), ("n", "ManningN", 2), ("z", "zb", 1), ("q", "Q", 3))
+
+
+def _params(c, kind, rng):
+    if kind == "n":
+        return np.asarray(c.ManningN_zone, dtype=np.float64) * (1 + 0.2 * rng.uniform(-1, 1, c.ManningN_zone.size))
+    if kind == "z":
+        return np.asarray(c.zb_cells, dtype=np.float64) + 0.02 * rng.standard_normal(c.zb_cells.size)
+    if kind == "q":
+        return np.asarray(c.bc.inletQ_TotalQ, dtype=np.float64) * 0.8
+    return None
+
+
+def _compare(c, seeds, tol=2e-13):
+    flat = R.flatten(c)
+    o = Oracle(flat)
+    rng = np.random.default_rng(17)
+    worst = 0.0
+    for Q in [c.Q0] + [cases.random_state_flat(flat, s, dry_frac=0.08) for s in seeds]:
+        sc = cases.flat_scale(flat, Q)
+        for kind, name, code in MODES:
+            p = _params(c, kind, rng)
+            if kind == "q" and p.size == 0:
+                continue
+            want = o.rhs(Q, p, code)
+            got = LIT.swe_2d_rhs(c, Q, p, name)
+            err = np.abs(got - want) / sc
+            worst = max(worst, float(err.max()))
+            assert (err <= tol).all(), (name, float(err.max()))
+    return worst
+
+
+@pytest.mark.parametrize("name", ["simple", "oneD_bump", "savannah"])
+def test_literal_restatement_agrees_on_the_reference_fixtures(name, oracle_lib):
+    c = cases.load(name)
+    worst = _compare(c, seeds=(3,) if name == "savannah" else (3, 4))
+    print(f"{name}: literal vs C++ oracle, worst error {worst:.2e} of the flux scale")
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_literal_restatement_agrees_with_symmetry_and_two_inlets(tmp_path, seed, oracle_lib):
+    _write_random_case(str(tmp_path), seed)
+    c = R.load_case(str(tmp_path), "rnd.srhhydro", ("constant", [3.0, 2.0, 0.1, 0.0]))
+    assert len(c.bc.kinds["symm"]) == 1 and len(c.bc.kinds["inletQ"]) == 2
+    _compare(c, seeds=(5, 6, 7))
+
+
+def test_roe_flux_every_branch(oracle_lib):
+    """Single-face fuzz: 4e4 random left / right states, a third of the sides at or below h_small (exact ties included), random
+    bed steps so that both 'virtual wall' branches, both one-sided branches, the dry-dry branch and the main branch all occur."""
+    c = cases.load("simple")
+    o = Oracle(R.flatten(c))
+    rng = np.random.default_rng(99)
+    hmin, g = 1e-3, 9.81
+    seen = {}
+    worst = 0.0
+    for _ in range(40000):
+        th = rng.uniform(0, 2 * np.pi)
+        nx, ny = np.cos(th), np.sin(th)
+        side = []
+        for _s in range(2):
+            h = float(np.exp(rng.uniform(np.log(1e-3), np.log(10.0))))
+            if rng.random() < 0.33:
+                h = float(rng.choice([1e-3, 5e-4, 9.999e-4]))          # the clamp leaves h = h_small; smaller values only occur in ghosts
+                h = max(h, 1e-3) if rng.random() < 0.7 else h
+            dry = h <= hmin
+            sp, a = rng.uniform(0, 3), rng.uniform(0, 2 * np.pi)
+            hu, hv = (0.0, 0.0) if dry and rng.random() < 0.8 else (h * sp * np.cos(a), h * sp * np.sin(a))
+            zb = rng.uniform(-1, 1) if rng.random() < 0.7 else rng.uniform(-12, 12)
+            hstill = rng.uniform(0.0, 5.0)
+            side.append((h - hstill, hstill, h, hu, hv, zb))
+        (xiL, hsL, hL, huL, hvL, zL), (xiR, hsR, hR, huR, hvR, zR) = side
+        if hL <= hmin and hR <= hmin:
+            br = "dry-dry"
+        elif (hL + zL) < (zR + hmin) and hR <= hmin:
+            br = "wall-R"
+        elif (hR + zR) < (zL + hmin) and hL <= hmin:
+            br = "wall-L"
+        elif hL <= hmin:
+            br = "dry-L"
+        elif hR <= hmin:
+            br = "dry-R"
+        else:
+            br = "wet"
+        seen[br] = seen.get(br, 0) + 1
+        want = o.roe(list(side[0]) + list(side[1]), nx, ny, g, hmin)
+        got = LIT.riemann_2d_roe(*side[0], *side[1], g, (nx, ny), hmin)
+        scale = 0.5 * g * (max(hL, hR) ** 2 + xiL ** 2 + xiR ** 2 + 2 * abs(xiL) * hsL + 2 * abs(xiR) * hsR) \
+            + (np.hypot(huL, hvL) + np.hypot(huR, hvR)) * (3.0 + np.sqrt(g * max(hL, hR))) + 1e-12
+        err = float(np.abs(got - want).max() / scale)
+        worst = max(worst, err)
+        assert err <= 1e-13, (br, side, got, want)
+    assert all(seen.get(b, 0) >= 100 for b in ("dry-dry", "wall-R", "wall-L", "dry-L", "dry-R", "wet")), seen
+    print(f"Roe flux, branches seen {seen}, worst error {worst:.2e} of the flux scale")
