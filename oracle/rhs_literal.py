@@ -172,3 +172,14 @@ def swe_2d_rhs(case, Q, params_vector=None, active_param_name=""):
     source_x = above_small_h * (g * xi * S0_cells[:, 0] - friction_x)
     source_y = above_small_h * (g * xi * S0_cells[:, 1] - friction_y)
     return updates_inviscid + np.concatenate([np.zeros(N), source_x, source_y])
+
+
+def custom_ODE_update_cells(case, Q, params_vector, dt, active_param_name=""):
+    """ode_solvers/custom_ODE_solvers.jl:5-33 -- explicit Euler with the reference's dry mask, which tests the NEW xi (the first
+    N entries of Q are xi, not h) against h_small and then sets xi := h_small, q := 0."""
+    N = case.mesh.numOfCells
+    Q_new = Q + dt * swe_2d_rhs(case, Q, params_vector, active_param_name)   # :11-16
+    dry_mask = Q_new[:N] < case.h_small                                      # :19
+    return np.concatenate([np.where(dry_mask, case.h_small, Q_new[:N]),      # :22-26
+                           np.where(dry_mask, 0.0, Q_new[N:2 * N]),
+                           np.where(dry_mask, 0.0, Q_new[2 * N:3 * N])])

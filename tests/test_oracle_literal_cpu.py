@@ -106,3 +106,21 @@ def test_roe_flux_every_branch(oracle_lib):
         assert err <= 1e-13, (br, side, got, want)
     assert all(seen.get(b, 0) >= 100 for b in ("dry-dry", "wall-R", "wall-L", "dry-L", "dry-R", "wet")), seen
     print(f"Roe flux, branches seen {seen}, worst error {worst:.2e} of the flux scale")
+
+
+def test_euler_stepper_with_the_xi_mask_quirk(oracle_lib):
+    """custom_ODE_update_cells: 40 steps from a state whose xi dips below h_small in places (the reference masks on xi, not h)."""
+    c = cases.load("oneD_bump")
+    o = Oracle(R.flatten(c))
+    N = c.mesh.numOfCells
+    Q = c.Q0.copy()
+    Q[:N] = np.where(np.arange(N) % 7 == 0, -0.02, Q[:N])                    # xi below h_small although h = xi + hstill is not
+    dt, nsteps = 2e-3, 40
+    want = o.euler(Q, dt, nsteps)
+    got = Q.copy()
+    masked = 0
+    for _ in range(nsteps):
+        got = LIT.custom_ODE_update_cells(c, got, None, dt)
+        masked += int((got[:N] == c.h_small).sum())
+    assert masked > 0                                                        # the quirk is exercised
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
