@@ -25,6 +25,11 @@ from . import srh2d_ref as R
 
 EPS = np.finfo(np.float64).eps          # eps(Float64)
 
+# Every function below also accepts COMPLEX arguments: predicates, clamps and `max` look at the real part only (they are
+# piecewise-constant selectors for ForwardDiff / Zygote too) and everything else is complex-analytic, so
+# imag(f(x + i e v)) / e with e = 1e-30 is the exact directional derivative -- an AD-free check of the oracle's dual numbers.
+re = np.real
+
 
 def smooth_abs(x):                      # smooth_functions.jl:10-12
     return np.sqrt(x ** 2 + EPS)
@@ -41,22 +46,22 @@ def smooth_pow2(x):                     # smooth_functions.jl:50-52 with y = 2
 def riemann_2d_roe(xiL, hstillL, hL, huL, hvL, zb_L, xiR, hstillR, hR, huR, hvR, zb_R, g, normal, hmin):
     """swe_2D_solvers.jl:4-164, one if / elseif chain; the two 'virtual wall' branches fall through to the main part."""
     nx, ny = normal
-    if hL <= hmin and hR <= hmin:                                            # :16-22
+    if re(hL) <= hmin and re(hR) <= hmin:                                    # :16-22
         return np.zeros(3)
-    elif ((hL + zb_L) < (zb_R + hmin)) and (hR <= hmin):                     # :23-37
+    elif (re(hL + zb_L) < re(zb_R + hmin)) and (re(hR) <= hmin):             # :23-37
         hR = hL
         huR = -huL
         hvR = -hvL
-    elif ((hR + zb_R) < (zb_L + hmin)) and (hL <= hmin):                     # :39-52
+    elif (re(hR + zb_R) < re(zb_L + hmin)) and (re(hL) <= hmin):             # :39-52
         hL = hR
         huL = -huR
         hvL = -hvR
-    elif hL <= hmin:                                                         # :54-64
+    elif re(hL) <= hmin:                                                     # :54-64
         h_flux = huR * nx + hvR * ny
         hu_flux = (huR * (huR / hR) + 0.5 * g * smooth_pow2(hR)) * nx + huR * (hvR / hR) * ny
         hv_flux = (hvR * (huR / hR)) * nx + (hvR * (hvR / hR) + 0.5 * g * smooth_pow2(hR)) * ny
         return np.array([h_flux, hu_flux, hv_flux])
-    elif hR <= hmin:                                                         # :65-76
+    elif re(hR) <= hmin:                                                     # :65-76
         h_flux = huL * nx + hvL * ny
         hu_flux = (huL * (huL / hL) + 0.5 * g * smooth_pow2(hL)) * nx + huL * (hvL / hL) * ny
         hv_flux = (hvL * (huL / hL)) * nx + (hvL * (hvL / hL) + 0.5 * g * smooth_pow2(hL)) * ny
@@ -99,7 +104,7 @@ def process_all_boundaries_2d(case, h, q_x, q_y, ManningN_cells, zb_cells, inlet
     for k, b in enumerate(kinds["inletQ"]):                                  # :640-730
         ic = np.asarray(b["internalCellIDs"]) - 1
         L = np.asarray(b["lengths"], dtype=np.float64)
-        drywet = np.array([1.0 if h[c] > hs else 0.0 for c in ic])           # :665
+        drywet = np.array([1.0 if re(h[c]) > hs else 0.0 for c in ic])       # :665
         total_A = 0.0
         for i in range(len(ic)):                                             # :674-676, sequential generator sum
             total_A = total_A + L[i] ** (5.0 / 3.0) * h[ic[i]] / ManningN_cells[ic[i]] * drywet[i]
@@ -109,7 +114,8 @@ def process_all_boundaries_2d(case, h, q_x, q_y, ManningN_cells, zb_cells, inlet
         updates.append((h[ic], -h[ic] * velocity_normals * fn[:, 0] * drywet, -h[ic] * velocity_normals * fn[:, 1] * drywet))
     for k, b in enumerate(kinds["exitH"]):                                   # :748-773
         ic = np.asarray(b["internalCellIDs"]) - 1
-        updates.append((np.maximum(hs, exitH_WSE[k] - zb_cells[ic]), q_x[ic], q_y[ic]))
+        d = exitH_WSE[k] - zb_cells[ic]
+        updates.append((np.where(re(d) > hs, d, hs), q_x[ic], q_y[ic]))      # max.(h_small, WSE - zb), :763-764
     for b in kinds["wall"]:                                                  # :777-799
         ic = np.asarray(b["internalCellIDs"]) - 1
         updates.append((h[ic], -q_x[ic], -q_y[ic]))
@@ -132,18 +138,21 @@ def swe_2d_rhs(case, Q, params_vector=None, active_param_name=""):
     g, k_n, h_small = case.g, case.k_n, case.h_small
     xi, q_x, q_y = Q[:N], Q[N:2 * N], Q[2 * N:3 * N]                          # :93-95
     h = xi + case.hstill                                                     # :101
-    h = np.where(h <= h_small, h_small, h)                                   # :104-106 (the test of q uses the clamped h)
-    q_x = np.where(h <= h_small, 0.0, q_x)
-    q_y = np.where(h <= h_small, 0.0, q_y)
+    h = np.where(re(h) <= h_small, h_small, h)                               # :104-106 (the test of q uses the clamped h)
+    q_x = np.where(re(h) <= h_small, 0.0, q_x)
+    q_y = np.where(re(h) <= h_small, 0.0, q_y)
     ManningN_cells, zb_cells, zb_ghost, S0_cells = case.ManningN_cells, case.zb_cells, case.zb_ghost, case.S0_cells
     inletQ_TotalQ, exitH_WSE = case.bc.inletQ_TotalQ, case.bc.exitH_WSE
     if active_param_name == "zb":                                            # :114-126
-        zb_cells = np.asarray(params_vector, dtype=np.float64)
-        zb_ghost, _zb_faces, S0_cells = R.update_bed_data(m, zb_cells)
+        zb_cells = np.asarray(params_vector)
+        zb_ghost, _zb_faces, S0_cells = R.update_bed_data(m, re(zb_cells))
+        if np.iscomplexobj(zb_cells):                                        # update_bed_data is linear in zb
+            zg_i, _zf_i, S0_i = R.update_bed_data(m, np.imag(zb_cells))
+            zb_ghost, S0_cells = zb_ghost + 1j * zg_i, S0_cells + 1j * S0_i
     elif active_param_name == "ManningN":                                    # :153-161, process_ManningN_2D.jl:88
         ManningN_cells = np.array([params_vector[int(mid)] for mid in case.matID])
     elif active_param_name == "Q":                                           # :190-199
-        inletQ_TotalQ = np.asarray(params_vector, dtype=np.float64)
+        inletQ_TotalQ = np.asarray(params_vector)
     h_ghost, q_x_ghost, q_y_ghost = process_all_boundaries_2d(case, h, q_x, q_y, ManningN_cells, zb_cells, inletQ_TotalQ, exitH_WSE)
     xi_ghost = h_ghost - case.hstill_ghost                                   # :220
     # compute_inviscid_fluxes, :281-434
@@ -168,7 +177,7 @@ def swe_2d_rhs(case, Q, params_vector=None, active_param_name=""):
     mag = smooth_sqrt(q_x ** 2 + q_y ** 2)
     friction_x = g * ManningN_cells ** 2 / k_n ** 2 / (h + h_small) ** (7.0 / 3.0) * mag * q_x
     friction_y = g * ManningN_cells ** 2 / k_n ** 2 / (h + h_small) ** (7.0 / 3.0) * mag * q_y
-    above_small_h = (h > h_small).astype(np.float64)
+    above_small_h = (re(h) > h_small).astype(np.float64)
     source_x = above_small_h * (g * xi * S0_cells[:, 0] - friction_x)
     source_y = above_small_h * (g * xi * S0_cells[:, 1] - friction_y)
     return updates_inviscid + np.concatenate([np.zeros(N), source_x, source_y])
@@ -179,7 +188,7 @@ def custom_ODE_update_cells(case, Q, params_vector, dt, active_param_name=""):
     N entries of Q are xi, not h) against h_small and then sets xi := h_small, q := 0."""
     N = case.mesh.numOfCells
     Q_new = Q + dt * swe_2d_rhs(case, Q, params_vector, active_param_name)   # :11-16
-    dry_mask = Q_new[:N] < case.h_small                                      # :19
+    dry_mask = re(Q_new[:N]) < case.h_small                                  # :19
     return np.concatenate([np.where(dry_mask, case.h_small, Q_new[:N]),      # :22-26
                            np.where(dry_mask, 0.0, Q_new[N:2 * N]),
                            np.where(dry_mask, 0.0, Q_new[2 * N:3 * N])])

@@ -124,3 +124,43 @@ def test_euler_stepper_with_the_xi_mask_quirk(oracle_lib):
         masked += int((got[:N] == c.h_small).sum())
     assert masked > 0                                                        # the quirk is exercised
     assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+
+def _complex_step_check(c, seeds, tol=5e-12):
+    """imag(literal(Q + i e v, p + i e pdot)) / e against the oracle's dual-number pass J_Q v + J_p pdot."""
+    flat = R.flatten(c)
+    o = Oracle(flat)
+    rng = np.random.default_rng(23)
+    e = 1e-30
+    N = c.mesh.numOfCells
+    worst = 0.0
+    for s in seeds:
+        Q = cases.random_state_flat(flat, s, dry_frac=0.08)
+        for kind, name, code in MODES:
+            p = _params(c, kind, rng)
+            if kind == "q" and p.size == 0:
+                continue
+            v = rng.standard_normal(3 * N)
+            pdot = rng.standard_normal(p.size) * (0.01 if kind != "q" else 1.0) if p is not None else None
+            want = o.jvp(Q, v, p, pdot, code)[1]
+            got = np.imag(LIT.swe_2d_rhs(c, Q + 1j * e * v, None if p is None else p + 1j * e * pdot, name)) / e
+            err = float(np.abs(got - want).max() / np.abs(want).max())
+            worst = max(worst, err)
+            assert err <= tol, (name, err)
+    return worst
+
+
+@pytest.mark.parametrize("name", ["simple", "oneD_bump", "savannah"])
+def test_oracle_dual_numbers_against_complex_step_of_the_literal_restatement(name, oracle_lib):
+    """The brute-force J^T lambda every VJP test compares with is assembled from the oracle's dual-number passes.  Here those
+    passes are checked without any AD: the complex-step derivative of the independently written restatement (exact to
+    rounding; predicates and clamps select on the real part, as ForwardDiff treats them) in all four parameter modes."""
+    c = cases.load(name)
+    worst = _complex_step_check(c, seeds=(11,) if name == "savannah" else (11, 12))
+    print(f"{name}: oracle dual pass vs complex step of the literal restatement, worst {worst:.2e} of the largest entry")
+
+
+def test_oracle_dual_numbers_with_symmetry_and_two_inlets(tmp_path, oracle_lib):
+    _write_random_case(str(tmp_path), 2)
+    c = R.load_case(str(tmp_path), "rnd.srhhydro", ("constant", [3.0, 2.0, 0.1, 0.0]))
+    _complex_step_check(c, seeds=(13, 14))
