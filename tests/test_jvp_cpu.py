@@ -245,3 +245,38 @@ def test_forward_mode_on_random_meshes_with_symmetry_and_two_inlets(host, tmp_pa
     assert (np.abs(dQ - ref) <= 1e-13 * cases.flat_scale(flat, Q)).all()
     assert np.abs(dQd - ref_d).max() <= 1e-12 * np.abs(ref_d).max()
     assert flat["n_symm"] == 1 and flat["n_inletq"] == 2
+
+
+@pytest.mark.parametrize("name", ["savannah", "oneD_bump", "simple", "random_symm"])
+def test_product_source_against_the_independent_literal_restatement(host, name, tmp_path):
+    """Not twin against twin: hg_jvp_impl.h (the source of the strict path and of the forward-mode kernels) against
+    oracle/rhs_literal.py, which was written independently of the C++ oracle in the Julia's own shapes -- values against its
+    RHS, tangents against its complex-step derivative (AD-free), all four parameter modes, states with dry cells."""
+    from oracle import rhs_literal as LIT
+    if name == "random_symm":
+        from tests.test_srh_reader_cpu import _write_random_case
+        _write_random_case(str(tmp_path), 4)
+        c = R.load_case(str(tmp_path), "rnd.srhhydro", ("constant", [3.0, 2.0, 0.1, 0.0]))
+        flat = R.flatten(c)
+    else:
+        c, flat = _flat(name)
+    N = c.mesh.numOfCells
+    hj = HostJvp(host, flat)
+    rng = np.random.default_rng(31)
+    e = 1e-30
+    Q = cases.random_state_flat(flat, 21, dry_frac=0.08)
+    sc = cases.flat_scale(flat, Q)
+    for mode, lit_name in (("none", ""), ("zb", "zb"), ("ManningN", "ManningN"), ("Q", "Q")):
+        params = {"none": None, "zb": c.zb_cells + 0.02 * rng.standard_normal(N),
+                  "ManningN": np.asarray(c.ManningN_zone, dtype=np.float64) * (1 + 0.1 * rng.uniform(-1, 1, c.ManningN_zone.size)),
+                  "Q": np.asarray(flat["inletQ_TotalQ"], dtype=np.float64) * 0.9}[mode]
+        if mode == "Q" and flat["n_inletq"] == 0:
+            continue
+        V = rng.standard_normal(3 * N)
+        pdot = None if params is None else rng.standard_normal(params.size) * (1.0 if mode == "Q" else 0.01)
+        dQ, dQd, rc = hj(Q, V, params, pdot, ACTIVE[mode])
+        assert rc == 0
+        want = LIT.swe_2d_rhs(c, Q, params, lit_name)
+        assert (np.abs(dQ - want) <= 2e-13 * sc).all(), (name, mode)
+        want_d = np.imag(LIT.swe_2d_rhs(c, Q + 1j * e * V, None if params is None else params + 1j * e * pdot, lit_name)) / e
+        assert np.abs(dQd - want_d).max() <= 5e-12 * np.abs(want_d).max(), (name, mode)
