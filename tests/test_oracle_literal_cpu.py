@@ -164,3 +164,25 @@ def test_oracle_dual_numbers_with_symmetry_and_two_inlets(tmp_path, oracle_lib):
     _write_random_case(str(tmp_path), 2)
     c = R.load_case(str(tmp_path), "rnd.srhhydro", ("constant", [3.0, 2.0, 0.1, 0.0]))
     _complex_step_check(c, seeds=(13, 14))
+
+
+class _OracleBackedContext:
+    """Stand-in with the device Context's rhs / rhs_vjp signatures, backed by the C++ oracle: lets the bodies the device tests
+    use (tests/literal_checks.py) run on the CPU."""
+    CODE = {None: 0, "zb": 1, "ManningN": 2, "Q": 3}
+
+    def __init__(self, flat):
+        self.o = Oracle(flat)
+
+    def rhs(self, Q, params=None, active=None):
+        return self.o.rhs(Q, params, self.CODE[active])
+
+    def rhs_vjp(self, Q, lam, params=None, active=None):
+        return self.o.vjp_bruteforce(Q, lam, params, self.CODE[active])[:2]
+
+
+@pytest.mark.parametrize("name", ["simple", "oneD_bump"])
+def test_shared_device_check_bodies_run_on_the_oracle(name, oracle_lib):
+    from tests import literal_checks as LC
+    assert LC.check_rhs(_OracleBackedContext, name, 2e-13) < 2e-13
+    assert LC.check_vjp_identity(_OracleBackedContext, name, 1e-11) < 1e-11
