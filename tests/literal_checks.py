@@ -51,7 +51,7 @@ def check_vjp_identity(make_ctx, name, tol):
     rng = np.random.default_rng(43)
     e = 1e-30
     worst = 0.0
-    Q = cases.random_state_flat(flat, 33, dry_frac=0.08)
+    Q = cases.random_state_flat(flat, 1, dry_frac=0.08)          # (the state of test_gpu_vjp.py)
     for mode, kind in MODES:
         p = params_for(c, kind, rng)
         if kind == "q" and p.size == 0:
