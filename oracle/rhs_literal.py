@@ -131,6 +131,14 @@ def process_all_boundaries_2d(case, h, q_x, q_y, ManningN_cells, zb_cells, inlet
     return all_h[idx], all_qx[idx], all_qy[idx]
 
 
+def compute_friction_terms(h, q_x, q_y, ManningN_cells, g, k_n, h_small):
+    """semi_discretize_swe_2D.jl:544-547, Manning branch, evaluated left to right like the Julia expression."""
+    mag = smooth_sqrt(q_x ** 2 + q_y ** 2)
+    friction_x = g * ManningN_cells ** 2 / k_n ** 2 / (h + h_small) ** (7.0 / 3.0) * mag * q_x
+    friction_y = g * ManningN_cells ** 2 / k_n ** 2 / (h + h_small) ** (7.0 / 3.0) * mag * q_y
+    return friction_x, friction_y
+
+
 def swe_2d_rhs(case, Q, params_vector=None, active_param_name=""):
     """semi_discretize_swe_2D.jl:18-277 for the constant-Manning / inversion / sensitivity configurations."""
     m = case.mesh
@@ -174,9 +182,7 @@ def swe_2d_rhs(case, Q, params_vector=None, active_param_name=""):
     upd = np.array(updates_inviscid_cells)
     updates_inviscid = np.concatenate([upd[:, 0], upd[:, 1], upd[:, 2]])     # rearrange_vector_of_vectors, :437-446
     # compute_friction_terms :544-547 (evaluated left to right), compute_source_terms :463-478
-    mag = smooth_sqrt(q_x ** 2 + q_y ** 2)
-    friction_x = g * ManningN_cells ** 2 / k_n ** 2 / (h + h_small) ** (7.0 / 3.0) * mag * q_x
-    friction_y = g * ManningN_cells ** 2 / k_n ** 2 / (h + h_small) ** (7.0 / 3.0) * mag * q_y
+    friction_x, friction_y = compute_friction_terms(h, q_x, q_y, ManningN_cells, g, k_n, h_small)
     above_small_h = (re(h) > h_small).astype(np.float64)
     source_x = above_small_h * (g * xi * S0_cells[:, 0] - friction_x)
     source_y = above_small_h * (g * xi * S0_cells[:, 1] - friction_y)

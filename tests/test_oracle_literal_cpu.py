@@ -186,3 +186,22 @@ def test_shared_device_check_bodies_run_on_the_oracle(name, oracle_lib):
     from tests import literal_checks as LC
     assert LC.check_rhs(_OracleBackedContext, name, 2e-13) < 2e-13
     assert LC.check_vjp_identity(_OracleBackedContext, name, 1e-11) < 1e-11
+
+
+@pytest.mark.parametrize("name", ["savannah", "oneD_bump", "oneD_uniform"])
+def test_literal_restatement_has_its_own_pins_to_the_reference_files(name):
+    """Not only through the C++ oracle: the literal friction terms reproduce the reference's friction_x/y_truth, and its RHS at
+    the reference's saved final state of the sensitivity run is at the steady-state residual level."""
+    c, t = cases.load(name), cases.truth(name)
+    hs = c.h_small
+    h = t["h_truth"]
+    qx, qy = t["u_truth"] * (h + hs), t["v_truth"] * (h + hs)   # process_forward_simulation_results_2D.jl:32-33
+    fx, fy = LIT.compute_friction_terms(h, qx, qy, t["ManningN_cells_truth"], c.g, c.k_n, hs)
+    assert np.abs(fx - t["friction_x_truth"]).max() <= 6e-16 * np.abs(t["friction_x_truth"]).max()
+    assert np.abs(fy - t["friction_y_truth"]).max() <= 6e-16 * max(np.abs(t["friction_y_truth"]).max(), 1e-30) + 1e-30
+    if name == "oneD_bump":
+        cs = cases.load("oneD_bump_sens")
+        tj = np.load(cases.GOLD + "/oneD_bump_sens/trajectory.npz")["forward_simulation_results"]
+        p = np.array([0.03, 0.02, 0.03])
+        r = [np.abs(LIT.swe_2d_rhs(cs, tj[k], p, "ManningN")).max() for k in (0, 2)]
+        assert r[0] > 1.0 and r[1] < 5e-5
