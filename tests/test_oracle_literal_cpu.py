@@ -181,7 +181,7 @@ class _OracleBackedContext:
         return self.o.vjp_bruteforce(Q, lam, params, self.CODE[active])[:2]
 
 
-@pytest.mark.parametrize("name", ["simple", "oneD_bump"])
+@pytest.mark.parametrize("name", ["simple", "oneD_bump", "savannah"])
 def test_shared_device_check_bodies_run_on_the_oracle(name, oracle_lib):
     from tests import literal_checks as LC
     assert LC.check_rhs(_OracleBackedContext, name, 2e-13) < 2e-13
