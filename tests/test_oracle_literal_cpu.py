@@ -205,3 +205,35 @@ def test_literal_restatement_has_its_own_pins_to_the_reference_files(name):
         p = np.array([0.03, 0.02, 0.03])
         r = [np.abs(LIT.swe_2d_rhs(cs, tj[k], p, "ManningN")).max() for k in (0, 2)]
         assert r[0] > 1.0 and r[1] < 5e-5
+
+
+def test_literal_restatement_reproduces_the_reference_transient_on_its_own():
+    """The hard pin of tests/test_oracle_golden.py::test_reference_trajectory_hard_pin without the C++ oracle anywhere: the literal
+    restatement (values and, by complex step, the partials with respect to the two Manning zones) integrated with the restated
+    Tsit5 the way the reference ran (Dual-aware error norm, fastpow, dense-output saves) lands on the reference's saved state of
+    the uniform-flow channel at t = 1 s -- about 25 accepted steps x 7 stages on a moving transient."""
+    from tests import tsit5_ref as T
+    name, p = "oneD_uniform_sens", np.array([0.03, 0.03])
+    c = cases.load(name)
+    tj = np.load(cases.GOLD + f"/{name}/trajectory.npz")
+    idx, ref = tj["early_index"], tj["forward_simulation_results_early"]
+    assert idx[0] == 1 and np.array_equal(tj["forward_simulation_results"][0], c.Q0)
+    K, N = p.size, c.mesh.numOfCells
+    e = 1e-30
+
+    def rhs(U):
+        out = np.empty_like(U)
+        for k in range(K):
+            ek = np.zeros(K)
+            ek[k] = 1.0
+            z = LIT.swe_2d_rhs(c, U[0] + 1j * e * U[1 + k], p + 1j * e * ek, "ManningN")
+            out[0], out[1 + k] = z.real, z.imag / e
+        return out
+
+    U0 = np.zeros((1 + K, 3 * N))
+    U0[0] = c.Q0
+    _, saves, st = T.solve(rhs, U0, 0.0, 1.3, 0.02, True, 1e-6, 1e-3, np.array([1.0]), saveat="interp", norm=T.dual_norm, pow="fastpow")
+    err = max(np.abs(saves[0][0][:N] - ref[0][:N]).max(), np.abs(saves[0][0][N:2 * N] - ref[0][N:2 * N]).max())
+    print(f"literal restatement + Tsit5 vs the reference's saved state at t = 1 s: {err:.1e}  {st}")
+    assert np.abs(ref[0][:N] - c.Q0[:N]).max() > 1e-3          # a real transient
+    assert err <= 2e-9
