@@ -86,3 +86,38 @@ def test_chunk_rows_cover_the_vector_at_aligned_host_addresses(hg):
                 assert prev >= landed
             assert prev == N
     assert lib.hg_debug_chunk_rows(0, 3, 3, 32, 100, C.byref(r0), C.byref(r1)) != 0      # c out of range
+
+
+@pytest.mark.parametrize("tile", [128, 256])
+def test_tile_builder_accounts_for_every_face_and_halo_cell(hg, tile):
+    """hg_plan_stats against the mesh adjacency: with cells renumbered so that tile t owns the internal cells [t T, (t+1) T), every
+    interior face is stored once in the tile that owns both its cells and once in EACH of the two tiles it connects otherwise
+    (cut faces are evaluated redundantly, no flux exchange); every boundary face once; a tile's halo is the set of distinct
+    neighbour cells outside it."""
+    from hydrograd_jl_b200 import synthetic as S
+    flat, _ = S.river(300, 120)
+    N, ld, base = int(flat["n_cells"]), int(flat["ld"]), int(flat["index_base"])
+    st, perm = hg.plan_stats(flat, tile_cells=tile, want_perm=True)
+    assert sorted(perm.tolist()) == list(range(N))                     # a permutation of the reference ids
+    tile_of = np.empty(N, dtype=np.int64)
+    tile_of[perm] = np.arange(N) // tile
+    assert st["n_tiles"] == (N + tile - 1) // tile and st["max_local"] >= min(tile, N)
+    nf = np.asarray(flat["cell_nfaces"])
+    neigh = np.asarray(flat["cell_neighbors"]).reshape(ld, N).T - base
+    faces = np.abs(np.asarray(flat["cell_faces"]).reshape(ld, N).T) - base
+    isb = np.asarray(flat["face_is_boundary"]).astype(bool)
+    same = cut = bnd = 0
+    halo = set()
+    for j in range(ld):
+        rows = np.nonzero(j < nf)[0]
+        b = isb[faces[rows, j]]
+        bnd += int(b.sum())
+        r, nb = rows[~b], neigh[rows[~b], j]
+        s = tile_of[r] == tile_of[nb]
+        same += int(s.sum())                                          # seen from both cells: two per face
+        cut += int((~s).sum())                                        # seen from both cells: one per (face, tile)
+        halo.update(zip(tile_of[r[~s]].tolist(), nb[~s].tolist()))
+    assert st["sum_cell_faces"] == int(nf.sum())
+    assert st["interior_tile_faces"] == same // 2 + cut
+    assert st["tile_faces"] == same // 2 + cut + bnd
+    assert st["halo_cells"] == len(halo)
