@@ -139,6 +139,9 @@ SYMBOLS = {
                                 c_i64p, c_i64p]),
     "hg_plan_pipeline": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(BcDesc), C.POINTER(FieldsDesc), C.POINTER(Options),
                                    c_i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "hg_plan_open": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(BcDesc), C.POINTER(FieldsDesc), C.POINTER(Options), C.POINTER(_vp)]),
+    "hg_plan_close": (None, [_vp]),
+    "hg_plan_array": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), c_i64p, C.POINTER(C.c_int32)]),
     "hg_debug_chunk_rows": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_i64p, c_i64p]),
     "hg_flush_l2": (C.c_int, [_vp]),
     "hg_set_ude_model": (C.c_int, [_vp, C.POINTER(UdeDesc), c_f64p]),

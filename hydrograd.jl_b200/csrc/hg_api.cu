@@ -1797,6 +1797,60 @@ int hg_plan_pipeline(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields
   return HG_OK;
 }
 
+// Host-only: the tile tables hg_create would upload for this mesh, by name (no GPU touched).  The CPU tests walk them with a
+// plain-Python model of the tile kernel's data path (tests/test_tile_tables_cpu.py): what the builder emits is checked against
+// the mesh and the reference restatement without a device.
+struct hg_plan { std::unique_ptr<hg_ctx> ctx; std::vector<int64_t> dims; };
+int hg_plan_open(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_desc* f, const hg_options* opt, hg_plan** out) {
+  if (!out) return HG_ERR_ARG;
+  std::unique_ptr<hg_plan> p(new hg_plan());
+  p->ctx.reset(new hg_ctx());
+  hg_ctx* ctx = p->ctx.get();
+  if (opt) ctx->opt = *opt; else hg_default_options(&ctx->opt);
+  std::vector<int32_t> cf_ptr, cf_nb, cf_face;
+  std::vector<double> cf_nx, cf_ny, cf_len;
+  int rc = hg::build_host(ctx, m, b, f, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
+  if (rc == HG_OK) rc = hg::build_tiles(ctx, m, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
+  if (rc != HG_OK) { set_global_err(ctx->err); return rc; }
+  const hg::FusedHost& fh = ctx->fh;
+  p->dims = {ctx->N, ctx->B, fh.n_tiles, fh.T, fh.NF, fh.Ns, hg::kTileDesc, fh.n_chunks};
+  *out = p.release();
+  return HG_OK;
+}
+void hg_plan_close(hg_plan* p) { delete p; }
+// name: dims | perm iperm tile_desc halo bface_e (i32) | face_lr (u32) | cf_idx (u16) | face_nx face_ny face_len (f64) |
+// bc_type bc_group bc_ghost bc_cell_ref inlet_ptr (i32) | bc_nx bc_ny bc_l53 bc_l23 bc_hstill bc_zb (f64)
+int hg_plan_array(const hg_plan* p, const char* name, const void** ptr, int64_t* count, int32_t* dtype) {
+  if (!p || !name || !ptr || !count || !dtype) return HG_ERR_ARG;
+  const hg::FusedHost& fh = p->ctx->fh;
+  const hg::BcHost& bh = p->ctx->bch;
+  const std::string n(name);
+  auto give = [&](const auto& v, int32_t code) { *ptr = v.data(); *count = (int64_t)v.size(); *dtype = code; return HG_OK; };
+  if (n == "dims") return give(p->dims, 1);
+  if (n == "perm") return give(fh.perm, 3);
+  if (n == "iperm") return give(fh.iperm, 3);
+  if (n == "tile_desc") return give(fh.tile_desc, 3);
+  if (n == "halo") return give(fh.halo, 3);
+  if (n == "bface_e") return give(fh.bface_e, 3);
+  if (n == "face_lr") return give(fh.face_lr, 4);
+  if (n == "cf_idx") return give(fh.cf_idx, 5);
+  if (n == "face_nx") return give(fh.face_nx, 0);
+  if (n == "face_ny") return give(fh.face_ny, 0);
+  if (n == "face_len") return give(fh.face_len, 0);
+  if (n == "bc_type") return give(bh.type, 3);
+  if (n == "bc_group") return give(bh.group, 3);
+  if (n == "bc_ghost") return give(bh.ghost, 3);
+  if (n == "bc_cell_ref") return give(bh.cell_ref, 3);
+  if (n == "inlet_ptr") return give(bh.inlet_ptr, 3);
+  if (n == "bc_nx") return give(bh.nx, 0);
+  if (n == "bc_ny") return give(bh.ny, 0);
+  if (n == "bc_l53") return give(bh.l53, 0);
+  if (n == "bc_l23") return give(bh.l23, 0);
+  if (n == "bc_hstill") return give(bh.hstill_g, 0);
+  if (n == "bc_zb") return give(bh.zb_g, 0);
+  return HG_ERR_ARG;
+}
+
 // Host-only: the rows [r0, r1) chunk c of a component moves when that component's row 0 sits at host address host_addr -- the
 // geometry hg_rhs / hg_rhs_vjp use (chunk_rows above), exposed so that the CPU tests can check coverage, alignment and the
 // margins the stage tables assume.

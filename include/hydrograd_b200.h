@@ -516,6 +516,17 @@ HG_API int hg_plan_pipeline(const hg_mesh_desc* mesh, const hg_bc_desc* bc, cons
 /* Host-only: rows [r0, r1) that chunk c (of K, nominal size rows_per_chunk) of a [N] component moves when the component starts at
  * host address host_addr: boundaries are shifted so that every copy starts at a multiple of 256 bytes (test hook). */
 HG_API int hg_debug_chunk_rows(uint64_t host_addr, int32_t c, int32_t K, int64_t rows_per_chunk, int64_t N, int64_t* r0, int64_t* r1);
+
+/* Host-only: the tile tables hg_create would upload for this mesh, by name (test / inspection hook; no GPU touched).
+ * hg_plan_array: "dims" (i64: N, B, n_tiles, tile_cells, slots per cell, component stride, ints per tile descriptor, n_chunks);
+ * "perm" "iperm" "tile_desc" "halo" "bface_e" "bc_type" "bc_group" "bc_ghost" "bc_cell_ref" "inlet_ptr" (i32); "face_lr" (u32);
+ * "cf_idx" (u16); "face_nx" "face_ny" "face_len" "bc_nx" "bc_ny" "bc_l53" "bc_l23" "bc_hstill" "bc_zb" (f64).  The pointers
+ * stay valid until hg_plan_close.  The layout is described in DESIGN.md section 3.                                      */
+typedef struct hg_plan hg_plan;
+HG_API int hg_plan_open(const hg_mesh_desc* mesh, const hg_bc_desc* bc, const hg_fields_desc* fields, const hg_options* opt, hg_plan** out);
+HG_API void hg_plan_close(hg_plan* p);
+HG_API int hg_plan_array(const hg_plan* p, const char* name, const void** ptr, int64_t* count,
+                  int32_t* dtype /* 0 f64, 1 i64, 2 u8, 3 i32, 4 u32, 5 u16 */);
 /* Accuracy probe of the kernels' branch-free fp64 helpers (hg_device.cuh): out[i] = f(x[i]) evaluated on the device,
  * kind 0 = 1/x, 1 = 1/sqrt(x), 2 = sqrt(x), 3 = sqrt(x^2 + eps) (smooth abs), 4 = x^(-7/3); x > 0, host pointers.          */
 HG_API int hg_debug_math(hg_ctx* ctx, int32_t kind, int64_t n, const double* x, double* out);

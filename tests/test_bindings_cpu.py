@@ -36,6 +36,7 @@ def _c_type(t):
              "double *": L.c_f64p, "int64_t *": L.c_i64p, "int32_t *": i32p, "float *": f32p, "uint8_t *": L.c_u8p, "char *": C.c_char_p,
              "void *": C.c_void_p, "hg_ctx *": C.c_void_p, "hg_case *": C.c_void_p, "hg_ctx * *": P(C.c_void_p), "hg_case * *": P(C.c_void_p),
              "hg_json *": C.c_void_p, "hg_json * *": P(C.c_void_p),
+                 "hg_plan *": C.c_void_p, "hg_plan * *": P(C.c_void_p),
              "void * *": P(C.c_void_p), "double * *": P(L.c_f64p), "hg_allreduce_fn": L.ALLREDUCE_FN}
     if t in table:
         return table[t]
