@@ -114,7 +114,8 @@ def _walk_tables(c, t, Q, check_structure=True):
     return out
 
 
-@pytest.mark.parametrize("name,tile", [("simple", 128), ("oneD_bump", 128), ("savannah", 128), ("savannah", 256), ("random_symm", 128)])
+@pytest.mark.parametrize("name,tile", [("simple", 128), ("oneD_bump", 128), ("savannah", 128), ("savannah", 192), ("savannah", 256),
+                                       ("savannah", 384), ("savannah", 512), ("random_symm", 128)])
 def test_tile_tables_reproduce_the_oracle_rhs(hg, name, tile, tmp_path, oracle_lib):
     if name == "random_symm":
         _write_random_case(str(tmp_path), 3, ni=15, nj=11)          # 165+ cells: two tiles, symmetry, two inlets
