@@ -118,7 +118,7 @@ def plan_pipeline(flat: dict, tile_cells=256, reorder=True, pipeline_chunks=0):
 
 def plan_tables(flat: dict, tile_cells=256, reorder=True):
     """Host-only: the tile tables hg_create would upload (hg_plan_open / hg_plan_array), copied into numpy arrays by name,
-    plus the entries of "dims" as ints (N, B, n_tiles, T, NF, Ns, n_desc, n_chunks)."""
+    plus the entries of "dims" as ints (N, B, n_tiles, T, NF, Ns, n_desc, n_chunks, n_interior_tiles, comm_band0)."""
     lib = L.load()
     mesh, bc, fields, keep = _descs(flat)
     opt = _options(lib, 0, tile_cells, reorder)
@@ -129,7 +129,7 @@ def plan_tables(flat: dict, tile_cells=256, reorder=True):
     types = {0: np.float64, 1: np.int64, 2: np.uint8, 3: np.int32, 4: np.uint32, 5: np.uint16}
     out = {}
     try:
-        for name in ("dims", "perm", "iperm", "tile_desc", "halo", "bface_e", "face_lr", "cf_idx", "face_nx", "face_ny", "face_len",
+        for name in ("dims", "perm", "iperm", "tile_desc", "halo", "bface_e", "tile_order", "band_order", "comm_order", "face_lr", "cf_idx", "face_nx", "face_ny", "face_len",
                      "bc_type", "bc_group", "bc_ghost", "bc_cell_ref", "inlet_ptr", "bc_nx", "bc_ny", "bc_l53", "bc_l23", "bc_hstill", "bc_zb"):
             ptr, cnt, dt = C.c_void_p(), C.c_int64(), C.c_int32()
             rc = lib.hg_plan_array(h, name.encode(), C.byref(ptr), C.byref(cnt), C.byref(dt))
@@ -141,7 +141,7 @@ def plan_tables(flat: dict, tile_cells=256, reorder=True):
                          if n else np.zeros(0, dtype=ty))
     finally:
         lib.hg_plan_close(h)
-    out.update(zip(("N", "B", "n_tiles", "T", "NF", "Ns", "n_desc", "n_chunks"), (int(x) for x in out["dims"])))
+    out.update(zip(("N", "B", "n_tiles", "T", "NF", "Ns", "n_desc", "n_chunks", "n_interior_tiles", "comm_band0"), (int(x) for x in out["dims"])))
     return out
 
 

@@ -1813,12 +1813,12 @@ int hg_plan_open(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_des
   if (rc == HG_OK) rc = hg::build_tiles(ctx, m, cf_ptr, cf_nb, cf_nx, cf_ny, cf_len, cf_face);
   if (rc != HG_OK) { set_global_err(ctx->err); return rc; }
   const hg::FusedHost& fh = ctx->fh;
-  p->dims = {ctx->N, ctx->B, fh.n_tiles, fh.T, fh.NF, fh.Ns, hg::kTileDesc, fh.n_chunks};
+  p->dims = {ctx->N, ctx->B, fh.n_tiles, fh.T, fh.NF, fh.Ns, hg::kTileDesc, fh.n_chunks, fh.n_interior_tiles, fh.comm_band0};
   *out = p.release();
   return HG_OK;
 }
 void hg_plan_close(hg_plan* p) { delete p; }
-// name: dims | perm iperm tile_desc halo bface_e (i32) | face_lr (u32) | cf_idx (u16) | face_nx face_ny face_len (f64) |
+// name: dims | perm iperm tile_desc halo bface_e tile_order band_order comm_order (i32) | face_lr (u32) | cf_idx (u16) | face_nx face_ny face_len (f64) |
 // bc_type bc_group bc_ghost bc_cell_ref inlet_ptr (i32) | bc_nx bc_ny bc_l53 bc_l23 bc_hstill bc_zb (f64)
 int hg_plan_array(const hg_plan* p, const char* name, const void** ptr, int64_t* count, int32_t* dtype) {
   if (!p || !name || !ptr || !count || !dtype) return HG_ERR_ARG;
@@ -1832,6 +1832,9 @@ int hg_plan_array(const hg_plan* p, const char* name, const void** ptr, int64_t*
   if (n == "tile_desc") return give(fh.tile_desc, 3);
   if (n == "halo") return give(fh.halo, 3);
   if (n == "bface_e") return give(fh.bface_e, 3);
+  if (n == "tile_order") return give(fh.tile_order, 3);
+  if (n == "band_order") return give(fh.band_order, 3);
+  if (n == "comm_order") return give(fh.comm_order, 3);
   if (n == "face_lr") return give(fh.face_lr, 4);
   if (n == "cf_idx") return give(fh.cf_idx, 5);
   if (n == "face_nx") return give(fh.face_nx, 0);

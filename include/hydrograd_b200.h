@@ -518,7 +518,9 @@ HG_API int hg_plan_pipeline(const hg_mesh_desc* mesh, const hg_bc_desc* bc, cons
 HG_API int hg_debug_chunk_rows(uint64_t host_addr, int32_t c, int32_t K, int64_t rows_per_chunk, int64_t N, int64_t* r0, int64_t* r1);
 
 /* Host-only: the tile tables hg_create would upload for this mesh, by name (test / inspection hook; no GPU touched).
- * hg_plan_array: "dims" (i64: N, B, n_tiles, tile_cells, slots per cell, component stride, ints per tile descriptor, n_chunks);
+ * hg_plan_array: "dims" (i64: N, B, n_tiles, tile_cells, slots per cell, component stride, ints per tile descriptor, n_chunks,
+ * tiles without halo faces, first band position of comm_order); "tile_order" "band_order" "comm_order" (i32: the launch orders of
+ * the host-buffer pipeline, of the two-phase overlap and of the library-owned transport; empty on a mesh without halo faces);
  * "perm" "iperm" "tile_desc" "halo" "bface_e" "bc_type" "bc_group" "bc_ghost" "bc_cell_ref" "inlet_ptr" (i32); "face_lr" (u32);
  * "cf_idx" (u16); "face_nx" "face_ny" "face_len" "bc_nx" "bc_ny" "bc_l53" "bc_l23" "bc_hstill" "bc_zb" (f64).  The pointers
  * stay valid until hg_plan_close.  The layout is described in DESIGN.md section 3.                                      */

@@ -263,3 +263,32 @@ def test_partitioned_tile_tables_give_the_single_mesh_bits(hg, name, P, oracle_l
     assert np.array_equal(out, single)                                # rank-count independent to the bit
     want = Oracle(flat).rhs(Q)
     assert (np.abs(out - want) <= 2e-13 * cases.flat_scale(flat, Q)).all()
+
+
+def test_launch_orders_of_a_rank_local_mesh(hg):
+    """band_order (two-phase overlap): the tiles without halo faces first, then the band; comm_order (library-owned transport): the
+    band in the middle of the launch, interior tiles on both sides; tile_order (host-buffer pipeline): a permutation."""
+    from hydrograd_jl_b200 import parallel as PAR
+    c = cases.load("savannah")
+    flat = R.flatten(c)
+    N = int(flat["n_cells"])
+    cen = np.asarray(flat["cell_centroids"])
+    part = PAR.rcb_partition(cen[:N], cen[N:], 4, keep_together=PAR.inlet_cell_groups(flat))
+    bands = 0
+    for rank in range(4):
+        loc, _ = PAR.extract_local(flat, part, rank)
+        t = hg.plan_tables(loc, tile_cells=128)
+        nd, nt = t["n_desc"], t["n_tiles"]
+        band = set()
+        for tile in range(nt):
+            nf, nint, bfp = (int(t["tile_desc"][tile * nd + k]) for k in (5, 9, 10))
+            if any(int(t["bc_type"][int(e)]) == BC_HALO for e in t["bface_e"][bfp:bfp + nf - nint]):
+                band.add(tile)
+        bands += len(band)
+        ni, b0 = t["n_interior_tiles"], t["comm_band0"]
+        assert ni == nt - len(band)
+        for order in (t["band_order"], t["comm_order"], t["tile_order"]):
+            assert sorted(order.tolist()) == list(range(nt))
+        assert set(t["band_order"][ni:].tolist()) == band
+        assert set(t["comm_order"][b0:b0 + len(band)].tolist()) == band and b0 == ni // 2
+    assert bands > 0
