@@ -292,3 +292,35 @@ def test_launch_orders_of_a_rank_local_mesh(hg):
         assert set(t["band_order"][ni:].tolist()) == band
         assert set(t["comm_order"][b0:b0 + len(band)].tolist()) == band and b0 == ni // 2
     assert bands > 0
+
+
+@pytest.mark.parametrize("which", ["river", "dam_thin"])
+def test_synthetic_meshes_tiles_and_partitions(hg, which, oracle_lib):
+    """The benchmark mesh families at test size (mixed triangles / quadrilaterals; river: inlet-q, exit-h, walls, six Manning zones;
+    dam break with a thin film: wet/dry fronts): three tile shapes against the oracle, 2 and 5 ranks bit-identical to one."""
+    from hydrograd_jl_b200 import parallel as PAR
+    from hydrograd_jl_b200 import synthetic as S
+    flat, Q0 = S.river(60, 24) if which == "river" else S.dam_break(36, thin_film=True)
+    N = int(flat["n_cells"])
+    mesh, o = Mesh(flat), Oracle(flat)
+    for tile in (128, 224, 256):
+        t = hg.plan_tables(flat, tile_cells=tile)
+        for k, Q in enumerate((Q0, cases.random_state_flat(flat, 5, dry_frac=0.1))):
+            got = walk_tables(mesh, t, Q, check_structure=(k == 0 and tile == 128))
+            assert (np.abs(got - o.rhs(Q)) <= 2e-13 * cases.flat_scale(flat, Q)).all(), (which, tile, k)
+    cen = np.asarray(flat["cell_centroids"])
+    Q = cases.random_state_flat(flat, 6, dry_frac=0.1)
+    single = walk_tables(mesh, hg.plan_tables(flat, tile_cells=128), Q, check_structure=False)
+    for P in (2, 5):
+        part = PAR.rcb_partition(cen[:N], cen[N:], P, keep_together=PAR.inlet_cell_groups(flat))
+        out = np.full(3 * N, np.nan)
+        for rank in range(P):
+            loc, info = PAR.extract_local(flat, part, rank, Q)
+            m = Mesh(loc)
+            own, rem = info["own"], info["halo_remote"]
+            n_phys = m.B - rem.size
+            remote = lambda e: (Q[rem[e - n_phys]], Q[N + rem[e - n_phys]], Q[2 * N + rem[e - n_phys]])
+            got = walk_tables(m, hg.plan_tables(loc, tile_cells=128), info["Q"], check_structure=True, remote=remote)
+            n = own.size
+            out[own], out[N + own], out[2 * N + own] = got[:n], got[n:2 * n], got[2 * n:]
+        assert np.array_equal(out, single), (which, P)
