@@ -130,7 +130,7 @@ def plan_tables(flat: dict, tile_cells=256, reorder=True):
     out = {}
     try:
         for name in ("dims", "perm", "iperm", "tile_desc", "halo", "bface_e", "tile_order", "band_order", "comm_order", "face_lr", "cf_idx", "face_nx", "face_ny", "face_len",
-                     "bc_type", "bc_group", "bc_ghost", "bc_cell_ref", "inlet_ptr", "bc_nx", "bc_ny", "bc_l53", "bc_l23", "bc_hstill", "bc_zb"):
+                     "bc_type", "bc_group", "bc_ghost", "bc_cell_ref", "inlet_ptr", "bcell_ref", "bcell_ptr", "bcell_ent", "cf_rev", "bc_nx", "bc_ny", "bc_l53", "bc_l23", "bc_hstill", "bc_zb"):
             ptr, cnt, dt = C.c_void_p(), C.c_int64(), C.c_int32()
             rc = lib.hg_plan_array(h, name.encode(), C.byref(ptr), C.byref(cnt), C.byref(dt))
             if rc:

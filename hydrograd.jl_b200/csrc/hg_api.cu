@@ -1819,7 +1819,7 @@ int hg_plan_open(const hg_mesh_desc* m, const hg_bc_desc* b, const hg_fields_des
 }
 void hg_plan_close(hg_plan* p) { delete p; }
 // name: dims | perm iperm tile_desc halo bface_e tile_order band_order comm_order (i32) | face_lr (u32) | cf_idx (u16) | face_nx face_ny face_len (f64) |
-// bc_type bc_group bc_ghost bc_cell_ref inlet_ptr (i32) | bc_nx bc_ny bc_l53 bc_l23 bc_hstill bc_zb (f64)
+// bc_type bc_group bc_ghost bc_cell_ref inlet_ptr bcell_ref bcell_ptr bcell_ent cf_rev (i32) | bc_nx bc_ny bc_l53 bc_l23 bc_hstill bc_zb (f64)
 int hg_plan_array(const hg_plan* p, const char* name, const void** ptr, int64_t* count, int32_t* dtype) {
   if (!p || !name || !ptr || !count || !dtype) return HG_ERR_ARG;
   const hg::FusedHost& fh = p->ctx->fh;
@@ -1845,6 +1845,10 @@ int hg_plan_array(const hg_plan* p, const char* name, const void** ptr, int64_t*
   if (n == "bc_ghost") return give(bh.ghost, 3);
   if (n == "bc_cell_ref") return give(bh.cell_ref, 3);
   if (n == "inlet_ptr") return give(bh.inlet_ptr, 3);
+  if (n == "bcell_ref") return give(bh.bcell_ref, 3);
+  if (n == "bcell_ptr") return give(bh.bcell_ptr, 3);
+  if (n == "bcell_ent") return give(bh.bcell_ent, 3);
+  if (n == "cf_rev") return give(bh.cf_rev, 3);
   if (n == "bc_nx") return give(bh.nx, 0);
   if (n == "bc_ny") return give(bh.ny, 0);
   if (n == "bc_l53") return give(bh.l53, 0);

@@ -521,6 +521,8 @@ HG_API int hg_debug_chunk_rows(uint64_t host_addr, int32_t c, int32_t K, int64_t
  * hg_plan_array: "dims" (i64: N, B, n_tiles, tile_cells, slots per cell, component stride, ints per tile descriptor, n_chunks,
  * tiles without halo faces, first band position of comm_order); "tile_order" "band_order" "comm_order" (i32: the launch orders of
  * the host-buffer pipeline, of the two-phase overlap and of the library-owned transport; empty on a mesh without halo faces);
+ * "bcell_ref" "bcell_ptr" "bcell_ent" (i32: distinct boundary-adjacent cells -> their boundary entries) "cf_rev" (i32: per cell-face
+ * of the reference-order CSR, where the same face sits in the neighbour's list; -1 on boundary faces);
  * "perm" "iperm" "tile_desc" "halo" "bface_e" "bc_type" "bc_group" "bc_ghost" "bc_cell_ref" "inlet_ptr" (i32); "face_lr" (u32);
  * "cf_idx" (u16); "face_nx" "face_ny" "face_len" "bc_nx" "bc_ny" "bc_l53" "bc_l23" "bc_hstill" "bc_zb" (f64).  The pointers
  * stay valid until hg_plan_close.  The layout is described in DESIGN.md section 3.                                      */

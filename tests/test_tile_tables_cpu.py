@@ -324,3 +324,32 @@ def test_synthetic_meshes_tiles_and_partitions(hg, which, oracle_lib):
             n = own.size
             out[own], out[N + own], out[2 * N + own] = got[:n], got[n:2 * n], got[2 * n:]
         assert np.array_equal(out, single), (which, P)
+
+
+@pytest.mark.parametrize("name", ["savannah", "oneD_bump"])
+def test_adjoint_side_tables(hg, name):
+    """What the VJP's follow-up kernels index with: the boundary entries grouped by their owned cell (deterministic scatter of the
+    boundary adjoints) and, per cell-face of the reference-order CSR, the position of the same face in the neighbour's list
+    (transposed Green-Gauss for the bed gradient)."""
+    flat = R.flatten(cases.load(name))
+    mesh = Mesh(flat)
+    t = hg.plan_tables(flat, tile_cells=128)
+    ref, ptr, ent = t["bcell_ref"], t["bcell_ptr"], t["bcell_ent"]
+    assert (np.diff(ref) > 0).all() and ptr[0] == 0 and ptr[-1] == mesh.B and ptr.size == ref.size + 1
+    assert sorted(ent.tolist()) == list(range(mesh.B))
+    for k in range(ref.size):
+        es = ent[ptr[k]:ptr[k + 1]]
+        assert (t["bc_cell_ref"][es] == ref[k]).all() and (np.diff(es) > 0).all()
+    cf_ptr = np.concatenate([[0], np.cumsum(mesh.nf)])
+    rev = t["cf_rev"]
+    assert rev.size == cf_ptr[-1]
+    for i in range(mesh.N):
+        for j in range(int(mesh.nf[i])):
+            k = cf_ptr[i] + j
+            if mesh.isb[mesh.face[i, j]]:
+                assert rev[k] == -1
+            else:
+                nb = int(mesh.neigh[i, j])
+                jj = int(rev[k]) - cf_ptr[nb]
+                assert 0 <= jj < mesh.nf[nb] and mesh.neigh[nb, jj] == i and mesh.face[nb, jj] == mesh.face[i, j]
+                assert rev[rev[k]] == k
