@@ -353,3 +353,32 @@ def test_adjoint_side_tables(hg, name):
                 jj = int(rev[k]) - cf_ptr[nb]
                 assert 0 <= jj < mesh.nf[nb] and mesh.neigh[nb, jj] == i and mesh.face[nb, jj] == mesh.face[i, j]
                 assert rev[rev[k]] == k
+
+
+def test_shared_memory_bank_statistics_of_the_tables(hg):
+    """A performance property of the tables, computed from the tables: a half-warp's 64-bit shared-memory gather takes one
+    wavefront per distinct address in the most loaded of the 16 eight-byte banks.  Phase 2 (16 consecutive faces read their L and
+    their R cells): the builder's bank matching keeps it near 1.1; phase 3 (16 consecutive cells read their j-th face): ~1.9,
+    the known remaining conflict.  Guards both against regressions of the builder."""
+    from hydrograd_jl_b200 import synthetic as S
+    flat, _ = S.river(150, 100)
+    t = hg.plan_tables(flat, tile_cells=256)
+    nd, T, NF = t["n_desc"], t["T"], t["NF"]
+
+    def wavefronts(idx):
+        return np.bincount(np.unique(idx) % 16, minlength=16).max()
+
+    w2 = n2 = w3 = n3 = 0
+    for tile in range(t["n_tiles"]):
+        c0, nc, hp, nh, fp, nf, nfp, _, _, nint, bfp = (int(x) for x in t["tile_desc"][tile * nd:tile * nd + 11])
+        lr = t["face_lr"][fp:fp + nint].astype(np.int64)
+        for b in range(0, nint, 16):
+            w2 += wavefronts(lr[b:b + 16] & 0xFFFF) + wavefronts(lr[b:b + 16] >> 16)
+            n2 += 2
+        cf = t["cf_idx"][tile * T * NF:(tile * T + nc) * NF].astype(np.int64).reshape(nc, NF) & 0x7FFF
+        for b in range(0, nc, 16):
+            for j in range(NF):
+                w3 += wavefronts(cf[b:b + 16, j])
+                n3 += 1
+    print(f"wavefronts per half-warp gather: phase 2 {w2 / n2:.3f}, phase 3 {w3 / n3:.3f}")
+    assert w2 / n2 <= 1.2 and w3 / n3 <= 2.1
